@@ -1,0 +1,559 @@
+// api.cu -- the C ABI of libfscnn_b200.so (see include/fscnn_b200.h): context, state_dict manifest,
+// BN folding / weight packing plan, workspace plan, and the stage sequencing of the forward path
+// (reference models/fast_scnn.py:33-46).  Host-only logic; every device operation is a kernel from
+// the sibling .cu files enqueued on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fscnn_b200.h"
+#include "kernels.h"
+
+using namespace fscnn;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+struct Param { std::string name; int64_t numel; };
+
+struct BneckPlan { const char* name; int cin, cout, stride; };
+const BneckPlan kBnecks[9] = {   // GlobalFeatureExtractor._make_layer, models/fast_scnn.py:170-180
+    {"bottleneck1.0", 64, 64, 2}, {"bottleneck1.1", 64, 64, 1}, {"bottleneck1.2", 64, 64, 1},
+    {"bottleneck2.0", 64, 96, 2}, {"bottleneck2.1", 96, 96, 1}, {"bottleneck2.2", 96, 96, 1},
+    {"bottleneck3.0", 96, 128, 1}, {"bottleneck3.1", 128, 128, 1}, {"bottleneck3.2", 128, 128, 1},
+};
+
+enum Stage { kStem = 0, kDs1, kDs2, kB0, kPpm = kB0 + 9, kFfm, kCls1, kCls2Head, kAux, kNumStages };
+const char* kStageNames[kNumStages] = {
+    "stem", "l2d.dsconv1", "l2d.dsconv2", "gfe.bottleneck1.0", "gfe.bottleneck1.1", "gfe.bottleneck1.2",
+    "gfe.bottleneck2.0", "gfe.bottleneck2.1", "gfe.bottleneck2.2", "gfe.bottleneck3.0", "gfe.bottleneck3.1",
+    "gfe.bottleneck3.2", "gfe.ppm", "ffm", "cls.dsconv1", "cls.dsconv2+head", "aux"};
+
+// Spatial sizes of every stage for an h x w input.
+struct Dims {
+    int h, w;      // input
+    int h1, w1;    // stem: 3x3 s2 p0
+    int h2, w2;    // dsconv1: s2 p1
+    int h3, w3;    // dsconv2: s2 p1 (higher_res, /8)
+    int h4, w4;    // bottleneck1 (/16)
+    int h5, w5;    // bottleneck2,3 / ppm (/32)
+    bool ok;
+};
+
+Dims make_dims(int h, int w) {
+    Dims d{};
+    d.h = h; d.w = w;
+    d.h1 = (h - 3) / 2 + 1; d.w1 = (w - 3) / 2 + 1;
+    d.h2 = (d.h1 - 1) / 2 + 1; d.w2 = (d.w1 - 1) / 2 + 1;
+    d.h3 = (d.h2 - 1) / 2 + 1; d.w3 = (d.w2 - 1) / 2 + 1;
+    d.h4 = (d.h3 - 1) / 2 + 1; d.w4 = (d.w3 - 1) / 2 + 1;
+    d.h5 = (d.h4 - 1) / 2 + 1; d.w5 = (d.w4 - 1) / 2 + 1;
+    d.ok = h >= 3 && w >= 3 && d.h5 >= 1 && d.w5 >= 1;
+    return d;
+}
+
+// Workspace layout for a micro-batch of `mb` images: byte offsets of every stage tensor.
+struct WsPlan {
+    size_t stem, ds1, higher, b[9], ppm, rowsum, z, ffm, cls1, logits, aux_logits, total;
+};
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+struct fscnn_ctx {
+    int nc = 0, ncp = 0, aux = 0, prec = 0;
+    std::vector<Param> params;
+    size_t packed_floats = 0;
+    bool loaded = false;
+    int64_t launches = 0;
+    int micro_batch = 0;
+    // offsets (floats) into the packed buffer, fixed at create time
+    struct Off {
+        size_t stem_w, stem_b;
+        size_t ds_wd[4], ds_bd[4], ds_wp[4], ds_bp[4];     // l2d.dsconv1, l2d.dsconv2, cls.dsconv1, cls.dsconv2
+        size_t bn_we[9], bn_be[9], bn_wd[9], bn_bd[9], bn_wp[9], bn_bp[9];
+        size_t ppm_wc[4], ppm_bc[4], ppm_wo, ppm_bo;
+        size_t ffm_wd, ffm_bd, ffm_wcat, ffm_bcat;
+        size_t head_w, head_b;
+        size_t aux_w, aux_b, auxh_w, auxh_b;
+    } off{};
+    // device pointers resolved by load_weights
+    StemW stem{};
+    DsW ds[4]{};
+    BneckW bn[9]{};
+    PpmW ppm{};
+    FfmW ffm{};
+    HeadW head{};
+    AuxW auxw{};
+
+    int esize() const { return prec == FSCNN_PREC_BF16 ? 2 : 4; }
+    int eff_mb(int n, int h, int w) const {
+        int mb = micro_batch;
+        if (mb <= 0) {   // default: about 16 Mpixel of input per micro-batch
+            long long px = (long long)h * w;
+            mb = (int)((16ll << 20) / (px > 0 ? px : 1));
+            if (mb < 1) mb = 1;
+            if (mb > 64) mb = 64;
+        }
+        return mb < n ? mb : n;
+    }
+    WsPlan plan(int mb, const Dims& d) const {
+        WsPlan p{};
+        size_t o = 0;
+        const size_t es = esize();
+        auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes); return at; };
+        p.stem = take((size_t)mb * d.h1 * d.w1 * 32 * es);
+        p.ds1 = take((size_t)mb * d.h2 * d.w2 * 48 * es);
+        p.higher = take((size_t)mb * d.h3 * d.w3 * 64 * es);
+        for (int i = 0; i < 9; ++i) {
+            const bool lvl4 = i < 3;
+            p.b[i] = take((size_t)mb * (lvl4 ? d.h4 * d.w4 : d.h5 * d.w5) * kBnecks[i].cout * es);
+        }
+        p.ppm = take((size_t)mb * d.h5 * d.w5 * 128 * es);
+        p.rowsum = take((size_t)mb * d.h5 * 12 * 128 * 4);
+        p.z = take((size_t)mb * 50 * 128 * 4);
+        p.ffm = take((size_t)mb * d.h3 * d.w3 * 128 * es);
+        p.cls1 = take((size_t)mb * d.h3 * d.w3 * 128 * es);
+        p.logits = take((size_t)mb * d.h3 * d.w3 * ncp * 4);
+        p.aux_logits = aux ? take((size_t)mb * d.h3 * d.w3 * ncp * 4) : 0;
+        p.total = o;
+        return p;
+    }
+};
+
+namespace {
+
+void add_conv(fscnn_ctx* c, const std::string& name, int64_t wn, int64_t bias_n = 0) {
+    c->params.push_back({name + ".weight", wn});
+    if (bias_n) c->params.push_back({name + ".bias", bias_n});
+}
+void add_bn(fscnn_ctx* c, const std::string& name, int64_t ch) {
+    for (const char* k : {".weight", ".bias", ".running_mean", ".running_var"}) c->params.push_back({name + k, ch});
+}
+
+void build_manifest_and_offsets(fscnn_ctx* c) {
+    size_t o = 0;
+    auto take = [&](size_t floats) { size_t at = o; o += (floats + 63) & ~(size_t)63; return at; };   // 256-byte granules
+    auto& f = c->off;
+    // LearningToDownsample (models/fast_scnn.py:148-161)
+    add_conv(c, "learning_to_downsample.conv.conv.0", 32 * 27);
+    add_bn(c, "learning_to_downsample.conv.conv.1", 32);
+    f.stem_w = take(27 * 32); f.stem_b = take(32);
+    const struct { const char* p; int cin, cout; } dss[4] = {{"learning_to_downsample.dsconv1", 32, 48},
+                                                              {"learning_to_downsample.dsconv2", 48, 64},
+                                                              {"classifier.dsconv1", 128, 128},
+                                                              {"classifier.dsconv2", 128, 128}};
+    auto add_ds = [&](int i) {
+        const std::string p = dss[i].p;
+        add_conv(c, p + ".conv.0", dss[i].cin * 9); add_bn(c, p + ".conv.1", dss[i].cin);
+        add_conv(c, p + ".conv.3", (int64_t)dss[i].cout * dss[i].cin); add_bn(c, p + ".conv.4", dss[i].cout);
+        f.ds_wd[i] = take(9 * dss[i].cin); f.ds_bd[i] = take(dss[i].cin);
+        f.ds_wp[i] = take((size_t)dss[i].cin * dss[i].cout); f.ds_bp[i] = take(dss[i].cout);
+    };
+    add_ds(0); add_ds(1);
+    // GlobalFeatureExtractor (:164-187)
+    for (int i = 0; i < 9; ++i) {
+        const std::string p = std::string("global_feature_extractor.") + kBnecks[i].name + ".block";
+        const int ci = kBnecks[i].cin, ce = 6 * ci, co = kBnecks[i].cout;
+        add_conv(c, p + ".0.conv.0", (int64_t)ce * ci); add_bn(c, p + ".0.conv.1", ce);
+        add_conv(c, p + ".1.conv.0", ce * 9); add_bn(c, p + ".1.conv.1", ce);
+        add_conv(c, p + ".2", (int64_t)co * ce); add_bn(c, p + ".3", co);
+        f.bn_we[i] = take((size_t)ci * ce); f.bn_be[i] = take(ce);
+        f.bn_wd[i] = take(9 * ce); f.bn_bd[i] = take(ce);
+        f.bn_wp[i] = take((size_t)ce * co); f.bn_bp[i] = take(co);
+    }
+    for (int i = 0; i < 4; ++i) {
+        const std::string p = "global_feature_extractor.ppm.conv" + std::to_string(i + 1) + ".conv";
+        add_conv(c, p + ".0", 32 * 128); add_bn(c, p + ".1", 32);
+        f.ppm_wc[i] = take(128 * 32); f.ppm_bc[i] = take(32);
+    }
+    add_conv(c, "global_feature_extractor.ppm.out.conv.0", 128 * 256);
+    add_bn(c, "global_feature_extractor.ppm.out.conv.1", 128);
+    f.ppm_wo = take(256 * 128); f.ppm_bo = take(128);
+    // FeatureFusionModule (:190-218)
+    add_conv(c, "feature_fusion.dwconv.conv.0", 128 * 9); add_bn(c, "feature_fusion.dwconv.conv.1", 128);
+    add_conv(c, "feature_fusion.conv_lower_res.0", 128 * 128, 128); add_bn(c, "feature_fusion.conv_lower_res.1", 128);
+    add_conv(c, "feature_fusion.conv_higher_res.0", 128 * 64, 128); add_bn(c, "feature_fusion.conv_higher_res.1", 128);
+    f.ffm_wd = take(9 * 128); f.ffm_bd = take(128); f.ffm_wcat = take(192 * 128); f.ffm_bcat = take(128);
+    // Classifer (:221-237)
+    add_ds(2); add_ds(3);
+    add_conv(c, "classifier.conv.1", (int64_t)c->nc * 128, c->nc);
+    f.head_w = take((size_t)128 * c->ncp); f.head_b = take(c->ncp);
+    if (c->aux) {   // aux head (:24-31)
+        add_conv(c, "auxlayer.0", 32 * 64 * 9); add_bn(c, "auxlayer.1", 32);
+        add_conv(c, "auxlayer.4", (int64_t)c->nc * 32, c->nc);
+        f.aux_w = take(576 * 32); f.aux_b = take(32);
+        f.auxh_w = take((size_t)32 * c->ncp); f.auxh_b = take(c->ncp);
+    }
+    c->packed_floats = o;
+}
+
+struct Loader {
+    std::unordered_map<std::string, const fscnn_tensor*> map;
+    cudaStream_t s;
+    int err = 0;
+    const float* get(const std::string& name, int64_t numel) {
+        auto it = map.find(name);
+        if (it == map.end()) { err = fail(FSCNN_ENOENT, "state_dict tensor '%s' is missing", name.c_str()); return nullptr; }
+        if (it->second->numel != numel || !it->second->d_data) {
+            err = fail(FSCNN_EINVAL, "state_dict tensor '%s': numel %lld, expected %lld", name.c_str(),
+                       (long long)it->second->numel, (long long)numel);
+            return nullptr;
+        }
+        return it->second->d_data;
+    }
+    // conv `conv` (+ optional bias) followed by BN `bn` ("" = none) -> out_w (k-major, ld_out) / out_b
+    void fold(const std::string& conv, bool has_bias, const std::string& bn, int cout, int kdim, int taps, int tap_major,
+              float* out_w, int ld_out, float* out_b, int accumulate = 0) {
+        if (err) return;
+        const float* w = get(conv + ".weight", (int64_t)cout * kdim);
+        const float* cb = has_bias ? get(conv + ".bias", cout) : nullptr;
+        const float *g = nullptr, *b = nullptr, *m = nullptr, *v = nullptr;
+        if (!bn.empty()) {
+            g = get(bn + ".weight", cout); b = get(bn + ".bias", cout);
+            m = get(bn + ".running_mean", cout); v = get(bn + ".running_var", cout);
+        }
+        if (err) return;
+        if (launch_fold(w, cb, g, b, m, v, cout, kdim, taps, tap_major, out_w, ld_out, out_b, accumulate, s) != cudaSuccess)
+            err = fail(FSCNN_ECUDA, "fold kernel launch failed for '%s': %s", conv.c_str(),
+                       cudaGetErrorString(cudaGetLastError()));
+    }
+};
+
+template <typename T>
+int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
+               cudaStream_t s) {
+    cudaError_t e = cudaSuccess;
+    auto at = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
+    auto atf = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    for (int st = first; st <= last && e == cudaSuccess; ++st) {
+        if (st == kStem) {
+            e = launch_stem<T>(x, c->stem, at(p.stem), m, d.h, d.w, d.h1, d.w1, s);
+        } else if (st == kDs1) {
+            e = launch_dsconv<T>(32, 48, 2, at(p.stem), c->ds[0], at(p.ds1), nullptr, nullptr, m, d.h1, d.w1, d.h2, d.w2, s);
+        } else if (st == kDs2) {
+            e = launch_dsconv<T>(48, 64, 2, at(p.ds1), c->ds[1], at(p.higher), nullptr, nullptr, m, d.h2, d.w2, d.h3, d.w3, s);
+        } else if (st >= kB0 && st < kB0 + 9) {
+            const int i = st - kB0;
+            const T* in = i == 0 ? at(p.higher) : at(p.b[i - 1]);
+            const int hi = i == 0 ? d.h3 : (i <= 3 ? d.h4 : d.h5), wi = i == 0 ? d.w3 : (i <= 3 ? d.w4 : d.w5);
+            const int ho = i < 3 ? d.h4 : d.h5, wo = i < 3 ? d.w4 : d.w5;
+            e = launch_bottleneck<T>(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn[i], at(p.b[i]), m, hi, wi,
+                                     ho, wo, s);
+        } else if (st == kPpm) {
+            e = launch_ppm<T>(at(p.b[8]), c->ppm, atf(p.rowsum), atf(p.z), at(p.ppm), m, d.h5, d.w5, s);
+            c->launches += 2;
+        } else if (st == kFfm) {
+            e = launch_ffm<T>(at(p.higher), at(p.ppm), c->ffm, at(p.ffm), m, d.h3, d.w3, d.h5, d.w5, s);
+        } else if (st == kCls1) {
+            e = launch_dsconv<T>(128, 128, 1, at(p.ffm), c->ds[2], at(p.cls1), nullptr, nullptr, m, d.h3, d.w3, d.h3, d.w3, s);
+        } else if (st == kCls2Head) {
+            e = launch_dsconv<T>(128, 128, 1, at(p.cls1), c->ds[3], nullptr, &c->head, atf(p.logits), m, d.h3, d.w3, d.h3,
+                                 d.w3, s);
+        } else if (st == kAux) {
+            if (!c->aux) continue;
+            e = launch_aux<T>(at(p.higher), c->auxw, atf(p.aux_logits), m, d.h3, d.w3, s);
+        }
+        c->launches += 1;
+    }
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int dispatch_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
+                    cudaStream_t s) {
+    return c->prec == FSCNN_PREC_BF16 ? run_stages<bf16>(c, x, m, d, p, ws, first, last, s)
+                                      : run_stages<float>(c, x, m, d, p, ws, first, last, s);
+}
+
+int check_forward_args(const fscnn_ctx* c, const void* x, int n, int h, int w, const void* ws, size_t ws_bytes, Dims* d,
+                       int* mb, WsPlan* plan) {
+    if (!c) return fail(FSCNN_EINVAL, "null context");
+    if (!c->loaded) return fail(FSCNN_ESTATE, "fscnn_load_weights has not been called");
+    if (!x || !ws) return fail(FSCNN_EINVAL, "null input or workspace pointer");
+    if (n < 1) return fail(FSCNN_EINVAL, "batch size %d < 1", n);
+    *d = make_dims(h, w);
+    if (!d->ok) return fail(FSCNN_EINVAL, "input %dx%d is too small for five stride-2 stages", h, w);
+    if (((uintptr_t)x & 15) || ((uintptr_t)ws & 255)) return fail(FSCNN_EINVAL, "input must be 16-byte and workspace 256-byte aligned");
+    *mb = c->eff_mb(n, h, w);
+    *plan = c->plan(*mb, *d);
+    if (ws_bytes < plan->total)
+        return fail(FSCNN_ENOMEM, "workspace of %zu bytes is smaller than the %zu needed", ws_bytes, plan->total);
+    return FSCNN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fscnn_abi_version(void) { return FSCNN_ABI_VERSION; }
+const char* fscnn_last_error(void) { return g_err.c_str(); }
+int64_t fscnn_conf_len(int num_classes) { return (int64_t)(num_classes + 1) * (num_classes + 1) + 2; }
+
+int fscnn_create(fscnn_ctx** out, int num_classes, int aux, int precision) {
+    if (!out) return fail(FSCNN_EINVAL, "null output pointer");
+    if (num_classes < 1 || num_classes > 256) return fail(FSCNN_EINVAL, "num_classes %d outside [1, 256]", num_classes);
+    if (precision != FSCNN_PREC_FP32 && precision != FSCNN_PREC_BF16) return fail(FSCNN_EINVAL, "unknown precision %d", precision);
+    fscnn_ctx* c = new fscnn_ctx();
+    c->nc = num_classes;
+    c->ncp = (num_classes + 3) & ~3;
+    c->aux = aux ? 1 : 0;
+    c->prec = precision;
+    build_manifest_and_offsets(c);
+    *out = c;
+    return FSCNN_OK;
+}
+
+void fscnn_destroy(fscnn_ctx* ctx) { delete ctx; }
+
+int fscnn_param_count(const fscnn_ctx* ctx) { return ctx ? (int)ctx->params.size() : 0; }
+const char* fscnn_param_name(const fscnn_ctx* ctx, int i) {
+    return (ctx && i >= 0 && i < (int)ctx->params.size()) ? ctx->params[i].name.c_str() : nullptr;
+}
+int64_t fscnn_param_numel(const fscnn_ctx* ctx, int i) {
+    return (ctx && i >= 0 && i < (int)ctx->params.size()) ? ctx->params[i].numel : -1;
+}
+
+int fscnn_packed_weight_bytes(const fscnn_ctx* ctx, size_t* out_bytes) {
+    if (!ctx || !out_bytes) return fail(FSCNN_EINVAL, "null argument");
+    *out_bytes = ctx->packed_floats * sizeof(float);
+    return FSCNN_OK;
+}
+
+int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors, void* d_packed, size_t packed_bytes,
+                       void* stream) {
+    if (!c || !tensors || !d_packed) return fail(FSCNN_EINVAL, "null argument");
+    if (packed_bytes < c->packed_floats * sizeof(float))
+        return fail(FSCNN_ENOMEM, "packed buffer of %zu bytes is smaller than the %zu needed", packed_bytes,
+                    c->packed_floats * sizeof(float));
+    if ((uintptr_t)d_packed & 255) return fail(FSCNN_EINVAL, "packed buffer must be 256-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    Loader L;
+    L.s = s;
+    for (int i = 0; i < n_tensors; ++i)
+        if (tensors[i].name) L.map[tensors[i].name] = &tensors[i];
+    float* P = reinterpret_cast<float*>(d_packed);
+    if (cudaMemsetAsync(P, 0, c->packed_floats * sizeof(float), s) != cudaSuccess)
+        return fail(FSCNN_ECUDA, "memset of the packed buffer failed: %s", cudaGetErrorString(cudaGetLastError()));
+    const auto& f = c->off;
+    c->loaded = false;
+
+    L.fold("learning_to_downsample.conv.conv.0", false, "learning_to_downsample.conv.conv.1", 32, 27, 1, 0, P + f.stem_w, 32,
+           P + f.stem_b);
+    c->stem = {P + f.stem_w, P + f.stem_b};
+    const struct { const char* p; int cin, cout; } dss[4] = {{"learning_to_downsample.dsconv1", 32, 48},
+                                                              {"learning_to_downsample.dsconv2", 48, 64},
+                                                              {"classifier.dsconv1", 128, 128},
+                                                              {"classifier.dsconv2", 128, 128}};
+    for (int i = 0; i < 4; ++i) {
+        const std::string p = dss[i].p;
+        L.fold(p + ".conv.0", false, p + ".conv.1", dss[i].cin, 9, 1, 0, P + f.ds_wd[i], dss[i].cin, P + f.ds_bd[i]);
+        L.fold(p + ".conv.3", false, p + ".conv.4", dss[i].cout, dss[i].cin, 1, 0, P + f.ds_wp[i], dss[i].cout, P + f.ds_bp[i]);
+        c->ds[i] = {P + f.ds_wd[i], P + f.ds_bd[i], P + f.ds_wp[i], P + f.ds_bp[i]};
+    }
+    for (int i = 0; i < 9; ++i) {
+        const std::string p = std::string("global_feature_extractor.") + kBnecks[i].name + ".block";
+        const int ci = kBnecks[i].cin, ce = 6 * ci, co = kBnecks[i].cout;
+        L.fold(p + ".0.conv.0", false, p + ".0.conv.1", ce, ci, 1, 0, P + f.bn_we[i], ce, P + f.bn_be[i]);
+        L.fold(p + ".1.conv.0", false, p + ".1.conv.1", ce, 9, 1, 0, P + f.bn_wd[i], ce, P + f.bn_bd[i]);
+        L.fold(p + ".2", false, p + ".3", co, ce, 1, 0, P + f.bn_wp[i], co, P + f.bn_bp[i]);
+        c->bn[i] = {P + f.bn_we[i], P + f.bn_be[i], P + f.bn_wd[i], P + f.bn_bd[i], P + f.bn_wp[i], P + f.bn_bp[i]};
+    }
+    for (int i = 0; i < 4; ++i) {
+        const std::string p = "global_feature_extractor.ppm.conv" + std::to_string(i + 1) + ".conv";
+        L.fold(p + ".0", false, p + ".1", 32, 128, 1, 0, P + f.ppm_wc[i], 32, P + f.ppm_bc[i]);
+        c->ppm.wc[i] = P + f.ppm_wc[i];
+        c->ppm.bc[i] = P + f.ppm_bc[i];
+        c->ppm.wo_s[i] = P + f.ppm_wo + (size_t)(128 + 32 * i) * 128;   // cat order: x, feat1..feat4 (:143)
+    }
+    L.fold("global_feature_extractor.ppm.out.conv.0", false, "global_feature_extractor.ppm.out.conv.1", 128, 256, 1, 0,
+           P + f.ppm_wo, 128, P + f.ppm_bo);
+    c->ppm.wo_x = P + f.ppm_wo;
+    c->ppm.bo = P + f.ppm_bo;
+    L.fold("feature_fusion.dwconv.conv.0", false, "feature_fusion.dwconv.conv.1", 128, 9, 1, 0, P + f.ffm_wd, 128, P + f.ffm_bd);
+    L.fold("feature_fusion.conv_higher_res.0", true, "feature_fusion.conv_higher_res.1", 128, 64, 1, 0, P + f.ffm_wcat, 128,
+           P + f.ffm_bcat, 0);
+    L.fold("feature_fusion.conv_lower_res.0", true, "feature_fusion.conv_lower_res.1", 128, 128, 1, 0,
+           P + f.ffm_wcat + (size_t)64 * 128, 128, P + f.ffm_bcat, 1);
+    c->ffm = {P + f.ffm_wd, P + f.ffm_bd, P + f.ffm_wcat, P + f.ffm_bcat};
+    L.fold("classifier.conv.1", true, "", c->nc, 128, 1, 0, P + f.head_w, c->ncp, P + f.head_b);
+    c->head = {P + f.head_w, P + f.head_b, c->nc, c->ncp};
+    if (c->aux) {
+        L.fold("auxlayer.0", false, "auxlayer.1", 32, 576, 9, 1, P + f.aux_w, 32, P + f.aux_b);
+        L.fold("auxlayer.4", true, "", c->nc, 32, 1, 0, P + f.auxh_w, c->ncp, P + f.auxh_b);
+        c->auxw = {P + f.aux_w, P + f.aux_b, {P + f.auxh_w, P + f.auxh_b, c->nc, c->ncp}};
+    }
+    if (L.err) return L.err;
+    c->loaded = true;
+    return FSCNN_OK;
+}
+
+int fscnn_workspace_bytes(const fscnn_ctx* c, int n, int h, int w, size_t* out_bytes) {
+    if (!c || !out_bytes) return fail(FSCNN_EINVAL, "null argument");
+    const Dims d = make_dims(h, w);
+    if (!d.ok || n < 1) return fail(FSCNN_EINVAL, "bad shape n=%d h=%d w=%d", n, h, w);
+    *out_bytes = c->plan(c->eff_mb(n, h, w), d).total;
+    return FSCNN_OK;
+}
+
+int fscnn_set_micro_batch(fscnn_ctx* c, int images) {
+    if (!c || images < 0) return fail(FSCNN_EINVAL, "bad argument");
+    c->micro_batch = images;
+    return FSCNN_OK;
+}
+
+int64_t fscnn_launch_count(const fscnn_ctx* c) { return c ? c->launches : 0; }
+int fscnn_stage_count(const fscnn_ctx* c) { return c ? (c->aux ? kNumStages : kNumStages - 1) : 0; }
+const char* fscnn_stage_name(const fscnn_ctx* c, int stage) {
+    return (c && stage >= 0 && stage < fscnn_stage_count(c)) ? kStageNames[stage] : nullptr;
+}
+
+int fscnn_tap_info(const fscnn_ctx* c, int n, int h, int w, const char* tap, fscnn_tap* out) {
+    if (!c || !tap || !out) return fail(FSCNN_EINVAL, "null argument");
+    const Dims d = make_dims(h, w);
+    if (!d.ok || n < 1) return fail(FSCNN_EINVAL, "bad shape n=%d h=%d w=%d", n, h, w);
+    const int mb = c->eff_mb(n, h, w);
+    const WsPlan p = c->plan(mb, d);
+    const std::string t = tap;
+    const int es = c->esize();
+    auto set = [&](size_t off, int hh, int ww, int ch, int cs, int eb) {
+        *out = {off, mb, hh, ww, ch, cs, eb};
+        return FSCNN_OK;
+    };
+    if (t == "l2d.conv") return set(p.stem, d.h1, d.w1, 32, 32, es);
+    if (t == "l2d.dsconv1") return set(p.ds1, d.h2, d.w2, 48, 48, es);
+    if (t == "l2d.dsconv2") return set(p.higher, d.h3, d.w3, 64, 64, es);
+    for (int i = 0; i < 9; ++i)
+        if (t == std::string("gfe.") + kBnecks[i].name)
+            return set(p.b[i], i < 3 ? d.h4 : d.h5, i < 3 ? d.w4 : d.w5, kBnecks[i].cout, kBnecks[i].cout, es);
+    if (t == "gfe.ppm") return set(p.ppm, d.h5, d.w5, 128, 128, es);
+    if (t == "ffm") return set(p.ffm, d.h3, d.w3, 128, 128, es);
+    if (t == "cls.dsconv1") return set(p.cls1, d.h3, d.w3, 128, 128, es);
+    if (t == "cls.logits_lowres") return set(p.logits, d.h3, d.w3, c->nc, c->ncp, 4);
+    if (t == "aux.logits_lowres" && c->aux) return set(p.aux_logits, d.h3, d.w3, c->nc, c->ncp, 4);
+    return fail(FSCNN_ENOENT, "unknown tap '%s'", tap);
+}
+
+int fscnn_forward_range(fscnn_ctx* c, const float* d_x, int n, int h, int w, int first, int last, void* ws, size_t ws_bytes,
+                        void* stream) {
+    Dims d; int mb; WsPlan p;
+    int rc = check_forward_args(c, d_x, n, h, w, ws, ws_bytes, &d, &mb, &p);
+    if (rc) return rc;
+    if (n > mb) return fail(FSCNN_EINVAL, "forward_range handles one micro-batch (%d images), got %d", mb, n);
+    if (first < 0 || last >= fscnn_stage_count(c) || first > last) return fail(FSCNN_EINVAL, "bad stage range [%d, %d]", first, last);
+    return dispatch_stages(c, d_x, n, d, p, (char*)ws, first, last, (cudaStream_t)stream);
+}
+
+int fscnn_forward_logits(fscnn_ctx* c, const float* d_x, int n, int h, int w, float* d_logits, float* d_aux, void* ws,
+                         size_t ws_bytes, void* stream) {
+    Dims d; int mb; WsPlan p;
+    int rc = check_forward_args(c, d_x, n, h, w, ws, ws_bytes, &d, &mb, &p);
+    if (rc) return rc;
+    if (!d_logits) return fail(FSCNN_EINVAL, "null logits pointer");
+    if (((uintptr_t)d_logits & 15) || ((uintptr_t)d_aux & 15)) return fail(FSCNN_EINVAL, "logits must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t img = (size_t)3 * h * w, lg = (size_t)c->nc * h * w;
+    const bool want_aux = c->aux && d_aux;
+    for (int i0 = 0; i0 < n; i0 += mb) {
+        const int m = n - i0 < mb ? n - i0 : mb;
+        rc = dispatch_stages(c, d_x + i0 * img, m, d, p, (char*)ws, kStem, want_aux ? kAux : kCls2Head, s);
+        if (rc) return rc;
+        cudaError_t e = launch_up_logits(reinterpret_cast<float*>((char*)ws + p.logits), c->nc, c->ncp, d_logits + i0 * lg, m,
+                                         d.h3, d.w3, h, w, s);
+        c->launches += 1;
+        if (e == cudaSuccess && want_aux) {
+            e = launch_up_logits(reinterpret_cast<float*>((char*)ws + p.aux_logits), c->nc, c->ncp, d_aux + i0 * lg, m, d.h3,
+                                 d.w3, h, w, s);
+            c->launches += 1;
+        }
+        if (e != cudaSuccess) return fail(FSCNN_ECUDA, "upsample launch failed: %s", cudaGetErrorString(e));
+    }
+    return FSCNN_OK;
+}
+
+static int forward_mask_impl(fscnn_ctx* c, const float* d_x, const void* d_labels, int label_dtype, int n, int h, int w,
+                             long long* d_conf, void* d_mask, int mask_dtype, void* ws, size_t ws_bytes, void* stream) {
+    Dims d; int mb; WsPlan p;
+    int rc = check_forward_args(c, d_x, n, h, w, ws, ws_bytes, &d, &mb, &p);
+    if (rc) return rc;
+    if (mask_dtype != FSCNN_U8 && mask_dtype != FSCNN_I32 && mask_dtype != FSCNN_I64) return fail(FSCNN_EINVAL, "bad mask dtype %d", mask_dtype);
+    if (d_labels && label_dtype != FSCNN_U8 && label_dtype != FSCNN_I32 && label_dtype != FSCNN_I64)
+        return fail(FSCNN_EINVAL, "bad label dtype %d", label_dtype);
+    if ((uintptr_t)d_mask & 15) return fail(FSCNN_EINVAL, "mask must be 16-byte aligned");
+    const size_t msz = mask_dtype == FSCNN_U8 ? 1 : (mask_dtype == FSCNN_I32 ? 4 : 8);
+    const size_t lsz = label_dtype == FSCNN_U8 ? 1 : (label_dtype == FSCNN_I32 ? 4 : 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t img = (size_t)3 * h * w, px = (size_t)h * w;
+    for (int i0 = 0; i0 < n; i0 += mb) {
+        const int m = n - i0 < mb ? n - i0 : mb;
+        rc = dispatch_stages(c, d_x + i0 * img, m, d, p, (char*)ws, kStem, kCls2Head, s);
+        if (rc) return rc;
+        cudaError_t e = launch_up_argmax(reinterpret_cast<float*>((char*)ws + p.logits), c->nc, c->ncp,
+                                         d_mask ? (char*)d_mask + i0 * px * msz : nullptr, mask_dtype,
+                                         d_labels ? (const char*)d_labels + i0 * px * lsz : nullptr, label_dtype,
+                                         reinterpret_cast<unsigned long long*>(d_conf), m, d.h3, d.w3, h, w, s);
+        c->launches += 1;
+        if (e != cudaSuccess) return fail(FSCNN_ECUDA, "upsample+argmax launch failed: %s", cudaGetErrorString(e));
+    }
+    return FSCNN_OK;
+}
+
+int fscnn_forward_mask(fscnn_ctx* c, const float* d_x, int n, int h, int w, void* d_mask, int mask_dtype, void* ws,
+                       size_t ws_bytes, void* stream) {
+    if (!d_mask) return fail(FSCNN_EINVAL, "null mask pointer");
+    return forward_mask_impl(c, d_x, nullptr, 0, n, h, w, nullptr, d_mask, mask_dtype, ws, ws_bytes, stream);
+}
+
+int fscnn_forward_confusion(fscnn_ctx* c, const float* d_x, const void* d_labels, int label_dtype, int n, int h, int w,
+                            long long* d_conf, void* d_mask, int mask_dtype, void* ws, size_t ws_bytes, void* stream) {
+    if (!d_labels || !d_conf) return fail(FSCNN_EINVAL, "null labels or confusion pointer");
+    return forward_mask_impl(c, d_x, d_labels, label_dtype, n, h, w, d_conf, d_mask, d_mask ? mask_dtype : FSCNN_U8, ws,
+                             ws_bytes, stream);
+}
+
+int fscnn_confusion_from_mask(const void* d_pred, int pred_dtype, const void* d_label, int label_dtype, int64_t n_pixels,
+                              int num_classes, long long* d_conf, void* stream) {
+    if (!d_conf || n_pixels < 0) return fail(FSCNN_EINVAL, "bad argument");
+    if (n_pixels == 0) return FSCNN_OK;
+    if (!d_pred || !d_label) return fail(FSCNN_EINVAL, "null class map");
+    if (num_classes < 1 || num_classes > 1 << 15) return fail(FSCNN_EINVAL, "num_classes %d out of range", num_classes);
+    for (int dt : {pred_dtype, label_dtype})
+        if (dt != FSCNN_U8 && dt != FSCNN_I32 && dt != FSCNN_I64) return fail(FSCNN_EINVAL, "bad dtype %d", dt);
+    cudaError_t e = launch_confusion(d_pred, pred_dtype, d_label, label_dtype, n_pixels, num_classes,
+                                     reinterpret_cast<unsigned long long*>(d_conf), (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "confusion launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_conf_to_totals(const long long* h_conf, int nc, long long* h_inter, long long* h_union, long long* h_correct,
+                         long long* h_label) {
+    if (!h_conf || !h_inter || !h_union || !h_correct || !h_label || nc < 1) return fail(FSCNN_EINVAL, "bad argument");
+    const int w = nc + 1;
+    for (int k = 0; k < nc; ++k) {
+        long long area_pred = 0, area_lab = 0;
+        for (int r = 0; r < w; ++r) area_pred += h_conf[r * w + k];   // every labeled pixel predicted k
+        for (int q = 0; q < w; ++q) area_lab += h_conf[k * w + q];    // every pixel labeled k
+        h_inter[k] = h_conf[k * w + k];
+        h_union[k] = area_pred + area_lab - h_inter[k];
+    }
+    *h_label = h_conf[w * w];
+    *h_correct = h_conf[w * w + 1];
+    return FSCNN_OK;
+}
+
+}  // extern "C"

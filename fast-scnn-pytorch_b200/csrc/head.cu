@@ -1,0 +1,363 @@
+// head.cu -- the tail of the forward path:
+//   up_logits  : F.interpolate(logits, size, 'bilinear', align_corners=True) (reference
+//                models/fast_scnn.py:40 and :44) -> NCHW fp32, API-parity output of forward();
+//   up_argmax  : the same resize fused with torch.argmax(outputs[0], 1) (eval.py:45, demo.py:48) and,
+//                when labels are given, with SegmentationMetric's counting (utils/metric.py:73-105),
+//                so the full-resolution logits (159 MB / image at 1024x2048) never exist;
+//   confusion  : metric counting for class maps that already exist on the device.
+//
+// One CTA covers 64 output rows x 128 columns; a thread owns 8 rows x 4 adjacent columns.  The
+// low-resolution logits the CTA needs (<= 10 x 18 pixels, because the resize ratio is always < 1/8)
+// are staged class-major in shared memory, so every class costs 9 conflict-free LDS per thread for
+// 32 output pixels.  Interpolation order matches ATen's upsample_bilinear2d: horizontal lerp first,
+// then vertical.  argmax keeps the FIRST maximal class and treats NaN as maximal, like torch.
+#include "kernels.h"
+
+#include "../../include/fscnn_b200.h"
+
+namespace fscnn {
+
+constexpr int kTR = 12, kTC = 20;        // staged low-res tile (<= 10 x 18 needed; the 3rd tap column/row may overhang)
+constexpr int kHistMaxBins = 4096;       // (nc+1)^2 above this -> histogram goes straight to global atomics
+
+template <int DT>
+struct Lab;
+template <> struct Lab<FSCNN_U8> { typedef unsigned char type; };
+template <> struct Lab<FSCNN_I32> { typedef int type; };
+template <> struct Lab<FSCNN_I64> { typedef long long type; };
+
+__device__ __forceinline__ long long load_label(const void* p, int dtype, size_t i) {
+    if (dtype == FSCNN_U8) return (long long)__ldg(reinterpret_cast<const unsigned char*>(p) + i);
+    if (dtype == FSCNN_I32) return (long long)__ldg(reinterpret_cast<const int*>(p) + i);
+    return __ldg(reinterpret_cast<const long long*>(p) + i);
+}
+
+// Adds one (label, pred) observation to the confusion accumulator held in `hist` (shared, uint32) or,
+// when hist == nullptr, directly to the global int64 accumulator.
+struct ConfSink {
+    unsigned int* hist;
+    unsigned long long* conf;
+    int nc;
+    __device__ __forceinline__ void add(int row, int col, unsigned int count) const {
+        const int bin = row * (nc + 1) + col;
+        if (hist) atomicAdd(hist + bin, count);
+        else atomicAdd(conf + bin, (unsigned long long)count);
+    }
+};
+
+// MODE 0: write NCHW fp32 logits.  MODE 1: argmax mask (+ optional confusion counts).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restrict__ out_logits, void* __restrict__ mask,
+                int mask_dtype, const void* __restrict__ labels, int label_dtype, unsigned long long* __restrict__ conf,
+                int hl, int wl, int H, int W, int use_smem_hist) {
+    extern __shared__ __align__(16) float dynsm[];
+    float* Ls = dynsm;                                            // [nc][kTR][kTC]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(dynsm + nc * kTR * kTC);
+    __shared__ unsigned int blk_labeled, blk_correct;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z;
+    const int yb = blockIdx.y * 64, xb = blockIdx.x * 128;
+    const float scy = H > 1 ? (float)(hl - 1) / (float)(H - 1) : 0.f;
+    const float scx = W > 1 ? (float)(wl - 1) / (float)(W - 1) : 0.f;
+    const int rb = min((int)(scy * (float)yb), hl - 1);          // first staged low-res row / column
+    const int cb = min((int)(scx * (float)xb), wl - 1);
+    const bool do_hist = (MODE == 1) && (labels != nullptr);
+
+    for (int i = tid; i < kTR * kTC * ncp; i += kThreads) {
+        const int c = i % ncp, px = i / ncp;
+        const int r = px / kTC, q = px % kTC;
+        if (c < nc) {
+            const int rr = min(rb + r, hl - 1), qq = min(cb + q, wl - 1);
+            Ls[(c * kTR + r) * kTC + q] = __ldg(low + (((size_t)n * hl + rr) * wl + qq) * ncp + c);
+        }
+    }
+    if (do_hist) {
+        if (use_smem_hist)
+            for (int i = tid; i < (nc + 1) * (nc + 1); i += kThreads) hist[i] = 0u;
+        if (tid == 0) { blk_labeled = 0u; blk_correct = 0u; }
+    }
+    __syncthreads();
+
+    const int x0 = xb + lane * 4, y0 = yb + warp * 8;
+    if (x0 >= W || y0 >= H) {
+        if (!do_hist) return;
+    }
+    // horizontal taps of the 4 columns, relative to the staged tile
+    float lx[4], hx[4];
+    int dx[4];
+    const int c0 = min((int)(scx * (float)x0), wl - 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float fx = scx * (float)(x0 + j);
+        const int q = min((int)fx, wl - 1);
+        dx[j] = q - c0;
+        lx[j] = fx - (float)q;
+        hx[j] = 1.f - lx[j];
+    }
+    float ly[8], hy[8];
+    int dy[8];
+    const int r0 = min((int)(scy * (float)y0), hl - 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float fy = scy * (float)(y0 + i);
+        const int r = min((int)fy, hl - 1);
+        dy[i] = r - r0;
+        ly[i] = fy - (float)r;
+        hy[i] = 1.f - ly[i];
+    }
+    // tile-relative offsets of the 3 rows / 3 columns (clamped at the image border like ATen's x1 = x0 + (x0 < w-1))
+    int ro[3], co[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        ro[k] = (min(r0 + k, hl - 1) - rb) * kTC;
+        co[k] = min(c0 + k, wl - 1) - cb;
+    }
+
+    float best[8][4];
+    int bidx[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { best[i][j] = 0.f; bidx[i][j] = 0; }
+
+    const bool live = (x0 < W) && (y0 < H);
+    if (live) {
+        for (int c = 0; c < nc; ++c) {
+            const float* lc = Ls + c * kTR * kTC;
+            float v[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) v[r][q] = lc[ro[r] + co[q]];
+            float hrow[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = dx[j] ? v[r][1] : v[r][0];
+                    const float b = dx[j] ? v[r][2] : v[r][1];
+                    hrow[r][j] = hx[j] * a + lx[j] * b;
+                }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float val[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float t = dy[i] ? hrow[1][j] : hrow[0][j];
+                    const float b = dy[i] ? hrow[2][j] : hrow[1][j];
+                    val[j] = hy[i] * t + ly[i] * b;
+                }
+                if (MODE == 0) {
+                    if (y0 + i < H) {
+                        float* o = out_logits + (((size_t)n * nc + c) * H + (y0 + i)) * W + x0;
+                        if ((W & 3) == 0) {
+                            __stcs(reinterpret_cast<float4*>(o), make_float4(val[0], val[1], val[2], val[3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (x0 + j < W) o[j] = val[j];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        // first max wins; NaN beats everything except an earlier NaN
+                        const bool upd = (c == 0) || (!(val[j] <= best[i][j]) && (best[i][j] == best[i][j]));
+                        if (upd) { best[i][j] = val[j]; bidx[i][j] = c; }
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 0) return;
+
+    // ---- write the mask ----
+    if (live && mask) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (y0 + i >= H) break;
+            const size_t off = ((size_t)n * H + (y0 + i)) * W + x0;
+            if (mask_dtype == FSCNN_U8) {
+                unsigned char* m = reinterpret_cast<unsigned char*>(mask) + off;
+                if ((W & 3) == 0) {
+                    *reinterpret_cast<uchar4*>(m) = make_uchar4((unsigned char)bidx[i][0], (unsigned char)bidx[i][1],
+                                                                (unsigned char)bidx[i][2], (unsigned char)bidx[i][3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x0 + j < W) m[j] = (unsigned char)bidx[i][j];
+                }
+            } else if (mask_dtype == FSCNN_I32) {
+                int* m = reinterpret_cast<int*>(mask) + off;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x0 + j < W) m[j] = bidx[i][j];
+            } else {
+                long long* m = reinterpret_cast<long long*>(mask) + off;
+                if ((W & 1) == 0) {
+                    *reinterpret_cast<longlong2*>(m) = make_longlong2(bidx[i][0], bidx[i][1]);
+                    *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(bidx[i][2], bidx[i][3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x0 + j < W) m[j] = bidx[i][j];
+                }
+            }
+        }
+    }
+    if (!do_hist) return;
+
+    // ---- SegmentationMetric counting: run-length aggregated shared-memory atomics ----
+    const ConfSink sink{use_smem_hist ? hist : nullptr, conf, nc};
+    unsigned int labeled = 0, correct = 0;
+    if (live) {
+        int run_row = -1, run_col = 0;
+        unsigned int run = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (y0 + i >= H) break;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (x0 + j >= W) break;
+                const long long lab = load_label(labels, label_dtype, ((size_t)n * H + (y0 + i)) * W + x0 + j);
+                if (lab < 0) continue;                      // metric.py:79/:96 -- label+1 > 0 marks a labeled pixel
+                const int row = lab < nc ? (int)lab : nc;   // labels >= nclass: overflow row
+                const int col = bidx[i][j];
+                labeled += 1;
+                correct += (lab == (long long)col);
+                if (row == run_row && col == run_col) { run += 1; continue; }
+                if (run) sink.add(run_row, run_col, run);
+                run_row = row; run_col = col; run = 1;
+            }
+        }
+        if (run) sink.add(run_row, run_col, run);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        labeled += __shfl_xor_sync(0xffffffffu, labeled, o);
+        correct += __shfl_xor_sync(0xffffffffu, correct, o);
+    }
+    if (lane == 0) { atomicAdd(&blk_labeled, labeled); atomicAdd(&blk_correct, correct); }
+    __syncthreads();
+    const int nb = (nc + 1) * (nc + 1);
+    if (use_smem_hist)
+        for (int i = tid; i < nb; i += kThreads) {
+            const unsigned int v = hist[i];
+            if (v) atomicAdd(conf + i, (unsigned long long)v);
+        }
+    if (tid == 0) {
+        if (blk_labeled) atomicAdd(conf + nb, (unsigned long long)blk_labeled);
+        if (blk_correct) atomicAdd(conf + nb + 1, (unsigned long long)blk_correct);
+    }
+}
+
+static size_t up_smem_bytes(int nc, bool hist) {
+    size_t b = (size_t)nc * kTR * kTC * sizeof(float);
+    if (hist) b += (size_t)(nc + 1) * (nc + 1) * sizeof(unsigned int);
+    return b;
+}
+
+cudaError_t launch_up_logits(const float* low, int nc, int ncp, float* out, int n, int hl, int wl, int h, int w,
+                             cudaStream_t s) {
+    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1)) return cudaErrorInvalidValue;
+    static unsigned long long configured = 0;
+    static size_t configured_bytes = 48 * 1024;
+    const size_t smem = up_smem_bytes(nc, false);
+    if (smem > configured_bytes) { configured = 0; configured_bytes = smem; }
+    if (smem > 48 * 1024) {
+        cudaError_t e = ensure_dyn_smem(upsample_kernel<0>, configured_bytes, configured);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(ceil_div(w, 128), ceil_div(h, 64), n);
+    upsample_kernel<0><<<grid, kThreads, smem, s>>>(low, nc, ncp, out, nullptr, 0, nullptr, 0, nullptr, hl, wl, h, w, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
+                             int label_dtype, unsigned long long* conf, int n, int hl, int wl, int h, int w,
+                             cudaStream_t s) {
+    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1)) return cudaErrorInvalidValue;
+    const bool hist = labels != nullptr;
+    const int smem_hist = hist && ((nc + 1) * (nc + 1) <= kHistMaxBins);
+    static unsigned long long configured = 0;
+    static size_t configured_bytes = 48 * 1024;
+    const size_t smem = up_smem_bytes(nc, smem_hist);
+    if (smem > configured_bytes) { configured = 0; configured_bytes = smem; }
+    if (smem > 48 * 1024) {
+        cudaError_t e = ensure_dyn_smem(upsample_kernel<1>, configured_bytes, configured);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(ceil_div(w, 128), ceil_div(h, 64), n);
+    upsample_kernel<1><<<grid, kThreads, smem, s>>>(low, nc, ncp, nullptr, mask, mask_dtype, labels, label_dtype, conf, hl,
+                                                    wl, h, w, smem_hist);
+    return cudaGetLastError();
+}
+
+// ---- SegmentationMetric counting on existing class maps (utils/metric.py:73-105) ----
+__global__ void __launch_bounds__(kThreads)
+confusion_kernel(const void* __restrict__ pred, int pred_dtype, const void* __restrict__ label, int label_dtype,
+                 long long npix, int nc, unsigned long long* __restrict__ conf, int use_smem_hist) {
+    extern __shared__ unsigned int hist_dyn[];
+    __shared__ unsigned int blk_labeled, blk_correct;
+    const int tid = threadIdx.x;
+    const int nb = (nc + 1) * (nc + 1);
+    if (use_smem_hist)
+        for (int i = tid; i < nb; i += kThreads) hist_dyn[i] = 0u;
+    if (tid == 0) { blk_labeled = 0u; blk_correct = 0u; }
+    __syncthreads();
+    const ConfSink sink{use_smem_hist ? hist_dyn : nullptr, conf, nc};
+    unsigned int labeled = 0, correct = 0;
+    // each thread walks a contiguous run of 16 pixels so that equal neighbours aggregate
+    const long long chunk = 16;
+    for (long long base = ((long long)blockIdx.x * kThreads + tid) * chunk; base < npix;
+         base += (long long)gridDim.x * kThreads * chunk) {
+        int run_row = -1, run_col = 0;
+        unsigned int run = 0;
+        const long long end = base + chunk < npix ? base + chunk : npix;
+        for (long long i = base; i < end; ++i) {
+            const long long lab = load_label(label, label_dtype, (size_t)i);
+            if (lab < 0) continue;
+            const long long pr = load_label(pred, pred_dtype, (size_t)i);
+            const int row = lab < nc ? (int)lab : nc;
+            const int col = (pr >= 0 && pr < nc) ? (int)pr : nc;   // preds outside the class range: overflow column
+            labeled += 1;
+            correct += (lab == pr);
+            if (row == run_row && col == run_col) { run += 1; continue; }
+            if (run) sink.add(run_row, run_col, run);
+            run_row = row; run_col = col; run = 1;
+        }
+        if (run) sink.add(run_row, run_col, run);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        labeled += __shfl_xor_sync(0xffffffffu, labeled, o);
+        correct += __shfl_xor_sync(0xffffffffu, correct, o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&blk_labeled, labeled); atomicAdd(&blk_correct, correct); }
+    __syncthreads();
+    if (use_smem_hist)
+        for (int i = tid; i < nb; i += kThreads) {
+            const unsigned int v = hist_dyn[i];
+            if (v) atomicAdd(conf + i, (unsigned long long)v);
+        }
+    if (tid == 0) {
+        if (blk_labeled) atomicAdd(conf + nb, (unsigned long long)blk_labeled);
+        if (blk_correct) atomicAdd(conf + nb + 1, (unsigned long long)blk_correct);
+    }
+}
+
+cudaError_t launch_confusion(const void* pred, int pred_dtype, const void* label, int label_dtype, long long npix, int nc,
+                             unsigned long long* conf, cudaStream_t s) {
+    if (npix <= 0) return cudaSuccess;
+    const int nb = (nc + 1) * (nc + 1);
+    const int smem_hist = nb <= kHistMaxBins;
+    long long blocks = (npix + (long long)kThreads * 16 - 1) / ((long long)kThreads * 16);
+    if (blocks > 148 * 8) blocks = 148 * 8;   // grid-stride beyond 8 CTAs per SM
+    confusion_kernel<<<(unsigned)blocks, kThreads, smem_hist ? nb * sizeof(unsigned int) : 0, s>>>(
+        pred, pred_dtype, label, label_dtype, npix, nc, conf, smem_hist);
+    return cudaGetLastError();
+}
+
+}  // namespace fscnn

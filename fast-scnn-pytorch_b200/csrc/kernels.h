@@ -1,0 +1,66 @@
+// kernels.h -- host-side launchers of the Fast-SCNN stage kernels (one .cu per kernel family).
+#pragma once
+#include "common.cuh"
+
+namespace fscnn {
+
+// Folded (BatchNorm merged) fp32 weights, "k-major": W[k][cout] so that a contraction chunk is a
+// dense [KC][COUT] tile.  Depthwise weights are tap-major: W[tap][channel].
+struct StemW { const float *w, *b; };                       // [27][32] (k = ci*9+ky*3+kx), [32]
+struct DsW { const float *wd, *bd, *wp, *bp; };             // [9][cin], [cin], [cin][cout], [cout]
+struct HeadW { const float *w, *b; int nc, ncp; };          // [cin][ncp], [ncp]; ncp = nc rounded up to 4
+struct BneckW { const float *we, *be, *wd, *bd, *wp, *bp; };  // [cin][6cin],[6cin],[9][6cin],[6cin],[6cin][cout],[cout]
+struct PpmW {
+    const float* wc[4]; const float* bc[4];                 // branch convs [128][32], [32]
+    const float* wo_x; const float* wo_s[4]; const float* bo;  // out conv split: [128][128], 4x[32][128], [128]
+};
+struct FfmW { const float *wd, *bd, *wcat, *bcat; };        // [9][128],[128],[192][128] (64 higher | 128 lower),[128]
+struct AuxW { const float *w, *b; HeadW head; };            // [576][32] (k = tap*64+ci), [32]
+
+template <typename T>
+cudaError_t launch_stem(const float* x, const StemW& w, T* out, int n, int h, int wd, int ho, int wo, cudaStream_t s);
+
+// _DSConv: DW3x3(stride, pad 1)+ReLU -> PW 1x1+ReLU, optionally chained with the classifier's 1x1 head
+// (head != nullptr: `out` is not written, low-res logits [n][ho][wo][ncp] fp32 are).
+template <typename T>
+cudaError_t launch_dsconv(int cin, int cout, int stride, const T* in, const DsW& w, T* out, const HeadW* head,
+                          float* logits, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
+
+// LinearBottleneck: PW expand+ReLU -> DW3x3(stride)+ReLU -> PW project (+ residual).
+template <typename T>
+cudaError_t launch_bottleneck(int cin, int cout, int stride, const T* in, const BneckW& w, T* out,
+                              int n, int hi, int wi, int ho, int wo, cudaStream_t s);
+
+// PyramidPooling in three launches: per-row partial bin sums, per-bin reduce + branch conv + projection
+// through the out conv, then the K=128 contraction with the interpolated branch term.
+template <typename T>
+cudaError_t launch_ppm(const T* in, const PpmW& w, float* rowsum, float* z, T* out, int n, int h, int wd, cudaStream_t s);
+
+// FeatureFusionModule: bilinear (align_corners) upsample of `lower` to higher's size, DW3x3+ReLU,
+// both 1x1 convs as one K=192 contraction, add, ReLU.
+template <typename T>
+cudaError_t launch_ffm(const T* higher, const T* lower, const FfmW& w, T* out, int n, int hh, int wh, int hl, int wl,
+                       cudaStream_t s);
+
+// Aux head: dense 3x3 (64->32, pad 1)+ReLU -> 1x1 to classes; low-res logits [n][h][w][ncp] fp32.
+template <typename T>
+cudaError_t launch_aux(const T* higher, const AuxW& w, float* logits, int n, int h, int wd, cudaStream_t s);
+
+// Final bilinear (align_corners) upsample of low-res logits [n][hl][wl][ncp]:
+//  - to full-resolution NCHW fp32 logits (API parity with FastSCNN.forward), or
+//  - fused with argmax (first max wins, NaN counts as max) and optionally the confusion histogram.
+cudaError_t launch_up_logits(const float* low, int nc, int ncp, float* out, int n, int hl, int wl, int h, int w,
+                             cudaStream_t s);
+cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
+                             int label_dtype, unsigned long long* conf, int n, int hl, int wl, int h, int w,
+                             cudaStream_t s);
+cudaError_t launch_confusion(const void* pred, int pred_dtype, const void* label, int label_dtype, long long npix, int nc,
+                             unsigned long long* conf, cudaStream_t s);
+
+// BN folding + repack (load time).  out_w[k'][co] = w[co][k] * gamma/sqrt(var+eps); with taps > 1 and
+// `tap_major` the k index (ci*taps + tap) is permuted to (tap*cin + ci).  out_b = beta + (cbias - mean)*scale.
+cudaError_t launch_fold(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
+                        const float* var, int cout, int kdim, int taps, int tap_major, float* out_w, int ld_out,
+                        float* out_b, int accumulate_bias, cudaStream_t s);
+
+}  // namespace fscnn

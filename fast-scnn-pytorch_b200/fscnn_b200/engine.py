@@ -1,0 +1,162 @@
+"""Engine: one native context + its device buffers, all allocated by PyTorch.
+
+The engine is what ``models.fast_scnn.FastSCNN`` (the drop-in nn.Module) delegates to in eval mode
+on a CUDA tensor.  Ownership follows include/fscnn_b200.h: torch owns every buffer (packed
+weights, workspace, outputs); the native library only enqueues kernels on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import native
+
+PRECISIONS = {'fp32': native.PREC_FP32, 'bf16': native.PREC_BF16}
+_DTYPE_CODE = {torch.uint8: native.U8, torch.int32: native.I32, torch.int64: native.I64}
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    def __init__(self, num_classes: int, aux: bool, precision: str = 'fp32'):
+        if precision not in PRECISIONS:
+            raise ValueError(f'precision must be one of {sorted(PRECISIONS)}, got {precision!r}')
+        self.lib = native.lib()
+        self.num_classes, self.aux, self.precision = int(num_classes), bool(aux), precision
+        handle = C.c_void_p()
+        native.check(self.lib.fscnn_create(C.byref(handle), self.num_classes, int(self.aux), PRECISIONS[precision]),
+                     'fscnn_create')
+        self._ctx = handle
+        self._packed: Optional[torch.Tensor] = None
+        self._ws: Dict[torch.device, torch.Tensor] = {}
+        self.device: Optional[torch.device] = None
+
+    def __del__(self):
+        ctx, self._ctx = getattr(self, '_ctx', None), None
+        if ctx:
+            self.lib.fscnn_destroy(ctx)
+
+    # ---- weights ---------------------------------------------------------------------------
+    def param_manifest(self):
+        n = self.lib.fscnn_param_count(self._ctx)
+        return [(self.lib.fscnn_param_name(self._ctx, i).decode(), int(self.lib.fscnn_param_numel(self._ctx, i)))
+                for i in range(n)]
+
+    def load_state_dict(self, state_dict, device: torch.device) -> None:
+        """Folds BN into the convolutions and repacks, on `device` (fscnn_load_weights)."""
+        device = torch.device(device)
+        manifest = self.param_manifest()
+        keep, arr = [], (native.Tensor * len(manifest))()
+        for i, (name, numel) in enumerate(manifest):
+            if name not in state_dict:
+                raise KeyError(f'state_dict is missing {name!r}')
+            t = state_dict[name].detach().to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            arr[i] = native.Tensor(name.encode(), t.data_ptr(), t.numel())
+        nbytes = C.c_size_t()
+        native.check(self.lib.fscnn_packed_weight_bytes(self._ctx, C.byref(nbytes)))
+        with torch.cuda.device(device):
+            packed = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+            native.check(self.lib.fscnn_load_weights(self._ctx, arr, len(manifest), packed.data_ptr(), nbytes.value,
+                                                     _stream_ptr()), 'fscnn_load_weights')
+            # the fold kernels read `keep` asynchronously; hold the staging tensors until they are done
+            torch.cuda.current_stream().synchronize()
+        self._packed, self.device = packed, device
+        self._ws.clear()
+
+    # ---- buffers ---------------------------------------------------------------------------
+    def _workspace(self, n: int, h: int, w: int) -> torch.Tensor:
+        need = C.c_size_t()
+        native.check(self.lib.fscnn_workspace_bytes(self._ctx, n, h, w, C.byref(need)), 'fscnn_workspace_bytes')
+        ws = self._ws.get(self.device)
+        if ws is None or ws.numel() < need.value:
+            ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            self._ws[self.device] = ws
+        return ws
+
+    def _check_input(self, x: torch.Tensor) -> Tuple[int, int, int]:
+        if self._packed is None:
+            raise RuntimeError('Engine.load_state_dict has not been called')
+        if not x.is_cuda or x.device != self.device:
+            raise RuntimeError(f'input is on {x.device}, weights are on {self.device}; there is no CPU path')
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f'expected an [N,3,H,W] image batch, got {tuple(x.shape)}')
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            raise ValueError('input must be a contiguous float32 tensor')
+        return x.shape[0], x.shape[2], x.shape[3]
+
+    # ---- the forward path --------------------------------------------------------------------
+    def forward_logits(self, x: torch.Tensor, want_aux: bool):
+        n, h, w = self._check_input(x)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(n, h, w)
+            logits = torch.empty((n, self.num_classes, h, w), dtype=torch.float32, device=self.device)
+            aux = torch.empty_like(logits) if (want_aux and self.aux) else None
+            native.check(self.lib.fscnn_forward_logits(self._ctx, x.data_ptr(), n, h, w, logits.data_ptr(),
+                                                       aux.data_ptr() if aux is not None else None, ws.data_ptr(),
+                                                       ws.numel(), _stream_ptr()), 'fscnn_forward_logits')
+        return logits, aux
+
+    def forward_mask(self, x: torch.Tensor, out_dtype=torch.uint8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n, h, w = self._check_input(x)
+        if out_dtype not in _DTYPE_CODE:
+            raise ValueError('mask dtype must be torch.uint8, torch.int32 or torch.int64')
+        with torch.cuda.device(self.device):
+            ws = self._workspace(n, h, w)
+            mask = out if out is not None else torch.empty((n, h, w), dtype=out_dtype, device=self.device)
+            native.check(self.lib.fscnn_forward_mask(self._ctx, x.data_ptr(), n, h, w, mask.data_ptr(),
+                                                     _DTYPE_CODE[mask.dtype], ws.data_ptr(), ws.numel(), _stream_ptr()),
+                         'fscnn_forward_mask')
+        return mask
+
+    def forward_confusion(self, x: torch.Tensor, labels: torch.Tensor, conf: torch.Tensor,
+                          mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n, h, w = self._check_input(x)
+        if labels.dtype not in _DTYPE_CODE or tuple(labels.shape) != (n, h, w) or not labels.is_contiguous():
+            raise ValueError('labels must be a contiguous [N,H,W] uint8/int32/int64 tensor')
+        if labels.device != self.device or conf.device != self.device:
+            raise RuntimeError('labels / conf must be on the model device')
+        if conf.dtype != torch.int64 or conf.numel() != self.conf_len() or not conf.is_contiguous():
+            raise ValueError(f'conf must be a contiguous int64[{self.conf_len()}] tensor')
+        with torch.cuda.device(self.device):
+            ws = self._workspace(n, h, w)
+            native.check(self.lib.fscnn_forward_confusion(
+                self._ctx, x.data_ptr(), labels.data_ptr(), _DTYPE_CODE[labels.dtype], n, h, w, conf.data_ptr(),
+                mask.data_ptr() if mask is not None else None, _DTYPE_CODE[mask.dtype] if mask is not None else 0,
+                ws.data_ptr(), ws.numel(), _stream_ptr()), 'fscnn_forward_confusion')
+        return conf
+
+    def conf_len(self) -> int:
+        return int(self.lib.fscnn_conf_len(self.num_classes))
+
+    # ---- test / profiling hooks ----------------------------------------------------------------
+    def stage_names(self):
+        return [self.lib.fscnn_stage_name(self._ctx, i).decode() for i in range(self.lib.fscnn_stage_count(self._ctx))]
+
+    def forward_range(self, x: torch.Tensor, first: int, last: int) -> None:
+        n, h, w = self._check_input(x)
+        with torch.cuda.device(self.device):
+            ws = self._workspace(n, h, w)
+            native.check(self.lib.fscnn_forward_range(self._ctx, x.data_ptr(), n, h, w, first, last, ws.data_ptr(),
+                                                      ws.numel(), _stream_ptr()), 'fscnn_forward_range')
+
+    def tap_view(self, name: str, n: int, h: int, w: int) -> torch.Tensor:
+        """A [n,h',w',c] view (NHWC) of a stage tensor inside the workspace."""
+        tap = native.Tap()
+        native.check(self.lib.fscnn_tap_info(self._ctx, n, h, w, name.encode(), C.byref(tap)), 'fscnn_tap_info')
+        ws = self._workspace(n, h, w)
+        dtype = torch.float32 if tap.elem_bytes == 4 else torch.bfloat16
+        count = tap.n * tap.h * tap.w * tap.c_stride
+        flat = ws[tap.offset_bytes: tap.offset_bytes + count * tap.elem_bytes].view(dtype)
+        return flat.view(tap.n, tap.h, tap.w, tap.c_stride)[..., :tap.c]
+
+    def launch_count(self) -> int:
+        return int(self.lib.fscnn_launch_count(self._ctx))
+
+    def set_micro_batch(self, images: int) -> None:
+        native.check(self.lib.fscnn_set_micro_batch(self._ctx, int(images)))
+        self._ws.clear()

@@ -1,0 +1,161 @@
+/*
+ * fscnn_b200.h -- C ABI of libfscnn_b200.so: the B200 (sm_100a) implementation of the
+ * Fast-SCNN segmentation forward path (forward -> argmax -> SegmentationMetric counts).
+ *
+ * This is the drop-in boundary.  The reference (Shinokawa/Fast-SCNN-pytorch) is pure Python
+ * and has no FFI of its own; what it binds for this path are torch.nn modules and numpy.  Each
+ * entry point below names the reference interface it replaces (file:line into the reference
+ * checkout).  The Python host (fast-scnn-pytorch_b200/models/fast_scnn.py, utils/metric.py)
+ * binds these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / ATen / pybind types cross this boundary;
+ *  - every pointer named d_* is DEVICE memory owned by the caller (PyTorch allocates it);
+ *    pointers named h_* are HOST memory; the library never allocates or frees device memory and
+ *    never synchronises the device inside a forward call (CUDA-graph capturable);
+ *  - all work is enqueued on the cudaStream_t passed as `stream` (void* here so that C callers
+ *    need no CUDA headers);
+ *  - every function returns 0 on success or a negative FSCNN_E* code; fscnn_last_error() returns
+ *    a thread-local message for the last failure on the calling thread;
+ *  - activations inside the workspace are NHWC; public inputs/outputs keep the reference's
+ *    layouts: images and logits NCHW fp32, masks / labels [N,H,W].
+ */
+#ifndef FSCNN_B200_H
+#define FSCNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSCNN_ABI_VERSION 1
+
+/* error codes */
+#define FSCNN_OK 0
+#define FSCNN_EINVAL (-22)   /* bad argument (shape, dtype, null pointer, alignment) */
+#define FSCNN_ENOENT (-2)    /* a required state_dict tensor / tap name was not found */
+#define FSCNN_ENOMEM (-12)   /* caller-provided buffer too small */
+#define FSCNN_ECUDA (-5)     /* a CUDA runtime call or kernel launch failed */
+#define FSCNN_ESTATE (-1)    /* call order violated (e.g. forward before load_weights) */
+
+/* activation precision of the internal stage tensors */
+#define FSCNN_PREC_FP32 0    /* fp32 storage + fp32 FMA: the exactness path (1e-4 vs reference) */
+#define FSCNN_PREC_BF16 1    /* bf16 storage + bf16 tensor-core contractions, fp32 accumulate */
+
+/* element types of masks / labels */
+#define FSCNN_U8 0
+#define FSCNN_I32 1
+#define FSCNN_I64 2
+
+typedef struct fscnn_ctx fscnn_ctx;
+
+/* One raw state_dict tensor handed to fscnn_load_weights (reference on-disk layout:
+ * train.py:449 torch.save(model.state_dict()); key names as in models/fast_scnn.py). */
+typedef struct fscnn_tensor {
+    const char* name;       /* state_dict key, without any "module." prefix */
+    const float* d_data;    /* fp32, contiguous, device memory */
+    int64_t numel;
+} fscnn_tensor;
+
+/* Shape of one stage-boundary tensor inside the workspace (for parity tests). */
+typedef struct fscnn_tap {
+    size_t offset_bytes;    /* from the start of the workspace */
+    int n, h, w, c;         /* NHWC extents */
+    int c_stride;           /* elements between consecutive pixels (>= c) */
+    int elem_bytes;         /* 4 = fp32, 2 = bf16 */
+} fscnn_tap;
+
+int fscnn_abi_version(void);
+const char* fscnn_last_error(void);
+
+/* Replaces FastSCNN.__init__ (models/fast_scnn.py:16-31): builds the layer plan for
+ * `num_classes` outputs, with or without the aux head.  `precision` is FSCNN_PREC_*. */
+int fscnn_create(fscnn_ctx** out, int num_classes, int aux, int precision);
+void fscnn_destroy(fscnn_ctx* ctx);
+
+/* Manifest of the state_dict tensors the forward path reads:
+ * fscnn_param_count, then name / numel per index.  Lets a host validate a checkpoint. */
+int fscnn_param_count(const fscnn_ctx* ctx);
+const char* fscnn_param_name(const fscnn_ctx* ctx, int index);
+int64_t fscnn_param_numel(const fscnn_ctx* ctx, int index);
+
+/* Bytes of device memory the folded / repacked weights need. */
+int fscnn_packed_weight_bytes(const fscnn_ctx* ctx, size_t* out_bytes);
+
+/* Replaces nn.Module.load_state_dict + the eval-mode BatchNorm of every layer
+ * (models/fast_scnn.py:55-57, 70-75, 86-88, 107-108, 198-203 and 251-255): folds BN
+ * (eps 1e-5) into each convolution and repacks to the kernels' layouts, on the device.
+ * `d_packed` (>= fscnn_packed_weight_bytes, 256-byte aligned) stays owned by the caller and
+ * must outlive the ctx's forward calls.  May be called again after the weights change. */
+int fscnn_load_weights(fscnn_ctx* ctx, const fscnn_tensor* tensors, int n_tensors,
+                       void* d_packed, size_t packed_bytes, void* stream);
+
+/* Bytes of workspace a forward over an [n,3,h,w] batch needs (stage tensors, NHWC). */
+int fscnn_workspace_bytes(const fscnn_ctx* ctx, int n, int h, int w, size_t* out_bytes);
+
+/* Replaces FastSCNN.forward (models/fast_scnn.py:33-46): x is NCHW fp32 [n,3,h,w];
+ * d_logits is NCHW fp32 [n,nc,h,w]; d_aux_logits (same shape) may be NULL (must be non-NULL
+ * to get the aux output when the ctx was created with aux=1). */
+int fscnn_forward_logits(fscnn_ctx* ctx, const float* d_x, int n, int h, int w,
+                         float* d_logits, float* d_aux_logits,
+                         void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces forward + torch.argmax(outputs[0], 1) (eval.py:43-45, demo.py:47-48) without ever
+ * materialising the full-resolution logits.  d_mask is [n,h,w] of mask_dtype (FSCNN_U8 needs
+ * num_classes <= 256; FSCNN_I64 reproduces torch.argmax's dtype). */
+int fscnn_forward_mask(fscnn_ctx* ctx, const float* d_x, int n, int h, int w,
+                       void* d_mask, int mask_dtype,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces forward + argmax + SegmentationMetric.update (eval.py:43-49, utils/metric.py:56-105)
+ * for one batch: ADDS this batch's counts into d_conf, an int64[(nc+1)*(nc+1)+2] accumulator
+ * (rows = label clipped to nc, cols = pred, then `labeled`, `correct`; see fscnn_conf_len).
+ * d_labels is [n,h,w] of label_dtype; d_mask may be NULL. */
+int fscnn_forward_confusion(fscnn_ctx* ctx, const float* d_x, const void* d_labels, int label_dtype,
+                            int n, int h, int w, long long* d_conf,
+                            void* d_mask, int mask_dtype,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Number of int64 elements of a confusion accumulator for `num_classes` classes. */
+int64_t fscnn_conf_len(int num_classes);
+
+/* Replaces batch_pix_accuracy + batch_intersection_union (utils/metric.py:73-105) for class maps
+ * that are already on the device: ADDS into d_conf (layout as above). */
+int fscnn_confusion_from_mask(const void* d_pred, int pred_dtype, const void* d_label, int label_dtype,
+                              int64_t n_pixels, int num_classes, long long* d_conf, void* stream);
+
+/* Host-side finalisation, utils/metric.py:42-54 and :56-63: turns a confusion accumulator (host
+ * copy) into total_inter[nc], total_union[nc], total_correct, total_label. */
+int fscnn_conf_to_totals(const long long* h_conf, int num_classes, long long* h_inter, long long* h_union,
+                         long long* h_correct, long long* h_label);
+
+/* ---- test / profiling hooks ---------------------------------------------------------- */
+
+/* Number of pipeline stages and their names ("stem", "l2d.dsconv1", ... "head"). */
+int fscnn_stage_count(const fscnn_ctx* ctx);
+const char* fscnn_stage_name(const fscnn_ctx* ctx, int stage);
+
+/* Runs stages [first, last] only, reading / writing the stage tensors in the workspace (the
+ * input image is read by stage 0).  Lets a test inject the oracle's tensor before one stage and
+ * check that stage in isolation. */
+int fscnn_forward_range(fscnn_ctx* ctx, const float* d_x, int n, int h, int w, int first_stage, int last_stage,
+                        void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Where the stage-boundary tensor `tap` ("l2d.conv", "l2d.dsconv1", "l2d.dsconv2",
+ * "gfe.bottleneck1.0" ... "gfe.ppm", "ffm", "cls.dsconv1", "cls.logits_lowres",
+ * "aux.logits_lowres") lives in a workspace planned for [n,3,h,w]. */
+int fscnn_tap_info(const fscnn_ctx* ctx, int n, int h, int w, const char* tap, fscnn_tap* out);
+
+/* Kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */
+int64_t fscnn_launch_count(const fscnn_ctx* ctx);
+
+/* Tuning: images pushed through the whole pipeline together (default: chosen from h*w so that a
+ * micro-batch's stage tensors stay L2-resident).  0 restores the default. */
+int fscnn_set_micro_batch(fscnn_ctx* ctx, int images);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSCNN_B200_H */

@@ -1,0 +1,106 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, the drop-in module
+tree reproduces the reference state_dict layout, and host-only entry points behave."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import fastscnn_oracle as fo
+import metric_oracle as mo
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from fscnn_b200 import native
+    header = open(os.path.join(ROOT, 'include', 'fscnn_b200.h')).read()
+    declared = set(re.findall(r'\b(fscnn_[a-z_0-9]+)\s*\(', header))
+    declared -= {'fscnn_ctx', 'fscnn_tensor', 'fscnn_tap'}
+    lib = native.lib()
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), sym
+    assert set(native.EXPORTED_SYMBOLS) == declared
+    assert lib.fscnn_abi_version() == 1
+
+
+@pytest.mark.parametrize('nc,aux', [(19, False), (2, True)])
+def test_state_dict_layout_matches_reference(nc, aux):
+    from models.fast_scnn import FastSCNN
+    model = FastSCNN(nc, aux=aux)
+    spec = fo.state_dict_spec(nc, aux)   # verified against the reference by tests/test_oracle_golden.py fixtures
+    sd = model.state_dict()
+    assert list(sd.keys()) == [name for name, _, _ in spec]
+    for name, shape, _ in spec:
+        assert tuple(sd[name].shape) == tuple(shape), name
+    assert len(sd) == (276 if aux else 268)
+    # attribute paths the reference's callers introspect
+    assert model.classifier.conv[1].out_channels == nc
+    assert model.global_feature_extractor.ppm.conv1.conv[0].in_channels == 128
+    assert callable(model.global_feature_extractor.ppm.pool)
+
+
+def test_native_manifest_matches_state_dict():
+    from fscnn_b200 import native
+    lib = native.lib()
+    for nc, aux in ((19, 0), (3, 1)):
+        ctx = C.c_void_p()
+        native.check(lib.fscnn_create(C.byref(ctx), nc, aux, native.PREC_FP32))
+        names = {lib.fscnn_param_name(ctx, i).decode(): lib.fscnn_param_numel(ctx, i) for i in range(lib.fscnn_param_count(ctx))}
+        spec = {n: int(np.prod(s)) for n, s, k in fo.state_dict_spec(nc, bool(aux)) if k != 'bn_n'}
+        assert names == spec
+        nbytes = C.c_size_t()
+        native.check(lib.fscnn_workspace_bytes(ctx, 1, 1024, 2048, C.byref(nbytes)))
+        assert 100e6 < nbytes.value < 400e6
+        assert lib.fscnn_workspace_bytes(ctx, 1, 2, 2, C.byref(nbytes)) < 0
+        assert b'bad shape' in lib.fscnn_last_error()
+        tap = native.Tap()
+        native.check(lib.fscnn_tap_info(ctx, 1, 1024, 2048, b'l2d.conv', C.byref(tap)))
+        assert (tap.h, tap.w, tap.c) == (511, 1023, 32)
+        native.check(lib.fscnn_tap_info(ctx, 1, 360, 640, b'gfe.ppm', C.byref(tap)))
+        assert (tap.h, tap.w, tap.c) == (12, 20, 128)
+        assert lib.fscnn_tap_info(ctx, 1, 360, 640, b'nope', C.byref(tap)) < 0
+        lib.fscnn_destroy(ctx)
+    assert lib.fscnn_create(C.byref(ctx), 0, 0, 0) < 0
+
+
+def test_checkpoint_variants_load():
+    from models.fast_scnn import FastSCNN, get_fast_scnn
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in fo.make_state_dict(2, False, 3).items()}
+    FastSCNN(2).load_state_dict(sd)
+    FastSCNN(2).load_state_dict({'module.' + k: v for k, v in sd.items()})
+    FastSCNN(2).load_state_dict({'state_dict': sd, 'epoch': 3})
+    FastSCNN(2, num_class=7)                       # unknown kwargs are swallowed like the reference
+    assert get_fast_scnn('tusimple').num_classes == 2 and get_fast_scnn('citys').num_classes == 19
+    with pytest.raises(TypeError):
+        get_fast_scnn('citys', num_classes=3)      # positional clash, same as the reference (Appendix E)
+    with pytest.raises(KeyError):
+        get_fast_scnn('bdd100k', pretrained=True)  # no acronym, same as the reference
+
+
+def test_cpu_or_train_mode_raises():
+    from models.fast_scnn import FastSCNN
+    m = FastSCNN(2).eval()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(NotImplementedError):
+        m.train()(torch.zeros(1, 3, 64, 64))
+
+
+def test_conf_to_totals_host_function():
+    from fscnn_b200 import native
+    rng = np.random.RandomState(0)
+    for nc in (2, 19):
+        pred = rng.randint(-1, nc + 2, size=(3, 40, 50))
+        label = rng.randint(-2, nc + 2, size=(3, 40, 50))
+        conf = mo.confusion_counts(pred, label, nc)
+        inter, union = np.zeros(nc, np.int64), np.zeros(nc, np.int64)
+        correct, labeled = C.c_longlong(), C.c_longlong()
+        ll = C.POINTER(C.c_longlong)
+        native.check(native.lib().fscnn_conf_to_totals(conf.ctypes.data_as(ll), nc, inter.ctypes.data_as(ll),
+                                                       union.ctypes.data_as(ll), C.byref(correct), C.byref(labeled)))
+        o = mo.SegmentationMetricOracle(nc)
+        o.update(pred, label)
+        assert np.array_equal(inter, o.total_inter) and np.array_equal(union, o.total_union)
+        assert (correct.value, labeled.value) == (o.total_correct, o.total_label)
