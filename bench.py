@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- Cityscapes-size (19 classes, 1024x2048) batched evaluation throughput of the B200
+Fast-SCNN forward path: forward + fused upsample/argmax + SegmentationMetric counting.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16] [--batch B]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+    python bench.py --impl reference ...      (the reference's CPU path, timed on the host cores)
+
+One "step" = one pass of the hot path over a batch of B synthetic images per GPU.  Rank 0 prints ONE
+JSON line (see the keys below).  `value` is device-resident throughput (inputs already in HBM);
+`e2e` is the same metric through the public Python API with pinned HOST buffers, host->device
+copies and the device->host read of the metric state inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'fast-scnn-pytorch_b200'))
+
+METRIC, UNIT = 'cityscapes_1024x2048_images_per_sec', 'images/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('FSCNN_BENCH_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+    ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
+    ap.add_argument('--micro-batch', type=int, default=0, help='0 = library default')
+    ap.add_argument('--height', type=int, default=1024)
+    ap.add_argument('--width', type=int, default=2048)
+    ap.add_argument('--classes', type=int, default=19)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-stage-times', action='store_true')
+    ap.add_argument('--latency', action='store_true', help='also report batch-1 latency (CUDA graph replay)')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': float(p['hbm_gbs']), 'bf16_tflops': float(p.get('bf16_tflops_sustained', p['bf16_tflops'])),
+                'sm_max_mhz': float(p.get('sm_max_mhz', 1965.0)), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1400.0, 'sm_max_mhz': 1965.0, 'source': 'fallback'}
+
+
+# ---------------------------------------------------------------------------------------------
+# shapes, algorithmic bytes and flops per stage ("plan-P")
+# ---------------------------------------------------------------------------------------------
+def stage_model(h, w, nc, es):
+    """Per-image algorithmic HBM bytes and flops of every kernel of the plan (each stage tensor
+    written once and read once; activations `es` bytes/element; input image fp32)."""
+    c = lambda n: (n - 1) // 2 + 1
+    h1, w1 = (h - 3) // 2 + 1, (w - 3) // 2 + 1
+    h2, w2 = c(h1), c(w1)
+    h3, w3 = c(h2), c(w2)
+    h4, w4 = c(h3), c(w3)
+    h5, w5 = c(h4), c(w4)
+    st = []
+
+    def add(name, rd, wr, flops):
+        st.append({'stage': name, 'bytes': float(rd + wr), 'flops': float(flops)})
+
+    add('stem', 3 * h * w * 4, h1 * w1 * 32 * es, 2 * h1 * w1 * 32 * 27)
+    add('l2d.dsconv1', h1 * w1 * 32 * es, h2 * w2 * 48 * es, 2 * h2 * w2 * (32 * 9 + 32 * 48))
+    add('l2d.dsconv2', h2 * w2 * 48 * es, h3 * w3 * 64 * es, 2 * h3 * w3 * (48 * 9 + 48 * 64))
+    plan = [('gfe.bottleneck1.0', 64, 64, h3, w3, h4, w4), ('gfe.bottleneck1.1', 64, 64, h4, w4, h4, w4),
+            ('gfe.bottleneck1.2', 64, 64, h4, w4, h4, w4), ('gfe.bottleneck2.0', 64, 96, h4, w4, h5, w5),
+            ('gfe.bottleneck2.1', 96, 96, h5, w5, h5, w5), ('gfe.bottleneck2.2', 96, 96, h5, w5, h5, w5),
+            ('gfe.bottleneck3.0', 96, 128, h5, w5, h5, w5), ('gfe.bottleneck3.1', 128, 128, h5, w5, h5, w5),
+            ('gfe.bottleneck3.2', 128, 128, h5, w5, h5, w5)]
+    for name, ci, co, hi, wi, ho, wo in plan:
+        add(name, hi * wi * ci * es, ho * wo * co * es,
+            2 * (hi * wi * ci * 6 * ci + ho * wo * 6 * ci * 9 + ho * wo * 6 * ci * co))
+    add('gfe.ppm', 2 * h5 * w5 * 128 * es, h5 * w5 * 128 * es, 2 * (h5 * w5 * 128 * 128 + 50 * 128 * 32 + 50 * 32 * 128))
+    add('ffm', h3 * w3 * 64 * es + h5 * w5 * 128 * es, h3 * w3 * 128 * es, 2 * h3 * w3 * (128 * 9 + 192 * 128))
+    add('cls.dsconv1', h3 * w3 * 128 * es, h3 * w3 * 128 * es, 2 * h3 * w3 * (128 * 9 + 128 * 128))
+    add('cls.dsconv2+head', h3 * w3 * 128 * es, h3 * w3 * nc * 4, 2 * h3 * w3 * (128 * 9 + 128 * 128 + 128 * nc))
+    add('up8+argmax+metric', h3 * w3 * nc * 4, h * w * 1, 6 * h * w * nc)
+    return st
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the reference's own path (ATen-functional port + numpy metric oracle) on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_rate(h, w, nc, budget_s, warmup, steps=None):
+    """images/s of forward + argmax + host SegmentationMetric on the CPU, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import numpy as np
+    import torch
+    import fastscnn_oracle as fo
+    import fastscnn_torch_port as tp
+    import metric_oracle as mo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = tp.to_torch_state_dict(fo.make_state_dict(nc, False, 7))
+    rng = np.random.RandomState(0)
+    x = torch.from_numpy(rng.standard_normal((1, 3, h, w)).astype(np.float32))
+    labels = rng.randint(-1, nc, size=(1, h, w)).astype(np.int64)
+    metric = mo.SegmentationMetricOracle(nc)
+    for _ in range(max(1, warmup)):
+        tp.eval_step(sd, x, labels, nc, metric)
+    t0, done = time.perf_counter(), 0
+    while True:
+        tp.eval_step(sd, x, labels, nc, metric)
+        done += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done >= steps) or (steps is None and el >= budget_s and done >= 3):
+            break
+    return done / el, done, el, cores, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    rate, done, el, cores, threads = cpu_reference_rate(args.height, args.width, args.classes, 0.0, args.warmup, args.steps)
+    sample = f'{done} timed single-image steps of {args.height}x{args.width} after {max(1, args.warmup)} warm-up'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
+        'warmup': max(1, args.warmup), 'ms_per_step': 1e3 * el / done, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'cityscapes_eval_nc{args.classes}_{args.height}x{args.width}_fwd_argmax_metric',
+                   'batch_per_step': 1, 'note': 'reference path = ATen-functional port of models/fast_scnn.py + host metric, CPU'},
+        'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
+                         'host_cpus': cores},
+        'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# native arm
+# ---------------------------------------------------------------------------------------------
+def run_native_arm(args):
+    import torch
+    import torch.distributed as dist
+    from models.fast_scnn import FastSCNN
+    from utils.metric import SegmentationMetric
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    h, w, nc, B = args.height, args.width, args.classes, args.batch
+    es = 4 if args.precision == 'fp32' else 2
+
+    torch.manual_seed(1234 + rank)
+    model = FastSCNN(nc, precision=args.precision).eval()
+    with torch.no_grad():   # random-init weights of the architecture, with non-trivial BN statistics
+        for name, buf in model.named_buffers():
+            if name.endswith('running_mean'):
+                buf.normal_(0, 0.1)
+            elif name.endswith('running_var'):
+                buf.uniform_(0.8, 1.2)
+    model.to(dev)
+    x = torch.randn(B, 3, h, w, device=dev)
+    labels = torch.randint(-1, nc, (B, h, w), device=dev, dtype=torch.int64)
+    metric = SegmentationMetric(nc, device=dev)
+    eng = model._engine(dev)
+    if args.micro_batch:
+        eng.set_micro_batch(args.micro_batch)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        model.evaluate(x, labels, metric)
+
+    # ---- device-resident throughput ----
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    if world > 1:
+        metric.all_reduce()            # the path's only collective: one NCCL sum of the confusion state
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API with host buffers ----
+    xh = torch.empty((B, 3, h, w), dtype=torch.float32).pin_memory()
+    xh.copy_(x)
+    lh = torch.empty((B, h, w), dtype=torch.int64).pin_memory()
+    lh.copy_(labels)
+    xd, ld = torch.empty_like(x), torch.empty_like(labels)
+    metric.reset()
+
+    def step_e2e():
+        xd.copy_(xh, non_blocking=True)
+        ld.copy_(lh, non_blocking=True)
+        model.evaluate(xd, ld, metric)
+        return metric.get()            # device -> host read of the metric state (synchronises)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(e2e_steps):
+        step_e2e()
+    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
+    h2d = xh.numel() * 4 + lh.numel() * 8
+    d2h = metric.conf_len() * 8
+
+    out = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(3, args.warmup), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16', 'data': 'synthetic',
+        'config': {'workload': f'cityscapes_eval_nc{nc}_{h}x{w}_fwd_argmax_metric', 'batch_per_gpu': B,
+                   'global_batch': B * world, 'precision': args.precision, 'l2_policy': 'inputs_exceed_l2',
+                   'input_bytes_per_step_per_gpu': int(x.numel() * 4 + labels.numel() * 8),
+                   'parallelism': f'dp{world}', 'weights': 'random-init, randomised BN stats'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps, 'host_buffers': 'pinned fp32 NCHW images + int64 labels'},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+    }
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    stages = stage_model(h, w, nc, es)
+    plan_bytes = sum(s['bytes'] for s in stages)
+    plan_flops = sum(s['flops'] for s in stages)
+    per_img_s = (ms / 1e3) / (B * args.steps)
+    out['pipeline'] = {'plan_bytes_per_image': plan_bytes, 'flops_per_image': plan_flops,
+                       'achieved_gbs': plan_bytes / per_img_s / 1e9, 'hbm_frac': plan_bytes / per_img_s / 1e9 / peaks['hbm_gbs'],
+                       'achieved_tflops': plan_flops / per_img_s / 1e12}
+
+    # ---- per-kernel timing with CUDA events on the launch stream (one micro-batch per launch) ----
+    if not args.no_stage_times:
+        names = eng.stage_names()
+        import ctypes as C
+        from fscnn_b200 import native
+        need = C.c_size_t()
+        native.check(eng.lib.fscnn_workspace_bytes(eng._ctx, B, h, w, C.byref(need)))
+        tap = native.Tap()
+        native.check(eng.lib.fscnn_tap_info(eng._ctx, B, h, w, b'l2d.conv', C.byref(tap)))
+        mb = tap.n                                   # images per launch (the library's micro-batch)
+        xs = x[:mb].contiguous()
+        eng.forward_range(xs, 0, len(names) - 1)     # fill every stage tensor once
+        reps = 5
+        table = []
+        for i, name in enumerate(names):
+            eng.forward_range(xs, i, i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                eng.forward_range(xs, i, i)
+            b.record()
+            torch.cuda.synchronize()
+            table.append((name, a.elapsed_time(b) / reps / mb * 1e3))   # microseconds per image
+        mask = torch.empty((mb, h, w), dtype=torch.uint8, device=dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        full_us = None
+        for timed in (False, True):
+            if timed:
+                a.record()
+            for _ in range(reps):
+                model.evaluate(xs, labels[:mb].contiguous(), metric, mask=None)
+            if timed:
+                b.record()
+        torch.cuda.synchronize()
+        full_us = a.elapsed_time(b) / reps / mb * 1e3
+        tail_us = max(full_us - sum(t for _, t in table), 0.0)
+        table.append(('up8+argmax+metric', tail_us))
+        model_by_name = {s['stage']: s for s in stages}
+        rows = []
+        for name, us in table:
+            m = model_by_name.get(name if name != 'stem' else 'stem')
+            if m is None:
+                continue
+            rows.append({'stage': name, 'us_per_image': us, 'gbs': m['bytes'] / us / 1e3, 'tflops': m['flops'] / us / 1e6,
+                         'bytes': m['bytes'], 'flops': m['flops']})
+        out['stages'] = rows
+        top = max(rows, key=lambda r: r['us_per_image'])
+        hbm_time = top['bytes'] / (peaks['hbm_gbs'] * 1e9)
+        tens_time = top['flops'] / (peaks['bf16_tflops'] * 1e12)
+        if args.precision == 'bf16' and tens_time > hbm_time:
+            roof = {'bound': 'tensor', 'achieved': top['tflops'], 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                    'frac': top['tflops'] / peaks['bf16_tflops']}
+        else:
+            roof = {'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                    'frac': top['gbs'] / peaks['hbm_gbs']}
+        roof.update({'kernel': top['stage'], 'traffic': None, 'peak_source': peaks['source'], 'images_per_launch': mb,
+                     'us_per_launch': top['us_per_image'] * mb,
+                     'note': 'fp32 path: this kernel is FP32-FMA bound on CUDA cores; fma_frac = achieved fp32 TFLOP/s / '
+                             '(148 SM x 128 lanes x 2 x sm_mhz)' if args.precision == 'fp32' else ''})
+        if args.precision == 'fp32':
+            mhz = (clocks or {}).get('sm_mhz') or peaks['sm_max_mhz']
+            roof['fma_frac'] = top['tflops'] / (148 * 128 * 2 * mhz * 1e6 / 1e12)
+        out['roofline'] = roof
+
+    if args.latency:
+        xs1 = x[:1].contiguous()
+        mask1 = torch.empty((1, h, w), dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            model.predict(xs1, out=mask1)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            model.predict(xs1, out=mask1)
+        for _ in range(20):
+            g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(200):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        out['latency_batch1_ms'] = a.elapsed_time(b) / 200
+
+    if world == 1 and not args.no_cpu_baseline:
+        rate, done, el, cores, threads = cpu_reference_rate(h, w, nc, 12.0, 1)
+        out['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host_cpus': cores,
+                               'sample': f'{done} single-image {h}x{w} steps in {el:.1f} s (forward+argmax+host metric), '
+                                         'ATen-functional port of the reference on all host threads'}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_native_arm(args)
+
+
+if __name__ == '__main__':
+    main()

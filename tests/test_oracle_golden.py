@@ -99,3 +99,19 @@ def test_adaptive_pool_bins_overlap():
     out = fo.adaptive_avg_pool(x, 3)
     # rows [0,11) [10,22) [21,32)
     assert np.isclose(out[0, 0, 1, 0], x[0, 0, 10:22, 0:2].mean())
+
+
+@pytest.mark.parametrize('name', ['fwd_nc19_aux_n2_65x97', 'fwd_nc2_n1_360x640'])
+def test_torch_port_matches_reference(name):
+    """The ATen-functional port used as the CPU baseline reproduces the reference's outputs."""
+    import torch
+    import fastscnn_torch_port as tp
+    g, sd, x, nc, aux = load_case(name)
+    outs = tp.forward(tp.to_torch_state_dict(sd), torch.from_numpy(x), aux=aux)
+    logits = outs[0].numpy()
+    if 'logits' in g.files:
+        assert rel_err(logits, g['logits']) < 2e-6
+        assert rel_err(outs[1].numpy()[:, :, ::3, ::5], g['aux_logits_sample']) < 2e-6
+    else:
+        assert rel_err(logits[:, :, ::7, ::11], g['logits_sample']) < 2e-6
+    assert (np.argmax(logits, 1) != g['mask']).mean() < 1e-4
