@@ -91,11 +91,14 @@ struct fscnn_ctx {
         size_t ffm_wd, ffm_bd, ffm_wcat, ffm_bcat;
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
+        size_t bn_we_img[9], bn_wp_img[9];                  // bf16 tcgen05 operand images (offsets still in floats)
     } off{};
     // device pointers resolved by load_weights
     StemW stem{};
     DsW ds[4]{};
     BneckW bn[9]{};
+    const bf16* bn_we_img[9]{};
+    const bf16* bn_wp_img[9]{};
     PpmW ppm{};
     FfmW ffm{};
     HeadW head{};
@@ -200,6 +203,12 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
         f.aux_w = take(576 * 32); f.aux_b = take(32);
         f.auxh_w = take((size_t)32 * c->ncp); f.auxh_b = take(c->ncp);
     }
+    if (c->prec == FSCNN_PREC_BF16)
+        for (int i = 0; i < 9; ++i) {
+            const int ci = kBnecks[i].cin, ce = 6 * ci, co = kBnecks[i].cout;
+            f.bn_we_img[i] = take((size_t)ce * ci / 2);
+            f.bn_wp_img[i] = take((size_t)co * ce / 2);
+        }
     c->packed_floats = o;
 }
 
@@ -233,7 +242,19 @@ struct Loader {
             err = fail(FSCNN_ECUDA, "fold kernel launch failed for '%s': %s", conv.c_str(),
                        cudaGetErrorString(cudaGetLastError()));
     }
+    void fold_umma(const std::string& conv, const std::string& bn, int nrows, int kdim, int nc, int kc, bf16* out) {
+        if (err) return;
+        const float* w = get(conv + ".weight", (int64_t)nrows * kdim);
+        const float* g = get(bn + ".weight", nrows);
+        const float* v = get(bn + ".running_var", nrows);
+        if (err) return;
+        if (launch_fold_umma(w, g, v, nrows, kdim, nc, kc, out, s) != cudaSuccess)
+            err = fail(FSCNN_ECUDA, "umma fold launch failed for '%s': %s", conv.c_str(), cudaGetErrorString(cudaGetLastError()));
+    }
 };
+
+template <typename T>
+cudaError_t bottleneck_dispatch(fscnn_ctx* c, int i, const T* in, T* out, int m, int hi, int wi, int ho, int wo, cudaStream_t s);
 
 template <typename T>
 int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
@@ -253,8 +274,7 @@ int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan&
             const T* in = i == 0 ? at(p.higher) : at(p.b[i - 1]);
             const int hi = i == 0 ? d.h3 : (i <= 3 ? d.h4 : d.h5), wi = i == 0 ? d.w3 : (i <= 3 ? d.w4 : d.w5);
             const int ho = i < 3 ? d.h4 : d.h5, wo = i < 3 ? d.w4 : d.w5;
-            e = launch_bottleneck<T>(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn[i], at(p.b[i]), m, hi, wi,
-                                     ho, wo, s);
+            e = bottleneck_dispatch<T>(c, i, in, at(p.b[i]), m, hi, wi, ho, wo, s);
         } else if (st == kPpm) {
             e = launch_ppm<T>(at(p.b[8]), c->ppm, atf(p.rowsum), atf(p.z), at(p.ppm), m, d.h5, d.w5, s);
             c->launches += 2;
@@ -273,6 +293,18 @@ int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan&
     }
     if (e != cudaSuccess) return fail(FSCNN_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return FSCNN_OK;
+}
+
+template <>
+cudaError_t bottleneck_dispatch<float>(fscnn_ctx* c, int i, const float* in, float* out, int m, int hi, int wi, int ho, int wo,
+                                       cudaStream_t s) {
+    return launch_bottleneck<float>(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn[i], out, m, hi, wi, ho, wo, s);
+}
+template <>
+cudaError_t bottleneck_dispatch<bf16>(fscnn_ctx* c, int i, const bf16* in, bf16* out, int m, int hi, int wi, int ho, int wo,
+                                      cudaStream_t s) {
+    return launch_bottleneck_tc(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn[i], c->bn_we_img[i],
+                                c->bn_wp_img[i], out, m, hi, wi, ho, wo, s);
 }
 
 int dispatch_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
@@ -373,6 +405,14 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         L.fold(p + ".1.conv.0", false, p + ".1.conv.1", ce, 9, 1, 0, P + f.bn_wd[i], ce, P + f.bn_bd[i]);
         L.fold(p + ".2", false, p + ".3", co, ce, 1, 0, P + f.bn_wp[i], co, P + f.bn_bp[i]);
         c->bn[i] = {P + f.bn_we[i], P + f.bn_be[i], P + f.bn_wd[i], P + f.bn_bd[i], P + f.bn_wp[i], P + f.bn_bp[i]};
+        if (c->prec == FSCNN_PREC_BF16) {
+            bf16* we_img = reinterpret_cast<bf16*>(P + f.bn_we_img[i]);
+            bf16* wp_img = reinterpret_cast<bf16*>(P + f.bn_wp_img[i]);
+            L.fold_umma(p + ".0.conv.0", p + ".0.conv.1", ce, ci, 64, ci, we_img);   // expand: chunks of 64 rows
+            L.fold_umma(p + ".2", p + ".3", co, ce, co, 64, wp_img);                 // project: chunks of 64 columns
+            c->bn_we_img[i] = we_img;
+            c->bn_wp_img[i] = wp_img;
+        }
     }
     for (int i = 0; i < 4; ++i) {
         const std::string p = "global_feature_extractor.ppm.conv" + std::to_string(i + 1) + ".conv";

@@ -42,4 +42,28 @@ cudaError_t launch_fold(const float* w, const float* cbias, const float* gamma, 
     return cudaGetLastError();
 }
 
+
+// bf16 B-operand images for tcgen05.mma (umma.cuh): W'[n][k] = W[n][k] * scale[n] cut into chunks of NC rows x KC
+// columns (chunk index = (n/NC)*(K/KC) + k/KC); inside a chunk 8x8 core matrices are ordered [k/8][n/8], i.e. element
+// (n, k) sits at bf16 index ((k/8)*(NC/8) + n/8)*64 + (n%8)*8 + k%8 -- exactly the shared-memory image the kernels
+// bulk-copy (LBO = NC*16 bytes, SBO = 128 bytes).
+__global__ void fold_umma_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ var,
+                                 int nrows, int kdim, int NC, int KC, __nv_bfloat16* __restrict__ out) {
+    const int total = nrows * kdim;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / kdim, k = i % kdim;
+        const float scale = gamma ? gamma[n] / sqrtf(var[n] + 1e-5f) : 1.f;
+        const int chunk = (n / NC) * (kdim / KC) + k / KC;
+        const int nl = n % NC, kl = k % KC;
+        const size_t o = (size_t)chunk * NC * KC + ((size_t)(kl >> 3) * (NC >> 3) + (nl >> 3)) * 64 + (nl & 7) * 8 + (kl & 7);
+        out[o] = __float2bfloat16_rn(w[i] * scale);
+    }
+}
+
+cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* var, int nrows, int kdim, int nc, int kc,
+                             bf16* out, cudaStream_t s) {
+    fold_umma_kernel<<<ceil_div(nrows * kdim, 256), 256, 0, s>>>(w, gamma, var, nrows, kdim, nc, kc, out);
+    return cudaGetLastError();
+}
+
 }  // namespace fscnn

@@ -63,4 +63,12 @@ cudaError_t launch_fold(const float* w, const float* cbias, const float* gamma, 
                         const float* var, int cout, int kdim, int taps, int tap_major, float* out_w, int ld_out,
                         float* out_b, int accumulate_bias, cudaStream_t s);
 
+
+// bf16 tensor-core (tcgen05 / TMEM) variants ------------------------------------------------------------
+cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* var, int nrows, int kdim, int nc, int kc,
+                             bf16* out, cudaStream_t s);
+// we_img: expand weights [6cin x cin] in chunks of 64 rows; wp_img: project weights [cout x 6cin] in chunks of 64 columns
+cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const BneckW& w, const bf16* we_img,
+                                 const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
+
 }  // namespace fscnn

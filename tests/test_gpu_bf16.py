@@ -1,0 +1,94 @@
+"""bf16 fast path (bf16 stage tensors, tcgen05 tensor-core contractions with fp32 accumulation)
+against the reference fixtures.  Stated tolerance: every stage fed with the reference's input within
+1.5e-2 of the output's absmax; end-to-end logits within 4e-2 of absmax; at most 3 % of mask pixels
+differ.  For scale: the reference's own bf16 autocast disagrees with its fp32 run by 3-4e-2 of absmax
+and on 1.1-4.6 % of pixels."""
+import numpy as np
+import pytest
+import torch
+
+import fastscnn_oracle as fo
+import metric_oracle as mo
+from helpers import build_model, load_case, rel_err
+from test_gpu_parity import STAGE_IO, nhwc
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda', 0)
+STAGE_TOL, LOGIT_TOL, MASK_TOL = 1.5e-2, 4e-2, 3e-2
+
+
+@pytest.mark.parametrize('case', ['fwd_nc19_aux_n2_65x97', 'fwd_nc3_aux_n3_64x40'])
+def test_bf16_each_stage_in_isolation(case):
+    g, sd, x, nc, aux = load_case(case)
+    model = build_model(sd, nc, aux, DEV, precision='bf16')
+    xd = torch.from_numpy(x).to(DEV)
+    eng = model._engine(DEV)
+    n, _, h, w = x.shape
+    names = eng.stage_names()
+    failures = []
+    for stage, ins, out in STAGE_IO:
+        idx = names.index(stage)
+        for tap in ins or []:
+            v = eng.tap_view(tap, n, h, w)
+            v.copy_(nhwc(g['tap/' + tap]).to(DEV).to(v.dtype))
+        eng.forward_range(xd, idx, idx)
+        got = eng.tap_view(out, n, h, w).permute(0, 3, 1, 2).float().cpu().numpy()
+        err = rel_err(got, g['tap/' + out])
+        if not err < STAGE_TOL:
+            failures.append((stage, err))
+    assert not failures, failures
+
+
+@pytest.mark.parametrize('case', ['fwd_nc19_aux_n2_65x97', 'fwd_nc2_n1_360x640', 'fwd_nc19_n1_256x512'])
+def test_bf16_forward_and_mask(case):
+    g, sd, x, nc, aux = load_case(case)
+    model = build_model(sd, nc, aux, DEV, precision='bf16')
+    xd = torch.from_numpy(x).to(DEV)
+    logits = model(xd)[0].cpu().numpy()
+    scale = float(g['logits_absmax'])
+    if 'logits' in g.files:
+        assert np.abs(logits - g['logits']).max() / scale < LOGIT_TOL
+    else:
+        assert np.abs(logits[:, :, ::7, ::11] - g['logits_sample']).max() / scale < LOGIT_TOL
+    mask = model.predict(xd).cpu().numpy()
+    assert (mask != g['mask']).mean() < MASK_TOL
+    assert np.array_equal(mask, np.argmax(logits, 1))      # fused argmax == argmax of the path's own logits
+
+
+def test_bf16_full_size_and_metric():
+    """1x3x1024x2048, 19 classes: mask agreement with the fp32 oracle and exact metric counting."""
+    from utils.metric import SegmentationMetric
+    nc, h, w = 19, 1024, 2048
+    sd = fo.make_state_dict(nc, False, 7)
+    x = fo.make_input(1, h, w, 31)
+    sd = fo.calibrate_classifier_bias(sd, x)
+    low = fo.forward(sd, x, full_res=False)[0]
+    ref_mask = fo.upsample_argmax(low, h, w)
+    labels = fo.make_labels(1, h, w, nc, seed=3)
+    model = build_model(sd, nc, False, DEV, precision='bf16')
+    xd = torch.from_numpy(x).to(DEV)
+    metric = SegmentationMetric(nc)
+    mask = torch.empty((1, h, w), dtype=torch.uint8, device=DEV)
+    model.evaluate(xd, torch.from_numpy(labels).to(DEV), metric, mask=mask)
+    mask = mask.cpu().numpy()
+    assert (mask != ref_mask).mean() < MASK_TOL
+    got_low = model._engine(DEV).tap_view('cls.logits_lowres', 1, h, w).permute(0, 3, 1, 2).cpu().numpy()
+    assert rel_err(got_low, low) < LOGIT_TOL
+    assert np.array_equal(metric.device_confusion().cpu().numpy(), mo.confusion_counts(mask, labels, nc))
+    o = mo.SegmentationMetricOracle(nc)
+    o.update(mask.astype(np.int64), labels)
+    assert metric.get() == o.get()
+
+
+def test_bf16_batch_invariance():
+    nc = 2
+    sd = fo.make_state_dict(nc, False, 5)
+    x = fo.make_input(5, 120, 168, 6)
+    model = build_model(sd, nc, False, DEV, precision='bf16')
+    xd = torch.from_numpy(x).to(DEV)
+    full = model.predict(xd)
+    eng = model._engine(DEV)
+    eng.set_micro_batch(2)
+    assert torch.equal(model.predict(xd), full)
+    eng.set_micro_batch(0)
+    assert torch.equal(model.predict(xd[3:4].contiguous()), full[3:4])
