@@ -92,6 +92,7 @@ struct fscnn_ctx {
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
         size_t bn_we_img[9], bn_wp_img[9];                  // bf16 tcgen05 operand images (offsets still in floats)
+        size_t ds_wp_img[4], head_img, ffm_img;
     } off{};
     // device pointers resolved by load_weights
     StemW stem{};
@@ -99,6 +100,9 @@ struct fscnn_ctx {
     BneckW bn[9]{};
     const bf16* bn_we_img[9]{};
     const bf16* bn_wp_img[9]{};
+    const bf16* ds_wp_img[4]{};
+    const bf16* head_img = nullptr;
+    const bf16* ffm_img = nullptr;
     PpmW ppm{};
     FfmW ffm{};
     HeadW head{};
@@ -209,6 +213,11 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
             f.bn_we_img[i] = take((size_t)ce * ci / 2);
             f.bn_wp_img[i] = take((size_t)co * ce / 2);
         }
+    if (c->prec == FSCNN_PREC_BF16) {
+        for (int i = 0; i < 4; ++i) f.ds_wp_img[i] = take((size_t)dss[i].cin * dss[i].cout / 2);
+        f.head_img = take((size_t)((c->nc + 15) & ~15) * 128 / 2);
+        f.ffm_img = take((size_t)128 * 192 / 2);
+    }
     c->packed_floats = o;
 }
 
@@ -245,8 +254,8 @@ struct Loader {
     void fold_umma(const std::string& conv, const std::string& bn, int nrows, int kdim, int nc, int kc, bf16* out) {
         if (err) return;
         const float* w = get(conv + ".weight", (int64_t)nrows * kdim);
-        const float* g = get(bn + ".weight", nrows);
-        const float* v = get(bn + ".running_var", nrows);
+        const float* g = bn.empty() ? nullptr : get(bn + ".weight", nrows);
+        const float* v = bn.empty() ? nullptr : get(bn + ".running_var", nrows);
         if (err) return;
         if (launch_fold_umma(w, g, v, nrows, kdim, nc, kc, out, s) != cudaSuccess)
             err = fail(FSCNN_ECUDA, "umma fold launch failed for '%s': %s", conv.c_str(), cudaGetErrorString(cudaGetLastError()));
@@ -255,6 +264,13 @@ struct Loader {
 
 template <typename T>
 cudaError_t bottleneck_dispatch(fscnn_ctx* c, int i, const T* in, T* out, int m, int hi, int wi, int ho, int wo, cudaStream_t s);
+
+template <typename T>
+cudaError_t dsconv_dispatch(fscnn_ctx* c, int i, int cin, int cout, int stride, const T* in, T* out, bool head, float* logits,
+                            int m, int hi, int wi, int ho, int wo, cudaStream_t s);
+
+template <typename T>
+cudaError_t ffm_dispatch(fscnn_ctx* c, const T* higher, const T* lower, T* out, int m, int hh, int wh, int hl, int wl, cudaStream_t s);
 
 template <typename T>
 int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
@@ -266,9 +282,9 @@ int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan&
         if (st == kStem) {
             e = launch_stem<T>(x, c->stem, at(p.stem), m, d.h, d.w, d.h1, d.w1, s);
         } else if (st == kDs1) {
-            e = launch_dsconv<T>(32, 48, 2, at(p.stem), c->ds[0], at(p.ds1), nullptr, nullptr, m, d.h1, d.w1, d.h2, d.w2, s);
+            e = dsconv_dispatch<T>(c, 0, 32, 48, 2, at(p.stem), at(p.ds1), false, nullptr, m, d.h1, d.w1, d.h2, d.w2, s);
         } else if (st == kDs2) {
-            e = launch_dsconv<T>(48, 64, 2, at(p.ds1), c->ds[1], at(p.higher), nullptr, nullptr, m, d.h2, d.w2, d.h3, d.w3, s);
+            e = dsconv_dispatch<T>(c, 1, 48, 64, 2, at(p.ds1), at(p.higher), false, nullptr, m, d.h2, d.w2, d.h3, d.w3, s);
         } else if (st >= kB0 && st < kB0 + 9) {
             const int i = st - kB0;
             const T* in = i == 0 ? at(p.higher) : at(p.b[i - 1]);
@@ -279,12 +295,11 @@ int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan&
             e = launch_ppm<T>(at(p.b[8]), c->ppm, atf(p.rowsum), atf(p.z), at(p.ppm), m, d.h5, d.w5, s);
             c->launches += 2;
         } else if (st == kFfm) {
-            e = launch_ffm<T>(at(p.higher), at(p.ppm), c->ffm, at(p.ffm), m, d.h3, d.w3, d.h5, d.w5, s);
+            e = ffm_dispatch<T>(c, at(p.higher), at(p.ppm), at(p.ffm), m, d.h3, d.w3, d.h5, d.w5, s);
         } else if (st == kCls1) {
-            e = launch_dsconv<T>(128, 128, 1, at(p.ffm), c->ds[2], at(p.cls1), nullptr, nullptr, m, d.h3, d.w3, d.h3, d.w3, s);
+            e = dsconv_dispatch<T>(c, 2, 128, 128, 1, at(p.ffm), at(p.cls1), false, nullptr, m, d.h3, d.w3, d.h3, d.w3, s);
         } else if (st == kCls2Head) {
-            e = launch_dsconv<T>(128, 128, 1, at(p.cls1), c->ds[3], nullptr, &c->head, atf(p.logits), m, d.h3, d.w3, d.h3,
-                                 d.w3, s);
+            e = dsconv_dispatch<T>(c, 3, 128, 128, 1, at(p.cls1), nullptr, true, atf(p.logits), m, d.h3, d.w3, d.h3, d.w3, s);
         } else if (st == kAux) {
             if (!c->aux) continue;
             e = launch_aux<T>(at(p.higher), c->auxw, atf(p.aux_logits), m, d.h3, d.w3, s);
@@ -305,6 +320,29 @@ cudaError_t bottleneck_dispatch<bf16>(fscnn_ctx* c, int i, const bf16* in, bf16*
                                       cudaStream_t s) {
     return launch_bottleneck_tc(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn[i], c->bn_we_img[i],
                                 c->bn_wp_img[i], out, m, hi, wi, ho, wo, s);
+}
+
+template <>
+cudaError_t dsconv_dispatch<float>(fscnn_ctx* c, int i, int cin, int cout, int stride, const float* in, float* out, bool head,
+                                   float* logits, int m, int hi, int wi, int ho, int wo, cudaStream_t s) {
+    return launch_dsconv<float>(cin, cout, stride, in, c->ds[i], out, head ? &c->head : nullptr, logits, m, hi, wi, ho, wo, s);
+}
+template <>
+cudaError_t dsconv_dispatch<bf16>(fscnn_ctx* c, int i, int cin, int cout, int stride, const bf16* in, bf16* out, bool head,
+                                  float* logits, int m, int hi, int wi, int ho, int wo, cudaStream_t s) {
+    return launch_dsconv_tc(cin, cout, stride, in, c->ds[i], c->ds_wp_img[i], out, head ? &c->head : nullptr, c->head_img, logits,
+                            m, hi, wi, ho, wo, s);
+}
+
+template <>
+cudaError_t ffm_dispatch<float>(fscnn_ctx* c, const float* higher, const float* lower, float* out, int m, int hh, int wh, int hl,
+                                int wl, cudaStream_t s) {
+    return launch_ffm<float>(higher, lower, c->ffm, out, m, hh, wh, hl, wl, s);
+}
+template <>
+cudaError_t ffm_dispatch<bf16>(fscnn_ctx* c, const bf16* higher, const bf16* lower, bf16* out, int m, int hh, int wh, int hl,
+                               int wl, cudaStream_t s) {
+    return launch_ffm_tc(higher, lower, c->ffm, c->ffm_img, out, m, hh, wh, hl, wl, s);
 }
 
 int dispatch_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
@@ -397,6 +435,11 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         L.fold(p + ".conv.0", false, p + ".conv.1", dss[i].cin, 9, 1, 0, P + f.ds_wd[i], dss[i].cin, P + f.ds_bd[i]);
         L.fold(p + ".conv.3", false, p + ".conv.4", dss[i].cout, dss[i].cin, 1, 0, P + f.ds_wp[i], dss[i].cout, P + f.ds_bp[i]);
         c->ds[i] = {P + f.ds_wd[i], P + f.ds_bd[i], P + f.ds_wp[i], P + f.ds_bp[i]};
+        if (c->prec == FSCNN_PREC_BF16) {
+            bf16* img = reinterpret_cast<bf16*>(P + f.ds_wp_img[i]);
+            L.fold_umma(p + ".conv.3", p + ".conv.4", dss[i].cout, dss[i].cin, dss[i].cout, dss[i].cin, img);
+            c->ds_wp_img[i] = img;
+        }
     }
     for (int i = 0; i < 9; ++i) {
         const std::string p = std::string("global_feature_extractor.") + kBnecks[i].name + ".block";
@@ -431,8 +474,19 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
     L.fold("feature_fusion.conv_lower_res.0", true, "feature_fusion.conv_lower_res.1", 128, 128, 1, 0,
            P + f.ffm_wcat + (size_t)64 * 128, 128, P + f.ffm_bcat, 1);
     c->ffm = {P + f.ffm_wd, P + f.ffm_bd, P + f.ffm_wcat, P + f.ffm_bcat};
+    if (c->prec == FSCNN_PREC_BF16) {   // [128 x 192] image, k-block major: columns 0..63 = higher, 64..191 = lower
+        bf16* img = reinterpret_cast<bf16*>(P + f.ffm_img);
+        L.fold_umma("feature_fusion.conv_higher_res.0", "feature_fusion.conv_higher_res.1", 128, 64, 128, 64, img);
+        L.fold_umma("feature_fusion.conv_lower_res.0", "feature_fusion.conv_lower_res.1", 128, 128, 128, 128, img + 128 * 64);
+        c->ffm_img = img;
+    }
     L.fold("classifier.conv.1", true, "", c->nc, 128, 1, 0, P + f.head_w, c->ncp, P + f.head_b);
     c->head = {P + f.head_w, P + f.head_b, c->nc, c->ncp};
+    if (c->prec == FSCNN_PREC_BF16) {
+        bf16* img = reinterpret_cast<bf16*>(P + f.head_img);
+        L.fold_umma("classifier.conv.1", "", c->nc, 128, (c->nc + 15) & ~15, 128, img);   // rows >= nc stay zero
+        c->head_img = img;
+    }
     if (c->aux) {
         L.fold("auxlayer.0", false, "auxlayer.1", 32, 576, 9, 1, P + f.aux_w, 32, P + f.aux_b);
         L.fold("auxlayer.4", true, "", c->nc, 32, 1, 0, P + f.auxh_w, c->ncp, P + f.auxh_b);

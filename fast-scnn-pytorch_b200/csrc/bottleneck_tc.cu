@@ -44,25 +44,6 @@ struct TcCfg {
     static_assert(CEXP % CE == 0 && CIN % 16 == 0 && COUT % 16 == 0, "shape");
 };
 
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-}
-
 template <int CIN, int COUT, int STRIDE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restrict__ we_img, const bf16* __restrict__ wp_img,
@@ -101,7 +82,7 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
         const bool ok = (m < C::PIN && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi);
         const bf16* src = ok ? in + (((size_t)n * Hi + iy) * Wi + ix) * CIN + k8 * 8 : in;
         const uint32_t dst = sX + (m >> 7) * C::XT_BYTES + ((k8 * 16 + ((m & 127) >> 3)) << 7) + ((m & 7) << 4);
-        cp_async16_zfill(dst, src, ok);
+        cp_async16z(dst, src, ok);
     }
     cp_async_wait_all();
     fence_async_proxy();
@@ -160,7 +141,7 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
                             const int c = c0 + g * 8 + 2 * h;
                             const float a = ok ? relu(__uint_as_float(r[g * 8 + 2 * h]) + Bes[c]) : 0.f;
                             const float b = ok ? relu(__uint_as_float(r[g * 8 + 2 * h + 1]) + Bes[c + 1]) : 0.f;
-                            pk[h] = pack_bf16(a, b);
+                            pk[h] = packbf(a, b);
                         }
                         const uint32_t dst = sE + pin * (CE * 2) + ((((c0 >> 3) + g) ^ (pin & 7)) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
@@ -197,7 +178,7 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
                     const uint32_t src = sE + pin * (CE * 2) + ((j ^ (pin & 7)) << 4);
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
                     float f[8];
-                    unpack8(v, f);
+                    unpackbf8(v, f);
 #pragma unroll
                     for (int o = 0; o < 4; ++o) {
                         const int ky = r - o * STRIDE;
@@ -212,8 +193,8 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
             for (int o = 0; o < 4; ++o) {
                 const int p = (4 * rg + o) * 16 + x;
                 const uint32_t dst = sD + ((j * 16 + (p >> 3)) << 7) + ((p & 7) << 4);
-                const uint32_t p0 = pack_bf16(relu(acc[o][0]), relu(acc[o][1])), p1 = pack_bf16(relu(acc[o][2]), relu(acc[o][3]));
-                const uint32_t p2 = pack_bf16(relu(acc[o][4]), relu(acc[o][5])), p3 = pack_bf16(relu(acc[o][6]), relu(acc[o][7]));
+                const uint32_t p0 = packbf(relu(acc[o][0]), relu(acc[o][1])), p1 = packbf(relu(acc[o][2]), relu(acc[o][3]));
+                const uint32_t p2 = packbf(relu(acc[o][4]), relu(acc[o][5])), p3 = packbf(relu(acc[o][6]), relu(acc[o][7]));
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
             }
         }
@@ -260,12 +241,12 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
                         const uint32_t src = sX + (m >> 7) * C::XT_BYTES + (((co >> 3) * 16 + ((m & 127) >> 3)) << 7) + ((m & 7) << 4);
                         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xv.x), "=r"(xv.y), "=r"(xv.z), "=r"(xv.w) : "r"(src));
                         float f[8];
-                        unpack8(xv, f);
+                        unpackbf8(xv, f);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] += f[i];
                     }
                     uint4 o;
-                    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+                    o.x = packbf(v[0], v[1]); o.y = packbf(v[2], v[3]); o.z = packbf(v[4], v[5]); o.w = packbf(v[6], v[7]);
                     *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * COUT + co) = o;
                 }
             }

@@ -32,6 +32,26 @@ __device__ __forceinline__ long long load_label(const void* p, int dtype, size_t
     return __ldg(reinterpret_cast<const long long*>(p) + i);
 }
 
+// four consecutive labels starting at element i (vector loads when the row pitch keeps them aligned)
+__device__ __forceinline__ void load_labels4(const void* p, int dtype, size_t i, bool aligned, int remaining, long long (&out)[4]) {
+    if (aligned) {
+        if (dtype == FSCNN_U8) {
+            const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(reinterpret_cast<const unsigned char*>(p) + i));
+            out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        } else if (dtype == FSCNN_I32) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(p) + i));
+            out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+        } else {
+            const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(p) + i));
+            const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(reinterpret_cast<const long long*>(p) + i) + 1);
+            out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = j < remaining ? load_label(p, dtype, i + j) : -1;
+    }
+}
+
 // Adds one (label, pred) observation to the confusion accumulator held in `hist` (shared, uint32) or,
 // when hist == nullptr, directly to the global int64 accumulator.
 struct ConfSink {
@@ -47,7 +67,7 @@ struct ConfSink {
 
 // MODE 0: write NCHW fp32 logits.  MODE 1: argmax mask (+ optional confusion counts).
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restrict__ out_logits, void* __restrict__ mask,
                 int mask_dtype, const void* __restrict__ labels, int label_dtype, unsigned long long* __restrict__ conf,
                 int hl, int wl, int H, int W, int use_smem_hist) {
@@ -65,12 +85,20 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     const int cb = min((int)(scx * (float)xb), wl - 1);
     const bool do_hist = (MODE == 1) && (labels != nullptr);
 
-    for (int i = tid; i < kTR * kTC * ncp; i += kThreads) {
-        const int c = i % ncp, px = i / ncp;
-        const int r = px / kTC, q = px % kTC;
-        if (c < nc) {
+    // stage the low-res tile class-major: one float4 (4 classes of one pixel) per item, independent loads in flight
+    {
+        const int nv = ncp >> 2;
+        for (int i = tid; i < kTR * kTC * nv; i += kThreads) {
+            const int v = i % nv, px = i / nv;
+            const int r = px / kTC, q = px % kTC;
             const int rr = min(rb + r, hl - 1), qq = min(cb + q, wl - 1);
-            Ls[(c * kTR + r) * kTC + q] = __ldg(low + (((size_t)n * hl + rr) * wl + qq) * ncp + c);
+            const float4 t = __ldg(reinterpret_cast<const float4*>(low + (((size_t)n * hl + rr) * wl + qq) * ncp) + v);
+            const int c = 4 * v;
+            float* dst = Ls + (c * kTR + r) * kTC + q;
+            dst[0] = t.x;
+            if (c + 1 < nc) dst[kTR * kTC] = t.y;
+            if (c + 2 < nc) dst[2 * kTR * kTC] = t.z;
+            if (c + 3 < nc) dst[3 * kTR * kTC] = t.w;
         }
     }
     if (do_hist) {
@@ -218,10 +246,12 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (y0 + i >= H) break;
+            long long labs[4];
+            load_labels4(labels, label_dtype, ((size_t)n * H + (y0 + i)) * W + x0, (W & 3) == 0, W - x0, labs);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (x0 + j >= W) break;
-                const long long lab = load_label(labels, label_dtype, ((size_t)n * H + (y0 + i)) * W + x0 + j);
+                const long long lab = labs[j];
                 if (lab < 0) continue;                      // metric.py:79/:96 -- label+1 > 0 marks a labeled pixel
                 const int row = lab < nc ? (int)lab : nc;   // labels >= nclass: overflow row
                 const int col = bidx[i][j];

@@ -71,4 +71,13 @@ cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* va
 cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const BneckW& w, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 
+// wp_img: pointwise weights [cout x cin] as one chunk; wh_img (head != nullptr): head weights [round_up(nc,16) x cout]
+cudaError_t launch_dsconv_tc(int cin, int cout, int stride, const bf16* in, const DsW& w, const bf16* wp_img, bf16* out,
+                             const HeadW* head, const bf16* wh_img, float* logits, int n, int hi, int wi, int ho, int wo,
+                             cudaStream_t s);
+
+// wcat_img: the stacked [128 x 192] weight (64 higher | 128 lower input channels) as one chunk
+cudaError_t launch_ffm_tc(const bf16* higher, const bf16* lower, const FfmW& w, const bf16* wcat_img, bf16* out, int n, int hh,
+                          int wh, int hl, int wl, cudaStream_t s);
+
 }  // namespace fscnn

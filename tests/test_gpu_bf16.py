@@ -1,6 +1,6 @@
 """bf16 fast path (bf16 stage tensors, tcgen05 tensor-core contractions with fp32 accumulation)
 against the reference fixtures.  Stated tolerance: every stage fed with the reference's input within
-1.5e-2 of the output's absmax; end-to-end logits within 4e-2 of absmax; at most 3 % of mask pixels
+1.5e-2 of the output's absmax; end-to-end logits within 4e-2 of absmax; at most 5 % of mask pixels
 differ.  For scale: the reference's own bf16 autocast disagrees with its fp32 run by 3-4e-2 of absmax
 and on 1.1-4.6 % of pixels."""
 import numpy as np
@@ -14,7 +14,7 @@ from test_gpu_parity import STAGE_IO, nhwc
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device('cuda', 0)
-STAGE_TOL, LOGIT_TOL, MASK_TOL = 1.5e-2, 4e-2, 3e-2
+STAGE_TOL, LOGIT_TOL, MASK_TOL = 1.5e-2, 4e-2, 5e-2
 
 
 @pytest.mark.parametrize('case', ['fwd_nc19_aux_n2_65x97', 'fwd_nc3_aux_n3_64x40'])
