@@ -4,7 +4,8 @@
 // 1x1 contractions run as tcgen05.mma (bf16 operands from shared memory, fp32 accumulators in
 // TMEM), the depthwise stage runs on the CUDA cores in fp32 between them.
 //
-// CTA = 8x16 output pixels (M = 128 rows of the project MMA), 256 threads.
+// CTA = 8x16 output pixels (M = 128 rows of the project MMA), 512 threads (16 warps keep the LDS / TMEM
+// latencies of the CUDA-core phases covered while one elected thread feeds the tensor core).
 //   X  : input halo tile, bf16, as NMT MMA A-tiles of 128 rows (core-matrix layout [k/8][row/8])
 //   per chunk of CE = 64 expanded channels:
 //     We/Wp chunk  <- one bulk copy each (weights are pre-packed in the shared-memory image)
@@ -17,6 +18,8 @@
 #include "umma.cuh"
 
 namespace fscnn {
+
+constexpr int kNT = 512;   // threads per CTA of this kernel
 
 template <int CIN, int COUT, int STRIDE>
 struct TcCfg {
@@ -31,12 +34,13 @@ struct TcCfg {
     static constexpr int oX = 0;
     static constexpr int oE = oX + NMT * XT_BYTES;
     static constexpr int oD = oE + PINP * CE * 2;
-    static constexpr int oWe = oD + P * CE * 2;
-    static constexpr int oWp = oWe + CE * CIN * 2;
-    static constexpr int oWd = oWp + COUT * CE * 2;
-    static constexpr int oBe = oWd + 9 * CE * 4;
-    static constexpr int oBd = oBe + CE * 4;
-    static constexpr int oValid = oBd + CE * 4;
+    static constexpr int WE_BYTES = CE * CIN * 2, WP_BYTES = COUT * CE * 2;
+    static constexpr int oWe = oD + P * CE * 2;            // 2 buffers
+    static constexpr int oWp = oWe + 2 * WE_BYTES;         // 2 buffers
+    static constexpr int oWd = oWp + 2 * WP_BYTES;         // fp32 tables of ALL chunks: Wd[9][CEXP], Be[CEXP], Bd[CEXP]
+    static constexpr int oBe = oWd + 9 * CEXP * 4;
+    static constexpr int oBd = oBe + CEXP * 4;
+    static constexpr int oValid = oBd + CEXP * 4;
     static constexpr int smem_bytes = oValid + ROWS;
     static constexpr int TM_EXP = 0, TM_PROJ = NMT * CE;
     static constexpr int TM_COLS = (NMT * CE + COUT) <= 256 ? 256 : 512;
@@ -45,17 +49,17 @@ struct TcCfg {
 };
 
 template <int CIN, int COUT, int STRIDE, bool RES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kNT, 1)
 bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restrict__ we_img, const bf16* __restrict__ wp_img,
                      bf16* __restrict__ out, int Hi, int Wi, int Ho, int Wo) {
     using C = TcCfg<CIN, COUT, STRIDE>;
     constexpr int CE = C::CE, IW = C::IW, NMT = C::NMT;
     extern __shared__ __align__(128) uint8_t sm[];
-    __shared__ __align__(8) uint64_t bar_w, bar_exp, bar_proj;
+    __shared__ __align__(8) uint64_t bar_we[2], bar_wp[2], bar_exp, bar_proj;
     __shared__ uint32_t tmem_base_s;
-    float* Wds = reinterpret_cast<float*>(sm + C::oWd);
-    float* Bes = reinterpret_cast<float*>(sm + C::oBe);
-    float* Bds = reinterpret_cast<float*>(sm + C::oBd);
+    const float* Wd_all = reinterpret_cast<const float*>(sm + C::oWd);
+    const float* Be_all = reinterpret_cast<const float*>(sm + C::oBe);
+    const float* Bd_all = reinterpret_cast<const float*>(sm + C::oBd);
     uint8_t* valid = sm + C::oValid;
     const uint32_t sX = smem_u32(sm + C::oX), sE = smem_u32(sm + C::oE), sD = smem_u32(sm + C::oD);
     const uint32_t sWe = smem_u32(sm + C::oWe), sWp = smem_u32(sm + C::oWp);
@@ -65,18 +69,47 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
     const int oy0 = blockIdx.y * C::TH, ox0 = blockIdx.x * C::TW;
     const int iy0 = oy0 * STRIDE - 1, ix0 = ox0 * STRIDE - 1;
 
+    // weight chunk e lives in buffer e & 1; the bulk copies run one to two chunks ahead of their MMAs
+    auto prefetch_we = [&](int e) {
+        mbar_arrive_expect_tx(&bar_we[e & 1], C::WE_BYTES);
+        bulk_g2s(sm + C::oWe + (e & 1) * C::WE_BYTES, we_img + (size_t)e * CE * CIN, C::WE_BYTES, &bar_we[e & 1]);
+    };
+    auto prefetch_wp = [&](int e) {
+        mbar_arrive_expect_tx(&bar_wp[e & 1], C::WP_BYTES);
+        bulk_g2s(sm + C::oWp + (e & 1) * C::WP_BYTES, wp_img + (size_t)e * COUT * CE, C::WP_BYTES, &bar_wp[e & 1]);
+    };
+    constexpr uint32_t idesc_exp = make_idesc_bf16(128, CE);
+    constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT);
+    auto issue_expand = [&](int e, uint32_t tmem) {
+        mbar_wait(&bar_we[e & 1], (e >> 1) & 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int mt = 0; mt < NMT; ++mt)
+#pragma unroll
+            for (int k16 = 0; k16 < CIN / 16; ++k16) {
+                const uint64_t da = make_smem_desc(sX + mt * C::XT_BYTES + k16 * 2 * 2048, 2048, 128);
+                const uint64_t db = make_smem_desc(sWe + (e & 1) * C::WE_BYTES + k16 * 2 * (CE * 16), CE * 16, 128);
+                umma_bf16_ss(tmem + C::TM_EXP + mt * CE, da, db, idesc_exp, k16 > 0);
+            }
+        umma_commit(&bar_exp);
+    };
+
     if (tid == 0) {
-        mbar_init(&bar_w, 1); mbar_init(&bar_exp, 1); mbar_init(&bar_proj, 1);
+        mbar_init(&bar_we[0], 1); mbar_init(&bar_we[1], 1); mbar_init(&bar_wp[0], 1); mbar_init(&bar_wp[1], 1);
+        mbar_init(&bar_exp, 1); mbar_init(&bar_proj, 1);
         fence_mbar_init();
+        prefetch_we(0);
+        if (C::NCH > 1) prefetch_we(1);
+        prefetch_wp(0);
     }
     if (warp == 0) { tmem_alloc(&tmem_base_s, C::TM_COLS); tmem_relinquish(); }
 
     // ---- stage the input halo tile as MMA A-tiles (lanes along rows -> conflict-free 16-byte stores) ----
-    for (int m = tid; m < C::ROWS; m += kThreads) {
+    for (int m = tid; m < C::ROWS; m += kNT) {
         const int iy = iy0 + m / IW, ix = ix0 + m % IW;
         valid[m] = (m < C::PIN && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) ? 1 : 0;
     }
-    for (int i = tid; i < C::ROWS * (CIN / 8); i += kThreads) {
+    for (int i = tid; i < C::ROWS * (CIN / 8); i += kNT) {
         const int m = i % C::ROWS, k8 = i / C::ROWS;
         const int iy = iy0 + m / IW, ix = ix0 + m % IW;
         const bool ok = (m < C::PIN && iy >= 0 && iy < Hi && ix >= 0 && ix < Wi);
@@ -84,129 +117,113 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
         const uint32_t dst = sX + (m >> 7) * C::XT_BYTES + ((k8 * 16 + ((m & 127) >> 3)) << 7) + ((m & 7) << 4);
         cp_async16z(dst, src, ok);
     }
+    {   // fp32 depthwise weights and the two bias vectors of every chunk, once
+        float* wd_s = reinterpret_cast<float*>(sm + C::oWd);
+        float* be_s = reinterpret_cast<float*>(sm + C::oBe);
+        float* bd_s = reinterpret_cast<float*>(sm + C::oBd);
+        for (int i = tid; i < 9 * C::CEXP / 4; i += kNT) reinterpret_cast<float4*>(wd_s)[i] = __ldg(reinterpret_cast<const float4*>(w.wd) + i);
+        for (int i = tid; i < C::CEXP / 4; i += kNT) {
+            reinterpret_cast<float4*>(be_s)[i] = __ldg(reinterpret_cast<const float4*>(w.be) + i);
+            reinterpret_cast<float4*>(bd_s)[i] = __ldg(reinterpret_cast<const float4*>(w.bd) + i);
+        }
+    }
     cp_async_wait_all();
     fence_async_proxy();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
-
-    constexpr uint32_t idesc_exp = make_idesc_bf16(128, CE);
-    constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT);
+    if (tid == 0) issue_expand(0, tmem);
 
 #pragma unroll 1
     for (int e = 0; e < C::NCH; ++e) {
-        // ---- (1) weights of this chunk: two bulk copies, small fp32 tables by plain loads ----
-        if (tid == 0) {
-            if (e > 0) mbar_wait(&bar_proj, (e - 1) & 1);   // previous project MMA has finished reading Wp / D
-            mbar_arrive_expect_tx(&bar_w, CE * CIN * 2 + COUT * CE * 2);
-            bulk_g2s(sm + C::oWe, we_img + (size_t)e * CE * CIN, CE * CIN * 2, &bar_w);
-            bulk_g2s(sm + C::oWp, wp_img + (size_t)e * COUT * CE, COUT * CE * 2, &bar_w);
-        }
-        for (int i = tid; i < 9 * CE; i += kThreads) Wds[i] = __ldg(w.wd + (i / CE) * C::CEXP + e * CE + (i % CE));
-        if (tid < CE) { Bes[tid] = __ldg(w.be + e * CE + tid); Bds[tid] = __ldg(w.bd + e * CE + tid); }
-        // ---- (2) expand MMAs ----
-        if (tid == 0) {
-            mbar_wait(&bar_w, e & 1);
-            tc_fence_after_sync();
-#pragma unroll
-            for (int mt = 0; mt < NMT; ++mt)
-#pragma unroll
-                for (int k16 = 0; k16 < CIN / 16; ++k16) {
-                    const uint64_t da = make_smem_desc(sX + mt * C::XT_BYTES + k16 * 2 * 2048, 2048, 128);
-                    const uint64_t db = make_smem_desc(sWe + k16 * 2 * (CE * 16), CE * 16, 128);
-                    umma_bf16_ss(tmem + C::TM_EXP + mt * CE, da, db, idesc_exp, k16 > 0);
-                }
-            umma_commit(&bar_exp);
-        }
-        __syncthreads();   // Wds / Bes / Bds visible
+        const float* Bes = Be_all + e * CE;
+        const float* Bds = Bd_all + e * CE;
+        const float* Wds = Wd_all + e * CE;      // tap t at Wds[t * CEXP + c]
         // ---- (3) expand epilogue: TMEM -> bias, ReLU, image mask -> bf16 rows of E ----
         mbar_wait(&bar_exp, e & 1);
         tc_fence_after_sync();
-        for (int task = warp; task < NMT * 4; task += kThreads / 32) {
-            const int mt = task >> 2, q = task & 3;
+        for (int task = warp; task < NMT * 8; task += kNT / 32) {   // task = (M-tile, 32-column half, lane quarter)
+            const int q = task & 3, ch = (task >> 2) & 1, mt = task >> 3;
             const int pin = mt * 128 + q * 32 + lane;
             const bool ok = valid[pin];
+            const int c0 = ch * 32;
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + C::TM_EXP + mt * CE + c0, r);
+            tmem_ld_wait();
+            if (pin < C::PINP) {
 #pragma unroll
-            for (int c0 = 0; c0 < CE; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + C::TM_EXP + mt * CE + c0, r);
-                tmem_ld_wait();
-                if (pin < C::PINP) {
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const int c = c0 + g * 8 + 2 * h;
-                            const float a = ok ? relu(__uint_as_float(r[g * 8 + 2 * h]) + Bes[c]) : 0.f;
-                            const float b = ok ? relu(__uint_as_float(r[g * 8 + 2 * h + 1]) + Bes[c + 1]) : 0.f;
-                            pk[h] = packbf(a, b);
-                        }
-                        const uint32_t dst = sE + pin * (CE * 2) + ((((c0 >> 3) + g) ^ (pin & 7)) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    for (int h = 0; h < 4; ++h) {
+                        const int c = c0 + g * 8 + 2 * h;
+                        const float a = ok ? relu(__uint_as_float(r[g * 8 + 2 * h]) + Bes[c]) : 0.f;
+                        const float b = ok ? relu(__uint_as_float(r[g * 8 + 2 * h + 1]) + Bes[c + 1]) : 0.f;
+                        pk[h] = packbf(a, b);
                     }
+                    sts128(sE + pin * (CE * 2) + ((((c0 >> 3) + g) ^ (pin & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }
             }
         }
         tc_fence_before_sync();
         __syncthreads();
-        // ---- (4) depthwise 3x3 in fp32: thread = (column x, 4-row group rg, 8-channel chunk j) ----
+        // ---- the tensor core runs ahead: expand MMAs of the NEXT chunk overlap this chunk's depthwise phase ----
+        if (tid == 0) {
+            tc_fence_after_sync();
+            if (e + 1 < C::NCH) issue_expand(e + 1, tmem);
+            if (e + 2 < C::NCH) prefetch_we(e + 2);          // buffer e&1: expand(e) has completed (bar_exp waited above)
+        }
+        if (e > 0) mbar_wait(&bar_proj, (e - 1) & 1);        // project(e-1) done: D and Wp buffer (e+1)&1 are free
+        if (tid == 0 && e + 1 < C::NCH) prefetch_wp(e + 1);
+        // ---- (4) depthwise 3x3 in fp32: thread = (column x, 2-row group rg, 8-channel chunk j) ----
         {
-            const int x = tid & 15, rg = (tid >> 4) & 1, j = tid >> 5;
-            float wk[9][8];
+            const int x = tid & 15, rg = (tid >> 4) & 3, j = tid >> 6;
+            float acc[2][8];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float4 a = *reinterpret_cast<const float4*>(Wds + t * CE + j * 8);
-                const float4 b = *reinterpret_cast<const float4*>(Wds + t * CE + j * 8 + 4);
-                wk[t][0] = a.x; wk[t][1] = a.y; wk[t][2] = a.z; wk[t][3] = a.w;
-                wk[t][4] = b.x; wk[t][5] = b.y; wk[t][6] = b.z; wk[t][7] = b.w;
-            }
-            float acc[4][8];
-#pragma unroll
-            for (int o = 0; o < 4; ++o)
+            for (int o = 0; o < 2; ++o)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[o][c] = Bds[j * 8 + c];
-            constexpr int NR = 3 * STRIDE + 3;   // input rows feeding 4 output rows
+            constexpr int NR = STRIDE + 3;   // input rows feeding 2 output rows
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
-                const int iy = (4 * rg) * STRIDE + r;
+                const int iy = (2 * rg) * STRIDE + r;
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int pin = iy * IW + x * STRIDE + kx;
-                    uint4 v;
-                    const uint32_t src = sE + pin * (CE * 2) + ((j ^ (pin & 7)) << 4);
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
                     float f[8];
-                    unpackbf8(v, f);
+                    unpackbf8(lds128(sE + pin * (CE * 2) + ((j ^ (pin & 7)) << 4)), f);
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) {
+                    for (int o = 0; o < 2; ++o) {
                         const int ky = r - o * STRIDE;
                         if (ky >= 0 && ky < 3) {
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(f[c], wk[ky * 3 + kx][c], acc[o][c]);
+                            const float4 wa = *reinterpret_cast<const float4*>(Wds + (ky * 3 + kx) * C::CEXP + j * 8);
+                            const float4 wb = *reinterpret_cast<const float4*>(Wds + (ky * 3 + kx) * C::CEXP + j * 8 + 4);
+                            acc[o][0] = fmaf(f[0], wa.x, acc[o][0]); acc[o][1] = fmaf(f[1], wa.y, acc[o][1]);
+                            acc[o][2] = fmaf(f[2], wa.z, acc[o][2]); acc[o][3] = fmaf(f[3], wa.w, acc[o][3]);
+                            acc[o][4] = fmaf(f[4], wb.x, acc[o][4]); acc[o][5] = fmaf(f[5], wb.y, acc[o][5]);
+                            acc[o][6] = fmaf(f[6], wb.z, acc[o][6]); acc[o][7] = fmaf(f[7], wb.w, acc[o][7]);
                         }
                     }
                 }
             }
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const int p = (4 * rg + o) * 16 + x;
-                const uint32_t dst = sD + ((j * 16 + (p >> 3)) << 7) + ((p & 7) << 4);
-                const uint32_t p0 = packbf(relu(acc[o][0]), relu(acc[o][1])), p1 = packbf(relu(acc[o][2]), relu(acc[o][3]));
-                const uint32_t p2 = packbf(relu(acc[o][4]), relu(acc[o][5])), p3 = packbf(relu(acc[o][6]), relu(acc[o][7]));
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+            for (int o = 0; o < 2; ++o) {
+                const int p = (2 * rg + o) * 16 + x;
+                sts128(sD + a_tile_off(p, j), packbf(relu(acc[o][0]), relu(acc[o][1])), packbf(relu(acc[o][2]), relu(acc[o][3])),
+                       packbf(relu(acc[o][4]), relu(acc[o][5])), packbf(relu(acc[o][6]), relu(acc[o][7])));
             }
         }
         fence_async_proxy();
         __syncthreads();
         // ---- (5) project MMAs, accumulated across chunks ----
         if (tid == 0) {
+            mbar_wait(&bar_wp[e & 1], (e >> 1) & 1);
             tc_fence_after_sync();
 #pragma unroll
             for (int k16 = 0; k16 < CE / 16; ++k16) {
                 const uint64_t da = make_smem_desc(sD + k16 * 2 * 2048, 2048, 128);
-                const uint64_t db = make_smem_desc(sWp + k16 * 2 * (COUT * 16), COUT * 16, 128);
+                const uint64_t db = make_smem_desc(sWp + (e & 1) * C::WP_BYTES + k16 * 2 * (COUT * 16), COUT * 16, 128);
                 umma_bf16_ss(tmem + C::TM_PROJ, da, db, idesc_proj, (e | k16) != 0);
             }
             umma_commit(&bar_proj);
@@ -217,38 +234,32 @@ bottleneck_tc_kernel(const bf16* __restrict__ in, BneckW w, const bf16* __restri
     mbar_wait(&bar_proj, (C::NCH - 1) & 1);
     tc_fence_after_sync();
     {
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;   // 16 warps = 4 lane quarters x 4 column parts
         const int p = q * 32 + lane;
         const int py = p >> 4, px = p & 15;
         const int oy = oy0 + py, ox = ox0 + px;
         const bool live = (oy < Ho) && (ox < Wo);
-        constexpr int CH = COUT / 2;   // columns per warp-half (32, 48 or 64)
+        constexpr int CP = COUT / 4;   // columns per part: 16, 24 or 32
+        uint32_t r[CP];
 #pragma unroll
-        for (int c0 = 0; c0 < CH; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(tmem + ((uint32_t)(q * 32) << 16) + C::TM_PROJ + half * CH + c0, r);
-            tmem_ld_wait();
-            if (live) {
+        for (int c0 = 0; c0 < CP; c0 += 8) tmem_ld_32x32b_x8(tmem + ((uint32_t)(q * 32) << 16) + C::TM_PROJ + part * CP + c0, r + c0);
+        tmem_ld_wait();
+        if (live) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    const int co = half * CH + c0 + g * 8;
-                    float v[8];
+            for (int c0 = 0; c0 < CP; c0 += 8) {
+                const int co = part * CP + c0;
+                float v[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) + __ldg(w.bp + co + i);
-                    if (RES) {   // stride 1: centre of the halo tile, still resident in X
-                        const int m = (py + 1) * IW + (px + 1);
-                        uint4 xv;
-                        const uint32_t src = sX + (m >> 7) * C::XT_BYTES + (((co >> 3) * 16 + ((m & 127) >> 3)) << 7) + ((m & 7) << 4);
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(xv.x), "=r"(xv.y), "=r"(xv.z), "=r"(xv.w) : "r"(src));
-                        float f[8];
-                        unpackbf8(xv, f);
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[c0 + i]) + __ldg(w.bp + co + i);
+                if (RES) {   // stride 1: centre of the halo tile, still resident in X
+                    const int m = (py + 1) * IW + (px + 1);
+                    float f[8];
+                    unpackbf8(lds128(sX + (m >> 7) * C::XT_BYTES + a_tile_off(m & 127, co >> 3)), f);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] += f[i];
-                    }
-                    uint4 o;
-                    o.x = packbf(v[0], v[1]); o.y = packbf(v[2], v[3]); o.z = packbf(v[4], v[5]); o.w = packbf(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * COUT + co) = o;
+                    for (int i = 0; i < 8; ++i) v[i] += f[i];
                 }
+                *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * COUT + co) =
+                    make_uint4(packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
             }
         }
     }
@@ -265,7 +276,7 @@ static cudaError_t run_tc(const bf16* in, const BneckW& w, const bf16* we_img, c
     cudaError_t e = ensure_dyn_smem(bottleneck_tc_kernel<CIN, COUT, STRIDE, RES>, C::smem_bytes, configured);
     if (e != cudaSuccess) return e;
     dim3 grid(ceil_div(wo, C::TW), ceil_div(ho, C::TH), n);
-    bottleneck_tc_kernel<CIN, COUT, STRIDE, RES><<<grid, kThreads, C::smem_bytes, s>>>(in, w, we_img, wp_img, out, hi, wi, ho, wo);
+    bottleneck_tc_kernel<CIN, COUT, STRIDE, RES><<<grid, kNT, C::smem_bytes, s>>>(in, w, we_img, wp_img, out, hi, wi, ho, wo);
     return cudaGetLastError();
 }
 

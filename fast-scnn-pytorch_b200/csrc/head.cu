@@ -58,6 +58,10 @@ struct ConfSink {
     unsigned int* hist;
     unsigned long long* conf;
     int nc;
+    __device__ __forceinline__ void add_key(int bin, unsigned int count) const {
+        if (hist) atomicAdd(hist + bin, count);
+        else atomicAdd(conf + bin, (unsigned long long)count);
+    }
     __device__ __forceinline__ void add(int row, int col, unsigned int count) const {
         const int bin = row * (nc + 1) + col;
         if (hist) atomicAdd(hist + bin, count);
@@ -112,28 +116,27 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     if (x0 >= W || y0 >= H) {
         if (!do_hist) return;
     }
-    // horizontal taps of the 4 columns, relative to the staged tile
-    float lx[4], hx[4];
-    int dx[4];
+    // Separable interpolation weights, class-invariant: column j mixes the three staged columns c0..c0+2 with
+    // (hx, lx, 0) or (0, hx, lx); row i mixes the three staged rows likewise.  A zero weight adds an exact 0, so for
+    // finite logits each pixel is fma(lx, b, hx*a) of its own two taps -- horizontal first, then vertical, like ATen.
+    float wx[4][3], wy[8][3];
     const int c0 = min((int)(scx * (float)x0), wl - 1);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float fx = scx * (float)(x0 + j);
         const int q = min((int)fx, wl - 1);
-        dx[j] = q - c0;
-        lx[j] = fx - (float)q;
-        hx[j] = 1.f - lx[j];
+        const float lx = fx - (float)q, hx = 1.f - lx;
+        const bool s = (q - c0) != 0;
+        wx[j][0] = s ? 0.f : hx; wx[j][1] = s ? hx : lx; wx[j][2] = s ? lx : 0.f;
     }
-    float ly[8], hy[8];
-    int dy[8];
     const int r0 = min((int)(scy * (float)y0), hl - 1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float fy = scy * (float)(y0 + i);
         const int r = min((int)fy, hl - 1);
-        dy[i] = r - r0;
-        ly[i] = fy - (float)r;
-        hy[i] = 1.f - ly[i];
+        const float ly = fy - (float)r, hy = 1.f - ly;
+        const bool s = (r - r0) != 0;
+        wy[i][0] = s ? 0.f : hy; wy[i][1] = s ? hy : ly; wy[i][2] = s ? ly : 0.f;
     }
     // tile-relative offsets of the 3 rows / 3 columns (clamped at the image border like ATen's x1 = x0 + (x0 < w-1))
     int ro[3], co[3];
@@ -151,32 +154,28 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
         for (int j = 0; j < 4; ++j) { best[i][j] = 0.f; bidx[i][j] = 0; }
 
     const bool live = (x0 < W) && (y0 < H);
+    if (live && do_hist) {   // pull this thread's label rows towards L1 while the class loop runs
+        const size_t esz = label_dtype == FSCNN_U8 ? 1 : (label_dtype == FSCNN_I32 ? 4 : 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (y0 + i < H)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(labels) + (((size_t)n * H + (y0 + i)) * W + x0) * esz));
+    }
     if (live) {
         for (int c = 0; c < nc; ++c) {
             const float* lc = Ls + c * kTR * kTC;
-            float v[3][3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) v[r][q] = lc[ro[r] + co[q]];
             float hrow[3][4];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r) {
+                const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float a = dx[j] ? v[r][1] : v[r][0];
-                    const float b = dx[j] ? v[r][2] : v[r][1];
-                    hrow[r][j] = hx[j] * a + lx[j] * b;
-                }
+                for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v2, fmaf(wx[j][1], v1, wx[j][0] * v0));
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float val[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float t = dy[i] ? hrow[1][j] : hrow[0][j];
-                    const float b = dy[i] ? hrow[2][j] : hrow[1][j];
-                    val[j] = hy[i] * t + ly[i] * b;
-                }
+                for (int j = 0; j < 4; ++j) val[j] = fmaf(wy[i][2], hrow[2][j], fmaf(wy[i][1], hrow[1][j], wy[i][0] * hrow[0][j]));
                 if (MODE == 0) {
                     if (y0 + i < H) {
                         float* o = out_logits + (((size_t)n * nc + c) * H + (y0 + i)) * W + x0;
@@ -201,36 +200,41 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     }
     if (MODE == 0) return;
 
-    // ---- write the mask ----
+    // ---- write the mask (no early exits: every loop unrolls and bidx stays in registers) ----
     if (live && mask) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (y0 + i >= H) break;
-            const size_t off = ((size_t)n * H + (y0 + i)) * W + x0;
-            if (mask_dtype == FSCNN_U8) {
-                unsigned char* m = reinterpret_cast<unsigned char*>(mask) + off;
-                if ((W & 3) == 0) {
-                    *reinterpret_cast<uchar4*>(m) = make_uchar4((unsigned char)bidx[i][0], (unsigned char)bidx[i][1],
-                                                                (unsigned char)bidx[i][2], (unsigned char)bidx[i][3]);
+            if (y0 + i < H) {
+                const size_t off = ((size_t)n * H + (y0 + i)) * W + x0;
+                if (mask_dtype == FSCNN_U8) {
+                    unsigned char* m = reinterpret_cast<unsigned char*>(mask) + off;
+                    if ((W & 3) == 0) {
+                        *reinterpret_cast<uchar4*>(m) = make_uchar4((unsigned char)bidx[i][0], (unsigned char)bidx[i][1],
+                                                                    (unsigned char)bidx[i][2], (unsigned char)bidx[i][3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (x0 + j < W) m[j] = (unsigned char)bidx[i][j];
+                    }
+                } else if (mask_dtype == FSCNN_I32) {
+                    int* m = reinterpret_cast<int*>(mask) + off;
+                    if ((W & 3) == 0) {
+                        *reinterpret_cast<int4*>(m) = make_int4(bidx[i][0], bidx[i][1], bidx[i][2], bidx[i][3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (x0 + j < W) m[j] = bidx[i][j];
+                    }
                 } else {
+                    long long* m = reinterpret_cast<long long*>(mask) + off;
+                    if ((W & 3) == 0) {
+                        *reinterpret_cast<longlong2*>(m) = make_longlong2(bidx[i][0], bidx[i][1]);
+                        *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(bidx[i][2], bidx[i][3]);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (x0 + j < W) m[j] = (unsigned char)bidx[i][j];
-                }
-            } else if (mask_dtype == FSCNN_I32) {
-                int* m = reinterpret_cast<int*>(mask) + off;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x0 + j < W) m[j] = bidx[i][j];
-            } else {
-                long long* m = reinterpret_cast<long long*>(mask) + off;
-                if ((W & 1) == 0) {
-                    *reinterpret_cast<longlong2*>(m) = make_longlong2(bidx[i][0], bidx[i][1]);
-                    *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(bidx[i][2], bidx[i][3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (x0 + j < W) m[j] = bidx[i][j];
+                        for (int j = 0; j < 4; ++j)
+                            if (x0 + j < W) m[j] = bidx[i][j];
+                    }
                 }
             }
         }
@@ -241,28 +245,37 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     const ConfSink sink{use_smem_hist ? hist : nullptr, conf, nc};
     unsigned int labeled = 0, correct = 0;
     if (live) {
-        int run_row = -1, run_col = 0;
+        // all label rows first (independent loads in flight), reduced to a row code: -1 = unlabeled, nc = label >= nclass
+        int code[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            long long labs[4] = {-1, -1, -1, -1};
+            if (y0 + i < H) load_labels4(labels, label_dtype, ((size_t)n * H + (y0 + i)) * W + x0, (W & 3) == 0, W - x0, labs);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) code[i][j] = labs[j] < 0 ? -1 : (labs[j] < nc ? (int)labs[j] : nc);
+        }
+        int run_key = -1;
         unsigned int run = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (y0 + i >= H) break;
-            long long labs[4];
-            load_labels4(labels, label_dtype, ((size_t)n * H + (y0 + i)) * W + x0, (W & 3) == 0, W - x0, labs);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (x0 + j >= W) break;
-                const long long lab = labs[j];
-                if (lab < 0) continue;                      // metric.py:79/:96 -- label+1 > 0 marks a labeled pixel
-                const int row = lab < nc ? (int)lab : nc;   // labels >= nclass: overflow row
-                const int col = bidx[i][j];
-                labeled += 1;
-                correct += (lab == (long long)col);
-                if (row == run_row && col == run_col) { run += 1; continue; }
-                if (run) sink.add(run_row, run_col, run);
-                run_row = row; run_col = col; run = 1;
+                const int row = code[i][j];
+                if (row >= 0) {                              // metric.py:79/:96 -- label+1 > 0 marks a labeled pixel
+                    const int col = bidx[i][j];
+                    const int key = row * (nc + 1) + col;
+                    labeled += 1;
+                    correct += (row == col);
+                    if (key == run_key) {
+                        run += 1;
+                    } else {
+                        if (run) sink.add_key(run_key, run);
+                        run_key = key; run = 1;
+                    }
+                }
             }
         }
-        if (run) sink.add(run_row, run_col, run);
+        if (run) sink.add_key(run_key, run);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
