@@ -82,6 +82,7 @@ struct fscnn_ctx {
     bool loaded = false;
     int64_t launches = 0;
     int micro_batch = 0;
+    StemIn in{FSCNN_IN_F32_NCHW, {0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
     // offsets (floats) into the packed buffer, fixed at create time
     struct Off {
         size_t stem_w, stem_b;
@@ -92,7 +93,7 @@ struct fscnn_ctx {
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
         size_t bn_we_img[9], bn_wp_img[9];                  // bf16 tcgen05 operand images (offsets still in floats)
-        size_t ds_wp_img[4], head_img, ffm_img;
+        size_t ds_wp_img[4], head_img, ffm_img, stem_img;
     } off{};
     // device pointers resolved by load_weights
     StemW stem{};
@@ -103,6 +104,7 @@ struct fscnn_ctx {
     const bf16* ds_wp_img[4]{};
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
+    const bf16* stem_img = nullptr;
     PpmW ppm{};
     FfmW ffm{};
     HeadW head{};
@@ -217,6 +219,7 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
         for (int i = 0; i < 4; ++i) f.ds_wp_img[i] = take((size_t)dss[i].cin * dss[i].cout / 2);
         f.head_img = take((size_t)((c->nc + 15) & ~15) * 128 / 2);
         f.ffm_img = take((size_t)128 * 192 / 2);
+        f.stem_img = take((size_t)32 * 32 / 2);
     }
     c->packed_floats = o;
 }
@@ -273,14 +276,17 @@ template <typename T>
 cudaError_t ffm_dispatch(fscnn_ctx* c, const T* higher, const T* lower, T* out, int m, int hh, int wh, int hl, int wl, cudaStream_t s);
 
 template <typename T>
-int run_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
+cudaError_t stem_dispatch(fscnn_ctx* c, const void* x, T* out, int m, const Dims& d, cudaStream_t s);
+
+template <typename T>
+int run_stages(fscnn_ctx* c, const void* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
                cudaStream_t s) {
     cudaError_t e = cudaSuccess;
     auto at = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
     auto atf = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
     for (int st = first; st <= last && e == cudaSuccess; ++st) {
         if (st == kStem) {
-            e = launch_stem<T>(x, c->stem, at(p.stem), m, d.h, d.w, d.h1, d.w1, s);
+            e = stem_dispatch<T>(c, x, at(p.stem), m, d, s);
         } else if (st == kDs1) {
             e = dsconv_dispatch<T>(c, 0, 32, 48, 2, at(p.stem), at(p.ds1), false, nullptr, m, d.h1, d.w1, d.h2, d.w2, s);
         } else if (st == kDs2) {
@@ -345,7 +351,16 @@ cudaError_t ffm_dispatch<bf16>(fscnn_ctx* c, const bf16* higher, const bf16* low
     return launch_ffm_tc(higher, lower, c->ffm, c->ffm_img, out, m, hh, wh, hl, wl, s);
 }
 
-int dispatch_stages(fscnn_ctx* c, const float* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
+template <>
+cudaError_t stem_dispatch<float>(fscnn_ctx* c, const void* x, float* out, int m, const Dims& d, cudaStream_t s) {
+    return launch_stem<float>(x, c->in, c->stem, out, m, d.h, d.w, d.h1, d.w1, s);
+}
+template <>
+cudaError_t stem_dispatch<bf16>(fscnn_ctx* c, const void* x, bf16* out, int m, const Dims& d, cudaStream_t s) {
+    return launch_stem_tc(x, c->in, c->stem_img, c->stem.b, out, m, d.h, d.w, d.h1, d.w1, s);
+}
+
+int dispatch_stages(fscnn_ctx* c, const void* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
                     cudaStream_t s) {
     return c->prec == FSCNN_PREC_BF16 ? run_stages<bf16>(c, x, m, d, p, ws, first, last, s)
                                       : run_stages<float>(c, x, m, d, p, ws, first, last, s);
@@ -426,6 +441,11 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
     L.fold("learning_to_downsample.conv.conv.0", false, "learning_to_downsample.conv.conv.1", 32, 27, 1, 0, P + f.stem_w, 32,
            P + f.stem_b);
     c->stem = {P + f.stem_w, P + f.stem_b};
+    if (c->prec == FSCNN_PREC_BF16) {   // [32 x 27] padded to K = 32 (columns 27..31 stay zero)
+        bf16* img = reinterpret_cast<bf16*>(P + f.stem_img);
+        L.fold_umma("learning_to_downsample.conv.conv.0", "learning_to_downsample.conv.conv.1", 32, 27, 32, 32, img);
+        c->stem_img = img;
+    }
     const struct { const char* p; int cin, cout; } dss[4] = {{"learning_to_downsample.dsconv1", 32, 48},
                                                               {"learning_to_downsample.dsconv2", 48, 64},
                                                               {"classifier.dsconv1", 128, 128},
@@ -505,6 +525,19 @@ int fscnn_workspace_bytes(const fscnn_ctx* c, int n, int h, int w, size_t* out_b
     return FSCNN_OK;
 }
 
+int fscnn_set_input_format(fscnn_ctx* c, int format, const float* mean3, const float* std3) {
+    if (!c) return fail(FSCNN_EINVAL, "null context");
+    if (format != FSCNN_IN_F32_NCHW && format != FSCNN_IN_U8_NHWC) return fail(FSCNN_EINVAL, "unknown input format %d", format);
+    c->in.format = format;
+    for (int i = 0; i < 3; ++i) {
+        c->in.mean[i] = mean3 ? mean3[i] : 0.f;
+        const float sd = std3 ? std3[i] : 1.f;
+        if (!(sd > 0.f)) return fail(FSCNN_EINVAL, "std[%d] must be positive", i);
+        c->in.inv_std[i] = 1.f / sd;
+    }
+    return FSCNN_OK;
+}
+
 int fscnn_set_micro_batch(fscnn_ctx* c, int images) {
     if (!c || images < 0) return fail(FSCNN_EINVAL, "bad argument");
     c->micro_batch = images;
@@ -543,7 +576,7 @@ int fscnn_tap_info(const fscnn_ctx* c, int n, int h, int w, const char* tap, fsc
     return fail(FSCNN_ENOENT, "unknown tap '%s'", tap);
 }
 
-int fscnn_forward_range(fscnn_ctx* c, const float* d_x, int n, int h, int w, int first, int last, void* ws, size_t ws_bytes,
+int fscnn_forward_range(fscnn_ctx* c, const void* d_x, int n, int h, int w, int first, int last, void* ws, size_t ws_bytes,
                         void* stream) {
     Dims d; int mb; WsPlan p;
     int rc = check_forward_args(c, d_x, n, h, w, ws, ws_bytes, &d, &mb, &p);
@@ -553,7 +586,7 @@ int fscnn_forward_range(fscnn_ctx* c, const float* d_x, int n, int h, int w, int
     return dispatch_stages(c, d_x, n, d, p, (char*)ws, first, last, (cudaStream_t)stream);
 }
 
-int fscnn_forward_logits(fscnn_ctx* c, const float* d_x, int n, int h, int w, float* d_logits, float* d_aux, void* ws,
+int fscnn_forward_logits(fscnn_ctx* c, const void* d_x, int n, int h, int w, float* d_logits, float* d_aux, void* ws,
                          size_t ws_bytes, void* stream) {
     Dims d; int mb; WsPlan p;
     int rc = check_forward_args(c, d_x, n, h, w, ws, ws_bytes, &d, &mb, &p);
@@ -561,11 +594,11 @@ int fscnn_forward_logits(fscnn_ctx* c, const float* d_x, int n, int h, int w, fl
     if (!d_logits) return fail(FSCNN_EINVAL, "null logits pointer");
     if (((uintptr_t)d_logits & 15) || ((uintptr_t)d_aux & 15)) return fail(FSCNN_EINVAL, "logits must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t img = (size_t)3 * h * w, lg = (size_t)c->nc * h * w;
+    const size_t img = (size_t)3 * h * w * (c->in.format == FSCNN_IN_U8_NHWC ? 1 : 4), lg = (size_t)c->nc * h * w;
     const bool want_aux = c->aux && d_aux;
     for (int i0 = 0; i0 < n; i0 += mb) {
         const int m = n - i0 < mb ? n - i0 : mb;
-        rc = dispatch_stages(c, d_x + i0 * img, m, d, p, (char*)ws, kStem, want_aux ? kAux : kCls2Head, s);
+        rc = dispatch_stages(c, (const char*)d_x + i0 * img, m, d, p, (char*)ws, kStem, want_aux ? kAux : kCls2Head, s);
         if (rc) return rc;
         cudaError_t e = launch_up_logits(reinterpret_cast<float*>((char*)ws + p.logits), c->nc, c->ncp, d_logits + i0 * lg, m,
                                          d.h3, d.w3, h, w, s);
@@ -580,7 +613,7 @@ int fscnn_forward_logits(fscnn_ctx* c, const float* d_x, int n, int h, int w, fl
     return FSCNN_OK;
 }
 
-static int forward_mask_impl(fscnn_ctx* c, const float* d_x, const void* d_labels, int label_dtype, int n, int h, int w,
+static int forward_mask_impl(fscnn_ctx* c, const void* d_x, const void* d_labels, int label_dtype, int n, int h, int w,
                              long long* d_conf, void* d_mask, int mask_dtype, void* ws, size_t ws_bytes, void* stream) {
     Dims d; int mb; WsPlan p;
     int rc = check_forward_args(c, d_x, n, h, w, ws, ws_bytes, &d, &mb, &p);
@@ -592,10 +625,10 @@ static int forward_mask_impl(fscnn_ctx* c, const float* d_x, const void* d_label
     const size_t msz = mask_dtype == FSCNN_U8 ? 1 : (mask_dtype == FSCNN_I32 ? 4 : 8);
     const size_t lsz = label_dtype == FSCNN_U8 ? 1 : (label_dtype == FSCNN_I32 ? 4 : 8);
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t img = (size_t)3 * h * w, px = (size_t)h * w;
+    const size_t img = (size_t)3 * h * w * (c->in.format == FSCNN_IN_U8_NHWC ? 1 : 4), px = (size_t)h * w;
     for (int i0 = 0; i0 < n; i0 += mb) {
         const int m = n - i0 < mb ? n - i0 : mb;
-        rc = dispatch_stages(c, d_x + i0 * img, m, d, p, (char*)ws, kStem, kCls2Head, s);
+        rc = dispatch_stages(c, (const char*)d_x + i0 * img, m, d, p, (char*)ws, kStem, kCls2Head, s);
         if (rc) return rc;
         cudaError_t e = launch_up_argmax(reinterpret_cast<float*>((char*)ws + p.logits), c->nc, c->ncp,
                                          d_mask ? (char*)d_mask + i0 * px * msz : nullptr, mask_dtype,
@@ -607,13 +640,13 @@ static int forward_mask_impl(fscnn_ctx* c, const float* d_x, const void* d_label
     return FSCNN_OK;
 }
 
-int fscnn_forward_mask(fscnn_ctx* c, const float* d_x, int n, int h, int w, void* d_mask, int mask_dtype, void* ws,
+int fscnn_forward_mask(fscnn_ctx* c, const void* d_x, int n, int h, int w, void* d_mask, int mask_dtype, void* ws,
                        size_t ws_bytes, void* stream) {
     if (!d_mask) return fail(FSCNN_EINVAL, "null mask pointer");
     return forward_mask_impl(c, d_x, nullptr, 0, n, h, w, nullptr, d_mask, mask_dtype, ws, ws_bytes, stream);
 }
 
-int fscnn_forward_confusion(fscnn_ctx* c, const float* d_x, const void* d_labels, int label_dtype, int n, int h, int w,
+int fscnn_forward_confusion(fscnn_ctx* c, const void* d_x, const void* d_labels, int label_dtype, int n, int h, int w,
                             long long* d_conf, void* d_mask, int mask_dtype, void* ws, size_t ws_bytes, void* stream) {
     if (!d_labels || !d_conf) return fail(FSCNN_EINVAL, "null labels or confusion pointer");
     return forward_mask_impl(c, d_x, d_labels, label_dtype, n, h, w, d_conf, d_mask, d_mask ? mask_dtype : FSCNN_U8, ws,

@@ -25,10 +25,15 @@ struct DsTcCfg {
     static constexpr int NSTRIP = 16 * (TH / RPS) * NCK;
     static constexpr int H_BYTES = round_up(PINP * ROWB, 128);
     static constexpr int A2_BYTES = HEAD ? 128 * COUT * 2 : 0;
-    static constexpr int oH = 0;                        // halo tile; HEAD: re-used as the second A operand
-    static constexpr int oA = oH + (H_BYTES > A2_BYTES ? H_BYTES : A2_BYTES);
-    static constexpr int oB = oA + 128 * CIN * 2;
-    static constexpr int oWd = oB + COUT * CIN * 2;
+    // CIN = 128: the weight image is bulk-copied over the halo tile once the depthwise phase is done with it, and the
+    // head's second A operand re-uses the first one's tile, so two CTAs fit in one SM's shared memory.
+    static constexpr bool ALIAS_B = (CIN >= 128);
+    static_assert(!HEAD || (ALIAS_B && COUT <= CIN), "HEAD re-uses the A tile");
+    static constexpr int oH = 0;
+    static constexpr int B_BYTES = COUT * CIN * 2;
+    static constexpr int oA = oH + (ALIAS_B ? (H_BYTES > B_BYTES ? H_BYTES : B_BYTES) : H_BYTES);
+    static constexpr int oB = ALIAS_B ? oH : oA + 128 * CIN * 2;
+    static constexpr int oWd = ALIAS_B ? oA + 128 * CIN * 2 : oB + B_BYTES;
     static constexpr int oBd = oWd + 9 * CIN * 4;
     static constexpr int oBp = oBd + CIN * 4;
     static constexpr int oB2 = round_up(oBp + COUT * 4, 128);   // HEAD: head weight image (ncp16 x COUT), sized at run time
@@ -44,7 +49,7 @@ __device__ __forceinline__ int chunk_swz(int pin, int k8) {
 }
 
 template <int CIN, int COUT, int STRIDE, bool HEAD>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp_img, bf16* __restrict__ out, HeadW head,
                  const bf16* __restrict__ wh_img, int ncp16, float* __restrict__ logits, int Hi, int Wi, int Ho, int Wo) {
     using C = DsTcCfg<CIN, COUT, STRIDE, HEAD>;
@@ -66,10 +71,10 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
     if (tid == 0) {
         mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1); mbar_init(&bar_mma2, 1);
         fence_mbar_init();
-        const uint32_t bytes = COUT * CIN * 2 + (HEAD ? ncp16 * COUT * 2 : 0);
-        mbar_arrive_expect_tx(&bar_w, bytes);
-        bulk_g2s(sm + C::oB, wp_img, COUT * CIN * 2, &bar_w);
-        if (HEAD) bulk_g2s(sm + C::oB2, wh_img, ncp16 * COUT * 2, &bar_w);
+        if (!C::ALIAS_B) {
+            mbar_arrive_expect_tx(&bar_w, COUT * CIN * 2);
+            bulk_g2s(sm + C::oB, wp_img, COUT * CIN * 2, &bar_w);
+        }
     }
     if (warp == 0) { tmem_alloc(&tmem_base_s, tm_cols); tmem_relinquish(); }
 
@@ -91,47 +96,53 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
     const uint32_t tmem = tmem_base_s;
 
     // ---- depthwise 3x3 (fp32) -> A-operand tile ----
+    if (CIN == 128 && STRIDE == 1) {
 #pragma unroll 1
-    for (int it = tid; it < C::NSTRIP; it += kThreads) {
-        const int x = it & 15, rg = (it >> 4) % (C::TH / RPS), k8 = it / (16 * (C::TH / RPS));
-        float wk[9][8];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float4 a = *reinterpret_cast<const float4*>(Wds + t * CIN + k8 * 8);
-            const float4 b = *reinterpret_cast<const float4*>(Wds + t * CIN + k8 * 8 + 4);
-            wk[t][0] = a.x; wk[t][1] = a.y; wk[t][2] = a.z; wk[t][3] = a.w;
-            wk[t][4] = b.x; wk[t][5] = b.y; wk[t][6] = b.z; wk[t][7] = b.w;
-        }
-        float acc[RPS][8];
-#pragma unroll
-        for (int o = 0; o < RPS; ++o)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[o][c] = Bds[k8 * 8 + c];
-        constexpr int NR = (RPS - 1) * STRIDE + 3;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int iy = (RPS * rg) * STRIDE + r;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int pin = iy * IW + x * STRIDE + kx;
-                float f[8];
-                unpackbf8(lds128(sH + pin * C::ROWB + (chunk_swz<CIN>(pin, k8) << 4)), f);
-#pragma unroll
-                for (int o = 0; o < RPS; ++o) {
-                    const int ky = r - o * STRIDE;
-                    if (ky >= 0 && ky < 3) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(f[c], wk[ky * 3 + kx][c], acc[o][c]);
+        for (int it = tid; it < 16 * (CIN / 4); it += kThreads)
+            dw3x3_s1_col4<C::ROWB, IW>(sH, it & 15, it >> 4, Wds, CIN, Bds, sA, 0);
+    } else {
+    #pragma unroll 1
+        for (int it = tid; it < C::NSTRIP; it += kThreads) {
+            const int x = it & 15, rg = (it >> 4) % (C::TH / RPS), k8 = it / (16 * (C::TH / RPS));
+            float wk[9][8];
+    #pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 a = *reinterpret_cast<const float4*>(Wds + t * CIN + k8 * 8);
+                const float4 b = *reinterpret_cast<const float4*>(Wds + t * CIN + k8 * 8 + 4);
+                wk[t][0] = a.x; wk[t][1] = a.y; wk[t][2] = a.z; wk[t][3] = a.w;
+                wk[t][4] = b.x; wk[t][5] = b.y; wk[t][6] = b.z; wk[t][7] = b.w;
+            }
+            float acc[RPS][8];
+    #pragma unroll
+            for (int o = 0; o < RPS; ++o)
+    #pragma unroll
+                for (int c = 0; c < 8; ++c) acc[o][c] = Bds[k8 * 8 + c];
+            constexpr int NR = (RPS - 1) * STRIDE + 3;
+    #pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const int iy = (RPS * rg) * STRIDE + r;
+    #pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int pin = iy * IW + x * STRIDE + kx;
+                    float f[8];
+                    unpackbf8(lds128(sH + pin * C::ROWB + (chunk_swz<CIN>(pin, k8) << 4)), f);
+    #pragma unroll
+                    for (int o = 0; o < RPS; ++o) {
+                        const int ky = r - o * STRIDE;
+                        if (ky >= 0 && ky < 3) {
+    #pragma unroll
+                            for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(f[c], wk[ky * 3 + kx][c], acc[o][c]);
+                        }
                     }
                 }
             }
-        }
-#pragma unroll
-        for (int o = 0; o < RPS; ++o) {
-            const int p = (RPS * rg + o) * 16 + x;
-            sts128(sA + ((k8 * 16 + (p >> 3)) << 7) + ((p & 7) << 4), packbf(relu(acc[o][0]), relu(acc[o][1])),
-                   packbf(relu(acc[o][2]), relu(acc[o][3])), packbf(relu(acc[o][4]), relu(acc[o][5])),
-                   packbf(relu(acc[o][6]), relu(acc[o][7])));
+    #pragma unroll
+            for (int o = 0; o < RPS; ++o) {
+                const int p = (RPS * rg + o) * 16 + x;
+                sts128(sA + ((k8 * 16 + (p >> 3)) << 7) + ((p & 7) << 4), packbf(relu(acc[o][0]), relu(acc[o][1])),
+                       packbf(relu(acc[o][2]), relu(acc[o][3])), packbf(relu(acc[o][4]), relu(acc[o][5])),
+                       packbf(relu(acc[o][6]), relu(acc[o][7])));
+            }
         }
     }
     fence_async_proxy();
@@ -139,6 +150,11 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
 
     // ---- pointwise contraction on the tensor core ----
     if (tid == 0) {
+        if (C::ALIAS_B) {   // the halo tile is dead: stream the weight image (and the head's) over it
+            mbar_arrive_expect_tx(&bar_w, COUT * CIN * 2 + (HEAD ? ncp16 * COUT * 2 : 0));
+            bulk_g2s(sm + C::oB, wp_img, COUT * CIN * 2, &bar_w);
+            if (HEAD) bulk_g2s(sm + C::oB2, wh_img, ncp16 * COUT * 2, &bar_w);
+        }
         mbar_wait(&bar_w, 0);
         tc_fence_after_sync();
         constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
@@ -172,7 +188,7 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
             if (!HEAD) {
                 if (live) *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * COUT + co) = make_uint4(a, b, c, d);
             } else {
-                sts128(sH + (((co >> 3) * 16 + (p >> 3)) << 7) + ((p & 7) << 4), a, b, c, d);   // second A operand (halo tile is dead)
+                sts128(sA + a_tile_off(p, co >> 3), a, b, c, d);   // second A operand over the first (its MMA has completed)
             }
         }
     }
@@ -185,7 +201,7 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
             const uint32_t idesc2 = make_idesc_bf16(128, ncp16);
 #pragma unroll
             for (int k16 = 0; k16 < COUT / 16; ++k16)
-                umma_bf16_ss(tmem + COUT, make_smem_desc(sH + k16 * 4096, 2048, 128),
+                umma_bf16_ss(tmem + COUT, make_smem_desc(sA + k16 * 4096, 2048, 128),
                              make_smem_desc(sB2 + k16 * 2 * (ncp16 * 16), ncp16 * 16, 128), idesc2, k16 > 0);
             umma_commit(&bar_mma2);
         }

@@ -15,17 +15,17 @@ namespace fscnn {
 
 namespace {
 constexpr int kIW = 18, kPIN = 180, kPINP = 184, kCL = 128, kCH = 64, kK = 192, kCO = 128;
-constexpr int oU = 0;                               // [184][256 B]
-constexpr int oA = oU + kPINP * kCL * 2;            // 128 x 192 bf16
-constexpr int oB = oA + 128 * kK * 2;               // 128 x 192 bf16
-constexpr int oWd = oB + kCO * kK * 2;              // fp32 [9][128]
+constexpr int oU = 0;                               // [184][256 B] resized halo tile ...
+constexpr int oB = 0;                               // ... later overwritten by the 128 x 192 weight image (48 KB)
+constexpr int oA = kCO * kK * 2;                    // 128 x 192 bf16
+constexpr int oWd = oA + 128 * kK * 2;              // fp32 [9][128]
 constexpr int oBd = oWd + 9 * kCL * 4;
 constexpr int oBc = oBd + kCL * 4;
 constexpr int oTab = oBc + kCO * 4;                 // per halo pixel: int4 {top-left idx, bottom-left idx, dx, -} or x = -1 outside
 constexpr int kSmem = oTab + kPINP * 16;
 }  // namespace
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 ffm_tc_kernel(const bf16* __restrict__ higher, const bf16* __restrict__ lower, FfmW w, const bf16* __restrict__ wcat_img,
               bf16* __restrict__ out, int Hh, int Wh, int Hl, int Wl) {
     extern __shared__ __align__(128) uint8_t sm[];
@@ -42,8 +42,6 @@ ffm_tc_kernel(const bf16* __restrict__ higher, const bf16* __restrict__ lower, F
     if (tid == 0) {
         mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(&bar_w, kCO * kK * 2);
-        bulk_g2s(sm + oB, wcat_img, kCO * kK * 2, &bar_w);
     }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 128); tmem_relinquish(); }
 
@@ -104,51 +102,16 @@ ffm_tc_kernel(const bf16* __restrict__ higher, const bf16* __restrict__ lower, F
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-    // depthwise 3x3 + bias + ReLU on U -> A columns 64..191; strip = (column x, 4-row group, chunk)
+    // depthwise 3x3 + bias + ReLU on U -> A columns 64..191 (one output column x 4 channels per item)
 #pragma unroll 1
-    for (int it = tid; it < 16 * 2 * 16; it += kThreads) {
-        const int x = it & 15, rg = (it >> 4) & 1, k8 = it >> 5;
-        float wk[9][8];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const float4 a = *reinterpret_cast<const float4*>(Wds + t * kCL + k8 * 8);
-            const float4 b = *reinterpret_cast<const float4*>(Wds + t * kCL + k8 * 8 + 4);
-            wk[t][0] = a.x; wk[t][1] = a.y; wk[t][2] = a.z; wk[t][3] = a.w;
-            wk[t][4] = b.x; wk[t][5] = b.y; wk[t][6] = b.z; wk[t][7] = b.w;
-        }
-        float acc[4][8];
-#pragma unroll
-        for (int o = 0; o < 4; ++o)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[o][c] = Bds[k8 * 8 + c];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int pin = (4 * rg + r) * kIW + x + kx;
-                float f[8];
-                unpackbf8(lds128(sU + pin * (kCL * 2) + ((k8 ^ (pin & 7)) << 4)), f);
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const int ky = r - o;
-                    if (ky >= 0 && ky < 3) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(f[c], wk[ky * 3 + kx][c], acc[o][c]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const int p = (4 * rg + o) * 16 + x;
-            sts128(sA + a_tile_off(p, 8 + k8), packbf(relu(acc[o][0]), relu(acc[o][1])), packbf(relu(acc[o][2]), relu(acc[o][3])),
-                   packbf(relu(acc[o][4]), relu(acc[o][5])), packbf(relu(acc[o][6]), relu(acc[o][7])));
-        }
-    }
+    for (int it = tid; it < 16 * (kCL / 4); it += kThreads)
+        dw3x3_s1_col4<kCL * 2, kIW>(sU, it & 15, it >> 4, Wds, kCL, Bds, sA, 8);
     fence_async_proxy();
     __syncthreads();
 
     if (tid == 0) {
+        mbar_arrive_expect_tx(&bar_w, kCO * kK * 2);     // U is dead: the weight image streams over it
+        bulk_g2s(sm + oB, wcat_img, kCO * kK * 2, &bar_w);
         mbar_wait(&bar_w, 0);
         tc_fence_after_sync();
         constexpr uint32_t idesc = make_idesc_bf16(128, kCO);

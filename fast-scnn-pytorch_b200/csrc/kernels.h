@@ -6,6 +6,7 @@ namespace fscnn {
 
 // Folded (BatchNorm merged) fp32 weights, "k-major": W[k][cout] so that a contraction chunk is a
 // dense [KC][COUT] tile.  Depthwise weights are tap-major: W[tap][channel].
+struct StemIn { int format; float mean[3]; float inv_std[3]; };   // FSCNN_IN_*; uint8 input: (x/255 - mean) * inv_std
 struct StemW { const float *w, *b; };                       // [27][32] (k = ci*9+ky*3+kx), [32]
 struct DsW { const float *wd, *bd, *wp, *bp; };             // [9][cin], [cin], [cin][cout], [cout]
 struct HeadW { const float *w, *b; int nc, ncp; };          // [cin][ncp], [ncp]; ncp = nc rounded up to 4
@@ -18,7 +19,7 @@ struct FfmW { const float *wd, *bd, *wcat, *bcat; };        // [9][128],[128],[1
 struct AuxW { const float *w, *b; HeadW head; };            // [576][32] (k = tap*64+ci), [32]
 
 template <typename T>
-cudaError_t launch_stem(const float* x, const StemW& w, T* out, int n, int h, int wd, int ho, int wo, cudaStream_t s);
+cudaError_t launch_stem(const void* x, const StemIn& in, const StemW& w, T* out, int n, int h, int wd, int ho, int wo, cudaStream_t s);
 
 // _DSConv: DW3x3(stride, pad 1)+ReLU -> PW 1x1+ReLU, optionally chained with the classifier's 1x1 head
 // (head != nullptr: `out` is not written, low-res logits [n][ho][wo][ncp] fp32 are).
@@ -79,5 +80,9 @@ cudaError_t launch_dsconv_tc(int cin, int cout, int stride, const bf16* in, cons
 // wcat_img: the stacked [128 x 192] weight (64 higher | 128 lower input channels) as one chunk
 cudaError_t launch_ffm_tc(const bf16* higher, const bf16* lower, const FfmW& w, const bf16* wcat_img, bf16* out, int n, int hh,
                           int wh, int hl, int wl, cudaStream_t s);
+
+// w_img: stem weights [32 x 27] padded to K = 32 as one chunk
+cudaError_t launch_stem_tc(const void* x, const StemIn& in, const bf16* w_img, const float* bias, bf16* out, int n, int h,
+                           int wd, int ho, int wo, cudaStream_t s);
 
 }  // namespace fscnn

@@ -8,12 +8,16 @@
 // memory as broadcast float4s (2 LDS.128 per 32 FMA).  A CTA is 8 warps = 8 output rows x 32 cols.
 #include "kernels.h"
 
+#include "../../include/fscnn_b200.h"
+
 namespace fscnn {
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads) stem_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
+template <typename T, int FMT>
+__global__ void __launch_bounds__(kThreads) stem_kernel(const void* __restrict__ xin, StemIn prm, const float* __restrict__ wpk,
                                                          const float* __restrict__ bias, T* __restrict__ out,
                                                          int H, int W, int Ho, int Wo) {
+    const float* x = reinterpret_cast<const float*>(xin);
+    const unsigned char* xb = reinterpret_cast<const unsigned char*>(xin);
     __shared__ __align__(16) float ws[27 * 32];
     __shared__ float bs[32];
     for (int i = threadIdx.x; i < 27 * 32; i += kThreads) ws[i] = __ldg(wpk + i);
@@ -41,7 +45,12 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(const float* __restrict_
         for (int ky = 0; ky < 3; ++ky) {
             const float* row = x + (((size_t)n * 3 + ci) * H + (oy * 2 + ky)) * W + ix0;
             float r[9];
-            if (vec_ok) {
+            if (FMT == FSCNN_IN_U8_NHWC) {   // raw uint8 HWC: ToTensor + Normalize fused into the load
+                const unsigned char* rb = xb + (((size_t)n * H + (oy * 2 + ky)) * W + ix0) * 3 + ci;
+#pragma unroll
+                for (int c = 0; c < 9; ++c)
+                    r[c] = (ix0 + c < W) ? ((float)__ldg(rb + 3 * c) * (1.f / 255.f) - prm.mean[ci]) * prm.inv_std[ci] : 0.f;
+            } else if (vec_ok) {
                 const float4 v0 = __ldg(reinterpret_cast<const float4*>(row));
                 const float4 v1 = __ldg(reinterpret_cast<const float4*>(row) + 1);
                 r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w;
@@ -74,13 +83,17 @@ __global__ void __launch_bounds__(kThreads) stem_kernel(const float* __restrict_
 }
 
 template <typename T>
-cudaError_t launch_stem(const float* x, const StemW& w, T* out, int n, int h, int wd, int ho, int wo, cudaStream_t s) {
+cudaError_t launch_stem(const void* x, const StemIn& in, const StemW& w, T* out, int n, int h, int wd, int ho, int wo,
+                        cudaStream_t s) {
     dim3 grid(ceil_div(wo, 32), ceil_div(ho, 8), n);
-    stem_kernel<T><<<grid, kThreads, 0, s>>>(x, w.w, w.b, out, h, wd, ho, wo);
+    if (in.format == FSCNN_IN_U8_NHWC)
+        stem_kernel<T, FSCNN_IN_U8_NHWC><<<grid, kThreads, 0, s>>>(x, in, w.w, w.b, out, h, wd, ho, wo);
+    else
+        stem_kernel<T, FSCNN_IN_F32_NCHW><<<grid, kThreads, 0, s>>>(x, in, w.w, w.b, out, h, wd, ho, wo);
     return cudaGetLastError();
 }
 
-template cudaError_t launch_stem<float>(const float*, const StemW&, float*, int, int, int, int, int, cudaStream_t);
-template cudaError_t launch_stem<bf16>(const float*, const StemW&, bf16*, int, int, int, int, int, cudaStream_t);
+template cudaError_t launch_stem<float>(const void*, const StemIn&, const StemW&, float*, int, int, int, int, int, cudaStream_t);
+template cudaError_t launch_stem<bf16>(const void*, const StemIn&, const StemW&, bf16*, int, int, int, int, int, cudaStream_t);
 
 }  // namespace fscnn

@@ -34,6 +34,7 @@ class Engine:
         self._packed: Optional[torch.Tensor] = None
         self._ws: Dict[torch.device, torch.Tensor] = {}
         self.device: Optional[torch.device] = None
+        self._input_state = (native.IN_F32_NCHW, None, None)
 
     def __del__(self):
         ctx, self._ctx = getattr(self, '_ctx', None), None
@@ -78,20 +79,38 @@ class Engine:
             self._ws[self.device] = ws
         return ws
 
-    def _check_input(self, x: torch.Tensor) -> Tuple[int, int, int]:
+    def _set_input_format(self, fmt: int, mean, std) -> None:
+        state = (fmt, tuple(mean) if mean is not None else None, tuple(std) if std is not None else None)
+        if state == self._input_state:
+            return
+        f3 = C.c_float * 3
+        native.check(self.lib.fscnn_set_input_format(self._ctx, fmt, f3(*state[1]) if state[1] else None,
+                                                     f3(*state[2]) if state[2] else None), 'fscnn_set_input_format')
+        self._input_state = state
+
+    def _check_input(self, x: torch.Tensor, norm=None) -> Tuple[int, int, int]:
+        """Accepts float32 [N,3,H,W] (the reference's normalised tensor) or raw uint8 [N,H,W,3] images; for
+        the latter `norm` = (mean, std) is applied inside the stem kernel (None: /255 only)."""
         if self._packed is None:
             raise RuntimeError('Engine.load_state_dict has not been called')
         if not x.is_cuda or x.device != self.device:
             raise RuntimeError(f'input is on {x.device}, weights are on {self.device}; there is no CPU path')
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError(f'expected an [N,3,H,W] image batch, got {tuple(x.shape)}')
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            raise ValueError('input must be a contiguous float32 tensor')
+        if not x.is_contiguous() or x.dim() != 4:
+            raise ValueError('input must be a contiguous 4-d tensor')
+        if x.dtype == torch.uint8:
+            if x.shape[3] != 3:
+                raise ValueError(f'uint8 input must be [N,H,W,3], got {tuple(x.shape)}')
+            mean, std = norm if norm is not None else (None, None)
+            self._set_input_format(native.IN_U8_NHWC, mean, std)
+            return x.shape[0], x.shape[1], x.shape[2]
+        if x.dtype != torch.float32 or x.shape[1] != 3:
+            raise ValueError(f'expected float32 [N,3,H,W] or uint8 [N,H,W,3], got {x.dtype} {tuple(x.shape)}')
+        self._set_input_format(native.IN_F32_NCHW, None, None)
         return x.shape[0], x.shape[2], x.shape[3]
 
     # ---- the forward path --------------------------------------------------------------------
-    def forward_logits(self, x: torch.Tensor, want_aux: bool):
-        n, h, w = self._check_input(x)
+    def forward_logits(self, x: torch.Tensor, want_aux: bool, norm=None):
+        n, h, w = self._check_input(x, norm)
         with torch.cuda.device(self.device):
             ws = self._workspace(n, h, w)
             logits = torch.empty((n, self.num_classes, h, w), dtype=torch.float32, device=self.device)
@@ -101,8 +120,8 @@ class Engine:
                                                        ws.numel(), _stream_ptr()), 'fscnn_forward_logits')
         return logits, aux
 
-    def forward_mask(self, x: torch.Tensor, out_dtype=torch.uint8, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        n, h, w = self._check_input(x)
+    def forward_mask(self, x: torch.Tensor, out_dtype=torch.uint8, out: Optional[torch.Tensor] = None, norm=None) -> torch.Tensor:
+        n, h, w = self._check_input(x, norm)
         if out_dtype not in _DTYPE_CODE:
             raise ValueError('mask dtype must be torch.uint8, torch.int32 or torch.int64')
         with torch.cuda.device(self.device):
@@ -114,8 +133,8 @@ class Engine:
         return mask
 
     def forward_confusion(self, x: torch.Tensor, labels: torch.Tensor, conf: torch.Tensor,
-                          mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        n, h, w = self._check_input(x)
+                          mask: Optional[torch.Tensor] = None, norm=None) -> torch.Tensor:
+        n, h, w = self._check_input(x, norm)
         if labels.dtype not in _DTYPE_CODE or tuple(labels.shape) != (n, h, w) or not labels.is_contiguous():
             raise ValueError('labels must be a contiguous [N,H,W] uint8/int32/int64 tensor')
         if labels.device != self.device or conf.device != self.device:
@@ -137,8 +156,8 @@ class Engine:
     def stage_names(self):
         return [self.lib.fscnn_stage_name(self._ctx, i).decode() for i in range(self.lib.fscnn_stage_count(self._ctx))]
 
-    def forward_range(self, x: torch.Tensor, first: int, last: int) -> None:
-        n, h, w = self._check_input(x)
+    def forward_range(self, x: torch.Tensor, first: int, last: int, norm=None) -> None:
+        n, h, w = self._check_input(x, norm)
         with torch.cuda.device(self.device):
             ws = self._workspace(n, h, w)
             native.check(self.lib.fscnn_forward_range(self._ctx, x.data_ptr(), n, h, w, first, last, ws.data_ptr(),

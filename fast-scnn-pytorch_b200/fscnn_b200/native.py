@@ -12,6 +12,7 @@ _LIB_NAME = 'libfscnn_b200.so'
 
 PREC_FP32, PREC_BF16 = 0, 1
 U8, I32, I64 = 0, 1, 2
+IN_F32_NCHW, IN_U8_NHWC = 0, 1
 
 
 class NativeError(RuntimeError):
@@ -42,6 +43,7 @@ _SIGNATURES = {
     'fscnn_param_numel': (C.c_int64, [C.c_void_p, C.c_int]),
     'fscnn_packed_weight_bytes': (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     'fscnn_load_weights': (C.c_int, [C.c_void_p, C.POINTER(Tensor), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'fscnn_set_input_format': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'fscnn_workspace_bytes': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     'fscnn_forward_logits': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -15,8 +15,10 @@ final upsample (+ argmax, + metric histogram) -- lives in ``libfscnn_b200.so``. 
 eager-PyTorch fallback: a CPU tensor or training mode raises.
 
 Additions over the reference (optional, all keyword-only or new methods):
-``precision='fp32'|'bf16'`` constructor keyword, ``predict(x)`` (fused upsample+argmax mask) and
-``evaluate(x, labels, metric)`` (fused SegmentationMetric counting).
+``precision='fp32'|'bf16'`` constructor keyword, ``predict(x)`` (fused upsample+argmax mask),
+``evaluate(x, labels, metric)`` (fused SegmentationMetric counting), and raw ``uint8 [N,H,W,3]`` image
+batches: ``transforms.ToTensor()`` + ``Normalize(mean, std)`` (eval.py:22-25) then run inside the stem
+kernel (``normalize=(mean, std)``, default ImageNet as in the reference; ``normalize=None`` = /255 only).
 """
 from __future__ import annotations
 
@@ -35,6 +37,10 @@ NUM_CLASS = {'citys': 19, 'tusimple': 2, 'bdd100k': 2, 'custom': 2}
 # checkpoint file acronyms, reference models/fast_scnn.py:241-248
 _ACRONYMS = {'pascal_voc': 'voc', 'pascal_aug': 'voc', 'ade20k': 'ade', 'coco': 'coco', 'citys': 'citys',
              'tusimple': 'tusimple'}
+
+
+# transforms.Normalize constants every reference driver uses (eval.py:22-25, demo.py:37-40)
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
 
 class _ParamHolder(nn.Module):
@@ -218,28 +224,35 @@ class FastSCNN(nn.Module):
 
     @staticmethod
     def _as_input(x: torch.Tensor) -> torch.Tensor:
-        if x.dim() != 4 or x.size(1) != 3:
+        if x.dim() != 4:
+            raise ValueError(f'expected an [N,3,H,W] float batch or an [N,H,W,3] uint8 batch, got {tuple(x.shape)}')
+        if x.dtype == torch.uint8:
+            if x.size(3) != 3:
+                raise ValueError(f'uint8 images must be [N,H,W,3], got {tuple(x.shape)}')
+            return x.detach().contiguous()
+        if x.size(1) != 3:
             raise ValueError(f'expected an [N,3,H,W] batch, got {tuple(x.shape)}')
         return x.detach().to(torch.float32).contiguous()
 
     # ---- reference API --------------------------------------------------------------------------
-    def forward(self, x):
+    def forward(self, x, normalize=(IMAGENET_MEAN, IMAGENET_STD)):
         """Returns ``(logits,)`` or ``(logits, aux_logits)``: NCHW fp32 at the input resolution
-        (reference models/fast_scnn.py:33-46)."""
+        (reference models/fast_scnn.py:33-46).  ``normalize`` only applies to raw uint8 input."""
         x = self._as_input(x)
-        logits, aux = self._engine(x.device).forward_logits(x, want_aux=self.aux)
+        logits, aux = self._engine(x.device).forward_logits(x, want_aux=self.aux, norm=normalize)
         return (logits, aux) if self.aux else (logits,)
 
     # ---- fused fast paths (additions) ------------------------------------------------------------
     @torch.no_grad()
-    def predict(self, x, out_dtype=torch.uint8, out: Optional[torch.Tensor] = None):
+    def predict(self, x, out_dtype=torch.uint8, out: Optional[torch.Tensor] = None, normalize=(IMAGENET_MEAN, IMAGENET_STD)):
         """``torch.argmax(model(x)[0], 1)`` (eval.py:43-45) without materialising full-resolution
         logits.  ``out_dtype=torch.int64`` reproduces torch.argmax's dtype."""
         x = self._as_input(x)
-        return self._engine(x.device).forward_mask(x, out_dtype, out)
+        return self._engine(x.device).forward_mask(x, out_dtype, out, norm=normalize)
 
     @torch.no_grad()
-    def evaluate(self, x, labels, metric=None, conf: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None):
+    def evaluate(self, x, labels, metric=None, conf: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                 normalize=(IMAGENET_MEAN, IMAGENET_STD)):
         """forward + argmax + ``SegmentationMetric.update`` (eval.py:43-49) in one pass: accumulates this
         batch into an int64 confusion tensor on the device and returns it.  Pass ``metric`` (a
         ``utils.metric.SegmentationMetric``) to accumulate into its device-side state instead."""
@@ -249,7 +262,7 @@ class FastSCNN(nn.Module):
             conf = metric.device_confusion(x.device)
         elif conf is None:
             conf = torch.zeros(eng.conf_len(), dtype=torch.int64, device=x.device)
-        return eng.forward_confusion(x, labels.to(x.device).contiguous(), conf, mask)
+        return eng.forward_confusion(x, labels.to(x.device).contiguous(), conf, mask, norm=normalize)
 
 
 def get_fast_scnn(dataset='citys', pretrained=False, root='./weights', map_cpu=False, **kwargs):

@@ -49,6 +49,10 @@ extern "C" {
 #define FSCNN_I32 1
 #define FSCNN_I64 2
 
+/* layout of the image batch handed to the forward calls */
+#define FSCNN_IN_F32_NCHW 0  /* float32 [n,3,h,w], already normalised: what the reference's transforms produce */
+#define FSCNN_IN_U8_NHWC 1   /* uint8 [n,h,w,3] raw RGB: ToTensor + Normalize(mean, std) are applied inside the stem */
+
 typedef struct fscnn_ctx fscnn_ctx;
 
 /* One raw state_dict tensor handed to fscnn_load_weights (reference on-disk layout:
@@ -92,20 +96,27 @@ int fscnn_packed_weight_bytes(const fscnn_ctx* ctx, size_t* out_bytes);
 int fscnn_load_weights(fscnn_ctx* ctx, const fscnn_tensor* tensors, int n_tensors,
                        void* d_packed, size_t packed_bytes, void* stream);
 
+/* Selects how the forward calls interpret their image pointer.  With FSCNN_IN_U8_NHWC the stem
+ * kernel computes (x / 255 - mean[c]) / std[c] on load, replacing transforms.ToTensor() +
+ * transforms.Normalize(mean, std) (reference eval.py:22-25, demo.py:37-40); mean / std == NULL means
+ * "/255 only" (the custom-dataset convention, data_loader/custom.py:175).  Default: FSCNN_IN_F32_NCHW. */
+int fscnn_set_input_format(fscnn_ctx* ctx, int format, const float* mean3, const float* std3);
+
 /* Bytes of workspace a forward over an [n,3,h,w] batch needs (stage tensors, NHWC). */
 int fscnn_workspace_bytes(const fscnn_ctx* ctx, int n, int h, int w, size_t* out_bytes);
 
-/* Replaces FastSCNN.forward (models/fast_scnn.py:33-46): x is NCHW fp32 [n,3,h,w];
+/* Replaces FastSCNN.forward (models/fast_scnn.py:33-46): x is NCHW fp32 [n,3,h,w] (or uint8 [n,h,w,3] after
+ * fscnn_set_input_format(FSCNN_IN_U8_NHWC); the same holds for every forward entry point below);
  * d_logits is NCHW fp32 [n,nc,h,w]; d_aux_logits (same shape) may be NULL (must be non-NULL
  * to get the aux output when the ctx was created with aux=1). */
-int fscnn_forward_logits(fscnn_ctx* ctx, const float* d_x, int n, int h, int w,
+int fscnn_forward_logits(fscnn_ctx* ctx, const void* d_x, int n, int h, int w,
                          float* d_logits, float* d_aux_logits,
                          void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Replaces forward + torch.argmax(outputs[0], 1) (eval.py:43-45, demo.py:47-48) without ever
  * materialising the full-resolution logits.  d_mask is [n,h,w] of mask_dtype (FSCNN_U8 needs
  * num_classes <= 256; FSCNN_I64 reproduces torch.argmax's dtype). */
-int fscnn_forward_mask(fscnn_ctx* ctx, const float* d_x, int n, int h, int w,
+int fscnn_forward_mask(fscnn_ctx* ctx, const void* d_x, int n, int h, int w,
                        void* d_mask, int mask_dtype,
                        void* d_workspace, size_t workspace_bytes, void* stream);
 
@@ -113,7 +124,7 @@ int fscnn_forward_mask(fscnn_ctx* ctx, const float* d_x, int n, int h, int w,
  * for one batch: ADDS this batch's counts into d_conf, an int64[(nc+1)*(nc+1)+2] accumulator
  * (rows = label clipped to nc, cols = pred, then `labeled`, `correct`; see fscnn_conf_len).
  * d_labels is [n,h,w] of label_dtype; d_mask may be NULL. */
-int fscnn_forward_confusion(fscnn_ctx* ctx, const float* d_x, const void* d_labels, int label_dtype,
+int fscnn_forward_confusion(fscnn_ctx* ctx, const void* d_x, const void* d_labels, int label_dtype,
                             int n, int h, int w, long long* d_conf,
                             void* d_mask, int mask_dtype,
                             void* d_workspace, size_t workspace_bytes, void* stream);
@@ -140,7 +151,7 @@ const char* fscnn_stage_name(const fscnn_ctx* ctx, int stage);
 /* Runs stages [first, last] only, reading / writing the stage tensors in the workspace (the
  * input image is read by stage 0).  Lets a test inject the oracle's tensor before one stage and
  * check that stage in isolation. */
-int fscnn_forward_range(fscnn_ctx* ctx, const float* d_x, int n, int h, int w, int first_stage, int last_stage,
+int fscnn_forward_range(fscnn_ctx* ctx, const void* d_x, int n, int h, int w, int first_stage, int last_stage,
                         void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Where the stage-boundary tensor `tap` ("l2d.conv", "l2d.dsconv1", "l2d.dsconv2",

@@ -227,3 +227,45 @@ def test_errors_are_loud():
     model.train()
     with pytest.raises(NotImplementedError):
         model(torch.zeros(1, 3, 64, 64, device=DEV))
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 4e-2)])
+def test_uint8_input_fuses_totensor_normalize(precision, tol):
+    """Raw uint8 HWC images: the stem applies ToTensor + Normalize(mean, std) (eval.py:22-25) on load."""
+    from models.fast_scnn import IMAGENET_MEAN, IMAGENET_STD
+    nc = 19
+    sd = fo.make_state_dict(nc, False, 7)
+    rng = np.random.RandomState(4)
+    img = rng.randint(0, 256, size=(2, 97, 131, 3)).astype(np.uint8)
+    mean, std = np.array(IMAGENET_MEAN, np.float32), np.array(IMAGENET_STD, np.float32)
+    x = ((img.astype(np.float32) / np.float32(255) - mean) / std).transpose(0, 3, 1, 2).copy()   # what the reference's transforms produce
+    ref = fo.forward(sd, x)[0]
+    model = build_model(sd, nc, False, DEV, precision=precision)
+    got = model(torch.from_numpy(img).to(DEV))[0].cpu().numpy()
+    assert rel_err(got, ref) < tol
+    # and the /255-only convention of the custom dataset path (data_loader/custom.py:175)
+    ref2 = fo.forward(sd, (img.astype(np.float32) / np.float32(255)).transpose(0, 3, 1, 2).copy())[0]
+    got2 = model(torch.from_numpy(img).to(DEV), normalize=None)[0].cpu().numpy()
+    assert rel_err(got2, ref2) < tol
+    # same mask through the fused path, float and uint8 inputs agree
+    m1 = model.predict(torch.from_numpy(img).to(DEV))
+    m2 = model.predict(torch.from_numpy(x).to(DEV))
+    assert (m1 != m2).float().mean().item() < (1e-3 if precision == 'fp32' else 2e-2)
+
+
+def test_streaming_evaluator_matches_batchwise():
+    from fscnn_b200 import StreamingEvaluator
+    from utils.metric import SegmentationMetric
+    nc = 19
+    sd = fo.make_state_dict(nc, False, 7)
+    model = build_model(sd, nc, False, DEV)
+    rng = np.random.RandomState(9)
+    batches = [(torch.from_numpy(rng.randint(0, 256, size=(2, 96, 128, 3)).astype(np.uint8)).pin_memory(),
+                torch.from_numpy(rng.randint(0, nc + 1, size=(2, 96, 128)).astype(np.uint8)).pin_memory()) for _ in range(5)]
+    m_stream, m_ref = SegmentationMetric(nc, device=DEV), SegmentationMetric(nc, device=DEV)
+    ev = StreamingEvaluator(model, m_stream, batches[0][0], batches[0][1], device=DEV)
+    for img, lab in batches:
+        ev.submit(img, lab)
+        model.evaluate(img.to(DEV), lab.to(DEV), m_ref)
+    assert ev.result() == m_ref.get()
+    assert np.array_equal(m_stream.total_inter, m_ref.total_inter) and m_stream.total_label == 5 * 2 * 96 * 128
