@@ -354,15 +354,19 @@ def run_native_arm(args):
         eng.forward_range(xs, 0, len(names) - 1)     # fill every stage tensor once
         reps = 5
         table = []
+        fused_front = args.precision == 'bf16'      # bf16: stem + dsconv1 run as ONE kernel (l2d_front_tc.cu)
         for i, name in enumerate(names):
-            eng.forward_range(xs, i, i)
+            if fused_front and name == 'l2d.dsconv1':
+                continue
+            j = i + 1 if (fused_front and name == 'stem') else i
+            eng.forward_range(xs, i, j)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(reps):
-                eng.forward_range(xs, i, i)
+                eng.forward_range(xs, i, j)
             b.record()
             torch.cuda.synchronize()
-            table.append((name, a.elapsed_time(b) / reps / mb * 1e3))   # microseconds per image
+            table.append(('stem+l2d.dsconv1' if j != i else name, a.elapsed_time(b) / reps / mb * 1e3))   # microseconds per image
         mask = torch.empty((mb, h, w), dtype=torch.uint8, device=dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         full_us = None
@@ -378,6 +382,10 @@ def run_native_arm(args):
         tail_us = max(full_us - sum(t for _, t in table), 0.0)
         table.append(('up8+argmax+metric', tail_us))
         model_by_name = {s['stage']: s for s in stages}
+        if fused_front:   # plan-P bytes of both stages (the denominator is not changed); the fused kernel's own traffic beside it
+            a_, b_ = model_by_name['stem'], model_by_name['l2d.dsconv1']
+            model_by_name['stem+l2d.dsconv1'] = {'stage': 'stem+l2d.dsconv1', 'bytes': a_['bytes'] + b_['bytes'], 'flops': a_['flops'] + b_['flops'],
+                                                 'fused_bytes': 3.0 * h * w * 4 + ((((h - 3) // 2 + 1) - 1) // 2 + 1) * ((((w - 3) // 2 + 1) - 1) // 2 + 1) * 48.0 * es}
         rows = []
         for name, us in table:
             m = model_by_name.get(name if name != 'stem' else 'stem')
@@ -385,6 +393,9 @@ def run_native_arm(args):
                 continue
             rows.append({'stage': name, 'us_per_image': us, 'gbs': m['bytes'] / us / 1e3, 'tflops': m['flops'] / us / 1e6,
                          'bytes': m['bytes'], 'flops': m['flops']})
+            if 'fused_bytes' in m:
+                rows[-1]['fused_bytes'] = m['fused_bytes']
+                rows[-1]['fused_gbs'] = m['fused_bytes'] / us / 1e3
         out['stages'] = rows
         top = max(rows, key=lambda r: r['us_per_image'])
         hbm_time = top['bytes'] / (peaks['hbm_gbs'] * 1e9)

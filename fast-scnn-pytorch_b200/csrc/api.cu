@@ -82,6 +82,8 @@ struct fscnn_ctx {
     bool loaded = false;
     int64_t launches = 0;
     int micro_batch = 0;
+    bool in_dirty = false; // uint8 input: the normalisation-folded stem image must be rebuilt before the next launch
+    int fuse_front = 1;   // bf16: stem + dsconv1 in one kernel whenever both stages are requested
     StemIn in{FSCNN_IN_F32_NCHW, {0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
     // offsets (floats) into the packed buffer, fixed at create time
     struct Off {
@@ -93,7 +95,7 @@ struct fscnn_ctx {
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
         size_t bn_we_img[9], bn_wp_img[9];                  // bf16 tcgen05 operand images (offsets still in floats)
-        size_t ds_wp_img[4], head_img, ffm_img, stem_img;
+        size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8;
     } off{};
     // device pointers resolved by load_weights
     StemW stem{};
@@ -105,6 +107,8 @@ struct fscnn_ctx {
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
     const bf16* stem_img = nullptr;
+    bf16* stem_img_u8 = nullptr;
+    float* stem_b_u8 = nullptr;
     PpmW ppm{};
     FfmW ffm{};
     HeadW head{};
@@ -220,6 +224,8 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
         f.head_img = take((size_t)((c->nc + 15) & ~15) * 128 / 2);
         f.ffm_img = take((size_t)128 * 192 / 2);
         f.stem_img = take((size_t)32 * 32 / 2);
+        f.stem_img_u8 = take((size_t)32 * 32 / 2);
+        f.stem_b_u8 = take(32);
     }
     c->packed_floats = o;
 }
@@ -277,6 +283,9 @@ cudaError_t ffm_dispatch(fscnn_ctx* c, const T* higher, const T* lower, T* out, 
 
 template <typename T>
 cudaError_t stem_dispatch(fscnn_ctx* c, const void* x, T* out, int m, const Dims& d, cudaStream_t s);
+// returns true (and sets *e) if stem + dsconv1 were issued as one fused launch
+template <typename T>
+bool front_fused(fscnn_ctx* c, const void* x, T* out_ds1, int m, const Dims& d, cudaStream_t s, cudaError_t* e);
 
 template <typename T>
 int run_stages(fscnn_ctx* c, const void* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
@@ -285,7 +294,9 @@ int run_stages(fscnn_ctx* c, const void* x, int m, const Dims& d, const WsPlan& 
     auto at = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
     auto atf = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
     for (int st = first; st <= last && e == cudaSuccess; ++st) {
-        if (st == kStem) {
+        if (st == kStem && last >= kDs1 && front_fused<T>(c, x, at(p.ds1), m, d, s, &e)) {
+            ++st;   // dsconv1 is done too
+        } else if (st == kStem) {
             e = stem_dispatch<T>(c, x, at(p.stem), m, d, s);
         } else if (st == kDs1) {
             e = dsconv_dispatch<T>(c, 0, 32, 48, 2, at(p.stem), at(p.ds1), false, nullptr, m, d.h1, d.w1, d.h2, d.w2, s);
@@ -358,6 +369,23 @@ cudaError_t stem_dispatch<float>(fscnn_ctx* c, const void* x, float* out, int m,
 template <>
 cudaError_t stem_dispatch<bf16>(fscnn_ctx* c, const void* x, bf16* out, int m, const Dims& d, cudaStream_t s) {
     return launch_stem_tc(x, c->in, c->stem_img, c->stem.b, out, m, d.h, d.w, d.h1, d.w1, s);
+}
+
+template <>
+bool front_fused<float>(fscnn_ctx*, const void*, float*, int, const Dims&, cudaStream_t, cudaError_t*) { return false; }
+template <>
+bool front_fused<bf16>(fscnn_ctx* c, const void* x, bf16* out_ds1, int m, const Dims& d, cudaStream_t s, cudaError_t* e) {
+    if (!c->fuse_front) return false;
+    const bool u8 = c->in.format == FSCNN_IN_U8_NHWC;
+    if (u8 && c->in_dirty) {
+        *e = launch_stem_refold(c->stem.w, c->stem.b, c->in, c->stem_img_u8, c->stem_b_u8, s);
+        if (*e != cudaSuccess) return true;
+        c->in_dirty = false;
+        c->launches += 1;
+    }
+    *e = launch_l2d_front_tc(x, c->in, u8 ? c->stem_img_u8 : c->stem_img, u8 ? c->stem_b_u8 : c->stem.b, c->ds[0], c->ds_wp_img[0],
+                             out_ds1, m, d.h, d.w, d.h1, d.w1, d.h2, d.w2, s);
+    return true;
 }
 
 int dispatch_stages(fscnn_ctx* c, const void* x, int m, const Dims& d, const WsPlan& p, char* ws, int first, int last,
@@ -445,6 +473,9 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         bf16* img = reinterpret_cast<bf16*>(P + f.stem_img);
         L.fold_umma("learning_to_downsample.conv.conv.0", "learning_to_downsample.conv.conv.1", 32, 27, 32, 32, img);
         c->stem_img = img;
+        c->stem_img_u8 = reinterpret_cast<bf16*>(P + f.stem_img_u8);
+        c->stem_b_u8 = P + f.stem_b_u8;
+        c->in_dirty = true;
     }
     const struct { const char* p; int cin, cout; } dss[4] = {{"learning_to_downsample.dsconv1", 32, 48},
                                                               {"learning_to_downsample.dsconv2", 48, 64},
@@ -535,7 +566,15 @@ int fscnn_set_input_format(fscnn_ctx* c, int format, const float* mean3, const f
         if (!(sd > 0.f)) return fail(FSCNN_EINVAL, "std[%d] must be positive", i);
         c->in.inv_std[i] = 1.f / sd;
     }
+    c->in_dirty = true;
     return FSCNN_OK;
+}
+
+int fscnn_set_option(fscnn_ctx* c, const char* key, int value) {
+    if (!c || !key) return fail(FSCNN_EINVAL, "null argument");
+    if (!strcmp(key, "fuse_front")) { c->fuse_front = value ? 1 : 0; return FSCNN_OK; }
+    if (!strcmp(key, "micro_batch")) return fscnn_set_micro_batch(c, value);
+    return fail(FSCNN_ENOENT, "unknown option '%s'", key);
 }
 
 int fscnn_set_micro_batch(fscnn_ctx* c, int images) {

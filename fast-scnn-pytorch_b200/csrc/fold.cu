@@ -60,6 +60,31 @@ __global__ void fold_umma_kernel(const float* __restrict__ w, const float* __res
     }
 }
 
+// uint8-input stem: fold ToTensor + Normalize, y_c = (x_c/255 - mean_c) * inv_std_c, into the (already BN-folded)
+// stem weights  w[k][n] (k = ci*9 + tap)  ->  bf16 image W'[n][k] = w[k][n] * inv_std_ci / 255  and
+// b'[n] = b[n] - sum_k w[k][n] * mean_ci * inv_std_ci.  Exact because the stem convolution has no padding.
+__global__ void stem_refold_kernel(const float* __restrict__ w, const float* __restrict__ b, StemIn in,
+                                   __nv_bfloat16* __restrict__ img, float* __restrict__ bias) {
+    const int n = threadIdx.x;   // 32 output channels
+    if (n >= 32) return;
+    float acc = b[n];
+    for (int k = 0; k < 32; ++k) {
+        float v = 0.f;
+        if (k < 27) {
+            const int ci = k / 9;
+            v = w[k * 32 + n] * (in.inv_std[ci] * (1.f / 255.f));
+            acc -= w[k * 32 + n] * in.mean[ci] * in.inv_std[ci];
+        }
+        img[((k >> 3) * 4 + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(v);
+    }
+    bias[n] = acc;
+}
+
+cudaError_t launch_stem_refold(const float* w, const float* b, const StemIn& in, bf16* img, float* bias, cudaStream_t s) {
+    stem_refold_kernel<<<1, 32, 0, s>>>(w, b, in, img, bias);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* var, int nrows, int kdim, int nc, int kc,
                              bf16* out, cudaStream_t s) {
     fold_umma_kernel<<<ceil_div(nrows * kdim, 256), 256, 0, s>>>(w, gamma, var, nrows, kdim, nc, kc, out);

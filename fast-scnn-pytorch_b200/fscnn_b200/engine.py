@@ -176,6 +176,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.fscnn_launch_count(self._ctx))
 
+    def set_option(self, key: str, value: int) -> None:
+        native.check(self.lib.fscnn_set_option(self._ctx, key.encode(), int(value)), 'fscnn_set_option')
+        self._ws.clear()
+
     def set_micro_batch(self, images: int) -> None:
         native.check(self.lib.fscnn_set_micro_batch(self._ctx, int(images)))
         self._ws.clear()

@@ -63,6 +63,7 @@ _SIGNATURES = {
     'fscnn_tap_info': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(Tap)]),
     'fscnn_launch_count': (C.c_int64, [C.c_void_p]),
     'fscnn_set_micro_batch': (C.c_int, [C.c_void_p, C.c_int]),
+    'fscnn_set_option': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

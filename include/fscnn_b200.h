@@ -166,6 +166,10 @@ int64_t fscnn_launch_count(const fscnn_ctx* ctx);
  * micro-batch's stage tensors stay L2-resident).  0 restores the default. */
 int fscnn_set_micro_batch(fscnn_ctx* ctx, int images);
 
+/* Tuning / A-B switches: "fuse_front" (1 = stem + dsconv1 as one kernel in the bf16 path, default),
+ * "micro_batch" (as fscnn_set_micro_batch). */
+int fscnn_set_option(fscnn_ctx* ctx, const char* key, int value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,14 +229,15 @@ def test_errors_are_loud():
         model(torch.zeros(1, 3, 64, 64, device=DEV))
 
 
+@pytest.mark.parametrize('shape', [(2, 97, 131, 3), (1, 100, 132, 3)])   # row pitch not / is a multiple of 4 bytes
 @pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('bf16', 4e-2)])
-def test_uint8_input_fuses_totensor_normalize(precision, tol):
+def test_uint8_input_fuses_totensor_normalize(precision, tol, shape):
     """Raw uint8 HWC images: the stem applies ToTensor + Normalize(mean, std) (eval.py:22-25) on load."""
     from models.fast_scnn import IMAGENET_MEAN, IMAGENET_STD
     nc = 19
     sd = fo.make_state_dict(nc, False, 7)
     rng = np.random.RandomState(4)
-    img = rng.randint(0, 256, size=(2, 97, 131, 3)).astype(np.uint8)
+    img = rng.randint(0, 256, size=shape).astype(np.uint8)
     mean, std = np.array(IMAGENET_MEAN, np.float32), np.array(IMAGENET_STD, np.float32)
     x = ((img.astype(np.float32) / np.float32(255) - mean) / std).transpose(0, 3, 1, 2).copy()   # what the reference's transforms produce
     ref = fo.forward(sd, x)[0]
