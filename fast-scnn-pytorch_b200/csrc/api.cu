@@ -502,8 +502,9 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         if (c->prec == FSCNN_PREC_BF16) {
             bf16* we_img = reinterpret_cast<bf16*>(P + f.bn_we_img[i]);
             bf16* wp_img = reinterpret_cast<bf16*>(P + f.bn_wp_img[i]);
-            L.fold_umma(p + ".0.conv.0", p + ".0.conv.1", ce, ci, 64, ci, we_img);   // expand: chunks of 64 rows
-            L.fold_umma(p + ".2", p + ".3", co, ce, co, 64, wp_img);                 // project: chunks of 64 columns
+            const int chunk = bottleneck_tc_chunk(kBnecks[i].stride);
+            L.fold_umma(p + ".0.conv.0", p + ".0.conv.1", ce, ci, chunk, ci, we_img);   // expand: chunks of `chunk` rows
+            L.fold_umma(p + ".2", p + ".3", co, ce, co, chunk, wp_img);                 // project: chunks of `chunk` columns
             c->bn_we_img[i] = we_img;
             c->bn_wp_img[i] = wp_img;
         }

@@ -4,6 +4,12 @@
 // 1x1 contractions run as tcgen05.mma (bf16 operands from shared memory, fp32 accumulators in
 // TMEM), the depthwise stage runs on the CUDA cores in fp32 between them.
 //
+// Measured alternative (round 1, rejected): running the depthwise 3x3 itself on the tensor core as 9 * CE/16
+// block-diagonal MMAs (N = 16) over shifted views of a column-major expanded tile is numerically exact and needs 3x
+// fewer CUDA-core instructions, but every SS-mode tcgen05.mma costs >= 64 cycles for its 128 x 16 A-operand read
+// whatever N is (tc_probe: 64.1 cyc/MMA for N = 16..128), so 36 of them per chunk made the kernel tensor-pipe bound
+// and 25-30 % slower than the CUDA-core depthwise below.
+//
 // CTA = 8x16 output pixels (M = 128 rows of the project MMA), 512 threads (16 warps keep the LDS / TMEM
 // latencies of the CUDA-core phases covered while one elected thread feeds the tensor core).
 //   X  : input halo tile, bf16, as NMT MMA A-tiles of 128 rows (core-matrix layout [k/8][row/8])
@@ -279,6 +285,9 @@ static cudaError_t run_tc(const bf16* in, const BneckW& w, const bf16* we_img, c
     bottleneck_tc_kernel<CIN, COUT, STRIDE, RES><<<grid, kNT, C::smem_bytes, s>>>(in, w, we_img, wp_img, out, hi, wi, ho, wo);
     return cudaGetLastError();
 }
+
+// expanded channels per chunk: the weight images handed to launch_bottleneck_tc must be cut accordingly
+int bottleneck_tc_chunk(int) { return 64; }
 
 cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const BneckW& w, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s) {

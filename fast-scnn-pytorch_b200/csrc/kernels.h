@@ -68,7 +68,9 @@ cudaError_t launch_fold(const float* w, const float* cbias, const float* gamma, 
 // bf16 tensor-core (tcgen05 / TMEM) variants ------------------------------------------------------------
 cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* var, int nrows, int kdim, int nc, int kc,
                              bf16* out, cudaStream_t s);
-// we_img: expand weights [6cin x cin] in chunks of 64 rows; wp_img: project weights [cout x 6cin] in chunks of 64 columns
+// we_img: expand weights [6cin x cin] in chunks of CE rows; wp_img: project weights [cout x 6cin] in chunks of CE columns,
+// CE = bottleneck_tc_chunk(stride)
+int bottleneck_tc_chunk(int stride);
 cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const BneckW& w, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 
