@@ -33,7 +33,8 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('FSCNN_BENCH_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default=os.environ.get('FSCNN_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16'],
+                    help='bf16 = tensor-core fast path (headline); fp32 = exactness path (also timed briefly as fp32_exact)')
     ap.add_argument('--batch', type=int, default=16, help='images per GPU per step')
     ap.add_argument('--micro-batch', type=int, default=0, help='0 = library default')
     ap.add_argument('--height', type=int, default=1024)
@@ -41,6 +42,7 @@ def parse_args():
     ap.add_argument('--classes', type=int, default=19)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-stage-times', action='store_true')
+    ap.add_argument('--no-fp32', action='store_true', help='skip the short fp32 exactness-path timing')
     ap.add_argument('--latency', action='store_true', help='also report batch-1 latency (CUDA graph replay)')
     return ap.parse_args()
 
@@ -406,7 +408,14 @@ def run_native_arm(args):
         else:
             roof = {'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': top['gbs'] / peaks['hbm_gbs']}
-        roof.update({'kernel': top['stage'], 'traffic': None, 'peak_source': peaks['source'], 'images_per_launch': mb,
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, 'profiles', 'kernel_traffic.json')
+        if os.path.exists(tpath):
+            rec = json.load(open(tpath)).get(args.precision, {}).get(top['stage'])
+            if rec:
+                traffic = rec['dram_bytes_per_image'] * mb
+        roof.update({'kernel': top['stage'], 'traffic': traffic, 'algorithmic_bytes_per_launch': top['bytes'] * mb,
+                     'peak_source': peaks['source'], 'images_per_launch': mb,
                      'us_per_launch': top['us_per_image'] * mb,
                      'note': 'fp32 path: this kernel is FP32-FMA bound on CUDA cores; fma_frac = achieved fp32 TFLOP/s / '
                              '(148 SM x 128 lanes x 2 x sm_mhz)' if args.precision == 'fp32' else ''})
@@ -414,6 +423,25 @@ def run_native_arm(args):
             mhz = (clocks or {}).get('sm_mhz') or peaks['sm_max_mhz']
             roof['fma_frac'] = top['tflops'] / (148 * 128 * 2 * mhz * 1e6 / 1e12)
         out['roofline'] = roof
+
+    if args.precision != 'fp32' and not args.no_fp32:
+        # the fp32 exactness path (parity 1e-4 vs the reference) on the same inputs, short run
+        m32 = FastSCNN(nc, precision='fp32').eval()
+        m32.load_state_dict(model.state_dict())
+        m32.to(dev)
+        met32 = SegmentationMetric(nc, device=dev)
+        for _ in range(2):
+            m32.evaluate(x, labels, met32)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            m32.evaluate(x, labels, met32)
+        b.record()
+        torch.cuda.synchronize()
+        out['fp32_exact'] = {'value': B * 5 / (a.elapsed_time(b) / 1e3), 'unit': UNIT, 'steps': 5, 'n_gpus': 1,
+                             'note': 'fp32 storage + fp32 FMA path on rank 0 (logits within 1e-4 of the reference)'}
+        del m32, met32
 
     if args.latency:
         xs1 = x[:1].contiguous()

@@ -69,6 +69,38 @@ struct ConfSink {
     }
 };
 
+// Finite-logit argmax over the classes for a thread's 8x4 output pixels.  Rows i < K interpolate between the
+// horizontally-lerped staged rows 0/1, rows i >= K between rows 1/2 (K is warp-uniform and a template constant, so the
+// vertical step is one FMUL + one FFMA per pixel).  `v > best` keeps the first maximal class.
+template <int K>
+__device__ __forceinline__ void argmax_fast(const float* __restrict__ Ls, int nc, const int (&ro)[3], const int (&co)[3],
+                                            const float (&wx)[4][3], const float (&wy)[8][3], float (&best)[8][4], int (&bidx)[8][4]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { best[i][j] = -INFINITY; bidx[i][j] = 0; }
+    for (int c = 0; c < nc; ++c) {
+        const float* lc = Ls + c * kTR * kTC;
+        float hrow[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (K == 8 && r == 2) continue;          // the third staged row is never used
+            const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v2, fmaf(wx[j][1], v1, wx[j][0] * v0));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float wa = i < K ? wy[i][0] : wy[i][1], wb = i < K ? wy[i][1] : wy[i][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float val = fmaf(wb, i < K ? hrow[1][j] : hrow[2][j], wa * (i < K ? hrow[0][j] : hrow[1][j]));
+                if (val > best[i][j]) { best[i][j] = val; bidx[i][j] = c; }
+            }
+        }
+    }
+}
+
 // MODE 0: write NCHW fp32 logits.  MODE 1: argmax mask (+ optional confusion counts).
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -90,6 +122,7 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     const bool do_hist = (MODE == 1) && (labels != nullptr);
 
     // stage the low-res tile class-major: one float4 (4 classes of one pixel) per item, independent loads in flight
+    int nonfinite = 0;
     {
         const int nv = ncp >> 2;
         for (int i = tid; i < kTR * kTC * nv; i += kThreads) {
@@ -98,6 +131,7 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             const int rr = min(rb + r, hl - 1), qq = min(cb + q, wl - 1);
             const float4 t = __ldg(reinterpret_cast<const float4*>(low + (((size_t)n * hl + rr) * wl + qq) * ncp) + v);
             const int c = 4 * v;
+            nonfinite |= !(fabsf(t.x) <= 3.4e38f) | !(fabsf(t.y) <= 3.4e38f) | !(fabsf(t.z) <= 3.4e38f) | !(fabsf(t.w) <= 3.4e38f);
             float* dst = Ls + (c * kTR + r) * kTC + q;
             dst[0] = t.x;
             if (c + 1 < nc) dst[kTR * kTC] = t.y;
@@ -110,7 +144,8 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             for (int i = tid; i < (nc + 1) * (nc + 1); i += kThreads) hist[i] = 0u;
         if (tid == 0) { blk_labeled = 0u; blk_correct = 0u; }
     }
-    __syncthreads();
+    // NaN / Inf among the staged logits (padding classes are finite zeros) selects the exact-semantics slow loop
+    const bool slow = __syncthreads_or(nonfinite) != 0;
 
     const int x0 = xb + lane * 4, y0 = yb + warp * 8;
     if (x0 >= W || y0 >= H) {
@@ -130,12 +165,14 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
         wx[j][0] = s ? 0.f : hx; wx[j][1] = s ? hx : lx; wx[j][2] = s ? lx : 0.f;
     }
     const int r0 = min((int)(scy * (float)y0), hl - 1);
+    int rows_on_first_pair = 0;   // rows whose taps are staged rows (r0, r0+1); the rest use (r0+1, r0+2)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float fy = scy * (float)(y0 + i);
         const int r = min((int)fy, hl - 1);
         const float ly = fy - (float)r, hy = 1.f - ly;
         const bool s = (r - r0) != 0;
+        rows_on_first_pair += s ? 0 : 1;
         wy[i][0] = s ? 0.f : hy; wy[i][1] = s ? hy : ly; wy[i][2] = s ? ly : 0.f;
     }
     // tile-relative offsets of the 3 rows / 3 columns (clamped at the image border like ATen's x1 = x0 + (x0 < w-1))
@@ -161,7 +198,21 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             if (y0 + i < H)
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(labels) + (((size_t)n * H + (y0 + i)) * W + x0) * esz));
     }
-    if (live) {
+    if (MODE == 1 && live && !slow) {
+        // all logits finite: plain `>` argmax, and the vertical taps picked at compile time.  The number of rows that
+        // still use the first staged row pair is the same for every lane of the warp (they share y0).
+        const int k = rows_on_first_pair;
+        switch (k) {
+            case 1: argmax_fast<1>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+            case 2: argmax_fast<2>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+            case 3: argmax_fast<3>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+            case 4: argmax_fast<4>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+            case 5: argmax_fast<5>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+            case 6: argmax_fast<6>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+            case 7: argmax_fast<7>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+            default: argmax_fast<8>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+        }
+    } else if (live) {
         for (int c = 0; c < nc; ++c) {
             const float* lc = Ls + c * kTR * kTC;
             float hrow[3][4];

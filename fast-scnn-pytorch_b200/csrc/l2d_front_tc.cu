@@ -18,6 +18,13 @@
 
 namespace fscnn {
 
+#ifdef FSCNN_PHASE_TIMING   // debug build only: per-phase clock64 stamps of one CTA (see tools/phase_timing.py)
+__device__ long long g_front_phase[16];
+#define PHASE_STAMP(i) do { if (tid == 0 && blockIdx.x == 7 && blockIdx.y == 9 && blockIdx.z == 0) g_front_phase[i] = clock64(); } while (0)
+#else
+#define PHASE_STAMP(i) do { } while (0)
+#endif
+
 namespace {
 constexpr int SH = 17, SW = 33, SPIX = SH * SW;       // stem pixels per CTA (561)
 constexpr int NMT = 5;                                 // A tiles of 128 stem pixels
@@ -55,32 +62,34 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     const int sy0 = 2 * oy0 - 1, sx0 = 2 * ox0 - 1;      // first stem pixel of the halo tile (may be -1)
     const int iy0 = 2 * sy0, ix0 = 2 * sx0;              // first input row / column of the patch (may be -2)
 
+    PHASE_STAMP(0);
     if (tid == 0) { mbar_init(&bar_stem, 1); mbar_init(&bar_pw, 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
+    PHASE_STAMP(1);
     if (tid < 128) reinterpret_cast<uint4*>(sm + oWs)[tid] = __ldg(reinterpret_cast<const uint4*>(ws_img) + tid);
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWp)[tid] = __ldg(reinterpret_cast<const uint4*>(wp_img) + tid);
     for (int i = tid; i < 9 * 32; i += kThreads) Wds[i] = __ldg(w.wd + i);
     if (tid < 32) { Bss[tid] = __ldg(bs + tid); Bds[tid] = __ldg(w.bd + tid); }
     if (tid < 48) Bps[tid] = __ldg(w.bp + tid);
 
-    // ---- stage the input patch: every thread first issues ALL of its loads (independent, fully unrolled), then stores ----
+    // ---- stage the input patch.  fp32 NCHW: thread = (channel, column), walks the 35 rows with a constant pointer
+    //      step; all 35 loads are issued before the first store, and there is no per-element index arithmetic ----
     if (FMT == FSCNN_IN_F32_NCHW) {
         const float* xf = reinterpret_cast<const float*>(x);
-        constexpr int NEL = 3 * PR * PC, PER = (NEL + kThreads - 1) / kThreads;   // 7035 elements, 28 per thread
-        float v[PER];
+        if (tid < 3 * PC) {
+            const int ci = tid / PC, c = tid - ci * PC;
+            const int ix = ix0 + c;
+            const bool cok = ix >= 0 && ix < W;
+            const float* src = xf + (((size_t)n * 3 + ci) * H) * W + (cok ? ix : 0);
+            float v[PR];
 #pragma unroll
-        for (int it = 0; it < PER; ++it) {
-            const int i = tid + it * kThreads;
-            const int line = i / PC, c = i - line * PC;          // line = ci * PR + r
-            const int ci = line / PR, r = line - ci * PR;
-            const int iy = iy0 + r, ix = ix0 + c;
-            v[it] = (i < NEL && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xf + (((size_t)n * 3 + ci) * H + iy) * W + ix) : 0.f;
-        }
+            for (int r = 0; r < PR; ++r) {
+                const int iy = iy0 + r;
+                v[r] = (cok && iy >= 0 && iy < H) ? __ldg(src + (size_t)iy * W) : 0.f;
+            }
+            float* dst = In + ci * PR * PLD + c;
 #pragma unroll
-        for (int it = 0; it < PER; ++it) {
-            const int i = tid + it * kThreads;
-            const int line = i / PC, c = i - line * PC;
-            if (i < NEL) In[line * PLD + c] = v[it];
+            for (int r = 0; r < PR; ++r) dst[r * PLD] = v[r];
         }
     } else {
         // raw uint8 HWC: park each 201-byte patch row as 52 32-bit words (row start rounded down to 4 bytes).  ToTensor +
@@ -91,20 +100,23 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         const int rowb = W * 3;
         const int b0 = ix0 * 3 - 2;                                  // ix0*3 == 2 (mod 4)
         if ((W & 3) == 0) {
-            constexpr int PERW = (kRawWords + kThreads - 1) / kThreads;   // 1820 words, 8 per thread, all loads in flight
-            uint32_t v[PERW];
+            // thread = (word column wq < 52, row group rg < 4): 9 rows each, all loads in flight before the stores
+            if (tid < 4 * kRW) {
+                const int rg = tid / kRW, wq = tid - rg * kRW;
+                const int b = b0 + 4 * wq;
+                const bool cok = b >= 0 && b < rowb;
+                const unsigned char* src = xb + (size_t)n * H * rowb + (cok ? b : 0);
+                uint32_t v[9];
 #pragma unroll
-            for (int it = 0; it < PERW; ++it) {
-                const int i = tid + it * kThreads;
-                const int r = i / kRW, wq = i - r * kRW;
-                const int iy = iy0 + r, b = b0 + 4 * wq;
-                v[it] = (i < kRawWords && iy >= 0 && iy < H && b >= 0 && b < rowb)
-                            ? __ldg(reinterpret_cast<const uint32_t*>(xb + ((size_t)n * H + iy) * rowb + b)) : 0u;
-            }
+                for (int j = 0; j < 9; ++j) {
+                    const int r = rg * 9 + j, iy = iy0 + r;
+                    v[j] = (cok && r < PR && iy >= 0 && iy < H) ? __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)iy * rowb)) : 0u;
+                }
 #pragma unroll
-            for (int it = 0; it < PERW; ++it) {
-                const int i = tid + it * kThreads;
-                if (i < kRawWords) Raw[i] = v[it];
+                for (int j = 0; j < 9; ++j) {
+                    const int r = rg * 9 + j;
+                    if (r < PR) Raw[r * kRW + wq] = v[j];
+                }
             }
         } else {   // unaligned row pitch: byte loads into the same layout
             unsigned char* rawb = reinterpret_cast<unsigned char*>(Raw);
@@ -119,12 +131,13 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
+    PHASE_STAMP(2);   // patch staged
 
     // ---- im2col gather of the 561 stem pixels into five A tiles; k = ci*9 + ky*3 + kx ----
     if (FMT == FSCNN_IN_U8_NHWC) {
         const unsigned char* rawb = reinterpret_cast<const unsigned char*>(sm + oIn);
         const int pl = tid & 127, hi = tid >> 7;
-#pragma unroll 1
+#pragma unroll
         for (int mt = 0; mt < NMT; ++mt) {
             const int m = mt * 128 + pl;
             const int sr = m / SW, sc = m - sr * SW;
@@ -151,7 +164,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     } else {
         {
             const int pl = tid & 127, hi = tid >> 7;
-    #pragma unroll 1
+    #pragma unroll
             for (int mt = 0; mt < NMT; ++mt) {
                 const int m = mt * 128 + pl;
                 const int sr = m / SW, sc = m - sr * SW;
@@ -181,6 +194,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     }
     fence_async_proxy();
     __syncthreads();
+    PHASE_STAMP(3);   // im2col gathered
     if (tid == 0) {
         tc_fence_after_sync();
         constexpr uint32_t idesc = make_idesc_bf16(128, 32);
@@ -194,6 +208,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     }
     mbar_wait(&bar_stem, 0);
     tc_fence_after_sync();
+    PHASE_STAMP(4);   // stem MMAs done
 
     // ---- stem epilogue: bias, ReLU, zero outside the stem image (the depthwise conv pads with zeros) -> E ----
     for (int task = warp; task < NMT * 4; task += kThreads / 32) {
@@ -222,6 +237,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     }
     tc_fence_before_sync();
     __syncthreads();
+    PHASE_STAMP(5);   // stem epilogue done
 
     // ---- depthwise 3x3 stride 2 (fp32): strip = (column x, 2-row group, 8-channel chunk) -> A2 (over the dead A tiles) ----
     {
@@ -262,6 +278,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     }
     fence_async_proxy();
     __syncthreads();
+    PHASE_STAMP(6);   // depthwise done
     if (tid == 0) {
         tc_fence_after_sync();
         constexpr uint32_t idesc = make_idesc_bf16(128, 48);
@@ -273,6 +290,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     }
     mbar_wait(&bar_pw, 0);
     tc_fence_after_sync();
+    PHASE_STAMP(7);   // pointwise MMAs done
     {
         const int q = warp & 3, half = warp >> 2;           // 24 channels per warp half
         const int p = q * 32 + lane;
@@ -294,7 +312,9 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     }
     tc_fence_before_sync();
     __syncthreads();
+    PHASE_STAMP(8);   // output written
     if (warp == 0) tmem_dealloc(tmem, 256);
+    PHASE_STAMP(9);
 }
 
 cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_img, const float* bs, const DsW& w,
@@ -312,5 +332,11 @@ cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_
     }
     return cudaGetLastError();
 }
+
+#ifdef FSCNN_PHASE_TIMING
+extern "C" int fscnn_debug_front_phases(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_front_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 }  // namespace fscnn
