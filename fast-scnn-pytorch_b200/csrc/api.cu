@@ -117,11 +117,12 @@ struct fscnn_ctx {
     int esize() const { return prec == FSCNN_PREC_BF16 ? 2 : 4; }
     int eff_mb(int n, int h, int w) const {
         int mb = micro_batch;
-        if (mb <= 0) {   // default: about 16 Mpixel of input per micro-batch
+        if (mb <= 0) {   // default: about 64 Mpixel of input per micro-batch (32 images at 1024x2048): the small late
+                         // stages then launch several full waves and the per-launch gaps amortise (measured +12 % vs 8)
             long long px = (long long)h * w;
-            mb = (int)((16ll << 20) / (px > 0 ? px : 1));
+            mb = (int)((64ll << 20) / (px > 0 ? px : 1));
             if (mb < 1) mb = 1;
-            if (mb > 64) mb = 64;
+            if (mb > 128) mb = 128;
         }
         return mb < n ? mb : n;
     }
