@@ -72,6 +72,12 @@ struct ConfSink {
 // Finite-logit argmax over the classes for a thread's 8x4 output pixels.  Rows i < K interpolate between the
 // horizontally-lerped staged rows 0/1, rows i >= K between rows 1/2 (K is warp-uniform and a template constant, so the
 // vertical step is one FMUL + one FFMA per pixel).  `v > best` keeps the first maximal class.
+//
+// Exact branch-and-bound: every interpolated value of class c inside this 8x4 block is a convex combination of the
+// block's 3x3 low-res taps, so it lies in [min9_c, max9_c] (up to a few ulp of rounding).  With T = max_c min9_c, a class
+// whose max9_c is below T (minus 2e-6 x the block's largest |logit|, ~8x the rounding bound) cannot be the argmax of ANY pixel
+// of the block and is skipped; all others are interpolated and compared in class order as before.  The mask is
+// bit-identical to the exhaustive loop; only the time depends on how many classes are competitive locally.
 template <int K>
 __device__ __forceinline__ void argmax_fast(const float* __restrict__ Ls, int nc, const int (&ro)[3], const int (&co)[3],
                                             const float (&wx)[4][3], const float (&wy)[8][3], float (&best)[8][4], int (&bidx)[8][4]) {
@@ -79,15 +85,35 @@ __device__ __forceinline__ void argmax_fast(const float* __restrict__ Ls, int nc
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { best[i][j] = -INFINITY; bidx[i][j] = 0; }
+    const int o00 = ro[0] + co[0], o01 = ro[0] + co[1], o02 = ro[0] + co[2];
+    const int o10 = ro[1] + co[0], o11 = ro[1] + co[1], o12 = ro[1] + co[2];
+    const int o20 = ro[2] + co[0], o21 = ro[2] + co[1], o22 = ro[2] + co[2];
+    float T = -INFINITY, amax = 0.f;
     for (int c = 0; c < nc; ++c) {
         const float* lc = Ls + c * kTR * kTC;
+        const float a0 = lc[o00], a1 = lc[o01], a2 = lc[o02], a3 = lc[o10], a4 = lc[o11], a5 = lc[o12], a6 = lc[o20], a7 = lc[o21], a8 = lc[o22];
+        const float mn = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(a4, a5), fminf(fminf(a6, a7), a8)));
+        const float mx = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(fmaxf(a6, a7), a8)));
+        T = fmaxf(T, mn);
+        amax = fmaxf(amax, fmaxf(fabsf(mn), fabsf(mx)));
+    }
+    // rounding of the two lerps is below 4 ulp of the largest tap magnitude (2.4e-7 relative); 2e-6 leaves 8x headroom
+    const float cut = T - (2e-6f * amax + 1e-30f);
+    for (int c = 0; c < nc; ++c) {
+        const float* lc = Ls + c * kTR * kTC;
+        float v[3][3];
+        v[0][0] = lc[o00]; v[0][1] = lc[o01]; v[0][2] = lc[o02];
+        v[1][0] = lc[o10]; v[1][1] = lc[o11]; v[1][2] = lc[o12];
+        v[2][0] = lc[o20]; v[2][1] = lc[o21]; v[2][2] = lc[o22];
+        const float mx = fmaxf(fmaxf(fmaxf(v[0][0], v[0][1]), fmaxf(v[0][2], v[1][0])),
+                               fmaxf(fmaxf(v[1][1], v[1][2]), fmaxf(fmaxf(v[2][0], v[2][1]), v[2][2])));
+        if (mx < cut) continue;   // cannot win anywhere in this block
         float hrow[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             if (K == 8 && r == 2) continue;          // the third staged row is never used
-            const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v2, fmaf(wx[j][1], v1, wx[j][0] * v0));
+            for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v[r][2], fmaf(wx[j][1], v[r][1], wx[j][0] * v[r][0]));
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -270,3 +270,22 @@ def test_streaming_evaluator_matches_batchwise():
         model.evaluate(img.to(DEV), lab.to(DEV), m_ref)
     assert ev.result() == m_ref.get()
     assert np.array_equal(m_stream.total_inter, m_ref.total_inter) and m_stream.total_label == 5 * 2 * 96 * 128
+
+
+def test_argmax_pruning_is_exact_on_adversarial_logits():
+    """The fused argmax skips classes that provably cannot win inside a thread's pixel block.  Stress it with logits
+    whose classes are nearly tied / cross inside blocks: the mask must still equal argmax of the path's own logits."""
+    nc = 19
+    rng = np.random.RandomState(17)
+    for scale_w, bias_scale in ((1e-3, 0.0), (1.0, 0.0), (0.05, 5.0)):
+        sd = fo.make_state_dict(nc, False, 23)
+        sd['classifier.conv.1.weight'] = (sd['classifier.conv.1.weight'] * scale_w).astype(np.float32)
+        sd['classifier.conv.1.bias'] = (rng.standard_normal(nc) * bias_scale).astype(np.float32)
+        model = build_model(sd, nc, False, DEV)
+        xd = torch.from_numpy(fo.make_input(2, 264, 392, 5)).to(DEV)
+        assert torch.equal(model.predict(xd).long(), torch.argmax(model(xd)[0], 1))
+    # all logits identical everywhere: nothing can be pruned, class 0 wins every pixel
+    sd['classifier.conv.1.weight'] = np.zeros_like(sd['classifier.conv.1.weight'])
+    sd['classifier.conv.1.bias'] = np.zeros(nc, np.float32)
+    model = build_model(sd, nc, False, DEV)
+    assert int(model.predict(xd).max()) == 0
