@@ -47,6 +47,35 @@ __device__ __forceinline__ void cp_async4z(uint32_t dst, const void* src, bool v
 __device__ __forceinline__ uint32_t a_rg_off(int m, int k8) { return (uint32_t)(m >> 3) * 512 + k8 * 128 + (m & 7) * 16; }
 }  // namespace
 
+// one 16-byte im2col piece (taps 8*KQ .. 8*KQ+7) for row `pl` of each of the five MMA tiles
+template <int FMT, int KQ>
+__device__ __forceinline__ void gather_chunk(const uint8_t* __restrict__ patch, uint32_t sA, int pl) {
+#pragma unroll
+    for (int mt = 0; mt < NMT; ++mt) {
+        const int m = mt * 128 + pl;
+        if (m >= 568) continue;
+        const int sr = m / SW, sc = m - sr * SW;
+        const bool ok = m < SPIX;
+        float v[8];
+        if (FMT == FSCNN_IN_U8_NHWC) {
+            const unsigned char* base = patch + (2 * sr) * (kRW * 4) + 2 + (2 * sc) * 3;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = KQ * 8 + q;
+                v[q] = (ok && k < 27) ? (float)base[((k % 9) / 3) * (kRW * 4) + (k % 3) * 3 + k / 9] : 0.f;
+            }
+        } else {
+            const float* base = reinterpret_cast<const float*>(patch) + (2 * sr) * PLD + 2 * sc;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int k = KQ * 8 + q;
+                v[q] = (ok && k < 27) ? base[((k / 9) * PR + (k % 9) / 3) * PLD + k % 3] : 0.f;
+            }
+        }
+        sts128(sA + a_rg_off(m, KQ), packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
+    }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 2)
 l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict__ ws_img, const float* __restrict__ bs,
@@ -80,14 +109,24 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
             if (tid < 3 * PC) {   // thread = (channel, column): 35 rows, constant pointer step
                 const int ci = tid / PC, c = tid - ci * PC;
                 const int ix = ix0 + c;
-                const bool cok = ix >= 0 && ix < W;
-                const float* src = xf + (((size_t)n * 3 + ci) * H) * W + (cok ? ix : 0);
-                const uint32_t dst = dst0 + (ci * PR * PLD + c) * 4;
+                uint32_t dst = dst0 + (ci * PR * PLD + c) * 4;
+                if (iy0 >= 0 && iy0 + PR <= H && ix0 >= 0 && ix0 + PC <= W) {   // interior tile (CTA-uniform): no predicates
+                    const float* src = xf + ((((size_t)n * 3 + ci) * H) + iy0) * W + ix;
 #pragma unroll
-                for (int r = 0; r < PR; ++r) {
-                    const int iy = iy0 + r;
-                    const bool ok = cok && iy >= 0 && iy < H;
-                    cp_async4z(dst + r * PLD * 4, ok ? src + (size_t)iy * W : xf, ok);
+                    for (int r = 0; r < PR; ++r) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+                        dst += PLD * 4;
+                        src += W;
+                    }
+                } else {
+                    const bool cok = ix >= 0 && ix < W;
+                    const float* src = xf + (((size_t)n * 3 + ci) * H) * W + (cok ? ix : 0);
+#pragma unroll
+                    for (int r = 0; r < PR; ++r) {
+                        const int iy = iy0 + r;
+                        const bool ok = cok && iy >= 0 && iy < H;
+                        cp_async4z(dst + r * PLD * 4, ok ? src + (size_t)iy * W : xf, ok);
+                    }
                 }
             }
         } else {
@@ -98,13 +137,24 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
                 if (tid < 4 * kRW) {   // thread = (word column, group of 9 rows)
                     const int rg = tid / kRW, wq = tid - rg * kRW;
                     const int bb = b0 + 4 * wq;
-                    const bool cok = bb >= 0 && bb < rowb;
-                    const unsigned char* src = xb + (size_t)n * H * rowb + (cok ? bb : 0);
+                    if (iy0 >= 0 && iy0 + PR <= H && b0 >= 0 && b0 + 4 * kRW <= rowb) {   // interior tile: no predicates
+                        const unsigned char* src = xb + ((size_t)n * H + iy0 + rg * 9) * rowb + bb;
+                        uint32_t dst = dst0 + (rg * 9 * kRW + wq) * 4;
 #pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        const int r = rg * 9 + j, iy = iy0 + r;
-                        const bool ok = cok && iy >= 0 && iy < H;
-                        if (r < PR) cp_async4z(dst0 + (r * kRW + wq) * 4, ok ? src + (size_t)iy * rowb : xb, ok);
+                        for (int j = 0; j < 9; ++j) {
+                            if (rg * 9 + j < PR) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+                            dst += kRW * 4;
+                            src += rowb;
+                        }
+                    } else {
+                        const bool cok = bb >= 0 && bb < rowb;
+                        const unsigned char* src = xb + (size_t)n * H * rowb + (cok ? bb : 0);
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            const int r = rg * 9 + j, iy = iy0 + r;
+                            const bool ok = cok && iy >= 0 && iy < H;
+                            if (r < PR) cp_async4z(dst0 + (r * kRW + wq) * 4, ok ? src + (size_t)iy * rowb : xb, ok);
+                        }
                     }
                 }
             } else {   // unaligned row pitch: plain byte loads into the same layout
@@ -137,35 +187,13 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         __syncthreads();                                       // patch of tile t visible; everything of tile t-1 retired
         if (t + gridDim.x < ntiles) prefetch(t + gridDim.x, b ^ 1);   // overlaps the whole tile
 
-        // ---- im2col gather of the 561 stem pixels into A; k = ci*9 + ky*3 + kx ----
+        // ---- im2col gather of the 561 stem pixels into A; k = ci*9 + ky*3 + kx.  Thread = (row within the MMA tile,
+        //      half of the taps); the half is warp-uniform and each variant unrolls to constant tap offsets ----
         {
-            const int pl = tid & 127, hi = tid >> 7;
-#pragma unroll
-            for (int mt = 0; mt < NMT; ++mt) {
-                const int m = mt * 128 + pl;
-                const int sr = m / SW, sc = m - sr * SW;
-                const bool ok = m < SPIX;
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    float v[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int k = (hi ? 16 : 0) + kk * 8 + q;   // hi is warp-uniform; both variants unroll to constants
-                        v[q] = 0.f;
-                        if (FMT == FSCNN_IN_U8_NHWC) {
-                            const unsigned char* base = sm + oBuf + b * kBuf + (2 * sr) * (kRW * 4) + 2 + (2 * sc) * 3;
-                            if (hi == 0) { if (ok) v[q] = (float)base[(((kk * 8 + q) % 9) / 3) * (kRW * 4) + ((kk * 8 + q) % 3) * 3 + (kk * 8 + q) / 9]; }
-                            else if (ok && 16 + kk * 8 + q < 27) v[q] = (float)base[(((16 + kk * 8 + q) % 9) / 3) * (kRW * 4) + ((16 + kk * 8 + q) % 3) * 3 + (16 + kk * 8 + q) / 9];
-                        } else {
-                            const float* base = reinterpret_cast<const float*>(sm + oBuf + b * kBuf) + (2 * sr) * PLD + 2 * sc;
-                            if (hi == 0) { if (ok) v[q] = base[(((kk * 8 + q) / 9) * PR + ((kk * 8 + q) % 9) / 3) * PLD + (kk * 8 + q) % 3]; }
-                            else if (ok && 16 + kk * 8 + q < 27) v[q] = base[(((16 + kk * 8 + q) / 9) * PR + ((16 + kk * 8 + q) % 9) / 3) * PLD + (16 + kk * 8 + q) % 3];
-                        }
-                        (void)k;
-                    }
-                    if (m < 568) sts128(sA + a_rg_off(m, 2 * hi + kk), packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
-                }
-            }
+            const int pl = tid & 127;
+            const uint8_t* patch = sm + oBuf + b * kBuf;
+            if (tid < 128) { gather_chunk<FMT, 0>(patch, sA, pl); gather_chunk<FMT, 1>(patch, sA, pl); }
+            else           { gather_chunk<FMT, 2>(patch, sA, pl); gather_chunk<FMT, 3>(patch, sA, pl); }
         }
         fence_async_proxy();
         tc_fence_before_sync();
