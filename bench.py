@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-stage-times', action='store_true')
     ap.add_argument('--no-fp32', action='store_true', help='skip the short fp32 exactness-path timing')
-    ap.add_argument('--latency', action='store_true', help='also report batch-1 latency (CUDA graph replay)')
+    ap.add_argument('--no-latency', dest='latency', action='store_false', help='skip the batch-1 CUDA-graph latency')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary workloads (480x640, 360x640)')
     return ap.parse_args()
 
 
@@ -482,6 +483,28 @@ def run_native_arm(args):
         b.record()
         torch.cuda.synchronize()
         out['latency_batch1_ms'] = a.elapsed_time(b) / 200
+
+    if not args.no_extra:
+        # BASELINE.json's other inference shapes (2-class TuSimple 480x640 and drivable-area 360x640), device-resident, rank 0
+        extra = []
+        for enc, eh, ew, eb in ((2, 480, 640, 128), (2, 360, 640, 128)):
+            em = FastSCNN(enc, precision=args.precision).eval().to(dev)
+            ex = torch.randn(eb, 3, eh, ew, device=dev)
+            el = torch.randint(-1, enc, (eb, eh, ew), device=dev, dtype=torch.int64)
+            emet = SegmentationMetric(enc, device=dev)
+            for _ in range(3):
+                em.evaluate(ex, el, emet)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                em.evaluate(ex, el, emet)
+            b.record()
+            torch.cuda.synchronize()
+            extra.append({'workload': f'eval_nc{enc}_{eh}x{ew}_fwd_argmax_metric', 'batch': eb, 'value': eb * 10 / (a.elapsed_time(b) / 1e3),
+                          'unit': UNIT, 'n_gpus': 1, 'precision': args.precision})
+            del em, ex, el, emet
+        out['other_workloads'] = extra
 
     if world == 1 and not args.no_cpu_baseline:
         rate, done, el, cores, threads = cpu_reference_rate(h, w, nc, 12.0, 1)

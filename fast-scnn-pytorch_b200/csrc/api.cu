@@ -708,6 +708,18 @@ int fscnn_confusion_from_mask(const void* d_pred, int pred_dtype, const void* d_
     return FSCNN_OK;
 }
 
+int fscnn_colorize(const void* d_mask, int mask_dtype, int64_t n_pixels, const unsigned char* h_palette768, unsigned char* d_rgb,
+                   void* stream) {
+    if (n_pixels < 0 || !h_palette768) return fail(FSCNN_EINVAL, "bad argument");
+    if (n_pixels == 0) return FSCNN_OK;
+    if (!d_mask || !d_rgb) return fail(FSCNN_EINVAL, "null device pointer");
+    if (mask_dtype != FSCNN_U8 && mask_dtype != FSCNN_I32 && mask_dtype != FSCNN_I64) return fail(FSCNN_EINVAL, "bad dtype %d", mask_dtype);
+    if ((uintptr_t)d_rgb & 3) return fail(FSCNN_EINVAL, "rgb output must be 4-byte aligned");
+    cudaError_t e = launch_colorize(d_mask, mask_dtype, n_pixels, h_palette768, d_rgb, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "colorize launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
 int fscnn_conf_to_totals(const long long* h_conf, int nc, long long* h_inter, long long* h_union, long long* h_correct,
                          long long* h_label) {
     if (!h_conf || !h_inter || !h_union || !h_correct || !h_label || nc < 1) return fail(FSCNN_EINVAL, "bad argument");

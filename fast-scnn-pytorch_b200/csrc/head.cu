@@ -480,4 +480,44 @@ cudaError_t launch_confusion(const void* pred, int pred_dtype, const void* label
     return cudaGetLastError();
 }
 
+
+// ---- palette rendering of a class map (the step right after the path: reference utils/visualize.py:7-36 puts a
+//      palette on the uint8 mask with PIL on the host; here rgb[p] = palette[mask[p]] in one pass on the device) ----
+struct Palette { unsigned char rgb[768]; };
+
+__global__ void __launch_bounds__(kThreads)
+colorize_kernel(const void* __restrict__ mask, int dtype, long long npix, Palette pal, unsigned char* __restrict__ rgb) {
+    __shared__ unsigned char ps[768];
+    for (int i = threadIdx.x; i < 768; i += kThreads) ps[i] = pal.rgb[i];
+    __syncthreads();
+    for (long long q = ((long long)blockIdx.x * kThreads + threadIdx.x) * 4; q < npix; q += (long long)gridDim.x * kThreads * 4) {
+        unsigned char o[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long v = q + j < npix ? load_label(mask, dtype, (size_t)(q + j)) : 0;
+            const int c = (int)(v & 255);
+            o[3 * j] = ps[3 * c]; o[3 * j + 1] = ps[3 * c + 1]; o[3 * j + 2] = ps[3 * c + 2];
+        }
+        if (q + 4 <= npix) {   // 12 bytes at a 4-byte aligned offset (q is a multiple of 4)
+            uint32_t* dst = reinterpret_cast<uint32_t*>(rgb + 3 * q);
+            dst[0] = o[0] | (o[1] << 8) | (o[2] << 16) | ((uint32_t)o[3] << 24);
+            dst[1] = o[4] | (o[5] << 8) | (o[6] << 16) | ((uint32_t)o[7] << 24);
+            dst[2] = o[8] | (o[9] << 8) | (o[10] << 16) | ((uint32_t)o[11] << 24);
+        } else {
+            for (int j = 0; q + j < npix; ++j) { rgb[3 * (q + j)] = o[3 * j]; rgb[3 * (q + j) + 1] = o[3 * j + 1]; rgb[3 * (q + j) + 2] = o[3 * j + 2]; }
+        }
+    }
+}
+
+cudaError_t launch_colorize(const void* mask, int dtype, long long npix, const unsigned char* palette768, unsigned char* rgb,
+                            cudaStream_t s) {
+    if (npix <= 0) return cudaSuccess;
+    Palette pal;
+    for (int i = 0; i < 768; ++i) pal.rgb[i] = palette768[i];
+    long long blocks = (npix + kThreads * 4 - 1) / (kThreads * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    colorize_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(mask, dtype, npix, pal, rgb);
+    return cudaGetLastError();
+}
+
 }  // namespace fscnn

@@ -58,6 +58,10 @@ cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int 
 cudaError_t launch_confusion(const void* pred, int pred_dtype, const void* label, int label_dtype, long long npix, int nc,
                              unsigned long long* conf, cudaStream_t s);
 
+// rgb[p] = palette[mask[p] & 255]; palette768 is HOST memory (256 x RGB), passed to the kernel by value
+cudaError_t launch_colorize(const void* mask, int dtype, long long npix, const unsigned char* palette768, unsigned char* rgb,
+                            cudaStream_t s);
+
 // BN folding + repack (load time).  out_w[k'][co] = w[co][k] * gamma/sqrt(var+eps); with taps > 1 and
 // `tap_major` the k index (ci*taps + tap) is permuted to (tap*cin + ci).  out_b = beta + (cbias - mean)*scale.
 cudaError_t launch_fold(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,

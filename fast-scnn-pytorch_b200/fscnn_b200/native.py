@@ -54,6 +54,7 @@ _SIGNATURES = {
     'fscnn_conf_len': (C.c_int64, [C.c_int]),
     'fscnn_confusion_from_mask': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                             C.c_void_p]),
+    'fscnn_colorize': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_void_p, C.c_void_p]),
     'fscnn_conf_to_totals': (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong),
                                        C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     'fscnn_stage_count': (C.c_int, [C.c_void_p]),

@@ -142,6 +142,12 @@ int fscnn_confusion_from_mask(const void* d_pred, int pred_dtype, const void* d_
 int fscnn_conf_to_totals(const long long* h_conf, int num_classes, long long* h_inter, long long* h_union,
                          long long* h_correct, long long* h_label);
 
+/* The step right after the path: replaces get_color_pallete (utils/visualize.py:7-36, a
+ * PIL palette on the host) with d_rgb[p] = palette[d_mask[p] & 255] on the device.  h_palette768 is HOST memory,
+ * 256 x (R,G,B); d_rgb is [n_pixels][3] uint8. */
+int fscnn_colorize(const void* d_mask, int mask_dtype, int64_t n_pixels, const unsigned char* h_palette768,
+                   unsigned char* d_rgb, void* stream);
+
 /* ---- test / profiling hooks ---------------------------------------------------------- */
 
 /* Number of pipeline stages and their names ("stem", "l2d.dsconv1", ... "head"). */

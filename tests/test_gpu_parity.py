@@ -289,3 +289,12 @@ def test_argmax_pruning_is_exact_on_adversarial_logits():
     sd['classifier.conv.1.bias'] = np.zeros(nc, np.float32)
     model = build_model(sd, nc, False, DEV)
     assert int(model.predict(xd).max()) == 0
+
+
+def test_colorize_kernel():
+    from utils.visualize import colorize, palette_for
+    rng = np.random.RandomState(2)
+    for dt in (torch.uint8, torch.int64):
+        m = torch.from_numpy(rng.randint(0, 19, size=(2, 37, 53)).astype(np.int64)).to(dt).to(DEV)
+        rgb = colorize(m, 'citys').cpu().numpy()
+        assert np.array_equal(rgb, palette_for('citys')[m.cpu().numpy().astype(np.int64)])

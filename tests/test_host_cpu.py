@@ -106,3 +106,16 @@ def test_conf_to_totals_host_function():
         o.update(pred, label)
         assert np.array_equal(inter, o.total_inter) and np.array_equal(union, o.total_union)
         assert (correct.value, labeled.value) == (o.total_correct, o.total_label)
+
+
+def test_palette_output_matches_reference_tables():
+    """get_color_pallete keeps the reference contract (PIL 'P' image + dataset palette, utils/visualize.py:7-36)."""
+    from utils.visualize import get_color_pallete, palette_for
+    mask = np.arange(19, dtype=np.int64).reshape(1, 19).repeat(3, 0)
+    img = get_color_pallete(mask, 'citys')
+    assert img.mode == 'P' and img.size == (19, 3)
+    rgb = np.asarray(img.convert('RGB'))
+    assert tuple(rgb[0, 0]) == (128, 64, 128) and tuple(rgb[0, 13]) == (0, 0, 142) and tuple(rgb[0, 18]) == (119, 11, 32)
+    voc = palette_for('tusimple')
+    assert tuple(voc[0]) == (0, 0, 0) and tuple(voc[1]) == (128, 0, 0) and tuple(voc[2]) == (0, 128, 0) and tuple(voc[15]) == (192, 128, 128)
+    assert tuple(np.asarray(get_color_pallete(np.array([[1, 2]]), 'tusimple').convert('RGB'))[0, 1]) == (0, 128, 0)
