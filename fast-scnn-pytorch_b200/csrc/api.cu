@@ -94,7 +94,7 @@ struct fscnn_ctx {
         size_t ffm_wd, ffm_bd, ffm_wcat, ffm_bcat;
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
-        size_t bn_we_img[9], bn_wp_img[9];                  // bf16 tcgen05 operand images (offsets still in floats)
+        size_t bn_we_img[9], bn_wp_img[9], bn_tab_img[9];   // bf16 tcgen05 operand images + constant tables (offsets still in floats)
         size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8;
     } off{};
     // device pointers resolved by load_weights
@@ -103,6 +103,7 @@ struct fscnn_ctx {
     BneckW bn[9]{};
     const bf16* bn_we_img[9]{};
     const bf16* bn_wp_img[9]{};
+    const unsigned char* bn_tab_img[9]{};
     const bf16* ds_wp_img[4]{};
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
@@ -219,6 +220,7 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
             const int ci = kBnecks[i].cin, ce = 6 * ci, co = kBnecks[i].cout;
             f.bn_we_img[i] = take((size_t)ce * ci / 2);
             f.bn_wp_img[i] = take((size_t)co * ce / 2);
+            f.bn_tab_img[i] = take((bottleneck_tc_tab_bytes(ci, co) + 3) / 4);
         }
     if (c->prec == FSCNN_PREC_BF16) {
         for (int i = 0; i < 4; ++i) f.ds_wp_img[i] = take((size_t)dss[i].cin * dss[i].cout / 2);
@@ -336,7 +338,7 @@ cudaError_t bottleneck_dispatch<float>(fscnn_ctx* c, int i, const float* in, flo
 template <>
 cudaError_t bottleneck_dispatch<bf16>(fscnn_ctx* c, int i, const bf16* in, bf16* out, int m, int hi, int wi, int ho, int wo,
                                       cudaStream_t s) {
-    return launch_bottleneck_tc(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn[i], c->bn_we_img[i],
+    return launch_bottleneck_tc(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn_tab_img[i], c->bn_we_img[i],
                                 c->bn_wp_img[i], out, m, hi, wi, ho, wo, s);
 }
 
@@ -508,6 +510,10 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
             L.fold_umma(p + ".2", p + ".3", co, ce, co, chunk, wp_img);                 // project: chunks of `chunk` columns
             c->bn_we_img[i] = we_img;
             c->bn_wp_img[i] = wp_img;
+            unsigned char* tab = reinterpret_cast<unsigned char*>(P + f.bn_tab_img[i]);
+            if (!L.err && launch_pack_bneck_tab(c->bn[i], ce, co, tab, L.s) != cudaSuccess)
+                L.err = fail(FSCNN_ECUDA, "table pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            c->bn_tab_img[i] = tab;
         }
     }
     for (int i = 0; i < 4; ++i) {

@@ -126,6 +126,16 @@ __device__ __forceinline__ void store_vec(T* p, const float* v) {
     else Act<T>::st1(p, v[0]);
 }
 
+// SM count of the current device (persistent kernels size their grid with it)
+inline int num_sms() {
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& v = cached[dev & 63];
+    if (!v && (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)) v = 148;
+    return v;
+}
+
 // Opt a kernel into `bytes` of dynamic shared memory once per device (the attribute is per context).
 template <typename F>
 inline cudaError_t ensure_dyn_smem(F* func, size_t bytes, unsigned long long& done_mask) {

@@ -75,7 +75,10 @@ cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* va
 // we_img: expand weights [6cin x cin] in chunks of CE rows; wp_img: project weights [cout x 6cin] in chunks of CE columns,
 // CE = bottleneck_tc_chunk(stride)
 int bottleneck_tc_chunk(int stride);
-cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const BneckW& w, const bf16* we_img,
+// tab_img: the constant tables packed by launch_pack_bneck_tab (bottleneck_tc_tab_bytes(cin, cout) bytes, 16-byte aligned)
+size_t bottleneck_tc_tab_bytes(int cin, int cout);
+cudaError_t launch_pack_bneck_tab(const BneckW& w, int cexp, int cout, unsigned char* out, cudaStream_t s);
+cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 
 // wp_img: pointwise weights [cout x cin] as one chunk; wh_img (head != nullptr): head weights [round_up(nc,16) x cout]

@@ -35,6 +35,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier over `count` threads (a subset of the CTA: the compute warps of a warp-specialised kernel)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -48,6 +53,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 
 // ---- proxies / fences ----------------------------------------------------------------------------
 // generic-proxy (st.shared) writes must be fenced before the tensor core (async proxy) reads them
+// one halo tile through the tensor map of tma_host.h: coordinates {0, x0, y0, 0, n}, may be negative / out of range
+__device__ __forceinline__ void tma_load_halo(uint32_t dst_smem, const void* tmap, int x0, int y0, int n, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(0), "r"(x0), "r"(y0), "r"(0), "r"(n), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -122,6 +137,26 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ uint32_t packbf(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
+}
+// ReLU fused into the fp32 -> bf16x2 pack (F2FP.RELU.BF16.F32.PACK_AB): a -> low half, b -> high half
+__device__ __forceinline__ uint32_t packbf_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// fp32 accumulate of bf16 x bf16 products without unpacking (FHFMA.BF16 reads register halves directly; full FFMA
+// rate on sm_100a, see fma2_probe.cu).  The product of two bf16 values is exact in fp32, so this equals
+// fmaf(float(x), float(w), acc).
+__device__ __forceinline__ void fhfma_x2(float& a0, float& a1, uint32_t x, uint32_t w) {
+    const uint16_t xl = (uint16_t)x, xh = (uint16_t)(x >> 16), wl = (uint16_t)w, wh = (uint16_t)(w >> 16);
+    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(a0) : "h"(xl), "h"(wl));
+    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(a1) : "h"(xh), "h"(wh));
+}
+__device__ __forceinline__ void fhfma8(float (&acc)[8], const uint4& x, const uint4& w) {
+    fhfma_x2(acc[0], acc[1], x.x, w.x);
+    fhfma_x2(acc[2], acc[3], x.y, w.y);
+    fhfma_x2(acc[4], acc[5], x.z, w.z);
+    fhfma_x2(acc[6], acc[7], x.w, w.w);
 }
 __device__ __forceinline__ void unpackbf8(const uint4& v, float (&f)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};

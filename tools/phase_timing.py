@@ -1,5 +1,5 @@
-"""Debug utility (library built with -DFSCNN_PHASE_TIMING): prints the clock64 deltas between the phases of one CTA of
-the fused stem+dsconv1 kernel while the GPU is busy with a full batch."""
+"""Debug utility (library built with EXTRA=-DFSCNN_PHASE_TIMING): prints the clock64 deltas between the phases of one
+CTA (its second tile) of the persistent <64,64,1> bf16 bottleneck kernel while the GPU is busy with a full batch."""
 import ctypes as C
 import os
 import sys
@@ -17,11 +17,14 @@ for _ in range(3):
     model.predict(x)
 torch.cuda.synchronize()
 lib = C.CDLL(native.lib_path())
-buf = (C.c_longlong * 16)()
-assert lib.fscnn_debug_front_phases(buf) == 0
+buf = (C.c_longlong * 64)()
+assert lib.fscnn_debug_bneck_phases(buf) == 0
 t = list(buf)
-names = ['alloc/barriers', 'stage patch (+sync)', 'im2col gather (+sync)', 'stem MMAs (+wait)', 'stem epilogue (+sync)', 'depthwise (+sync)',
-         'pointwise MMAs (+wait)', 'output epilogue (+sync)', 'dealloc']
+nch = 6
+names = []
+for e in range(nch):
+    names += [f'chunk {e}: wait expand MMA', f'chunk {e}: expand epilogue (+barrier)', f'chunk {e}: depthwise (+proj wait, barrier)']
+names += ['wait last project MMA', 'output epilogue + store']
 for i, nme in enumerate(names):
-    print(f'{nme:28s} {t[i + 1] - t[i]:8d} cycles')
-print(f'{"total":28s} {t[9] - t[0]:8d} cycles')
+    print(f'{nme:44s} {t[i + 1] - t[i]:8d} cycles')
+print(f'{"total":44s} {t[len(names)] - t[0]:8d} cycles')
