@@ -57,10 +57,10 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_mma2;
     __shared__ uint32_t tmem_base_s;
-    float* Wds = reinterpret_cast<float*>(sm + C::oWd);
     float* Bds = reinterpret_cast<float*>(sm + C::oBd);
     float* Bps = reinterpret_cast<float*>(sm + C::oBp);
     const uint32_t sH = smem_u32(sm + C::oH), sA = smem_u32(sm + C::oA), sB = smem_u32(sm + C::oB), sB2 = smem_u32(sm + C::oB2);
+    const uint32_t sWd = smem_u32(sm + C::oWd);   // depthwise weights [9][CIN] as bf16 (FHFMA operands)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = blockIdx.z;
@@ -86,7 +86,8 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
         const bf16* src = ok ? in + (((size_t)n * Hi + iy) * Wi + ix) * CIN + k8 * 8 : in;
         cp_async16z(sH + pin * C::ROWB + (chunk_swz<CIN>(pin, k8) << 4), src, ok);
     }
-    for (int i = tid; i < 9 * CIN; i += kThreads) Wds[i] = __ldg(w.wd + i);
+    for (int i = tid; i < 9 * CIN / 2; i += kThreads)
+        reinterpret_cast<uint32_t*>(sm + C::oWd)[i] = packbf(__ldg(w.wd + 2 * i), __ldg(w.wd + 2 * i + 1));
     for (int i = tid; i < CIN; i += kThreads) Bds[i] = __ldg(w.bd + i);
     for (int i = tid; i < COUT; i += kThreads) Bps[i] = __ldg(w.bp + i);
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -99,24 +100,24 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
     if (CIN == 128 && STRIDE == 1) {
 #pragma unroll 1
         for (int it = tid; it < 16 * (CIN / 4); it += kThreads)
-            dw3x3_s1_col4<C::ROWB, IW>(sH, it & 15, it >> 4, Wds, CIN, Bds, sA, 0);
+            dw3x3_s1_col4<C::ROWB, IW>(sH, it & 15, it >> 4, sWd, CIN, Bds, sA, 0);
     } else {
     #pragma unroll 1
         for (int it = tid; it < C::NSTRIP; it += kThreads) {
             const int x = it & 15, rg = (it >> 4) % (C::TH / RPS), k8 = it / (16 * (C::TH / RPS));
-            float wk[9][8];
+            uint4 wk[9];
     #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float4 a = *reinterpret_cast<const float4*>(Wds + t * CIN + k8 * 8);
-                const float4 b = *reinterpret_cast<const float4*>(Wds + t * CIN + k8 * 8 + 4);
-                wk[t][0] = a.x; wk[t][1] = a.y; wk[t][2] = a.z; wk[t][3] = a.w;
-                wk[t][4] = b.x; wk[t][5] = b.y; wk[t][6] = b.z; wk[t][7] = b.w;
-            }
+            for (int t = 0; t < 9; ++t) wk[t] = lds128(sWd + (t * CIN + k8 * 8) * 2);
             float acc[RPS][8];
+            {
+                const float4 ba = *reinterpret_cast<const float4*>(Bds + k8 * 8);
+                const float4 bb = *reinterpret_cast<const float4*>(Bds + k8 * 8 + 4);
     #pragma unroll
-            for (int o = 0; o < RPS; ++o)
-    #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[o][c] = Bds[k8 * 8 + c];
+                for (int o = 0; o < RPS; ++o) {
+                    acc[o][0] = ba.x; acc[o][1] = ba.y; acc[o][2] = ba.z; acc[o][3] = ba.w;
+                    acc[o][4] = bb.x; acc[o][5] = bb.y; acc[o][6] = bb.z; acc[o][7] = bb.w;
+                }
+            }
             constexpr int NR = (RPS - 1) * STRIDE + 3;
     #pragma unroll
             for (int r = 0; r < NR; ++r) {
@@ -124,24 +125,19 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
     #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int pin = iy * IW + x * STRIDE + kx;
-                    float f[8];
-                    unpackbf8(lds128(sH + pin * C::ROWB + (chunk_swz<CIN>(pin, k8) << 4)), f);
+                    const uint4 v = lds128(sH + pin * C::ROWB + (chunk_swz<CIN>(pin, k8) << 4));
     #pragma unroll
                     for (int o = 0; o < RPS; ++o) {
                         const int ky = r - o * STRIDE;
-                        if (ky >= 0 && ky < 3) {
-    #pragma unroll
-                            for (int c = 0; c < 8; ++c) acc[o][c] = fmaf(f[c], wk[ky * 3 + kx][c], acc[o][c]);
-                        }
+                        if (ky >= 0 && ky < 3) fhfma8(acc[o], v, wk[ky * 3 + kx]);
                     }
                 }
             }
     #pragma unroll
             for (int o = 0; o < RPS; ++o) {
                 const int p = (RPS * rg + o) * 16 + x;
-                sts128(sA + ((k8 * 16 + (p >> 3)) << 7) + ((p & 7) << 4), packbf(relu(acc[o][0]), relu(acc[o][1])),
-                       packbf(relu(acc[o][2]), relu(acc[o][3])), packbf(relu(acc[o][4]), relu(acc[o][5])),
-                       packbf(relu(acc[o][6]), relu(acc[o][7])));
+                sts128(sA + ((k8 * 16 + (p >> 3)) << 7) + ((p & 7) << 4), packbf_relu(acc[o][0], acc[o][1]),
+                       packbf_relu(acc[o][2], acc[o][3]), packbf_relu(acc[o][4], acc[o][5]), packbf_relu(acc[o][6], acc[o][7]));
             }
         }
     }
@@ -181,10 +177,13 @@ dsconv_tc_kernel(const bf16* __restrict__ in, DsW w, const bf16* __restrict__ wp
 #pragma unroll
         for (int c0 = 0; c0 < CH; c0 += 8) {
             const int co = half * CH + c0;
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = relu(__uint_as_float(r[c0 + i]) + Bps[co + i]);
-            const uint32_t a = packbf(v[0], v[1]), b = packbf(v[2], v[3]), c = packbf(v[4], v[5]), d = packbf(v[6], v[7]);
+            const float4 ba = *reinterpret_cast<const float4*>(Bps + co);
+            const float4 bb = *reinterpret_cast<const float4*>(Bps + co + 4);
+            const uint32_t* q8 = r + c0;
+            const uint32_t a = packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y);
+            const uint32_t b = packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w);
+            const uint32_t c = packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y);
+            const uint32_t d = packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w);
             if (!HEAD) {
                 if (live) *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * COUT + co) = make_uint4(a, b, c, d);
             } else {

@@ -31,7 +31,7 @@ ffm_tc_kernel(const bf16* __restrict__ higher, const bf16* __restrict__ lower, F
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t bar_w, bar_mma;
     __shared__ uint32_t tmem_base_s;
-    float* Wds = reinterpret_cast<float*>(sm + oWd);
+    const uint32_t sWd = smem_u32(sm + oWd);   // depthwise weights [9][128] as bf16 (FHFMA operands)
     float* Bds = reinterpret_cast<float*>(sm + oBd);
     float* Bcs = reinterpret_cast<float*>(sm + oBc);
     int4* tab = reinterpret_cast<int4*>(sm + oTab);
@@ -69,7 +69,8 @@ ffm_tc_kernel(const bf16* __restrict__ higher, const bf16* __restrict__ lower, F
         }
         tab[pin] = t;
     }
-    for (int i = tid; i < 9 * kCL; i += kThreads) Wds[i] = __ldg(w.wd + i);
+    for (int i = tid; i < 9 * kCL / 2; i += kThreads)
+        reinterpret_cast<uint32_t*>(sm + oWd)[i] = packbf(__ldg(w.wd + 2 * i), __ldg(w.wd + 2 * i + 1));
     if (tid < kCL) { Bds[tid] = __ldg(w.bd + tid); Bcs[tid] = __ldg(w.bcat + tid); }
     __syncthreads();
 
@@ -105,7 +106,7 @@ ffm_tc_kernel(const bf16* __restrict__ higher, const bf16* __restrict__ lower, F
     // depthwise 3x3 + bias + ReLU on U -> A columns 64..191 (one output column x 4 channels per item)
 #pragma unroll 1
     for (int it = tid; it < 16 * (kCL / 4); it += kThreads)
-        dw3x3_s1_col4<kCL * 2, kIW>(sU, it & 15, it >> 4, Wds, kCL, Bds, sA, 8);
+        dw3x3_s1_col4<kCL * 2, kIW>(sU, it & 15, it >> 4, sWd, kCL, Bds, sA, 8);
     fence_async_proxy();
     __syncthreads();
 
@@ -137,10 +138,14 @@ ffm_tc_kernel(const bf16* __restrict__ higher, const bf16* __restrict__ lower, F
             bf16* op = out + (((size_t)n * Hh + oy) * Wh + ox) * kCO + half * 64;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 8) {
-                float v[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = relu(__uint_as_float(r[c0 + i]) + Bcs[half * 64 + c0 + i]);
-                *reinterpret_cast<uint4*>(op + c0) = make_uint4(packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
+                const float4 ba = *reinterpret_cast<const float4*>(Bcs + half * 64 + c0);
+                const float4 bb = *reinterpret_cast<const float4*>(Bcs + half * 64 + c0 + 4);
+                const uint32_t* q8 = r + c0;
+                *reinterpret_cast<uint4*>(op + c0) =
+                    make_uint4(packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
+                               packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
+                               packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
+                               packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
             }
         }
     }

@@ -31,7 +31,7 @@ constexpr int oA = 2 * kBuf;                           // A[568 rows][64 B], row
 constexpr int kABytes = 71 * 512;                      // 71 groups of 8 rows (the 5th MMA tile's unused rows read into the weights)
 constexpr int oWs = oA + kABytes;                      // stem weight image 32 x 32 bf16
 constexpr int oWp = oWs + 2048;                        // pointwise image 48 x 32 bf16
-constexpr int oWd = oWp + 3072;                        // fp32 [9][32]
+constexpr int oWd = oWp + 3072;                        // depthwise weights [9][32], bf16 in the first 576 bytes (FHFMA operands)
 constexpr int oBs = oWd + 9 * 32 * 4;                  // stem bias [32]
 constexpr int oBd = oBs + 128;                         // dw bias [32]
 constexpr int oBp = oBd + 128;                         // pw bias [48]
@@ -84,24 +84,22 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t bar_stem, bar_pw;
     __shared__ uint32_t tmem_base_s;
-    float* Wds = reinterpret_cast<float*>(sm + oWd);
     float* Bss = reinterpret_cast<float*>(sm + oBs);
     float* Bds = reinterpret_cast<float*>(sm + oBd);
     float* Bps = reinterpret_cast<float*>(sm + oBp);
-    const uint32_t sBuf = smem_u32(sm + oBuf), sA = smem_u32(sm + oA), sWs = smem_u32(sm + oWs), sWp = smem_u32(sm + oWp);
+    const uint32_t sBuf = smem_u32(sm + oBuf), sA = smem_u32(sm + oA), sWs = smem_u32(sm + oWs), sWp = smem_u32(sm + oWp), sWd = smem_u32(sm + oWd);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) { mbar_init(&bar_stem, 1); mbar_init(&bar_pw, 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
     if (tid < 128) reinterpret_cast<uint4*>(sm + oWs)[tid] = __ldg(reinterpret_cast<const uint4*>(ws_img) + tid);
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWp)[tid] = __ldg(reinterpret_cast<const uint4*>(wp_img) + tid);
-    for (int i = tid; i < 9 * 32; i += kThreads) Wds[i] = __ldg(w.wd + i);
+    if (tid < 9 * 32 / 2) reinterpret_cast<uint32_t*>(sm + oWd)[tid] = packbf(__ldg(w.wd + 2 * tid), __ldg(w.wd + 2 * tid + 1));
     if (tid < 32) { Bss[tid] = __ldg(bs + tid); Bds[tid] = __ldg(w.bd + tid); }
     if (tid < 48) Bps[tid] = __ldg(w.bp + tid);
 
     // asynchronous fetch of tile t's input patch into buffer b (no registers, no waiting)
-    auto prefetch = [&](int t, int b) {
-        const int txi = t % tiles_x, tyi = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+    auto prefetch = [&](int txi, int tyi, int n, int b) {
         const int iy0 = 4 * (tyi * 8) - 2, ix0 = 4 * (txi * 16) - 2;
         const uint32_t dst0 = sBuf + b * kBuf;
         if (FMT == FSCNN_IN_F32_NCHW) {
@@ -169,8 +167,17 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    // tile coordinates advance by gridDim.x tiles per iteration: decomposed once, then carried (no divisions in the loop)
     int t = blockIdx.x;
-    if (t < ntiles) prefetch(t, 0);
+    const int gstep = gridDim.x;
+    const int step_x = gstep % tiles_x, step_y = (gstep / tiles_x) % tiles_y, step_n = gstep / (tiles_x * tiles_y);
+    int nx_x = t % tiles_x, nx_y = (t / tiles_x) % tiles_y, nx_n = t / (tiles_x * tiles_y);   // coordinates of the NEXT tile to fetch
+    auto advance = [&]() {
+        nx_x += step_x; if (nx_x >= tiles_x) { nx_x -= tiles_x; ++nx_y; }
+        nx_y += step_y; if (nx_y >= tiles_y) { nx_y -= tiles_y; ++nx_n; }
+        nx_n += step_n;
+    };
+    if (t < ntiles) prefetch(nx_x, nx_y, nx_n, 0);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -179,13 +186,14 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
 #pragma unroll 1
     for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
         const int b = it & 1;
-        const int txi = t % tiles_x, tyi = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+        const int txi = nx_x, tyi = nx_y, n = nx_n;
+        advance();
         const int oy0 = tyi * 8, ox0 = txi * 16;
         const int sy0 = 2 * oy0 - 1, sx0 = 2 * ox0 - 1;      // first stem pixel of the halo tile (may be -1)
         const uint32_t sIn = sBuf + b * kBuf;                 // this tile's patch; later its E tile
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                       // patch of tile t visible; everything of tile t-1 retired
-        if (t + gridDim.x < ntiles) prefetch(t + gridDim.x, b ^ 1);   // overlaps the whole tile
+        if (t + gstep < ntiles) prefetch(nx_x, nx_y, nx_n, b ^ 1);   // overlaps the whole tile
 
         // ---- im2col gather of the 561 stem pixels into A; k = ci*9 + ky*3 + kx.  Thread = (row within the MMA tile,
         //      half of the taps); the half is warp-uniform and each variant unrolls to constant tap offsets ----
@@ -223,17 +231,21 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
             tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + TM_STEM + mt * 32, r);
             tmem_ld_wait();
             if (m < SPIX) {
+                if (ok) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int h2 = 0; h2 < 4; ++h2) {
-                        const int c = g * 8 + 2 * h2;
-                        const float a = ok ? relu(__uint_as_float(r[c]) + Bss[c]) : 0.f;
-                        const float b2 = ok ? relu(__uint_as_float(r[c + 1]) + Bss[c + 1]) : 0.f;
-                        pk[h2] = packbf(a, b2);
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 ba = *reinterpret_cast<const float4*>(Bss + g * 8);
+                        const float4 bb = *reinterpret_cast<const float4*>(Bss + g * 8 + 4);
+                        const uint32_t* q8 = r + g * 8;
+                        sts128(sIn + m * 64 + ((g ^ ((m >> 1) & 3)) << 4),
+                               packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
+                               packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
+                               packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
+                               packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
                     }
-                    sts128(sIn + m * 64 + ((g ^ ((m >> 1) & 3)) << 4), pk[0], pk[1], pk[2], pk[3]);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) sts128(sIn + m * 64 + ((g ^ ((m >> 1) & 3)) << 4), 0u, 0u, 0u, 0u);
                 }
             }
         }
@@ -244,37 +256,37 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         {
             const int xq = tid & 15, rg = (tid >> 4) & 3, k8 = tid >> 6;
             float acc[2][8];
+            {
+                const float4 ba = *reinterpret_cast<const float4*>(Bds + k8 * 8);
+                const float4 bb = *reinterpret_cast<const float4*>(Bds + k8 * 8 + 4);
 #pragma unroll
-            for (int o = 0; o < 2; ++o)
+                for (int o = 0; o < 2; ++o) {
+                    acc[o][0] = ba.x; acc[o][1] = ba.y; acc[o][2] = ba.z; acc[o][3] = ba.w;
+                    acc[o][4] = bb.x; acc[o][5] = bb.y; acc[o][6] = bb.z; acc[o][7] = bb.w;
+                }
+            }
+            uint4 wv[9];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[o][c] = Bds[k8 * 8 + c];
+            for (int tp = 0; tp < 9; ++tp) wv[tp] = lds128(sWd + (tp * 32 + k8 * 8) * 2);
 #pragma unroll
             for (int r = 0; r < 5; ++r) {
                 const int sr = 4 * rg + r;
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int m = sr * SW + 2 * xq + kx;
-                    float f[8];
-                    unpackbf8(lds128(sIn + m * 64 + ((k8 ^ ((m >> 1) & 3)) << 4)), f);
+                    const uint4 v = lds128(sIn + m * 64 + ((k8 ^ ((m >> 1) & 3)) << 4));
 #pragma unroll
                     for (int o = 0; o < 2; ++o) {
                         const int ky = r - 2 * o;
-                        if (ky >= 0 && ky < 3) {
-                            const float4 wa = *reinterpret_cast<const float4*>(Wds + (ky * 3 + kx) * 32 + k8 * 8);
-                            const float4 wb = *reinterpret_cast<const float4*>(Wds + (ky * 3 + kx) * 32 + k8 * 8 + 4);
-                            acc[o][0] = fmaf(f[0], wa.x, acc[o][0]); acc[o][1] = fmaf(f[1], wa.y, acc[o][1]);
-                            acc[o][2] = fmaf(f[2], wa.z, acc[o][2]); acc[o][3] = fmaf(f[3], wa.w, acc[o][3]);
-                            acc[o][4] = fmaf(f[4], wb.x, acc[o][4]); acc[o][5] = fmaf(f[5], wb.y, acc[o][5]);
-                            acc[o][6] = fmaf(f[6], wb.z, acc[o][6]); acc[o][7] = fmaf(f[7], wb.w, acc[o][7]);
-                        }
+                        if (ky >= 0 && ky < 3) fhfma8(acc[o], v, wv[ky * 3 + kx]);
                     }
                 }
             }
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
                 const int p = (2 * rg + o) * 16 + xq;
-                sts128(sA + a_rg_off(p, k8), packbf(relu(acc[o][0]), relu(acc[o][1])), packbf(relu(acc[o][2]), relu(acc[o][3])),
-                       packbf(relu(acc[o][4]), relu(acc[o][5])), packbf(relu(acc[o][6]), relu(acc[o][7])));
+                sts128(sA + a_rg_off(p, k8), packbf_relu(acc[o][0], acc[o][1]), packbf_relu(acc[o][2], acc[o][3]),
+                       packbf_relu(acc[o][4], acc[o][5]), packbf_relu(acc[o][6], acc[o][7]));
             }
         }
         fence_async_proxy();
@@ -303,10 +315,14 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
                 bf16* op = out + (((size_t)n * H2 + oy) * W2 + ox) * 48 + half * 24;
 #pragma unroll
                 for (int c0 = 0; c0 < 24; c0 += 8) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = relu(__uint_as_float(r[c0 + i]) + Bps[half * 24 + c0 + i]);
-                    *reinterpret_cast<uint4*>(op + c0) = make_uint4(packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
+                    const float4 ba = *reinterpret_cast<const float4*>(Bps + half * 24 + c0);
+                    const float4 bb = *reinterpret_cast<const float4*>(Bps + half * 24 + c0 + 4);
+                    const uint32_t* q8 = r + c0;
+                    *reinterpret_cast<uint4*>(op + c0) =
+                        make_uint4(packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
+                                   packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
+                                   packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
+                                   packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
                 }
             }
         }
