@@ -95,7 +95,7 @@ struct fscnn_ctx {
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
         size_t bn_we_img[9], bn_wp_img[9], bn_tab_img[9];   // bf16 tcgen05 operand images + constant tables (offsets still in floats)
-        size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8;
+        size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8, stem_imgx, stem_imgx_u8;
     } off{};
     // device pointers resolved by load_weights
     StemW stem{};
@@ -110,6 +110,8 @@ struct fscnn_ctx {
     const bf16* stem_img = nullptr;
     bf16* stem_img_u8 = nullptr;
     float* stem_b_u8 = nullptr;
+    bf16* stem_imgx = nullptr;      // fused front kernel: RGBX images (fp32 input / uint8 input with folded normalisation)
+    bf16* stem_imgx_u8 = nullptr;
     PpmW ppm{};
     FfmW ffm{};
     HeadW head{};
@@ -229,6 +231,8 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
         f.stem_img = take((size_t)32 * 32 / 2);
         f.stem_img_u8 = take((size_t)32 * 32 / 2);
         f.stem_b_u8 = take(32);
+        f.stem_imgx = take((size_t)3 * 32 * 16 / 2);
+        f.stem_imgx_u8 = take((size_t)3 * 32 * 16 / 2);
     }
     c->packed_floats = o;
 }
@@ -382,11 +386,12 @@ bool front_fused<bf16>(fscnn_ctx* c, const void* x, bf16* out_ds1, int m, const 
     const bool u8 = c->in.format == FSCNN_IN_U8_NHWC;
     if (u8 && c->in_dirty) {
         *e = launch_stem_refold(c->stem.w, c->stem.b, c->in, c->stem_img_u8, c->stem_b_u8, s);
+        if (*e == cudaSuccess) *e = launch_stem_pack_rgbx(c->stem.w, c->stem.b, c->in, 1, c->stem_imgx_u8, c->stem_b_u8, s);
         if (*e != cudaSuccess) return true;
         c->in_dirty = false;
-        c->launches += 1;
+        c->launches += 2;
     }
-    *e = launch_l2d_front_tc(x, c->in, u8 ? c->stem_img_u8 : c->stem_img, u8 ? c->stem_b_u8 : c->stem.b, c->ds[0], c->ds_wp_img[0],
+    *e = launch_l2d_front_tc(x, c->in, u8 ? c->stem_imgx_u8 : c->stem_imgx, u8 ? c->stem_b_u8 : c->stem.b, c->ds[0], c->ds_wp_img[0],
                              out_ds1, m, d.h, d.w, d.h1, d.w1, d.h2, d.w2, s);
     return true;
 }
@@ -478,6 +483,10 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         c->stem_img = img;
         c->stem_img_u8 = reinterpret_cast<bf16*>(P + f.stem_img_u8);
         c->stem_b_u8 = P + f.stem_b_u8;
+        c->stem_imgx = reinterpret_cast<bf16*>(P + f.stem_imgx);
+        c->stem_imgx_u8 = reinterpret_cast<bf16*>(P + f.stem_imgx_u8);
+        if (!L.err && launch_stem_pack_rgbx(c->stem.w, c->stem.b, c->in, 0, c->stem_imgx, nullptr, L.s) != cudaSuccess)
+            L.err = fail(FSCNN_ECUDA, "stem pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         c->in_dirty = true;
     }
     const struct { const char* p; int cin, cout; } dss[4] = {{"learning_to_downsample.dsconv1", 32, 48},

@@ -80,6 +80,34 @@ __global__ void stem_refold_kernel(const float* __restrict__ w, const float* __r
     bias[n] = acc;
 }
 
+// Stem weights for the gather-free fused kernel (l2d_front_tc.cu): one 32 x 16 B-operand image per kernel row ky with
+// k = kx * 4 + c over 4 pixels x RGBX; the 4th pixel and the 4th channel get zero weights.  w is the BN-folded
+// [27][32] table (k = ci*9 + ky*3 + kx).  With `norm` the uint8 ToTensor + Normalize is folded in as in
+// stem_refold_kernel and the matching bias is written.
+__global__ void stem_pack_rgbx_kernel(const float* __restrict__ w, const float* __restrict__ b, StemIn in, int norm,
+                                      __nv_bfloat16* __restrict__ img, float* __restrict__ bias) {
+    const int n = threadIdx.x;   // 32 output channels
+    if (n >= 32) return;
+    float acc = b[n];
+    for (int ky = 0; ky < 3; ++ky)
+        for (int k = 0; k < 16; ++k) {
+            const int kx = k >> 2, c = k & 3;
+            float v = 0.f;
+            if (kx < 3 && c < 3) {
+                const float wv = w[(c * 9 + ky * 3 + kx) * 32 + n];
+                v = norm ? wv * (in.inv_std[c] * (1.f / 255.f)) : wv;
+                if (norm) acc -= wv * in.mean[c] * in.inv_std[c];
+            }
+            img[ky * 512 + ((k >> 3) * 4 + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(v);
+        }
+    if (bias) bias[n] = acc;
+}
+
+cudaError_t launch_stem_pack_rgbx(const float* w, const float* b, const StemIn& in, int norm, bf16* img, float* bias, cudaStream_t s) {
+    stem_pack_rgbx_kernel<<<1, 32, 0, s>>>(w, b, in, norm, img, bias);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stem_refold(const float* w, const float* b, const StemIn& in, bf16* img, float* bias, cudaStream_t s) {
     stem_refold_kernel<<<1, 32, 0, s>>>(w, b, in, img, bias);
     return cudaGetLastError();

@@ -96,7 +96,9 @@ cudaError_t launch_stem_tc(const void* x, const StemIn& in, const bf16* w_img, c
 
 // uint8 input: stem weights / bias with ToTensor + Normalize folded in (run when the input format changes)
 cudaError_t launch_stem_refold(const float* w, const float* b, const StemIn& in, bf16* img, float* bias, cudaStream_t s);
-// stem + dsconv1 fused (the stem's output never reaches HBM); ws_img / wp_img as for launch_stem_tc / launch_dsconv_tc
+// stem images of the fused kernel: 3 x (32 x 16) bf16, k = kx*4 + c over RGBX pixels (norm: uint8 normalisation folded in, bias written)
+cudaError_t launch_stem_pack_rgbx(const float* w, const float* b, const StemIn& in, int norm, bf16* img, float* bias, cudaStream_t s);
+// stem + dsconv1 fused (the stem's output never reaches HBM); ws_img from launch_stem_pack_rgbx, wp_img as for launch_dsconv_tc
 cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_img, const float* bs, const DsW& w,
                                 const bf16* wp_img, bf16* out, int n, int h, int wd, int h1, int w1, int h2, int w2, cudaStream_t s);
 

@@ -6,10 +6,15 @@
 //
 // One tile = 8x16 dsconv1 output pixels; it needs the 17x33 stem pixels around them (halo of the
 // stride-2 depthwise conv), i.e. a 35x67 input patch.  Per tile:
-//   patch (fp32 NCHW planes, or raw uint8 HWC rows with ToTensor/Normalize folded into the stem weights)
-//   -> im2col gather into A[561 x 32] -> 10 MMAs into TMEM[5][128 x 32] -> bias, ReLU, zero outside the
-//   stem image -> bf16 E[561][32] (over the dead patch) -> depthwise s2 (fp32) -> A2[128 x 32] (over the
-//   dead A) -> 2 MMAs [128 x 48] -> bias, ReLU -> bf16 NHWC.
+//   raw patch (fp32 NCHW planes, or raw uint8 HWC rows with ToTensor/Normalize folded into the stem weights)
+//   -> repacked once as bf16 RGBX pixels (8 bytes each), even and odd patch rows in separate planes of pitch 544 B.
+//   The stem's im2col matrix is then never built: with 4-channel pixels a stride-2 step is exactly 16 bytes, the
+//   row pitch of a SWIZZLE_NONE core matrix, so row (sr, sc) of the A operand of kernel row ky IS the 32 bytes at
+//   plane[(2 sr + ky)] + 16 sc (4 pixels x 4 channels = K 16; the 4th pixel and 4th channel meet zero weights).
+//   Consecutive rows overlap by half (LBO = 16 B, SBO = 128 B; verified by tc_probe.cu), stem rows are 34 A rows apart.
+//   -> 15 MMAs (5 row tiles x 3 kernel rows, K = 16, N = 32) into TMEM -> bias, ReLU, zero outside the stem image
+//   -> bf16 E[561][32] (over the dead raw patch) -> depthwise s2 (FHFMA.BF16, fp32 accumulate) -> A2[128 x 32]
+//   -> 2 MMAs [128 x 48] -> bias, ReLU -> bf16 NHWC.
 // The kernel is PERSISTENT (2 CTAs per SM, each walking tiles blockIdx.x, +gridDim.x, ...): barriers, TMEM
 // and weights are set up once, and the next tile's patch is fetched with cp.async into the other half of a
 // double buffer while the current tile computes, so the global-load latency is off the critical path.
@@ -22,22 +27,28 @@ namespace fscnn {
 
 namespace {
 constexpr int SH = 17, SW = 33, SPIX = SH * SW;       // stem pixels per tile (561)
-constexpr int NMT = 5;                                 // MMA row tiles of 128 stem pixels
+constexpr int SWP = 34, MROWS = SH * SWP;              // A rows: stem row pitch 34 (column 33 is a dummy) -> 578
+constexpr int NMT = 5;                                 // MMA row tiles of 128 A rows
 constexpr int PR = 35, PC = 67, PLD = 68;              // input patch rows / cols / pitch (fp32 planes)
 constexpr int kRW = 52;                                // uint8 input: 52 words (208 bytes) per patch row
-constexpr int kBuf = 35968;                            // one half of the double buffer: patch (28560 B) or E (561 x 64 B)
+constexpr int kBuf = 35968;                            // one half of the double buffer: raw patch (28560 B) or E (561 x 64 B)
+constexpr int kPP = SWP * 16;                          // RGBX plane row pitch: 68 pixels x 8 B = 544 B
 constexpr int oBuf = 0;
-constexpr int oA = 2 * kBuf;                           // A[568 rows][64 B], row-group-major core matrices; later A2 (8 KB)
-constexpr int kABytes = 71 * 512;                      // 71 groups of 8 rows (the 5th MMA tile's unused rows read into the weights)
-constexpr int oWs = oA + kABytes;                      // stem weight image 32 x 32 bf16
-constexpr int oWp = oWs + 2048;                        // pointwise image 48 x 32 bf16
-constexpr int oWd = oWp + 3072;                        // depthwise weights [9][32], bf16 in the first 576 bytes (FHFMA operands)
-constexpr int oBs = oWd + 9 * 32 * 4;                  // stem bias [32]
+constexpr int oP2 = 2 * kBuf;                          // RGBX planes: 18 even rows, then 17 odd rows
+constexpr int oP2o = oP2 + 18 * kPP;
+constexpr int kP2Bytes = round_up(35 * kPP, 128);
+constexpr int oA2 = oP2 + kP2Bytes;                    // A2[128 rows][64 B], row-group-major core matrices (8 KB)
+constexpr int oWs = oA2 + 8192;                        // stem weight image: 3 kernel rows x (32 x 16) bf16
+constexpr int oWp = oWs + 3072;                        // pointwise image 48 x 32 bf16
+constexpr int oWd = oWp + 3072;                        // depthwise weights [9][32] bf16 (FHFMA operands)
+constexpr int oBs = oWd + 640;                         // stem bias [32]
 constexpr int oBd = oBs + 128;                         // dw bias [32]
 constexpr int oBp = oBd + 128;                         // pw bias [48]
 constexpr int kSmem = oBp + 192;
 constexpr int TM_STEM = 0, TM_PW = NMT * 32;           // 160 + 48 columns -> allocate 256
 static_assert(kSmem <= 115600, "two CTAs per SM: 2 x (kSmem + 1 KB reserved + static) must fit 228 KB");
+// the last row tile reads A rows up to 639: they must stay inside the allocation (their results are never used)
+static_assert(oP2o + (NMT * 128 + 1) * 16 <= kSmem, "A over-read");
 
 __device__ __forceinline__ void cp_async4z(uint32_t dst, const void* src, bool valid) {
     const int sz = valid ? 4 : 0;
@@ -47,34 +58,12 @@ __device__ __forceinline__ void cp_async4z(uint32_t dst, const void* src, bool v
 __device__ __forceinline__ uint32_t a_rg_off(int m, int k8) { return (uint32_t)(m >> 3) * 512 + k8 * 128 + (m & 7) * 16; }
 }  // namespace
 
-// one 16-byte im2col piece (taps 8*KQ .. 8*KQ+7) for row `pl` of each of the five MMA tiles
-template <int FMT, int KQ>
-__device__ __forceinline__ void gather_chunk(const uint8_t* __restrict__ patch, uint32_t sA, int pl) {
-#pragma unroll
-    for (int mt = 0; mt < NMT; ++mt) {
-        const int m = mt * 128 + pl;
-        if (m >= 568) continue;
-        const int sr = m / SW, sc = m - sr * SW;
-        const bool ok = m < SPIX;
-        float v[8];
-        if (FMT == FSCNN_IN_U8_NHWC) {
-            const unsigned char* base = patch + (2 * sr) * (kRW * 4) + 2 + (2 * sc) * 3;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k = KQ * 8 + q;
-                v[q] = (ok && k < 27) ? (float)base[((k % 9) / 3) * (kRW * 4) + (k % 3) * 3 + k / 9] : 0.f;
-            }
-        } else {
-            const float* base = reinterpret_cast<const float*>(patch) + (2 * sr) * PLD + 2 * sc;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int k = KQ * 8 + q;
-                v[q] = (ok && k < 27) ? base[((k / 9) * PR + (k % 9) / 3) * PLD + k % 3] : 0.f;
-            }
-        }
-        sts128(sA + a_rg_off(m, KQ), packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
-    }
-}
+#ifdef FSCNN_PHASE_TIMING   // debug build only: clock64 stamps of the 4th tile of CTA 7
+__device__ long long g_front_phase[16];
+#define FR_STAMP(i) do { if (tid == 0 && blockIdx.x == 7 && it == 3) g_front_phase[i] = clock64(); } while (0)
+#else
+#define FR_STAMP(i) do { } while (0)
+#endif
 
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -87,12 +76,14 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
     float* Bss = reinterpret_cast<float*>(sm + oBs);
     float* Bds = reinterpret_cast<float*>(sm + oBd);
     float* Bps = reinterpret_cast<float*>(sm + oBp);
-    const uint32_t sBuf = smem_u32(sm + oBuf), sA = smem_u32(sm + oA), sWs = smem_u32(sm + oWs), sWp = smem_u32(sm + oWp), sWd = smem_u32(sm + oWd);
+    const uint32_t sBuf = smem_u32(sm + oBuf), sP2 = smem_u32(sm + oP2), sA = smem_u32(sm + oA2), sWs = smem_u32(sm + oWs), sWp = smem_u32(sm + oWp),
+                   sWd = smem_u32(sm + oWd);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) { mbar_init(&bar_stem, 1); mbar_init(&bar_pw, 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
-    if (tid < 128) reinterpret_cast<uint4*>(sm + oWs)[tid] = __ldg(reinterpret_cast<const uint4*>(ws_img) + tid);
+    if (tid < 192) reinterpret_cast<uint4*>(sm + oWs)[tid] = __ldg(reinterpret_cast<const uint4*>(ws_img) + tid);
+    for (int i = tid; i < kP2Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(sm + oP2)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad pixels stay finite
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWp)[tid] = __ldg(reinterpret_cast<const uint4*>(wp_img) + tid);
     if (tid < 9 * 32 / 2) reinterpret_cast<uint32_t*>(sm + oWd)[tid] = packbf(__ldg(w.wd + 2 * tid), __ldg(w.wd + 2 * tid + 1));
     if (tid < 32) { Bss[tid] = __ldg(bs + tid); Bds[tid] = __ldg(w.bd + tid); }
@@ -191,46 +182,63 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         const int oy0 = tyi * 8, ox0 = txi * 16;
         const int sy0 = 2 * oy0 - 1, sx0 = 2 * ox0 - 1;      // first stem pixel of the halo tile (may be -1)
         const uint32_t sIn = sBuf + b * kBuf;                 // this tile's patch; later its E tile
+        FR_STAMP(0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                       // patch of tile t visible; everything of tile t-1 retired
+        FR_STAMP(1);
         if (t + gstep < ntiles) prefetch(nx_x, nx_y, nx_n, b ^ 1);   // overlaps the whole tile
 
-        // ---- im2col gather of the 561 stem pixels into A; k = ci*9 + ky*3 + kx.  Thread = (row within the MMA tile,
-        //      half of the taps); the half is warp-uniform and each variant unrolls to constant tap offsets ----
+        FR_STAMP(2);
+        // ---- repack the raw patch as bf16 RGBX pixels, even / odd rows in separate planes (this IS the A operand) ----
         {
-            const int pl = tid & 127;
             const uint8_t* patch = sm + oBuf + b * kBuf;
-            if (tid < 128) { gather_chunk<FMT, 0>(patch, sA, pl); gather_chunk<FMT, 1>(patch, sA, pl); }
-            else           { gather_chunk<FMT, 2>(patch, sA, pl); gather_chunk<FMT, 3>(patch, sA, pl); }
+#pragma unroll 1
+            for (int i = tid; i < PR * PC; i += kThreads) {
+                const int r = i / PC, px = i - r * PC;
+                float v0, v1, v2;
+                if (FMT == FSCNN_IN_U8_NHWC) {
+                    const unsigned char* q = patch + r * (kRW * 4) + 2 + 3 * px;
+                    v0 = (float)q[0]; v1 = (float)q[1]; v2 = (float)q[2];
+                } else {
+                    const float* q = reinterpret_cast<const float*>(patch) + r * PLD + px;
+                    v0 = q[0]; v1 = q[PR * PLD]; v2 = q[2 * PR * PLD];
+                }
+                sts64(sP2 + (r & 1) * (18 * kPP) + (r >> 1) * kPP + px * 8, packbf(v0, v1), packbf(v2, 0.f));
+            }
         }
         fence_async_proxy();
         tc_fence_before_sync();
         __syncthreads();
+        FR_STAMP(3);
         if (tid == 0) {
             tc_fence_after_sync();
             constexpr uint32_t idesc = make_idesc_bf16(128, 32);
 #pragma unroll
             for (int mt = 0; mt < NMT; ++mt)
 #pragma unroll
-                for (int k16 = 0; k16 < 2; ++k16)
-                    umma_bf16_ss(tmem + TM_STEM + mt * 32, make_smem_desc(sA + mt * (16 * 512) + k16 * 256, 128, 512),
-                                 make_smem_desc(sWs + k16 * 1024, 512, 128), idesc, k16 > 0);
+                for (int ky = 0; ky < 3; ++ky)   // kernel row ky reads plane (ky & 1) from its row (ky >> 1) on; K = 16 = 4 pixels x RGBX
+                    umma_bf16_ss(tmem + TM_STEM + mt * 32,
+                                 make_smem_desc(sP2 + (ky & 1) * (18 * kPP) + (ky >> 1) * kPP + mt * (128 * 16), 16, 128),
+                                 make_smem_desc(sWs + ky * 1024, 512, 128), idesc, ky > 0);
             umma_commit(&bar_stem);
         }
         mbar_wait(&bar_stem, it & 1);
         tc_fence_after_sync();
+        FR_STAMP(4);
 
         // ---- stem epilogue: bias, ReLU, zero outside the stem image (the depthwise conv pads with zeros) -> E (over the patch) ----
         for (int task = warp; task < NMT * 4; task += kThreads / 32) {
             const int mt = task >> 2, q = task & 3;
-            const int m = mt * 128 + q * 32 + lane;
-            const int sr = m / SW, sc = m - sr * SW;
+            const int ma = mt * 128 + q * 32 + lane;             // A row: stem row pitch 34
+            const int sr = ma / SWP, sc = ma - sr * SWP;
+            const int m = sr * SW + sc;                           // E row
+            const bool row = ma < MROWS && sc < SW;
             const int sy = sy0 + sr, sx = sx0 + sc;
-            const bool ok = m < SPIX && sy >= 0 && sy < H1 && sx >= 0 && sx < W1;
+            const bool ok = row && sy >= 0 && sy < H1 && sx >= 0 && sx < W1;
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + TM_STEM + mt * 32, r);
             tmem_ld_wait();
-            if (m < SPIX) {
+            if (row) {
                 if (ok) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -251,8 +259,9 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         }
         tc_fence_before_sync();
         __syncthreads();
+        FR_STAMP(5);
 
-        // ---- depthwise 3x3 stride 2 (fp32): strip = (column x, 2-row group, 8-channel chunk) -> A2 (over the dead A) ----
+        // ---- depthwise 3x3 stride 2 (fp32): strip = (column x, 2-row group, 8-channel chunk) -> A2 ----
         {
             const int xq = tid & 15, rg = (tid >> 4) & 3, k8 = tid >> 6;
             float acc[2][8];
@@ -292,6 +301,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         fence_async_proxy();
         tc_fence_before_sync();
         __syncthreads();
+        FR_STAMP(6);
         if (tid == 0) {
             tc_fence_after_sync();
             constexpr uint32_t idesc = make_idesc_bf16(128, 48);
@@ -303,6 +313,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         }
         mbar_wait(&bar_pw, it & 1);
         tc_fence_after_sync();
+        FR_STAMP(7);
         {
             const int q = warp & 3, half = warp >> 2;           // 24 channels per warp half
             const int p = q * 32 + lane;
@@ -327,11 +338,18 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
             }
         }
         tc_fence_before_sync();   // TMEM reads of this tile are ordered before the next tile's MMAs by the loop-top barrier
+        FR_STAMP(8);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
+
+#ifdef FSCNN_PHASE_TIMING
+extern "C" int fscnn_debug_front_phases(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_front_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_img, const float* bs, const DsW& w,
                                 const bf16* wp_img, bf16* out, int n, int h, int wd, int h1, int w1, int h2, int w2, cudaStream_t s) {

@@ -111,6 +111,43 @@ __global__ void probe_strided(const __nv_bfloat16* A /*[128][K]*/, const __nv_bf
 }
 
 // throughput: `reps` x (M=128, N=256, K=64) MMAs per CTA on garbage data, then `reps` x32 TMEM loads per warp
+// Overlapping-window A operand: row m of the 128 x 16 tile is the 32 bytes at S + 16*m of a linear bf16 array, i.e.
+// the second core matrix along K starts 16 bytes after the first (LBO = 16 B, SBO = 128 B) and consecutive rows
+// overlap by half.  This is what lets a stride-2 3x3 convolution over 4-channel bf16 pixels read its im2col rows
+// straight out of the input patch (l2d_front_tc.cu).
+__global__ void probe_overlap(const __nv_bfloat16* S /*[8*130]*/, const __nv_bfloat16* B /*[16][16]*/, float* D) {
+    __shared__ __align__(128) uint8_t sa[130 * 16];
+    __shared__ __align__(128) uint8_t sb[16 * 16 * 2];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 130; i += blockDim.x) reinterpret_cast<uint4*>(sa)[i] = reinterpret_cast<const uint4*>(S)[i];
+    for (int i = tid; i < 16 * 2; i += blockDim.x) {
+        const int n = i / 2, k8 = i % 2;
+        *reinterpret_cast<uint4*>(sb + (k8 * 2 + n / 8) * 128 + (n % 8) * 16) = *reinterpret_cast<const uint4*>(B + n * 16 + k8 * 8);
+    }
+    if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(&tmem_base_s, 32); tmem_relinquish(); }
+    fence_async_proxy();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t taddr = tmem_base_s;
+    if (tid == 0) {
+        umma_bf16_ss(taddr, make_smem_desc(smem_u32(sa), 16, 128), make_smem_desc(smem_u32(sb), 256, 128), make_idesc_bf16(128, 16), 0);
+        umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after_sync();
+    uint32_t r[16];
+    tmem_ld_32x32b_x16(taddr + ((uint32_t)(warp * 32) << 16), r);
+    tmem_ld_wait();
+    for (int i = 0; i < 16; ++i) D[(warp * 32 + lane) * 16 + i] = __uint_as_float(r[i]);
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(taddr, 32);
+}
+
 __global__ void probe_rate(long long* cycles, int reps) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -234,6 +271,24 @@ int main() {
         double err = 0;
         for (int i = 0; i < M * 16; ++i) err = fmax(err, fabs(got16[i] - ref16[i]));
         printf("strided A (SBO=160B, start +208B, LBO=%dB), N=16: max abs err %.4g\n", npin * 16, err);
+        if (!(err < 1e-3)) bad = 1;
+    }
+    {   // overlapping windows: A[m][k] = S[8*m + k]
+        std::vector<float> ref16(M * 16), got16(M * 16);
+        for (int m = 0; m < 128; ++m)
+            for (int n2 = 0; n2 < 16; ++n2) {
+                float s2 = 0;
+                for (int k = 0; k < 16; ++k) s2 += fA[8 * m + k] * fB[n2 * 16 + k];
+                ref16[m * 16 + n2] = s2;
+            }
+        cudaMemset(dD, 0, M * N * 4);
+        probe_overlap<<<1, 128>>>(dA, dB, dD);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("overlap probe: CUDA error %s\n", cudaGetErrorString(e)); return 2; }
+        cudaMemcpy(got16.data(), dD, M * 16 * 4, cudaMemcpyDeviceToHost);
+        double err = 0;
+        for (int i = 0; i < 128 * 16; ++i) err = fmax(err, fabs(got16[i] - ref16[i]));
+        printf("overlapping-window A (LBO=16B, SBO=128B), N=16, K=16: max abs err %.4g\n", err);
         if (!(err < 1e-3)) bad = 1;
     }
     for (int threads : {128, 256}) {

@@ -28,3 +28,13 @@ names += ['wait last project MMA', 'output epilogue + store']
 for i, nme in enumerate(names):
     print(f'{nme:44s} {t[i + 1] - t[i]:8d} cycles')
 print(f'{"total":44s} {t[len(names)] - t[0]:8d} cycles')
+
+fbuf = (C.c_longlong * 16)()
+if hasattr(lib, 'fscnn_debug_front_phases') and lib.fscnn_debug_front_phases(fbuf) == 0:
+    f = list(fbuf)
+    print('fused front kernel, one tile of one CTA (2 CTAs share the SM):')
+    fn = ['wait patch (+sync)', 'issue next prefetch', 'repack raw -> RGBX planes (+sync)', 'stem MMAs issue + wait', 'stem epilogue (+sync)',
+          'depthwise (+sync)', 'pointwise MMA issue + wait', 'output epilogue']
+    for i, nme in enumerate(fn):
+        print(f'{nme:44s} {f[i + 1] - f[i]:8d} cycles')
+    print(f'{"total":44s} {f[8] - f[0]:8d} cycles')
