@@ -19,6 +19,7 @@
 // and weights are set up once, and the next tile's patch is fetched with cp.async into the other half of a
 // double buffer while the current tile computes, so the global-load latency is off the critical path.
 #include "kernels.h"
+#include "tma_host.h"
 #include "umma.cuh"
 
 #include "../../include/fscnn_b200.h"
@@ -29,9 +30,12 @@ namespace {
 constexpr int SH = 17, SW = 33, SPIX = SH * SW;       // stem pixels per tile (561)
 constexpr int SWP = 34, MROWS = SH * SWP;              // A rows: stem row pitch 34 (column 33 is a dummy) -> 578
 constexpr int NMT = 5;                                 // MMA row tiles of 128 A rows
-constexpr int PR = 35, PC = 67, PLD = 68;              // input patch rows / cols / pitch (fp32 planes)
-constexpr int kRW = 52;                                // uint8 input: 52 words (208 bytes) per patch row
-constexpr int kBuf = 35968;                            // one half of the double buffer: raw patch (28560 B) or E (561 x 64 B)
+constexpr int PR = 35, PC = 67;                        // input patch rows / columns the tile needs
+// The raw patch starts 2 pixels left of the first needed column so that its first byte is 16-byte aligned in global
+// memory (a TMA requirement): fp32 planes of 69 used columns at pitch 72, uint8 rows of 56 words (224 bytes).
+constexpr int PCR = 69, PLD = 72;
+constexpr int kRW = 56;
+constexpr int kBuf = 35968;                            // one half of the double buffer: raw patch (30240 B) or E (561 x 64 B)
 constexpr int kPP = SWP * 16;                          // RGBX plane row pitch: 68 pixels x 8 B = 544 B
 constexpr int oBuf = 0;
 constexpr int oP2 = 2 * kBuf;                          // RGBX planes: 18 even rows, then 17 odd rows
@@ -67,11 +71,11 @@ __device__ long long g_front_phase[16];
 
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 2)
-l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict__ ws_img, const float* __restrict__ bs,
+l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const void* __restrict__ x, StemIn prm, const bf16* __restrict__ ws_img, const float* __restrict__ bs,
                  DsW w, const bf16* __restrict__ wp_img, bf16* __restrict__ out, int H, int W, int H1, int W1, int H2, int W2,
                  int tiles_x, int tiles_y, int ntiles) {
     extern __shared__ __align__(128) uint8_t sm[];
-    __shared__ __align__(8) uint64_t bar_stem, bar_pw;
+    __shared__ __align__(8) uint64_t bar_stem, bar_pw, bar_patch[2];
     __shared__ uint32_t tmem_base_s;
     float* Bss = reinterpret_cast<float*>(sm + oBs);
     float* Bds = reinterpret_cast<float*>(sm + oBd);
@@ -80,7 +84,7 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
                    sWd = smem_u32(sm + oWd);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid == 0) { mbar_init(&bar_stem, 1); mbar_init(&bar_pw, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&bar_stem, 1); mbar_init(&bar_pw, 1); mbar_init(&bar_patch[0], 1); mbar_init(&bar_patch[1], 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWs)[tid] = __ldg(reinterpret_cast<const uint4*>(ws_img) + tid);
     for (int i = tid; i < kP2Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(sm + oP2)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad pixels stay finite
@@ -91,15 +95,26 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
 
     // asynchronous fetch of tile t's input patch into buffer b (no registers, no waiting)
     auto prefetch = [&](int txi, int tyi, int n, int b) {
-        const int iy0 = 4 * (tyi * 8) - 2, ix0 = 4 * (txi * 16) - 2;
+        const int iy0 = 4 * (tyi * 8) - 2, ix0 = 4 * (txi * 16) - 4;   // ix0: raw patch start (needed columns start at ix0 + 2)
         const uint32_t dst0 = sBuf + b * kBuf;
-        if (FMT == FSCNN_IN_F32_NCHW) {
+        if (use_tma) {   // one tensor copy per patch: fp32 planes {68, 35, 3} or uint8 rows {208 bytes, 35}; zero fill outside the image
+            if (tid == 0) {
+                fence_async_proxy();   // the buffer was last touched through the generic proxy (E of the previous tile)
+                if (FMT == FSCNN_IN_F32_NCHW) {
+                    mbar_arrive_expect_tx(&bar_patch[b], 3 * PR * PLD * 4);
+                    tma_load_3d(dst0, &xmap, ix0, iy0, n * 3, &bar_patch[b]);
+                } else {
+                    mbar_arrive_expect_tx(&bar_patch[b], PR * kRW * 4);
+                    tma_load_3d(dst0, &xmap, ix0 * 3 - 4, iy0, n, &bar_patch[b]);
+                }
+            }
+        } else if (FMT == FSCNN_IN_F32_NCHW) {
             const float* xf = reinterpret_cast<const float*>(x);
-            if (tid < 3 * PC) {   // thread = (channel, column): 35 rows, constant pointer step
-                const int ci = tid / PC, c = tid - ci * PC;
+            if (tid < 3 * PCR) {   // thread = (channel, column): 35 rows, constant pointer step
+                const int ci = tid / PCR, c = tid - ci * PCR;
                 const int ix = ix0 + c;
                 uint32_t dst = dst0 + (ci * PR * PLD + c) * 4;
-                if (iy0 >= 0 && iy0 + PR <= H && ix0 >= 0 && ix0 + PC <= W) {   // interior tile (CTA-uniform): no predicates
+                if (iy0 >= 0 && iy0 + PR <= H && ix0 >= 0 && ix0 + PCR <= W) {   // interior tile (CTA-uniform): no predicates
                     const float* src = xf + ((((size_t)n * 3 + ci) * H) + iy0) * W + ix;
 #pragma unroll
                     for (int r = 0; r < PR; ++r) {
@@ -119,9 +134,9 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
                 }
             }
         } else {
-            // raw uint8 HWC rows as 52 aligned 32-bit words each (row start rounded down to 4 bytes: ix0*3 == 2 mod 4)
+            // raw uint8 HWC rows as 56 aligned 32-bit words each, starting at byte ix0*3 - 4 (a multiple of 16)
             const unsigned char* xb = reinterpret_cast<const unsigned char*>(x);
-            const int rowb = W * 3, b0 = ix0 * 3 - 2;
+            const int rowb = W * 3, b0 = ix0 * 3 - 4;
             if ((W & 3) == 0) {
                 if (tid < 4 * kRW) {   // thread = (word column, group of 9 rows)
                     const int rg = tid / kRW, wq = tid - rg * kRW;
@@ -183,7 +198,8 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
         const int sy0 = 2 * oy0 - 1, sx0 = 2 * ox0 - 1;      // first stem pixel of the halo tile (may be -1)
         const uint32_t sIn = sBuf + b * kBuf;                 // this tile's patch; later its E tile
         FR_STAMP(0);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (use_tma) mbar_wait(&bar_patch[b], (it >> 1) & 1);
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                                       // patch of tile t visible; everything of tile t-1 retired
         FR_STAMP(1);
         if (t + gstep < ntiles) prefetch(nx_x, nx_y, nx_n, b ^ 1);   // overlaps the whole tile
@@ -197,10 +213,10 @@ l2d_front_kernel(const void* __restrict__ x, StemIn prm, const bf16* __restrict_
                 const int r = i / PC, px = i - r * PC;
                 float v0, v1, v2;
                 if (FMT == FSCNN_IN_U8_NHWC) {
-                    const unsigned char* q = patch + r * (kRW * 4) + 2 + 3 * px;
+                    const unsigned char* q = patch + r * (kRW * 4) + 10 + 3 * px;
                     v0 = (float)q[0]; v1 = (float)q[1]; v2 = (float)q[2];
                 } else {
-                    const float* q = reinterpret_cast<const float*>(patch) + r * PLD + px;
+                    const float* q = reinterpret_cast<const float*>(patch) + r * PLD + px + 2;
                     v0 = q[0]; v1 = q[PR * PLD]; v2 = q[2 * PR * PLD];
                 }
                 sts64(sP2 + (r & 1) * (18 * kPP) + (r >> 1) * kPP + px * 8, packbf(v0, v1), packbf(v2, 0.f));
@@ -365,16 +381,31 @@ cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_
     if (ntiles_ll > 0x7fffffff) return cudaErrorInvalidValue;
     const int ntiles = (int)ntiles_ll;
     const int grid = ntiles < 2 * num_sms ? ntiles : 2 * num_sms;   // persistent: two CTAs per SM
+    // TMA needs 16-byte aligned rows; other shapes keep the per-thread cp.async path
+    CUtensorMap xmap{};
+    int use_tma = 0;
     if (in.format == FSCNN_IN_U8_NHWC) {
+        if ((wd * 3) % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            const cuuint64_t dims[3] = {(cuuint64_t)wd * 3, (cuuint64_t)h, (cuuint64_t)n};
+            const cuuint64_t strides[2] = {(cuuint64_t)wd * 3, (cuuint64_t)h * wd * 3};
+            const cuuint32_t box[3] = {kRW * 4, PR, 1};
+            use_tma = make_tiled_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, x, dims, strides, box) == cudaSuccess;
+        }
         cudaError_t e = ensure_dyn_smem(l2d_front_kernel<FSCNN_IN_U8_NHWC>, kSmem, cfg_u8);
         if (e != cudaSuccess) return e;
-        l2d_front_kernel<FSCNN_IN_U8_NHWC><<<grid, kThreads, kSmem, s>>>(x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2, tiles_x,
-                                                                          tiles_y, ntiles);
+        l2d_front_kernel<FSCNN_IN_U8_NHWC><<<grid, kThreads, kSmem, s>>>(xmap, use_tma, x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2,
+                                                                          tiles_x, tiles_y, ntiles);
     } else {
+        if (wd % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            const cuuint64_t dims[3] = {(cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n * 3};
+            const cuuint64_t strides[2] = {(cuuint64_t)wd * 4, (cuuint64_t)h * wd * 4};
+            const cuuint32_t box[3] = {PLD, PR, 3};
+            use_tma = make_tiled_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x, dims, strides, box) == cudaSuccess;
+        }
         cudaError_t e = ensure_dyn_smem(l2d_front_kernel<FSCNN_IN_F32_NCHW>, kSmem, cfg_f32);
         if (e != cudaSuccess) return e;
-        l2d_front_kernel<FSCNN_IN_F32_NCHW><<<grid, kThreads, kSmem, s>>>(x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2, tiles_x,
-                                                                           tiles_y, ntiles);
+        l2d_front_kernel<FSCNN_IN_F32_NCHW><<<grid, kThreads, kSmem, s>>>(xmap, use_tma, x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2,
+                                                                           tiles_x, tiles_y, ntiles);
     }
     return cudaGetLastError();
 }

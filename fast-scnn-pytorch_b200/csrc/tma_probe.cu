@@ -70,6 +70,58 @@ static int run(EncodeFn enc, int N, int H, int W, int C, int IH, int IW, int ix0
     return bad != 0;
 }
 
+__global__ void probe3(const __grid_constant__ CUtensorMap tmap, uint8_t* out, int bytes, int c0, int c1, int c2) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t sbar = (uint32_t)__cvta_generic_to_shared(&bar), sdst = (uint32_t)__cvta_generic_to_shared(sm);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(sdst), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(sbar) : "memory");
+    }
+    __syncthreads();
+    asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}" ::"r"(sbar) : "memory");
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = sm[i];
+}
+
+static int run3(EncodeFn enc, bool u8, int N, int H, int W, int x0, int y0, int n) {
+    const int es = u8 ? 1 : 4, planes = u8 ? 1 : 3, rowe = u8 ? W * 3 : W, bw = u8 ? 224 : 72;
+    const size_t total = (size_t)N * 3 * H * W * es;
+    std::vector<uint8_t> h(total);
+    for (size_t i = 0; i < total; ++i) h[i] = (uint8_t)(1 + (i * 2654435761u >> 9) % 250);
+    uint8_t* d; cudaMalloc(&d, total); cudaMemcpy(d, h.data(), total, cudaMemcpyHostToDevice);
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {(cuuint64_t)rowe, (cuuint64_t)H, (cuuint64_t)(u8 ? N : N * 3)};
+    const cuuint64_t strides[2] = {(cuuint64_t)rowe * es, (cuuint64_t)rowe * es * H};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, 35, (cuuint32_t)planes};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tm, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("3-D encode failed: %d (u8=%d)\n", (int)r, (int)u8); return 1; }
+    const int bytes = bw * es * 35 * planes;
+    uint8_t* dout; cudaMalloc(&dout, bytes);
+    cudaFuncSetAttribute(probe3, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    probe3<<<1, 128, bytes>>>(tm, dout, bytes, x0, y0, u8 ? n : n * 3);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("3-D kernel failed (u8=%d): %s\n", (int)u8, cudaGetErrorString(e)); return 1; }
+    std::vector<uint8_t> o(bytes);
+    cudaMemcpy(o.data(), dout, bytes, cudaMemcpyDeviceToHost);
+    long bad = 0;
+    for (int p = 0; p < planes; ++p)
+        for (int rr = 0; rr < 35; ++rr)
+            for (int c = 0; c < bw * es; ++c) {
+                const int y = y0 + rr; const long xb = (long)x0 * es + c;
+                const uint8_t want = (y >= 0 && y < H && xb >= 0 && xb < (long)rowe * es)
+                    ? h[(((size_t)(u8 ? n : n * 3 + p)) * H + y) * rowe * es + xb] : 0;
+                if (o[((size_t)p * 35 + rr) * bw * es + c] != want) ++bad;
+            }
+    printf("3-D %s patch at (%d,%d) n=%d of %dx%d: %ld mismatches of %d bytes\n", u8 ? "uint8" : "fp32", y0, x0, n, H, W, bad, bytes);
+    cudaFree(d); cudaFree(dout);
+    return bad != 0;
+}
+
 int main() {
     EncodeFn enc = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -82,6 +134,11 @@ int main() {
     bad += run(enc, 2, 32, 64, 96, 10, 18, -1, 7, 0);
     bad += run(enc, 2, 32, 64, 128, 10, 18, 47, -1, 1);
     bad += run(enc, 1, 65, 97, 128, 10, 18, 81, 57, 0);     // odd sizes, partial tile
+    // the innermost start coordinate must be a multiple of 16 bytes (x0 = -2 floats is an illegal instruction at run time)
+    bad += run3(enc, false, 2, 128, 256, -4, -2, 1);
+    bad += run3(enc, false, 2, 128, 256, 188, 94, 0);
+    bad += run3(enc, true, 2, 128, 256, -16, -2, 1);
+    bad += run3(enc, true, 2, 128, 256, 12 * 48 - 16, 94, 0);
     printf(bad ? "FAILED\n" : "all ok\n");
     return bad;
 }
