@@ -69,13 +69,15 @@ __device__ long long g_front_phase[16];
 #define FR_STAMP(i) do { } while (0)
 #endif
 
+constexpr int kFrontThreads = kThreads + 32;   // 8 compute warps + the control warp (TMA patch loads, every tcgen05.mma)
+
 template <int FMT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kFrontThreads, 2)
 l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const void* __restrict__ x, StemIn prm, const bf16* __restrict__ ws_img, const float* __restrict__ bs,
                  DsW w, const bf16* __restrict__ wp_img, bf16* __restrict__ out, int H, int W, int H1, int W1, int H2, int W2,
                  int tiles_x, int tiles_y, int ntiles) {
     extern __shared__ __align__(128) uint8_t sm[];
-    __shared__ __align__(8) uint64_t bar_stem, bar_pw, bar_patch[2];
+    __shared__ __align__(8) uint64_t bar_stem[NMT], bar_pw, bar_patch[2], bar_repack, bar_dw;
     __shared__ uint32_t tmem_base_s;
     float* Bss = reinterpret_cast<float*>(sm + oBs);
     float* Bds = reinterpret_cast<float*>(sm + oBd);
@@ -84,31 +86,27 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
                    sWd = smem_u32(sm + oWd);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid == 0) { mbar_init(&bar_stem, 1); mbar_init(&bar_pw, 1); mbar_init(&bar_patch[0], 1); mbar_init(&bar_patch[1], 1); fence_mbar_init(); }
+    if (tid == 0) {
+        for (int i = 0; i < NMT; ++i) mbar_init(&bar_stem[i], 1);
+        mbar_init(&bar_pw, 1);
+        mbar_init(&bar_patch[0], 1); mbar_init(&bar_patch[1], 1);
+        mbar_init(&bar_repack, kThreads / 32); mbar_init(&bar_dw, kThreads / 32);
+        fence_mbar_init();
+    }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWs)[tid] = __ldg(reinterpret_cast<const uint4*>(ws_img) + tid);
-    for (int i = tid; i < kP2Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(sm + oP2)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad pixels stay finite
+    for (int i = tid; i < kP2Bytes / 16; i += kFrontThreads) reinterpret_cast<uint4*>(sm + oP2)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad pixels stay finite
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWp)[tid] = __ldg(reinterpret_cast<const uint4*>(wp_img) + tid);
     if (tid < 9 * 32 / 2) reinterpret_cast<uint32_t*>(sm + oWd)[tid] = packbf(__ldg(w.wd + 2 * tid), __ldg(w.wd + 2 * tid + 1));
     if (tid < 32) { Bss[tid] = __ldg(bs + tid); Bds[tid] = __ldg(w.bd + tid); }
     if (tid < 48) Bps[tid] = __ldg(w.bp + tid);
 
-    // asynchronous fetch of tile t's input patch into buffer b (no registers, no waiting)
+    // fallback when the rows are not 16-byte aligned (no TMA): the compute threads fetch the patch of a tile with 4-byte
+    // cp.async into buffer b (no registers, no waiting)
     auto prefetch = [&](int txi, int tyi, int n, int b) {
         const int iy0 = 4 * (tyi * 8) - 2, ix0 = 4 * (txi * 16) - 4;   // ix0: raw patch start (needed columns start at ix0 + 2)
         const uint32_t dst0 = sBuf + b * kBuf;
-        if (use_tma) {   // one tensor copy per patch: fp32 planes {68, 35, 3} or uint8 rows {208 bytes, 35}; zero fill outside the image
-            if (tid == 0) {
-                fence_async_proxy();   // the buffer was last touched through the generic proxy (E of the previous tile)
-                if (FMT == FSCNN_IN_F32_NCHW) {
-                    mbar_arrive_expect_tx(&bar_patch[b], 3 * PR * PLD * 4);
-                    tma_load_3d(dst0, &xmap, ix0, iy0, n * 3, &bar_patch[b]);
-                } else {
-                    mbar_arrive_expect_tx(&bar_patch[b], PR * kRW * 4);
-                    tma_load_3d(dst0, &xmap, ix0 * 3 - 4, iy0, n, &bar_patch[b]);
-                }
-            }
-        } else if (FMT == FSCNN_IN_F32_NCHW) {
+        if (FMT == FSCNN_IN_F32_NCHW) {
             const float* xf = reinterpret_cast<const float*>(x);
             if (tid < 3 * PCR) {   // thread = (channel, column): 35 rows, constant pointer step
                 const int ci = tid / PCR, c = tid - ci * PCR;
@@ -183,14 +181,60 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
         nx_y += step_y; if (nx_y >= tiles_y) { nx_y -= tiles_y; ++nx_n; }
         nx_n += step_n;
     };
-    if (t < ntiles) prefetch(nx_x, nx_y, nx_n, 0);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
+    if (warp == kThreads / 32) {
+        // =========================== control warp ===========================
+        if (lane == 0) {
+            auto tma_patch = [&](int b) {   // patch of tile (nx_x, nx_y, nx_n) -> buffer b: fp32 planes {72, 35, 3} or uint8 rows {224 bytes, 35}
+                const int iy0 = 4 * (nx_y * 8) - 2, ix0 = 4 * (nx_x * 16) - 4;
+                if (FMT == FSCNN_IN_F32_NCHW) {
+                    mbar_arrive_expect_tx(&bar_patch[b], 3 * PR * PLD * 4);
+                    tma_load_3d(sBuf + b * kBuf, &xmap, ix0, iy0, nx_n * 3, &bar_patch[b]);
+                } else {
+                    mbar_arrive_expect_tx(&bar_patch[b], PR * kRW * 4);
+                    tma_load_3d(sBuf + b * kBuf, &xmap, ix0 * 3 - 4, iy0, nx_n, &bar_patch[b]);
+                }
+                advance();
+            };
+            int tl = t;                                        // next tile to load
+            if (use_tma) {
+                tma_prefetch_desc(&xmap);
+                if (tl < ntiles) { tma_patch(0); tl += gstep; }
+                if (tl < ntiles) { tma_patch(1); tl += gstep; }
+            }
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 32), idesc_p = make_idesc_bf16(128, 48);
 #pragma unroll 1
-    for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
+            for (int it = 0; t < ntiles; t += gstep, ++it) {
+                mbar_wait(&bar_repack, it & 1);               // RGBX planes written (writers fenced the async proxy), TMEM stem region drained
+                tc_fence_after_sync();
+#pragma unroll
+                for (int mt = 0; mt < NMT; ++mt) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)   // kernel row ky reads plane (ky & 1) from its row (ky >> 1) on; K = 16 = 4 pixels x RGBX
+                        umma_bf16_ss(tmem + TM_STEM + mt * 32,
+                                     make_smem_desc(sP2 + (ky & 1) * (18 * kPP) + (ky >> 1) * kPP + mt * (128 * 16), 16, 128),
+                                     make_smem_desc(sWs + ky * 1024, 512, 128), idesc_s, ky > 0);
+                    umma_commit(&bar_stem[mt]);   // one barrier per row tile: its epilogue starts while the later tiles still multiply
+                }
+                mbar_wait(&bar_dw, it & 1);                   // A2 written, E of this tile dead, TMEM pointwise region drained
+                tc_fence_after_sync();
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16)
+                    umma_bf16_ss(tmem + TM_PW, make_smem_desc(sA + k16 * 256, 128, 512), make_smem_desc(sWp + k16 * 2 * 768, 768, 128),
+                                 idesc_p, k16 > 0);
+                umma_commit(&bar_pw);
+                if (use_tma && tl < ntiles) { tma_patch(it & 1); tl += gstep; }   // this tile's buffer is free: fetch tile it + 2
+            }
+        }
+    } else {
+    // =========================== compute warps ===========================
+    if (!use_tma && t < ntiles) prefetch(nx_x, nx_y, nx_n, 0);
+#pragma unroll 1
+    for (int it = 0; t < ntiles; t += gstep, ++it) {
         const int b = it & 1;
         const int txi = nx_x, tyi = nx_y, n = nx_n;
         advance();
@@ -198,11 +242,14 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
         const int sy0 = 2 * oy0 - 1, sx0 = 2 * ox0 - 1;      // first stem pixel of the halo tile (may be -1)
         const uint32_t sIn = sBuf + b * kBuf;                 // this tile's patch; later its E tile
         FR_STAMP(0);
-        if (use_tma) mbar_wait(&bar_patch[b], (it >> 1) & 1);
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                       // patch of tile t visible; everything of tile t-1 retired
+        if (use_tma) {
+            mbar_wait(&bar_patch[b], (it >> 1) & 1);
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            named_bar_sync(2, kThreads);                       // patch visible to every warp; all reads of E(it-1) are done
+            if (t + gstep < ntiles) prefetch(nx_x, nx_y, nx_n, b ^ 1);
+        }
         FR_STAMP(1);
-        if (t + gstep < ntiles) prefetch(nx_x, nx_y, nx_n, b ^ 1);   // overlaps the whole tile
 
         FR_STAMP(2);
         // ---- repack the raw patch as bf16 RGBX pixels, even / odd rows in separate planes (this IS the A operand) ----
@@ -223,28 +270,17 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
             }
         }
         fence_async_proxy();
-        tc_fence_before_sync();
-        __syncthreads();
+        tc_fence_before_sync();      // this warp's TMEM reads of the previous tile precede the MMAs the arrival releases
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_repack);
         FR_STAMP(3);
-        if (tid == 0) {
-            tc_fence_after_sync();
-            constexpr uint32_t idesc = make_idesc_bf16(128, 32);
-#pragma unroll
-            for (int mt = 0; mt < NMT; ++mt)
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky)   // kernel row ky reads plane (ky & 1) from its row (ky >> 1) on; K = 16 = 4 pixels x RGBX
-                    umma_bf16_ss(tmem + TM_STEM + mt * 32,
-                                 make_smem_desc(sP2 + (ky & 1) * (18 * kPP) + (ky >> 1) * kPP + mt * (128 * 16), 16, 128),
-                                 make_smem_desc(sWs + ky * 1024, 512, 128), idesc, ky > 0);
-            umma_commit(&bar_stem);
-        }
-        mbar_wait(&bar_stem, it & 1);
-        tc_fence_after_sync();
         FR_STAMP(4);
 
         // ---- stem epilogue: bias, ReLU, zero outside the stem image (the depthwise conv pads with zeros) -> E (over the patch) ----
         for (int task = warp; task < NMT * 4; task += kThreads / 32) {
             const int mt = task >> 2, q = task & 3;
+            mbar_wait(&bar_stem[mt], it & 1);
+            tc_fence_after_sync();
             const int ma = mt * 128 + q * 32 + lane;             // A row: stem row pitch 34
             const int sr = ma / SWP, sc = ma - sr * SWP;
             const int m = sr * SW + sc;                           // E row
@@ -273,8 +309,7 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
                 }
             }
         }
-        tc_fence_before_sync();
-        __syncthreads();
+        named_bar_sync(1, kThreads);                          // E complete (and every stem MMA of this tile has been waited for)
         FR_STAMP(5);
 
         // ---- depthwise 3x3 stride 2 (fp32): strip = (column x, 2-row group, 8-channel chunk) -> A2 ----
@@ -316,17 +351,9 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
         }
         fence_async_proxy();
         tc_fence_before_sync();
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_dw);
         FR_STAMP(6);
-        if (tid == 0) {
-            tc_fence_after_sync();
-            constexpr uint32_t idesc = make_idesc_bf16(128, 48);
-#pragma unroll
-            for (int k16 = 0; k16 < 2; ++k16)
-                umma_bf16_ss(tmem + TM_PW, make_smem_desc(sA + k16 * 256, 128, 512), make_smem_desc(sWp + k16 * 2 * 768, 768, 128),
-                             idesc, k16 > 0);
-            umma_commit(&bar_pw);
-        }
         mbar_wait(&bar_pw, it & 1);
         tc_fence_after_sync();
         FR_STAMP(7);
@@ -353,10 +380,11 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
                 }
             }
         }
-        tc_fence_before_sync();   // TMEM reads of this tile are ordered before the next tile's MMAs by the loop-top barrier
         FR_STAMP(8);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }   // compute warps
+    tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
@@ -393,7 +421,7 @@ cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_
         }
         cudaError_t e = ensure_dyn_smem(l2d_front_kernel<FSCNN_IN_U8_NHWC>, kSmem, cfg_u8);
         if (e != cudaSuccess) return e;
-        l2d_front_kernel<FSCNN_IN_U8_NHWC><<<grid, kThreads, kSmem, s>>>(xmap, use_tma, x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2,
+        l2d_front_kernel<FSCNN_IN_U8_NHWC><<<grid, kFrontThreads, kSmem, s>>>(xmap, use_tma, x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2,
                                                                           tiles_x, tiles_y, ntiles);
     } else {
         if (wd % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
@@ -404,7 +432,7 @@ cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_
         }
         cudaError_t e = ensure_dyn_smem(l2d_front_kernel<FSCNN_IN_F32_NCHW>, kSmem, cfg_f32);
         if (e != cudaSuccess) return e;
-        l2d_front_kernel<FSCNN_IN_F32_NCHW><<<grid, kThreads, kSmem, s>>>(xmap, use_tma, x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2,
+        l2d_front_kernel<FSCNN_IN_F32_NCHW><<<grid, kFrontThreads, kSmem, s>>>(xmap, use_tma, x, in, ws_img, bs, w, wp_img, out, h, wd, h1, w1, h2, w2,
                                                                            tiles_x, tiles_y, ntiles);
     }
     return cudaGetLastError();
