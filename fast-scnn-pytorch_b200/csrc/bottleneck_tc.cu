@@ -341,12 +341,9 @@ size_t bottleneck_tc_tab_bytes(int cin, int cout) { return (size_t)9 * 6 * cin *
 
 cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s) {
+    if (stride == 1) return launch_bottleneck_s1_tc(cin, cout, in, tab_img, we_img, wp_img, out, n, hi, wi, s);
     if (cin == 64 && cout == 64 && stride == 2) return run_tc<64, 64, 2, false>(in, tab_img, we_img, wp_img, out, n, hi, wi, ho, wo, s);
-    if (cin == 64 && cout == 64 && stride == 1) return run_tc<64, 64, 1, true>(in, tab_img, we_img, wp_img, out, n, hi, wi, ho, wo, s);
     if (cin == 64 && cout == 96 && stride == 2) return run_tc<64, 96, 2, false>(in, tab_img, we_img, wp_img, out, n, hi, wi, ho, wo, s);
-    if (cin == 96 && cout == 96 && stride == 1) return run_tc<96, 96, 1, true>(in, tab_img, we_img, wp_img, out, n, hi, wi, ho, wo, s);
-    if (cin == 96 && cout == 128 && stride == 1) return run_tc<96, 128, 1, false>(in, tab_img, we_img, wp_img, out, n, hi, wi, ho, wo, s);
-    if (cin == 128 && cout == 128 && stride == 1) return run_tc<128, 128, 1, true>(in, tab_img, we_img, wp_img, out, n, hi, wi, ho, wo, s);
     return cudaErrorInvalidValue;
 }
 

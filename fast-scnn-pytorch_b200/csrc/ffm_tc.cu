@@ -36,6 +36,16 @@ constexpr int kSmem = oTab + 2 * kTabBytes;
 static_assert(kSmem <= 227 * 1024, "shared memory");
 }  // namespace
 
+#ifdef FSCNN_PHASE_TIMING   // debug build only: clock64 stamps of the 3rd tile of CTA 9
+__device__ long long g_ffm_phase[16];
+#define FF_STAMP(i) do { if (tid == 0 && blockIdx.x == 9 && lt == 2) g_ffm_phase[i] = clock64(); } while (0)
+extern "C" int fscnn_debug_ffm_phases(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, g_ffm_phase, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#else
+#define FF_STAMP(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kFfNTall, 1)
 ffm_tc_kernel(const __grid_constant__ CUtensorMap hmap, const bf16* __restrict__ lower, FfmW w, const bf16* __restrict__ wcat_img,
               bf16* __restrict__ out, int Hh, int Wh, int Hl, int Wl, int tiles_x, int tiles_y, int ntiles) {
@@ -161,8 +171,10 @@ ffm_tc_kernel(const __grid_constant__ CUtensorMap hmap, const bf16* __restrict__
         for (int lt = 0; lt < my_tiles; ++lt) {
             int n, oy0, ox0;
             tile_origin(lt, n, oy0, ox0);
+            FF_STAMP(0);
             if (lt > 0) named_bar_sync(1, kFfNT);                // every depthwise read of U(lt-1) is done; tab[lt&1] is visible
             // ---- U = resize(lower) on the halo tile; item = (halo pixel, 8-channel chunk), lanes along chunks ----
+            FF_STAMP(1);
             const bf16* lbase = lower + (size_t)n * Hl * Wl * kCL;
             const uint8_t* tabp = sm + oTab + (lt & 1) * kTabBytes;
 #pragma unroll 2
@@ -186,16 +198,21 @@ ffm_tc_kernel(const __grid_constant__ CUtensorMap hmap, const bf16* __restrict__
                 }
                 sts128(sU + pin * (kCL * 2) + ((k8 ^ (pin & 7)) << 4), o.x, o.y, o.z, o.w);
             }
+            FF_STAMP(2);
             named_bar_sync(2, kFfNT);                            // U complete
+            FF_STAMP(3);
             // ---- depthwise 3x3 + bias + ReLU on U -> A[lt&1] columns 64..191 (one output column x 4 channels per thread);
             //      A[lt&1] is free: this warp waited for MMA(lt-2) in its epilogue ----
             dw3x3_s1_col4<kCL * 2, kIW>(sU, tid & 15, tid >> 4, sWd, kCL, Bds, sA + (lt & 1) * kABytes, 8);
+            FF_STAMP(4);
             fence_async_proxy();
             tc_fence_before_sync();      // this warp's TMEM reads of tile lt-2 precede the MMA the arrival releases
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_a[lt & 1]);
             if (lt + 1 < my_tiles) build_tab(lt + 1);            // published by the named barrier at the top of the next iteration
+            FF_STAMP(5);
             if (lt >= 1) epilogue(lt - 1);
+            FF_STAMP(6);
         }
         epilogue(my_tiles - 1);
     }

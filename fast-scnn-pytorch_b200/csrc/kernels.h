@@ -78,6 +78,9 @@ int bottleneck_tc_chunk(int stride);
 // tab_img: the constant tables packed by launch_pack_bneck_tab (bottleneck_tc_tab_bytes(cin, cout) bytes, 16-byte aligned)
 size_t bottleneck_tc_tab_bytes(int cin, int cout);
 cudaError_t launch_pack_bneck_tab(const BneckW& w, int cexp, int cout, unsigned char* out, cudaStream_t s);
+// stride-1 layers: three-role pipeline (bottleneck_s1_tc.cu); launch_bottleneck_tc dispatches to it
+cudaError_t launch_bottleneck_s1_tc(int cin, int cout, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
+                                    const bf16* wp_img, bf16* out, int n, int h, int w, cudaStream_t s);
 cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 

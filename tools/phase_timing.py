@@ -38,3 +38,22 @@ if hasattr(lib, 'fscnn_debug_front_phases') and lib.fscnn_debug_front_phases(fbu
     for i, nme in enumerate(fn):
         print(f'{nme:44s} {f[i + 1] - f[i]:8d} cycles')
     print(f'{"total":44s} {f[8] - f[0]:8d} cycles')
+
+gbuf = (C.c_longlong * 16)()
+if hasattr(lib, 'fscnn_debug_ffm_phases') and lib.fscnn_debug_ffm_phases(gbuf) == 0:
+    g = list(gbuf)
+    print('FFM kernel, one tile (thread 0 of one CTA):')
+    gn = ['barrier: U(t-1) consumed', 'U: bilinear resize', 'barrier: U complete', 'depthwise', 'arrive + tap table', 'epilogue(t-1)']
+    for i, nme in enumerate(gn):
+        print(f'{nme:44s} {g[i + 1] - g[i]:8d} cycles')
+    print(f'{"total":44s} {g[6] - g[0]:8d} cycles')
+
+sbuf = (C.c_longlong * 64)()
+if hasattr(lib, 'fscnn_debug_s1_phases') and lib.fscnn_debug_s1_phases(sbuf) == 0:
+    s1 = list(sbuf)
+    t0 = s1[0]
+    print('stride-1 bottleneck pipeline, chunks 8..11 of one CTA (cycles since the first stamp):')
+    print('  expand warp : loop top | expand MMA done | E buffer free | E written      depthwise warp: loop top | E ready | FMAs done | D written')
+    for c in range(4):
+        r = [v - t0 for v in s1[c * 8:c * 8 + 8]]
+        print(f'  chunk {8 + c}: {r[0]:8d} {r[1]:8d} {r[2]:8d} {r[3]:8d}      {r[4]:8d} {r[5]:8d} {r[6]:8d} {r[7]:8d}')
