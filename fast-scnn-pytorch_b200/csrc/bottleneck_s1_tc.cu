@@ -340,6 +340,8 @@ bottleneck_s1_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __res
                 }
             }
             S1_STAMP(0, 6);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_efree[g & 1]);       // every read of E[g&1] has been consumed: release it before the D hand-off
             if (g >= 2) mbar_wait(&bar_proj[g & 1], ((g - 2) >> 1) & 1);   // project(g-2) has completed: D[g&1] is free
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
@@ -349,7 +351,7 @@ bottleneck_s1_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __res
             }
             fence_async_proxy();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&bar_dready[g & 1]); mbar_arrive(&bar_efree[g & 1]); }
+            if (lane == 0) mbar_arrive(&bar_dready[g & 1]);
             S1_STAMP(0, 7);
         }
     }

@@ -18,16 +18,17 @@ for _ in range(3):
 torch.cuda.synchronize()
 lib = C.CDLL(native.lib_path())
 buf = (C.c_longlong * 64)()
-assert lib.fscnn_debug_bneck_phases(buf) == 0
+have_bneck = hasattr(lib, 'fscnn_debug_bneck_phases') and lib.fscnn_debug_bneck_phases(buf) == 0
 t = list(buf)
-nch = 6
-names = []
-for e in range(nch):
-    names += [f'chunk {e}: wait expand MMA', f'chunk {e}: expand epilogue (+barrier)', f'chunk {e}: depthwise (+proj wait, barrier)']
-names += ['wait last project MMA', 'output epilogue + store']
-for i, nme in enumerate(names):
-    print(f'{nme:44s} {t[i + 1] - t[i]:8d} cycles')
-print(f'{"total":44s} {t[len(names)] - t[0]:8d} cycles')
+if have_bneck:
+    nch = 6
+    names = []
+    for e in range(nch):
+        names += [f'chunk {e}: wait expand MMA', f'chunk {e}: expand epilogue (+barrier)', f'chunk {e}: depthwise (+proj wait, barrier)']
+    names += ['wait last project MMA', 'output epilogue + store']
+    for i, nme in enumerate(names):
+        print(f'{nme:44s} {t[i + 1] - t[i]:8d} cycles')
+    print(f'{"total":44s} {t[len(names)] - t[0]:8d} cycles')
 
 fbuf = (C.c_longlong * 16)()
 if hasattr(lib, 'fscnn_debug_front_phases') and lib.fscnn_debug_front_phases(fbuf) == 0:
