@@ -92,3 +92,36 @@ def test_bf16_batch_invariance():
     assert torch.equal(model.predict(xd), full)
     eng.set_micro_batch(0)
     assert torch.equal(model.predict(xd[3:4].contiguous()), full[3:4])
+
+
+@pytest.mark.parametrize('shape,batch,nc', [((520, 776), 16, 19), ((328, 520), 24, 3)])
+def test_bf16_persistent_pipelines_many_tiles(shape, batch, nc):
+    """The bf16 kernels are persistent, software-pipelined CTAs: a CTA's result for a tile must not depend on which tiles
+    it processed before or which CTA got it.  Odd sizes (partial tiles in both directions at every scale) and a batch that
+    gives every CTA several tiles at each stage; per-image runs, micro-batched runs and the full batch must agree bit for
+    bit (logits and mask), with float32 and uint8 input."""
+    h, w = shape
+    sd = fo.make_state_dict(nc, False, 11)
+    x = fo.make_input(batch, h, w, 12)
+    model = build_model(sd, nc, False, DEV, precision='bf16')
+    eng = model._engine(DEV)
+    xd = torch.from_numpy(x).to(DEV)
+    full_logits = model(xd)[0]
+    full_mask = model.predict(xd)
+    assert torch.isfinite(full_logits).all()
+    eng.set_micro_batch(5)                      # different tile -> CTA assignment, ragged last micro-batch
+    assert torch.equal(model.predict(xd), full_mask)
+    assert torch.equal(model(xd)[0], full_logits)
+    eng.set_micro_batch(0)
+    for i in (0, batch // 2, batch - 1):        # a single image: every CTA gets at most a few tiles
+        assert torch.equal(model.predict(xd[i:i + 1].contiguous()), full_mask[i:i + 1])
+    # the same through the uint8 HWC input format (normalisation folded into the stem weights)
+    xu = torch.randint(0, 256, (batch, h, w, 3), dtype=torch.uint8, device=DEV)
+    mu = model.predict(xu)
+    eng.set_micro_batch(3)
+    assert torch.equal(model.predict(xu), mu)
+    eng.set_micro_batch(0)
+    assert torch.equal(model.predict(xu[batch - 1:].contiguous()), mu[batch - 1:])
+    # and against the fp32 path: the masks agree within the bf16 tolerance on every image
+    m32 = build_model(sd, nc, False, DEV, precision='fp32').predict(xd)
+    assert (m32 != full_mask).float().mean().item() < MASK_TOL
