@@ -42,7 +42,9 @@ struct DsTcCfg {
     static constexpr int oWd = oB + B_BYTES;             // bf16 [9][CIN]
     static constexpr int oBd = oWd + round_up(9 * CIN * 2, 16);
     static constexpr int oBp = oBd + CIN * 4;
-    static constexpr int oB2 = round_up(oBp + COUT * 4, 128);   // HEAD: head weight image (ncp16 x COUT), sized at run time
+    static constexpr int oB2 = round_up(oBp + COUT * 4, 128);   // HEAD: head weight image (ncp16 x COUT), sized at run time;
+                                                                 // else: per-warp output staging (16 x 32 pixels x CP channels)
+    static constexpr int STAGE_BYTES = HEAD ? 0 : 16 * 32 * (COUT / ((COUT % 32 == 0) ? 4 : COUT / 16)) * 2;
     static constexpr int NPART = (COUT % 32 == 0) ? 4 : COUT / 16;   // epilogue column parts (16 warps = 4 quarters x 4 parts)
     static constexpr int CP = COUT / NPART;                           // columns per part: 32, 16 or 16
     static_assert(CIN % 16 == 0 && COUT % 16 == 0 && CP % 8 == 0 && NPART <= 4, "shape");
@@ -141,8 +143,6 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
             int n, oy0, ox0;
             tile_origin(blockIdx.x + lt * gstep, n, oy0, ox0);
             const int p = q * 32 + lane;
-            const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
-            const bool live = (oy < Ho) && (ox < Wo);
             mbar_wait(&bar_mma[lt & 1], (lt >> 1) & 1);
             tc_fence_after_sync();
             if (part < C::NPART) {
@@ -151,6 +151,11 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
                 for (int c0 = 0; c0 < CP; c0 += 8)
                     tmem_ld_32x32b_x8(tmem + ((uint32_t)(q * 32) << 16) + (lt & 1) * COUT + part * CP + c0, r + c0);
                 tmem_ld_wait();
+                // !HEAD: a lane owns one pixel (TMEM lane) and CP channels; storing that directly touches 32 different 128-byte
+                // lines per instruction.  The warp stages its 32 x CP block in a private shared-memory slab (XOR-swizzled
+                // 16-byte chunks) and writes it back with consecutive lanes on consecutive chunks: 4x fewer lines per store.
+                constexpr int NCK8 = CP / 8;                              // 16-byte chunks per pixel in this warp's block: 4 or 2
+                const uint32_t slab = sB2 + warp * (32 * CP * 2);
 #pragma unroll
                 for (int c0 = 0; c0 < CP; c0 += 8) {
                     const int co = part * CP + c0;
@@ -162,10 +167,25 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
                     const uint32_t c = packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y);
                     const uint32_t d = packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w);
                     if (!HEAD) {
-                        if (live) *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * COUT + co) = make_uint4(a, b, c, d);
+                        const int sw = NCK8 == 4 ? (lane >> 1) & 3 : (lane >> 2) & 1;
+                        sts128(slab + lane * (CP * 2) + (((c0 >> 3) ^ sw) << 4), a, b, c, d);
                     } else {
                         sts128(sA + (lt & 1) * C::A_BYTES + a_tile_off(p, co >> 3), a, b, c, d);   // its MMA has completed
                     }
+                }
+                if (!HEAD) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < NCK8; ++i) {
+                        const int px = lane / NCK8 + i * (32 / NCK8), ch = lane % NCK8;   // pixel within the warp's 32, chunk
+                        const int sw = NCK8 == 4 ? (px >> 1) & 3 : (px >> 2) & 1;
+                        const uint4 v = lds128(slab + px * (CP * 2) + ((ch ^ sw) << 4));
+                        const int pp = q * 32 + px;
+                        const int yy = oy0 + (pp >> 4), xx = ox0 + (pp & 15);
+                        if (yy < Ho && xx < Wo)
+                            *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + yy) * Wo + xx) * COUT + part * CP + ch * 8) = v;
+                    }
+                    __syncwarp();
                 }
             }
             if (HEAD) {
@@ -277,7 +297,7 @@ static cudaError_t run_ds_tc(const bf16* in, const DsW& w, const bf16* wp_img, b
     int ncp16 = 0;
     if (HEAD) { h = *head; ncp16 = round_up(h.nc, 16); }
     if (HEAD && 2 * COUT + 2 * ncp16 > 512) return cudaErrorInvalidValue;   // TMEM budget (nc <= 128)
-    const size_t smem = C::oB2 + (HEAD ? (size_t)ncp16 * COUT * 2 : 0);
+    const size_t smem = C::oB2 + (HEAD ? (size_t)ncp16 * COUT * 2 : (size_t)C::STAGE_BYTES);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static unsigned long long configured = 0;
     static size_t configured_bytes = 0;
