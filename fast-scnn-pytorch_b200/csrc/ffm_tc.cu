@@ -145,27 +145,37 @@ ffm_tc_kernel(const __grid_constant__ CUtensorMap hmap, const bf16* __restrict__
         auto epilogue = [&](int lt) {
             int n, oy0, ox0;
             tile_origin(lt, n, oy0, ox0);
-            const int p = q * 32 + lane;
-            const int oy = oy0 + (p >> 4), ox = ox0 + (p & 15);
             mbar_wait(&bar_mma[lt & 1], (lt >> 1) & 1);
             tc_fence_after_sync();
             uint32_t r[32];
             tmem_ld_32x32b_x32(tmem + ((uint32_t)(q * 32) << 16) + (lt & 1) * kCO + part * 32, r);
             tmem_ld_wait();
-            if (oy < Hh && ox < Wh) {
-                bf16* op = out + (((size_t)n * Hh + oy) * Wh + ox) * kCO + part * 32;
+            // A lane owns one pixel (TMEM lane) x 32 channels; storing that directly touches 32 different 128-byte lines per
+            // instruction.  Stage the warp's 32 x 32 block in a private 2 KB slab (XOR-swizzled 16-byte chunks) inside the
+            // depthwise half of A[lt&1] -- its MMA has completed and the next writer (depthwise lt+2) is behind the named
+            // barrier every warp passes after this epilogue -- and write it back with consecutive lanes on consecutive chunks.
+            const uint32_t slab = sA + (lt & 1) * kABytes + 128 * kCH * 2 + warp * 2048;
 #pragma unroll
-                for (int c0 = 0; c0 < 32; c0 += 8) {
-                    const float4 ba = *reinterpret_cast<const float4*>(Bcs + part * 32 + c0);
-                    const float4 bb = *reinterpret_cast<const float4*>(Bcs + part * 32 + c0 + 4);
-                    const uint32_t* q8 = r + c0;
-                    *reinterpret_cast<uint4*>(op + c0) =
-                        make_uint4(packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
-                                   packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
-                                   packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
-                                   packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
-                }
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+                const float4 ba = *reinterpret_cast<const float4*>(Bcs + part * 32 + c0);
+                const float4 bb = *reinterpret_cast<const float4*>(Bcs + part * 32 + c0 + 4);
+                const uint32_t* q8 = r + c0;
+                sts128(slab + lane * 64 + (((c0 >> 3) ^ ((lane >> 1) & 3)) << 4),
+                       packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
+                       packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
+                       packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
+                       packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int px = (lane >> 2) + 8 * i, ch = lane & 3;
+                const uint4 v = lds128(slab + px * 64 + ((ch ^ ((px >> 1) & 3)) << 4));
+                const int pp = q * 32 + px;
+                const int yy = oy0 + (pp >> 4), xx = ox0 + (pp & 15);
+                if (yy < Hh && xx < Wh) *reinterpret_cast<uint4*>(out + (((size_t)n * Hh + yy) * Wh + xx) * kCO + part * 32 + ch * 8) = v;
+            }
+            __syncwarp();
         };
 #pragma unroll 1
         for (int lt = 0; lt < my_tiles; ++lt) {
