@@ -32,10 +32,15 @@ constexpr int kNTall = kNT + 32;   // + the control warp
 
 #ifdef FSCNN_PHASE_TIMING   // debug build only: clock64 stamps of the second tile of CTA 5 of the <64,64,1> kernel
 __device__ long long g_bneck_phase[64];
-#define BN_STAMP(i) do { if (CIN == 64 && STRIDE == 1 && tid == 0 && blockIdx.x == 5 && lt == 1) g_bneck_phase[i] = clock64(); } while (0)
+#define BN_STAMP(i) do { if (CIN == 64 && COUT == 64 && tid == 0 && blockIdx.x == 5 && lt == 1) g_bneck_phase[i] = clock64(); } while (0)
 #else
 #define BN_STAMP(i) do { } while (0)
 #endif
+
+// 16-byte chunk permutation of an E row (128 B per halo pixel).  The expand epilogue writes 8 consecutive pixels per
+// quarter-warp, the stride-2 depthwise reads every other pixel: XOR-ing with (pin ^ pin >> 3) keeps both conflict-free
+// (pin & 7 alone makes the stride-2 reads 2-way conflicted: only 4 of the 8 chunk slots get used).
+__device__ __forceinline__ int e_swz(int pin) { return (pin ^ (pin >> 3)) & 7; }
 
 template <int CIN, int COUT, int STRIDE>
 struct TcCfg {
@@ -200,7 +205,7 @@ bottleneck_tc_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __res
                                 const float4 ba = *reinterpret_cast<const float4*>(Bes + c0 + h * 8);
                                 const float4 bb = *reinterpret_cast<const float4*>(Bes + c0 + h * 8 + 4);
                                 const uint32_t* q8 = r + h * 8;
-                                sts128(sE + pin * (CE * 2) + ((((c0 >> 3) + h) ^ (pin & 7)) << 4),
+                                sts128(sE + pin * (CE * 2) + ((((c0 >> 3) + h) ^ e_swz(pin)) << 4),
                                        packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
                                        packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
                                        packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
@@ -208,7 +213,7 @@ bottleneck_tc_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __res
                             }
                         } else {     // outside the image: the depthwise zero padding
 #pragma unroll
-                            for (int h = 0; h < 4; ++h) sts128(sE + pin * (CE * 2) + ((((c0 >> 3) + h) ^ (pin & 7)) << 4), 0u, 0u, 0u, 0u);
+                            for (int h = 0; h < 4; ++h) sts128(sE + pin * (CE * 2) + ((((c0 >> 3) + h) ^ e_swz(pin)) << 4), 0u, 0u, 0u, 0u);
                         }
                     }
                 }
@@ -241,7 +246,7 @@ bottleneck_tc_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __res
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) {
                             const int pin = iy * IW + x * STRIDE + kx;
-                            const uint4 v = lds128(sE + pin * (CE * 2) + ((j ^ (pin & 7)) << 4));
+                            const uint4 v = lds128(sE + pin * (CE * 2) + ((j ^ e_swz(pin)) << 4));
 #pragma unroll
                             for (int o = 0; o < 2; ++o) {
                                 const int ky = r - o * STRIDE;

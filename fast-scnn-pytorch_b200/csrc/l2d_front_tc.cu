@@ -58,6 +58,10 @@ __device__ __forceinline__ void cp_async4z(uint32_t dst, const void* src, bool v
     const int sz = valid ? 4 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
+// E tile: 64 bytes (32 channels) per stem pixel, two pixels per 128-byte line; the 16-byte chunk slot within the line is
+// XOR-permuted so that both the epilogue (8 consecutive pixels per quarter-warp) and the stride-2 depthwise (every other
+// pixel) touch 8 distinct slots
+__device__ __forceinline__ uint32_t e_off(int m, int k8) { return (uint32_t)(m >> 1) * 128 + (((((m & 1) << 2) | k8) ^ ((m >> 1) & 7)) << 4); }
 // A operand with row-group-major core matrices: element (row m, 16-byte chunk k8) ; LBO = 128, SBO = 512
 __device__ __forceinline__ uint32_t a_rg_off(int m, int k8) { return (uint32_t)(m >> 3) * 512 + k8 * 128 + (m & 7) * 16; }
 }  // namespace
@@ -297,7 +301,7 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
                         const float4 ba = *reinterpret_cast<const float4*>(Bss + g * 8);
                         const float4 bb = *reinterpret_cast<const float4*>(Bss + g * 8 + 4);
                         const uint32_t* q8 = r + g * 8;
-                        sts128(sIn + m * 64 + ((g ^ ((m >> 1) & 3)) << 4),
+                        sts128(sIn + e_off(m, g),
                                packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
                                packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
                                packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
@@ -305,7 +309,7 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
                     }
                 } else {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) sts128(sIn + m * 64 + ((g ^ ((m >> 1) & 3)) << 4), 0u, 0u, 0u, 0u);
+                    for (int g = 0; g < 4; ++g) sts128(sIn + e_off(m, g), 0u, 0u, 0u, 0u);
                 }
             }
         }
@@ -334,7 +338,7 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int m = sr * SW + 2 * xq + kx;
-                    const uint4 v = lds128(sIn + m * 64 + ((k8 ^ ((m >> 1) & 3)) << 4));
+                    const uint4 v = lds128(sIn + e_off(m, k8));
 #pragma unroll
                     for (int o = 0; o < 2; ++o) {
                         const int ky = r - 2 * o;
