@@ -267,6 +267,12 @@ struct Loader {
             err = fail(FSCNN_ECUDA, "fold kernel launch failed for '%s': %s", conv.c_str(),
                        cudaGetErrorString(cudaGetLastError()));
     }
+    // bf16 contexts only: depthwise tables become bf16-representable with error-diffused rounding (fold.cu)
+    void round_dw(const fscnn_ctx* c, float* wd, int ch) {
+        if (err || c->prec != FSCNN_PREC_BF16) return;
+        if (launch_dw_round_bf16(wd, ch, s) != cudaSuccess)
+            err = fail(FSCNN_ECUDA, "depthwise rounding launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     void fold_umma(const std::string& conv, const std::string& bn, int nrows, int kdim, int nc, int kc, bf16* out) {
         if (err) return;
         const float* w = get(conv + ".weight", (int64_t)nrows * kdim);
@@ -496,6 +502,7 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
     for (int i = 0; i < 4; ++i) {
         const std::string p = dss[i].p;
         L.fold(p + ".conv.0", false, p + ".conv.1", dss[i].cin, 9, 1, 0, P + f.ds_wd[i], dss[i].cin, P + f.ds_bd[i]);
+        L.round_dw(c, P + f.ds_wd[i], dss[i].cin);
         L.fold(p + ".conv.3", false, p + ".conv.4", dss[i].cout, dss[i].cin, 1, 0, P + f.ds_wp[i], dss[i].cout, P + f.ds_bp[i]);
         c->ds[i] = {P + f.ds_wd[i], P + f.ds_bd[i], P + f.ds_wp[i], P + f.ds_bp[i]};
         if (c->prec == FSCNN_PREC_BF16) {
@@ -509,6 +516,7 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         const int ci = kBnecks[i].cin, ce = 6 * ci, co = kBnecks[i].cout;
         L.fold(p + ".0.conv.0", false, p + ".0.conv.1", ce, ci, 1, 0, P + f.bn_we[i], ce, P + f.bn_be[i]);
         L.fold(p + ".1.conv.0", false, p + ".1.conv.1", ce, 9, 1, 0, P + f.bn_wd[i], ce, P + f.bn_bd[i]);
+        L.round_dw(c, P + f.bn_wd[i], ce);
         L.fold(p + ".2", false, p + ".3", co, ce, 1, 0, P + f.bn_wp[i], co, P + f.bn_bp[i]);
         c->bn[i] = {P + f.bn_we[i], P + f.bn_be[i], P + f.bn_wd[i], P + f.bn_bd[i], P + f.bn_wp[i], P + f.bn_bp[i]};
         if (c->prec == FSCNN_PREC_BF16) {
@@ -537,6 +545,7 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
     c->ppm.wo_x = P + f.ppm_wo;
     c->ppm.bo = P + f.ppm_bo;
     L.fold("feature_fusion.dwconv.conv.0", false, "feature_fusion.dwconv.conv.1", 128, 9, 1, 0, P + f.ffm_wd, 128, P + f.ffm_bd);
+    L.round_dw(c, P + f.ffm_wd, 128);
     L.fold("feature_fusion.conv_higher_res.0", true, "feature_fusion.conv_higher_res.1", 128, 64, 1, 0, P + f.ffm_wcat, 128,
            P + f.ffm_bcat, 0);
     L.fold("feature_fusion.conv_lower_res.0", true, "feature_fusion.conv_lower_res.1", 128, 128, 1, 0,

@@ -81,7 +81,7 @@ __global__ void stem_refold_kernel(const float* __restrict__ w, const float* __r
 }
 
 // Stem weights for the gather-free fused kernel (l2d_front_tc.cu): one 32 x 16 B-operand image per kernel row ky with
-// k = kx * 4 + c over 4 pixels x RGBX; the 4th pixel and the 4th channel get zero weights.  w is the BN-folded
+// k = kx * 4 + c over 4 pixels x RGBX; the 4th pixel and the 4th channel get zero weights (except the two bias slots, below).  w is the BN-folded
 // [27][32] table (k = ci*9 + ky*3 + kx).  With `norm` the uint8 ToTensor + Normalize is folded in as in
 // stem_refold_kernel and the matching bias is written.
 __global__ void stem_pack_rgbx_kernel(const float* __restrict__ w, const float* __restrict__ b, StemIn in, int norm,
@@ -100,6 +100,12 @@ __global__ void stem_pack_rgbx_kernel(const float* __restrict__ w, const float* 
             }
             img[ky * 512 + ((k >> 3) * 4 + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(v);
         }
+    // The kernel stores 1.0 in the X channel of every pixel, so the bias rides along in the contraction: its bf16 head in the
+    // X slot of pixel 0 of kernel row 0 (k = 3), the remainder in the X slot of pixel 1 (k = 7); relative error 2^-17.
+    const __nv_bfloat16 bh = __float2bfloat16_rn(acc);
+    const __nv_bfloat16 bl = __float2bfloat16_rn(acc - __bfloat162float(bh));
+    img[((n >> 3)) * 64 + (n & 7) * 8 + 3] = bh;
+    img[((n >> 3)) * 64 + (n & 7) * 8 + 7] = bl;
     if (bias) bias[n] = acc;
 }
 
@@ -116,6 +122,37 @@ cudaError_t launch_stem_refold(const float* w, const float* b, const StemIn& in,
 cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* var, int nrows, int kdim, int nc, int kc,
                              bf16* out, cudaStream_t s) {
     fold_umma_kernel<<<ceil_div(nrows * kdim, 256), 256, 0, s>>>(w, gamma, var, nrows, kdim, nc, kc, out);
+    return cudaGetLastError();
+}
+
+// bf16 path: the depthwise kernels multiply with FHFMA.BF16, so the BN-folded depthwise weights [9][C] are rounded to
+// bf16.  Every depthwise input of the network is non-negative (post-ReLU) and spatially smooth, so the harmful part of
+// the rounding error is its sum over the 9 taps (a gain error on the local mean).  Error-diffused rounding removes it:
+// taps are visited from the largest to the smallest magnitude, each is rounded after adding the error carried from the
+// previous ones; the sum of the 9 rounded weights then differs from the exact sum by at most half an ulp of the
+// SMALLEST tap.  The table is rewritten in place with the bf16-representable values (the kernels' own conversion is
+// then exact).  One thread per channel.
+__global__ void dw_round_bf16_kernel(float* __restrict__ wd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float w[9];
+    int order[9];
+    for (int t = 0; t < 9; ++t) { w[t] = wd[t * C + c]; order[t] = t; }
+    for (int i = 0; i < 9; ++i)            // selection sort by |w| descending (9 elements)
+        for (int j = i + 1; j < 9; ++j)
+            if (fabsf(w[order[j]]) > fabsf(w[order[i]])) { const int o = order[i]; order[i] = order[j]; order[j] = o; }
+    float carry = 0.f;
+    for (int i = 0; i < 9; ++i) {
+        const int t = order[i];
+        const float v = w[t] + carry;
+        const float q = __bfloat162float(__float2bfloat16_rn(v));
+        carry = v - q;
+        wd[t * C + c] = q;
+    }
+}
+
+cudaError_t launch_dw_round_bf16(float* wd, int c, cudaStream_t s) {
+    dw_round_bf16_kernel<<<ceil_div(c, 128), 128, 0, s>>>(wd, c);
     return cudaGetLastError();
 }
 

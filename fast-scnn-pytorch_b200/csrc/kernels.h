@@ -75,6 +75,8 @@ cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* va
 // we_img: expand weights [6cin x cin] in chunks of CE rows; wp_img: project weights [cout x 6cin] in chunks of CE columns,
 // CE = bottleneck_tc_chunk(stride)
 int bottleneck_tc_chunk(int stride);
+// bf16 path: error-diffused rounding of a folded depthwise table [9][c] to bf16-representable values, in place
+cudaError_t launch_dw_round_bf16(float* wd, int c, cudaStream_t s);
 // tab_img: the constant tables packed by launch_pack_bneck_tab (bottleneck_tc_tab_bytes(cin, cout) bytes, 16-byte aligned)
 size_t bottleneck_tc_tab_bytes(int cin, int cout);
 cudaError_t launch_pack_bneck_tab(const BneckW& w, int cexp, int cout, unsigned char* out, cudaStream_t s);

@@ -10,7 +10,8 @@
 //   -> repacked once as bf16 RGBX pixels (8 bytes each), even and odd patch rows in separate planes of pitch 544 B.
 //   The stem's im2col matrix is then never built: with 4-channel pixels a stride-2 step is exactly 16 bytes, the
 //   row pitch of a SWIZZLE_NONE core matrix, so row (sr, sc) of the A operand of kernel row ky IS the 32 bytes at
-//   plane[(2 sr + ky)] + 16 sc (4 pixels x 4 channels = K 16; the 4th pixel and 4th channel meet zero weights).
+//   plane[(2 sr + ky)] + 16 sc (4 pixels x 4 channels = K 16; the 4th pixel meets zero weights, the 4th channel is the constant 1.0 and
+//   carries the folded BN bias through the contraction as a bf16 head + remainder pair).
 //   Consecutive rows overlap by half (LBO = 16 B, SBO = 128 B; verified by tc_probe.cu), stem rows are 34 A rows apart.
 //   -> 15 MMAs (5 row tiles x 3 kernel rows, K = 16, N = 32) into TMEM -> bias, ReLU, zero outside the stem image
 //   -> bf16 E[561][32] (over the dead raw patch) -> depthwise s2 (FHFMA.BF16, fp32 accumulate) -> A2[128 x 32]
@@ -27,7 +28,7 @@
 namespace fscnn {
 
 namespace {
-constexpr int SH = 17, SW = 33, SPIX = SH * SW;       // stem pixels per tile (561)
+constexpr int SH = 17, SW = 33;                        // stem pixels per tile: 17 x 33 = 561
 constexpr int SWP = 34, MROWS = SH * SWP;              // A rows: stem row pitch 34 (column 33 is a dummy) -> 578
 constexpr int NMT = 5;                                 // MMA row tiles of 128 A rows
 constexpr int PR = 35, PC = 67;                        // input patch rows / columns the tile needs
@@ -83,7 +84,6 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ __align__(8) uint64_t bar_stem[NMT], bar_pw, bar_patch[2], bar_repack, bar_dw;
     __shared__ uint32_t tmem_base_s;
-    float* Bss = reinterpret_cast<float*>(sm + oBs);
     float* Bds = reinterpret_cast<float*>(sm + oBd);
     float* Bps = reinterpret_cast<float*>(sm + oBp);
     const uint32_t sBuf = smem_u32(sm + oBuf), sP2 = smem_u32(sm + oP2), sA = smem_u32(sm + oA2), sWs = smem_u32(sm + oWs), sWp = smem_u32(sm + oWp),
@@ -102,7 +102,7 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
     for (int i = tid; i < kP2Bytes / 16; i += kFrontThreads) reinterpret_cast<uint4*>(sm + oP2)[i] = make_uint4(0u, 0u, 0u, 0u);   // pad pixels stay finite
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWp)[tid] = __ldg(reinterpret_cast<const uint4*>(wp_img) + tid);
     if (tid < 9 * 32 / 2) reinterpret_cast<uint32_t*>(sm + oWd)[tid] = packbf(__ldg(w.wd + 2 * tid), __ldg(w.wd + 2 * tid + 1));
-    if (tid < 32) { Bss[tid] = __ldg(bs + tid); Bds[tid] = __ldg(w.bd + tid); }
+    if (tid < 32) Bds[tid] = __ldg(w.bd + tid);
     if (tid < 48) Bps[tid] = __ldg(w.bp + tid);
 
     // fallback when the rows are not 16-byte aligned (no TMA): the compute threads fetch the patch of a tile with 4-byte
@@ -270,7 +270,7 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
                     const float* q = reinterpret_cast<const float*>(patch) + r * PLD + px + 2;
                     v0 = q[0]; v1 = q[PR * PLD]; v2 = q[2 * PR * PLD];
                 }
-                sts64(sP2 + (r & 1) * (18 * kPP) + (r >> 1) * kPP + px * 8, packbf(v0, v1), packbf(v2, 0.f));
+                sts64(sP2 + (r & 1) * (18 * kPP) + (r >> 1) * kPP + px * 8, packbf(v0, v1), packbf(v2, 1.f));   // X = 1: carries the bias through the MMA
             }
         }
         fence_async_proxy();
@@ -298,14 +298,12 @@ l2d_front_kernel(const __grid_constant__ CUtensorMap xmap, int use_tma, const vo
                 if (ok) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const float4 ba = *reinterpret_cast<const float4*>(Bss + g * 8);
-                        const float4 bb = *reinterpret_cast<const float4*>(Bss + g * 8 + 4);
-                        const uint32_t* q8 = r + g * 8;
+                        const uint32_t* q8 = r + g * 8;      // the bias is already in the accumulator (X-channel trick)
                         sts128(sIn + e_off(m, g),
-                               packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
-                               packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
-                               packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
-                               packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
+                               packbf_relu(__uint_as_float(q8[0]), __uint_as_float(q8[1])),
+                               packbf_relu(__uint_as_float(q8[2]), __uint_as_float(q8[3])),
+                               packbf_relu(__uint_as_float(q8[4]), __uint_as_float(q8[5])),
+                               packbf_relu(__uint_as_float(q8[6]), __uint_as_float(q8[7])));
                     }
                 } else {
 #pragma unroll
