@@ -95,6 +95,7 @@ struct fscnn_ctx {
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
         size_t bn_we_img[9], bn_wp_img[9], bn_tab_img[9];   // bf16 tcgen05 operand images + constant tables (offsets still in floats)
+        size_t bn_weT_img[9], bn_wpT_img[9], bn_tabT_img[9]; // stride-1 layers: operands of the transposed-expand kernel
         size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8, stem_imgx, stem_imgx_u8;
     } off{};
     // device pointers resolved by load_weights
@@ -104,6 +105,10 @@ struct fscnn_ctx {
     const bf16* bn_we_img[9]{};
     const bf16* bn_wp_img[9]{};
     const unsigned char* bn_tab_img[9]{};
+    const bf16* bn_weT_img[9]{};
+    const bf16* bn_wpT_img[9]{};
+    const unsigned char* bn_tabT_img[9]{};
+    int s1_transposed = 1;   // bf16 stride-1 bottlenecks: transposed-expand kernel (0 = the three-role kernel)
     const bf16* ds_wp_img[4]{};
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
@@ -223,6 +228,11 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
             f.bn_we_img[i] = take((size_t)ce * ci / 2);
             f.bn_wp_img[i] = take((size_t)co * ce / 2);
             f.bn_tab_img[i] = take((bottleneck_tc_tab_bytes(ci, co) + 3) / 4);
+            if (kBnecks[i].stride == 1) {
+                f.bn_weT_img[i] = take((bottleneck_s1t_we_bytes(ci) + 3) / 4);
+                f.bn_wpT_img[i] = take((bottleneck_s1t_wp_bytes(ci, co) + 3) / 4);
+                f.bn_tabT_img[i] = take((bottleneck_s1t_tab_bytes(ci, co) + 3) / 4);
+            }
         }
     if (c->prec == FSCNN_PREC_BF16) {
         for (int i = 0; i < 4; ++i) f.ds_wp_img[i] = take((size_t)dss[i].cin * dss[i].cout / 2);
@@ -348,6 +358,9 @@ cudaError_t bottleneck_dispatch<float>(fscnn_ctx* c, int i, const float* in, flo
 template <>
 cudaError_t bottleneck_dispatch<bf16>(fscnn_ctx* c, int i, const bf16* in, bf16* out, int m, int hi, int wi, int ho, int wo,
                                       cudaStream_t s) {
+    if (kBnecks[i].stride == 1 && c->s1_transposed)
+        return launch_bottleneck_s1t_tc(kBnecks[i].cin, kBnecks[i].cout, in, c->bn_tabT_img[i], c->bn_weT_img[i], c->bn_wpT_img[i], out,
+                                        m, hi, wi, s);
     return launch_bottleneck_tc(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn_tab_img[i], c->bn_we_img[i],
                                 c->bn_wp_img[i], out, m, hi, wi, ho, wo, s);
 }
@@ -531,6 +544,19 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
             if (!L.err && launch_pack_bneck_tab(c->bn[i], ce, co, tab, L.s) != cudaSuccess)
                 L.err = fail(FSCNN_ECUDA, "table pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->bn_tab_img[i] = tab;
+            if (kBnecks[i].stride == 1) {
+                bf16* weT = reinterpret_cast<bf16*>(P + f.bn_weT_img[i]);
+                bf16* wpT = reinterpret_cast<bf16*>(P + f.bn_wpT_img[i]);
+                unsigned char* tabT = reinterpret_cast<unsigned char*>(P + f.bn_tabT_img[i]);
+                if (!L.err && cudaMemsetAsync(wpT, 0, bottleneck_s1t_wp_bytes(ci, co), L.s) != cudaSuccess)
+                    L.err = fail(FSCNN_ECUDA, "memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+                L.fold_umma(p + ".2", p + ".3", co, ce, co, 128, wpT);              // project: chunks of 128 columns
+                if (!L.err && launch_pack_s1t(c->bn[i], ci, co, weT, tabT, L.s) != cudaSuccess)
+                    L.err = fail(FSCNN_ECUDA, "s1t pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                c->bn_weT_img[i] = weT;
+                c->bn_wpT_img[i] = wpT;
+                c->bn_tabT_img[i] = tabT;
+            }
         }
     }
     for (int i = 0; i < 4; ++i) {
@@ -599,6 +625,7 @@ int fscnn_set_input_format(fscnn_ctx* c, int format, const float* mean3, const f
 int fscnn_set_option(fscnn_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(FSCNN_EINVAL, "null argument");
     if (!strcmp(key, "fuse_front")) { c->fuse_front = value ? 1 : 0; return FSCNN_OK; }
+    if (!strcmp(key, "s1_transposed")) { c->s1_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "micro_batch")) return fscnn_set_micro_batch(c, value);
     return fail(FSCNN_ENOENT, "unknown option '%s'", key);
 }

@@ -1,0 +1,384 @@
+// bottleneck_s1t_tc.cu -- bf16 LinearBottleneck, stride 1 (reference models/fast_scnn.py:95-115), with the expand 1x1
+// computed TRANSPOSED so that the expanded tensor never touches shared memory:
+//
+//   expand   E^T[128 ch x 192 px] = We^T[128 ch x CIN] * X^T   (tcgen05.mma, A = weight chunk, B = the TMA halo tile, which
+//            is already K-major [pixel][cin]).  TMEM lane = expanded channel, TMEM column = halo pixel (10 x 18 = 180 used).
+//            The BN-folded expand bias rides in 16 extra K columns (bf16 head + remainder) against a constant block of ones.
+//   depthwise each thread owns ONE expanded channel (its TMEM lane) and two output rows: it pulls 4 halo rows x 18 columns
+//            out of TMEM (tcgen05.ld), ReLU + bf16-packs them in registers (cvt.rn.relu.bf16x2) and runs the 3x3 taps as
+//            FHFMA.BF16 with its 9 weights in registers.  No E tile, no LDS, no bank conflicts.
+//   project  D[128 px x 128 ch] (bf16, K-major A operand written by the depthwise threads) * Wp chunk -> TMEM accumulator
+//            over the chunks of 128 expanded channels; + bias (+ residual) -> bf16 NHWC.
+//
+// One persistent CTA per SM: 16 compute warps (TMEM lane quarter = warp % 4, row strip = warp / 4) + a control warp whose
+// lane 0 issues every TMA load, bulk copy and MMA from a non-blocking event loop.  The expand accumulator and D are
+// double-buffered: the tensor core works two chunks ahead of the CUDA cores; every hand-off is an mbarrier.
+#include "kernels.h"
+#include "tma_host.h"
+#include "umma.cuh"
+
+namespace fscnn {
+
+namespace {
+constexpr int kTWarps = 16;
+constexpr int kTThreads = (kTWarps + 1) * 32;
+
+__device__ __forceinline__ bool mbar_test_t(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+          "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+          "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+          "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+          "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+}
+
+// acc += bf16 half XH of x  *  bf16 half WH of w   (FHFMA.BF16 with register-half selectors, fp32 accumulate)
+// (xh / wh are compile-time constants after unrolling)
+__device__ __forceinline__ void fhfma_sel(float& acc, uint32_t x, int xh, uint32_t w, int wh) {
+    const uint16_t xs = xh ? (uint16_t)(x >> 16) : (uint16_t)x;
+    const uint16_t ws = wh ? (uint16_t)(w >> 16) : (uint16_t)w;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(xs), "h"(ws));
+}
+
+__device__ __forceinline__ void sts_bf16_relu(uint32_t addr, float v) {
+    uint16_t h;
+    asm("cvt.rn.relu.bf16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(h) : "memory");
+}
+}  // namespace
+
+template <int CIN, int COUT>
+struct T1Cfg {
+    static constexpr int TH = 8, TW = 16, IH = 10, IW = 18, PIN = IH * IW, NB = 192;
+    static constexpr int CM = 128, CEXP = 6 * CIN, NCH = (CEXP + CM - 1) / CM;
+    static constexpr int KA = CIN + 16;                        // expand K: input channels + the bias columns
+    static constexpr int X_BYTES = PIN * CIN * 2;              // [CIN/8][PIN][8]: LBO = PIN*16, SBO = 128
+    static constexpr int XS = X_BYTES;
+    static constexpr int WE_BYTES = CM * KA * 2;               // A image [KA/8][128 rows][8]: LBO = 2048, SBO = 128
+    static constexpr int WP_BYTES = COUT * CM * 2;             // B image [128/8][COUT rows][8]: LBO = COUT*16, SBO = 128
+    static constexpr int D_LBO = 128 * 16 + 16;                // K-major D tile; the +16 spreads the four 8-channel groups of a warp over the banks
+    static constexpr int D_BYTES = (CM / 8) * D_LBO;
+    static constexpr int ONES_BYTES = 2 * NB * 16;             // B rows {1, 1, 0 x 6} | zeros: the bias columns' partner
+    static constexpr int LIMIT = 227 * 1024 - 256;
+    static constexpr int FIXED = 2 * WE_BYTES + 2 * D_BYTES + ONES_BYTES;
+    static constexpr int XB = (FIXED + 2 * XS + 2 * WP_BYTES <= LIMIT) ? 2 : 1;
+    static constexpr int WPB = (FIXED + XB * XS + 2 * WP_BYTES <= LIMIT) ? 2 : 1;
+    static constexpr int oX = 0;
+    static constexpr int oWe = XB * XS;
+    static constexpr int oWp = oWe + 2 * WE_BYTES;
+    static constexpr int oD = oWp + WPB * WP_BYTES;
+    static constexpr int oOnes = oD + 2 * D_BYTES;
+    static constexpr int smem_bytes = oOnes + ONES_BYTES;
+    static constexpr int TM_PROJ = 2 * NB;                     // expand accumulators: 2 buffers x 192 columns
+    static constexpr int TM_COLS = 512;
+    static constexpr int TAB_BYTES = NCH * CM * 32 + COUT * 4; // per expanded channel {bf16 w[9], pad, f32 bd, pad} | f32 Bp[COUT]
+    static_assert(TM_PROJ + COUT <= 512 && smem_bytes <= LIMIT, "budget");
+    static_assert(CIN % 16 == 0 && COUT % 32 == 0 && XS % 128 == 0, "shape");
+};
+
+template <int CIN, int COUT, bool RES>
+__global__ void __launch_bounds__(kTThreads, 1)
+bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restrict__ in, const unsigned char* __restrict__ tab,
+                      const bf16* __restrict__ we_img, const bf16* __restrict__ wp_img, bf16* __restrict__ out, int H, int W,
+                      int tiles_x, int tiles_y, int ntiles) {
+    using C = T1Cfg<CIN, COUT>;
+    constexpr int IW = C::IW, NCH = C::NCH, PIN = C::PIN, XB = C::XB, WPB = C::WPB, CM = C::CM;
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) uint64_t bar_we[2], bar_wp[2], bar_exp[2], bar_tmfree[2], bar_dready[2], bar_proj[2], bar_x[2],
+        bar_projfree, bar_tiledone;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t sX = smem_u32(sm + C::oX), sWe = smem_u32(sm + C::oWe), sWp = smem_u32(sm + C::oWp), sD = smem_u32(sm + C::oD),
+                   sOnes = smem_u32(sm + C::oOnes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gstep = gridDim.x;
+    const int my_tiles = (ntiles - (int)blockIdx.x + gstep - 1) / gstep;
+    const int total = my_tiles * NCH;                     // chunks this CTA processes, numbered g = lt * NCH + e
+    auto tile_origin = [&](int lt, int& n, int& oy0, int& ox0) {
+        const int tile = blockIdx.x + lt * gstep;
+        const int tx = tile % tiles_x, r = tile / tiles_x;
+        n = r / tiles_y; oy0 = (r % tiles_y) * C::TH; ox0 = tx * C::TW;
+    };
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_we[i], 1); mbar_init(&bar_wp[i], 1); mbar_init(&bar_exp[i], 1); mbar_init(&bar_proj[i], 1); mbar_init(&bar_x[i], 1);
+            mbar_init(&bar_tmfree[i], kTWarps); mbar_init(&bar_dready[i], kTWarps);
+        }
+        mbar_init(&bar_projfree, kTWarps); mbar_init(&bar_tiledone, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 2 * C::NB; i += kTThreads)      // the constant B block of the bias columns
+        *reinterpret_cast<uint4*>(sm + C::oOnes + i * 16) = make_uint4(i < C::NB ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    fence_async_proxy();
+    if (warp == 0) { tmem_alloc(&tmem_base_s, C::TM_COLS); tmem_relinquish(); }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == kTWarps) {
+        // =========================== control warp ===========================
+        if (lane == 0) {
+            auto prefetch_we = [&](int g) {
+                mbar_arrive_expect_tx(&bar_we[g & 1], C::WE_BYTES);
+                bulk_g2s(sm + C::oWe + (g & 1) * C::WE_BYTES, we_img + (size_t)(g % NCH) * CM * C::KA, C::WE_BYTES, &bar_we[g & 1]);
+            };
+            auto prefetch_wp = [&](int g) {
+                mbar_arrive_expect_tx(&bar_wp[g % WPB], C::WP_BYTES);
+                bulk_g2s(sm + C::oWp + (g % WPB) * C::WP_BYTES, wp_img + (size_t)(g % NCH) * COUT * CM, C::WP_BYTES, &bar_wp[g % WPB]);
+            };
+            auto load_x = [&](int lt) {
+                int n, oy0, ox0;
+                tile_origin(lt, n, oy0, ox0);
+                const int xb = lt % XB;
+                mbar_arrive_expect_tx(&bar_x[xb], C::X_BYTES);
+                tma_load_halo(sX + xb * C::XS, &xmap, ox0 - 1, oy0 - 1, n, &bar_x[xb]);
+            };
+            constexpr uint32_t idesc_exp = make_idesc_bf16(128, C::NB);
+            constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT);
+            tma_prefetch_desc(&xmap);
+            load_x(0);
+            if (XB == 2 && my_tiles > 1) load_x(1);
+            prefetch_we(0);
+            if (total > 1) prefetch_we(1);
+            prefetch_wp(0);
+            if (WPB == 2 && total > 1) prefetch_wp(1);
+            int ke = 0, kp = 0, kw = 2, kq = WPB, kx = XB, exp_done = 0, proj_done = 0;
+#pragma unroll 1
+            while (kp < total) {
+                // ---- expand(ke): needs its halo tile (first chunk of a tile), its weight chunk, and the TMEM buffer drained ----
+                if (ke < total) {
+                    const int lt = ke / NCH, e = ke - lt * NCH, xb = lt % XB;
+                    bool ok = mbar_test_t(&bar_we[ke & 1], (ke >> 1) & 1);
+                    if (ok && e == 0) ok = mbar_test_t(&bar_x[xb], (lt / XB) & 1);
+                    if (ok && ke >= 2) ok = mbar_test_t(&bar_tmfree[ke & 1], ((ke - 2) >> 1) & 1);
+                    if (ok) {
+                        if (ke >= 2 && exp_done < ke - 1) exp_done = ke - 1;     // its TMEM was drained: expand(ke-2) has completed
+                        tc_fence_after_sync();
+                        const uint32_t a0 = sWe + (ke & 1) * C::WE_BYTES;
+#pragma unroll
+                        for (int k16 = 0; k16 < CIN / 16; ++k16) {
+                            const uint64_t da = make_smem_desc(a0 + k16 * 2 * 2048, 2048, 128);
+                            const uint64_t db = make_smem_desc(sX + xb * C::XS + k16 * 2 * (PIN * 16), PIN * 16, 128);
+                            umma_bf16_ss(tmem + (ke & 1) * C::NB, da, db, idesc_exp, k16 > 0);
+                        }
+                        umma_bf16_ss(tmem + (ke & 1) * C::NB, make_smem_desc(a0 + (CIN / 16) * 2 * 2048, 2048, 128),
+                                     make_smem_desc(sOnes, C::NB * 16, 128), idesc_exp, 1);
+                        umma_commit(&bar_exp[ke & 1]);
+                        ++ke;
+                    }
+                }
+                // ---- completion tracking of the expand MMAs, in order ----
+                if (exp_done < ke && mbar_test_t(&bar_exp[exp_done & 1], (exp_done >> 1) & 1)) ++exp_done;
+                if (kw < total && exp_done > kw - 2) { prefetch_we(kw); ++kw; }
+                if (kx < my_tiles && exp_done > (kx - XB) * NCH + NCH - 1) { load_x(kx); ++kx; }
+                // ---- project(kp): needs D written, its weight chunk, and (first chunk of a tile) the previous tile's accumulator read ----
+                {
+                    const int lt = kp / NCH, e = kp - lt * NCH;
+                    bool ok = mbar_test_t(&bar_dready[kp & 1], (kp >> 1) & 1);
+                    if (ok) ok = mbar_test_t(&bar_wp[kp % WPB], (kp / WPB) & 1);
+                    if (ok && e == 0 && lt > 0) ok = mbar_test_t(&bar_projfree, (lt - 1) & 1);
+                    if (ok) {
+                        if (kp >= 2 && proj_done < kp - 1) proj_done = kp - 1;   // D[kp&1] was rewritten: project(kp-2) has completed
+                        tc_fence_after_sync();
+                        const int ksteps = ((C::CEXP - e * CM) < CM ? (C::CEXP - e * CM) : CM) / 16;
+                        for (int k16 = 0; k16 < ksteps; ++k16) {
+                            const uint64_t da = make_smem_desc(sD + (kp & 1) * C::D_BYTES + k16 * 2 * C::D_LBO, C::D_LBO, 128);
+                            const uint64_t db = make_smem_desc(sWp + (kp % WPB) * C::WP_BYTES + k16 * 2 * (COUT * 16), COUT * 16, 128);
+                            umma_bf16_ss(tmem + C::TM_PROJ, da, db, idesc_proj, (e | k16) != 0);
+                        }
+                        umma_commit(&bar_proj[kp & 1]);
+                        if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
+                        ++kp;
+                    }
+                }
+                if (proj_done < kp && mbar_test_t(&bar_proj[proj_done & 1], (proj_done >> 1) & 1)) ++proj_done;
+                if (kq < total && proj_done > kq - WPB) { prefetch_wp(kq); ++kq; }
+            }
+        }
+    } else {
+        // =========================== compute warps ===========================
+        const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter (32 expanded channels), row strip (output rows 2s, 2s+1)
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const float* Bp_g = reinterpret_cast<const float*>(tab + (size_t)NCH * CM * 32);
+        int n = 0, oy0 = 0, ox0 = 0, pn = 0, poy0 = 0, pox0 = 0;
+        auto output_epilogue = [&](int lt, int tn, int toy0, int tox0) {   // + bias (+ residual from global, L2-resident), bf16 NHWC store
+            mbar_wait(&bar_tiledone, lt & 1);                 // every project MMA of tile lt has completed
+            tc_fence_after_sync();
+            const int p = q * 32 + lane;
+            const int oy = toy0 + (p >> 4), ox = tox0 + (p & 15);
+            const bool live = (oy < H) && (ox < W);
+            const size_t pix = ((size_t)tn * H + oy) * W + ox;
+            constexpr int CP = COUT / 4;                  // columns per warp: 16, 24 or 32
+#pragma unroll
+            for (int c0 = 0; c0 < CP; c0 += 8) {
+                const int co = s * CP + c0;
+                uint32_t r[8];
+                tmem_ld_32x32b_x8(tmem + lane_base + C::TM_PROJ + co, r);
+                uint4 res = make_uint4(0u, 0u, 0u, 0u);
+                if (RES && live) res = __ldg(reinterpret_cast<const uint4*>(in + pix * CIN + co));
+                const float4 ba = __ldg(reinterpret_cast<const float4*>(Bp_g + co));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(Bp_g + co + 4));
+                tmem_ld_wait();
+                if (live) {
+                    float v[8] = {__uint_as_float(r[0]) + ba.x, __uint_as_float(r[1]) + ba.y, __uint_as_float(r[2]) + ba.z,
+                                  __uint_as_float(r[3]) + ba.w, __uint_as_float(r[4]) + bb.x, __uint_as_float(r[5]) + bb.y,
+                                  __uint_as_float(r[6]) + bb.z, __uint_as_float(r[7]) + bb.w};
+                    if (RES) {
+                        float f[8];
+                        unpackbf8(res, f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += f[i];
+                    }
+                    *reinterpret_cast<uint4*>(out + pix * COUT + co) =
+                        make_uint4(packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_projfree);       // the next tile's first project MMA may overwrite the accumulator
+        };
+#pragma unroll 1
+        for (int g = 0; g < total; ++g) {
+            const int lt = g / NCH, e = g - lt * NCH;
+            if (e == 0) { pn = n; poy0 = oy0; pox0 = ox0; tile_origin(lt, n, oy0, ox0); }
+            const bool active = (e * CM + q * 32) < C::CEXP;     // warp-uniform: the last chunk of a 576-channel layer is half empty
+            // this thread's channel: 9 bf16 taps + fp32 bias from the (L1-resident) table, requested before the wait
+            uint4 wa = make_uint4(0u, 0u, 0u, 0u), wb = wa;
+            if (active) {
+                const uint4* rec = reinterpret_cast<const uint4*>(tab + (size_t)(e * CM + q * 32 + lane) * 32);
+                wa = __ldg(rec);
+                wb = __ldg(rec + 1);
+            }
+            mbar_wait(&bar_exp[g & 1], (g >> 1) & 1);            // expand(g) has completed
+            tc_fence_after_sync();
+            uint32_t Ep[4][9];                                   // halo rows 2s .. 2s+3, column pairs (2i, 2i+1), ReLU'd bf16
+            if (active) {
+                uint32_t r[72];
+                const uint32_t t0 = tmem + lane_base + (g & 1) * C::NB + (2 * s) * IW;
+                tmem_ld_32x32b_x64(t0, r);
+                tmem_ld_32x32b_x8(t0 + 64, r + 64);
+                tmem_ld_wait();
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                    for (int i = 0; i < 9; ++i)
+                        Ep[rr][i] = packbf_relu(__uint_as_float(r[rr * IW + 2 * i]), __uint_as_float(r[rr * IW + 2 * i + 1]));
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tmfree[g & 1]);      // expand(g+2) may overwrite this accumulator
+            if (active) {
+                // zero padding of the depthwise conv: halo columns outside the image (halo rows are skipped below)
+                const int ix0 = ox0 - 1;
+                if (ix0 < 0 || ix0 + IW > W) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) {
+                        const int xa = ix0 + 2 * i, xb2 = xa + 1;
+                        const uint32_t m = ((xa >= 0 && xa < W) ? 0x0000FFFFu : 0u) | ((xb2 >= 0 && xb2 < W) ? 0xFFFF0000u : 0u);
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) Ep[rr][i] &= m;
+                    }
+                }
+                const uint32_t wq[5] = {wa.x, wa.y, wa.z, wa.w, wb.x};
+                const float bd = __uint_as_float(wb.y);
+                float acc[2][16];
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) acc[o][x] = bd;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int iy = oy0 - 1 + 2 * s + rr;
+                    if (iy >= 0 && iy < H) {                      // warp-uniform
+#pragma unroll
+                        for (int o = 0; o < 2; ++o) {
+                            const int ky = rr - o;
+                            if (ky >= 0 && ky < 3) {
+#pragma unroll
+                                for (int x = 0; x < 16; ++x) {
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx)
+                                        fhfma_sel(acc[o][x], Ep[rr][(x + kx) >> 1], (x + kx) & 1, wq[(ky * 3 + kx) >> 1], (ky * 3 + kx) & 1);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (g >= 2) mbar_wait(&bar_proj[g & 1], ((g - 2) >> 1) & 1);   // project(g-2) has completed: D[g&1] is free
+                const int k = q * 32 + lane;
+                const uint32_t d0 = sD + (g & 1) * C::D_BYTES + (k >> 3) * C::D_LBO + (k & 7) * 2 + s * 512;
+#pragma unroll
+                for (int o = 0; o < 2; ++o)
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) sts_bf16_relu(d0 + o * 256 + (x >> 3) * 128 + (x & 7) * 16, acc[o][x]);
+            } else if (g >= 2) {
+                mbar_wait(&bar_proj[g & 1], ((g - 2) >> 1) & 1);   // stay in step with the barrier's phases
+            }
+            fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_dready[g & 1]);
+            if (e == 0 && lt >= 1) output_epilogue(lt - 1, pn, poy0, pox0);   // deferred by one chunk: keeps the pipeline fed
+        }
+        output_epilogue(my_tiles - 1, n, oy0, ox0);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, C::TM_COLS);
+}
+
+template <int CIN, int COUT, bool RES>
+static cudaError_t run_s1t(const bf16* in, const unsigned char* tab, const bf16* we_img, const bf16* wp_img, bf16* out, int n, int h,
+                           int w, cudaStream_t s) {
+    using C = T1Cfg<CIN, COUT>;
+    static unsigned long long configured = 0;
+    cudaError_t e = ensure_dyn_smem(bottleneck_s1t_kernel<CIN, COUT, RES>, C::smem_bytes, configured);
+    if (e != cudaSuccess) return e;
+    CUtensorMap xmap;
+    e = make_nhwc_halo_map(&xmap, in, n, h, w, CIN, C::IH, C::IW);
+    if (e != cudaSuccess) return e;
+    const int tiles_x = ceil_div(w, C::TW), tiles_y = ceil_div(h, C::TH), ntiles = tiles_x * tiles_y * n;
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    bottleneck_s1t_kernel<CIN, COUT, RES><<<grid, kTThreads, C::smem_bytes, s>>>(xmap, in, tab, we_img, wp_img, out, h, w, tiles_x,
+                                                                                 tiles_y, ntiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bottleneck_s1t_tc(int cin, int cout, const bf16* in, const unsigned char* tab, const bf16* we_img,
+                                     const bf16* wp_img, bf16* out, int n, int h, int w, cudaStream_t s) {
+    if (cin == 64 && cout == 64) return run_s1t<64, 64, true>(in, tab, we_img, wp_img, out, n, h, w, s);
+    if (cin == 96 && cout == 96) return run_s1t<96, 96, true>(in, tab, we_img, wp_img, out, n, h, w, s);
+    if (cin == 96 && cout == 128) return run_s1t<96, 128, false>(in, tab, we_img, wp_img, out, n, h, w, s);
+    if (cin == 128 && cout == 128) return run_s1t<128, 128, true>(in, tab, we_img, wp_img, out, n, h, w, s);
+    return cudaErrorInvalidValue;
+}
+
+// image sizes (bytes) of the transposed kernel's operands for a stride-1 layer
+size_t bottleneck_s1t_we_bytes(int cin) { const int nch = (6 * cin + 127) / 128; return (size_t)nch * 128 * (cin + 16) * 2; }
+size_t bottleneck_s1t_wp_bytes(int cin, int cout) { const int nch = (6 * cin + 127) / 128; return (size_t)nch * cout * 128 * 2; }
+size_t bottleneck_s1t_tab_bytes(int cin, int cout) { const int nch = (6 * cin + 127) / 128; return (size_t)nch * 128 * 32 + (size_t)cout * 4; }
+
+}  // namespace fscnn

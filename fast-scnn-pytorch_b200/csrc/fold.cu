@@ -172,4 +172,47 @@ cudaError_t launch_pack_bneck_tab(const BneckW& w, int cexp, int cout, unsigned 
     return cudaGetLastError();
 }
 
+// Transposed stride-1 bottleneck kernel (bottleneck_s1t_tc.cu): the expand weights are the A operand, cut into chunks of 128
+// expanded channels (rows) x (cin + 16) K columns, 8x8 core matrices ordered [k/8][row/8] (LBO = 2048 B, SBO = 128 B).  The 16
+// extra K columns carry the BN-folded expand bias as bf16 head + remainder (relative error 2^-17), zeros elsewhere; rows past
+// 6*cin (the half-empty last chunk of a 576-channel layer) are zero.  we is the folded fp32 table [cin][cexp].
+__global__ void pack_s1t_we_kernel(const float* __restrict__ we, const float* __restrict__ be, int cin, int cexp,
+                                   __nv_bfloat16* __restrict__ out) {
+    const int KA = cin + 16, nch = (cexp + 127) / 128, total = nch * 128 * KA;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int chunk = i / (128 * KA), rem = i % (128 * KA), n = rem / KA, k = rem % KA;
+        const int ch = chunk * 128 + n;
+        float v = 0.f;
+        if (ch < cexp) {
+            if (k < cin) v = we[(size_t)k * cexp + ch];
+            else if (k == cin) v = __bfloat162float(__float2bfloat16_rn(be[ch]));
+            else if (k == cin + 1) v = be[ch] - __bfloat162float(__float2bfloat16_rn(be[ch]));
+        }
+        out[(size_t)chunk * 128 * KA + ((size_t)(k >> 3) * 16 + (n >> 3)) * 64 + (n & 7) * 8 + (k & 7)] = __float2bfloat16_rn(v);
+    }
+}
+
+// per expanded channel a 32-byte record {bf16 w[9], 2 B pad, f32 depthwise bias, 8 B pad}, then f32 project bias [cout]
+__global__ void pack_s1t_tab_kernel(const float* __restrict__ wd, const float* __restrict__ bd, const float* __restrict__ bp,
+                                    int cexp, int cout, unsigned char* __restrict__ out) {
+    const int nrec = (cexp + 127) / 128 * 128;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nrec; c += gridDim.x * blockDim.x) {
+        __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(out + (size_t)c * 32);
+        for (int t = 0; t < 16; ++t) w[t] = __float2bfloat16_rn(0.f);
+        if (c < cexp) {
+            for (int t = 0; t < 9; ++t) w[t] = __float2bfloat16_rn(wd[(size_t)t * cexp + c]);
+            reinterpret_cast<float*>(out + (size_t)c * 32)[5] = bd[c];
+        }
+    }
+    float* bpo = reinterpret_cast<float*>(out + (size_t)nrec * 32);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cout; i += gridDim.x * blockDim.x) bpo[i] = bp[i];
+}
+
+cudaError_t launch_pack_s1t(const BneckW& w, int cin, int cout, bf16* we_img, unsigned char* tab, cudaStream_t s) {
+    const int cexp = 6 * cin;
+    pack_s1t_we_kernel<<<64, 256, 0, s>>>(w.we, w.be, cin, cexp, we_img);
+    pack_s1t_tab_kernel<<<8, 128, 0, s>>>(w.wd, w.bd, w.bp, cexp, cout, tab);
+    return cudaGetLastError();
+}
+
 }  // namespace fscnn

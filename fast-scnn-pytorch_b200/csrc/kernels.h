@@ -83,6 +83,14 @@ cudaError_t launch_pack_bneck_tab(const BneckW& w, int cexp, int cout, unsigned 
 // stride-1 layers: three-role pipeline (bottleneck_s1_tc.cu); launch_bottleneck_tc dispatches to it
 cudaError_t launch_bottleneck_s1_tc(int cin, int cout, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
                                     const bf16* wp_img, bf16* out, int n, int h, int w, cudaStream_t s);
+// stride-1 layers, transposed expand (bottleneck_s1t_tc.cu): the expanded tile goes TMEM -> registers, never through shared
+// memory.  we_img / tab from launch_pack_s1t, wp_img = launch_fold_umma(project, nc = cout, kc = 128) into a zeroed buffer.
+size_t bottleneck_s1t_we_bytes(int cin);
+size_t bottleneck_s1t_wp_bytes(int cin, int cout);
+size_t bottleneck_s1t_tab_bytes(int cin, int cout);
+cudaError_t launch_pack_s1t(const BneckW& w, int cin, int cout, bf16* we_img, unsigned char* tab, cudaStream_t s);
+cudaError_t launch_bottleneck_s1t_tc(int cin, int cout, const bf16* in, const unsigned char* tab, const bf16* we_img,
+                                     const bf16* wp_img, bf16* out, int n, int h, int w, cudaStream_t s);
 cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 
