@@ -131,6 +131,25 @@ struct fscnn_ctx {
             mb = (int)((64ll << 20) / (px > 0 ? px : 1));
             if (mb < 1) mb = 1;
             if (mb > 128) mb = 128;
+            // ... nudged (within +-25 %) to the count whose 8x16-pixel tiles at the coarsest level (/32: seven of the nine
+            // bottlenecks + PPM, a handful of tiles per image) fill whole waves of persistent CTAs: 37 images at 1024x2048
+            // (16 tiles each = 4 x 148) instead of 32 (3.46 waves, the last one 46 % full)
+            if (n > mb * 3 / 4) {
+                const Dims d = make_dims(h, w);
+                const int sms = num_sms();
+                if (d.ok && sms > 0) {
+                    const long long t5 = (long long)((d.h5 + 7) / 8) * ((d.w5 + 15) / 16);
+                    int best = mb;
+                    double best_eff = 0.0;
+                    const int hi = (mb * 5 / 4 < 128 ? mb * 5 / 4 : 128) < n ? (mb * 5 / 4 < 128 ? mb * 5 / 4 : 128) : n;
+                    for (int c = mb * 3 / 4 > 1 ? mb * 3 / 4 : 1; c <= hi; ++c) {
+                        const long long tiles = t5 * c, waves = (tiles + sms - 1) / sms;
+                        const double eff = (double)tiles / (double)(waves * sms);
+                        if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && abs(c - mb) < abs(best - mb))) { best_eff = eff; best = c; }
+                    }
+                    mb = best;
+                }
+            }
         }
         return mb < n ? mb : n;
     }

@@ -7,12 +7,12 @@
 //   depthwise each thread owns ONE expanded channel (its TMEM lane) and two output rows: it pulls 4 halo rows x 18 columns
 //            out of TMEM (tcgen05.ld), ReLU + bf16-packs them in registers (cvt.rn.relu.bf16x2) and runs the 3x3 taps as
 //            FHFMA.BF16 with its 9 weights in registers.  No E tile, no LDS, no bank conflicts.
-//   project  D[128 px x 128 ch] (bf16, K-major A operand written by the depthwise threads) * Wp chunk -> TMEM accumulator
+//   project  D[128 px x 128 ch] (bf16, MN-major A operand written by the depthwise threads) * Wp chunk -> TMEM accumulator
 //            over the chunks of 128 expanded channels; + bias (+ residual) -> bf16 NHWC.
 //
 // One persistent CTA per SM: 16 compute warps (TMEM lane quarter = warp % 4, row strip = warp / 4) + a control warp whose
-// lane 0 issues every TMA load, bulk copy and MMA from a non-blocking event loop.  The expand accumulator and D are
-// double-buffered: the tensor core works two chunks ahead of the CUDA cores; every hand-off is an mbarrier.
+// lane 0 issues every TMA load, bulk copy and MMA from a non-blocking event loop.  The expand accumulator and the
+// weight chunks are double-buffered: the tensor core works two chunks ahead of the CUDA cores; every hand-off is an mbarrier.
 #include "kernels.h"
 #include "tma_host.h"
 #include "umma.cuh"
@@ -56,10 +56,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t* r) 
 
 // acc += bf16 half XH of x  *  bf16 half WH of w   (FHFMA.BF16 with register-half selectors, fp32 accumulate)
 // (xh / wh are compile-time constants after unrolling)
-__device__ __forceinline__ void fhfma_sel(float& acc, uint32_t x, int xh, uint32_t w, int wh) {
+__device__ __forceinline__ float fhfma_sel(float c, uint32_t x, int xh, uint32_t w, int wh) {
     const uint16_t xs = xh ? (uint16_t)(x >> 16) : (uint16_t)x;
     const uint16_t ws = wh ? (uint16_t)(w >> 16) : (uint16_t)w;
-    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(xs), "h"(ws));
+    float d;
+    asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(xs), "h"(ws), "f"(c));
+    return d;
 }
 
 __device__ __forceinline__ void sts_bf16_relu(uint32_t addr, float v) {
@@ -78,18 +80,34 @@ struct T1Cfg {
     static constexpr int XS = X_BYTES;
     static constexpr int WE_BYTES = CM * KA * 2;               // A image [KA/8][128 rows][8]: LBO = 2048, SBO = 128
     static constexpr int WP_BYTES = COUT * CM * 2;             // B image [128/8][COUT rows][8]: LBO = COUT*16, SBO = 128
-    static constexpr int D_LBO = 128 * 16 + 16;                // K-major D tile; the +16 spreads the four 8-channel groups of a warp over the banks
-    static constexpr int D_BYTES = (CM / 8) * D_LBO;
-    static constexpr int ONES_BYTES = 2 * NB * 16;             // B rows {1, 1, 0 x 6} | zeros: the bias columns' partner
+    // D (project A operand, 128 px x 128 ch) is stored MN-major: 16 bytes = 8 consecutive pixels of one channel, a core
+    // matrix = 8 channels x 16 B, channel blocks 128 B apart (LBO), pixel blocks 2048 B apart (SBO).  A depthwise thread owns
+    // one channel and a row of 16 pixels: two 16-byte stores per row, and a warp's store covers 512 contiguous bytes.
+    static constexpr int D_LBO = 128, D_SBO = 2048;
+    static constexpr int D_BYTES = 16 * D_SBO;
+    static constexpr int ONES_BYTES = 256;                     // one core matrix of B rows {1, 1, 0 x 6} + one of zeros, re-read for every
+                                                               // 8-row group (SBO = 0): the bias columns' partner
     static constexpr int LIMIT = 227 * 1024 - 256;
-    static constexpr int FIXED = 2 * WE_BYTES + 2 * D_BYTES + ONES_BYTES;
-    static constexpr int XB = (FIXED + 2 * XS + 2 * WP_BYTES <= LIMIT) ? 2 : 1;
-    static constexpr int WPB = (FIXED + XB * XS + 2 * WP_BYTES <= LIMIT) ? 2 : 1;
+    // Every CTA needs every weight chunk for every tile: streamed, that is (We + Wp) x 148 SMs out of the same L2 lines per
+    // chunk step, and the copies (not the MMAs or the FMAs) set the pace.  With 64 input channels all of it (108 KB) stays
+    // resident in shared memory instead.
+    static constexpr bool WRES = NCH * (WE_BYTES + WP_BYTES) + 2 * XS + 2 * D_BYTES + ONES_BYTES <= LIMIT;
+    static constexpr int WEB = WRES ? NCH : 2;                 // expand weight buffers
+    // streamed: weights first (a chunk's copy must overlap the chunk before), then D, then the halo tile
+    static constexpr int FIXED = WEB * WE_BYTES + D_BYTES + ONES_BYTES + XS;
+    static constexpr int WPB = WRES ? NCH : ((FIXED + 2 * WP_BYTES <= LIMIT) ? 2 : 1);
+#ifdef S1T_PREFER_X
+    static constexpr int XB = (FIXED + WPB * WP_BYTES + XS <= LIMIT) ? 2 : 1;
+    static constexpr int DB = (FIXED + WPB * WP_BYTES + (XB - 1) * XS + D_BYTES <= LIMIT) ? 2 : 1;
+#else
+    static constexpr int DB = (FIXED + WPB * WP_BYTES + D_BYTES <= LIMIT) ? 2 : 1;
+    static constexpr int XB = (FIXED + WPB * WP_BYTES + (DB - 1) * D_BYTES + XS <= LIMIT) ? 2 : 1;
+#endif
     static constexpr int oX = 0;
     static constexpr int oWe = XB * XS;
-    static constexpr int oWp = oWe + 2 * WE_BYTES;
+    static constexpr int oWp = oWe + WEB * WE_BYTES;
     static constexpr int oD = oWp + WPB * WP_BYTES;
-    static constexpr int oOnes = oD + 2 * D_BYTES;
+    static constexpr int oOnes = oD + DB * D_BYTES;
     static constexpr int smem_bytes = oOnes + ONES_BYTES;
     static constexpr int TM_PROJ = 2 * NB;                     // expand accumulators: 2 buffers x 192 columns
     static constexpr int TM_COLS = 512;
@@ -98,15 +116,29 @@ struct T1Cfg {
     static_assert(CIN % 16 == 0 && COUT % 32 == 0 && XS % 128 == 0, "shape");
 };
 
+#ifdef FSCNN_PHASE_TIMING   // debug build only: clock64 stamps of chunks 12..19 of CTA 5 of the <DBG_CIN,*> kernel
+#ifndef DBG_CIN
+#define DBG_CIN 128
+#endif
+__device__ long long g_s1t_phase[8 * 16];
+#define T_STAMP(cond, gg, slot) do { if (CIN == DBG_CIN && blockIdx.x == 5 && (cond) && (gg) >= 12 && (gg) < 20) g_s1t_phase[((gg) - 12) * 16 + (slot)] = clock64(); } while (0)
+extern "C" int fscnn_debug_s1t_phases(long long* out128) {
+    return cudaMemcpyFromSymbol(out128, g_s1t_phase, sizeof(long long) * 128) == cudaSuccess ? 0 : -1;
+}
+#else
+#define T_STAMP(cond, gg, slot) do { } while (0)
+#endif
+
 template <int CIN, int COUT, bool RES>
 __global__ void __launch_bounds__(kTThreads, 1)
 bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restrict__ in, const unsigned char* __restrict__ tab,
                       const bf16* __restrict__ we_img, const bf16* __restrict__ wp_img, bf16* __restrict__ out, int H, int W,
                       int tiles_x, int tiles_y, int ntiles) {
     using C = T1Cfg<CIN, COUT>;
-    constexpr int IW = C::IW, NCH = C::NCH, PIN = C::PIN, XB = C::XB, WPB = C::WPB, CM = C::CM;
+    constexpr int IW = C::IW, NCH = C::NCH, PIN = C::PIN, XB = C::XB, WPB = C::WPB, DB = C::DB, CM = C::CM;
+    constexpr bool WRES = C::WRES;
     extern __shared__ __align__(128) uint8_t sm[];
-    __shared__ __align__(8) uint64_t bar_we[2], bar_wp[2], bar_exp[2], bar_tmfree[2], bar_dready[2], bar_proj[2], bar_x[2],
+    __shared__ __align__(8) uint64_t bar_we[2], bar_wp[2], bar_wres, bar_exp[2], bar_tmfree[2], bar_x[2], bar_dready[2], bar_proj[2],
         bar_projfree, bar_tiledone;
     __shared__ uint32_t tmem_base_s;
     const uint32_t sX = smem_u32(sm + C::oX), sWe = smem_u32(sm + C::oWe), sWp = smem_u32(sm + C::oWp), sD = smem_u32(sm + C::oD),
@@ -124,14 +156,14 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_we[i], 1); mbar_init(&bar_wp[i], 1); mbar_init(&bar_exp[i], 1); mbar_init(&bar_proj[i], 1); mbar_init(&bar_x[i], 1);
-            mbar_init(&bar_tmfree[i], kTWarps); mbar_init(&bar_dready[i], kTWarps);
+            mbar_init(&bar_we[i], 1); mbar_init(&bar_wp[i], 1); mbar_init(&bar_exp[i], 1); mbar_init(&bar_x[i], 1);
+            mbar_init(&bar_tmfree[i], kTWarps); mbar_init(&bar_dready[i], kTWarps); mbar_init(&bar_proj[i], 1);
         }
-        mbar_init(&bar_projfree, kTWarps); mbar_init(&bar_tiledone, 1);
+        mbar_init(&bar_projfree, kTWarps); mbar_init(&bar_tiledone, 1); mbar_init(&bar_wres, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < 2 * C::NB; i += kTThreads)      // the constant B block of the bias columns
-        *reinterpret_cast<uint4*>(sm + C::oOnes + i * 16) = make_uint4(i < C::NB ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    if (tid < 16)                                         // the constant B block of the bias columns
+        *reinterpret_cast<uint4*>(sm + C::oOnes + tid * 16) = make_uint4(tid < 8 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
     fence_async_proxy();
     if (warp == 0) { tmem_alloc(&tmem_base_s, C::TM_COLS); tmem_relinquish(); }
     tc_fence_before_sync();
@@ -139,7 +171,11 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-    if (warp == kTWarps) {
+#ifndef S1T_CTL_WARP
+#define S1T_CTL_WARP 1
+#endif
+    constexpr int kCtl = S1T_CTL_WARP ? kTWarps : 0;      // the control warp's id
+    if (warp == kCtl) {
         // =========================== control warp ===========================
         if (lane == 0) {
             auto prefetch_we = [&](int g) {
@@ -158,27 +194,60 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 tma_load_halo(sX + xb * C::XS, &xmap, ox0 - 1, oy0 - 1, n, &bar_x[xb]);
             };
             constexpr uint32_t idesc_exp = make_idesc_bf16(128, C::NB);
-            constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT);
+            constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT) | (1u << 15);   // A (= D) is MN-major
             tma_prefetch_desc(&xmap);
             load_x(0);
             if (XB == 2 && my_tiles > 1) load_x(1);
-            prefetch_we(0);
-            if (total > 1) prefetch_we(1);
-            prefetch_wp(0);
-            if (WPB == 2 && total > 1) prefetch_wp(1);
-            int ke = 0, kp = 0, kw = 2, kq = WPB, kx = XB, exp_done = 0, proj_done = 0;
+            if (WRES) {      // all weight chunks, once
+                mbar_arrive_expect_tx(&bar_wres, NCH * (C::WE_BYTES + C::WP_BYTES));
+                for (int e = 0; e < NCH; ++e) {
+                    bulk_g2s(sm + C::oWe + e * C::WE_BYTES, we_img + (size_t)e * CM * C::KA, C::WE_BYTES, &bar_wres);
+                    bulk_g2s(sm + C::oWp + e * C::WP_BYTES, wp_img + (size_t)e * COUT * CM, C::WP_BYTES, &bar_wres);
+                }
+                mbar_wait(&bar_wres, 0);
+            } else {
+                prefetch_we(0);
+                if (total > 1) prefetch_we(1);
+                prefetch_wp(0);
+                if (WPB == 2 && total > 1) prefetch_wp(1);
+            }
+            int ke = 0, kp = 0, kw = WRES ? (1 << 30) : 2, kq = WRES ? (1 << 30) : WPB, kx = XB, exp_done = 0, proj_done = 0;
 #pragma unroll 1
             while (kp < total) {
+                const int progress0 = ke + kp + kw + kq + kx + exp_done + proj_done;
+                // ---- project(kp) first (its result frees D, which the compute warps need again within a chunk): needs D written, its weight chunk, and (first chunk of a tile) the previous tile's accumulator read ----
+                {
+                    const int lt = kp / NCH, e = kp - lt * NCH;
+                    bool ok = mbar_test_t(&bar_dready[kp % DB], (kp / DB) & 1);
+                    if (ok && !WRES) ok = mbar_test_t(&bar_wp[kp % WPB], (kp / WPB) & 1);
+                    if (ok && e == 0 && lt > 0) ok = mbar_test_t(&bar_projfree, (lt - 1) & 1);
+                    if (ok) {
+                        if (proj_done < kp - DB + 1) proj_done = kp - DB + 1;    // its D buffer was rewritten: project(kp-DB) has completed
+                        T_STAMP(true, kp, 8);
+                        tc_fence_after_sync();
+                        const int ksteps = ((C::CEXP - e * CM) < CM ? (C::CEXP - e * CM) : CM) / 16;
+                        for (int k16 = 0; k16 < ksteps; ++k16) {
+                            const uint64_t da = make_smem_desc(sD + (kp % DB) * C::D_BYTES + k16 * 2 * C::D_LBO, C::D_LBO, C::D_SBO);
+                            const uint64_t db = make_smem_desc(sWp + (WRES ? e : kp % WPB) * C::WP_BYTES + k16 * 2 * (COUT * 16), COUT * 16, 128);
+                            umma_bf16_ss(tmem + C::TM_PROJ, da, db, idesc_proj, (e | k16) != 0);
+                        }
+                        umma_commit(&bar_proj[kp % DB]);
+                        if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
+                        T_STAMP(true, kp, 9);
+                        ++kp;
+                    }
+                }
                 // ---- expand(ke): needs its halo tile (first chunk of a tile), its weight chunk, and the TMEM buffer drained ----
                 if (ke < total) {
                     const int lt = ke / NCH, e = ke - lt * NCH, xb = lt % XB;
-                    bool ok = mbar_test_t(&bar_we[ke & 1], (ke >> 1) & 1);
+                    bool ok = WRES || mbar_test_t(&bar_we[ke & 1], (ke >> 1) & 1);
                     if (ok && e == 0) ok = mbar_test_t(&bar_x[xb], (lt / XB) & 1);
                     if (ok && ke >= 2) ok = mbar_test_t(&bar_tmfree[ke & 1], ((ke - 2) >> 1) & 1);
                     if (ok) {
                         if (ke >= 2 && exp_done < ke - 1) exp_done = ke - 1;     // its TMEM was drained: expand(ke-2) has completed
+                        T_STAMP(true, ke, 10);
                         tc_fence_after_sync();
-                        const uint32_t a0 = sWe + (ke & 1) * C::WE_BYTES;
+                        const uint32_t a0 = sWe + (WRES ? e : (ke & 1)) * C::WE_BYTES;
 #pragma unroll
                         for (int k16 = 0; k16 < CIN / 16; ++k16) {
                             const uint64_t da = make_smem_desc(a0 + k16 * 2 * 2048, 2048, 128);
@@ -186,42 +255,25 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                             umma_bf16_ss(tmem + (ke & 1) * C::NB, da, db, idesc_exp, k16 > 0);
                         }
                         umma_bf16_ss(tmem + (ke & 1) * C::NB, make_smem_desc(a0 + (CIN / 16) * 2 * 2048, 2048, 128),
-                                     make_smem_desc(sOnes, C::NB * 16, 128), idesc_exp, 1);
+                                     make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
                         umma_commit(&bar_exp[ke & 1]);
+                        T_STAMP(true, ke, 11);
                         ++ke;
                     }
                 }
                 // ---- completion tracking of the expand MMAs, in order ----
-                if (exp_done < ke && mbar_test_t(&bar_exp[exp_done & 1], (exp_done >> 1) & 1)) ++exp_done;
-                if (kw < total && exp_done > kw - 2) { prefetch_we(kw); ++kw; }
+                if (exp_done < ke && mbar_test_t(&bar_exp[exp_done & 1], (exp_done >> 1) & 1)) { T_STAMP(true, exp_done, 12); ++exp_done; }
+                if (kw < total && exp_done > kw - 2) { T_STAMP(true, kw, 14); prefetch_we(kw); ++kw; }
                 if (kx < my_tiles && exp_done > (kx - XB) * NCH + NCH - 1) { load_x(kx); ++kx; }
-                // ---- project(kp): needs D written, its weight chunk, and (first chunk of a tile) the previous tile's accumulator read ----
-                {
-                    const int lt = kp / NCH, e = kp - lt * NCH;
-                    bool ok = mbar_test_t(&bar_dready[kp & 1], (kp >> 1) & 1);
-                    if (ok) ok = mbar_test_t(&bar_wp[kp % WPB], (kp / WPB) & 1);
-                    if (ok && e == 0 && lt > 0) ok = mbar_test_t(&bar_projfree, (lt - 1) & 1);
-                    if (ok) {
-                        if (kp >= 2 && proj_done < kp - 1) proj_done = kp - 1;   // D[kp&1] was rewritten: project(kp-2) has completed
-                        tc_fence_after_sync();
-                        const int ksteps = ((C::CEXP - e * CM) < CM ? (C::CEXP - e * CM) : CM) / 16;
-                        for (int k16 = 0; k16 < ksteps; ++k16) {
-                            const uint64_t da = make_smem_desc(sD + (kp & 1) * C::D_BYTES + k16 * 2 * C::D_LBO, C::D_LBO, 128);
-                            const uint64_t db = make_smem_desc(sWp + (kp % WPB) * C::WP_BYTES + k16 * 2 * (COUT * 16), COUT * 16, 128);
-                            umma_bf16_ss(tmem + C::TM_PROJ, da, db, idesc_proj, (e | k16) != 0);
-                        }
-                        umma_commit(&bar_proj[kp & 1]);
-                        if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
-                        ++kp;
-                    }
-                }
-                if (proj_done < kp && mbar_test_t(&bar_proj[proj_done & 1], (proj_done >> 1) & 1)) ++proj_done;
+                if (proj_done < kp && mbar_test_t(&bar_proj[proj_done % DB], (proj_done / DB) & 1)) { T_STAMP(true, proj_done, 13); ++proj_done; }
                 if (kq < total && proj_done > kq - WPB) { prefetch_wp(kq); ++kq; }
+                if (ke + kp + kw + kq + kx + exp_done + proj_done == progress0) __nanosleep(20);   // idle: leave the issue slots to the compute warps
             }
         }
     } else {
         // =========================== compute warps ===========================
-        const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter (32 expanded channels), row strip (output rows 2s, 2s+1)
+        const int cw = kCtl == 0 ? warp - 1 : warp;       // compute-warp index 0..15
+        const int q = warp & 3, s = cw >> 2;              // TMEM lane quarter = warp % 4 (hardware rule), row strip (output rows 2s, 2s+1)
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float* Bp_g = reinterpret_cast<const float*>(tab + (size_t)NCH * CM * 32);
         int n = 0, oy0 = 0, ox0 = 0, pn = 0, poy0 = 0, pox0 = 0;
@@ -273,7 +325,9 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 wa = __ldg(rec);
                 wb = __ldg(rec + 1);
             }
+            T_STAMP(tid == 64, g, 0);
             mbar_wait(&bar_exp[g & 1], (g >> 1) & 1);            // expand(g) has completed
+            T_STAMP(tid == 64, g, 1);
             tc_fence_after_sync();
             uint32_t Ep[4][9];                                   // halo rows 2s .. 2s+3, column pairs (2i, 2i+1), ReLU'd bf16
             if (active) {
@@ -291,9 +345,10 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tmfree[g & 1]);      // expand(g+2) may overwrite this accumulator
+            T_STAMP(tid == 64, g, 2);
             if (active) {
-                // zero padding of the depthwise conv: halo columns outside the image (halo rows are skipped below)
-                const int ix0 = ox0 - 1;
+                // zero padding of the depthwise conv: halo columns / rows outside the image (border tiles only)
+                const int ix0 = ox0 - 1, iy0 = oy0 - 1 + 2 * s;
                 if (ix0 < 0 || ix0 + IW > W) {
 #pragma unroll
                     for (int i = 0; i < 9; ++i) {
@@ -303,44 +358,52 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                         for (int rr = 0; rr < 4; ++rr) Ep[rr][i] &= m;
                     }
                 }
+                if (iy0 < 0 || iy0 + 4 > H) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr)
+                        if (iy0 + rr < 0 || iy0 + rr >= H) {
+#pragma unroll
+                            for (int i = 0; i < 9; ++i) Ep[rr][i] = 0u;
+                        }
+                }
                 const uint32_t wq[5] = {wa.x, wa.y, wa.z, wa.w, wb.x};
                 const float bd = __uint_as_float(wb.y);
                 float acc[2][16];
+                // straight-line: halo row rr feeds output rows o = rr - ky; the first tap of every accumulator adds the bias
 #pragma unroll
-                for (int o = 0; o < 2; ++o)
+                for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) acc[o][x] = bd;
+                    for (int o = 0; o < 2; ++o) {
+                        const int ky = rr - o;
+                        if (ky >= 0 && ky < 3) {
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const int iy = oy0 - 1 + 2 * s + rr;
-                    if (iy >= 0 && iy < H) {                      // warp-uniform
+                            for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                        for (int o = 0; o < 2; ++o) {
-                            const int ky = rr - o;
-                            if (ky >= 0 && ky < 3) {
-#pragma unroll
-                                for (int x = 0; x < 16; ++x) {
-#pragma unroll
-                                    for (int kx = 0; kx < 3; ++kx)
-                                        fhfma_sel(acc[o][x], Ep[rr][(x + kx) >> 1], (x + kx) & 1, wq[(ky * 3 + kx) >> 1], (ky * 3 + kx) & 1);
-                                }
-                            }
+                                for (int x = 0; x < 16; ++x)
+                                    acc[o][x] = fhfma_sel((ky | kx) ? acc[o][x] : bd, Ep[rr][(x + kx) >> 1], (x + kx) & 1,
+                                                          wq[(ky * 3 + kx) >> 1], (ky * 3 + kx) & 1);
                         }
                     }
-                }
-                if (g >= 2) mbar_wait(&bar_proj[g & 1], ((g - 2) >> 1) & 1);   // project(g-2) has completed: D[g&1] is free
+                T_STAMP(tid == 64, g, 3);
+                if (g >= DB) mbar_wait(&bar_proj[g % DB], (g / DB - 1) & 1);   // project(g-DB) has completed: this D buffer is free
+                T_STAMP(tid == 64, g, 4);
                 const int k = q * 32 + lane;
-                const uint32_t d0 = sD + (g & 1) * C::D_BYTES + (k >> 3) * C::D_LBO + (k & 7) * 2 + s * 512;
+                const uint32_t d0 = sD + (g % DB) * C::D_BYTES + (k >> 3) * C::D_LBO + (k & 7) * 16 + (4 * s) * C::D_SBO;
 #pragma unroll
                 for (int o = 0; o < 2; ++o)
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) sts_bf16_relu(d0 + o * 256 + (x >> 3) * 128 + (x & 7) * 16, acc[o][x]);
-            } else if (g >= 2) {
-                mbar_wait(&bar_proj[g & 1], ((g - 2) >> 1) & 1);   // stay in step with the barrier's phases
+                    for (int hx = 0; hx < 2; ++hx)
+                        sts128(d0 + (2 * o + hx) * C::D_SBO, packbf_relu(acc[o][8 * hx + 0], acc[o][8 * hx + 1]),
+                               packbf_relu(acc[o][8 * hx + 2], acc[o][8 * hx + 3]), packbf_relu(acc[o][8 * hx + 4], acc[o][8 * hx + 5]),
+                               packbf_relu(acc[o][8 * hx + 6], acc[o][8 * hx + 7]));
+            } else if (g >= DB) {
+                mbar_wait(&bar_proj[g % DB], (g / DB - 1) & 1);    // stay in step with the barrier's phases
             }
             fence_async_proxy();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_dready[g & 1]);
+            if (lane == 0) mbar_arrive(&bar_dready[g % DB]);
+            T_STAMP(tid == 64, g, 5);
+            T_STAMP(tid == 15 * 32, g, 6);
             if (e == 0 && lt >= 1) output_epilogue(lt - 1, pn, poy0, pox0);   // deferred by one chunk: keeps the pipeline fed
         }
         output_epilogue(my_tiles - 1, n, oy0, ox0);

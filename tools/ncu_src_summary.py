@@ -7,7 +7,8 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
 hdr = rows[hdr_i]
-body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+col_probe = hdr.index('# Samples')
+body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr) and r[0] != 'Address' and (r[col_probe] or '0').isdigit()]
 col = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
 tot = collections.Counter()

@@ -12,7 +12,7 @@ from fscnn_b200 import native
 
 dev = torch.device('cuda', 0)
 model = FastSCNN(19, precision='bf16').eval().to(dev)
-x = torch.randn(8, 3, 1024, 2048, device=dev)
+x = torch.randn(int(sys.argv[1]) if len(sys.argv) > 1 else 8, 3, 1024, 2048, device=dev)
 for _ in range(3):
     model.predict(x)
 torch.cuda.synchronize()
@@ -58,3 +58,13 @@ if hasattr(lib, 'fscnn_debug_s1_phases') and lib.fscnn_debug_s1_phases(sbuf) == 
     for c in range(4):
         r = [v - t0 for v in s1[c * 8:c * 8 + 8]]
         print(f'  chunk {8 + c}: {r[0]:8d} {r[1]:8d} {r[2]:8d} {r[3]:8d}      {r[4]:8d} {r[5]:8d} {r[6]:8d} {r[7]:8d}')
+
+tbuf = (C.c_longlong * 128)()
+if hasattr(lib, 'fscnn_debug_s1t_phases') and lib.fscnn_debug_s1t_phases(tbuf) == 0:
+    t = list(tbuf)
+    t0 = min(v for v in t if v > 0)
+    print('transposed stride-1 bottleneck, chunks 12..19 of CTA 5 (cycles since the first stamp)')
+    print('  warp0: top | exp done | ldtm+cvt | fma done | D free | D written || w15 written || ctl: proj issue..end | exp issue..end | exp seen done | proj seen done | We prefetch')
+    for c in range(8):
+        r = [(v - t0 if v > 0 else -1) for v in t[c * 16:c * 16 + 16]]
+        print(f'  chunk {12 + c}: ' + ' '.join(f'{v:7d}' for v in r[:6]) + ' || ' + f'{r[6]:7d}' + ' || ' + ' '.join(f'{v:7d}' for v in r[8:15]))
