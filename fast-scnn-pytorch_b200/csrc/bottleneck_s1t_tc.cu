@@ -10,8 +10,9 @@
 //   project  D[128 px x 128 ch] (bf16, MN-major A operand written by the depthwise threads) * Wp chunk -> TMEM accumulator
 //            over the chunks of 128 expanded channels; + bias (+ residual) -> bf16 NHWC.
 //
-// One persistent CTA per SM: 16 compute warps (TMEM lane quarter = warp % 4, row strip = warp / 4) + a control warp whose
-// lane 0 issues every TMA load, bulk copy and MMA from a non-blocking event loop.  The expand accumulator and the
+// One persistent CTA per SM: 16 compute warps (TMEM lane quarter = warp % 4, row strip = warp / 4) + two controller warps
+// (lane 0 each): one issues the halo loads, expand weight copies and expand MMAs, the other the project weight copies and
+// project MMAs, both in order with blocking mbarrier waits.  The expand accumulator and the
 // weight chunks are double-buffered: the tensor core works two chunks ahead of the CUDA cores; every hand-off is an mbarrier.
 #include "kernels.h"
 #include "tma_host.h"
@@ -21,7 +22,7 @@ namespace fscnn {
 
 namespace {
 constexpr int kTWarps = 16;
-constexpr int kTThreads = (kTWarps + 1) * 32;
+constexpr int kTThreads = (kTWarps + 2) * 32;   // 16 compute warps + expand controller + project controller
 
 __device__ __forceinline__ bool mbar_test_t(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -171,20 +172,16 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-#ifndef S1T_CTL_WARP
-#define S1T_CTL_WARP 1
-#endif
-    constexpr int kCtl = S1T_CTL_WARP ? kTWarps : 0;      // the control warp's id
-    if (warp == kCtl) {
-        // =========================== control warp ===========================
+    if (warp == kTWarps) {
+        // =========================== expand controller ===========================
+        // In-order, blocking: wait for what expand(ke) needs, issue it, wait for it to complete, recycle the buffers it read.
+        // (An event loop polling every barrier from one thread reacted thousands of cycles late: each poll is a dependent
+        // test + branch of a single warp sharing its scheduler with four FMA-bound warps.  mbarrier.try_wait parks the warp in
+        // hardware instead, and the expand / project sides no longer queue behind each other's blocking MMA issue.)
         if (lane == 0) {
             auto prefetch_we = [&](int g) {
                 mbar_arrive_expect_tx(&bar_we[g & 1], C::WE_BYTES);
                 bulk_g2s(sm + C::oWe + (g & 1) * C::WE_BYTES, we_img + (size_t)(g % NCH) * CM * C::KA, C::WE_BYTES, &bar_we[g & 1]);
-            };
-            auto prefetch_wp = [&](int g) {
-                mbar_arrive_expect_tx(&bar_wp[g % WPB], C::WP_BYTES);
-                bulk_g2s(sm + C::oWp + (g % WPB) * C::WP_BYTES, wp_img + (size_t)(g % NCH) * COUT * CM, C::WP_BYTES, &bar_wp[g % WPB]);
             };
             auto load_x = [&](int lt) {
                 int n, oy0, ox0;
@@ -194,11 +191,10 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 tma_load_halo(sX + xb * C::XS, &xmap, ox0 - 1, oy0 - 1, n, &bar_x[xb]);
             };
             constexpr uint32_t idesc_exp = make_idesc_bf16(128, C::NB);
-            constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT) | (1u << 15);   // A (= D) is MN-major
             tma_prefetch_desc(&xmap);
             load_x(0);
             if (XB == 2 && my_tiles > 1) load_x(1);
-            if (WRES) {      // all weight chunks, once
+            if (WRES) {      // all weight chunks, once (the project controller waits on the same barrier)
                 mbar_arrive_expect_tx(&bar_wres, NCH * (C::WE_BYTES + C::WP_BYTES));
                 for (int e = 0; e < NCH; ++e) {
                     bulk_g2s(sm + C::oWe + e * C::WE_BYTES, we_img + (size_t)e * CM * C::KA, C::WE_BYTES, &bar_wres);
@@ -208,72 +204,76 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
             } else {
                 prefetch_we(0);
                 if (total > 1) prefetch_we(1);
+            }
+#pragma unroll 1
+            for (int ke = 0; ke < total; ++ke) {
+                const int lt = ke / NCH, e = ke - lt * NCH, xb = lt % XB;
+                if (!WRES) mbar_wait(&bar_we[ke & 1], (ke >> 1) & 1);                    // its weight chunk
+                if (e == 0) mbar_wait(&bar_x[xb], (lt / XB) & 1);                         // its halo tile
+                if (ke >= 2) mbar_wait(&bar_tmfree[ke & 1], ((ke - 2) >> 1) & 1);         // its accumulator, drained by chunk ke-2
+                T_STAMP(true, ke, 10);
+                tc_fence_after_sync();
+                const uint32_t a0 = sWe + (WRES ? e : (ke & 1)) * C::WE_BYTES;
+#pragma unroll
+                for (int k16 = 0; k16 < CIN / 16; ++k16) {
+                    const uint64_t da = make_smem_desc(a0 + k16 * 2 * 2048, 2048, 128);
+                    const uint64_t db = make_smem_desc(sX + xb * C::XS + k16 * 2 * (PIN * 16), PIN * 16, 128);
+                    umma_bf16_ss(tmem + (ke & 1) * C::NB, da, db, idesc_exp, k16 > 0);
+                }
+                umma_bf16_ss(tmem + (ke & 1) * C::NB, make_smem_desc(a0 + (CIN / 16) * 2 * 2048, 2048, 128),
+                             make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
+                umma_commit(&bar_exp[ke & 1]);
+                T_STAMP(true, ke, 11);
+                const bool more_w = !WRES && ke + 2 < total, more_x = (e == NCH - 1) && (lt + XB < my_tiles);
+                if (more_w || more_x) {
+                    mbar_wait(&bar_exp[ke & 1], (ke >> 1) & 1);       // expand(ke) has completed: what it read may be overwritten
+                    T_STAMP(true, ke, 12);
+                    if (more_w) prefetch_we(ke + 2);
+                    if (more_x) load_x(lt + XB);
+                }
+            }
+        }
+    } else if (warp == kTWarps + 1) {
+        // =========================== project controller ===========================
+        if (lane == 0) {
+            auto prefetch_wp = [&](int g) {
+                mbar_arrive_expect_tx(&bar_wp[g % WPB], C::WP_BYTES);
+                bulk_g2s(sm + C::oWp + (g % WPB) * C::WP_BYTES, wp_img + (size_t)(g % NCH) * COUT * CM, C::WP_BYTES, &bar_wp[g % WPB]);
+            };
+            constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT) | (1u << 15);   // A (= D) is MN-major
+            if (WRES) {
+                mbar_wait(&bar_wres, 0);
+            } else {
                 prefetch_wp(0);
                 if (WPB == 2 && total > 1) prefetch_wp(1);
             }
-            int ke = 0, kp = 0, kw = WRES ? (1 << 30) : 2, kq = WRES ? (1 << 30) : WPB, kx = XB, exp_done = 0, proj_done = 0;
 #pragma unroll 1
-            while (kp < total) {
-                const int progress0 = ke + kp + kw + kq + kx + exp_done + proj_done;
-                // ---- project(kp) first (its result frees D, which the compute warps need again within a chunk): needs D written, its weight chunk, and (first chunk of a tile) the previous tile's accumulator read ----
-                {
-                    const int lt = kp / NCH, e = kp - lt * NCH;
-                    bool ok = mbar_test_t(&bar_dready[kp % DB], (kp / DB) & 1);
-                    if (ok && !WRES) ok = mbar_test_t(&bar_wp[kp % WPB], (kp / WPB) & 1);
-                    if (ok && e == 0 && lt > 0) ok = mbar_test_t(&bar_projfree, (lt - 1) & 1);
-                    if (ok) {
-                        if (proj_done < kp - DB + 1) proj_done = kp - DB + 1;    // its D buffer was rewritten: project(kp-DB) has completed
-                        T_STAMP(true, kp, 8);
-                        tc_fence_after_sync();
-                        const int ksteps = ((C::CEXP - e * CM) < CM ? (C::CEXP - e * CM) : CM) / 16;
-                        for (int k16 = 0; k16 < ksteps; ++k16) {
-                            const uint64_t da = make_smem_desc(sD + (kp % DB) * C::D_BYTES + k16 * 2 * C::D_LBO, C::D_LBO, C::D_SBO);
-                            const uint64_t db = make_smem_desc(sWp + (WRES ? e : kp % WPB) * C::WP_BYTES + k16 * 2 * (COUT * 16), COUT * 16, 128);
-                            umma_bf16_ss(tmem + C::TM_PROJ, da, db, idesc_proj, (e | k16) != 0);
-                        }
-                        umma_commit(&bar_proj[kp % DB]);
-                        if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
-                        T_STAMP(true, kp, 9);
-                        ++kp;
-                    }
+            for (int kp = 0; kp < total; ++kp) {
+                const int lt = kp / NCH, e = kp - lt * NCH;
+                if (!WRES) mbar_wait(&bar_wp[kp % WPB], (kp / WPB) & 1);                  // its weight chunk
+                if (e == 0 && lt > 0) mbar_wait(&bar_projfree, (lt - 1) & 1);             // the previous tile's accumulator has been read
+                mbar_wait(&bar_dready[kp % DB], (kp / DB) & 1);                           // D written by the depthwise threads
+                T_STAMP(true, kp, 8);
+                tc_fence_after_sync();
+                const int ksteps = ((C::CEXP - e * CM) < CM ? (C::CEXP - e * CM) : CM) / 16;
+                for (int k16 = 0; k16 < ksteps; ++k16) {
+                    const uint64_t da = make_smem_desc(sD + (kp % DB) * C::D_BYTES + k16 * 2 * C::D_LBO, C::D_LBO, C::D_SBO);
+                    const uint64_t db = make_smem_desc(sWp + (WRES ? e : kp % WPB) * C::WP_BYTES + k16 * 2 * (COUT * 16), COUT * 16, 128);
+                    umma_bf16_ss(tmem + C::TM_PROJ, da, db, idesc_proj, (e | k16) != 0);
                 }
-                // ---- expand(ke): needs its halo tile (first chunk of a tile), its weight chunk, and the TMEM buffer drained ----
-                if (ke < total) {
-                    const int lt = ke / NCH, e = ke - lt * NCH, xb = lt % XB;
-                    bool ok = WRES || mbar_test_t(&bar_we[ke & 1], (ke >> 1) & 1);
-                    if (ok && e == 0) ok = mbar_test_t(&bar_x[xb], (lt / XB) & 1);
-                    if (ok && ke >= 2) ok = mbar_test_t(&bar_tmfree[ke & 1], ((ke - 2) >> 1) & 1);
-                    if (ok) {
-                        if (ke >= 2 && exp_done < ke - 1) exp_done = ke - 1;     // its TMEM was drained: expand(ke-2) has completed
-                        T_STAMP(true, ke, 10);
-                        tc_fence_after_sync();
-                        const uint32_t a0 = sWe + (WRES ? e : (ke & 1)) * C::WE_BYTES;
-#pragma unroll
-                        for (int k16 = 0; k16 < CIN / 16; ++k16) {
-                            const uint64_t da = make_smem_desc(a0 + k16 * 2 * 2048, 2048, 128);
-                            const uint64_t db = make_smem_desc(sX + xb * C::XS + k16 * 2 * (PIN * 16), PIN * 16, 128);
-                            umma_bf16_ss(tmem + (ke & 1) * C::NB, da, db, idesc_exp, k16 > 0);
-                        }
-                        umma_bf16_ss(tmem + (ke & 1) * C::NB, make_smem_desc(a0 + (CIN / 16) * 2 * 2048, 2048, 128),
-                                     make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
-                        umma_commit(&bar_exp[ke & 1]);
-                        T_STAMP(true, ke, 11);
-                        ++ke;
-                    }
+                umma_commit(&bar_proj[kp % DB]);
+                if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
+                T_STAMP(true, kp, 9);
+                if (!WRES && kp + WPB < total) {
+                    mbar_wait(&bar_proj[kp % DB], (kp / DB) & 1);     // project(kp) has completed: its weight buffer is free
+                    T_STAMP(true, kp, 13);
+                    prefetch_wp(kp + WPB);
                 }
-                // ---- completion tracking of the expand MMAs, in order ----
-                if (exp_done < ke && mbar_test_t(&bar_exp[exp_done & 1], (exp_done >> 1) & 1)) { T_STAMP(true, exp_done, 12); ++exp_done; }
-                if (kw < total && exp_done > kw - 2) { T_STAMP(true, kw, 14); prefetch_we(kw); ++kw; }
-                if (kx < my_tiles && exp_done > (kx - XB) * NCH + NCH - 1) { load_x(kx); ++kx; }
-                if (proj_done < kp && mbar_test_t(&bar_proj[proj_done % DB], (proj_done / DB) & 1)) { T_STAMP(true, proj_done, 13); ++proj_done; }
-                if (kq < total && proj_done > kq - WPB) { prefetch_wp(kq); ++kq; }
-                if (ke + kp + kw + kq + kx + exp_done + proj_done == progress0) __nanosleep(20);   // idle: leave the issue slots to the compute warps
             }
         }
     } else {
         // =========================== compute warps ===========================
-        const int cw = kCtl == 0 ? warp - 1 : warp;       // compute-warp index 0..15
-        const int q = warp & 3, s = cw >> 2;              // TMEM lane quarter = warp % 4 (hardware rule), row strip (output rows 2s, 2s+1)
+        const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter = warp % 4 (hardware rule), row strip (output rows 2s, 2s+1)
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float* Bp_g = reinterpret_cast<const float*>(tab + (size_t)NCH * CM * 32);
         int n = 0, oy0 = 0, ox0 = 0, pn = 0, poy0 = 0, pox0 = 0;
@@ -325,9 +325,9 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 wa = __ldg(rec);
                 wb = __ldg(rec + 1);
             }
-            T_STAMP(tid == 64, g, 0);
+            T_STAMP(tid == 0, g, 0);
             mbar_wait(&bar_exp[g & 1], (g >> 1) & 1);            // expand(g) has completed
-            T_STAMP(tid == 64, g, 1);
+            T_STAMP(tid == 0, g, 1);
             tc_fence_after_sync();
             uint32_t Ep[4][9];                                   // halo rows 2s .. 2s+3, column pairs (2i, 2i+1), ReLU'd bf16
             if (active) {
@@ -345,7 +345,7 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tmfree[g & 1]);      // expand(g+2) may overwrite this accumulator
-            T_STAMP(tid == 64, g, 2);
+            T_STAMP(tid == 0, g, 2);
             if (active) {
                 // zero padding of the depthwise conv: halo columns / rows outside the image (border tiles only)
                 const int ix0 = ox0 - 1, iy0 = oy0 - 1 + 2 * s;
@@ -384,9 +384,9 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                                                           wq[(ky * 3 + kx) >> 1], (ky * 3 + kx) & 1);
                         }
                     }
-                T_STAMP(tid == 64, g, 3);
+                T_STAMP(tid == 0, g, 3);
                 if (g >= DB) mbar_wait(&bar_proj[g % DB], (g / DB - 1) & 1);   // project(g-DB) has completed: this D buffer is free
-                T_STAMP(tid == 64, g, 4);
+                T_STAMP(tid == 0, g, 4);
                 const int k = q * 32 + lane;
                 const uint32_t d0 = sD + (g % DB) * C::D_BYTES + (k >> 3) * C::D_LBO + (k & 7) * 16 + (4 * s) * C::D_SBO;
 #pragma unroll
@@ -402,7 +402,7 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
             fence_async_proxy();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dready[g % DB]);
-            T_STAMP(tid == 64, g, 5);
+            T_STAMP(tid == 0, g, 5);
             T_STAMP(tid == 15 * 32, g, 6);
             if (e == 0 && lt >= 1) output_epilogue(lt - 1, pn, poy0, pox0);   // deferred by one chunk: keeps the pipeline fed
         }
