@@ -131,7 +131,7 @@ extern "C" int fscnn_debug_s1t_phases(long long* out128) {
 #endif
 
 template <int CIN, int COUT, bool RES>
-__global__ void __launch_bounds__(kTThreads, 1)
+__global__ void __launch_bounds__(kTThreads, 1)   // 96 registers: the allocation granule is 1024 per warp (112 x 576 threads does not launch)
 bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restrict__ in, const unsigned char* __restrict__ tab,
                       const bf16* __restrict__ we_img, const bf16* __restrict__ wp_img, bf16* __restrict__ out, int H, int W,
                       int tiles_x, int tiles_y, int ntiles) {
@@ -278,40 +278,56 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
         const float* Bp_g = reinterpret_cast<const float*>(tab + (size_t)NCH * CM * 32);
         int n = 0, oy0 = 0, ox0 = 0, pn = 0, poy0 = 0, pox0 = 0;
         auto output_epilogue = [&](int lt, int tn, int toy0, int tox0) {   // + bias (+ residual from global, L2-resident), bf16 NHWC store
-            mbar_wait(&bar_tiledone, lt & 1);                 // every project MMA of tile lt has completed
-            tc_fence_after_sync();
             const int p = q * 32 + lane;
             const int oy = toy0 + (p >> 4), ox = tox0 + (p & 15);
             const bool live = (oy < H) && (ox < W);
             const size_t pix = ((size_t)tn * H + oy) * W + ox;
             constexpr int CP = COUT / 4;                  // columns per warp: 16, 24 or 32
+            const int co0 = s * CP;
+            // every global load is in flight before the first wait: the latency is paid once per tile, not once per piece
+            uint4 res[CP / 8];
 #pragma unroll
-            for (int c0 = 0; c0 < CP; c0 += 8) {
-                const int co = s * CP + c0;
-                uint32_t r[8];
-                tmem_ld_32x32b_x8(tmem + lane_base + C::TM_PROJ + co, r);
-                uint4 res = make_uint4(0u, 0u, 0u, 0u);
-                if (RES && live) res = __ldg(reinterpret_cast<const uint4*>(in + pix * CIN + co));
-                const float4 ba = __ldg(reinterpret_cast<const float4*>(Bp_g + co));
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(Bp_g + co + 4));
+            for (int i = 0; i < CP / 8; ++i) {
+                res[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (RES && live) res[i] = __ldg(reinterpret_cast<const uint4*>(in + pix * CIN + co0 + 8 * i));
+            }
+            mbar_wait(&bar_tiledone, lt & 1);                 // every project MMA of tile lt has completed
+            tc_fence_after_sync();
+            // accumulator columns in pieces of 16 (8 for the tail of a 24-column slice): keeps the register footprint small
+#pragma unroll
+            for (int c0 = 0; c0 < CP; c0 += 16) {
+                constexpr int kDummy = 0; (void)kDummy;
+                const int w16 = (CP - c0 >= 16) ? 16 : 8;
+                uint32_t r[16];
+                if (w16 == 16) tmem_ld_32x32b_x16(tmem + lane_base + C::TM_PROJ + co0 + c0, r);
+                else tmem_ld_32x32b_x8(tmem + lane_base + C::TM_PROJ + co0 + c0, r);
                 tmem_ld_wait();
+                if (c0 + 16 >= CP) {                         // last piece read: the next tile's first project MMA may overwrite the accumulator
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_projfree);
+                }
                 if (live) {
-                    float v[8] = {__uint_as_float(r[0]) + ba.x, __uint_as_float(r[1]) + ba.y, __uint_as_float(r[2]) + ba.z,
-                                  __uint_as_float(r[3]) + ba.w, __uint_as_float(r[4]) + bb.x, __uint_as_float(r[5]) + bb.y,
-                                  __uint_as_float(r[6]) + bb.z, __uint_as_float(r[7]) + bb.w};
-                    if (RES) {
-                        float f[8];
-                        unpackbf8(res, f);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] += f[i];
+                    for (int i = 0; i < w16 / 8; ++i) {
+                        const int co = co0 + c0 + 8 * i;
+                        const float4 ba = __ldg(reinterpret_cast<const float4*>(Bp_g + co));
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(Bp_g + co + 4));
+                        const uint32_t* q8 = r + 8 * i;
+                        float v[8] = {__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y, __uint_as_float(q8[2]) + ba.z,
+                                      __uint_as_float(q8[3]) + ba.w, __uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y,
+                                      __uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w};
+                        if (RES) {
+                            float f[8];
+                            unpackbf8(res[c0 / 8 + i], f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] += f[j];
+                        }
+                        *reinterpret_cast<uint4*>(out + pix * COUT + co) =
+                            make_uint4(packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
                     }
-                    *reinterpret_cast<uint4*>(out + pix * COUT + co) =
-                        make_uint4(packbf(v[0], v[1]), packbf(v[2], v[3]), packbf(v[4], v[5]), packbf(v[6], v[7]));
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_projfree);       // the next tile's first project MMA may overwrite the accumulator
         };
 #pragma unroll 1
         for (int g = 0; g < total; ++g) {
