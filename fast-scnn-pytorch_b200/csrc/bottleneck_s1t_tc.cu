@@ -121,10 +121,10 @@ struct T1Cfg {
 #ifndef DBG_CIN
 #define DBG_CIN 128
 #endif
-__device__ long long g_s1t_phase[8 * 16];
-#define T_STAMP(cond, gg, slot) do { if (CIN == DBG_CIN && blockIdx.x == 5 && (cond) && (gg) >= 12 && (gg) < 20) g_s1t_phase[((gg) - 12) * 16 + (slot)] = clock64(); } while (0)
+__device__ long long g_s1t_phase[8 * 16 * 3];   // [0,128): roles; [128,256): per-warp "D written"; [256,384): per-warp "top"
+#define T_STAMP(cond, gg, slot) do { if (CIN == DBG_CIN && blockIdx.x == 5 && (cond) && (gg) >= 12 && (gg) < 20) g_s1t_phase[((slot) / 128) * 128 + ((gg) - 12) * 16 + ((slot) % 128)] = clock64(); } while (0)
 extern "C" int fscnn_debug_s1t_phases(long long* out128) {
-    return cudaMemcpyFromSymbol(out128, g_s1t_phase, sizeof(long long) * 128) == cudaSuccess ? 0 : -1;
+    return cudaMemcpyFromSymbol(out128, g_s1t_phase, sizeof(long long) * 384) == cudaSuccess ? 0 : -1;
 }
 #else
 #define T_STAMP(cond, gg, slot) do { } while (0)
@@ -213,15 +213,14 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 if (ke >= 2) mbar_wait(&bar_tmfree[ke & 1], ((ke - 2) >> 1) & 1);         // its accumulator, drained by chunk ke-2
                 T_STAMP(true, ke, 10);
                 tc_fence_after_sync();
-                const uint32_t a0 = sWe + (WRES ? e : (ke & 1)) * C::WE_BYTES;
+                // descriptors advance by adding to the 14-bit start-address field (bytes >> 4): a handful of instructions per MMA
+                const uint64_t da0 = make_smem_desc(sWe + (WRES ? e : (ke & 1)) * C::WE_BYTES, 2048, 128);
+                const uint64_t db0 = make_smem_desc(sX + xb * C::XS, PIN * 16, 128);
+                const uint32_t dacc = tmem + (ke & 1) * C::NB;
 #pragma unroll
-                for (int k16 = 0; k16 < CIN / 16; ++k16) {
-                    const uint64_t da = make_smem_desc(a0 + k16 * 2 * 2048, 2048, 128);
-                    const uint64_t db = make_smem_desc(sX + xb * C::XS + k16 * 2 * (PIN * 16), PIN * 16, 128);
-                    umma_bf16_ss(tmem + (ke & 1) * C::NB, da, db, idesc_exp, k16 > 0);
-                }
-                umma_bf16_ss(tmem + (ke & 1) * C::NB, make_smem_desc(a0 + (CIN / 16) * 2 * 2048, 2048, 128),
-                             make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
+                for (int k16 = 0; k16 < CIN / 16; ++k16)
+                    umma_bf16_ss(dacc, da0 + (uint64_t)(k16 * ((2 * 2048) >> 4)), db0 + (uint64_t)(k16 * ((2 * PIN * 16) >> 4)), idesc_exp, k16 > 0);
+                umma_bf16_ss(dacc, da0 + (uint64_t)((CIN / 16) * ((2 * 2048) >> 4)), make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
                 umma_commit(&bar_exp[ke & 1]);
                 T_STAMP(true, ke, 11);
                 const bool more_w = !WRES && ke + 2 < total, more_x = (e == NCH - 1) && (lt + XB < my_tiles);
@@ -255,12 +254,14 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 mbar_wait(&bar_dready[kp % DB], (kp / DB) & 1);                           // D written by the depthwise threads
                 T_STAMP(true, kp, 8);
                 tc_fence_after_sync();
-                const int ksteps = ((C::CEXP - e * CM) < CM ? (C::CEXP - e * CM) : CM) / 16;
-                for (int k16 = 0; k16 < ksteps; ++k16) {
-                    const uint64_t da = make_smem_desc(sD + (kp % DB) * C::D_BYTES + k16 * 2 * C::D_LBO, C::D_LBO, C::D_SBO);
-                    const uint64_t db = make_smem_desc(sWp + (WRES ? e : kp % WPB) * C::WP_BYTES + k16 * 2 * (COUT * 16), COUT * 16, 128);
-                    umma_bf16_ss(tmem + C::TM_PROJ, da, db, idesc_proj, (e | k16) != 0);
-                }
+                const uint64_t da0 = make_smem_desc(sD + (kp % DB) * C::D_BYTES, C::D_LBO, C::D_SBO);
+                const uint64_t db0 = make_smem_desc(sWp + (WRES ? e : kp % WPB) * C::WP_BYTES, COUT * 16, 128);
+                const bool half = (C::CEXP - e * CM) < CM;       // the last chunk of a 576-channel layer holds 64 channels
+#pragma unroll
+                for (int k16 = 0; k16 < CM / 16; ++k16)
+                    if (k16 < CM / 32 || !half)
+                        umma_bf16_ss(tmem + C::TM_PROJ, da0 + (uint64_t)(k16 * ((2 * C::D_LBO) >> 4)),
+                                     db0 + (uint64_t)(k16 * ((2 * COUT * 16) >> 4)), idesc_proj, (e | k16) != 0);
                 umma_commit(&bar_proj[kp % DB]);
                 if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
                 T_STAMP(true, kp, 9);
@@ -342,6 +343,7 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 wb = __ldg(rec + 1);
             }
             T_STAMP(tid == 0, g, 0);
+            T_STAMP(lane == 0, g, 256 + warp);
             mbar_wait(&bar_exp[g & 1], (g >> 1) & 1);            // expand(g) has completed
             T_STAMP(tid == 0, g, 1);
             tc_fence_after_sync();
@@ -419,6 +421,7 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dready[g % DB]);
             T_STAMP(tid == 0, g, 5);
+            T_STAMP(lane == 0, g, 128 + warp);
             T_STAMP(tid == 15 * 32, g, 6);
             if (e == 0 && lt >= 1) output_epilogue(lt - 1, pn, poy0, pox0);   // deferred by one chunk: keeps the pipeline fed
         }

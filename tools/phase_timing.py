@@ -59,7 +59,7 @@ if hasattr(lib, 'fscnn_debug_s1_phases') and lib.fscnn_debug_s1_phases(sbuf) == 
         r = [v - t0 for v in s1[c * 8:c * 8 + 8]]
         print(f'  chunk {8 + c}: {r[0]:8d} {r[1]:8d} {r[2]:8d} {r[3]:8d}      {r[4]:8d} {r[5]:8d} {r[6]:8d} {r[7]:8d}')
 
-tbuf = (C.c_longlong * 128)()
+tbuf = (C.c_longlong * 384)()
 if hasattr(lib, 'fscnn_debug_s1t_phases') and lib.fscnn_debug_s1t_phases(tbuf) == 0:
     t = list(tbuf)
     t0 = min(v for v in t if v > 0)
@@ -68,3 +68,7 @@ if hasattr(lib, 'fscnn_debug_s1t_phases') and lib.fscnn_debug_s1t_phases(tbuf) =
     for c in range(8):
         r = [(v - t0 if v > 0 else -1) for v in t[c * 16:c * 16 + 16]]
         print(f'  chunk {12 + c}: ' + ' '.join(f'{v:7d}' for v in r[:6]) + ' || ' + f'{r[6]:7d}' + ' || ' + ' '.join(f'{v:7d}' for v in r[8:15]))
+    print('  per-warp loop top (cycles since first stamp), warps 0..15, then per-warp D written')
+    for c in range(8):
+        print(f'  chunk {12 + c} top: ' + ' '.join(f'{(v - t0 if v > 0 else -1):6d}' for v in t[256 + c * 16:256 + c * 16 + 16]))
+        print(f'  chunk {12 + c} Dwr: ' + ' '.join(f'{(v - t0 if v > 0 else -1):6d}' for v in t[128 + c * 16:128 + c * 16 + 16]))
