@@ -109,6 +109,7 @@ struct fscnn_ctx {
     const bf16* bn_wpT_img[9]{};
     const unsigned char* bn_tabT_img[9]{};
     int s1_transposed = 1;   // bf16 stride-1 bottlenecks: transposed-expand kernel (0 = the three-role kernel)
+    int s2_transposed = 1;   // bf16 stride-2 bottlenecks: transposed-expand kernel (0 = bottleneck_tc.cu)
     const bf16* ds_wp_img[4]{};
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
@@ -247,7 +248,7 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
             f.bn_we_img[i] = take((size_t)ce * ci / 2);
             f.bn_wp_img[i] = take((size_t)co * ce / 2);
             f.bn_tab_img[i] = take((bottleneck_tc_tab_bytes(ci, co) + 3) / 4);
-            if (kBnecks[i].stride == 1) {
+            {
                 f.bn_weT_img[i] = take((bottleneck_s1t_we_bytes(ci) + 3) / 4);
                 f.bn_wpT_img[i] = take((bottleneck_s1t_wp_bytes(ci, co) + 3) / 4);
                 f.bn_tabT_img[i] = take((bottleneck_s1t_tab_bytes(ci, co) + 3) / 4);
@@ -377,6 +378,9 @@ cudaError_t bottleneck_dispatch<float>(fscnn_ctx* c, int i, const float* in, flo
 template <>
 cudaError_t bottleneck_dispatch<bf16>(fscnn_ctx* c, int i, const bf16* in, bf16* out, int m, int hi, int wi, int ho, int wo,
                                       cudaStream_t s) {
+    if (kBnecks[i].stride == 2 && c->s2_transposed)
+        return launch_bottleneck_s2t_tc(kBnecks[i].cin, kBnecks[i].cout, in, c->bn_tabT_img[i], c->bn_weT_img[i], c->bn_wpT_img[i], out,
+                                        m, hi, wi, ho, wo, s);
     if (kBnecks[i].stride == 1 && c->s1_transposed)
         return launch_bottleneck_s1t_tc(kBnecks[i].cin, kBnecks[i].cout, in, c->bn_tabT_img[i], c->bn_weT_img[i], c->bn_wpT_img[i], out,
                                         m, hi, wi, s);
@@ -563,7 +567,7 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
             if (!L.err && launch_pack_bneck_tab(c->bn[i], ce, co, tab, L.s) != cudaSuccess)
                 L.err = fail(FSCNN_ECUDA, "table pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             c->bn_tab_img[i] = tab;
-            if (kBnecks[i].stride == 1) {
+            {
                 bf16* weT = reinterpret_cast<bf16*>(P + f.bn_weT_img[i]);
                 bf16* wpT = reinterpret_cast<bf16*>(P + f.bn_wpT_img[i]);
                 unsigned char* tabT = reinterpret_cast<unsigned char*>(P + f.bn_tabT_img[i]);
@@ -645,6 +649,7 @@ int fscnn_set_option(fscnn_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(FSCNN_EINVAL, "null argument");
     if (!strcmp(key, "fuse_front")) { c->fuse_front = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "s1_transposed")) { c->s1_transposed = value ? 1 : 0; return FSCNN_OK; }
+    if (!strcmp(key, "s2_transposed")) { c->s2_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "micro_batch")) return fscnn_set_micro_batch(c, value);
     return fail(FSCNN_ENOENT, "unknown option '%s'", key);
 }

@@ -91,6 +91,9 @@ size_t bottleneck_s1t_tab_bytes(int cin, int cout);
 cudaError_t launch_pack_s1t(const BneckW& w, int cin, int cout, bf16* we_img, unsigned char* tab, cudaStream_t s);
 cudaError_t launch_bottleneck_s1t_tc(int cin, int cout, const bf16* in, const unsigned char* tab, const bf16* we_img,
                                      const bf16* wp_img, bf16* out, int n, int h, int w, cudaStream_t s);
+// stride-2 layers, transposed expand over 2x2 sub-tiles of 4x8 output pixels (bottleneck_s2t_tc.cu); same operand images
+cudaError_t launch_bottleneck_s2t_tc(int cin, int cout, const bf16* in, const unsigned char* tab, const bf16* we_img,
+                                     const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
                                  const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 
