@@ -96,6 +96,7 @@ struct fscnn_ctx {
         size_t aux_w, aux_b, auxh_w, auxh_b;
         size_t bn_we_img[9], bn_wp_img[9], bn_tab_img[9];   // bf16 tcgen05 operand images + constant tables (offsets still in floats)
         size_t bn_weT_img[9], bn_wpT_img[9], bn_tabT_img[9]; // stride-1 layers: operands of the transposed-expand kernel
+        size_t ffm_tabT;   // FFM, transposed kernel: per-channel depthwise records + fused bias
         size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8, stem_imgx, stem_imgx_u8;
     } off{};
     // device pointers resolved by load_weights
@@ -113,6 +114,8 @@ struct fscnn_ctx {
     const bf16* ds_wp_img[4]{};
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
+    const unsigned char* ffm_tabT = nullptr;
+    int ffm_transposed = 1;  // bf16 FFM: resize on the tensor core + depthwise out of TMEM (0 = ffm_tc.cu)
     const bf16* stem_img = nullptr;
     bf16* stem_img_u8 = nullptr;
     float* stem_b_u8 = nullptr;
@@ -258,6 +261,7 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
         for (int i = 0; i < 4; ++i) f.ds_wp_img[i] = take((size_t)dss[i].cin * dss[i].cout / 2);
         f.head_img = take((size_t)((c->nc + 15) & ~15) * 128 / 2);
         f.ffm_img = take((size_t)128 * 192 / 2);
+        f.ffm_tabT = take((128 * 32 + 128 * 4) / 4);
         f.stem_img = take((size_t)32 * 32 / 2);
         f.stem_img_u8 = take((size_t)32 * 32 / 2);
         f.stem_b_u8 = take(32);
@@ -408,6 +412,8 @@ cudaError_t ffm_dispatch<float>(fscnn_ctx* c, const float* higher, const float* 
 template <>
 cudaError_t ffm_dispatch<bf16>(fscnn_ctx* c, const bf16* higher, const bf16* lower, bf16* out, int m, int hh, int wh, int hl,
                                int wl, cudaStream_t s) {
+    if (c->ffm_transposed && ffm_t_supported(hh, wh, hl, wl))
+        return launch_ffm_t_tc(higher, lower, c->ffm_tabT, c->ffm_img, out, m, hh, wh, hl, wl, s);
     return launch_ffm_tc(higher, lower, c->ffm, c->ffm_img, out, m, hh, wh, hl, wl, s);
 }
 
@@ -605,6 +611,10 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         L.fold_umma("feature_fusion.conv_higher_res.0", "feature_fusion.conv_higher_res.1", 128, 64, 128, 64, img);
         L.fold_umma("feature_fusion.conv_lower_res.0", "feature_fusion.conv_lower_res.1", 128, 128, 128, 128, img + 128 * 64);
         c->ffm_img = img;
+        unsigned char* ftab = reinterpret_cast<unsigned char*>(P + f.ffm_tabT);
+        if (!L.err && launch_pack_dw_tab(c->ffm.wd, c->ffm.bd, c->ffm.bcat, 128, 128, ftab, L.s) != cudaSuccess)
+            L.err = fail(FSCNN_ECUDA, "ffm table pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        c->ffm_tabT = ftab;
     }
     L.fold("classifier.conv.1", true, "", c->nc, 128, 1, 0, P + f.head_w, c->ncp, P + f.head_b);
     c->head = {P + f.head_w, P + f.head_b, c->nc, c->ncp};
@@ -650,6 +660,7 @@ int fscnn_set_option(fscnn_ctx* c, const char* key, int value) {
     if (!strcmp(key, "fuse_front")) { c->fuse_front = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "s1_transposed")) { c->s1_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "s2_transposed")) { c->s2_transposed = value ? 1 : 0; return FSCNN_OK; }
+    if (!strcmp(key, "ffm_transposed")) { c->ffm_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "micro_batch")) return fscnn_set_micro_batch(c, value);
     return fail(FSCNN_ENOENT, "unknown option '%s'", key);
 }

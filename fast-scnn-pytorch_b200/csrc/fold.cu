@@ -208,6 +208,11 @@ __global__ void pack_s1t_tab_kernel(const float* __restrict__ wd, const float* _
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cout; i += gridDim.x * blockDim.x) bpo[i] = bp[i];
 }
 
+cudaError_t launch_pack_dw_tab(const float* wd, const float* bd, const float* bout, int c, int cout, unsigned char* tab, cudaStream_t s) {
+    pack_s1t_tab_kernel<<<8, 128, 0, s>>>(wd, bd, bout, c, cout, tab);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack_s1t(const BneckW& w, int cin, int cout, bf16* we_img, unsigned char* tab, cudaStream_t s) {
     const int cexp = 6 * cin;
     pack_s1t_we_kernel<<<64, 256, 0, s>>>(w.we, w.be, cin, cexp, we_img);

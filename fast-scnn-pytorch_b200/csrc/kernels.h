@@ -102,6 +102,12 @@ cudaError_t launch_dsconv_tc(int cin, int cout, int stride, const bf16* in, cons
                              const HeadW* head, const bf16* wh_img, float* logits, int n, int hi, int wi, int ho, int wo,
                              cudaStream_t s);
 
+// transposed FFM (ffm_t_tc.cu): bilinear resize as an MMA against a per-tile interpolation matrix, depthwise out of TMEM.
+// tab = launch_pack_dw_tab(ffm.wd, ffm.bd, ffm.bcat, 128, 128): per-channel {9 bf16 taps, f32 bias} records + f32 fused bias
+bool ffm_t_supported(int hh, int wh, int hl, int wl);
+cudaError_t launch_pack_dw_tab(const float* wd, const float* bd, const float* bout, int c, int cout, unsigned char* tab, cudaStream_t s);
+cudaError_t launch_ffm_t_tc(const bf16* higher, const bf16* lower, const unsigned char* tab, const bf16* wcat_img, bf16* out, int n,
+                            int hh, int wh, int hl, int wl, cudaStream_t s);
 // wcat_img: the stacked [128 x 192] weight (64 higher | 128 lower input channels) as one chunk
 cudaError_t launch_ffm_tc(const bf16* higher, const bf16* lower, const FfmW& w, const bf16* wcat_img, bf16* out, int n, int hh,
                           int wh, int hl, int wl, cudaStream_t s);
