@@ -32,7 +32,10 @@ constexpr int R_LBO = kNB * 16, R_BYTES = (kKR / 8) * R_LBO;  // [48/8][192 px][
 constexpr int D_LBO = 128, D_SBO = 2048, D_BYTES = 16 * D_SBO;
 constexpr int W_BYTES = kCO * (kCH + kCL) * 2;                // [192/8][128 cout][8]: LBO 2048, SBO 128
 constexpr int oHi = 0, oPatch = oHi + 2 * HI_BYTES, oR = oPatch + 2 * PATCH_BYTES, oD = oR + 2 * R_BYTES, oW = oD + 2 * D_BYTES;
-constexpr int kSmemT = oW + W_BYTES;
+constexpr int oBias = oW + W_BYTES;                           // B block [2 k-blocks][128 cout][8]: {bias head, remainder, 0 x 6} | zeros
+constexpr int BIAS_BYTES = 2 * kCO * 16;
+constexpr int oOnes = oBias + BIAS_BYTES;                     // A block: one core matrix of rows {1, 1, 0 x 6} + one of zeros (SBO = 0)
+constexpr int kSmemT = oOnes + 256;
 static_assert(kSmemT <= 227 * 1024 - 256, "shared memory");
 constexpr int TM_OUT = 2 * kNB;                               // resize accumulators 2 x 192 columns, fuse accumulator 128
 }  // namespace
@@ -75,6 +78,15 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
     // 40..47) reads into the neighbouring channel group / buffer: those products meet zero weights, so they must be finite
     for (int i = tid; i < (2 * PATCH_BYTES + 2 * R_BYTES) / 16; i += kFThreads)
         *reinterpret_cast<uint4*>(sm + oPatch + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    // the fused bias rides through the tensor core: OUT += ones[128 px x 16] * biasblock[128 cout x 16]^T (bf16 head + remainder)
+    if (tid < kCO) {
+        const float b = __ldg(reinterpret_cast<const float*>(tab + (size_t)kCL * 32) + tid);
+        const __nv_bfloat16 bh = __float2bfloat16_rn(b), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+        const uint32_t w0 = (uint32_t)(*reinterpret_cast<const uint16_t*>(&bh)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&bl)) << 16);
+        *reinterpret_cast<uint4*>(sm + oBias + tid * 16) = make_uint4(w0, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sm + oBias + kCO * 16 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid < 16) *reinterpret_cast<uint4*>(sm + oOnes + tid * 16) = make_uint4(tid < 8 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
     fence_async_proxy();
     if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
     tc_fence_before_sync();
@@ -139,10 +151,12 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
                 tc_fence_after_sync();
                 const uint64_t dh0 = make_smem_desc(sHi + (t & 1) * HI_BYTES, 2048, 128);
                 const uint64_t dw0 = make_smem_desc(sW, 2048, 128);
+                umma_bf16_ss(tmem + TM_OUT, make_smem_desc(smem_u32(sm + oOnes), 128, 0), make_smem_desc(smem_u32(sm + oBias), kCO * 16, 128),
+                             idesc_hi, 0);                                                 // bias
 #pragma unroll
                 for (int k16 = 0; k16 < kCH / 16; ++k16)                                   // higher's 64 channels: ready before D is
                     umma_bf16_ss(tmem + TM_OUT, dh0 + (uint64_t)(k16 * ((2 * 2048) >> 4)), dw0 + (uint64_t)(k16 * ((2 * 2048) >> 4)),
-                                 idesc_hi, k16 > 0);
+                                 idesc_hi, 1);
                 mbar_wait(&bar_dready[t & 1], (t >> 1) & 1);                              // D written by the depthwise threads
                 tc_fence_after_sync();
                 const uint64_t dd0 = make_smem_desc(sD + (t & 1) * D_BYTES, D_LBO, D_SBO);
@@ -161,7 +175,6 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
         // =========================== compute warps ===========================
         const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter, row strip (output rows 2s, 2s+1) / 32-column slice
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const float* Bc_g = reinterpret_cast<const float*>(tab + (size_t)kCL * 32);
         // one row of the interpolation matrix per thread (threads 0..179)
         auto build_r = [&](int lt) {
             if (tid < kPIN) {
@@ -197,7 +210,7 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_r[lt & 1]);
         };
-        auto epilogue = [&](int lt) {                     // + bias, ReLU -> bf16 NHWC
+        auto epilogue = [&](int lt) {                     // ReLU -> bf16 NHWC (the bias is already in the accumulator)
             int n, oy0, ox0;
             tile_origin(lt, n, oy0, ox0);
             const int p = q * 32 + lane;
@@ -219,15 +232,10 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
                 if (live) {
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const int co = s * 32 + c0 + 8 * i;
-                        const float4 ba = __ldg(reinterpret_cast<const float4*>(Bc_g + co));
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(Bc_g + co + 4));
                         const uint32_t* q8 = r + 8 * i;
-                        *reinterpret_cast<uint4*>(out + pix * kCO + co) =
-                            make_uint4(packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
-                                       packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
-                                       packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
-                                       packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
+                        *reinterpret_cast<uint4*>(out + pix * kCO + s * 32 + c0 + 8 * i) =
+                            make_uint4(packbf_relu(__uint_as_float(q8[0]), __uint_as_float(q8[1])), packbf_relu(__uint_as_float(q8[2]), __uint_as_float(q8[3])),
+                                       packbf_relu(__uint_as_float(q8[4]), __uint_as_float(q8[5])), packbf_relu(__uint_as_float(q8[6]), __uint_as_float(q8[7])));
                     }
                 }
             }
