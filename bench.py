@@ -35,8 +35,8 @@ def parse_args():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('FSCNN_BENCH_PRECISION', 'bf16'), choices=['fp32', 'bf16'],
                     help='bf16 = tensor-core fast path (headline); fp32 = exactness path (also timed briefly as fp32_exact)')
-    ap.add_argument('--batch', type=int, default=37,
-                    help='images per GPU per step (37 x 16 coarsest-level tiles = 4 full waves of 148 persistent CTAs)')
+    ap.add_argument('--batch', type=int, default=111,
+                    help='images per GPU per step (111 x 16 coarsest-level tiles = 12 full waves of 148 persistent CTAs)')
     ap.add_argument('--micro-batch', type=int, default=0, help='0 = library default')
     ap.add_argument('--height', type=int, default=1024)
     ap.add_argument('--width', type=int, default=2048)

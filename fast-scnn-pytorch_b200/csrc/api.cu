@@ -129,15 +129,16 @@ struct fscnn_ctx {
     int esize() const { return prec == FSCNN_PREC_BF16 ? 2 : 4; }
     int eff_mb(int n, int h, int w) const {
         int mb = micro_batch;
-        if (mb <= 0) {   // default: about 64 Mpixel of input per micro-batch (32 images at 1024x2048): the small late
-                         // stages then launch several full waves and the per-launch gaps amortise (measured +12 % vs 8)
+        if (mb <= 0) {   // default: about 192 Mpixel of input per micro-batch (96 images at 1024x2048): the small late
+                         // stages then launch many full waves and the per-launch prologues / tails of the 19 persistent
+                         // kernels amortise (measured: 8 -> 32 images +12 %, 37 -> 111 images +5 %)
             long long px = (long long)h * w;
-            mb = (int)((64ll << 20) / (px > 0 ? px : 1));
+            mb = (int)((192ll << 20) / (px > 0 ? px : 1));
             if (mb < 1) mb = 1;
             if (mb > 128) mb = 128;
             // ... nudged (within +-25 %) to the count whose 8x16-pixel tiles at the coarsest level (/32: seven of the nine
             // bottlenecks + PPM, a handful of tiles per image) fill whole waves of persistent CTAs: 37 images at 1024x2048
-            // (16 tiles each = 4 x 148) instead of 32 (3.46 waves, the last one 46 % full)
+            // (16 tiles each = 4 x 148) and its multiples instead of 32 (3.46 waves, the last one 46 % full)
             if (n > mb * 3 / 4) {
                 const Dims d = make_dims(h, w);
                 const int sms = num_sms();

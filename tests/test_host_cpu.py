@@ -54,7 +54,7 @@ def test_native_manifest_matches_state_dict():
         native.check(lib.fscnn_workspace_bytes(ctx, 1, 1024, 2048, C.byref(nbytes)))
         assert 100e6 < nbytes.value < 400e6
         native.check(lib.fscnn_workspace_bytes(ctx, 1000, 1024, 2048, C.byref(nbytes)))   # capped by the micro-batch
-        assert nbytes.value < 40 * 400e6
+        assert nbytes.value < 128 * 400e6                                               # default micro-batch <= 128 images
         assert lib.fscnn_workspace_bytes(ctx, 1, 2, 2, C.byref(nbytes)) < 0
         assert b'bad shape' in lib.fscnn_last_error()
         tap = native.Tap()
