@@ -68,7 +68,7 @@ Dims make_dims(int h, int w) {
 
 // Workspace layout for a micro-batch of `mb` images: byte offsets of every stage tensor.
 struct WsPlan {
-    size_t stem, ds1, higher, b[9], ppm, rowsum, z, ffm, cls1, logits, aux_logits, total;
+    size_t stem, ds1, higher, b[9], ppm, rowsum, z, z16, ppm_r, ffm, cls1, logits, aux_logits, total;
 };
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -96,6 +96,7 @@ struct fscnn_ctx {
         size_t aux_w, aux_b, auxh_w, auxh_b;
         size_t bn_we_img[9], bn_wp_img[9], bn_tab_img[9];   // bf16 tcgen05 operand images + constant tables (offsets still in floats)
         size_t bn_weT_img[9], bn_wpT_img[9], bn_tabT_img[9]; // stride-1 layers: operands of the transposed-expand kernel
+        size_t ppm_wx_img;   // PPM out conv, x part + branch part as [128 x 128] operand images
         size_t ffm_tabT;   // FFM, transposed kernel: per-channel depthwise records + fused bias
         size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8, stem_imgx, stem_imgx_u8;
     } off{};
@@ -115,6 +116,8 @@ struct fscnn_ctx {
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
     const unsigned char* ffm_tabT = nullptr;
+    const bf16* ppm_wx_img = nullptr;
+    int ppm_tc = 1;          // bf16 PPM output stage on the tensor core (0 = ppm.cu's fp32 register-tile contraction)
     int ffm_transposed = 1;  // bf16 FFM: resize on the tensor core + depthwise out of TMEM (0 = ffm_tc.cu)
     const bf16* stem_img = nullptr;
     bf16* stem_img_u8 = nullptr;
@@ -173,6 +176,8 @@ struct fscnn_ctx {
         p.ppm = take((size_t)mb * d.h5 * d.w5 * 128 * es);
         p.rowsum = take((size_t)mb * d.h5 * 12 * 128 * 4);
         p.z = take((size_t)mb * 50 * 128 * 4);
+        p.z16 = take((size_t)mb * 128 * 64 * 2);
+        p.ppm_r = take((size_t)d.h5 * d.w5 * 64 * 2);
         p.ffm = take((size_t)mb * d.h3 * d.w3 * 128 * es);
         p.cls1 = take((size_t)mb * d.h3 * d.w3 * 128 * es);
         p.logits = take((size_t)mb * d.h3 * d.w3 * ncp * 4);
@@ -263,6 +268,7 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
         f.head_img = take((size_t)((c->nc + 15) & ~15) * 128 / 2);
         f.ffm_img = take((size_t)128 * 192 / 2);
         f.ffm_tabT = take((128 * 32 + 128 * 4) / 4);
+        f.ppm_wx_img = take((size_t)128 * 256 / 2);
         f.stem_img = take((size_t)32 * 32 / 2);
         f.stem_img_u8 = take((size_t)32 * 32 / 2);
         f.stem_b_u8 = take(32);
@@ -327,6 +333,8 @@ cudaError_t dsconv_dispatch(fscnn_ctx* c, int i, int cin, int cout, int stride, 
                             int m, int hi, int wi, int ho, int wo, cudaStream_t s);
 
 template <typename T>
+cudaError_t ppm_dispatch(fscnn_ctx* c, const T* in, float* rowsum, float* z, bf16* z16, bf16* r_img, T* out, int m, int h, int w, cudaStream_t s);
+template <typename T>
 cudaError_t ffm_dispatch(fscnn_ctx* c, const T* higher, const T* lower, T* out, int m, int hh, int wh, int hl, int wl, cudaStream_t s);
 
 template <typename T>
@@ -357,7 +365,8 @@ int run_stages(fscnn_ctx* c, const void* x, int m, const Dims& d, const WsPlan& 
             const int ho = i < 3 ? d.h4 : d.h5, wo = i < 3 ? d.w4 : d.w5;
             e = bottleneck_dispatch<T>(c, i, in, at(p.b[i]), m, hi, wi, ho, wo, s);
         } else if (st == kPpm) {
-            e = launch_ppm<T>(at(p.b[8]), c->ppm, atf(p.rowsum), atf(p.z), at(p.ppm), m, d.h5, d.w5, s);
+            e = ppm_dispatch<T>(c, at(p.b[8]), atf(p.rowsum), atf(p.z), reinterpret_cast<bf16*>(ws + p.z16), reinterpret_cast<bf16*>(ws + p.ppm_r),
+                                at(p.ppm), m, d.h5, d.w5, s);
             c->launches += 2;
         } else if (st == kFfm) {
             e = ffm_dispatch<T>(c, at(p.higher), at(p.ppm), at(p.ffm), m, d.h3, d.w3, d.h5, d.w5, s);
@@ -405,6 +414,15 @@ cudaError_t dsconv_dispatch<bf16>(fscnn_ctx* c, int i, int cin, int cout, int st
                             m, hi, wi, ho, wo, s);
 }
 
+template <>
+cudaError_t ppm_dispatch<float>(fscnn_ctx* c, const float* in, float* rowsum, float* z, bf16*, bf16*, float* out, int m, int h, int w, cudaStream_t s) {
+    return launch_ppm<float>(in, c->ppm, rowsum, z, out, m, h, w, s);
+}
+template <>
+cudaError_t ppm_dispatch<bf16>(fscnn_ctx* c, const bf16* in, float* rowsum, float* z, bf16* z16, bf16* r_img, bf16* out, int m, int h, int w, cudaStream_t s) {
+    if (c->ppm_tc) return launch_ppm_tc(in, c->ppm, c->ppm_wx_img, rowsum, z, z16, r_img, out, m, h, w, s);
+    return launch_ppm<bf16>(in, c->ppm, rowsum, z, out, m, h, w, s);
+}
 template <>
 cudaError_t ffm_dispatch<float>(fscnn_ctx* c, const float* higher, const float* lower, float* out, int m, int hh, int wh, int hl,
                                 int wl, cudaStream_t s) {
@@ -599,6 +617,11 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
     L.fold("global_feature_extractor.ppm.out.conv.0", false, "global_feature_extractor.ppm.out.conv.1", 128, 256, 1, 0,
            P + f.ppm_wo, 128, P + f.ppm_bo);
     c->ppm.wo_x = P + f.ppm_wo;
+    if (c->prec == FSCNN_PREC_BF16) {
+        bf16* img = reinterpret_cast<bf16*>(P + f.ppm_wx_img);
+        L.fold_umma("global_feature_extractor.ppm.out.conv.0", "global_feature_extractor.ppm.out.conv.1", 128, 256, 128, 128, img);
+        c->ppm_wx_img = img;   // chunk 0 = the 128 input channels of x (cat order: x first, :143)
+    }
     c->ppm.bo = P + f.ppm_bo;
     L.fold("feature_fusion.dwconv.conv.0", false, "feature_fusion.dwconv.conv.1", 128, 9, 1, 0, P + f.ffm_wd, 128, P + f.ffm_bd);
     L.round_dw(c, P + f.ffm_wd, 128);
@@ -662,6 +685,7 @@ int fscnn_set_option(fscnn_ctx* c, const char* key, int value) {
     if (!strcmp(key, "s1_transposed")) { c->s1_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "s2_transposed")) { c->s2_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "ffm_transposed")) { c->ffm_transposed = value ? 1 : 0; return FSCNN_OK; }
+    if (!strcmp(key, "ppm_tc")) { c->ppm_tc = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "micro_batch")) return fscnn_set_micro_batch(c, value);
     return fail(FSCNN_ENOENT, "unknown option '%s'", key);
 }

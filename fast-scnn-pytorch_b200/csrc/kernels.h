@@ -108,6 +108,12 @@ bool ffm_t_supported(int hh, int wh, int hl, int wl);
 cudaError_t launch_pack_dw_tab(const float* wd, const float* bd, const float* bout, int c, int cout, unsigned char* tab, cudaStream_t s);
 cudaError_t launch_ffm_t_tc(const bf16* higher, const bf16* lower, const unsigned char* tab, const bf16* wcat_img, bf16* out, int n,
                             int hh, int wh, int hl, int wl, cudaStream_t s);
+// bf16 PPM with the output stage on the tensor core (ppm_tc.cu): wx_img = launch_fold_umma(out conv, 128 rows, kdim 256,
+// nc 128, kc 128) chunk 0; z16: n x 16 KB, r_img: h x w x 64 bf16 (both workspace)
+cudaError_t launch_ppm_out_tc(const bf16* in, const bf16* wx_img, const bf16* z_img, const float* bias, bf16* r_img, bf16* out, int n,
+                              int h, int wd, cudaStream_t s);
+cudaError_t launch_ppm_tc(const bf16* in, const PpmW& w, const bf16* wx_img, float* rowsum, float* z, bf16* z16, bf16* r_img, bf16* out,
+                          int n, int h, int wd, cudaStream_t s);
 // wcat_img: the stacked [128 x 192] weight (64 higher | 128 lower input channels) as one chunk
 cudaError_t launch_ffm_tc(const bf16* higher, const bf16* lower, const FfmW& w, const bf16* wcat_img, bf16* out, int n, int hh,
                           int wh, int hl, int wl, cudaStream_t s);

@@ -38,11 +38,17 @@ __global__ void __launch_bounds__(kPpmC) ppm_rowsum_kernel(const T* __restrict__
     }
 }
 
+// z16 (bf16 path): the same vectors as a tcgen05 B-operand image per image, element (co, bin) at bf16 index
+// ((bin / 8) * 16 + co / 8) * 64 + (co % 8) * 8 + bin % 8, bins 50..63 zero (blockIdx.x runs to 64 then)
 __global__ void __launch_bounds__(kPpmC) ppm_branch_kernel(const float* __restrict__ rowsum, PpmW w, float* __restrict__ z,
-                                                            int h, int wd) {
+                                                            bf16* __restrict__ z16, int h, int wd) {
     __shared__ float mean[kPpmC];
     __shared__ float feat[32];
     const int bin = blockIdx.x, n = blockIdx.y, c = threadIdx.x;
+    if (bin >= kPpmBins) {   // zero padding of the operand image
+        z16[(size_t)n * kPpmC * 64 + ((size_t)(bin >> 3) * 16 + (c >> 3)) * 64 + (c & 7) * 8 + (bin & 7)] = __float2bfloat16_rn(0.f);
+        return;
+    }
     int si, s, local, colbase;
     if (bin < 1) { si = 0; s = 1; local = bin; colbase = 0; }
     else if (bin < 5) { si = 1; s = 2; local = bin - 1; colbase = 1; }
@@ -65,6 +71,7 @@ __global__ void __launch_bounds__(kPpmC) ppm_branch_kernel(const float* __restri
 #pragma unroll 8
     for (int j = 0; j < 32; ++j) o = fmaf(feat[j], __ldg(w.wo_s[si] + j * kPpmC + c), o);
     z[((size_t)n * kPpmBins + bin) * kPpmC + c] = o;
+    if (z16) z16[(size_t)n * kPpmC * 64 + ((size_t)(bin >> 3) * 16 + (c >> 3)) * 64 + (c & 7) * 8 + (bin & 7)] = __float2bfloat16_rn(o);
 }
 
 // bilinear align_corners sample of z_S (an SxS grid of 128-vectors) at output pixel (y, x), 4 channels
@@ -152,9 +159,17 @@ ppm_out_kernel(const T* __restrict__ in, PpmW w, const float* __restrict__ z, T*
 template <typename T>
 cudaError_t launch_ppm(const T* in, const PpmW& w, float* rowsum, float* z, T* out, int n, int h, int wd, cudaStream_t s) {
     ppm_rowsum_kernel<T><<<dim3(h, n), kPpmC, 0, s>>>(in, rowsum, h, wd);
-    ppm_branch_kernel<<<dim3(kPpmBins, n), kPpmC, 0, s>>>(rowsum, w, z, h, wd);
+    ppm_branch_kernel<<<dim3(kPpmBins, n), kPpmC, 0, s>>>(rowsum, w, z, nullptr, h, wd);
     ppm_out_kernel<T><<<dim3(ceil_div(h * wd, 128), n), kThreads, 0, s>>>(in, w, z, out, h, wd);
     return cudaGetLastError();
+}
+
+// bf16 path with the output stage on the tensor core (ppm_tc.cu)
+cudaError_t launch_ppm_tc(const bf16* in, const PpmW& w, const bf16* wx_img, float* rowsum, float* z, bf16* z16, bf16* r_img, bf16* out,
+                          int n, int h, int wd, cudaStream_t s) {
+    ppm_rowsum_kernel<bf16><<<dim3(h, n), kPpmC, 0, s>>>(in, rowsum, h, wd);
+    ppm_branch_kernel<<<dim3(64, n), kPpmC, 0, s>>>(rowsum, w, z, z16, h, wd);
+    return launch_ppm_out_tc(in, wx_img, z16, w.bo, r_img, out, n, h, wd, s);
 }
 
 template cudaError_t launch_ppm<float>(const float*, const PpmW&, float*, float*, float*, int, int, int, cudaStream_t);

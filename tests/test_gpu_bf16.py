@@ -127,13 +127,13 @@ def test_bf16_persistent_pipelines_many_tiles(shape, batch, nc):
     assert (m32 != full_mask).float().mean().item() < MASK_TOL
 
 
-GEN_OPTIONS = ('s1_transposed', 's2_transposed', 'ffm_transposed')
+GEN_OPTIONS = ('s1_transposed', 's2_transposed', 'ffm_transposed', 'ppm_tc')
 
 
 @pytest.mark.parametrize('case', ['fwd_nc19_aux_n2_65x97', 'fwd_nc3_aux_n3_64x40'])
 def test_bf16_both_kernel_generations_in_isolation(case):
-    """The bottlenecks and the FFM exist in two bf16 generations: the transposed-expand kernels (TMEM lane = channel,
-    depthwise in registers; default) and the shared-memory-tile kernels they replaced (fscnn_set_option(..., 0)).  Both
+    """The bottlenecks, the FFM and the PPM output stage exist in two bf16 generations: the transposed-expand / tensor-core
+    kernels (default) and the shared-memory-tile / register-tile kernels they replaced (fscnn_set_option(..., 0)).  Both
     must meet the stage tolerance against the reference fixtures, and they must agree with each other to bf16 precision."""
     g, sd, x, nc, aux = load_case(case)
     model = build_model(sd, nc, aux, DEV, precision='bf16')
@@ -141,7 +141,7 @@ def test_bf16_both_kernel_generations_in_isolation(case):
     eng = model._engine(DEV)
     n, _, h, w = x.shape
     names = eng.stage_names()
-    stages = [s for s in STAGE_IO if s[0].startswith('gfe.bottleneck') or s[0] == 'ffm']
+    stages = [s for s in STAGE_IO if s[0].startswith('gfe.bottleneck') or s[0] in ('ffm', 'gfe.ppm')]
     got = {}
     try:
         for gen in (1, 0):
