@@ -168,12 +168,14 @@ int fscnn_tap_info(const fscnn_ctx* ctx, int n, int h, int w, const char* tap, f
 /* Kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */
 int64_t fscnn_launch_count(const fscnn_ctx* ctx);
 
-/* Tuning: images pushed through the whole pipeline together (default: chosen from h*w so that a
- * micro-batch's stage tensors stay L2-resident).  0 restores the default. */
+/* Tuning: images pushed through the whole pipeline together (default: about 192 Mpixel of input, nudged to the count
+ * whose tiles at the coarsest level fill whole waves of persistent CTAs; at most 128).  0 restores the default. */
 int fscnn_set_micro_batch(fscnn_ctx* ctx, int images);
 
 /* Tuning / A-B switches: "fuse_front" (1 = stem + dsconv1 as one kernel in the bf16 path, default),
- * "micro_batch" (as fscnn_set_micro_batch). */
+ * "micro_batch" (as fscnn_set_micro_batch), and the bf16 kernel generations (1 = default, 0 = the kernels they replaced):
+ * "s1_transposed" / "s2_transposed" (LinearBottleneck, stride 1 / 2: transposed expand, depthwise out of TMEM),
+ * "ffm_transposed" (FeatureFusionModule: resize on the tensor core), "ppm_tc" (PyramidPooling output stage). */
 int fscnn_set_option(fscnn_ctx* ctx, const char* key, int value);
 
 #ifdef __cplusplus
