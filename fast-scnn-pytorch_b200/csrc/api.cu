@@ -117,6 +117,7 @@ struct fscnn_ctx {
     const bf16* ffm_img = nullptr;
     const unsigned char* ffm_tabT = nullptr;
     const bf16* ppm_wx_img = nullptr;
+    int front_transposed = 1;  // bf16 fused front kernel with the transposed stem (0 = l2d_front_tc.cu)
     int ppm_tc = 1;          // bf16 PPM output stage on the tensor core (0 = ppm.cu's fp32 register-tile contraction)
     int ffm_transposed = 1;  // bf16 FFM: resize on the tensor core + depthwise out of TMEM (0 = ffm_tc.cu)
     const bf16* stem_img = nullptr;
@@ -458,6 +459,11 @@ bool front_fused<bf16>(fscnn_ctx* c, const void* x, bf16* out_ds1, int m, const 
         c->in_dirty = false;
         c->launches += 2;
     }
+    if (c->front_transposed) {   // transposed stem (l2d_front_t_tc.cu); inputs without 16-byte aligned rows keep the previous kernel
+        *e = launch_l2d_front_t_tc(x, c->in, u8 ? c->stem_imgx_u8 : c->stem_imgx, c->ds[0], c->ds_wp_img[0], out_ds1, m, d.h, d.w, d.h1,
+                                   d.w1, d.h2, d.w2, s);
+        if (*e != cudaErrorNotSupported) return true;
+    }
     *e = launch_l2d_front_tc(x, c->in, u8 ? c->stem_imgx_u8 : c->stem_imgx, u8 ? c->stem_b_u8 : c->stem.b, c->ds[0], c->ds_wp_img[0],
                              out_ds1, m, d.h, d.w, d.h1, d.w1, d.h2, d.w2, s);
     return true;
@@ -686,6 +692,7 @@ int fscnn_set_option(fscnn_ctx* c, const char* key, int value) {
     if (!strcmp(key, "s2_transposed")) { c->s2_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "ffm_transposed")) { c->ffm_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "ppm_tc")) { c->ppm_tc = value ? 1 : 0; return FSCNN_OK; }
+    if (!strcmp(key, "front_transposed")) { c->front_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "micro_batch")) return fscnn_set_micro_batch(c, value);
     return fail(FSCNN_ENOENT, "unknown option '%s'", key);
 }

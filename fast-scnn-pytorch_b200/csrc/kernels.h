@@ -130,4 +130,8 @@ cudaError_t launch_stem_pack_rgbx(const float* w, const float* b, const StemIn& 
 cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_img, const float* bs, const DsW& w,
                                 const bf16* wp_img, bf16* out, int n, int h, int wd, int h1, int w1, int h2, int w2, cudaStream_t s);
 
+// the same with the transposed stem (l2d_front_t_tc.cu); cudaErrorNotSupported when the input rows are not 16-byte aligned
+cudaError_t launch_l2d_front_t_tc(const void* x, const StemIn& in, const bf16* ws_img, const DsW& w, const bf16* wp_img, bf16* out, int n,
+                                  int h, int wd, int h1, int w1, int h2, int w2, cudaStream_t s);
+
 }  // namespace fscnn
