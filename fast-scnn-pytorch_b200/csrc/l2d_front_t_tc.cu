@@ -157,32 +157,36 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
         const bool rp_on = tid < PC * 7;
         const int rp_c0 = rp_px <= 35 ? rp_px * 8 : -1;                               // sub-tile column 0: lc = px
         const int rp_c1 = rp_px >= 32 ? kSubP + (rp_px - 32) * 8 : -1;                // sub-tile column 1: lc = px - 32
-        const int rp_src = FMT == FSCNN_IN_U8_NHWC ? 10 + 3 * rp_px : (rp_px + 2) * 4;
+        const int rp_src = (FMT == FSCNN_IN_U8_NHWC ? 10 + 3 * rp_px : (rp_px + 2) * 4) + rp_ph * (FMT == FSCNN_IN_U8_NHWC ? kRW * 4 : PLD * 4);
+        int rp_r0[5], rp_r1[5];                           // plane-row offsets of this thread's 5 patch rows in sub-tile rows 0 / 1 (-1: not part)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int r = rp_ph + 7 * k;
+            rp_r0[k] = r <= 18 ? (r & 1) * kOdd + (r >> 1) * kPitch : -1;
+            rp_r1[k] = r >= 16 ? 2 * kSubP + (r & 1) * kOdd + ((r - 16) >> 1) * kPitch : -1;
+        }
         auto repack = [&](int lt) {
             if (rp_on) {
                 const uint8_t* patch = sm + oRaw + (lt & 1) * kRaw + rp_src;
                 const uint32_t pl = sPl + (lt & 1) * kPlanes;
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
-                    const int r = rp_ph + 7 * k;
                     float v0, v1, v2;
                     if (FMT == FSCNN_IN_U8_NHWC) {
-                        const unsigned char* qp = patch + r * (kRW * 4);
+                        const unsigned char* qp = patch + 7 * k * (kRW * 4);
                         v0 = (float)qp[0]; v1 = (float)qp[1]; v2 = (float)qp[2];
                     } else {
-                        const float* qp = reinterpret_cast<const float*>(patch + r * (PLD * 4));
+                        const float* qp = reinterpret_cast<const float*>(patch + 7 * k * (PLD * 4));
                         v0 = qp[0]; v1 = qp[PR * PLD]; v2 = qp[2 * PR * PLD];
                     }
                     const uint32_t lo = packbf(v0, v1), hi = packbf(v2, 1.f);   // X = 1: carries the bias through the MMA
-                    if (r <= 18) {                                                // sub-tile row 0: lr = r
-                        const uint32_t ro = pl + (r & 1) * kOdd + (r >> 1) * kPitch;
-                        if (rp_c0 >= 0) sts64(ro + rp_c0, lo, hi);
-                        if (rp_c1 >= 0) sts64(ro + rp_c1, lo, hi);
+                    if (rp_r0[k] >= 0) {
+                        if (rp_c0 >= 0) sts64(pl + rp_r0[k] + rp_c0, lo, hi);
+                        if (rp_c1 >= 0) sts64(pl + rp_r0[k] + rp_c1, lo, hi);
                     }
-                    if (r >= 16) {                                                // sub-tile row 1: lr = r - 16
-                        const uint32_t ro = pl + 2 * kSubP + (r & 1) * kOdd + ((r - 16) >> 1) * kPitch;
-                        if (rp_c0 >= 0) sts64(ro + rp_c0, lo, hi);
-                        if (rp_c1 >= 0) sts64(ro + rp_c1, lo, hi);
+                    if (rp_r1[k] >= 0) {
+                        if (rp_c0 >= 0) sts64(pl + rp_r1[k] + rp_c0, lo, hi);
+                        if (rp_c1 >= 0) sts64(pl + rp_r1[k] + rp_c1, lo, hi);
                     }
                 }
             }
@@ -190,9 +194,7 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_planes[lt & 1]);
         };
-        auto epilogue = [&](int lt) {                     // + bias, ReLU -> bf16 NHWC; slices s = 0..2 hold 16 of the 48 channels each
-            int n, oy0, ox0;
-            tile_origin(lt, n, oy0, ox0);
+        auto epilogue = [&](int lt, int n, int oy0, int ox0) {   // + bias, ReLU -> bf16 NHWC; slices s = 0..2 hold 16 of the 48 channels each
             const int oy = oy0 + 4 * (q >> 1) + (lane >> 3), ox = ox0 + 8 * (q & 1) + (lane & 7);   // accumulator row = sub-tile * 32 + row * 8 + column
             mbar_wait(&bar_proj[lt & 1], (lt >> 1) & 1);
             tc_fence_after_sync();
@@ -221,9 +223,10 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
         };
         mbar_wait(&bar_patch[0], 0);
         repack(0);
+        int n = 0, oy0 = 0, ox0 = 0, pn, poy0, pox0;
 #pragma unroll 1
         for (int t = 0; t < my_tiles; ++t) {
-            int n, oy0, ox0;
+            pn = n; poy0 = oy0; pox0 = ox0;
             tile_origin(t, n, oy0, ox0);
             if (t + 1 < my_tiles) {       // planes[(t+1)&1] are free: this warp saw the stem of tile t-1 complete one iteration ago
                 mbar_wait(&bar_patch[(t + 1) & 1], ((t + 1) >> 1) & 1);
@@ -282,9 +285,9 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             fence_async_proxy();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dready[t & 1]);
-            if (t >= 1) epilogue(t - 1);
+            if (t >= 1) epilogue(t - 1, pn, poy0, pox0);
         }
-        epilogue(my_tiles - 1);
+        epilogue(my_tiles - 1, n, oy0, ox0);
     }
     tc_fence_before_sync();
     __syncthreads();

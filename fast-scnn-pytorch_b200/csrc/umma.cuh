@@ -23,16 +23,22 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// try_wait parks the thread in hardware until the phase completes or the suspend-time hint (ns) expires; without a hint the
+// default limit is short and a waiting warp spins through SYNCS / YIELD / BRA (a quarter of all issued instructions of
+// the front kernel, ncu), competing with the compute warps of its scheduler
+#ifndef FSCNN_MBAR_HINT_NS
+#define FSCNN_MBAR_HINT_NS 100000
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(FSCNN_MBAR_HINT_NS)
         : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {

@@ -127,7 +127,7 @@ def test_bf16_persistent_pipelines_many_tiles(shape, batch, nc):
     assert (m32 != full_mask).float().mean().item() < MASK_TOL
 
 
-GEN_OPTIONS = ('s1_transposed', 's2_transposed', 'ffm_transposed', 'ppm_tc')
+GEN_OPTIONS = ('s1_transposed', 's2_transposed', 'ffm_transposed', 'ppm_tc', 'front_transposed')
 
 
 @pytest.mark.parametrize('case', ['fwd_nc19_aux_n2_65x97', 'fwd_nc3_aux_n3_64x40'])
@@ -155,11 +155,33 @@ def test_bf16_both_kernel_generations_in_isolation(case):
                 eng.forward_range(xd, idx, idx)
                 got[gen, stage] = eng.tap_view(out, n, h, w).permute(0, 3, 1, 2).float().cpu().numpy()
                 assert rel_err(got[gen, stage], g['tap/' + out]) < STAGE_TOL, (gen, stage)
+            # the fused front kernel (stem + dsconv1 in one launch) only runs when both stages are requested together
+            eng.forward_range(xd, names.index('stem'), names.index('l2d.dsconv1'))
+            got[gen, 'front'] = eng.tap_view('l2d.dsconv1', n, h, w).permute(0, 3, 1, 2).float().cpu().numpy()
+            assert rel_err(got[gen, 'front'], g['tap/l2d.dsconv1']) < STAGE_TOL, (gen, 'front')
     finally:
         for opt in GEN_OPTIONS:
             eng.set_option(opt, 1)
-    for stage, _, _ in stages:
+    for stage in [st[0] for st in stages] + ['front']:
         assert rel_err(got[1, stage], got[0, stage]) < STAGE_TOL, stage
+
+
+def test_bf16_front_kernel_input_formats():
+    """The transposed front kernel needs 16-byte aligned input rows (TMA); other widths fall back to the previous kernel.
+    Aligned and unaligned widths, float32 NCHW and uint8 HWC input: both kernel generations agree on the mask."""
+    nc = 3
+    sd = fo.make_state_dict(nc, False, 21)
+    for h, w in ((200, 336), (203, 333)):        # 336 * 3 bytes and 336 * 4 bytes are multiples of 16; 333 is not
+        model = build_model(sd, nc, False, DEV, precision='bf16')
+        eng = model._engine(DEV)
+        xf = torch.from_numpy(fo.make_input(3, h, w, 22)).to(DEV)
+        xu = torch.randint(0, 256, (3, h, w, 3), dtype=torch.uint8, device=DEV)
+        for x in (xf, xu):
+            new = model.predict(x)
+            eng.set_option('front_transposed', 0)
+            old = model.predict(x)
+            eng.set_option('front_transposed', 1)
+            assert (new != old).float().mean().item() < MASK_TOL
 
 
 def test_bf16_transposed_kernels_many_tiles():
