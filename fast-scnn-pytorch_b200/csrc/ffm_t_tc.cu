@@ -175,13 +175,14 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
         // =========================== compute warps ===========================
         const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter, row strip (output rows 2s, 2s+1) / 32-column slice
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        // one row of the interpolation matrix per thread (threads 0..179)
+        // one row of the interpolation matrix per thread: lanes 0..11 of every warp (16 x 12 = 192 >= 180 rows), so that no
+        // warp carries more of this than another
         auto build_r = [&](int lt) {
-            if (tid < kPIN) {
+            const int pin = warp * 12 + lane;
+            if (lane < 12 && pin < kPIN) {
                 int n, oy0, ox0, ry0, rx0;
                 tile_origin(lt, n, oy0, ox0);
                 patch_origin(oy0, ox0, ry0, rx0);
-                const int pin = tid;
                 const int y = oy0 - 1 + pin / kIW, x = ox0 - 1 + pin % kIW;
                 const uint32_t row = sR + (lt & 1) * R_BYTES + pin * 16;
 #pragma unroll
