@@ -207,8 +207,8 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
                     if (x1 != x0 && y1 != y0) put(jy1 * kPW + jx1, w11);
                 }
             }
-            fence_async_proxy();
-            __syncwarp();
+        };
+        auto publish_r = [&](int lt) {                    // after a fence.proxy.async of the writing threads
             if (lane == 0) mbar_arrive(&bar_r[lt & 1]);
         };
         auto epilogue = [&](int lt) {                     // ReLU -> bf16 NHWC (the bias is already in the accumulator)
@@ -248,6 +248,10 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
         const float bd = __uint_as_float(wb.y);
         build_r(0);
         if (my_tiles > 1) build_r(1);
+        fence_async_proxy();
+        __syncwarp();
+        publish_r(0);
+        if (my_tiles > 1) publish_r(1);
 #pragma unroll 1
         for (int t = 0; t < my_tiles; ++t) {
             mbar_wait(&bar_exp[t & 1], (t >> 1) & 1);            // resize(t) has completed
@@ -268,7 +272,6 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tmfree[t & 1]);      // resize(t+2) may overwrite this accumulator
-            if (t + 2 < my_tiles) build_r(t + 2);                // resize(t) has completed: R[t&1] may be rewritten
             float acc[2][16];
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr)
@@ -294,9 +297,11 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
                     sts128(d0 + (2 * o + hx) * D_SBO, packbf_relu(acc[o][8 * hx + 0], acc[o][8 * hx + 1]),
                            packbf_relu(acc[o][8 * hx + 2], acc[o][8 * hx + 3]), packbf_relu(acc[o][8 * hx + 4], acc[o][8 * hx + 5]),
                            packbf_relu(acc[o][8 * hx + 6], acc[o][8 * hx + 7]));
-            fence_async_proxy();
+            if (t + 2 < my_tiles) build_r(t + 2);                // resize(t) has completed: R[t&1] may be rewritten; needed two tiles from now
+            fence_async_proxy();                                 // one proxy fence (it costs a MEMBAR) for both the D and the R writes
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dready[t & 1]);
+            if (t + 2 < my_tiles) publish_r(t + 2);
             if (t >= 1) epilogue(t - 1);                         // deferred by one tile: fuse(t-1) ran during this tile's depthwise
         }
         epilogue(my_tiles - 1);
