@@ -190,9 +190,6 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
                     }
                 }
             }
-            fence_async_proxy();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_planes[lt & 1]);
         };
         auto epilogue = [&](int lt, int n, int oy0, int ox0) {   // + bias, ReLU -> bf16 NHWC; slices s = 0..2 hold 16 of the 48 channels each
             const int oy = oy0 + 4 * (q >> 1) + (lane >> 3), ox = ox0 + 8 * (q & 1) + (lane & 7);   // accumulator row = sub-tile * 32 + row * 8 + column
@@ -221,17 +218,19 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
                 }
             }
         };
+        // the planes are written TWO tiles ahead, next to the D stores, so that one proxy fence per tile covers both (the fence
+        // costs a MEMBAR that waits for the epilogue's global stores: it sits as far behind them as the loop allows)
         mbar_wait(&bar_patch[0], 0);
         repack(0);
+        if (my_tiles > 1) { mbar_wait(&bar_patch[1], 0); repack(1); }
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&bar_planes[0]); if (my_tiles > 1) mbar_arrive(&bar_planes[1]); }
         int n = 0, oy0 = 0, ox0 = 0, pn, poy0, pox0;
 #pragma unroll 1
         for (int t = 0; t < my_tiles; ++t) {
             pn = n; poy0 = oy0; pox0 = ox0;
             tile_origin(t, n, oy0, ox0);
-            if (t + 1 < my_tiles) {       // planes[(t+1)&1] are free: this warp saw the stem of tile t-1 complete one iteration ago
-                mbar_wait(&bar_patch[(t + 1) & 1], ((t + 1) >> 1) & 1);
-                repack(t + 1);
-            }
             mbar_wait(&bar_exp[t & 1], (t >> 1) & 1);            // stem(t) has completed
             tc_fence_after_sync();
             uint32_t Ep[3][9];                                   // stem rows 2s .. 2s+2, column pairs (2i, 2i+1), ReLU'd bf16
@@ -279,12 +278,16 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
                     for (int x = 0; x < 8; ++x)
                         acc[x] = fhfma_sel((ky | kx) ? acc[x] : bd, Ep[ky][(2 * x + kx) >> 1], (2 * x + kx) & 1, wq[(ky * 3 + kx) >> 1],
                                            (ky * 3 + kx) & 1);
+            if (t + 2 < my_tiles) {       // planes[t&1] are free (stem(t) has completed); the stem of tile t+2 runs during tile t+1
+                mbar_wait(&bar_patch[t & 1], ((t + 2) >> 1) & 1);
+                repack(t + 2);
+            }
             if (t >= 2) mbar_wait(&bar_proj[t & 1], ((t - 2) >> 1) & 1);   // pointwise(t-2) has completed: D[t&1] is free
             sts128(sD + (t & 1) * 8192 + (q * 4 + s) * 512 + (lane >> 3) * 128 + (lane & 7) * 16, packbf_relu(acc[0], acc[1]),
                    packbf_relu(acc[2], acc[3]), packbf_relu(acc[4], acc[5]), packbf_relu(acc[6], acc[7]));
             fence_async_proxy();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_dready[t & 1]);
+            if (lane == 0) { mbar_arrive(&bar_dready[t & 1]); if (t + 2 < my_tiles) mbar_arrive(&bar_planes[t & 1]); }
             if (t >= 1) epilogue(t - 1, pn, poy0, pox0);
         }
         epilogue(my_tiles - 1, n, oy0, ox0);
