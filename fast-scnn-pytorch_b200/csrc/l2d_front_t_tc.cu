@@ -226,11 +226,17 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
         fence_async_proxy();
         __syncwarp();
         if (lane == 0) { mbar_arrive(&bar_planes[0]); if (my_tiles > 1) mbar_arrive(&bar_planes[1]); }
-        int n = 0, oy0 = 0, ox0 = 0, pn, poy0, pox0;
+        // tile coordinates advance by gridDim.x tiles per iteration: decomposed once, then carried (no divisions in the loop)
+        const int step_x = gstep % tiles_x, step_y = (gstep / tiles_x) % tiles_y, step_n = gstep / (tiles_x * tiles_y);
+        int tx = (int)blockIdx.x % tiles_x, ty = ((int)blockIdx.x / tiles_x) % tiles_y, n = (int)blockIdx.x / (tiles_x * tiles_y);
+        int oy0 = 0, ox0 = 0, pn = 0, poy0 = 0, pox0 = 0, cn = 0;
 #pragma unroll 1
         for (int t = 0; t < my_tiles; ++t) {
-            pn = n; poy0 = oy0; pox0 = ox0;
-            tile_origin(t, n, oy0, ox0);
+            pn = cn; poy0 = oy0; pox0 = ox0;
+            cn = n; oy0 = ty * 8; ox0 = tx * 16;
+            tx += step_x; if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+            ty += step_y; if (ty >= tiles_y) { ty -= tiles_y; ++n; }
+            n += step_n;
             mbar_wait(&bar_exp[t & 1], (t >> 1) & 1);            // stem(t) has completed
             tc_fence_after_sync();
             uint32_t Ep[3][9];                                   // stem rows 2s .. 2s+2, column pairs (2i, 2i+1), ReLU'd bf16
@@ -290,7 +296,7 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             if (lane == 0) { mbar_arrive(&bar_dready[t & 1]); if (t + 2 < my_tiles) mbar_arrive(&bar_planes[t & 1]); }
             if (t >= 1) epilogue(t - 1, pn, poy0, pox0);
         }
-        epilogue(my_tiles - 1, n, oy0, ox0);
+        epilogue(my_tiles - 1, cn, oy0, ox0);
     }
     tc_fence_before_sync();
     __syncthreads();
