@@ -436,11 +436,22 @@ def run_native_arm(args):
                          'bytes': m['bytes'], 'flops': m['flops']})
             if name == 'up8+argmax+metric':
                 rows[-1]['us_per_image_no_pruning'] = tail_worst_us
+                # plan-P counts the low-res logits + a uint8 mask; this run is the fused-metric mode, which reads the
+                # caller's labels instead of writing a mask (int64 in the reference tensor layout): the bytes this launch must move
+                run_bytes = float(m['bytes'] - h * w * 1 + h * w * labels.element_size())
+                rows[-1]['bytes_fused_metric_mode'] = run_bytes
+                rows[-1]['gbs_fused_metric_mode'] = run_bytes / us / 1e3
             if 'fused_bytes' in m:
                 rows[-1]['fused_bytes'] = m['fused_bytes']
                 rows[-1]['fused_gbs'] = m['fused_bytes'] / us / 1e3
         out['stages'] = rows
-        top = max(rows, key=lambda r: r['us_per_image'])
+        top = dict(max(rows, key=lambda r: r['us_per_image']))
+        alu_note = ''
+        if 'bytes_fused_metric_mode' in top:   # the tail kernel: algorithmic bytes of the mode that was run (labels read, no mask written)
+            top['bytes'], top['gbs'] = top['bytes_fused_metric_mode'], top['gbs_fused_metric_mode']
+            alu_note = ('ALU-bound kernel (fp32 bilinear interpolation + compare / select of 19 classes x 2 Mpixel on the CUDA cores, exact '
+                        'class pruning); algorithmic bytes = low-res logits + the int64 labels the fused-metric mode reads (plan-P counts a '
+                        'uint8 mask instead: see stages[].bytes)')
         hbm_time = top['bytes'] / (peaks['hbm_gbs'] * 1e9)
         tens_time = top['flops'] / (peaks['bf16_tflops'] * 1e12)
         if args.precision == 'bf16' and tens_time > hbm_time:
@@ -459,7 +470,7 @@ def run_native_arm(args):
                      'peak_source': peaks['source'], 'images_per_launch': mb,
                      'us_per_launch': top['us_per_image'] * mb,
                      'note': 'fp32 path: this kernel is FP32-FMA bound on CUDA cores; fma_frac = achieved fp32 TFLOP/s / '
-                             '(148 SM x 128 lanes x 2 x sm_mhz)' if args.precision == 'fp32' else ''})
+                             '(148 SM x 128 lanes x 2 x sm_mhz)' if args.precision == 'fp32' else alu_note})
         if args.precision == 'fp32':
             mhz = (clocks or {}).get('sm_mhz') or peaks['sm_max_mhz']
             roof['fma_frac'] = top['tflops'] / (148 * 128 * 2 * mhz * 1e6 / 1e12)
