@@ -422,6 +422,20 @@ def run_native_arm(args):
         torch.cuda.synchronize()
         tail_worst_us = max(a.elapsed_time(b) / reps / mb * 1e3 - stage_sum, 0.0)
         del worst
+        # ... and on the labels: the histogram aggregates runs of equal (label, prediction) pairs before its shared-memory
+        # atomics; uniform-random labels (the timed workload) are its worst case, a single dominant class its best
+        dom = torch.zeros_like(labels[:mb])
+        dom[:, ::16, ::16] = -1
+        for timed in (False, True):
+            if timed:
+                a.record()
+            for _ in range(reps):
+                model.evaluate(xs, dom, metric, mask=None)
+            if timed:
+                b.record()
+        torch.cuda.synchronize()
+        tail_dom_us = max(a.elapsed_time(b) / reps / mb * 1e3 - stage_sum, 0.0)
+        del dom
         model_by_name = {s['stage']: s for s in stages}
         if fused_front:   # plan-P bytes of both stages (the denominator is not changed); the fused kernel's own traffic beside it
             a_, b_ = model_by_name['stem'], model_by_name['l2d.dsconv1']
@@ -436,6 +450,7 @@ def run_native_arm(args):
                          'bytes': m['bytes'], 'flops': m['flops']})
             if name == 'up8+argmax+metric':
                 rows[-1]['us_per_image_no_pruning'] = tail_worst_us
+                rows[-1]['us_per_image_dominant_class_labels'] = tail_dom_us
                 # plan-P counts the low-res logits + a uint8 mask; this run is the fused-metric mode, which reads the
                 # caller's labels instead of writing a mask (int64 in the reference tensor layout): the bytes this launch must move
                 run_bytes = float(m['bytes'] - h * w * 1 + h * w * labels.element_size())
