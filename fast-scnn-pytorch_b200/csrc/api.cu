@@ -838,6 +838,29 @@ int fscnn_colorize(const void* d_mask, int mask_dtype, int64_t n_pixels, const u
     return FSCNN_OK;
 }
 
+int fscnn_e2e_preprocess(const void* d_frames, int frame_dtype, int n, int h, int w, int base_size, const float* h_mean3,
+                         const float* h_std3, float* d_out, void* stream) {
+    if (!d_frames || !d_out) return fail(FSCNN_EINVAL, "null device pointer");
+    if (frame_dtype != FSCNN_U8 && frame_dtype != FSCNN_F32) return fail(FSCNN_EINVAL, "frames must be uint8 or float32, got dtype %d", frame_dtype);
+    if ((h_mean3 == nullptr) != (h_std3 == nullptr)) return fail(FSCNN_EINVAL, "mean and std go together");
+    if (n < 1 || h < 1 || w < 1 || base_size < 1) return fail(FSCNN_EINVAL, "bad shape n=%d h=%d w=%d base=%d", n, h, w, base_size);
+    cudaError_t e = launch_e2e_preprocess(d_frames, frame_dtype == FSCNN_U8, n, h, w, base_size, h_mean3, h_std3, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "e2e preprocess launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_e2e_postprocess(const float* d_low_logits, int num_classes, int padded_classes, int n, int hl, int wl, int base_h, int base_w,
+                          int out_h, int out_w, int apply_softmax, float* d_out, void* stream) {
+    if (!d_low_logits || !d_out) return fail(FSCNN_EINVAL, "null device pointer");
+    if (num_classes < 1 || num_classes > 32 || padded_classes < num_classes)
+        return fail(FSCNN_EINVAL, "e2e postprocess supports 1..32 classes (got %d, padded %d)", num_classes, padded_classes);
+    if (n < 1 || hl < 1 || wl < 1 || base_h < 1 || base_w < 1 || out_h < 1 || out_w < 1) return fail(FSCNN_EINVAL, "bad shape");
+    cudaError_t e = launch_e2e_postprocess(d_low_logits, num_classes, padded_classes, n, hl, wl, base_h, base_w, out_h, out_w, apply_softmax,
+                                           d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "e2e postprocess launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
 int fscnn_conf_to_totals(const long long* h_conf, int nc, long long* h_inter, long long* h_union, long long* h_correct,
                          long long* h_label) {
     if (!h_conf || !h_inter || !h_union || !h_correct || !h_label || nc < 1) return fail(FSCNN_EINVAL, "bad argument");

@@ -58,6 +58,12 @@ cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int 
 cudaError_t launch_confusion(const void* pred, int pred_dtype, const void* label, int label_dtype, long long npix, int nc,
                              unsigned long long* conf, cudaStream_t s);
 
+// camera-frame wrapper (e2e.cu): preprocess frames -> network input; low-res logits -> frame-size probabilities / logits
+cudaError_t launch_e2e_preprocess(const void* x, int is_u8, int n, int h, int w, int base, const float* mean3, const float* std3,
+                                  float* out, cudaStream_t s);
+cudaError_t launch_e2e_postprocess(const float* low, int nc, int ncp, int n, int hl, int wl, int bh, int bw, int oh, int ow,
+                                   int apply_softmax, float* out, cudaStream_t s);
+
 // rgb[p] = palette[mask[p] & 255]; palette768 is HOST memory (256 x RGB), passed to the kernel by value
 cudaError_t launch_colorize(const void* mask, int dtype, long long npix, const unsigned char* palette768, unsigned char* rgb,
                             cudaStream_t s);

@@ -173,6 +173,41 @@ class Engine:
         flat = ws[tap.offset_bytes: tap.offset_bytes + count * tap.elem_bytes].view(dtype)
         return flat.view(tap.n, tap.h, tap.w, tap.c_stride)[..., :tap.c]
 
+    # ---- camera-frame wrapper (reference export_onnx_fixed.py:34-98) ---------------------
+    def e2e_preprocess(self, frames: torch.Tensor, base_size: int, mean=None, std=None) -> torch.Tensor:
+        """frames [N,3,h,w] uint8 / float32 (0..255) -> float32 [N,3,base,base]: resize (align_corners=False), /255, normalise."""
+        if frames.dim() != 4 or frames.shape[1] != 3 or frames.dtype not in (torch.uint8, torch.float32):
+            raise ValueError(f'expected uint8 or float32 frames [N,3,H,W], got {frames.dtype} {tuple(frames.shape)}')
+        frames = frames.contiguous()
+        n, _, h, w = frames.shape
+        out = torch.empty((n, 3, base_size, base_size), dtype=torch.float32, device=frames.device)
+        m = (C.c_float * 3)(*[float(v) for v in mean]) if mean is not None else None
+        sd = (C.c_float * 3)(*[float(v) for v in std]) if std is not None else None
+        with torch.cuda.device(frames.device):
+            native.check(self.lib.fscnn_e2e_preprocess(frames.data_ptr(), native.U8 if frames.dtype == torch.uint8 else native.F32, n, h, w,
+                                                       base_size, m, sd, out.data_ptr(), _stream_ptr()), 'fscnn_e2e_preprocess')
+        return out
+
+    def e2e_forward(self, x: torch.Tensor, out_h: int, out_w: int, apply_softmax: bool, chunk: int = 32) -> torch.Tensor:
+        """network on x [N,3,H,W] float32 up to its low-resolution logits, then the fused x8 upsample + resize to (out_h, out_w)
+        (+ softmax): float32 [N,nc,out_h,out_w].  The full-resolution logits are never materialised."""
+        n, h, w = self._check_input(x, None)
+        names = self.stage_names()
+        last = names.index('cls.dsconv2+head')
+        out = torch.empty((n, self.num_classes, out_h, out_w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            for i0 in range(0, n, chunk):
+                xs = x[i0:i0 + chunk]
+                m = xs.shape[0]
+                self.forward_range(xs, 0, last)
+                tap = native.Tap()
+                native.check(self.lib.fscnn_tap_info(self._ctx, m, h, w, b'cls.logits_lowres', C.byref(tap)), 'fscnn_tap_info')
+                ws = self._workspace(m, h, w)
+                native.check(self.lib.fscnn_e2e_postprocess(ws.data_ptr() + tap.offset_bytes, self.num_classes, tap.c_stride, m, tap.h, tap.w,
+                                                            h, w, out_h, out_w, int(bool(apply_softmax)), out[i0:i0 + m].data_ptr(),
+                                                            _stream_ptr()), 'fscnn_e2e_postprocess')
+        return out
+
     def launch_count(self) -> int:
         return int(self.lib.fscnn_launch_count(self._ctx))
 

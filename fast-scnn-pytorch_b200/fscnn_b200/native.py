@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = 'libfscnn_b200.so'
 
 PREC_FP32, PREC_BF16 = 0, 1
-U8, I32, I64 = 0, 1, 2
+U8, I32, I64, F32 = 0, 1, 2, 3
 IN_F32_NCHW, IN_U8_NHWC = 0, 1
 
 
@@ -55,6 +55,10 @@ _SIGNATURES = {
     'fscnn_confusion_from_mask': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                             C.c_void_p]),
     'fscnn_colorize': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_void_p, C.c_void_p]),
+    'fscnn_e2e_preprocess': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.c_void_p, C.c_void_p]),
+    'fscnn_e2e_postprocess': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p]),
     'fscnn_conf_to_totals': (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong),
                                        C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     'fscnn_stage_count': (C.c_int, [C.c_void_p]),

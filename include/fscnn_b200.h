@@ -48,6 +48,7 @@ extern "C" {
 #define FSCNN_U8 0
 #define FSCNN_I32 1
 #define FSCNN_I64 2
+#define FSCNN_F32 3   /* float32 frames (fscnn_e2e_preprocess only) */
 
 /* layout of the image batch handed to the forward calls */
 #define FSCNN_IN_F32_NCHW 0  /* float32 [n,3,h,w], already normalised: what the reference's transforms produce */
@@ -147,6 +148,20 @@ int fscnn_conf_to_totals(const long long* h_conf, int num_classes, long long* h_
  * 256 x (R,G,B); d_rgb is [n_pixels][3] uint8. */
 int fscnn_colorize(const void* d_mask, int mask_dtype, int64_t n_pixels, const unsigned char* h_palette768,
                    unsigned char* d_rgb, void* stream);
+
+/* The camera-frame wrapper around the path: replaces EndToEndPreprocessing.forward and the tail of
+ * EndToEndFastSCNN.forward (export_onnx_fixed.py:43-60, :78-98).
+ *  preprocess : d_frames [n][3][h][w] uint8 (FSCNN_U8) or float32 (FSCNN_F32), values 0..255 -> bilinear resize
+ *               (align_corners=False) to base_size x base_size, / 255, optional (x - mean) / std (HOST float[3] each, both or
+ *               neither) -> d_out [n][3][base][base] float32, the input of fscnn_forward_*.
+ *  postprocess: the low-resolution logits of the network ([n][hl][wl][padded_classes] float32, the "cls.logits_lowres" tap)
+ *               -> x8 align_corners=True upsample to base_h x base_w (models/fast_scnn.py:40) composed with the resize to
+ *               out_h x out_w (align_corners=False) and, if apply_softmax, the softmax over the classes
+ *               -> d_out [n][num_classes][out_h][out_w] float32.  num_classes <= 32. */
+int fscnn_e2e_preprocess(const void* d_frames, int frame_dtype, int n, int h, int w, int base_size, const float* h_mean3,
+                         const float* h_std3, float* d_out, void* stream);
+int fscnn_e2e_postprocess(const float* d_low_logits, int num_classes, int padded_classes, int n, int hl, int wl, int base_h,
+                          int base_w, int out_h, int out_w, int apply_softmax, float* d_out, void* stream);
 
 /* ---- test / profiling hooks ---------------------------------------------------------- */
 
