@@ -569,6 +569,23 @@ def run_native_arm(args):
             extra.append({'workload': f'eval_nc{enc}_{eh}x{ew}_fwd_argmax_metric', 'batch': eb, 'value': eb * 10 / (a.elapsed_time(b) / 1e3),
                           'unit': UNIT, 'n_gpus': 1, 'precision': args.precision})
             del em, ex, el, emet
+        # the deployed camera pipeline (reference export_onnx_fixed.EndToEndFastSCNN): 640x360 uint8 frames -> 1024x1024
+        # -> 2-class network -> probabilities at 640x360, frames resident in HBM
+        from models.end_to_end import EndToEndFastSCNN
+        cam = EndToEndFastSCNN(FastSCNN(2, precision=args.precision).eval().to(dev), input_size=(640, 360), base_size=1024).eval()
+        frames = torch.randint(0, 256, (64, 3, 360, 640), dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            cam(frames)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            cam(frames)
+        b.record()
+        torch.cuda.synchronize()
+        extra.append({'workload': 'camera_frames_640x360_via_1024x1024_softmax_nc2', 'batch': 64, 'value': 64 * 5 / (a.elapsed_time(b) / 1e3),
+                      'unit': 'frames/s', 'n_gpus': 1, 'precision': args.precision})
+        del cam, frames
         out['other_workloads'] = extra
 
     if world == 1 and not args.no_cpu_baseline:
