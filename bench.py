@@ -211,6 +211,17 @@ def run_native_arm(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = None
+    try:   # multi-GPU boxes: run this rank (and first-touch its pinned host buffers) on the CPUs closest to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip().isdigit()]
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(int(vis[local]) if local < len(vis) else local)
+        pynvml.nvmlDeviceSetCpuAffinity(hnd)
+        numa = sorted(os.sched_getaffinity(0))
+        numa = f'{len(numa)} cpus ({numa[0]}-{numa[-1]})'
+    except Exception:   # no NVML / no permission: keep the inherited affinity
+        numa = None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     h, w, nc, B = args.height, args.width, args.classes, args.batch
@@ -339,7 +350,7 @@ def run_native_arm(args):
         'config': {'workload': f'cityscapes_eval_nc{nc}_{h}x{w}_fwd_argmax_metric', 'batch_per_gpu': B,
                    'global_batch': B * world, 'precision': args.precision, 'l2_policy': 'inputs_exceed_l2',
                    'input_bytes_per_step_per_gpu': int(x.numel() * 4 + labels.numel() * 8),
-                   'parallelism': f'dp{world}', 'weights': 'random-init, randomised BN stats'},
+                   'parallelism': f'dp{world}', 'cpu_affinity': numa, 'weights': 'random-init, randomised BN stats'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps, 'api': 'fscnn_b200.StreamingEvaluator.submit',
                 'host_buffers': 'pinned uint8 HWC images (ToTensor+Normalize fused into the stem) + uint8 labels; '
