@@ -321,7 +321,13 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
             if (active) {
                 // zero padding of the depthwise conv: halo columns / rows outside the image (border tiles only)
                 const int ix0 = ox0 - 1, iy0 = oy0 - 1 + 2 * s;
-                if (ix0 < 0 || ix0 + IW > W) {
+                if (ix0 == -1 && ix0 + IW <= W) {               // left image border: only halo column 0 is outside
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) Ep[rr][0] &= 0xFFFF0000u;
+                } else if (ix0 >= 0 && ix0 + IW == W + 1 && (IW & 1) == 0) {   // right border, width a multiple of the tile: only the last column
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) Ep[rr][IW / 2 - 1] &= 0x0000FFFFu;
+                } else if (ix0 < 0 || ix0 + IW > W) {           // anything else (odd sizes): per-column masks
 #pragma unroll
                     for (int i = 0; i < 9; ++i) {
                         const int xa = ix0 + 2 * i, xb2 = xa + 1;

@@ -249,7 +249,13 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
                 if (lane == 0) mbar_arrive(&bar_tmfree[u & 1]);  // expand(u+2) may overwrite this accumulator
                 // zero padding of the depthwise conv: halo columns / rows outside the image (border tiles only)
                 const int ix0 = 2 * (ox0 + C::SW * (sub & 1)) - 1, iy0 = 2 * (oy0 + C::SH * (sub >> 1)) - 1 + 2 * s;
-                if (ix0 < 0 || ix0 + IW > Wi) {
+                if (ix0 == -1 && ix0 + IW <= Wi) {               // left image border: only halo column 0 is outside
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) Ep[rr][0] &= 0xFFFF0000u;
+                } else if (ix0 >= 0 && ix0 + IW == Wi + 1 && (IW & 1) == 0) {   // right border, width a multiple of the tile: only the last column
+#pragma unroll
+                    for (int rr = 0; rr < 3; ++rr) Ep[rr][IW / 2 - 1] &= 0x0000FFFFu;
+                } else if (ix0 < 0 || ix0 + IW > Wi) {           // anything else (odd sizes): per-column masks
 #pragma unroll
                     for (int i = 0; i < 9; ++i) {
                         const int xa = ix0 + 2 * i, xb2 = xa + 1;
