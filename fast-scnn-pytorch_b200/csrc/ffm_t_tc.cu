@@ -175,11 +175,11 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
         // =========================== compute warps ===========================
         const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter, row strip (output rows 2s, 2s+1) / 32-column slice
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        // one row of the interpolation matrix per thread: lanes 0..11 of every warp (16 x 12 = 192 >= 180 rows), so that no
-        // warp carries more of this than another
+        // one row of the interpolation matrix per thread: lanes 0..22 of warps 0..7 (8 x 23 = 184 >= 180 rows): two builder warps
+        // per scheduler, and half the warp-level instructions of spreading 12 lanes over all 16 warps
         auto build_r = [&](int lt) {
-            const int pin = warp * 12 + lane;
-            if (lane < 12 && pin < kPIN) {
+            const int pin = warp * 23 + lane;
+            if (warp < 8 && lane < 23 && pin < kPIN) {
                 int n, oy0, ox0, ry0, rx0;
                 tile_origin(lt, n, oy0, ox0);
                 patch_origin(oy0, ox0, ry0, rx0);
