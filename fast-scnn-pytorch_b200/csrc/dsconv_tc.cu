@@ -42,7 +42,9 @@ struct DsTcCfg {
     static constexpr int oWd = oB + B_BYTES;             // bf16 [9][CIN]
     static constexpr int oBd = oWd + round_up(9 * CIN * 2, 16);
     static constexpr int oBp = oBd + CIN * 4;
-    static constexpr int oB2 = round_up(oBp + COUT * 4, 128);   // HEAD: head weight image (ncp16 x COUT), sized at run time;
+    static constexpr int oBias = round_up(oBp + COUT * 4, 128);  // B block [2 k-blocks][COUT][8]: {bias head, remainder, 0 x 6} | zeros
+    static constexpr int oOnes = oBias + 2 * COUT * 16;          // A block: rows {1, 1, 0 x 6} + zeros, re-read by every row group (SBO = 0)
+    static constexpr int oB2 = oOnes + 256;                      // HEAD: head weight image (ncp16 x COUT), sized at run time;
                                                                  // else: per-warp output staging (16 x 32 pixels x CP channels)
     static constexpr int STAGE_BYTES = HEAD ? 0 : 16 * 32 * (COUT / ((COUT % 32 == 0) ? 4 : COUT / 16)) * 2;
     static constexpr int NPART = (COUT % 32 == 0) ? 4 : COUT / 16;   // epilogue column parts (16 warps = 4 quarters x 4 parts)
@@ -89,6 +91,16 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
         reinterpret_cast<uint32_t*>(sm + C::oWd)[i] = packbf(__ldg(w.wd + 2 * i), __ldg(w.wd + 2 * i + 1));
     for (int i = tid; i < CIN; i += kDsNTall) Bds[i] = __ldg(w.bd + i);
     for (int i = tid; i < COUT; i += kDsNTall) Bps[i] = __ldg(w.bp + i);
+    // the pointwise bias rides through the tensor core: OUT = ones[128 x 16] * biasblock^T + A * W^T (bf16 head + remainder)
+    for (int i = tid; i < COUT; i += kDsNTall) {
+        const float b = __ldg(w.bp + i);
+        const __nv_bfloat16 bh = __float2bfloat16_rn(b), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+        const uint32_t w0 = (uint32_t)(*reinterpret_cast<const uint16_t*>(&bh)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&bl)) << 16);
+        *reinterpret_cast<uint4*>(sm + C::oBias + i * 16) = make_uint4(w0, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sm + C::oBias + COUT * 16 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid < 16) *reinterpret_cast<uint4*>(sm + C::oOnes + tid * 16) = make_uint4(tid < 8 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    fence_async_proxy();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -125,10 +137,12 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
             for (int lt = 0; lt < my_tiles; ++lt) {
                 mbar_wait(&bar_a[lt & 1], (lt >> 1) & 1);        // depthwise(lt) written (writers fenced the async proxy); halo[lt&1] is dead
                 tc_fence_after_sync();
+                umma_bf16_ss(tmem + (lt & 1) * COUT, make_smem_desc(smem_u32(sm + C::oOnes), 128, 0),
+                             make_smem_desc(smem_u32(sm + C::oBias), COUT * 16, 128), idesc, 0);   // bias
 #pragma unroll
                 for (int k16 = 0; k16 < CIN / 16; ++k16)
                     umma_bf16_ss(tmem + (lt & 1) * COUT, make_smem_desc(sA + (lt & 1) * C::A_BYTES + k16 * 4096, 2048, 128),
-                                 make_smem_desc(sB + k16 * 2 * (COUT * 16), COUT * 16, 128), idesc, k16 > 0);
+                                 make_smem_desc(sB + k16 * 2 * (COUT * 16), COUT * 16, 128), idesc, 1);
                 umma_commit(&bar_mma[lt & 1]);
                 if (lt + 2 < my_tiles) load_halo(lt + 2);
                 if (HEAD && lt >= 1) issue_head(lt - 1);
@@ -159,13 +173,11 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
 #pragma unroll
                 for (int c0 = 0; c0 < CP; c0 += 8) {
                     const int co = part * CP + c0;
-                    const float4 ba = *reinterpret_cast<const float4*>(Bps + co);
-                    const float4 bb = *reinterpret_cast<const float4*>(Bps + co + 4);
-                    const uint32_t* q8 = r + c0;
-                    const uint32_t a = packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y);
-                    const uint32_t b = packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w);
-                    const uint32_t c = packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y);
-                    const uint32_t d = packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w);
+                    const uint32_t* q8 = r + c0;      // the bias is already in the accumulator
+                    const uint32_t a = packbf_relu(__uint_as_float(q8[0]), __uint_as_float(q8[1]));
+                    const uint32_t b = packbf_relu(__uint_as_float(q8[2]), __uint_as_float(q8[3]));
+                    const uint32_t c = packbf_relu(__uint_as_float(q8[4]), __uint_as_float(q8[5]));
+                    const uint32_t d = packbf_relu(__uint_as_float(q8[6]), __uint_as_float(q8[7]));
                     if (!HEAD) {
                         const int sw = NCK8 == 4 ? (lane >> 1) & 3 : (lane >> 2) & 1;
                         sts128(slab + lane * (CP * 2) + (((c0 >> 3) ^ sw) << 4), a, b, c, d);
