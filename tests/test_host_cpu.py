@@ -119,3 +119,30 @@ def test_palette_output_matches_reference_tables():
     voc = palette_for('tusimple')
     assert tuple(voc[0]) == (0, 0, 0) and tuple(voc[1]) == (128, 0, 0) and tuple(voc[2]) == (0, 128, 0) and tuple(voc[15]) == (192, 128, 128)
     assert tuple(np.asarray(get_color_pallete(np.array([[1, 2]]), 'tusimple').convert('RGB'))[0, 1]) == (0, 128, 0)
+
+
+def test_kernel_generation_options_and_e2e_argument_checks():
+    """No GPU needed: the option keys of the bf16 kernel generations exist, unknown keys are refused, and the camera-frame
+    entry points validate their arguments before touching the device."""
+    from fscnn_b200 import native
+    lib = native.lib()
+    ctx = C.c_void_p()
+    native.check(lib.fscnn_create(C.byref(ctx), 19, 0, native.PREC_BF16))
+    try:
+        for key in (b's1_transposed', b's2_transposed', b'ffm_transposed', b'ppm_tc', b'front_transposed', b'fuse_front'):
+            for v in (0, 1):
+                assert lib.fscnn_set_option(ctx, key, v) == 0, key
+        assert lib.fscnn_set_option(ctx, b'no_such_option', 1) < 0
+        assert b'no_such_option' in lib.fscnn_last_error()
+        nbytes = C.c_size_t()
+        native.check(lib.fscnn_workspace_bytes(ctx, 111, 1024, 2048, C.byref(nbytes)))   # one wave-exact micro-batch, bf16
+        assert 111 * 60e6 < nbytes.value < 111 * 120e6
+    finally:
+        lib.fscnn_destroy(ctx)
+    assert lib.fscnn_e2e_preprocess(None, native.U8, 1, 8, 8, 16, None, None, None, None) < 0
+    dummy = C.c_void_p(16)
+    assert lib.fscnn_e2e_preprocess(dummy, native.I64, 1, 8, 8, 16, None, None, dummy, None) < 0          # frames are uint8 / float32
+    mean = (C.c_float * 3)(0.5, 0.5, 0.5)
+    assert lib.fscnn_e2e_preprocess(dummy, native.U8, 1, 8, 8, 16, mean, None, dummy, None) < 0            # mean without std
+    assert lib.fscnn_e2e_postprocess(dummy, 33, 36, 1, 4, 4, 32, 32, 8, 8, 1, dummy, None) < 0             # more than 32 classes
+    assert lib.fscnn_e2e_postprocess(dummy, 4, 2, 1, 4, 4, 32, 32, 8, 8, 1, dummy, None) < 0               # padded < classes
