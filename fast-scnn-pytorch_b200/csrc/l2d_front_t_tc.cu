@@ -29,7 +29,7 @@
 namespace fscnn {
 
 namespace {
-constexpr int kCW = 16, kCT = kCW * 32, kFTThreads = (kCW + 2) * 32;
+constexpr int kCW = 16, kFTThreads = (kCW + 2) * 32;
 constexpr int PR = 35, PC = 67;                        // input patch rows / columns the tile needs
 constexpr int PLD = 72, kRW = 56;                      // raw patch: fp32 planes of pitch 72 (needed columns start at +2), uint8 rows of 56 words
 constexpr int kRaw = 30720;                            // one raw patch buffer (fp32: 3 x 35 x 72 x 4 = 30240 B)
@@ -40,7 +40,9 @@ constexpr int kPlanes = 4 * kSubP + 512;               // + slack: the N padding
 constexpr int NB = 176;                                // MMA N: 9 x 18 = 162 stem pixels, padded
 constexpr int kZ = 2 * 224 * 16;                       // A buffer of one kernel row: 2 K blocks x 224 rows x 16 B
 constexpr int oRaw = 0, oPl = 2 * kRaw, oZ = oPl + 2 * kPlanes, oD = oZ + 3 * kZ, oWp = oD + 2 * 8192, oBp = oWp + 3072;
-constexpr int kSmemFT = oBp + 256;
+constexpr int oPB = oBp + 256;                         // pointwise bias as a B block [2 k-blocks][48][8]: {head, remainder, 0 x 6} | zeros
+constexpr int oOne = oPB + 2 * 48 * 16;                // MN-major A block of ones: k = 0, 1 rows of eight 1.0, rest zero; re-read by every pixel block
+constexpr int kSmemFT = oOne + 256;
 constexpr int TM_PW = 2 * NB;                          // stem accumulators 2 x 176 columns, pointwise accumulator 48
 static_assert(kSmemFT <= 227 * 1024 - 256, "shared memory");
 }  // namespace
@@ -82,7 +84,15 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             __ldg(reinterpret_cast<const uint4*>(ws_img + ky * 512 + (kb * 4 + (n >> 3)) * 64 + (n & 7) * 8));
     }
     if (tid < 192) reinterpret_cast<uint4*>(sm + oWp)[tid] = __ldg(reinterpret_cast<const uint4*>(wp_img) + tid);
-    if (tid < 48) Bps[tid] = __ldg(w.bp + tid);
+    if (tid < 48) {   // the pointwise bias rides through the tensor core (bf16 head + remainder against a block of ones)
+        const float b = __ldg(w.bp + tid);
+        Bps[tid] = b;
+        const __nv_bfloat16 bh = __float2bfloat16_rn(b), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+        const uint32_t w0 = (uint32_t)(*reinterpret_cast<const uint16_t*>(&bh)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&bl)) << 16);
+        *reinterpret_cast<uint4*>(sm + oPB + tid * 16) = make_uint4(w0, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sm + oPB + 48 * 16 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid >= 64 && tid < 80) *reinterpret_cast<uint4*>(sm + oOne + (tid - 64) * 16) = (tid - 64) < 2 ? make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u) : make_uint4(0u, 0u, 0u, 0u);
     fence_async_proxy();
     tc_fence_before_sync();
     __syncthreads();
@@ -134,10 +144,11 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
                 if (t > 0) mbar_wait(&bar_projfree, (t - 1) & 1);
                 mbar_wait(&bar_dready[t & 1], (t >> 1) & 1);
                 tc_fence_after_sync();
+                umma_bf16_ss(tmem + TM_PW, make_smem_desc(smem_u32(sm + oOne), 128, 0), make_smem_desc(smem_u32(sm + oPB), 768, 128), idesc_p, 0);   // bias
 #pragma unroll
                 for (int k16 = 0; k16 < 2; ++k16)
                     umma_bf16_ss(tmem + TM_PW, make_smem_desc(sD + (t & 1) * 8192 + k16 * 256, 128, 512),
-                                 make_smem_desc(sWp + k16 * 2 * 768, 768, 128), idesc_p, k16 > 0);
+                                 make_smem_desc(sWp + k16 * 2 * 768, 768, 128), idesc_p, 1);
                 umma_commit(&bar_proj[t & 1]);
             }
         }
@@ -207,14 +218,10 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
                 bf16* op = out + (((size_t)n * H2 + oy) * W2 + ox) * 48 + s * 16;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const float4 ba = *reinterpret_cast<const float4*>(Bps + s * 16 + 8 * i);
-                    const float4 bb = *reinterpret_cast<const float4*>(Bps + s * 16 + 8 * i + 4);
-                    const uint32_t* q8 = r + 8 * i;
+                    const uint32_t* q8 = r + 8 * i;      // the bias is already in the accumulator
                     *reinterpret_cast<uint4*>(op + 8 * i) =
-                        make_uint4(packbf_relu(__uint_as_float(q8[0]) + ba.x, __uint_as_float(q8[1]) + ba.y),
-                                   packbf_relu(__uint_as_float(q8[2]) + ba.z, __uint_as_float(q8[3]) + ba.w),
-                                   packbf_relu(__uint_as_float(q8[4]) + bb.x, __uint_as_float(q8[5]) + bb.y),
-                                   packbf_relu(__uint_as_float(q8[6]) + bb.z, __uint_as_float(q8[7]) + bb.w));
+                        make_uint4(packbf_relu(__uint_as_float(q8[0]), __uint_as_float(q8[1])), packbf_relu(__uint_as_float(q8[2]), __uint_as_float(q8[3])),
+                                   packbf_relu(__uint_as_float(q8[4]), __uint_as_float(q8[5])), packbf_relu(__uint_as_float(q8[6]), __uint_as_float(q8[7])));
                 }
             }
         };
