@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument('--no-stage-times', action='store_true')
     ap.add_argument('--no-fp32', action='store_true', help='skip the short fp32 exactness-path timing')
     ap.add_argument('--no-latency', dest='latency', action='store_false', help='skip the batch-1 CUDA-graph latency')
+    ap.add_argument('--only', default='', help="run one auxiliary measurement alone and print its JSON: 'eager'")
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary workloads (480x640, 360x640)')
     return ap.parse_args()
 
@@ -176,6 +177,42 @@ def cpu_reference_rate(h, w, nc, budget_s, warmup, steps=None):
         if (steps is not None and done >= steps) or (steps is None and el >= budget_s and done >= 3):
             break
     return done / el, done, el, cores, torch.get_num_threads()
+
+
+def gpu_eager_baseline(dev, h, w, nc, batches=(1, 16), reps=10):
+    """The honest GPU comparator: the reference's own op sequence (ATen-functional port, unfolded BN, NCHW
+    fp32 tensors) run eagerly through cuDNN / ATen on the SAME B200, fp32 and bf16 autocast, forward + torch.argmax,
+    synchronised.  Returns images/s per (precision, batch).  None of this repo's kernels are on this path."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import torch
+    import fastscnn_oracle as fo
+    import fastscnn_torch_port as tp
+    sd = {k: v.to(dev) for k, v in tp.to_torch_state_dict(fo.make_state_dict(nc, False, 7)).items()}
+    res = {}
+    torch.backends.cudnn.benchmark = True
+    for b in batches:
+        x = torch.randn(b, 3, h, w, device=dev)
+        for prec in ('fp32', 'bf16_autocast'):
+            def step():
+                if prec == 'fp32':
+                    return torch.argmax(tp.forward(sd, x)[0], 1)
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    return torch.argmax(tp.forward(sd, x)[0], 1)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                step()
+            e.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(e) / reps
+            res[f'{prec}_b{b}'] = {'images_per_s': b / (ms / 1e3), 'ms_per_step': ms}
+        del x
+    torch.backends.cudnn.benchmark = False
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference_arm(args):
@@ -612,6 +649,10 @@ def run_native_arm(args):
 
 def main():
     args = parse_args()
+    if args.only == 'eager':
+        import torch
+        print(json.dumps({'gpu_eager_baseline': gpu_eager_baseline(torch.device('cuda', 0), args.height, args.width, args.classes)}))
+        return
     if args.impl == 'reference':
         run_reference_arm(args)
     else:

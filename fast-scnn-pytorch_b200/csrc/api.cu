@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/fscnn_b200.h"
+#include <cstdlib>
 #include "kernels.h"
 
 using namespace fscnn;
@@ -312,6 +313,7 @@ struct Loader {
     // bf16 contexts only: depthwise tables become bf16-representable with error-diffused rounding (fold.cu)
     void round_dw(const fscnn_ctx* c, float* wd, int ch) {
         if (err || c->prec != FSCNN_PREC_BF16) return;
+        if (getenv("FSCNN_DW_ROUND_NEAREST")) return;   // experiment switch: plain round-to-nearest in the packers instead
         if (launch_dw_round_bf16(wd, ch, s) != cudaSuccess)
             err = fail(FSCNN_ECUDA, "depthwise rounding launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -772,15 +774,23 @@ int fscnn_forward_logits(fscnn_ctx* c, const void* d_x, int n, int h, int w, flo
     return FSCNN_OK;
 }
 
+static bool valid_label_dtype(int dt) { return dt == FSCNN_U8 || dt == FSCNN_I32 || dt == FSCNN_I64; }
+// class maps are read / written four elements at a time (uchar4 / int4 / 2 x longlong2) when the width is a multiple of 4
+static bool vec4_aligned(const void* p, int dt) {
+    const uintptr_t a = dt == FSCNN_U8 ? 4 : 16;
+    return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0;
+}
+
 static int forward_mask_impl(fscnn_ctx* c, const void* d_x, const void* d_labels, int label_dtype, int n, int h, int w,
                              long long* d_conf, void* d_mask, int mask_dtype, void* ws, size_t ws_bytes, void* stream) {
     Dims d; int mb; WsPlan p;
     int rc = check_forward_args(c, d_x, n, h, w, ws, ws_bytes, &d, &mb, &p);
     if (rc) return rc;
-    if (mask_dtype != FSCNN_U8 && mask_dtype != FSCNN_I32 && mask_dtype != FSCNN_I64) return fail(FSCNN_EINVAL, "bad mask dtype %d", mask_dtype);
-    if (d_labels && label_dtype != FSCNN_U8 && label_dtype != FSCNN_I32 && label_dtype != FSCNN_I64)
-        return fail(FSCNN_EINVAL, "bad label dtype %d", label_dtype);
-    if ((uintptr_t)d_mask & 15) return fail(FSCNN_EINVAL, "mask must be 16-byte aligned");
+    if (!valid_label_dtype(mask_dtype)) return fail(FSCNN_EINVAL, "bad mask dtype %d", mask_dtype);
+    if (d_labels && !valid_label_dtype(label_dtype)) return fail(FSCNN_EINVAL, "bad label dtype %d", label_dtype);
+    if (!vec4_aligned(d_mask, mask_dtype)) return fail(FSCNN_EINVAL, "mask must be aligned to 4 elements (4 bytes for uint8, 16 bytes for int32 / int64)");
+    if (d_labels && !vec4_aligned(d_labels, label_dtype))
+        return fail(FSCNN_EINVAL, "labels must be aligned to 4 elements (4 bytes for uint8, 16 bytes for int32 / int64)");
     const size_t msz = mask_dtype == FSCNN_U8 ? 1 : (mask_dtype == FSCNN_I32 ? 4 : 8);
     const size_t lsz = label_dtype == FSCNN_U8 ? 1 : (label_dtype == FSCNN_I32 ? 4 : 8);
     cudaStream_t s = (cudaStream_t)stream;
@@ -858,6 +868,24 @@ int fscnn_e2e_postprocess(const float* d_low_logits, int num_classes, int padded
     cudaError_t e = launch_e2e_postprocess(d_low_logits, num_classes, padded_classes, n, hl, wl, base_h, base_w, out_h, out_w, apply_softmax,
                                            d_out, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(FSCNN_ECUDA, "e2e postprocess launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_upsample_argmax(const float* d_low_logits, int nc, int ncp, int n, int hl, int wl, int h, int w, void* d_mask, int mask_dtype,
+                          const void* d_labels, int label_dtype, long long* d_conf, int flags, void* stream) {
+    if (!d_low_logits || (!d_mask && !d_labels)) return fail(FSCNN_EINVAL, "null device pointer");
+    if (nc < 1 || nc > 256 || ncp < nc || (ncp & 3)) return fail(FSCNN_EINVAL, "bad class count %d (padded %d)", nc, ncp);
+    if (n < 1 || hl < 1 || wl < 1 || h < 1 || w < 1) return fail(FSCNN_EINVAL, "bad shape");
+    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1))
+        return fail(FSCNN_EINVAL, "upsample ratio must be >= 7 (%dx%d -> %dx%d)", hl, wl, h, w);
+    if (d_mask && !valid_label_dtype(mask_dtype)) return fail(FSCNN_EINVAL, "bad mask dtype %d", mask_dtype);
+    if (d_labels && (!valid_label_dtype(label_dtype) || !d_conf)) return fail(FSCNN_EINVAL, "labels need a valid dtype and d_conf");
+    if ((reinterpret_cast<uintptr_t>(d_low_logits) & 15) || !vec4_aligned(d_mask, mask_dtype) || !vec4_aligned(d_labels, label_dtype))
+        return fail(FSCNN_EINVAL, "d_low_logits must be 16-byte aligned, d_mask / d_labels aligned to 4 elements");
+    cudaError_t e = launch_up_argmax(d_low_logits, nc, ncp, d_mask, mask_dtype, d_labels, label_dtype,
+                                     reinterpret_cast<unsigned long long*>(d_conf), n, hl, wl, h, w, (cudaStream_t)stream,
+                                     !(flags & FSCNN_TAIL_EXHAUSTIVE));
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "upsample+argmax launch failed: %s", cudaGetErrorString(e));
     return FSCNN_OK;
 }
 

@@ -69,17 +69,51 @@ struct ConfSink {
     }
 };
 
-// Finite-logit argmax over the classes for a thread's 8x4 output pixels.  Rows i < K interpolate between the
-// horizontally-lerped staged rows 0/1, rows i >= K between rows 1/2 (K is warp-uniform and a template constant, so the
-// vertical step is one FMUL + one FFMA per pixel).  `v > best` keeps the first maximal class.
-//
-// Exact branch-and-bound: every interpolated value of class c inside this 8x4 block is a convex combination of the
-// block's 3x3 low-res taps, so it lies in [min9_c, max9_c] (up to a few ulp of rounding).  With T = max_c min9_c, a class
-// whose max9_c is below T (minus 2e-6 x the block's largest |logit|, ~8x the rounding bound) cannot be the argmax of ANY pixel
-// of the block and is skipped; all others are interpolated and compared in class order as before.  The mask is
-// bit-identical to the exhaustive loop; only the time depends on how many classes are competitive locally.
+// ---- exact class pruning by pairwise dominance --------------------------------------------------------------
+// A low-resolution CELL is the 2x2 group of staged taps (R..R+1) x (Q..Q+1); every output pixel interpolates inside
+// exactly one cell.  The interpolation (horizontal fma/mul, then vertical fma/mul, all weights >= 0, round-to-nearest)
+// is a monotone non-decreasing function of each tap, so if class c is >= class d at all four corners of a cell, the
+// COMPUTED value of c is >= the computed value of d at every pixel of the cell.  With c < d that already means d can
+// never be torch.argmax's answer there (first maximal index wins); with c > d the four gaps must exceed the rounding
+// bound of the two lerps (< 4 ulp of the largest staged |logit|; 2e-6 x that leaves 8x headroom) so that c is strictly
+// larger.  Per cell, the champions (first maximal class) of corner (R,Q) and of corner (R+1,Q+1) each eliminate the
+// classes they dominate; what is left is a bit mask of the classes that can still win somewhere in the cell.  Constant
+// regions keep ONE class (no interpolation at all), a boundary between two regions keeps two, all-tied logits keep
+// class 0, and only logits where no class dominates another anywhere (e.g. class order flipping between neighbouring
+// taps) keep everything: the mask is bit-identical to the exhaustive loop in every case, only the time depends on the data.
+constexpr int kCR = kTR - 1, kCC = kTC - 1;      // 11 x 19 cells per staged tile
+
+__device__ __forceinline__ unsigned int dominated_by(const float* __restrict__ Ls, int nc, int o, int ch, float margin) {
+    const float* pc = Ls + ch * kTR * kTC + o;
+    const float p0 = pc[0], p1 = pc[1], p2 = pc[kTC], p3 = pc[kTC + 1];
+    unsigned int elim = 0u;
+    for (int d = 0; d < nc; ++d) {
+        const float* pd = Ls + d * kTR * kTC + o;
+        const float m = fminf(fminf(p0 - pd[0], p1 - pd[1]), fminf(p2 - pd[kTC], p3 - pd[kTC + 1]));
+        const bool e = ch < d ? (m >= 0.f) : (m > margin);      // d == ch: m == 0 > margin is false
+        elim |= (e ? 1u : 0u) << d;
+    }
+    return elim;
+}
+
+__device__ __forceinline__ unsigned int cell_survivors(const float* __restrict__ Ls, int nc, int o, float margin) {
+    int ch0 = 0, ch3 = 0;
+    float b0 = Ls[o], b3 = Ls[o + kTC + 1];
+    for (int c = 1; c < nc; ++c) {
+        const float v0 = Ls[c * kTR * kTC + o], v3 = Ls[c * kTR * kTC + o + kTC + 1];
+        if (v0 > b0) { b0 = v0; ch0 = c; }
+        if (v3 > b3) { b3 = v3; ch3 = c; }
+    }
+    unsigned int elim = dominated_by(Ls, nc, o, ch0, margin);
+    if (ch3 != ch0) elim |= dominated_by(Ls, nc, o, ch3, margin);
+    return ~elim & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+}
+
+// Finite-logit argmax over the candidate classes `cand` (ascending, so `v > best` keeps the first maximal class) for a
+// thread's 8x4 output pixels.  Rows i < K interpolate between the horizontally-lerped staged rows 0/1, rows i >= K
+// between rows 1/2 (K is warp-uniform and a template constant, so the vertical step is one FMUL + one FFMA per pixel).
 template <int K>
-__device__ __forceinline__ void argmax_fast(const float* __restrict__ Ls, int nc, const int (&ro)[3], const int (&co)[3],
+__device__ __forceinline__ void argmax_fast(const float* __restrict__ Ls, unsigned int cand, const int (&ro)[3], const int (&co)[3],
                                             const float (&wx)[4][3], const float (&wy)[8][3], float (&best)[8][4], int (&bidx)[8][4]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -88,26 +122,14 @@ __device__ __forceinline__ void argmax_fast(const float* __restrict__ Ls, int nc
     const int o00 = ro[0] + co[0], o01 = ro[0] + co[1], o02 = ro[0] + co[2];
     const int o10 = ro[1] + co[0], o11 = ro[1] + co[1], o12 = ro[1] + co[2];
     const int o20 = ro[2] + co[0], o21 = ro[2] + co[1], o22 = ro[2] + co[2];
-    float T = -INFINITY, amax = 0.f;
-    for (int c = 0; c < nc; ++c) {
-        const float* lc = Ls + c * kTR * kTC;
-        const float a0 = lc[o00], a1 = lc[o01], a2 = lc[o02], a3 = lc[o10], a4 = lc[o11], a5 = lc[o12], a6 = lc[o20], a7 = lc[o21], a8 = lc[o22];
-        const float mn = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(a4, a5), fminf(fminf(a6, a7), a8)));
-        const float mx = fmaxf(fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)), fmaxf(fmaxf(a4, a5), fmaxf(fmaxf(a6, a7), a8)));
-        T = fmaxf(T, mn);
-        amax = fmaxf(amax, fmaxf(fabsf(mn), fabsf(mx)));
-    }
-    // rounding of the two lerps is below 4 ulp of the largest tap magnitude (2.4e-7 relative); 2e-6 leaves 8x headroom
-    const float cut = T - (2e-6f * amax + 1e-30f);
-    for (int c = 0; c < nc; ++c) {
+    while (cand) {
+        const int c = __ffs(cand) - 1;
+        cand &= cand - 1u;
         const float* lc = Ls + c * kTR * kTC;
         float v[3][3];
         v[0][0] = lc[o00]; v[0][1] = lc[o01]; v[0][2] = lc[o02];
         v[1][0] = lc[o10]; v[1][1] = lc[o11]; v[1][2] = lc[o12];
-        v[2][0] = lc[o20]; v[2][1] = lc[o21]; v[2][2] = lc[o22];
-        const float mx = fmaxf(fmaxf(fmaxf(v[0][0], v[0][1]), fmaxf(v[0][2], v[1][0])),
-                               fmaxf(fmaxf(v[1][1], v[1][2]), fmaxf(fmaxf(v[2][0], v[2][1]), v[2][2])));
-        if (mx < cut) continue;   // cannot win anywhere in this block
+        if (K < 8) { v[2][0] = lc[o20]; v[2][1] = lc[o21]; v[2][2] = lc[o22]; }
         float hrow[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -132,11 +154,12 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
 upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restrict__ out_logits, void* __restrict__ mask,
                 int mask_dtype, const void* __restrict__ labels, int label_dtype, unsigned long long* __restrict__ conf,
-                int hl, int wl, int H, int W, int use_smem_hist) {
+                int hl, int wl, int H, int W, int use_smem_hist, int prune) {
     extern __shared__ __align__(16) float dynsm[];
     float* Ls = dynsm;                                            // [nc][kTR][kTC]
     unsigned int* hist = reinterpret_cast<unsigned int*>(dynsm + nc * kTR * kTC);
-    __shared__ unsigned int blk_labeled, blk_correct;
+    __shared__ unsigned int blk_labeled, blk_correct, tile_amax;
+    __shared__ unsigned int cellmask[kCR * kCC];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.z;
@@ -149,6 +172,8 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
 
     // stage the low-res tile class-major: one float4 (4 classes of one pixel) per item, independent loads in flight
     int nonfinite = 0;
+    float amax = 0.f;
+    if (MODE == 1 && tid == 0) tile_amax = 0u;
     {
         const int nv = ncp >> 2;
         for (int i = tid; i < kTR * kTC * nv; i += kThreads) {
@@ -158,6 +183,7 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             const float4 t = __ldg(reinterpret_cast<const float4*>(low + (((size_t)n * hl + rr) * wl + qq) * ncp) + v);
             const int c = 4 * v;
             nonfinite |= !(fabsf(t.x) <= 3.4e38f) | !(fabsf(t.y) <= 3.4e38f) | !(fabsf(t.z) <= 3.4e38f) | !(fabsf(t.w) <= 3.4e38f);
+            if (MODE == 1) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
             float* dst = Ls + (c * kTR + r) * kTC + q;
             dst[0] = t.x;
             if (c + 1 < nc) dst[kTR * kTC] = t.y;
@@ -170,8 +196,20 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             for (int i = tid; i < (nc + 1) * (nc + 1); i += kThreads) hist[i] = 0u;
         if (tid == 0) { blk_labeled = 0u; blk_correct = 0u; }
     }
-    // NaN / Inf among the staged logits (padding classes are finite zeros) selects the exact-semantics slow loop
-    const bool slow = __syncthreads_or(nonfinite) != 0;
+    // NaN / Inf among the staged logits (padding classes are finite zeros) selects the exact-semantics slow loop; so do
+    // more classes than the candidate bit mask holds
+    const bool slow = (__syncthreads_or(nonfinite) != 0) || nc > 32;
+    if (MODE == 1 && !slow) {
+        // the tile's largest |logit| (non-negative floats order like their bit patterns), then one cell per thread
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0) atomicMax(&tile_amax, __float_as_uint(amax));
+        __syncthreads();
+        const float margin = 2e-6f * __uint_as_float(tile_amax) + 1e-30f;
+        if (tid < kCR * kCC)      // prune == 0 (tests, worst-case timing): every class stays a candidate everywhere
+            cellmask[tid] = prune ? cell_survivors(Ls, nc, (tid / kCC) * kTC + (tid % kCC), margin) : (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+        __syncthreads();
+    }
 
     const int x0 = xb + lane * 4, y0 = yb + warp * 8;
     if (x0 >= W || y0 >= H) {
@@ -182,12 +220,14 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     // finite logits each pixel is fma(lx, b, hx*a) of its own two taps -- horizontal first, then vertical, like ATen.
     float wx[4][3], wy[8][3];
     const int c0 = min((int)(scx * (float)x0), wl - 1);
+    bool second_col = false;      // some column of this thread interpolates inside the cell to the right of c0's
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float fx = scx * (float)(x0 + j);
         const int q = min((int)fx, wl - 1);
         const float lx = fx - (float)q, hx = 1.f - lx;
         const bool s = (q - c0) != 0;
+        second_col |= s;
         wx[j][0] = s ? 0.f : hx; wx[j][1] = s ? hx : lx; wx[j][2] = s ? lx : 0.f;
     }
     const int r0 = min((int)(scy * (float)y0), hl - 1);
@@ -228,17 +268,36 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
         // all logits finite: plain `>` argmax, and the vertical taps picked at compile time.  The number of rows that
         // still use the first staged row pair is the same for every lane of the warp (they share y0).
         const int k = rows_on_first_pair;
-        switch (k) {
-            case 1: argmax_fast<1>(Ls, nc, ro, co, wx, wy, best, bidx); break;
-            case 2: argmax_fast<2>(Ls, nc, ro, co, wx, wy, best, bidx); break;
-            case 3: argmax_fast<3>(Ls, nc, ro, co, wx, wy, best, bidx); break;
-            case 4: argmax_fast<4>(Ls, nc, ro, co, wx, wy, best, bidx); break;
-            case 5: argmax_fast<5>(Ls, nc, ro, co, wx, wy, best, bidx); break;
-            case 6: argmax_fast<6>(Ls, nc, ro, co, wx, wy, best, bidx); break;
-            case 7: argmax_fast<7>(Ls, nc, ro, co, wx, wy, best, bidx); break;
-            default: argmax_fast<8>(Ls, nc, ro, co, wx, wy, best, bidx); break;
+        // candidate classes of this thread's block = union over the (at most 2 x 2) cells its pixels interpolate in
+        const unsigned int* cm = cellmask + (r0 - rb) * kCC + (c0 - cb);
+        unsigned int cand = cm[0];
+        if (second_col) cand |= cm[1];
+        if (k < 8) {
+            cand |= cm[kCC];
+            if (second_col) cand |= cm[kCC + 1];
+        }
+        if ((cand & (cand - 1u)) == 0u) {       // one class dominates the whole block: constant fill, no interpolation
+            const int c = __ffs(cand) - 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bidx[i][j] = c;
+        } else {
+            switch (k) {
+                case 1: argmax_fast<1>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+                case 2: argmax_fast<2>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+                case 3: argmax_fast<3>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+                case 4: argmax_fast<4>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+                case 5: argmax_fast<5>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+                case 6: argmax_fast<6>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+                case 7: argmax_fast<7>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+                default: argmax_fast<8>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+            }
         }
     } else if (live) {
+        // generic loop (full-resolution logits; NaN / Inf; more than 32 classes): every pixel reads exactly the 2 x 2 taps ATen
+        // reads -- a non-finite value under a zero weight of the 3-tap form would poison pixels torch keeps finite.
+        // hx = 1 - lx > 0 always, so a zero first weight identifies the columns / rows that use the second tap pair.
         for (int c = 0; c < nc; ++c) {
             const float* lc = Ls + c * kTR * kTC;
             float hrow[3][4];
@@ -246,13 +305,18 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             for (int r = 0; r < 3; ++r) {
                 const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v2, fmaf(wx[j][1], v1, wx[j][0] * v0));
+                for (int j = 0; j < 4; ++j) {
+                    const bool sx = wx[j][0] == 0.f;
+                    hrow[r][j] = fmaf(sx ? wx[j][2] : wx[j][1], sx ? v2 : v1, (sx ? wx[j][1] : wx[j][0]) * (sx ? v1 : v0));
+                }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float val[4];
+                const bool sy = wy[i][0] == 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) val[j] = fmaf(wy[i][2], hrow[2][j], fmaf(wy[i][1], hrow[1][j], wy[i][0] * hrow[0][j]));
+                for (int j = 0; j < 4; ++j)
+                    val[j] = fmaf(sy ? wy[i][2] : wy[i][1], sy ? hrow[2][j] : hrow[1][j], (sy ? wy[i][1] : wy[i][0]) * (sy ? hrow[1][j] : hrow[0][j]));
                 if (MODE == 0) {
                     if (y0 + i < H) {
                         float* o = out_logits + (((size_t)n * nc + c) * H + (y0 + i)) * W + x0;
@@ -391,13 +455,13 @@ cudaError_t launch_up_logits(const float* low, int nc, int ncp, float* out, int 
         if (e != cudaSuccess) return e;
     }
     dim3 grid(ceil_div(w, 128), ceil_div(h, 64), n);
-    upsample_kernel<0><<<grid, kThreads, smem, s>>>(low, nc, ncp, out, nullptr, 0, nullptr, 0, nullptr, hl, wl, h, w, 0);
+    upsample_kernel<0><<<grid, kThreads, smem, s>>>(low, nc, ncp, out, nullptr, 0, nullptr, 0, nullptr, hl, wl, h, w, 0, 0);
     return cudaGetLastError();
 }
 
 cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
                              int label_dtype, unsigned long long* conf, int n, int hl, int wl, int h, int w,
-                             cudaStream_t s) {
+                             cudaStream_t s, bool prune) {
     if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1)) return cudaErrorInvalidValue;
     const bool hist = labels != nullptr;
     const int smem_hist = hist && ((nc + 1) * (nc + 1) <= kHistMaxBins);
@@ -411,7 +475,7 @@ cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int 
     }
     dim3 grid(ceil_div(w, 128), ceil_div(h, 64), n);
     upsample_kernel<1><<<grid, kThreads, smem, s>>>(low, nc, ncp, nullptr, mask, mask_dtype, labels, label_dtype, conf, hl,
-                                                    wl, h, w, smem_hist);
+                                                    wl, h, w, smem_hist, prune ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -54,7 +54,7 @@ cudaError_t launch_up_logits(const float* low, int nc, int ncp, float* out, int 
                              cudaStream_t s);
 cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
                              int label_dtype, unsigned long long* conf, int n, int hl, int wl, int h, int w,
-                             cudaStream_t s);
+                             cudaStream_t s, bool prune = true);
 cudaError_t launch_confusion(const void* pred, int pred_dtype, const void* label, int label_dtype, long long npix, int nc,
                              unsigned long long* conf, cudaStream_t s);
 

@@ -120,10 +120,25 @@ class Engine:
                                                        ws.numel(), _stream_ptr()), 'fscnn_forward_logits')
         return logits, aux
 
+    def _check_class_map(self, t: torch.Tensor, n: int, h: int, w: int, what: str) -> None:
+        """A caller-provided class map goes to the kernels as a raw pointer: shape, layout, device, dtype and the
+        4-element alignment the vectorised accesses need (include/fscnn_b200.h) are checked here."""
+        if t.dtype not in _DTYPE_CODE:
+            raise ValueError(f'{what} must be torch.uint8, torch.int32 or torch.int64, got {t.dtype}')
+        if tuple(t.shape) != (n, h, w) or not t.is_contiguous():
+            raise ValueError(f'{what} must be a contiguous [{n},{h},{w}] tensor, got {tuple(t.shape)}')
+        if t.device != self.device:
+            raise RuntimeError(f'{what} is on {t.device}, the model is on {self.device}')
+        if t.data_ptr() % (4 * t.element_size()):
+            raise ValueError(f'{what} must be aligned to 4 elements ({4 * t.element_size()} bytes); pass a tensor that starts '
+                             f'at such an offset of its storage')
+
     def forward_mask(self, x: torch.Tensor, out_dtype=torch.uint8, out: Optional[torch.Tensor] = None, norm=None) -> torch.Tensor:
         n, h, w = self._check_input(x, norm)
         if out_dtype not in _DTYPE_CODE:
             raise ValueError('mask dtype must be torch.uint8, torch.int32 or torch.int64')
+        if out is not None:
+            self._check_class_map(out, n, h, w, 'out')
         with torch.cuda.device(self.device):
             ws = self._workspace(n, h, w)
             mask = out if out is not None else torch.empty((n, h, w), dtype=out_dtype, device=self.device)
@@ -135,10 +150,11 @@ class Engine:
     def forward_confusion(self, x: torch.Tensor, labels: torch.Tensor, conf: torch.Tensor,
                           mask: Optional[torch.Tensor] = None, norm=None) -> torch.Tensor:
         n, h, w = self._check_input(x, norm)
-        if labels.dtype not in _DTYPE_CODE or tuple(labels.shape) != (n, h, w) or not labels.is_contiguous():
-            raise ValueError('labels must be a contiguous [N,H,W] uint8/int32/int64 tensor')
-        if labels.device != self.device or conf.device != self.device:
-            raise RuntimeError('labels / conf must be on the model device')
+        self._check_class_map(labels, n, h, w, 'labels')
+        if mask is not None:
+            self._check_class_map(mask, n, h, w, 'mask')
+        if conf.device != self.device:
+            raise RuntimeError('conf must be on the model device')
         if conf.dtype != torch.int64 or conf.numel() != self.conf_len() or not conf.is_contiguous():
             raise ValueError(f'conf must be a contiguous int64[{self.conf_len()}] tensor')
         with torch.cuda.device(self.device):
@@ -148,6 +164,29 @@ class Engine:
                 mask.data_ptr() if mask is not None else None, _DTYPE_CODE[mask.dtype] if mask is not None else 0,
                 ws.data_ptr(), ws.numel(), _stream_ptr()), 'fscnn_forward_confusion')
         return conf
+
+    def upsample_argmax(self, low_logits: torch.Tensor, h: int, w: int, out_dtype=torch.uint8, labels: Optional[torch.Tensor] = None,
+                        conf: Optional[torch.Tensor] = None, want_mask: bool = True, exhaustive: bool = False) -> Optional[torch.Tensor]:
+        """The tail stage alone (fscnn_upsample_argmax): low_logits float32 [N,hl,wl,padded_classes] (NHWC, the layout of the
+        'cls.logits_lowres' tap) -> class map [N,h,w]; with labels, also adds the confusion counts into conf.  exhaustive=True
+        switches the exact class pruning off (same result, worst-case time)."""
+        if low_logits.dtype != torch.float32 or low_logits.dim() != 4 or not low_logits.is_contiguous() or not low_logits.is_cuda:
+            raise ValueError('low_logits must be a contiguous CUDA float32 [N,hl,wl,padded_classes] tensor')
+        n, hl, wl, ncp = low_logits.shape
+        dev = low_logits.device
+        mask = torch.empty((n, h, w), dtype=out_dtype, device=dev) if want_mask else None
+        if labels is not None:
+            if conf is None or conf.dtype != torch.int64 or conf.numel() != self.conf_len() or conf.device != dev:
+                raise ValueError(f'labels need conf: an int64[{self.conf_len()}] tensor on {dev}')
+            if labels.dtype not in _DTYPE_CODE or tuple(labels.shape) != (n, h, w) or not labels.is_contiguous() or labels.device != dev:
+                raise ValueError('labels must be a contiguous [N,h,w] uint8/int32/int64 tensor on the logits\' device')
+        with torch.cuda.device(dev):
+            native.check(self.lib.fscnn_upsample_argmax(
+                low_logits.data_ptr(), self.num_classes, ncp, n, hl, wl, h, w, mask.data_ptr() if mask is not None else None,
+                _DTYPE_CODE[out_dtype], labels.data_ptr() if labels is not None else None,
+                _DTYPE_CODE[labels.dtype] if labels is not None else 0, conf.data_ptr() if conf is not None else None,
+                native.TAIL_EXHAUSTIVE if exhaustive else 0, _stream_ptr()), 'fscnn_upsample_argmax')
+        return mask
 
     def conf_len(self) -> int:
         return int(self.lib.fscnn_conf_len(self.num_classes))

@@ -13,6 +13,7 @@ _LIB_NAME = 'libfscnn_b200.so'
 PREC_FP32, PREC_BF16 = 0, 1
 U8, I32, I64, F32 = 0, 1, 2, 3
 IN_F32_NCHW, IN_U8_NHWC = 0, 1
+TAIL_EXHAUSTIVE = 1
 
 
 class NativeError(RuntimeError):
@@ -59,6 +60,8 @@ _SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     'fscnn_e2e_postprocess': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_void_p]),
+    'fscnn_upsample_argmax': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'fscnn_conf_to_totals': (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong),
                                        C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     'fscnn_stage_count': (C.c_int, [C.c_void_p]),

@@ -176,10 +176,12 @@ class FastSCNN(nn.Module):
             self.auxlayer = nn.Sequential(nn.Conv2d(64, 32, 3, padding=1, bias=False), nn.BatchNorm2d(32), nn.ReLU(True),
                                           nn.Dropout(0.1), nn.Conv2d(32, num_classes, 1))
         self._rt = _Runtime()
+        self._fp_tensors = None
 
     def __getstate__(self):   # the native runtime is rebuilt lazily; it never travels with copies / pickles
         state = self.__dict__.copy()
         state['_rt'] = None
+        state['_fp_tensors'] = None
         return state
 
     def __setstate__(self, state):
@@ -196,11 +198,23 @@ class FastSCNN(nn.Module):
                 break
         if state_dict and all(k.startswith('module.') for k in state_dict):
             state_dict = OrderedDict((k[len('module.'):], v) for k, v in state_dict.items())
+        self._fp_tensors = None
         return super().load_state_dict(state_dict, strict=strict, **kwargs)
 
     # ---- native engine management ------------------------------------------------------------
+    def _apply(self, fn, recurse=True):
+        # .to() / .cuda() / .float() replace buffer objects: drop the cached tensor list the fingerprint walks
+        self._fp_tensors = None
+        return super()._apply(fn, recurse)
+
     def _fingerprint(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        """(storage address, in-place version) of every parameter and buffer: changes whenever the weights the engine was
+        packed from may have changed.  Called on every forward (eval.py:43 runs batch 1), so the tensor list is cached
+        instead of rebuilding ``state_dict()``; ``_apply`` and ``load_state_dict`` invalidate it."""
+        ts = self.__dict__.get('_fp_tensors')      # per module object: a DataParallel replica walks its own tensors
+        if ts is None:
+            ts = self._fp_tensors = list(self.state_dict(keep_vars=True).values())
+        return tuple([(t.data_ptr(), t._version) for t in ts])
 
     def _engine(self, device: torch.device):
         from fscnn_b200 import Engine

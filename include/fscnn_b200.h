@@ -116,7 +116,9 @@ int fscnn_forward_logits(fscnn_ctx* ctx, const void* d_x, int n, int h, int w,
 
 /* Replaces forward + torch.argmax(outputs[0], 1) (eval.py:43-45, demo.py:47-48) without ever
  * materialising the full-resolution logits.  d_mask is [n,h,w] of mask_dtype (FSCNN_U8 needs
- * num_classes <= 256; FSCNN_I64 reproduces torch.argmax's dtype). */
+ * num_classes <= 256; FSCNN_I64 reproduces torch.argmax's dtype).  Class maps (d_mask here, d_labels / d_mask below) are
+ * accessed four elements at a time: their base address must be aligned to 4 elements (4 bytes for FSCNN_U8, 16 bytes for
+ * FSCNN_I32 / FSCNN_I64), otherwise the call returns FSCNN_EINVAL. */
 int fscnn_forward_mask(fscnn_ctx* ctx, const void* d_x, int n, int h, int w,
                        void* d_mask, int mask_dtype,
                        void* d_workspace, size_t workspace_bytes, void* stream);
@@ -179,6 +181,21 @@ int fscnn_forward_range(fscnn_ctx* ctx, const void* d_x, int n, int h, int w, in
  * "gfe.bottleneck1.0" ... "gfe.ppm", "ffm", "cls.dsconv1", "cls.logits_lowres",
  * "aux.logits_lowres") lives in a workspace planned for [n,3,h,w]. */
 int fscnn_tap_info(const fscnn_ctx* ctx, int n, int h, int w, const char* tap, fscnn_tap* out);
+
+/* The tail of the path as a stage of its own: the x8 bilinear upsample (align_corners=True, models/fast_scnn.py:40)
+ * fused with torch.argmax(outputs[0], 1) (eval.py:45) and, when d_labels is given, with SegmentationMetric's counting
+ * (utils/metric.py:73-105), from caller-provided low-resolution logits [n][hl][wl][padded_classes] float32 (the layout of
+ * the "cls.logits_lowres" tap; padded_classes a multiple of 4, >= num_classes; 16-byte aligned).  d_mask [n][h][w]
+ * (mask_dtype; may be NULL when labels are given), d_labels [n][h][w] or NULL, d_conf int64[fscnn_conf_len] accumulated
+ * (required with labels).  (hl-1)*7 <= h-1 and (wl-1)*7 <= w-1 (the resize ratio of the network is 1/8).  Lets a test or a
+ * benchmark drive the fused kernel with logits of its own (ties, NaN, class boundaries, adversarial orderings).
+ * flags: FSCNN_TAIL_EXHAUSTIVE switches the exact class pruning off (every class is interpolated and compared at every
+ * pixel): the result is identical by construction, only the time differs -- the reference point of the pruning tests and
+ * of the worst-case timing. */
+#define FSCNN_TAIL_EXHAUSTIVE 1
+int fscnn_upsample_argmax(const float* d_low_logits, int num_classes, int padded_classes, int n, int hl, int wl, int h, int w,
+                          void* d_mask, int mask_dtype, const void* d_labels, int label_dtype, long long* d_conf, int flags,
+                          void* stream);
 
 /* Kernel launches issued by this ctx since creation (for bench.py's gpu_launches). */
 int64_t fscnn_launch_count(const fscnn_ctx* ctx);

@@ -83,5 +83,30 @@ def eval_step(sd, x, labels, nclass, metric):
     return pred
 
 
+@torch.no_grad()
+def forward_bf16_autocast(sd, x):
+    """The reference's OWN reduced-precision behaviour on this input: the same op sequence under
+    ``torch.autocast(bfloat16)`` on the CPU (ATen casts the convolutions to bf16, keeps BatchNorm / interpolation
+    accumulation in fp32).  Returns float32 logits.  This is the yardstick of the bf16 path's tolerance
+    (tests/test_gpu_bf16.py, __graft_entry__.smoke): how far does the reference itself move when it runs in bf16?"""
+    with torch.autocast('cpu', dtype=torch.bfloat16):
+        out = forward(sd, x)
+    return tuple(o.float() for o in out)
+
+
+def bf16_yardstick(sd_np, x_np, ref_logits=None):
+    """(max, rms) error / absmax and mask disagreement of the reference's bf16 autocast against its fp32 run, both
+    through this port, for a numpy state_dict and input.  ``ref_logits`` (numpy, fp32) may be passed to save the
+    fp32 run."""
+    sd = to_torch_state_dict(sd_np)
+    x = torch.from_numpy(np.asarray(x_np))
+    ref = torch.from_numpy(np.asarray(ref_logits)) if ref_logits is not None else forward(sd, x)[0]
+    low = forward_bf16_autocast(sd, x)[0]
+    d = (low - ref).abs()
+    scale = float(ref.abs().max())
+    return {'max': float(d.max()) / scale, 'rms': float(d.pow(2).mean().sqrt()) / scale,
+            'mask': float((low.argmax(1) != ref.argmax(1)).float().mean())}
+
+
 def to_torch_state_dict(sd_np):
     return {k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}

@@ -32,3 +32,33 @@ def build_model(sd, nc, aux, device, precision='fp32'):
     model = FastSCNN(nc, aux=aux, precision=precision).eval()
     model.load_state_dict(torch_state_dict(sd))
     return model.to(device)
+
+
+# ---- the bf16 path's stated tolerance, anchored on the reference's own bf16 behaviour ------------------------------------
+# Measured on a B200 (profiles/r02_bf16_error_budget.md): the path's logit error is the sum of ~45 independent bf16
+# roundings (stage tensors, expanded / depthwise tiles, weights) spread evenly over the stages, and its rms equals that
+# of the reference run under torch.autocast(bfloat16) on the same input (ratio 0.74-0.99 over six configurations, CPU and
+# cuDNN autocast alike), with FEWER differing mask pixels in all six.  The max over 1e5-1e7 logits of that heavy-tailed
+# error is a noisy statistic: ours / reference ranged 0.59-1.73 at equal rms.  The sharp criterion is therefore the rms,
+# the max gets the slack its variance needs, and fixed backstops guard against both being bad together.
+BF16_RMS_VS_REF, BF16_MAX_VS_REF, BF16_MASK_SLACK = 1.25, 2.0, 0.005
+BF16_MAX_BACKSTOP, BF16_MASK_BACKSTOP = 6e-2, 5e-2
+
+
+def bf16_errors(got_logits, ref_logits):
+    d = np.abs(np.asarray(got_logits, np.float64) - np.asarray(ref_logits, np.float64))
+    scale = float(np.abs(ref_logits).max())
+    return {'max': float(d.max()) / scale, 'rms': float(np.sqrt((d * d).mean())) / scale,
+            'mask': float((np.argmax(got_logits, 1) != np.argmax(ref_logits, 1)).mean())}
+
+
+def check_bf16_against_yardstick(ours, yard):
+    """ours / yard: dicts from bf16_errors / fastscnn_torch_port.bf16_yardstick.  Returns a list of violated criteria."""
+    bad = []
+    if not ours['rms'] <= BF16_RMS_VS_REF * yard['rms']:
+        bad.append(f"rms {ours['rms']:.3e} > {BF16_RMS_VS_REF} x reference bf16 rms {yard['rms']:.3e}")
+    if not ours['max'] <= min(BF16_MAX_VS_REF * yard['max'], BF16_MAX_BACKSTOP):
+        bad.append(f"max {ours['max']:.3e} > min({BF16_MAX_VS_REF} x reference bf16 max {yard['max']:.3e}, {BF16_MAX_BACKSTOP})")
+    if not ours['mask'] <= min(yard['mask'] + BF16_MASK_SLACK, BF16_MASK_BACKSTOP):
+        bad.append(f"mask disagreement {ours['mask']:.3%} > reference bf16 {yard['mask']:.3%} + {BF16_MASK_SLACK:.1%}")
+    return bad
