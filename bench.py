@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument('--no-fp32', action='store_true', help='skip the short fp32 exactness-path timing')
     ap.add_argument('--no-latency', dest='latency', action='store_false', help='skip the batch-1 CUDA-graph latency')
     ap.add_argument('--only', default='', help="run one auxiliary measurement alone and print its JSON: 'eager'")
+    ap.add_argument('--no-eager', action='store_true', help='skip the cuDNN-eager comparator on the same GPU')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary workloads (480x640, 360x640)')
     return ap.parse_args()
 
@@ -237,6 +238,75 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # native arm
 # ---------------------------------------------------------------------------------------------
+def init_recipe_d2(model, seed):
+    """Recipe D2 of SURVEY.md appendix D, restated with torch RNG (the oracle's numpy version is test infrastructure and is not
+    imported here): variance-preserving conv weights N(0, sqrt(2 / fan_in)), conv bias N(0, .05), BN gamma U(.8, 1.2),
+    beta / mean N(0, .1), var U(.8, 1.2).  Unlike plain random init (recipe D1: one class wins 99.997 % of the pixels) the
+    logits then have class regions and boundaries, which is what the data-dependent tail kernel has to be timed on."""
+    import math
+    import torch
+    import torch.nn as nn
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, nn.Conv2d):
+                fan_in = m.weight[0].numel()
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * math.sqrt(2.0 / fan_in))
+                if m.bias is not None:
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.05)
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.4 + 0.8)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) * 0.4 + 0.8)
+
+
+def smooth_images(n, h, w, dev, seed, chunk=8):
+    """Recipe D2's input: sum of bilinearly upsampled Gaussian noise at strides 64 / 16 / 4 / 1 (amplitudes 1 / .6 / .3 / .15)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = torch.empty((n, 3, h, w), device=dev)
+    for i0 in range(0, n, chunk):
+        m = min(chunk, n - i0)
+        acc = torch.zeros((m, 3, h, w), device=dev)
+        for stride, amp in ((64, 1.0), (16, 0.6), (4, 0.3), (1, 0.15)):
+            hs, ws = max(2, -(-h // stride) + 1), max(2, -(-w // stride) + 1)
+            z = torch.randn((m, 3, hs, ws), device=dev, generator=g)
+            acc += amp * (z if (hs, ws) == (h, w) else F.interpolate(z, size=(h, w), mode='bilinear', align_corners=True))
+        x[i0:i0 + m] = acc
+    return x
+
+
+def lowres_logits(eng, x, h, w):
+    """Runs the network up to its low-resolution logits and returns them as a contiguous [n, hl, wl, padded_classes] tensor
+    (the layout fscnn_upsample_argmax takes)."""
+    import ctypes as C
+    import torch
+    from fscnn_b200 import native
+    names = eng.stage_names()
+    eng.forward_range(x, 0, names.index('cls.dsconv2+head'))
+    tap = native.Tap()
+    native.check(eng.lib.fscnn_tap_info(eng._ctx, x.shape[0], h, w, b'cls.logits_lowres', C.byref(tap)))
+    ws = eng._workspace(x.shape[0], h, w)
+    count = tap.n * tap.h * tap.w * tap.c_stride
+    return ws[tap.offset_bytes: tap.offset_bytes + count * 4].view(torch.float32).view(tap.n, tap.h, tap.w, tap.c_stride).clone()
+
+
+def time_cuda(fn, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
 def run_native_arm(args):
     import torch
     import torch.distributed as dist
@@ -264,36 +334,51 @@ def run_native_arm(args):
     h, w, nc, B = args.height, args.width, args.classes, args.batch
     es = 4 if args.precision == 'fp32' else 2
 
-    torch.manual_seed(1234 + rank)
-    model = FastSCNN(nc, precision=args.precision).eval()
-    with torch.no_grad():   # random-init weights of the architecture, with non-trivial BN statistics
-        for name, buf in model.named_buffers():
-            if name.endswith('running_mean'):
-                buf.normal_(0, 0.1)
-            elif name.endswith('running_var'):
-                buf.uniform_(0.8, 1.2)
-    model.to(dev)
-    x = torch.randn(B, 3, h, w, device=dev)
-    labels = torch.randint(-1, nc, (B, h, w), device=dev, dtype=torch.int64)
-    metric = SegmentationMetric(nc, device=dev)
-    eng = model._engine(dev)
-    if args.micro_batch:
-        eng.set_micro_batch(args.micro_batch)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- the model and the batch: recipe D2 (class regions and boundaries; all classes present) ----
+    model = FastSCNN(nc, precision=args.precision).eval()
+    init_recipe_d2(model, 7)
+    model.to(dev)
+    eng = model._engine(dev)
+    if args.micro_batch:
+        eng.set_micro_batch(args.micro_batch)
+    x = smooth_images(B, h, w, dev, 1234 + rank)
+    with torch.no_grad():      # D2's calibration: subtract the mean logit per class so that every class wins somewhere
+        low = lowres_logits(eng, x[:min(B, 8)].contiguous(), h, w)
+        model.classifier.conv[1].bias -= low[..., :nc].mean(dim=(0, 1, 2))
+    if world > 1:              # every rank evaluates the same weights
+        dist.broadcast(model.classifier.conv[1].bias.data, src=0)
+    eng = model._engine(dev)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    labels = torch.randint(-1, nc, (B, h, w), device=dev, dtype=torch.int64, generator=g)   # -1 = ignore
+    labeled_per_step = int((labels >= 0).sum().item())
+    metric = SegmentationMetric(nc, device=dev)
+    probe = model.predict(x[:2].contiguous())
+    frac = torch.bincount(probe.flatten().long(), minlength=nc).float() / probe.numel()
+    classes_present, largest_class = int((frac > 1e-4).sum().item()), float(frac.max().item())
+    del probe
+
     def step_device():
         model.evaluate(x, labels, metric)
 
-    # ---- device-resident throughput ----
+    # ---- device-resident throughput: K steps + the path's only collective + the metric read-back, all inside the timed region ----
     sampler = ClockSampler(local)      # started before the warm-up so that it is already sampling (every 20 ms) when the timed
     if rank == 0:                      # regions run; only samples taken inside a timed region (device-resident + e2e) are kept
         sampler.start()
     for _ in range(max(3, args.warmup)):
         step_device()
+    metric.reset()
     barrier()
     sampler.begin()
     launches0 = eng.launch_count()
@@ -301,35 +386,110 @@ def run_native_arm(args):
     ev0.record()
     for _ in range(args.steps):
         step_device()
+    metric.all_reduce()                # one NCCL sum of the int64 confusion state (no-op on one GPU)
+    pix_acc, miou = metric.get()       # device -> host read of the reduced state, float64 pixAcc / mIoU as metric.py:42-54
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = eng.launch_count() - launches0
-    if world > 1:
-        metric.all_reduce()            # the path's only collective: one NCCL sum of the confusion state
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     sampler.end()
+    expect = torch.tensor([labeled_per_step * args.steps], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(expect)
+    if int(metric.total_label) != int(expect.item()):
+        raise SystemExit(f'metric check failed: total_label {metric.total_label} != {int(expect.item())} labeled pixels evaluated')
     barrier()
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API with host buffers ----
-    # (a) the streaming evaluator (fscnn_b200.StreamingEvaluator): raw uint8 HWC images + uint8 labels in pinned
-    #     host memory, H2D on a copy stream overlapped with compute, metric state read back every step;
-    # (b) the reference's own tensor layout (normalised fp32 NCHW + int64 labels), copied and evaluated step by step.
+    # ---- the same on recipe D1 (plain random init + randn images: one class wins everywhere -- what round 1 timed) ----
+    torch.manual_seed(1234 + rank)
+    model_d1 = FastSCNN(nc, precision=args.precision).eval()
+    with torch.no_grad():
+        for name, buf in model_d1.named_buffers():
+            if name.endswith('running_mean'):
+                buf.normal_(0, 0.1)
+            elif name.endswith('running_var'):
+                buf.uniform_(0.8, 1.2)
+    model_d1.to(dev)
+    x_d1 = torch.randn(min(B, 37), 3, h, w, device=dev)
+    met_d1 = SegmentationMetric(nc, device=dev)
+    lab_d1 = labels[:x_d1.shape[0]].contiguous()
+    barrier()
+    ms_d1 = max_over_ranks(time_cuda(lambda: model_d1.evaluate(x_d1, lab_d1, met_d1), 5, warm=3))
+    value_d1 = world * x_d1.shape[0] / (ms_d1 / 1e3)
+    low_d1 = lowres_logits(model_d1._engine(dev), x_d1, h, w) if rank == 0 else None
+    del model_d1, x_d1, met_d1
+
+    # ---- BASELINE config 3: 256 images sharded over the ranks (strong scaling), fused confusion + one all-reduce ----
+    shard = 256 // world
+    xs3 = x[:shard] if shard <= B else torch.cat([x] * (-(-shard // B)))[:shard]
+    ls3 = labels[:shard] if shard <= B else torch.cat([labels] * (-(-shard // B)))[:shard]
+    xs3, ls3 = xs3.contiguous(), ls3.contiguous()
+    met3 = SegmentationMetric(nc, device=dev)
+
+    def strong_step():
+        met3.reset()
+        model.evaluate(xs3, ls3, met3)
+        met3.all_reduce()
+        return met3.get()
+
+    barrier()
+    strong_ms = max_over_ranks(time_cuda(strong_step, 3, warm=2))
+    strong = {'workload': f'strong_256: 256 images of {h}x{w} sharded over {world} GPU(s), fused metric + all-reduce + read-back',
+              'images_per_gpu': shard, 'value': shard * world / (strong_ms / 1e3), 'unit': UNIT, 'ms': strong_ms, 'n_gpus': world}
+    del xs3, ls3, met3
+
+    # ---- BASELINE config 4: TuSimple 2-class 480x640, batch 512 per GPU (weak scaling) ----
+    tus = {}
+    if not args.no_extra:
+        m2 = FastSCNN(2, precision=args.precision).eval()
+        init_recipe_d2(m2, 9)
+        m2.to(dev)
+        met2 = SegmentationMetric(2, device=dev)
+        x2 = smooth_images(512, 480, 640, dev, 77 + rank, chunk=64)
+        l2 = torch.randint(-1, 2, (512, 480, 640), device=dev, dtype=torch.int64)
+        barrier()
+        t_f32 = max_over_ranks(time_cuda(lambda: m2.evaluate(x2, l2, met2), 5, warm=2))
+        xu2 = torch.randint(0, 256, (512, 480, 640, 3), dtype=torch.uint8, device=dev)
+        lu2 = torch.randint(0, 3, (512, 480, 640), dtype=torch.uint8, device=dev)
+        barrier()
+        t_u8 = max_over_ranks(time_cuda(lambda: m2.evaluate(xu2, lu2, met2), 5, warm=2))
+        tus = {'workload': 'tusimple_480x640_b512: 2 classes, 512 images per GPU per step, forward + argmax + metric',
+               'value': 512 * world / (t_f32 / 1e3), 'unit': UNIT, 'n_gpus': world, 'scaling': 'weak',
+               'value_uint8_inputs': 512 * world / (t_u8 / 1e3),
+               'note': 'value: fp32 NCHW images + int64 labels resident in HBM; value_uint8_inputs: uint8 HWC images + uint8 labels'}
+        del m2, met2, x2, l2, xu2, lu2
+        torch.cuda.empty_cache()
+
+    # ---- the node's host->device ceiling: plain pinned copies of the e2e buffers, all ranks at once ----
     from fscnn_b200 import StreamingEvaluator
     e2e_steps = max(3, args.steps)
     nbuf = 3
     img_h = [torch.randint(0, 256, (B, h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
     lab_h = [torch.randint(0, nc + 1, (B, h, w), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]   # nc = "ignore"-like overflow label
+    img_d, lab_d = torch.empty_like(img_h[0], device=dev), torch.empty_like(lab_h[0], device=dev)
+
+    def h2d_only():
+        for i in range(nbuf):
+            img_d.copy_(img_h[i], non_blocking=True)
+            lab_d.copy_(lab_h[i], non_blocking=True)
+
+    barrier()
+    h2d_ms = max_over_ranks(time_cuda(h2d_only, 3, warm=1))
+    h2d_bytes = img_h[0].numel() + lab_h[0].numel()
+    h2d_ceiling_gbs = world * nbuf * h2d_bytes / (h2d_ms / 1e3) / 1e9
+    del img_d, lab_d
+
+    # ---- end to end through the public API with host buffers ----
+    # (a) the streaming evaluator (fscnn_b200.StreamingEvaluator): raw uint8 HWC images + uint8 labels in pinned
+    #     host memory, H2D on a copy stream overlapped with compute, metric state read back every step;
+    # (b) the reference's own tensor layout (normalised fp32 NCHW + int64 labels), copied and evaluated step by step.
     metric.reset()
     ev = StreamingEvaluator(model, metric, img_h[0], lab_h[0], device=dev)
     for i in range(3):
         ev.submit(img_h[i % nbuf], lab_h[i % nbuf])
     ev.result()
     barrier()
-    launches_e2e0 = eng.launch_count()
     sampler.begin()
     ev0.record()
     for i in range(e2e_steps):
@@ -339,13 +499,9 @@ def run_native_arm(args):
     torch.cuda.synchronize()
     sampler.end()
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(ev0.elapsed_time(ev1))
     e2e_value = world * B * e2e_steps / (e2e_ms / 1e3)
-    h2d = img_h[0].numel() + lab_h[0].numel()
+    h2d = h2d_bytes
     d2h = metric.conf_len() * 8
     del ev, img_h, lab_h
 
@@ -364,22 +520,12 @@ def run_native_arm(args):
         return metric.get()            # device -> host read of the metric state (synchronises)
 
     ref_steps = max(3, min(args.steps, 6))
-    for _ in range(2):
-        step_ref_layout()
     barrier()
-    ev0.record()
-    for _ in range(ref_steps):
-        step_ref_layout()
-    ev1.record()
-    torch.cuda.synchronize()
-    ref_ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ref_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ref_ms = float(t.item())
-    e2e_ref_layout = {'value': world * Br * ref_steps / (ref_ms / 1e3), 'unit': UNIT, 'batch_per_gpu': Br,
+    ref_ms = max_over_ranks(time_cuda(step_ref_layout, ref_steps, warm=2))
+    e2e_ref_layout = {'value': world * Br / (ref_ms / 1e3), 'unit': UNIT, 'batch_per_gpu': Br,
                       'h2d_bytes_per_step': int(xh.numel() * 4 + lh.numel() * 8), 'd2h_bytes_per_step': int(d2h),
                       'steps': ref_steps, 'host_buffers': 'pinned fp32 NCHW images + int64 labels, no copy/compute overlap'}
+    del xh, lh, xd, ld
 
     out = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -388,15 +534,28 @@ def run_native_arm(args):
         'config': {'workload': f'cityscapes_eval_nc{nc}_{h}x{w}_fwd_argmax_metric', 'batch_per_gpu': B,
                    'global_batch': B * world, 'precision': args.precision, 'l2_policy': 'inputs_exceed_l2',
                    'input_bytes_per_step_per_gpu': int(x.numel() * 4 + labels.numel() * 8),
-                   'parallelism': f'dp{world}', 'cpu_affinity': numa, 'weights': 'random-init, randomised BN stats'},
+                   'parallelism': f'dp{world}', 'cpu_affinity': numa,
+                   'weights': 'recipe D2: variance-preserving random weights, randomised BN statistics, calibrated classifier bias',
+                   'inputs': 'multi-scale smooth noise images (fp32 NCHW), int64 labels uniform in [-1, nc)',
+                   'classes_present': classes_present, 'largest_class_fraction': largest_class,
+                   'timed_region': 'K x (forward + fused upsample/argmax/metric) + NCCL all-reduce of the confusion state + '
+                                   'device->host read + pixAcc/mIoU'},
+        'value_recipe_d1': value_d1,
+        'pixAcc_mIoU': [float(pix_acc), float(miou)],
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps, 'api': 'fscnn_b200.StreamingEvaluator.submit',
+                'h2d_gbs': e2e_value * h2d / B / 1e9, 'h2d_ceiling_gbs': h2d_ceiling_gbs,
+                'frac_of_h2d_ceiling': (e2e_value * h2d / B / 1e9) / h2d_ceiling_gbs,
                 'host_buffers': 'pinned uint8 HWC images (ToTensor+Normalize fused into the stem) + uint8 labels; '
-                                'H2D on a copy stream overlaps compute; metric state copied to the host every step'},
+                                'H2D on a copy stream overlaps compute; metric state copied to the host every step; '
+                                'h2d_ceiling_gbs = the same buffers copied with plain cudaMemcpyAsync by all ranks at once, no compute'},
         'e2e_reference_layout': e2e_ref_layout,
+        'strong_256': strong,
         'gpu_launches': int(launches),
         'clocks': clocks,
     }
+    if tus:
+        out['tusimple_480x640_b512'] = tus
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -416,8 +575,6 @@ def run_native_arm(args):
         names = eng.stage_names()
         import ctypes as C
         from fscnn_b200 import native
-        need = C.c_size_t()
-        native.check(eng.lib.fscnn_workspace_bytes(eng._ctx, B, h, w, C.byref(need)))
         tap = native.Tap()
         native.check(eng.lib.fscnn_tap_info(eng._ctx, B, h, w, b'l2d.conv', C.byref(tap)))
         mb = tap.n                                   # images per launch (the library's micro-batch)
@@ -425,66 +582,40 @@ def run_native_arm(args):
         eng.forward_range(xs, 0, len(names) - 1)     # fill every stage tensor once
         reps = 5
         table = []
-        fused_front = args.precision == 'bf16'      # bf16: stem + dsconv1 run as ONE kernel (l2d_front_tc.cu)
+        fused_front = args.precision == 'bf16'      # bf16: stem + dsconv1 run as ONE kernel
         for i, name in enumerate(names):
             if fused_front and name == 'l2d.dsconv1':
                 continue
             j = i + 1 if (fused_front and name == 'stem') else i
-            eng.forward_range(xs, i, j)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                eng.forward_range(xs, i, j)
-            b.record()
-            torch.cuda.synchronize()
-            table.append(('stem+l2d.dsconv1' if j != i else name, a.elapsed_time(b) / reps / mb * 1e3))   # microseconds per image
-        mask = torch.empty((mb, h, w), dtype=torch.uint8, device=dev)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        full_us = None
-        for timed in (False, True):
-            if timed:
-                a.record()
-            for _ in range(reps):
-                model.evaluate(xs, labels[:mb].contiguous(), metric, mask=None)
-            if timed:
-                b.record()
-        torch.cuda.synchronize()
-        full_us = a.elapsed_time(b) / reps / mb * 1e3
-        stage_sum = sum(t for _, t in table)
-        tail_us = max(full_us - stage_sum, 0.0)
-        table.append(('up8+argmax+metric', tail_us))
-        # the fused argmax prunes classes that provably cannot win inside a pixel block, so its time depends on the logits:
-        # re-time it with a zeroed classifier head (all classes tied everywhere => nothing can be pruned) as the worst case
-        worst = FastSCNN(nc, precision=args.precision).eval()
-        wsd = {k: v.clone() for k, v in model.state_dict().items()}
-        wsd['classifier.conv.1.weight'].zero_()
-        wsd['classifier.conv.1.bias'].zero_()
-        worst.load_state_dict(wsd)
-        worst.to(dev)
-        for timed in (False, True):
-            if timed:
-                a.record()
-            for _ in range(reps):
-                worst.evaluate(xs, labels[:mb].contiguous(), metric, mask=None)
-            if timed:
-                b.record()
-        torch.cuda.synchronize()
-        tail_worst_us = max(a.elapsed_time(b) / reps / mb * 1e3 - stage_sum, 0.0)
-        del worst
-        # ... and on the labels: the histogram aggregates runs of equal (label, prediction) pairs before its shared-memory
-        # atomics; uniform-random labels (the timed workload) are its worst case, a single dominant class its best
-        dom = torch.zeros_like(labels[:mb])
+            t = time_cuda(lambda: eng.forward_range(xs, i, j), reps, warm=1)
+            table.append(('stem+l2d.dsconv1' if j != i else name, t / mb * 1e3))   # microseconds per image
+        # the tail kernel (x8 upsample + argmax + metric counting) with its OWN event pair, on the logits of this batch; its time
+        # depends on the logits (exact class pruning) and on the labels (run-length aggregated counting), so both extremes are timed
+        lab_mb = labels[:mb].contiguous()
+        conf = torch.zeros(eng.conf_len(), dtype=torch.int64, device=dev)
+        low_d2 = lowres_logits(eng, xs, h, w)
+        hl_, wl_ = low_d2.shape[1], low_d2.shape[2]
+
+        def tail_us(low, lab, **kw):
+            n_ = low.shape[0]
+            return time_cuda(lambda: eng.upsample_argmax(low, h, w, labels=lab[:n_], conf=conf, want_mask=False, **kw), reps, warm=1) / n_ * 1e3
+
+        tail = tail_us(low_d2, lab_mb)
+        checker = ((torch.arange(hl_, device=dev)[:, None] + torch.arange(wl_, device=dev)[None, :]) % 2 * 2 - 1).float()
+        low_adv = torch.zeros_like(low_d2)
+        low_adv[..., :nc] = checker[None, :, :, None] * torch.arange(nc, device=dev).float()
+        dom = torch.zeros_like(lab_mb)
         dom[:, ::16, ::16] = -1
-        for timed in (False, True):
-            if timed:
-                a.record()
-            for _ in range(reps):
-                model.evaluate(xs, dom, metric, mask=None)
-            if timed:
-                b.record()
-        torch.cuda.synchronize()
-        tail_dom_us = max(a.elapsed_time(b) / reps / mb * 1e3 - stage_sum, 0.0)
-        del dom
+        tail_extra = {
+            'us_per_image_recipe_d1_logits': tail_us(low_d1, lab_mb),
+            'us_per_image_no_class_can_be_pruned': tail_us(low_adv, lab_mb),       # class order flips between neighbouring taps
+            'us_per_image_exhaustive_flag': tail_us(low_d2, lab_mb, exhaustive=True),
+            'us_per_image_dominant_class_labels': tail_us(low_d2, dom),
+            'us_per_image_mask_only_uint8': time_cuda(lambda: eng.upsample_argmax(low_d2, h, w), reps, warm=1) / mb * 1e3,
+        }
+        table.append(('up8+argmax+metric', tail))
+        del low_adv, dom
+        full_us = time_cuda(lambda: model.evaluate(xs, lab_mb, metric), reps, warm=1) / mb * 1e3
         model_by_name = {s['stage']: s for s in stages}
         if fused_front:   # plan-P bytes of both stages (the denominator is not changed); the fused kernel's own traffic beside it
             a_, b_ = model_by_name['stem'], model_by_name['l2d.dsconv1']
@@ -492,14 +623,13 @@ def run_native_arm(args):
                                                  'fused_bytes': 3.0 * h * w * 4 + ((((h - 3) // 2 + 1) - 1) // 2 + 1) * ((((w - 3) // 2 + 1) - 1) // 2 + 1) * 48.0 * es}
         rows = []
         for name, us in table:
-            m = model_by_name.get(name if name != 'stem' else 'stem')
+            m = model_by_name.get(name)
             if m is None:
                 continue
             rows.append({'stage': name, 'us_per_image': us, 'gbs': m['bytes'] / us / 1e3, 'tflops': m['flops'] / us / 1e6,
                          'bytes': m['bytes'], 'flops': m['flops']})
             if name == 'up8+argmax+metric':
-                rows[-1]['us_per_image_no_pruning'] = tail_worst_us
-                rows[-1]['us_per_image_dominant_class_labels'] = tail_dom_us
+                rows[-1].update(tail_extra)
                 # plan-P counts the low-res logits + a uint8 mask; this run is the fused-metric mode, which reads the
                 # caller's labels instead of writing a mask (int64 in the reference tensor layout): the bytes this launch must move
                 run_bytes = float(m['bytes'] - h * w * 1 + h * w * labels.element_size())
@@ -509,13 +639,17 @@ def run_native_arm(args):
                 rows[-1]['fused_bytes'] = m['fused_bytes']
                 rows[-1]['fused_gbs'] = m['fused_bytes'] / us / 1e3
         out['stages'] = rows
+        out['stage_sum_us_per_image'] = sum(r['us_per_image'] for r in rows)
+        out['full_step_us_per_image_one_launch_set'] = full_us
         top = dict(max(rows, key=lambda r: r['us_per_image']))
-        alu_note = ''
+        note = ''
         if 'bytes_fused_metric_mode' in top:   # the tail kernel: algorithmic bytes of the mode that was run (labels read, no mask written)
             top['bytes'], top['gbs'] = top['bytes_fused_metric_mode'], top['gbs_fused_metric_mode']
-            alu_note = ('ALU-bound kernel (fp32 bilinear interpolation + compare / select of 19 classes x 2 Mpixel on the CUDA cores, exact '
-                        'class pruning); algorithmic bytes = low-res logits + the int64 labels the fused-metric mode reads (plan-P counts a '
-                        'uint8 mask instead: see stages[].bytes)')
+            note = ('algorithmic bytes = low-res logits + the int64 labels the fused-metric mode reads (plan-P counts a uint8 mask '
+                    'instead: see stages[].bytes); timed with its own CUDA-event pair on this batch\'s logits')
+        elif 'fused_bytes' in top:
+            note = ('plan-P algorithmic bytes of the two stages this kernel fuses (SURVEY 8d); the fused kernel itself moves '
+                    f"{top['fused_bytes'] / 1e6:.1f} MB per image (stages[].fused_gbs): the stem output never reaches HBM")
         hbm_time = top['bytes'] / (peaks['hbm_gbs'] * 1e9)
         tens_time = top['flops'] / (peaks['bf16_tflops'] * 1e12)
         if args.precision == 'bf16' and tens_time > hbm_time:
@@ -530,32 +664,25 @@ def run_native_arm(args):
             rec = json.load(open(tpath)).get(args.precision, {}).get(top['stage'])
             if rec:
                 traffic = rec['dram_bytes_per_image'] * mb
-        roof.update({'kernel': top['stage'], 'traffic': traffic, 'algorithmic_bytes_per_launch': top['bytes'] * mb,
+        roof.update({'kernel': top['stage'], 'traffic': traffic, 'traffic_source': 'profiles/kernel_traffic.json (ncu --set full capture, scaled to this launch)',
+                     'algorithmic_bytes_per_launch': top['bytes'] * mb,
                      'peak_source': peaks['source'], 'images_per_launch': mb,
                      'us_per_launch': top['us_per_image'] * mb,
                      'note': 'fp32 path: this kernel is FP32-FMA bound on CUDA cores; fma_frac = achieved fp32 TFLOP/s / '
-                             '(148 SM x 128 lanes x 2 x sm_mhz)' if args.precision == 'fp32' else alu_note})
+                             '(148 SM x 128 lanes x 2 x sm_mhz)' if args.precision == 'fp32' else note})
         if args.precision == 'fp32':
             mhz = (clocks or {}).get('sm_mhz') or peaks['sm_max_mhz']
             roof['fma_frac'] = top['tflops'] / (148 * 128 * 2 * mhz * 1e6 / 1e12)
         out['roofline'] = roof
 
-    if not args.no_extra and rank == 0:
+    if not args.no_extra:
         # same workload with the camera / dataset byte layout resident in HBM (uint8 HWC images, ToTensor+Normalize fused into
         # the first kernel, uint8 labels): 8.4 MB per image instead of the reference tensor layout's 42 MB
         xu = torch.randint(0, 256, (B, h, w, 3), dtype=torch.uint8, device=dev)
         lu = torch.randint(0, nc + 1, (B, h, w), dtype=torch.uint8, device=dev)
         metu = SegmentationMetric(nc, device=dev)
-        for _ in range(3):
-            model.evaluate(xu, lu, metu)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(10):
-            model.evaluate(xu, lu, metu)
-        b.record()
-        torch.cuda.synchronize()
-        out['device_resident_uint8_inputs'] = {'value': B * 10 / (a.elapsed_time(b) / 1e3), 'unit': UNIT, 'steps': 10, 'n_gpus': 1,
+        t = time_cuda(lambda: model.evaluate(xu, lu, metu), 10, warm=3)
+        out['device_resident_uint8_inputs'] = {'value': B / (t / 1e3), 'unit': UNIT, 'steps': 10, 'n_gpus': 1,
                                                'note': 'uint8 HWC images + uint8 labels resident in HBM, rank 0'}
         del xu, lu, metu
         model.evaluate(x, labels, metric)      # back to the fp32 NCHW input format for what follows
@@ -566,16 +693,8 @@ def run_native_arm(args):
         m32.load_state_dict(model.state_dict())
         m32.to(dev)
         met32 = SegmentationMetric(nc, device=dev)
-        for _ in range(2):
-            m32.evaluate(x, labels, met32)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(5):
-            m32.evaluate(x, labels, met32)
-        b.record()
-        torch.cuda.synchronize()
-        out['fp32_exact'] = {'value': B * 5 / (a.elapsed_time(b) / 1e3), 'unit': UNIT, 'steps': 5, 'n_gpus': 1,
+        t = time_cuda(lambda: m32.evaluate(x, labels, met32), 5, warm=2)
+        out['fp32_exact'] = {'value': B / (t / 1e3), 'unit': UNIT, 'steps': 5, 'n_gpus': 1,
                              'note': 'fp32 storage + fp32 FMA path on rank 0 (logits within 1e-4 of the reference)'}
         del m32, met32
 
@@ -585,37 +704,30 @@ def run_native_arm(args):
         for _ in range(3):
             model.predict(xs1, out=mask1)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
             model.predict(xs1, out=mask1)
-        for _ in range(20):
-            g.replay()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(200):
-            g.replay()
-        b.record()
-        torch.cuda.synchronize()
-        out['latency_batch1_ms'] = a.elapsed_time(b) / 200
+        out['latency_batch1_ms'] = time_cuda(graph.replay, 1000, warm=200)        # 200 warm + 1000 timed replays
+        # what the reference's callers run (eval.py:43-45, demo.py:46-48): eager model(image) then torch.argmax, batch 1, no graph;
+        # and the fused eager call.  Host-side cost per call (parameter fingerprint, ctypes, tensor-map encodes) is inside.
+        out['latency_batch1_eager_ms'] = {
+            'forward_then_torch_argmax': time_cuda(lambda: torch.argmax(model(xs1)[0], 1), 100, warm=20),
+            'predict': time_cuda(lambda: model.predict(xs1, out=mask1), 200, warm=20),
+            'note': 'eager (no CUDA graph), synchronised at both ends; forward_then_torch_argmax materialises the 159 MB full-resolution logits like the reference',
+        }
 
     if not args.no_extra:
-        # BASELINE.json's other inference shapes (2-class TuSimple 480x640 and drivable-area 360x640), device-resident, rank 0
+        # BASELINE.json's other inference shape (2-class drivable-area 360x640), device-resident, rank 0
         extra = []
-        for enc, eh, ew, eb in ((2, 480, 640, 128), (2, 360, 640, 128)):
-            em = FastSCNN(enc, precision=args.precision).eval().to(dev)
-            ex = torch.randn(eb, 3, eh, ew, device=dev)
+        for enc, eh, ew, eb in ((2, 360, 640, 128),):
+            em = FastSCNN(enc, precision=args.precision).eval()
+            init_recipe_d2(em, 11)
+            em.to(dev)
+            ex = smooth_images(eb, eh, ew, dev, 5, chunk=64)
             el = torch.randint(-1, enc, (eb, eh, ew), device=dev, dtype=torch.int64)
             emet = SegmentationMetric(enc, device=dev)
-            for _ in range(3):
-                em.evaluate(ex, el, emet)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(10):
-                em.evaluate(ex, el, emet)
-            b.record()
-            torch.cuda.synchronize()
-            extra.append({'workload': f'eval_nc{enc}_{eh}x{ew}_fwd_argmax_metric', 'batch': eb, 'value': eb * 10 / (a.elapsed_time(b) / 1e3),
+            t = time_cuda(lambda: em.evaluate(ex, el, emet), 10, warm=3)
+            extra.append({'workload': f'eval_nc{enc}_{eh}x{ew}_fwd_argmax_metric', 'batch': eb, 'value': eb / (t / 1e3),
                           'unit': UNIT, 'n_gpus': 1, 'precision': args.precision})
             del em, ex, el, emet
         # the deployed camera pipeline (reference export_onnx_fixed.EndToEndFastSCNN): 640x360 uint8 frames -> 1024x1024
@@ -623,19 +735,20 @@ def run_native_arm(args):
         from models.end_to_end import EndToEndFastSCNN
         cam = EndToEndFastSCNN(FastSCNN(2, precision=args.precision).eval().to(dev), input_size=(640, 360), base_size=1024).eval()
         frames = torch.randint(0, 256, (64, 3, 360, 640), dtype=torch.uint8, device=dev)
-        for _ in range(2):
-            cam(frames)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(5):
-            cam(frames)
-        b.record()
-        torch.cuda.synchronize()
-        extra.append({'workload': 'camera_frames_640x360_via_1024x1024_softmax_nc2', 'batch': 64, 'value': 64 * 5 / (a.elapsed_time(b) / 1e3),
+        t = time_cuda(lambda: cam(frames), 5, warm=2)
+        extra.append({'workload': 'camera_frames_640x360_via_1024x1024_softmax_nc2', 'batch': 64, 'value': 64 / (t / 1e3),
                       'unit': 'frames/s', 'n_gpus': 1, 'precision': args.precision})
         del cam, frames
         out['other_workloads'] = extra
+
+    if world == 1 and not args.no_eager:
+        # the honest GPU comparator: the reference's op sequence run eagerly through cuDNN / ATen on this same GPU
+        torch.cuda.empty_cache()
+        out['gpu_eager_baseline'] = gpu_eager_baseline(dev, h, w, nc)
+        out['gpu_eager_baseline']['note'] = ('reference op sequence (ATen-functional port, unfolded BN, NCHW fp32 tensors) + torch.argmax, '
+                                             'cuDNN eager on this GPU, cudnn.benchmark on, synchronised; none of this repo\'s kernels')
+        best = max(v['images_per_s'] for k, v in out['gpu_eager_baseline'].items() if isinstance(v, dict))
+        out['gpu_eager_baseline']['speedup_device_resident_vs_best_eager'] = value / best
 
     if world == 1 and not args.no_cpu_baseline:
         rate, done, el, cores, threads = cpu_reference_rate(h, w, nc, 12.0, 1)

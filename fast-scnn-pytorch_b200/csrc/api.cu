@@ -10,7 +10,6 @@
 #include <vector>
 
 #include "../../include/fscnn_b200.h"
-#include <cstdlib>
 #include "kernels.h"
 
 using namespace fscnn;
@@ -313,7 +312,6 @@ struct Loader {
     // bf16 contexts only: depthwise tables become bf16-representable with error-diffused rounding (fold.cu)
     void round_dw(const fscnn_ctx* c, float* wd, int ch) {
         if (err || c->prec != FSCNN_PREC_BF16) return;
-        if (getenv("FSCNN_DW_ROUND_NEAREST")) return;   // experiment switch: plain round-to-nearest in the packers instead
         if (launch_dw_round_bf16(wd, ch, s) != cudaSuccess)
             err = fail(FSCNN_ECUDA, "depthwise rounding launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -876,8 +874,8 @@ int fscnn_upsample_argmax(const float* d_low_logits, int nc, int ncp, int n, int
     if (!d_low_logits || (!d_mask && !d_labels)) return fail(FSCNN_EINVAL, "null device pointer");
     if (nc < 1 || nc > 256 || ncp < nc || (ncp & 3)) return fail(FSCNN_EINVAL, "bad class count %d (padded %d)", nc, ncp);
     if (n < 1 || hl < 1 || wl < 1 || h < 1 || w < 1) return fail(FSCNN_EINVAL, "bad shape");
-    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1))
-        return fail(FSCNN_EINVAL, "upsample ratio must be >= 7 (%dx%d -> %dx%d)", hl, wl, h, w);
+    if ((double)(hl - 1) * 7.3 > (double)(h - 1) || (double)(wl - 1) * 7.3 > (double)(w - 1))
+        return fail(FSCNN_EINVAL, "upsample ratio must be >= 7.3 (%dx%d -> %dx%d)", hl, wl, h, w);
     if (d_mask && !valid_label_dtype(mask_dtype)) return fail(FSCNN_EINVAL, "bad mask dtype %d", mask_dtype);
     if (d_labels && (!valid_label_dtype(label_dtype) || !d_conf)) return fail(FSCNN_EINVAL, "labels need a valid dtype and d_conf");
     if ((reinterpret_cast<uintptr_t>(d_low_logits) & 15) || !vec4_aligned(d_mask, mask_dtype) || !vec4_aligned(d_labels, label_dtype))

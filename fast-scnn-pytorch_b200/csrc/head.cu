@@ -109,52 +109,178 @@ __device__ __forceinline__ unsigned int cell_survivors(const float* __restrict__
     return ~elim & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
 }
 
-// Finite-logit argmax over the candidate classes `cand` (ascending, so `v > best` keeps the first maximal class) for a
-// thread's 8x4 output pixels.  Rows i < K interpolate between the horizontally-lerped staged rows 0/1, rows i >= K
-// between rows 1/2 (K is warp-uniform and a template constant, so the vertical step is one FMUL + one FFMA per pixel).
-template <int K>
-__device__ __forceinline__ void argmax_fast(const float* __restrict__ Ls, unsigned int cand, const int (&ro)[3], const int (&co)[3],
-                                            const float (&wx)[4][3], const float (&wy)[8][3], float (&best)[8][4], int (&bidx)[8][4]) {
+// One 4-row half of a thread's 8x4 output block: finite-logit argmax over the candidate classes `cand` (ascending, so
+// `v > best` keeps the first maximal class).  Rows i < KH interpolate between the horizontally-lerped staged rows 0/1,
+// rows i >= KH between rows 1/2 (KH is warp-uniform and a template constant, so the vertical step is one FMUL + one FFMA
+// per pixel and unused staged rows are never read).  The winning class indices are kept packed, one byte per pixel, one
+// register per row (PRMT replaces the winner's byte), which is also the uint8 mask word the thread stores.
+template <int KH>
+__device__ __forceinline__ void argmax_half_fast(const float* __restrict__ Ls, unsigned int cand, const int (&ro)[3], const int (&co)[3],
+                                                 const float (&wx)[4][3], const float (&wa)[4], const float (&wb)[4], unsigned int (&idx)[4]) {
+    float best[4][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i) {
+        idx[i] = 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { best[i][j] = -INFINITY; bidx[i][j] = 0; }
-    const int o00 = ro[0] + co[0], o01 = ro[0] + co[1], o02 = ro[0] + co[2];
-    const int o10 = ro[1] + co[0], o11 = ro[1] + co[1], o12 = ro[1] + co[2];
-    const int o20 = ro[2] + co[0], o21 = ro[2] + co[1], o22 = ro[2] + co[2];
+        for (int j = 0; j < 4; ++j) best[i][j] = -INFINITY;
+    }
     while (cand) {
-        const int c = __ffs(cand) - 1;
+        const unsigned int c = __ffs(cand) - 1;
         cand &= cand - 1u;
         const float* lc = Ls + c * kTR * kTC;
-        float v[3][3];
-        v[0][0] = lc[o00]; v[0][1] = lc[o01]; v[0][2] = lc[o02];
-        v[1][0] = lc[o10]; v[1][1] = lc[o11]; v[1][2] = lc[o12];
-        if (K < 8) { v[2][0] = lc[o20]; v[2][1] = lc[o21]; v[2][2] = lc[o22]; }
         float hrow[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            if (K == 8 && r == 2) continue;          // the third staged row is never used
+            if ((KH == 4 && r == 2) || (KH == 0 && r == 0)) continue;      // staged rows this half never uses
+            const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v[r][2], fmaf(wx[j][1], v[r][1], wx[j][0] * v[r][0]));
+            for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v2, fmaf(wx[j][1], v1, wx[j][0] * v0));
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float wa = i < K ? wy[i][0] : wy[i][1], wb = i < K ? wy[i][1] : wy[i][2];
+        for (int i = 0; i < 4; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float val = fmaf(wb, i < K ? hrow[1][j] : hrow[2][j], wa * (i < K ? hrow[0][j] : hrow[1][j]));
-                if (val > best[i][j]) { best[i][j] = val; bidx[i][j] = c; }
+                const float val = fmaf(wb[i], i < KH ? hrow[1][j] : hrow[2][j], wa[i] * (i < KH ? hrow[0][j] : hrow[1][j]));
+                if (val > best[i][j]) {
+                    best[i][j] = val;
+                    idx[i] = __byte_perm(idx[i], c, j == 0 ? 0x3214 : (j == 1 ? 0x3240 : (j == 2 ? 0x3410 : 0x4210)));
+                }
             }
         }
     }
 }
 
-// MODE 0: write NCHW fp32 logits.  MODE 1: argmax mask (+ optional confusion counts).
-template <int MODE>
+// The same half with torch.argmax's full semantics (NaN is maximal, the first one wins) over all classes, reading exactly
+// the 2 x 2 taps ATen reads per pixel -- a non-finite value under a zero weight of the 3-tap form would poison pixels torch
+// keeps finite.  hx = 1 - lx > 0 always, so a zero first weight marks the columns that use the second tap pair; sy marks
+// the rows that do.  Used when a staged logit is NaN / Inf or there are more classes than the candidate mask holds.
+__device__ __forceinline__ void argmax_half_generic(const float* __restrict__ Ls, int nc, const int (&ro)[3], const int (&co)[3],
+                                                    const float (&wx)[4][3], const float (&wa)[4], const float (&wb)[4],
+                                                    unsigned int sy_mask, unsigned int (&idx)[4]) {
+    float best[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        idx[i] = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) best[i][j] = 0.f;
+    }
+    for (int c = 0; c < nc; ++c) {
+        const float* lc = Ls + c * kTR * kTC;
+        float hrow[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool sx = wx[j][0] == 0.f;
+                hrow[r][j] = fmaf(sx ? wx[j][2] : wx[j][1], sx ? v2 : v1, (sx ? wx[j][1] : wx[j][0]) * (sx ? v1 : v0));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool sy = (sy_mask >> i) & 1u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float val = fmaf(wb[i], sy ? hrow[2][j] : hrow[1][j], wa[i] * (sy ? hrow[1][j] : hrow[0][j]));
+                // first max wins; NaN beats everything except an earlier NaN
+                const bool upd = (c == 0) || (!(val <= best[i][j]) && (best[i][j] == best[i][j]));
+                if (upd) {
+                    best[i][j] = val;
+                    idx[i] = __byte_perm(idx[i], (unsigned int)c, j == 0 ? 0x3214 : (j == 1 ? 0x3240 : (j == 2 ? 0x3410 : 0x4210)));
+                }
+            }
+        }
+    }
+}
+
+// predicated shared-memory reduction: no branch, so 32 lanes with different run lengths stay converged
+__device__ __forceinline__ void red_shared_if(bool p, uint32_t addr, unsigned int v) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((int)p) : "memory");
+}
+
+// MODE 0: write NCHW fp32 logits (forward()'s API-parity output).
 __global__ void __launch_bounds__(kThreads, 2)
-upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restrict__ out_logits, void* __restrict__ mask,
-                int mask_dtype, const void* __restrict__ labels, int label_dtype, unsigned long long* __restrict__ conf,
-                int hl, int wl, int H, int W, int use_smem_hist, int prune) {
+upsample_logits_kernel(const float* __restrict__ low, int nc, int ncp, float* __restrict__ out_logits, int hl, int wl, int H, int W) {
+    extern __shared__ __align__(16) float dynsm[];
+    float* Ls = dynsm;                                            // [nc][kTR][kTC]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z;
+    const int yb = blockIdx.y * 64, xb = blockIdx.x * 128;
+    const float scy = H > 1 ? (float)(hl - 1) / (float)(H - 1) : 0.f;
+    const float scx = W > 1 ? (float)(wl - 1) / (float)(W - 1) : 0.f;
+    const int rb = min((int)(scy * (float)yb), hl - 1);          // first staged low-res row / column
+    const int cb = min((int)(scx * (float)xb), wl - 1);
+    {
+        const int nv = ncp >> 2;
+        for (int i = tid; i < kTR * kTC * nv; i += kThreads) {
+            const int v = i % nv, px = i / nv;
+            const int r = px / kTC, q = px % kTC;
+            const int rr = min(rb + r, hl - 1), qq = min(cb + q, wl - 1);
+            const float4 t = __ldg(reinterpret_cast<const float4*>(low + (((size_t)n * hl + rr) * wl + qq) * ncp) + v);
+            const int c = 4 * v;
+            float* dst = Ls + (c * kTR + r) * kTC + q;
+            dst[0] = t.x;
+            if (c + 1 < nc) dst[kTR * kTC] = t.y;
+            if (c + 2 < nc) dst[2 * kTR * kTC] = t.z;
+            if (c + 3 < nc) dst[3 * kTR * kTC] = t.w;
+        }
+    }
+    __syncthreads();
+    const int x0 = xb + lane * 4, y0 = yb + warp * 8;
+    if (x0 >= W || y0 >= H) return;
+    // Separable weights over the 3 x 3 staged taps of the thread's 8 x 4 block; every pixel reads exactly the 2 x 2 taps ATen
+    // reads (a non-finite logit under a zero weight would poison pixels torch keeps finite): hx = 1 - lx > 0 always, so
+    // `sx` / `sy` pick the tap pair explicitly.  Horizontal lerp first, then vertical, like ATen.
+    float hx[4], lx[4], hy[8], ly[8];
+    bool sx[4], sy[8];
+    const int c0 = min((int)(scx * (float)x0), wl - 1), r0 = min((int)(scy * (float)y0), hl - 1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float fx = scx * (float)(x0 + j);
+        const int q = min((int)fx, wl - 1);
+        lx[j] = fx - (float)q; hx[j] = 1.f - lx[j];
+        sx[j] = (q - c0) != 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float fy = scy * (float)(y0 + i);
+        const int r = min((int)fy, hl - 1);
+        ly[i] = fy - (float)r; hy[i] = 1.f - ly[i];
+        sy[i] = (r - r0) != 0;
+    }
+    const int base = (r0 - rb) * kTC + (c0 - cb);     // the staged tile holds clamped copies beyond the border (ATen's x1 = min(x0 + 1, w - 1))
+    for (int c = 0; c < nc; ++c) {
+        const float* lc = Ls + c * kTR * kTC + base;
+        float hrow[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float v0 = lc[r * kTC], v1 = lc[r * kTC + 1], v2 = lc[r * kTC + 2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(lx[j], sx[j] ? v2 : v1, hx[j] * (sx[j] ? v1 : v0));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (y0 + i >= H) continue;
+            float val[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) val[j] = fmaf(ly[i], sy[i] ? hrow[2][j] : hrow[1][j], hy[i] * (sy[i] ? hrow[1][j] : hrow[0][j]));
+            float* o = out_logits + (((size_t)n * nc + c) * H + (y0 + i)) * W + x0;
+            if ((W & 3) == 0) {
+                __stcs(reinterpret_cast<float4*>(o), make_float4(val[0], val[1], val[2], val[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x0 + j < W) o[j] = val[j];
+            }
+        }
+    }
+}
+
+// argmax mask (+ optional confusion counts) straight from the low-resolution logits.
+__global__ void __launch_bounds__(kThreads, 3)
+upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __restrict__ mask, int mask_dtype,
+                       const void* __restrict__ labels, int label_dtype, unsigned long long* __restrict__ conf,
+                       int hl, int wl, int H, int W, int use_smem_hist, int prune) {
     extern __shared__ __align__(16) float dynsm[];
     float* Ls = dynsm;                                            // [nc][kTR][kTC]
     unsigned int* hist = reinterpret_cast<unsigned int*>(dynsm + nc * kTR * kTC);
@@ -168,12 +294,21 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     const float scx = W > 1 ? (float)(wl - 1) / (float)(W - 1) : 0.f;
     const int rb = min((int)(scy * (float)yb), hl - 1);          // first staged low-res row / column
     const int cb = min((int)(scx * (float)xb), wl - 1);
-    const bool do_hist = (MODE == 1) && (labels != nullptr);
+    const bool do_hist = labels != nullptr;
+    const int x0 = xb + lane * 4, y0 = yb + warp * 8;
+    const bool live = (x0 < W) && (y0 < H);
 
+    if (live && do_hist) {   // pull this thread's label rows towards L1 while the logits are staged and the classes compared
+        const size_t esz = label_dtype == FSCNN_U8 ? 1 : (label_dtype == FSCNN_I32 ? 4 : 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (y0 + i < H)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(labels) + (((size_t)n * H + (y0 + i)) * W + x0) * esz));
+    }
     // stage the low-res tile class-major: one float4 (4 classes of one pixel) per item, independent loads in flight
     int nonfinite = 0;
     float amax = 0.f;
-    if (MODE == 1 && tid == 0) tile_amax = 0u;
+    if (tid == 0) { tile_amax = 0u; blk_labeled = 0u; blk_correct = 0u; }
     {
         const int nv = ncp >> 2;
         for (int i = tid; i < kTR * kTC * nv; i += kThreads) {
@@ -183,7 +318,7 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             const float4 t = __ldg(reinterpret_cast<const float4*>(low + (((size_t)n * hl + rr) * wl + qq) * ncp) + v);
             const int c = 4 * v;
             nonfinite |= !(fabsf(t.x) <= 3.4e38f) | !(fabsf(t.y) <= 3.4e38f) | !(fabsf(t.z) <= 3.4e38f) | !(fabsf(t.w) <= 3.4e38f);
-            if (MODE == 1) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
             float* dst = Ls + (c * kTR + r) * kTC + q;
             dst[0] = t.x;
             if (c + 1 < nc) dst[kTR * kTC] = t.y;
@@ -191,190 +326,136 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
             if (c + 3 < nc) dst[3 * kTR * kTC] = t.w;
         }
     }
-    if (do_hist) {
-        if (use_smem_hist)
-            for (int i = tid; i < (nc + 1) * (nc + 1); i += kThreads) hist[i] = 0u;
-        if (tid == 0) { blk_labeled = 0u; blk_correct = 0u; }
-    }
-    // NaN / Inf among the staged logits (padding classes are finite zeros) selects the exact-semantics slow loop; so do
+    if (do_hist && use_smem_hist)
+        for (int i = tid; i < (nc + 1) * (nc + 1); i += kThreads) hist[i] = 0u;
+    // NaN / Inf among the staged logits (padding classes are finite zeros) selects the exact-semantics generic loop; so do
     // more classes than the candidate bit mask holds
     const bool slow = (__syncthreads_or(nonfinite) != 0) || nc > 32;
-    if (MODE == 1 && !slow) {
-        // the tile's largest |logit| (non-negative floats order like their bit patterns), then one cell per thread
+    if (!slow) {
+        // the tile's largest |logit| (non-negative floats order like their bit patterns), then one cell per thread over the
+        // cells this tile's pixels interpolate in
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         if (lane == 0) atomicMax(&tile_amax, __float_as_uint(amax));
         __syncthreads();
         const float margin = 2e-6f * __uint_as_float(tile_amax) + 1e-30f;
-        if (tid < kCR * kCC)      // prune == 0 (tests, worst-case timing): every class stays a candidate everywhere
-            cellmask[tid] = prune ? cell_survivors(Ls, nc, (tid / kCC) * kTC + (tid % kCC), margin) : (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+        const int rn = min(min((int)(scy * (float)min(yb + 63, H - 1)), hl - 1) - rb + 1, kCR);
+        const int qn = min(min((int)(scx * (float)min(xb + 127, W - 1)), wl - 1) - cb + 1, kCC);
+        if (tid < rn * qn) {      // prune == 0 (tests, worst-case timing): every class stays a candidate everywhere
+            const int R = tid / qn, Q = tid - R * qn;
+            cellmask[R * kCC + Q] = prune ? cell_survivors(Ls, nc, R * kTC + Q, margin) : (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+        }
         __syncthreads();
     }
+    if (!live && !do_hist) return;
 
-    const int x0 = xb + lane * 4, y0 = yb + warp * 8;
-    if (x0 >= W || y0 >= H) {
-        if (!do_hist) return;
-    }
-    // Separable interpolation weights, class-invariant: column j mixes the three staged columns c0..c0+2 with
-    // (hx, lx, 0) or (0, hx, lx); row i mixes the three staged rows likewise.  A zero weight adds an exact 0, so for
-    // finite logits each pixel is fma(lx, b, hx*a) of its own two taps -- horizontal first, then vertical, like ATen.
-    float wx[4][3], wy[8][3];
-    const int c0 = min((int)(scx * (float)x0), wl - 1);
-    bool second_col = false;      // some column of this thread interpolates inside the cell to the right of c0's
+    unsigned int idx8[8];      // winning class of the thread's 8 rows x 4 columns, one byte per pixel
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float fx = scx * (float)(x0 + j);
-        const int q = min((int)fx, wl - 1);
-        const float lx = fx - (float)q, hx = 1.f - lx;
-        const bool s = (q - c0) != 0;
-        second_col |= s;
-        wx[j][0] = s ? 0.f : hx; wx[j][1] = s ? hx : lx; wx[j][2] = s ? lx : 0.f;
-    }
-    const int r0 = min((int)(scy * (float)y0), hl - 1);
-    int rows_on_first_pair = 0;   // rows whose taps are staged rows (r0, r0+1); the rest use (r0+1, r0+2)
+    for (int i = 0; i < 8; ++i) idx8[i] = 0u;
+    if (live) {
+        // Separable interpolation weights, class-invariant: column j mixes the three staged columns c0..c0+2 with
+        // (hx, lx, 0) or (0, hx, lx).  A zero weight adds an exact 0, so for finite logits each pixel is fma(lx, b, hx*a)
+        // of its own two taps -- horizontal first, then vertical, like ATen.
+        float wx[4][3];
+        const int c0 = min((int)(scx * (float)x0), wl - 1);
+        bool second_col = false;      // some column of this thread interpolates inside the cell to the right of c0's
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float fy = scy * (float)(y0 + i);
-        const int r = min((int)fy, hl - 1);
-        const float ly = fy - (float)r, hy = 1.f - ly;
-        const bool s = (r - r0) != 0;
-        rows_on_first_pair += s ? 0 : 1;
-        wy[i][0] = s ? 0.f : hy; wy[i][1] = s ? hy : ly; wy[i][2] = s ? ly : 0.f;
-    }
-    // tile-relative offsets of the 3 rows / 3 columns (clamped at the image border like ATen's x1 = x0 + (x0 < w-1))
-    int ro[3], co[3];
+        for (int j = 0; j < 4; ++j) {
+            const float fx = scx * (float)(x0 + j);
+            const int q = min((int)fx, wl - 1);
+            const float lx = fx - (float)q, hx = 1.f - lx;
+            const bool s = (q - c0) != 0;
+            second_col |= s;
+            wx[j][0] = s ? 0.f : hx; wx[j][1] = s ? hx : lx; wx[j][2] = s ? lx : 0.f;
+        }
+        const int r0 = min((int)(scy * (float)y0), hl - 1);
+        // tile-relative offsets of the 3 rows / 3 columns; the staged tile holds clamped copies beyond the image border,
+        // which is ATen's x1 = x0 + (x0 < w-1)
+        int ro[3], co[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        ro[k] = (min(r0 + k, hl - 1) - rb) * kTC;
-        co[k] = min(c0 + k, wl - 1) - cb;
-    }
-
-    float best[8][4];
-    int bidx[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { best[i][j] = 0.f; bidx[i][j] = 0; }
-
-    const bool live = (x0 < W) && (y0 < H);
-    if (live && do_hist) {   // pull this thread's label rows towards L1 while the class loop runs
-        const size_t esz = label_dtype == FSCNN_U8 ? 1 : (label_dtype == FSCNN_I32 ? 4 : 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (y0 + i < H)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(labels) + (((size_t)n * H + (y0 + i)) * W + x0) * esz));
-    }
-    if (MODE == 1 && live && !slow) {
-        // all logits finite: plain `>` argmax, and the vertical taps picked at compile time.  The number of rows that
-        // still use the first staged row pair is the same for every lane of the warp (they share y0).
-        const int k = rows_on_first_pair;
-        // candidate classes of this thread's block = union over the (at most 2 x 2) cells its pixels interpolate in
+        for (int k = 0; k < 3; ++k) {
+            ro[k] = (r0 + k - rb) * kTC;
+            co[k] = c0 + k - cb;
+        }
         const unsigned int* cm = cellmask + (r0 - rb) * kCC + (c0 - cb);
-        unsigned int cand = cm[0];
-        if (second_col) cand |= cm[1];
-        if (k < 8) {
-            cand |= cm[kCC];
-            if (second_col) cand |= cm[kCC + 1];
-        }
-        if ((cand & (cand - 1u)) == 0u) {       // one class dominates the whole block: constant fill, no interpolation
-            const int c = __ffs(cand) - 1;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+        for (int half = 0; half < 2; ++half) {
+            float wa[4], wb[4];
+            int kh = 0;               // rows of this half whose taps are staged rows (r0, r0+1); the rest use (r0+1, r0+2)
+            unsigned int sy_mask = 0u;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bidx[i][j] = c;
-        } else {
-            switch (k) {
-                case 1: argmax_fast<1>(Ls, cand, ro, co, wx, wy, best, bidx); break;
-                case 2: argmax_fast<2>(Ls, cand, ro, co, wx, wy, best, bidx); break;
-                case 3: argmax_fast<3>(Ls, cand, ro, co, wx, wy, best, bidx); break;
-                case 4: argmax_fast<4>(Ls, cand, ro, co, wx, wy, best, bidx); break;
-                case 5: argmax_fast<5>(Ls, cand, ro, co, wx, wy, best, bidx); break;
-                case 6: argmax_fast<6>(Ls, cand, ro, co, wx, wy, best, bidx); break;
-                case 7: argmax_fast<7>(Ls, cand, ro, co, wx, wy, best, bidx); break;
-                default: argmax_fast<8>(Ls, cand, ro, co, wx, wy, best, bidx); break;
+            for (int i = 0; i < 4; ++i) {
+                const float fy = scy * (float)(y0 + 4 * half + i);
+                const int r = min((int)fy, hl - 1);
+                const float ly = fy - (float)r;
+                wa[i] = 1.f - ly; wb[i] = ly;
+                const bool s = (r - r0) != 0;
+                kh += s ? 0 : 1;
+                sy_mask |= (s ? 1u : 0u) << i;
             }
-        }
-    } else if (live) {
-        // generic loop (full-resolution logits; NaN / Inf; more than 32 classes): every pixel reads exactly the 2 x 2 taps ATen
-        // reads -- a non-finite value under a zero weight of the 3-tap form would poison pixels torch keeps finite.
-        // hx = 1 - lx > 0 always, so a zero first weight identifies the columns / rows that use the second tap pair.
-        for (int c = 0; c < nc; ++c) {
-            const float* lc = Ls + c * kTR * kTC;
-            float hrow[3][4];
+            unsigned int (&idx)[4] = *reinterpret_cast<unsigned int (*)[4]>(&idx8[4 * half]);
+            if (!slow) {
+                // candidate classes of this half = union over the (at most 2 x 2) cells its pixels interpolate in; kh is the
+                // same for every lane of the warp (they share y0)
+                unsigned int cand = 0u;
+                if (kh > 0) cand |= cm[0] | (second_col ? cm[1] : 0u);
+                if (kh < 4) cand |= cm[kCC] | (second_col ? cm[kCC + 1] : 0u);
+                if ((cand & (cand - 1u)) == 0u) {      // one class dominates: constant fill, no interpolation
+                    const unsigned int fill = (unsigned int)(__ffs(cand) - 1) * 0x01010101u;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool sx = wx[j][0] == 0.f;
-                    hrow[r][j] = fmaf(sx ? wx[j][2] : wx[j][1], sx ? v2 : v1, (sx ? wx[j][1] : wx[j][0]) * (sx ? v1 : v0));
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float val[4];
-                const bool sy = wy[i][0] == 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    val[j] = fmaf(sy ? wy[i][2] : wy[i][1], sy ? hrow[2][j] : hrow[1][j], (sy ? wy[i][1] : wy[i][0]) * (sy ? hrow[1][j] : hrow[0][j]));
-                if (MODE == 0) {
-                    if (y0 + i < H) {
-                        float* o = out_logits + (((size_t)n * nc + c) * H + (y0 + i)) * W + x0;
-                        if ((W & 3) == 0) {
-                            __stcs(reinterpret_cast<float4*>(o), make_float4(val[0], val[1], val[2], val[3]));
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (x0 + j < W) o[j] = val[j];
-                        }
-                    }
+                    for (int i = 0; i < 4; ++i) idx[i] = fill;
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        // first max wins; NaN beats everything except an earlier NaN
-                        const bool upd = (c == 0) || (!(val[j] <= best[i][j]) && (best[i][j] == best[i][j]));
-                        if (upd) { best[i][j] = val[j]; bidx[i][j] = c; }
+                    switch (kh) {
+                        case 0: argmax_half_fast<0>(Ls, cand, ro, co, wx, wa, wb, idx); break;
+                        case 1: argmax_half_fast<1>(Ls, cand, ro, co, wx, wa, wb, idx); break;
+                        case 2: argmax_half_fast<2>(Ls, cand, ro, co, wx, wa, wb, idx); break;
+                        case 3: argmax_half_fast<3>(Ls, cand, ro, co, wx, wa, wb, idx); break;
+                        default: argmax_half_fast<4>(Ls, cand, ro, co, wx, wa, wb, idx); break;
                     }
                 }
+            } else {
+                argmax_half_generic(Ls, nc, ro, co, wx, wa, wb, sy_mask, idx);
             }
         }
     }
-    if (MODE == 0) return;
 
-    // ---- write the mask (no early exits: every loop unrolls and bidx stays in registers) ----
+    // ---- write the mask ----
     if (live && mask) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             if (y0 + i < H) {
                 const size_t off = ((size_t)n * H + (y0 + i)) * W + x0;
+                const int b0 = idx8[i] & 255u, b1 = (idx8[i] >> 8) & 255u, b2 = (idx8[i] >> 16) & 255u, b3 = idx8[i] >> 24;
                 if (mask_dtype == FSCNN_U8) {
                     unsigned char* m = reinterpret_cast<unsigned char*>(mask) + off;
                     if ((W & 3) == 0) {
-                        *reinterpret_cast<uchar4*>(m) = make_uchar4((unsigned char)bidx[i][0], (unsigned char)bidx[i][1],
-                                                                    (unsigned char)bidx[i][2], (unsigned char)bidx[i][3]);
+                        *reinterpret_cast<unsigned int*>(m) = idx8[i];
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (x0 + j < W) m[j] = (unsigned char)bidx[i][j];
+                        if (x0 < W) m[0] = (unsigned char)b0;
+                        if (x0 + 1 < W) m[1] = (unsigned char)b1;
+                        if (x0 + 2 < W) m[2] = (unsigned char)b2;
+                        if (x0 + 3 < W) m[3] = (unsigned char)b3;
                     }
                 } else if (mask_dtype == FSCNN_I32) {
                     int* m = reinterpret_cast<int*>(mask) + off;
                     if ((W & 3) == 0) {
-                        *reinterpret_cast<int4*>(m) = make_int4(bidx[i][0], bidx[i][1], bidx[i][2], bidx[i][3]);
+                        *reinterpret_cast<int4*>(m) = make_int4(b0, b1, b2, b3);
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (x0 + j < W) m[j] = bidx[i][j];
+                        if (x0 < W) m[0] = b0;
+                        if (x0 + 1 < W) m[1] = b1;
+                        if (x0 + 2 < W) m[2] = b2;
+                        if (x0 + 3 < W) m[3] = b3;
                     }
                 } else {
                     long long* m = reinterpret_cast<long long*>(mask) + off;
                     if ((W & 3) == 0) {
-                        *reinterpret_cast<longlong2*>(m) = make_longlong2(bidx[i][0], bidx[i][1]);
-                        *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(bidx[i][2], bidx[i][3]);
+                        *reinterpret_cast<longlong2*>(m) = make_longlong2(b0, b1);
+                        *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(b2, b3);
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (x0 + j < W) m[j] = bidx[i][j];
+                        if (x0 < W) m[0] = b0;
+                        if (x0 + 1 < W) m[1] = b1;
+                        if (x0 + 2 < W) m[2] = b2;
+                        if (x0 + 3 < W) m[3] = b3;
                     }
                 }
             }
@@ -382,41 +463,39 @@ upsample_kernel(const float* __restrict__ low, int nc, int ncp, float* __restric
     }
     if (!do_hist) return;
 
-    // ---- SegmentationMetric counting: run-length aggregated shared-memory atomics ----
-    const ConfSink sink{use_smem_hist ? hist : nullptr, conf, nc};
+    // ---- SegmentationMetric counting: run-length aggregated shared-memory reductions, branch free ----
+    // A thread walks its 32 pixels row by row and issues ONE predicated red.shared per run of equal (label, prediction)
+    // pairs: real label maps give a couple per thread, uniform-random labels one per pixel; no lane ever branches.
     unsigned int labeled = 0, correct = 0;
     if (live) {
-        // all label rows first (independent loads in flight), reduced to a row code: -1 = unlabeled, nc = label >= nclass
-        int code[8][4];
+        const int stride = nc + 1;
+        const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+        int run_key = 0;
+        unsigned int run = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             long long labs[4] = {-1, -1, -1, -1};
             if (y0 + i < H) load_labels4(labels, label_dtype, ((size_t)n * H + (y0 + i)) * W + x0, (W & 3) == 0, W - x0, labs);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) code[i][j] = labs[j] < 0 ? -1 : (labs[j] < nc ? (int)labs[j] : nc);
-        }
-        int run_key = -1;
-        unsigned int run = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-#pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int row = code[i][j];
-                if (row >= 0) {                              // metric.py:79/:96 -- label+1 > 0 marks a labeled pixel
-                    const int col = bidx[i][j];
-                    const int key = row * (nc + 1) + col;
-                    labeled += 1;
-                    correct += (row == col);
-                    if (key == run_key) {
-                        run += 1;
-                    } else {
-                        if (run) sink.add_key(run_key, run);
-                        run_key = key; run = 1;
-                    }
+                const bool ok = labs[j] >= 0;                     // metric.py:79/:96 -- label+1 > 0 marks a labeled pixel
+                const int row = labs[j] < nc ? (int)labs[j] : nc; // labels >= nclass: overflow row
+                const int col = (int)((idx8[i] >> (8 * j)) & 255u);
+                const int key = row * stride + col;
+                labeled += ok ? 1u : 0u;
+                correct += (ok && row == col) ? 1u : 0u;
+                const bool brk = ok && (key != run_key || run == 0u);      // a new run starts at this pixel
+                if (use_smem_hist) {
+                    red_shared_if(brk && run != 0u, hist_s + 4u * (uint32_t)run_key, run);
+                } else if (brk && run != 0u) {
+                    atomicAdd(conf + run_key, (unsigned long long)run);
                 }
+                run = brk ? 1u : run + (ok ? 1u : 0u);
+                run_key = brk ? key : run_key;
             }
         }
-        if (run) sink.add_key(run_key, run);
+        if (use_smem_hist) red_shared_if(run != 0u, hist_s + 4u * (uint32_t)run_key, run);
+        else if (run) atomicAdd(conf + run_key, (unsigned long long)run);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -451,18 +530,19 @@ cudaError_t launch_up_logits(const float* low, int nc, int ncp, float* out, int 
     const size_t smem = up_smem_bytes(nc, false);
     if (smem > configured_bytes) { configured = 0; configured_bytes = smem; }
     if (smem > 48 * 1024) {
-        cudaError_t e = ensure_dyn_smem(upsample_kernel<0>, configured_bytes, configured);
+        cudaError_t e = ensure_dyn_smem(upsample_logits_kernel, configured_bytes, configured);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(ceil_div(w, 128), ceil_div(h, 64), n);
-    upsample_kernel<0><<<grid, kThreads, smem, s>>>(low, nc, ncp, out, nullptr, 0, nullptr, 0, nullptr, hl, wl, h, w, 0, 0);
+    upsample_logits_kernel<<<grid, kThreads, smem, s>>>(low, nc, ncp, out, hl, wl, h, w);
     return cudaGetLastError();
 }
 
 cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
                              int label_dtype, unsigned long long* conf, int n, int hl, int wl, int h, int w,
                              cudaStream_t s, bool prune) {
-    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1)) return cudaErrorInvalidValue;
+    // a 128-pixel tile row must interpolate inside at most 18 low-res cells (17 + the one to the right): ratio < 17/124
+    if ((double)(hl - 1) * 7.3 > (double)(h - 1) || (double)(wl - 1) * 7.3 > (double)(w - 1)) return cudaErrorInvalidValue;
     const bool hist = labels != nullptr;
     const int smem_hist = hist && ((nc + 1) * (nc + 1) <= kHistMaxBins);
     static unsigned long long configured = 0;
@@ -470,12 +550,12 @@ cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int 
     const size_t smem = up_smem_bytes(nc, smem_hist);
     if (smem > configured_bytes) { configured = 0; configured_bytes = smem; }
     if (smem > 48 * 1024) {
-        cudaError_t e = ensure_dyn_smem(upsample_kernel<1>, configured_bytes, configured);
+        cudaError_t e = ensure_dyn_smem(upsample_argmax_kernel, configured_bytes, configured);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(ceil_div(w, 128), ceil_div(h, 64), n);
-    upsample_kernel<1><<<grid, kThreads, smem, s>>>(low, nc, ncp, nullptr, mask, mask_dtype, labels, label_dtype, conf, hl,
-                                                    wl, h, w, smem_hist, prune ? 1 : 0);
+    upsample_argmax_kernel<<<grid, kThreads, smem, s>>>(low, nc, ncp, mask, mask_dtype, labels, label_dtype, conf, hl, wl, h, w,
+                                                        smem_hist, prune ? 1 : 0);
     return cudaGetLastError();
 }
 

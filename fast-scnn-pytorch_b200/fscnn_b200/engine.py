@@ -129,9 +129,9 @@ class Engine:
             raise ValueError(f'{what} must be a contiguous [{n},{h},{w}] tensor, got {tuple(t.shape)}')
         if t.device != self.device:
             raise RuntimeError(f'{what} is on {t.device}, the model is on {self.device}')
-        if t.data_ptr() % (4 * t.element_size()):
-            raise ValueError(f'{what} must be aligned to 4 elements ({4 * t.element_size()} bytes); pass a tensor that starts '
-                             f'at such an offset of its storage')
+        align = 4 if t.dtype == torch.uint8 else 16           # uchar4 / int4 / longlong2 accesses
+        if t.data_ptr() % align:
+            raise ValueError(f'{what} must be {align}-byte aligned; pass a tensor that starts at such an offset of its storage')
 
     def forward_mask(self, x: torch.Tensor, out_dtype=torch.uint8, out: Optional[torch.Tensor] = None, norm=None) -> torch.Tensor:
         n, h, w = self._check_input(x, norm)

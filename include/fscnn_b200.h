@@ -187,7 +187,7 @@ int fscnn_tap_info(const fscnn_ctx* ctx, int n, int h, int w, const char* tap, f
  * (utils/metric.py:73-105), from caller-provided low-resolution logits [n][hl][wl][padded_classes] float32 (the layout of
  * the "cls.logits_lowres" tap; padded_classes a multiple of 4, >= num_classes; 16-byte aligned).  d_mask [n][h][w]
  * (mask_dtype; may be NULL when labels are given), d_labels [n][h][w] or NULL, d_conf int64[fscnn_conf_len] accumulated
- * (required with labels).  (hl-1)*7 <= h-1 and (wl-1)*7 <= w-1 (the resize ratio of the network is 1/8).  Lets a test or a
+ * (required with labels).  (hl-1)*7.3 <= h-1 and (wl-1)*7.3 <= w-1 (the resize ratio of the network is 1/8).  Lets a test or a
  * benchmark drive the fused kernel with logits of its own (ties, NaN, class boundaries, adversarial orderings).
  * flags: FSCNN_TAIL_EXHAUSTIVE switches the exact class pruning off (every class is interpolated and compared at every
  * pixel): the result is identical by construction, only the time differs -- the reference point of the pruning tests and
