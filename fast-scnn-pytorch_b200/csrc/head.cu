@@ -81,14 +81,21 @@ struct ConfSink {
 // regions keep ONE class (no interpolation at all), a boundary between two regions keeps two, all-tied logits keep
 // class 0, and only logits where no class dominates another anywhere (e.g. class order flipping between neighbouring
 // taps) keep everything: the mask is bit-identical to the exhaustive loop in every case, only the time depends on the data.
-constexpr int kCR = kTR - 1, kCC = kTC - 1;      // 11 x 19 cells per staged tile
+#ifndef FSCNN_TAIL_NW
+#define FSCNN_TAIL_NW 8
+#endif
+constexpr int kANW = FSCNN_TAIL_NW;              // warps per CTA of the argmax kernel: the CTA covers 8 * kANW rows x 128 columns
+constexpr int kATH = kANW * 32;
+constexpr int kATR = kANW + 4;                   // staged low-res rows: 8 * kANW / 7.3 + 3 taps
+constexpr int kACS = kATR * kTC;                 // class stride of the staged tile
+constexpr int kACR = kATR - 1, kCC = kTC - 1;    // cells per staged tile
 
 __device__ __forceinline__ unsigned int dominated_by(const float* __restrict__ Ls, int nc, int o, int ch, float margin) {
-    const float* pc = Ls + ch * kTR * kTC + o;
+    const float* pc = Ls + ch * kACS + o;
     const float p0 = pc[0], p1 = pc[1], p2 = pc[kTC], p3 = pc[kTC + 1];
     unsigned int elim = 0u;
     for (int d = 0; d < nc; ++d) {
-        const float* pd = Ls + d * kTR * kTC + o;
+        const float* pd = Ls + d * kACS + o;
         const float m = fminf(fminf(p0 - pd[0], p1 - pd[1]), fminf(p2 - pd[kTC], p3 - pd[kTC + 1]));
         const bool e = ch < d ? (m >= 0.f) : (m > margin);      // d == ch: m == 0 > margin is false
         elim |= (e ? 1u : 0u) << d;
@@ -100,7 +107,7 @@ __device__ __forceinline__ unsigned int cell_survivors(const float* __restrict__
     int ch0 = 0, ch3 = 0;
     float b0 = Ls[o], b3 = Ls[o + kTC + 1];
     for (int c = 1; c < nc; ++c) {
-        const float v0 = Ls[c * kTR * kTC + o], v3 = Ls[c * kTR * kTC + o + kTC + 1];
+        const float v0 = Ls[c * kACS + o], v3 = Ls[c * kACS + o + kTC + 1];
         if (v0 > b0) { b0 = v0; ch0 = c; }
         if (v3 > b3) { b3 = v3; ch3 = c; }
     }
@@ -127,7 +134,7 @@ __device__ __forceinline__ void argmax_half_fast(const float* __restrict__ Ls, u
     while (cand) {
         const unsigned int c = __ffs(cand) - 1;
         cand &= cand - 1u;
-        const float* lc = Ls + c * kTR * kTC;
+        const float* lc = Ls + c * kACS;
         float hrow[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -165,7 +172,7 @@ __device__ __forceinline__ void argmax_half_generic(const float* __restrict__ Ls
         for (int j = 0; j < 4; ++j) best[i][j] = 0.f;
     }
     for (int c = 0; c < nc; ++c) {
-        const float* lc = Ls + c * kTR * kTC;
+        const float* lc = Ls + c * kACS;
         float hrow[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -276,30 +283,79 @@ upsample_logits_kernel(const float* __restrict__ low, int nc, int ncp, float* __
     }
 }
 
-// argmax mask (+ optional confusion counts) straight from the low-resolution logits.
-__global__ void __launch_bounds__(kThreads, 3)
+// Four consecutive labels of row `i` starting at element `e`, reduced to a row code of the confusion accumulator:
+// -1 = unlabeled (label < 0; metric.py:79/:96, label+1 > 0 marks a labeled pixel), nc = label >= nclass (overflow row).
+// LDT: FSCNN_U8 / FSCNN_I32 / FSCNN_I64.  `aligned`: vector loads (the row pitch keeps 4-element groups aligned).
+template <int LDT>
+__device__ __forceinline__ void load_codes4(const void* __restrict__ p, size_t e, bool aligned, int remaining, int nc, int (&code)[4]) {
+    if (LDT == FSCNN_U8) {
+        const unsigned char* q = reinterpret_cast<const unsigned char*>(p) + e;
+        unsigned int v[4];
+        if (aligned) {
+            const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(q));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = j < remaining ? (unsigned int)__ldg(q + j) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) code[j] = v[j] == 0xffffffffu ? -1 : (int)min(v[j], (unsigned int)nc);
+    } else if (LDT == FSCNN_I32) {
+        const int* q = reinterpret_cast<const int*>(p) + e;
+        int v[4];
+        if (aligned) {
+            const int4 t = __ldg(reinterpret_cast<const int4*>(q));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = j < remaining ? __ldg(q + j) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) code[j] = v[j] < 0 ? -1 : min(v[j], nc);
+    } else {
+        const long long* q = reinterpret_cast<const long long*>(p) + e;
+        int lo[4], hi[4];
+        if (aligned) {
+            const int4 a = __ldg(reinterpret_cast<const int4*>(q)), b = __ldg(reinterpret_cast<const int4*>(q) + 1);
+            lo[0] = a.x; hi[0] = a.y; lo[1] = a.z; hi[1] = a.w; lo[2] = b.x; hi[2] = b.y; lo[3] = b.z; hi[3] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long t = j < remaining ? __ldg(q + j) : -1ll;
+                lo[j] = (int)(t & 0xffffffffll); hi[j] = (int)(t >> 32);
+            }
+        }
+        // sign from the high word; any value that does not fit [0, nc) in the low word alone is >= nclass
+#pragma unroll
+        for (int j = 0; j < 4; ++j) code[j] = hi[j] < 0 ? -1 : ((hi[j] == 0 && (unsigned int)lo[j] < (unsigned int)nc) ? lo[j] : nc);
+    }
+}
+
+// argmax mask (+ optional confusion counts) straight from the low-resolution logits.  LDT: label dtype, or -1 = no labels.
+template <int LDT>
+__global__ void __launch_bounds__(kATH, 768 / kATH)
 upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __restrict__ mask, int mask_dtype,
-                       const void* __restrict__ labels, int label_dtype, unsigned long long* __restrict__ conf,
+                       const void* __restrict__ labels, unsigned long long* __restrict__ conf,
                        int hl, int wl, int H, int W, int use_smem_hist, int prune) {
     extern __shared__ __align__(16) float dynsm[];
-    float* Ls = dynsm;                                            // [nc][kTR][kTC]
-    unsigned int* hist = reinterpret_cast<unsigned int*>(dynsm + nc * kTR * kTC);
+    float* Ls = dynsm;                                            // [nc][kATR][kTC]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(dynsm + nc * kACS);
     __shared__ unsigned int blk_labeled, blk_correct, tile_amax;
-    __shared__ unsigned int cellmask[kCR * kCC];
+    __shared__ unsigned int cellmask[kACR * kCC];
+    constexpr bool do_hist = LDT >= 0;
+    constexpr int esz = LDT == FSCNN_U8 ? 1 : (LDT == FSCNN_I32 ? 4 : 8);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.z;
-    const int yb = blockIdx.y * 64, xb = blockIdx.x * 128;
+    const int yb = blockIdx.y * (8 * kANW), xb = blockIdx.x * 128;
     const float scy = H > 1 ? (float)(hl - 1) / (float)(H - 1) : 0.f;
     const float scx = W > 1 ? (float)(wl - 1) / (float)(W - 1) : 0.f;
     const int rb = min((int)(scy * (float)yb), hl - 1);          // first staged low-res row / column
     const int cb = min((int)(scx * (float)xb), wl - 1);
-    const bool do_hist = labels != nullptr;
     const int x0 = xb + lane * 4, y0 = yb + warp * 8;
     const bool live = (x0 < W) && (y0 < H);
 
-    if (live && do_hist) {   // pull this thread's label rows towards L1 while the logits are staged and the classes compared
-        const size_t esz = label_dtype == FSCNN_U8 ? 1 : (label_dtype == FSCNN_I32 ? 4 : 8);
+    if (do_hist && live) {   // pull this thread's label rows towards L1 while the logits are staged and the classes compared
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             if (y0 + i < H)
@@ -311,23 +367,23 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
     if (tid == 0) { tile_amax = 0u; blk_labeled = 0u; blk_correct = 0u; }
     {
         const int nv = ncp >> 2;
-        for (int i = tid; i < kTR * kTC * nv; i += kThreads) {
-            const int v = i % nv, px = i / nv;
-            const int r = px / kTC, q = px % kTC;
+        for (int i = tid; i < kACS * nv; i += kATH) {
+            const int px = i / nv, v = i - px * nv;
+            const int r = px / kTC, q = px - r * kTC;
             const int rr = min(rb + r, hl - 1), qq = min(cb + q, wl - 1);
             const float4 t = __ldg(reinterpret_cast<const float4*>(low + (((size_t)n * hl + rr) * wl + qq) * ncp) + v);
             const int c = 4 * v;
             nonfinite |= !(fabsf(t.x) <= 3.4e38f) | !(fabsf(t.y) <= 3.4e38f) | !(fabsf(t.z) <= 3.4e38f) | !(fabsf(t.w) <= 3.4e38f);
             amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
-            float* dst = Ls + (c * kTR + r) * kTC + q;
+            float* dst = Ls + c * kACS + px;
             dst[0] = t.x;
-            if (c + 1 < nc) dst[kTR * kTC] = t.y;
-            if (c + 2 < nc) dst[2 * kTR * kTC] = t.z;
-            if (c + 3 < nc) dst[3 * kTR * kTC] = t.w;
+            if (c + 1 < nc) dst[kACS] = t.y;
+            if (c + 2 < nc) dst[2 * kACS] = t.z;
+            if (c + 3 < nc) dst[3 * kACS] = t.w;
         }
     }
     if (do_hist && use_smem_hist)
-        for (int i = tid; i < (nc + 1) * (nc + 1); i += kThreads) hist[i] = 0u;
+        for (int i = tid; i < (nc + 1) * (nc + 1); i += kATH) hist[i] = 0u;
     // NaN / Inf among the staged logits (padding classes are finite zeros) selects the exact-semantics generic loop; so do
     // more classes than the candidate bit mask holds
     const bool slow = (__syncthreads_or(nonfinite) != 0) || nc > 32;
@@ -339,7 +395,7 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
         if (lane == 0) atomicMax(&tile_amax, __float_as_uint(amax));
         __syncthreads();
         const float margin = 2e-6f * __uint_as_float(tile_amax) + 1e-30f;
-        const int rn = min(min((int)(scy * (float)min(yb + 63, H - 1)), hl - 1) - rb + 1, kCR);
+        const int rn = min(min((int)(scy * (float)min(yb + 8 * kANW - 1, H - 1)), hl - 1) - rb + 1, kACR);
         const int qn = min(min((int)(scx * (float)min(xb + 127, W - 1)), wl - 1) - cb + 1, kCC);
         if (tid < rn * qn) {      // prune == 0 (tests, worst-case timing): every class stays a candidate everywhere
             const int R = tid / qn, Q = tid - R * qn;
@@ -347,11 +403,8 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
         }
         __syncthreads();
     }
-    if (!live && !do_hist) return;
 
-    unsigned int idx8[8];      // winning class of the thread's 8 rows x 4 columns, one byte per pixel
-#pragma unroll
-    for (int i = 0; i < 8; ++i) idx8[i] = 0u;
+    unsigned int labeled = 0, correct = 0;
     if (live) {
         // Separable interpolation weights, class-invariant: column j mixes the three staged columns c0..c0+2 with
         // (hx, lx, 0) or (0, hx, lx).  A zero weight adds an exact 0, so for finite logits each pixel is fma(lx, b, hx*a)
@@ -378,14 +431,19 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
             co[k] = c0 + k - cb;
         }
         const unsigned int* cm = cellmask + (r0 - rb) * kCC + (c0 - cb);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
+        const int stride = nc + 1;
+        int run_key = -1;            // run-length state of the metric counting, carried across both halves
+        unsigned int run = 0;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {      // rows 0..3, then 4..7 of the thread's 8 x 4 block (one copy of the code)
+            const int yh = y0 + 4 * half;
             float wa[4], wb[4];
             int kh = 0;               // rows of this half whose taps are staged rows (r0, r0+1); the rest use (r0+1, r0+2)
             unsigned int sy_mask = 0u;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float fy = scy * (float)(y0 + 4 * half + i);
+                const float fy = scy * (float)(yh + i);
                 const int r = min((int)fy, hl - 1);
                 const float ly = fy - (float)r;
                 wa[i] = 1.f - ly; wb[i] = ly;
@@ -393,7 +451,7 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
                 kh += s ? 0 : 1;
                 sy_mask |= (s ? 1u : 0u) << i;
             }
-            unsigned int (&idx)[4] = *reinterpret_cast<unsigned int (*)[4]>(&idx8[4 * half]);
+            unsigned int idx[4];      // winning class of 4 rows x 4 columns, one byte per pixel
             if (!slow) {
                 // candidate classes of this half = union over the (at most 2 x 2) cells its pixels interpolate in; kh is the
                 // same for every lane of the warp (they share y0)
@@ -416,86 +474,101 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
             } else {
                 argmax_half_generic(Ls, nc, ro, co, wx, wa, wb, sy_mask, idx);
             }
-        }
-    }
 
-    // ---- write the mask ----
-    if (live && mask) {
+            // ---- write the mask ----
+            if (mask) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (y0 + i < H) {
-                const size_t off = ((size_t)n * H + (y0 + i)) * W + x0;
-                const int b0 = idx8[i] & 255u, b1 = (idx8[i] >> 8) & 255u, b2 = (idx8[i] >> 16) & 255u, b3 = idx8[i] >> 24;
-                if (mask_dtype == FSCNN_U8) {
-                    unsigned char* m = reinterpret_cast<unsigned char*>(mask) + off;
-                    if ((W & 3) == 0) {
-                        *reinterpret_cast<unsigned int*>(m) = idx8[i];
-                    } else {
-                        if (x0 < W) m[0] = (unsigned char)b0;
-                        if (x0 + 1 < W) m[1] = (unsigned char)b1;
-                        if (x0 + 2 < W) m[2] = (unsigned char)b2;
-                        if (x0 + 3 < W) m[3] = (unsigned char)b3;
-                    }
-                } else if (mask_dtype == FSCNN_I32) {
-                    int* m = reinterpret_cast<int*>(mask) + off;
-                    if ((W & 3) == 0) {
-                        *reinterpret_cast<int4*>(m) = make_int4(b0, b1, b2, b3);
-                    } else {
-                        if (x0 < W) m[0] = b0;
-                        if (x0 + 1 < W) m[1] = b1;
-                        if (x0 + 2 < W) m[2] = b2;
-                        if (x0 + 3 < W) m[3] = b3;
-                    }
-                } else {
-                    long long* m = reinterpret_cast<long long*>(mask) + off;
-                    if ((W & 3) == 0) {
-                        *reinterpret_cast<longlong2*>(m) = make_longlong2(b0, b1);
-                        *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(b2, b3);
-                    } else {
-                        if (x0 < W) m[0] = b0;
-                        if (x0 + 1 < W) m[1] = b1;
-                        if (x0 + 2 < W) m[2] = b2;
-                        if (x0 + 3 < W) m[3] = b3;
+                for (int i = 0; i < 4; ++i) {
+                    if (yh + i < H) {
+                        const size_t off = ((size_t)n * H + (yh + i)) * W + x0;
+                        const int b0 = idx[i] & 255u, b1 = (idx[i] >> 8) & 255u, b2 = (idx[i] >> 16) & 255u, b3 = idx[i] >> 24;
+                        if (mask_dtype == FSCNN_U8) {
+                            unsigned char* m = reinterpret_cast<unsigned char*>(mask) + off;
+                            if ((W & 3) == 0) {
+                                *reinterpret_cast<unsigned int*>(m) = idx[i];
+                            } else {
+                                if (x0 < W) m[0] = (unsigned char)b0;
+                                if (x0 + 1 < W) m[1] = (unsigned char)b1;
+                                if (x0 + 2 < W) m[2] = (unsigned char)b2;
+                                if (x0 + 3 < W) m[3] = (unsigned char)b3;
+                            }
+                        } else if (mask_dtype == FSCNN_I32) {
+                            int* m = reinterpret_cast<int*>(mask) + off;
+                            if ((W & 3) == 0) {
+                                *reinterpret_cast<int4*>(m) = make_int4(b0, b1, b2, b3);
+                            } else {
+                                if (x0 < W) m[0] = b0;
+                                if (x0 + 1 < W) m[1] = b1;
+                                if (x0 + 2 < W) m[2] = b2;
+                                if (x0 + 3 < W) m[3] = b3;
+                            }
+                        } else {
+                            long long* m = reinterpret_cast<long long*>(mask) + off;
+                            if ((W & 3) == 0) {
+                                *reinterpret_cast<longlong2*>(m) = make_longlong2(b0, b1);
+                                *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(b2, b3);
+                            } else {
+                                if (x0 < W) m[0] = b0;
+                                if (x0 + 1 < W) m[1] = b1;
+                                if (x0 + 2 < W) m[2] = b2;
+                                if (x0 + 3 < W) m[3] = b3;
+                            }
+                        }
                     }
                 }
             }
+
+            // ---- SegmentationMetric counting: run-length aggregated shared-memory reductions, branch free ----
+            // A thread walks its pixels row by row and issues ONE predicated red.shared per run of equal (label, prediction)
+            // pairs: real label maps give a couple per thread, uniform-random labels one per pixel; no lane ever branches.
+            if (do_hist) {
+                int code[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {       // all four row loads in flight before the first one is consumed
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) code[i][j] = -1;
+                    if (yh + i < H) load_codes4<LDT < 0 ? 0 : LDT>(labels, ((size_t)n * H + (yh + i)) * W + x0, (W & 3) == 0, W - x0, nc, code[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = code[i][j];
+                        const bool ok = row >= 0;
+                        const int col = (int)((idx[i] >> (8 * j)) & 255u);
+                        const int key = row * stride + col;
+                        const bool brk = ok && key != run_key;      // a new run starts at this pixel (run_key starts at -1)
+                        if (use_smem_hist) {
+                            // the run that ends here; before the first labeled pixel that is `0 pixels of bin 0`, which adds nothing
+                            red_shared_if(brk, hist_s + 4u * (uint32_t)max(run_key, 0), run);
+                        } else {
+                            labeled += ok ? 1u : 0u;
+                            correct += (row == col) ? 1u : 0u;                      // col >= 0, so an unlabeled pixel never matches
+                            if (brk && run != 0u) atomicAdd(conf + run_key, (unsigned long long)run);
+                        }
+                        run = brk ? 1u : run + (ok ? 1u : 0u);
+                        run_key = brk ? key : run_key;
+                    }
+                }
+            }
+        }
+        if (do_hist) {
+            if (use_smem_hist) red_shared_if(run != 0u, hist_s + 4u * (uint32_t)max(run_key, 0), run);
+            else if (run) atomicAdd(conf + run_key, (unsigned long long)run);
         }
     }
     if (!do_hist) return;
-
-    // ---- SegmentationMetric counting: run-length aggregated shared-memory reductions, branch free ----
-    // A thread walks its 32 pixels row by row and issues ONE predicated red.shared per run of equal (label, prediction)
-    // pairs: real label maps give a couple per thread, uniform-random labels one per pixel; no lane ever branches.
-    unsigned int labeled = 0, correct = 0;
-    if (live) {
-        const int stride = nc + 1;
-        const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(hist);
-        int run_key = 0;
-        unsigned int run = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            long long labs[4] = {-1, -1, -1, -1};
-            if (y0 + i < H) load_labels4(labels, label_dtype, ((size_t)n * H + (y0 + i)) * W + x0, (W & 3) == 0, W - x0, labs);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const bool ok = labs[j] >= 0;                     // metric.py:79/:96 -- label+1 > 0 marks a labeled pixel
-                const int row = labs[j] < nc ? (int)labs[j] : nc; // labels >= nclass: overflow row
-                const int col = (int)((idx8[i] >> (8 * j)) & 255u);
-                const int key = row * stride + col;
-                labeled += ok ? 1u : 0u;
-                correct += (ok && row == col) ? 1u : 0u;
-                const bool brk = ok && (key != run_key || run == 0u);      // a new run starts at this pixel
-                if (use_smem_hist) {
-                    red_shared_if(brk && run != 0u, hist_s + 4u * (uint32_t)run_key, run);
-                } else if (brk && run != 0u) {
-                    atomicAdd(conf + run_key, (unsigned long long)run);
-                }
-                run = brk ? 1u : run + (ok ? 1u : 0u);
-                run_key = brk ? key : run_key;
-            }
+    __syncthreads();
+    const int nb = (nc + 1) * (nc + 1);
+    if (use_smem_hist) {
+        // the tile's bins go to the global accumulator; `labeled` is their sum and `correct` the sum of the diagonal
+        // (bin = row * (nc + 1) + col, row == col < nc  <=>  bin % (nc + 2) == 0 and bin < nc * (nc + 2))
+        for (int i = tid; i < nb; i += kATH) {
+            const unsigned int v = hist[i];
+            if (v) atomicAdd(conf + i, (unsigned long long)v);
+            labeled += v;
+            correct += (i % (nc + 2) == 0 && i < nc * (nc + 2)) ? v : 0u;
         }
-        if (use_smem_hist) red_shared_if(run != 0u, hist_s + 4u * (uint32_t)run_key, run);
-        else if (run) atomicAdd(conf + run_key, (unsigned long long)run);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -504,20 +577,14 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
     }
     if (lane == 0) { atomicAdd(&blk_labeled, labeled); atomicAdd(&blk_correct, correct); }
     __syncthreads();
-    const int nb = (nc + 1) * (nc + 1);
-    if (use_smem_hist)
-        for (int i = tid; i < nb; i += kThreads) {
-            const unsigned int v = hist[i];
-            if (v) atomicAdd(conf + i, (unsigned long long)v);
-        }
     if (tid == 0) {
         if (blk_labeled) atomicAdd(conf + nb, (unsigned long long)blk_labeled);
         if (blk_correct) atomicAdd(conf + nb + 1, (unsigned long long)blk_correct);
     }
 }
 
-static size_t up_smem_bytes(int nc, bool hist) {
-    size_t b = (size_t)nc * kTR * kTC * sizeof(float);
+static size_t up_smem_bytes(int nc, bool hist, int rows = kTR) {
+    size_t b = (size_t)nc * rows * kTC * sizeof(float);
     if (hist) b += (size_t)(nc + 1) * (nc + 1) * sizeof(unsigned int);
     return b;
 }
@@ -538,25 +605,34 @@ cudaError_t launch_up_logits(const float* low, int nc, int ncp, float* out, int 
     return cudaGetLastError();
 }
 
+template <int LDT>
+static cudaError_t run_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
+                                 unsigned long long* conf, int n, int hl, int wl, int h, int w, cudaStream_t s, bool prune) {
+    const int smem_hist = (LDT >= 0) && ((nc + 1) * (nc + 1) <= kHistMaxBins);
+    static unsigned long long configured = 0;
+    static size_t configured_bytes = 48 * 1024;
+    const size_t smem = up_smem_bytes(nc, smem_hist, kATR);
+    if (smem > configured_bytes) { configured = 0; configured_bytes = smem; }
+    if (smem > 48 * 1024) {
+        cudaError_t e = ensure_dyn_smem(upsample_argmax_kernel<LDT>, configured_bytes, configured);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(ceil_div(w, 128), ceil_div(h, 8 * kANW), n);
+    upsample_argmax_kernel<LDT><<<grid, kATH, smem, s>>>(low, nc, ncp, mask, mask_dtype, labels, conf, hl, wl, h, w, smem_hist,
+                                                             prune ? 1 : 0);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
                              int label_dtype, unsigned long long* conf, int n, int hl, int wl, int h, int w,
                              cudaStream_t s, bool prune) {
     // a 128-pixel tile row must interpolate inside at most 18 low-res cells (17 + the one to the right): ratio < 17/124
     if ((double)(hl - 1) * 7.3 > (double)(h - 1) || (double)(wl - 1) * 7.3 > (double)(w - 1)) return cudaErrorInvalidValue;
-    const bool hist = labels != nullptr;
-    const int smem_hist = hist && ((nc + 1) * (nc + 1) <= kHistMaxBins);
-    static unsigned long long configured = 0;
-    static size_t configured_bytes = 48 * 1024;
-    const size_t smem = up_smem_bytes(nc, smem_hist);
-    if (smem > configured_bytes) { configured = 0; configured_bytes = smem; }
-    if (smem > 48 * 1024) {
-        cudaError_t e = ensure_dyn_smem(upsample_argmax_kernel, configured_bytes, configured);
-        if (e != cudaSuccess) return e;
-    }
-    dim3 grid(ceil_div(w, 128), ceil_div(h, 64), n);
-    upsample_argmax_kernel<<<grid, kThreads, smem, s>>>(low, nc, ncp, mask, mask_dtype, labels, label_dtype, conf, hl, wl, h, w,
-                                                        smem_hist, prune ? 1 : 0);
-    return cudaGetLastError();
+    if (!labels) return run_up_argmax<-1>(low, nc, ncp, mask, mask_dtype, nullptr, nullptr, n, hl, wl, h, w, s, prune);
+    if (label_dtype == FSCNN_U8) return run_up_argmax<FSCNN_U8>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune);
+    if (label_dtype == FSCNN_I32) return run_up_argmax<FSCNN_I32>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune);
+    if (label_dtype == FSCNN_I64) return run_up_argmax<FSCNN_I64>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune);
+    return cudaErrorInvalidValue;
 }
 
 // ---- SegmentationMetric counting on existing class maps (utils/metric.py:73-105) ----
