@@ -81,6 +81,9 @@ struct ConfSink {
 // regions keep ONE class (no interpolation at all), a boundary between two regions keeps two, all-tied logits keep
 // class 0, and only logits where no class dominates another anywhere (e.g. class order flipping between neighbouring
 // taps) keep everything: the mask is bit-identical to the exhaustive loop in every case, only the time depends on the data.
+#ifndef FSCNN_TAIL_PF
+#define FSCNN_TAIL_PF 1
+#endif
 #ifndef FSCNN_TAIL_NW
 #define FSCNN_TAIL_NW 8
 #endif
@@ -358,8 +361,15 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
     if (do_hist && live) {   // pull this thread's label rows towards L1 while the logits are staged and the classes compared
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (y0 + i < H)
+            if (y0 + i < H) {
+#if FSCNN_TAIL_PF == 1
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(labels) + (((size_t)n * H + (y0 + i)) * W + x0) * esz));
+#elif FSCNN_TAIL_PF == 2
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(labels) + (((size_t)n * H + (y0 + i)) * W + x0) * esz));
+#elif FSCNN_TAIL_PF == 3
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(reinterpret_cast<const char*>(labels) + (((size_t)n * H + (y0 + i)) * W + x0) * esz));
+#endif
+            }
     }
     // stage the low-res tile class-major: one float4 (4 classes of one pixel) per item, independent loads in flight
     int nonfinite = 0;

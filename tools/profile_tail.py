@@ -24,6 +24,8 @@ with torch.no_grad():
     model.classifier.conv[1].bias -= low[..., :nc].mean(dim=(0, 1, 2))
 eng = model._engine(dev)
 low = bench.lowres_logits(eng, x, h, w)
+if len(sys.argv) > 2 and sys.argv[2] == 'tied':
+    low.zero_()
 labels = torch.randint(-1, nc, (batch, h, w), device=dev)
 conf = torch.zeros(eng.conf_len(), dtype=torch.int64, device=dev)
 for _ in range(2):
