@@ -903,4 +903,114 @@ int fscnn_conf_to_totals(const long long* h_conf, int nc, long long* h_inter, lo
     return FSCNN_OK;
 }
 
+// ---- training step, first slice: see include/fscnn_b200.h ----
+static int train_ws_ok(const void* ws, size_t have, size_t need) {
+    if (!ws) return fail(FSCNN_EINVAL, "null workspace");
+    if (have < need) return fail(FSCNN_ENOMEM, "training workspace too small: %zu < %zu bytes", have, need);
+    if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(FSCNN_EINVAL, "workspace must be 16-byte aligned");
+    return FSCNN_OK;
+}
+
+int fscnn_train_workspace_bytes(int max_channels, int max_cout, int max_cin, size_t* out) {
+    if (!out || max_channels < 1 || max_cout < 1 || max_cin < 1) return fail(FSCNN_EINVAL, "bad argument");
+    *out = train_workspace_bytes(max_channels, max_cout, max_cin);
+    return FSCNN_OK;
+}
+
+int fscnn_train_dwconv3x3_forward(const float* d_x, const float* d_w, float* d_y, int n, int c, int h, int w, int stride, void* stream) {
+    if (!d_x || !d_w || !d_y) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || h < 1 || w < 1 || (stride != 1 && stride != 2)) return fail(FSCNN_EINVAL, "bad shape n=%d c=%d h=%d w=%d stride=%d", n, c, h, w, stride);
+    cudaError_t e = launch_train_dw_fwd(d_x, d_w, d_y, n, c, h, w, stride, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "depthwise forward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_dwconv3x3_backward(const float* d_x, const float* d_w, const float* d_dy, float* d_dx, float* d_dw, void* d_ws,
+                                   size_t ws_bytes, int n, int c, int h, int w, int stride, void* stream) {
+    if (!d_x || !d_w || !d_dy || (!d_dx && !d_dw)) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || h < 1 || w < 1 || (stride != 1 && stride != 2)) return fail(FSCNN_EINVAL, "bad shape");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_workspace_bytes(c, 1, 1));
+    if (rc) return rc;
+    cudaError_t e = launch_train_dw_bwd(d_x, d_w, d_dy, d_dx, d_dw, d_ws, n, c, h, w, stride, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "depthwise backward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_pwconv_forward(const float* d_x, const float* d_w, float* d_y, int n, int cin, int cout, int hw, void* stream) {
+    if (!d_x || !d_w || !d_y) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || n > 65535 || cin < 1 || cout < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad shape");
+    cudaError_t e = launch_train_pw_fwd(d_x, d_w, d_y, n, cin, cout, hw, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "pointwise forward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_pwconv_backward(const float* d_x, const float* d_w, const float* d_dy, float* d_dx, float* d_dw, void* d_ws,
+                                size_t ws_bytes, int n, int cin, int cout, int hw, void* stream) {
+    if (!d_x || !d_w || !d_dy || (!d_dx && !d_dw)) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || n > 64 || cin < 1 || cout < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad shape (the weight gradient takes at most 64 images per call)");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_workspace_bytes(1, cout, cin));
+    if (rc) return rc;
+    cudaError_t e = launch_train_pw_bwd(d_x, d_w, d_dy, d_dx, d_dw, d_ws, n, cin, cout, hw, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "pointwise backward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_batchnorm_forward(const float* d_x, const float* d_gamma, const float* d_beta, float* d_running_mean,
+                                  float* d_running_var, float* d_y, float* d_save_mean, float* d_save_rstd, void* d_ws, size_t ws_bytes,
+                                  int n, int c, int hw, float eps, float momentum, int relu, void* stream) {
+    if (!d_x || !d_gamma || !d_beta || !d_y || !d_save_mean || !d_save_rstd) return fail(FSCNN_EINVAL, "null device pointer");
+    if ((d_running_mean == nullptr) != (d_running_var == nullptr)) return fail(FSCNN_EINVAL, "running mean and var go together");
+    if (n < 1 || c < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad shape");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_workspace_bytes(c, 1, 1));
+    if (rc) return rc;
+    cudaError_t e = launch_train_bn_fwd(d_x, d_gamma, d_beta, d_running_mean, d_running_var, d_y, d_save_mean, d_save_rstd, d_ws, n, c, hw,
+                                        eps, momentum, relu, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "batchnorm forward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_batchnorm_backward(const float* d_x, const float* d_y, const float* d_dy, const float* d_gamma, const float* d_save_mean,
+                                   const float* d_save_rstd, float* d_dx, float* d_dgamma, float* d_dbeta, void* d_ws, size_t ws_bytes,
+                                   int n, int c, int hw, int relu, void* stream) {
+    if (!d_x || !d_dy || !d_gamma || !d_save_mean || !d_save_rstd || !d_dx || !d_dgamma || !d_dbeta || (relu && !d_y))
+        return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad shape");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_workspace_bytes(c, 1, 1));
+    if (rc) return rc;
+    cudaError_t e = launch_train_bn_bwd(d_x, d_y, d_dy, d_gamma, d_save_mean, d_save_rstd, d_dx, d_dgamma, d_dbeta, d_ws, n, c, hw, relu,
+                                        (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "batchnorm backward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_ohem_workspace_bytes(size_t* out) {
+    if (!out) return fail(FSCNN_EINVAL, "bad argument");
+    *out = train_ohem_workspace_bytes();
+    return FSCNN_OK;
+}
+
+int fscnn_train_ohem_forward(const float* d_logits, const long long* d_label, const float* d_class_weight, float* d_prob, float* d_out3,
+                             void* d_ws, size_t ws_bytes, int n, int c, int hw, long long ignore_label, float thresh, int min_kept,
+                             void* stream) {
+    if (!d_logits || !d_label || !d_prob || !d_out3) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || hw < 1 || min_kept < 0) return fail(FSCNN_EINVAL, "bad shape");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_ohem_workspace_bytes());
+    if (rc) return rc;
+    cudaError_t e = launch_train_ohem_fwd(d_logits, d_label, d_class_weight, d_prob, d_out3, d_ws, n, c, hw, ignore_label, thresh, min_kept,
+                                          (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "OHEM forward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_ohem_backward(const float* d_logits, const long long* d_label, const float* d_class_weight, const float* d_prob,
+                              const float* d_out3, const float* d_grad_out, float* d_dlogits, const void* d_ws, int n, int c, int hw,
+                              long long ignore_label, void* stream) {
+    if (!d_logits || !d_label || !d_prob || !d_out3 || !d_grad_out || !d_dlogits || !d_ws) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad shape");
+    cudaError_t e = launch_train_ohem_bwd(d_logits, d_label, d_class_weight, d_prob, d_out3, d_grad_out, d_dlogits, d_ws, n, c, hw,
+                                          ignore_label, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "OHEM backward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
 }  // extern "C"

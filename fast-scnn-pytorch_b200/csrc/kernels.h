@@ -140,4 +140,25 @@ cudaError_t launch_l2d_front_tc(const void* x, const StemIn& in, const bf16* ws_
 cudaError_t launch_l2d_front_t_tc(const void* x, const StemIn& in, const bf16* ws_img, const DsW& w, const bf16* wp_img, bf16* out, int n,
                                   int h, int wd, int h1, int w1, int h2, int w2, cudaStream_t s);
 
+// ---- training step, first slice (train.cu): fp32 NCHW tensors as autograd hands them over ----
+size_t train_workspace_bytes(int channels_max, int cout, int cin);
+size_t train_ohem_workspace_bytes();
+cudaError_t launch_train_dw_fwd(const float* x, const float* w, float* y, int n, int c, int h, int wd, int stride, cudaStream_t s);
+cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, void* ws, int n, int c, int h,
+                                int wd, int stride, cudaStream_t s);
+cudaError_t launch_train_pw_fwd(const float* x, const float* w, float* y, int n, int cin, int cout, int hw, cudaStream_t s);
+cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, void* ws, int n, int cin,
+                                int cout, int hw, cudaStream_t s);
+cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                float* y, float* save_mean, float* save_rstd, void* ws, int n, int c, int hw, float eps,
+                                float momentum, int relu, cudaStream_t s);
+cudaError_t launch_train_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                                const float* save_rstd, float* dx, float* dgamma, float* dbeta, void* ws, int n, int c, int hw,
+                                int relu, cudaStream_t s);
+cudaError_t launch_train_ohem_fwd(const float* logits, const long long* label, const float* weight, float* prob, float* out3, void* ws,
+                                  int n, int c, int hw, long long ignore, float thresh, int min_kept, cudaStream_t s);
+cudaError_t launch_train_ohem_bwd(const float* logits, const long long* label, const float* weight, const float* prob,
+                                  const float* out3, const float* gout, float* dlogits, const void* ws, int n, int c, int hw,
+                                  long long ignore, cudaStream_t s);
+
 }  // namespace fscnn

@@ -1,0 +1,610 @@
+// train.cu -- first slice of the training step (BASELINE config 5): the building blocks of
+// _DSConv / _DWConv / _ConvBNReLU(1x1) / LinearBottleneck in TRAINING mode and the OHEM loss, forward and backward, as
+// fp32 CUDA kernels behind the C ABI (fscnn_train_* in include/fscnn_b200.h).
+//
+//   depthwise 3x3 (pad 1, stride 1/2, groups = C)   nn.Conv2d(c, c, 3, s, 1, groups=c)      models/fast_scnn.py:70, :86
+//   pointwise 1x1                                    nn.Conv2d(cin, cout, 1)                 models/fast_scnn.py:73, :107
+//   BatchNorm2d, batch statistics (+ ReLU)           nn.BatchNorm2d in train mode            models/fast_scnn.py:71-75
+//   SoftmaxCrossEntropyOHEMLoss                      utils/loss.py:127-182 (host numpy argsort -> device radix select)
+//
+// Tensors keep PyTorch's layout (NCHW fp32, contiguous) because autograd hands them over that way; every reduction is
+// two-stage (per-CTA partials in a caller-provided workspace, then one finalising CTA) so results do not depend on atomics
+// ordering.  These kernels are the parity-checked reference point of the training path (tests/test_gpu_train.py against
+// torch.autograd of the unmodified reference modules); the tensor-core / fused versions of the eval path's design are the
+// next step of this row and are NOT claimed here.
+#include <cfloat>
+
+#include "kernels.h"
+
+namespace fscnn {
+
+namespace {
+constexpr int kT = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sumf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// sums NV values per thread over the CTA; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sm /* [NV][8] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = warp_sum(v[i]);
+        if (lane == 0) sm[i * 8 + warp] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+            for (int w = 0; w < kT / 32; ++w) s += sm[i * 8 + w];
+            v[i] = s;
+        }
+    }
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// depthwise 3x3, pad 1
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
+              int stride, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+        const long long plane = i / ((long long)Wo * Ho);
+        const int c = (int)(plane % C);
+        const float* xp = x + plane * H * W;
+        const float* wp = w + c * 9;
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * stride + ky - 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * stride + kx - 1;
+                if (ix >= 0 && ix < W) acc = fmaf(__ldg(xp + (long long)iy * W + ix), __ldg(wp + ky * 3 + kx), acc);
+            }
+        }
+        y[i] = acc;
+    }
+}
+
+// dx[n,c,iy,ix] = sum over the taps (ky,kx) with oy*s + ky - 1 == iy, ox*s + kx - 1 == ix of dy[n,c,oy,ox] * w[c,ky,kx]
+__global__ void __launch_bounds__(kT)
+dw_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int C, int H, int W, int Ho,
+                   int Wo, int stride, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int ix = (int)(i % W), iy = (int)((i / W) % H);
+        const long long plane = i / ((long long)W * H);
+        const int c = (int)(plane % C);
+        const float* dp = dy + plane * Ho * Wo;
+        const float* wp = w + c * 9;
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ty = iy + 1 - ky;
+            if (ty < 0 || ty % stride) continue;
+            const int oy = ty / stride;
+            if (oy >= Ho) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tx = ix + 1 - kx;
+                if (tx < 0 || tx % stride) continue;
+                const int ox = tx / stride;
+                if (ox < Wo) acc = fmaf(__ldg(dp + (long long)oy * Wo + ox), __ldg(wp + ky * 3 + kx), acc);
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+// dw[c,ky,kx] = sum over n,oy,ox of dy[n,c,oy,ox] * x[n,c,oy*s+ky-1,ox*s+kx-1].  grid (C, S): partial[s][c][9] (double)
+__global__ void __launch_bounds__(kT)
+dw_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ partial, int N, int C, int H,
+                     int W, int Ho, int Wo, int stride) {
+    __shared__ double sm[9 * 8];
+    const int c = blockIdx.x, S = gridDim.y;
+    double acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = 0.0;
+    const long long per = (long long)N * Ho * Wo;
+    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT) {
+        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho), n = (int)(i / ((long long)Wo * Ho));
+        const float g = __ldg(dy + (((long long)n * C + c) * Ho + oy) * Wo + ox);
+        const float* xp = x + ((long long)n * C + c) * H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * stride + ky - 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * stride + kx - 1;
+                if (ix >= 0 && ix < W) acc[ky * 3 + kx] += (double)g * (double)__ldg(xp + (long long)iy * W + ix);
+            }
+        }
+    }
+    block_sum<9>(acc, sm);
+    if (threadIdx.x == 0)
+        for (int t = 0; t < 9; ++t) partial[((long long)blockIdx.y * C + c) * 9 + t] = acc[t];
+}
+
+// out[i] = sum_s partial[s][i]
+__global__ void __launch_bounds__(kT)
+reduce_partials_kernel(const double* __restrict__ partial, float* __restrict__ out, int count, int S) {
+    const int i = blockIdx.x * kT + threadIdx.x;
+    if (i >= count) return;
+    double s = 0.0;
+    for (int k = 0; k < S; ++k) s += partial[(long long)k * count + i];
+    out[i] = (float)s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pointwise 1x1 as a tiled fp32 GEMM with generic operand strides:
+//   C[b][m][j] (+)= sum_k A(b, m, k) * B(b, k, j),  A(b,m,k) = A[b*sAb + m*sAm + k*sAk],  B(b,k,j) = B[b*sBb + k*sBk + j*sBj]
+//   forward      : A = W[cout][cin] (sAb 0),            B = x[n] ([cin][hw]),        C = y[n]
+//   data gradient: A = W^T (sAm 1, sAk cin),            B = dy[n] ([cout][hw]),      C = dx[n]
+//   weight grad. : A = dy[n] ([cout][hw]),              B = x[n]^T (sBk 1, sBj hw),  C = partial[b] ([cout][cin]), then reduced
+// 64 x 64 tile, K chunks of 16, 256 threads x (4 x 4) outputs.  `splitk` CTAs along grid.z share one batch item's K range.
+// ---------------------------------------------------------------------------------------------------------------------
+struct GemmArgs {
+    const float *A, *B;
+    float* C;
+    int M, N, K;
+    long long sAb, sAm, sAk, sBb, sBk, sBj, sCb;
+    int ldc, splitk;
+};
+
+__global__ void __launch_bounds__(kT)
+gemm_kernel(GemmArgs g) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4], Bs[BK][BN + 4];
+    const int b = blockIdx.z / g.splitk, sk = blockIdx.z % g.splitk;
+    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, tm = tid / 16, tj = tid % 16;
+    const float* A = g.A + b * g.sAb;
+    const float* B = g.B + b * g.sBb;
+    const int kper = ((g.K + g.splitk - 1) / g.splitk + BK - 1) / BK * BK;
+    const int k_begin = sk * kper, k_end = min(g.K, k_begin + kper);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // thread order inside a tile load follows the unit-stride dimension of the operand
+    const bool a_k_fast = g.sAk == 1, b_j_fast = g.sBj == 1;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        for (int i = tid; i < BM * BK; i += kT) {
+            const int k = a_k_fast ? i % BK : i / BM, m = a_k_fast ? i / BK : i % BM;
+            As[k][m] = (m0 + m < g.M && k0 + k < k_end) ? __ldg(A + (long long)(m0 + m) * g.sAm + (long long)(k0 + k) * g.sAk) : 0.f;
+        }
+        for (int i = tid; i < BN * BK; i += kT) {
+            const int j = b_j_fast ? i % BN : i / BK, k = b_j_fast ? i / BN : i % BK;
+            Bs[k][j] = (j0 + j < g.N && k0 + k < k_end) ? __ldg(B + (long long)(k0 + k) * g.sBk + (long long)(j0 + j) * g.sBj) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tj * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* C = g.C + (long long)blockIdx.z * g.sCb;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + tm * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jj = j0 + tj * 4 + j;
+            if (jj < g.N) C[(long long)m * g.ldc + jj] = acc[i][j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+reduce_partials_f_kernel(const float* __restrict__ partial, float* __restrict__ out, int count, int S) {
+    const int i = blockIdx.x * kT + threadIdx.x;
+    if (i >= count) return;
+    double s = 0.0;
+    for (int k = 0; k < S; ++k) s += (double)partial[(long long)k * count + i];
+    out[i] = (float)s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BatchNorm2d with batch statistics (train mode) + optional ReLU
+// ---------------------------------------------------------------------------------------------------------------------
+// grid (C, S): partial[s][c][2] = {sum x, sum x^2} over this CTA's share of the N*HW values of channel c
+__global__ void __launch_bounds__(kT)
+bn_stats_kernel(const float* __restrict__ x, double* __restrict__ partial, int N, int C, int HW) {
+    __shared__ double sm[2 * 8];
+    const int c = blockIdx.x, S = gridDim.y;
+    double v[2] = {0.0, 0.0};
+    const long long per = (long long)N * HW;
+    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT) {
+        const int n = (int)(i / HW), p = (int)(i % HW);
+        const double t = (double)__ldg(x + ((long long)n * C + c) * HW + p);
+        v[0] += t; v[1] += t * t;
+    }
+    block_sum<2>(v, sm);
+    if (threadIdx.x == 0) { partial[((long long)blockIdx.y * C + c) * 2] = v[0]; partial[((long long)blockIdx.y * C + c) * 2 + 1] = v[1]; }
+}
+
+// mean / biased variance -> save_mean, save_rstd; running stats with momentum and the UNBIASED variance (PyTorch semantics)
+__global__ void __launch_bounds__(kT)
+bn_finalize_kernel(const double* __restrict__ partial, int C, int S, long long count, float eps, float momentum,
+                   float* __restrict__ save_mean, float* __restrict__ save_rstd, float* __restrict__ running_mean,
+                   float* __restrict__ running_var) {
+    const int c = blockIdx.x * kT + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < S; ++k) { s += partial[((long long)k * C + c) * 2]; ss += partial[((long long)k * C + c) * 2 + 1]; }
+    const double mean = s / (double)count;
+    double var = ss / (double)count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int C, int HW, int relu,
+                long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int c = (int)((i / HW) % C);
+        float v = (x[i] - __ldg(mean + c)) * __ldg(rstd + c) * __ldg(gamma + c) + __ldg(beta + c);
+        if (relu) v = fmaxf(v, 0.f);
+        y[i] = v;
+    }
+}
+
+// grid (C, S): partial[s][c][2] = {sum g, sum g * xhat}, g = dy masked by the ReLU (y > 0) when relu
+__global__ void __launch_bounds__(kT)
+bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ partial, int N, int C,
+                     int HW, int relu) {
+    __shared__ double sm[2 * 8];
+    const int c = blockIdx.x, S = gridDim.y;
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    double v[2] = {0.0, 0.0};
+    const long long per = (long long)N * HW;
+    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT) {
+        const int n = (int)(i / HW), p = (int)(i % HW);
+        const long long e = ((long long)n * C + c) * HW + p;
+        float g = __ldg(dy + e);
+        if (relu && !(__ldg(y + e) > 0.f)) g = 0.f;
+        v[0] += (double)g;
+        v[1] += (double)g * (double)((__ldg(x + e) - mu) * rs);
+    }
+    block_sum<2>(v, sm);
+    if (threadIdx.x == 0) { partial[((long long)blockIdx.y * C + c) * 2] = v[0]; partial[((long long)blockIdx.y * C + c) * 2 + 1] = v[1]; }
+}
+
+// dbeta = sum g, dgamma = sum g*xhat; dx = gamma * rstd * (g - dbeta/m - xhat * dgamma/m)
+__global__ void __launch_bounds__(kT)
+bn_bwd_finalize_kernel(const double* __restrict__ partial, int C, int S, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * kT + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < S; ++k) { s += partial[((long long)k * C + c) * 2]; ss += partial[((long long)k * C + c) * 2 + 1]; }
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)ss;
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx, int C, int HW,
+                    int relu, float inv_count, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int c = (int)((i / HW) % C);
+        float g = dy[i];
+        if (relu && !(y[i] > 0.f)) g = 0.f;
+        const float rs = __ldg(rstd + c), xh = (x[i] - __ldg(mean + c)) * rs;
+        dx[i] = __ldg(gamma + c) * rs * (g - __ldg(dbeta + c) * inv_count - xh * __ldg(dgamma + c) * inv_count);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SoftmaxCrossEntropyOHEMLoss (utils/loss.py:143-182) on the device
+//   1. prob[p] = softmax(logits[:, p])[label[p]] for valid pixels (label != ignore), +inf-like sentinel otherwise
+//   2. keep-all if min_kept >= num_valid; else threshold = thresh, and if the min(num_valid, min_kept)-th smallest prob
+//      exceeds thresh the threshold becomes that value (loss.py:166-171): an exact order statistic by 4-pass radix select
+//      on the float bit patterns (probabilities are non-negative, so they order like unsigned integers)
+//   3. weighted cross entropy over the kept pixels, mean-reduced by the kept weights (nn.CrossEntropyLoss(weight, ignore))
+// ---------------------------------------------------------------------------------------------------------------------
+// state (device, int64/uint32 words): [0] num_valid, [1] selected prefix, [2] remaining rank, [3] threshold bits, [4] keep_all
+__global__ void __launch_bounds__(kT)
+ohem_prob_kernel(const float* __restrict__ logits, const long long* __restrict__ label, float* __restrict__ prob, int C, int HW,
+                 long long npix, long long ignore, unsigned long long* __restrict__ state) {
+    unsigned int valid = 0;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long n = i / HW, p = i % HW;
+        const long long lab = label[i];
+        float out = __uint_as_float(0x7f800000u);      // +inf: never selected, never kept
+        if (lab != ignore) {
+            valid += 1;
+            const float* lp = logits + n * C * HW + p;
+            float mx = -FLT_MAX;
+            for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(lp + (long long)c * HW));
+            float sum = 0.f, el = 0.f;
+            for (int c = 0; c < C; ++c) {           // same order as numpy's axis-0 sum (loss.py:153-155)
+                const float e = expf(__ldg(lp + (long long)c * HW) - mx);
+                sum += e;
+                if (c == lab) el = e;
+            }
+            out = el / sum;
+        }
+        prob[i] = out;
+    }
+    valid = (unsigned int)warp_sumf((float)valid) ;   // counts per warp stay below 2^24
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(state, (unsigned long long)valid);
+}
+
+// one radix pass: histogram of byte `shift/8` over the values whose higher bytes equal the selected prefix
+__global__ void __launch_bounds__(kT)
+ohem_hist_kernel(const float* __restrict__ prob, long long npix, int shift, const unsigned long long* __restrict__ state,
+                 unsigned int* __restrict__ hist) {
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned int prefix = (unsigned int)state[1];
+    const unsigned int mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const unsigned int b = __float_as_uint(prob[i]);
+        if (b < 0x7f800000u && (b & mask) == (prefix & mask)) atomicAdd(&h[(b >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// picks the bucket that holds the wanted rank, narrows prefix / rank; after the last pass fixes the threshold
+__global__ void ohem_select_kernel(unsigned long long* __restrict__ state, unsigned int* __restrict__ hist, int shift, int min_kept,
+                                   float thresh) {
+    if (threadIdx.x != 0) return;
+    if (shift == 24) {      // first pass: decide the mode
+        const unsigned long long nv = state[0];
+        state[4] = ((unsigned long long)min_kept >= nv) ? 1ull : 0ull;
+        state[1] = 0ull;
+        const unsigned long long k = nv < (unsigned long long)min_kept ? nv : (unsigned long long)min_kept;
+        state[2] = k > 0 ? k - 1 : 0;      // 0-based rank of the order statistic (loss.py:168)
+        state[3] = (unsigned long long)__float_as_uint(thresh);
+    }
+    unsigned long long rank = state[2];
+    unsigned int prefix = (unsigned int)state[1];
+    for (int b = 0; b < 256; ++b) {
+        const unsigned int cnt = hist[b];
+        hist[b] = 0u;
+        if (rank < cnt) {
+            prefix |= (unsigned int)b << shift;
+            for (int r = b + 1; r < 256; ++r) hist[r] = 0u;
+            break;
+        }
+        rank -= cnt;
+    }
+    state[1] = prefix;
+    state[2] = rank;
+    if (shift == 0 && min_kept > 0 && state[0] > 0) {
+        const float kth = __uint_as_float(prefix);
+        if (kth > thresh) state[3] = (unsigned long long)prefix;      // loss.py:170-171
+    }
+}
+
+// per pixel: kept = valid && (keep_all || prob <= threshold); partial sums {sum w*nll, sum w} (double) per CTA
+__global__ void __launch_bounds__(kT)
+ohem_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ label, const float* __restrict__ prob,
+                 const float* __restrict__ weight, int C, int HW, long long npix, long long ignore,
+                 const unsigned long long* __restrict__ state, double* __restrict__ partial) {
+    __shared__ double sm[2 * 8];
+    const bool keep_all = state[4] != 0ull;
+    const float thr = __uint_as_float((unsigned int)state[3]);
+    double v[2] = {0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long lab = label[i];
+        if (lab == ignore || !(keep_all || prob[i] <= thr)) continue;
+        const long long n = i / HW, p = i % HW;
+        const float* lp = logits + n * C * HW + p;
+        float mx = -FLT_MAX;
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(lp + (long long)c * HW));
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(__ldg(lp + (long long)c * HW) - mx);
+        const float nll = -((__ldg(lp + lab * HW) - mx) - logf(sum));
+        const float w = weight ? __ldg(weight + lab) : 1.f;
+        v[0] += (double)w * (double)nll;
+        v[1] += (double)w;
+    }
+    block_sum<2>(v, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 2] = v[0]; partial[blockIdx.x * 2 + 1] = v[1]; }
+}
+
+// out[0] = loss = sum w*nll / sum w, out[1] = sum w, out[2] = kept-mode threshold (for inspection)
+__global__ void ohem_finalize_kernel(const double* __restrict__ partial, int nblocks, const unsigned long long* __restrict__ state,
+                                     float* __restrict__ out) {
+    if (threadIdx.x != 0) return;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < nblocks; ++i) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    out[0] = (float)(a / b);           // 0/0 = NaN when nothing is kept, like torch's mean over an empty selection
+    out[1] = (float)b;
+    out[2] = __uint_as_float((unsigned int)state[3]);
+}
+
+// dlogits[n,c,p] = gout * w[label]/sum_w * (softmax_c - [c == label]) on kept pixels, 0 elsewhere
+__global__ void __launch_bounds__(kT)
+ohem_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ label, const float* __restrict__ prob,
+                 const float* __restrict__ weight, int C, int HW, long long npix, long long ignore,
+                 const unsigned long long* __restrict__ state, const float* __restrict__ loss_out, const float* __restrict__ gout,
+                 float* __restrict__ dlogits) {
+    const bool keep_all = state[4] != 0ull;
+    const float thr = __uint_as_float((unsigned int)state[3]);
+    const float scale = __ldg(gout) / __ldg(loss_out + 1);
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long n = i / HW, p = i % HW;
+        const long long lab = label[i];
+        const float* lp = logits + n * C * HW + p;
+        float* dp = dlogits + n * C * HW + p;
+        if (lab == ignore || !(keep_all || prob[i] <= thr)) {
+            for (int c = 0; c < C; ++c) dp[(long long)c * HW] = 0.f;
+            continue;
+        }
+        float mx = -FLT_MAX;
+        for (int c = 0; c < C; ++c) mx = fmaxf(mx, __ldg(lp + (long long)c * HW));
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) sum += expf(__ldg(lp + (long long)c * HW) - mx);
+        const float w = (weight ? __ldg(weight + lab) : 1.f) * scale, inv = 1.f / sum;
+        for (int c = 0; c < C; ++c) {
+            const float sm_c = expf(__ldg(lp + (long long)c * HW) - mx) * inv;
+            dp[(long long)c * HW] = w * (sm_c - (c == lab ? 1.f : 0.f));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------------------------
+static int grid_for(long long total) {
+    long long b = (total + kT - 1) / kT;
+    const long long cap = (long long)num_sms() * 16;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+static int splits_for(int channels, long long per_channel) {
+    long long want = (long long)num_sms() * 4 / (channels > 0 ? channels : 1);
+    long long maxs = (per_channel + kT * 4 - 1) / (kT * 4);
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    if (want > 64) want = 64;
+    return (int)want;
+}
+
+size_t train_workspace_bytes(int channels_max, int cout, int cin) {
+    // reductions: 64 splits x channels x 9 doubles; pointwise weight gradient: up to 64 split-K partials of [cout][cin] floats
+    return (size_t)64 * channels_max * 9 * sizeof(double) + (size_t)64 * cout * cin * sizeof(float) + 4096;
+}
+
+cudaError_t launch_train_dw_fwd(const float* x, const float* w, float* y, int n, int c, int h, int wd, int stride, cudaStream_t s) {
+    const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
+    const long long total = (long long)n * c * ho * wo;
+    dw_fwd_kernel<<<grid_for(total), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, stride, total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, void* ws, int n, int c, int h,
+                                int wd, int stride, cudaStream_t s) {
+    const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
+    if (dx) {
+        const long long total = (long long)n * c * h * wd;
+        dw_bwd_data_kernel<<<grid_for(total), kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, stride, total);
+    }
+    if (dw) {
+        const int S = splits_for(c, (long long)n * ho * wo);
+        dw_bwd_weight_kernel<<<dim3(c, S), kT, 0, s>>>(x, dy, reinterpret_cast<double*>(ws), n, c, h, wd, ho, wo, stride);
+        reduce_partials_kernel<<<(c * 9 + kT - 1) / kT, kT, 0, s>>>(reinterpret_cast<const double*>(ws), dw, c * 9, S);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_pw_fwd(const float* x, const float* w, float* y, int n, int cin, int cout, int hw, cudaStream_t s) {
+    GemmArgs g{w, x, y, cout, hw, cin, 0, cin, 1, (long long)cin * hw, hw, 1, (long long)cout * hw, hw, 1};
+    gemm_kernel<<<dim3((hw + 63) / 64, (cout + 63) / 64, n), kT, 0, s>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, void* ws, int n, int cin,
+                                int cout, int hw, cudaStream_t s) {
+    if (dx) {      // dx[n] = W^T dy[n]
+        GemmArgs g{w, dy, dx, cin, hw, cout, 0, 1, cin, (long long)cout * hw, hw, 1, (long long)cin * hw, hw, 1};
+        gemm_kernel<<<dim3((hw + 63) / 64, (cin + 63) / 64, n), kT, 0, s>>>(g);
+    }
+    if (dw) {      // dW = sum_n dy[n] x[n]^T, split over the pixels of every image
+        int splitk = (int)((long long)num_sms() * 2 / ((long long)n * ((cin + 63) / 64) * ((cout + 63) / 64)));
+        const int maxk = (hw + 255) / 256;
+        if (splitk > maxk) splitk = maxk;
+        if (splitk < 1) splitk = 1;
+        while ((long long)n * splitk > 64) { if (splitk > 1) --splitk; else break; }
+        const int parts = n * splitk;
+        float* partial = reinterpret_cast<float*>(ws);
+        if (parts > 64) return cudaErrorInvalidValue;      // the caller chunks the batch (train_workspace_bytes holds 64 partials)
+        GemmArgs g{dy, x, partial, cout, cin, hw, (long long)cout * hw, hw, 1, (long long)cin * hw, 1, hw, (long long)cout * cin, cin, splitk};
+        gemm_kernel<<<dim3((cin + 63) / 64, (cout + 63) / 64, parts), kT, 0, s>>>(g);
+        reduce_partials_f_kernel<<<(cout * cin + kT - 1) / kT, kT, 0, s>>>(partial, dw, cout * cin, parts);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                float* y, float* save_mean, float* save_rstd, void* ws, int n, int c, int hw, float eps,
+                                float momentum, int relu, cudaStream_t s) {
+    const int S = splits_for(c, (long long)n * hw);
+    double* partial = reinterpret_cast<double*>(ws);
+    bn_stats_kernel<<<dim3(c, S), kT, 0, s>>>(x, partial, n, c, hw);
+    bn_finalize_kernel<<<(c + kT - 1) / kT, kT, 0, s>>>(partial, c, S, (long long)n * hw, eps, momentum, save_mean, save_rstd,
+                                                         running_mean, running_var);
+    const long long total = (long long)n * c * hw;
+    bn_apply_kernel<<<grid_for(total), kT, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, c, hw, relu, total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                                const float* save_rstd, float* dx, float* dgamma, float* dbeta, void* ws, int n, int c, int hw,
+                                int relu, cudaStream_t s) {
+    const int S = splits_for(c, (long long)n * hw);
+    double* partial = reinterpret_cast<double*>(ws);
+    bn_bwd_reduce_kernel<<<dim3(c, S), kT, 0, s>>>(x, y, dy, save_mean, save_rstd, partial, n, c, hw, relu);
+    bn_bwd_finalize_kernel<<<(c + kT - 1) / kT, kT, 0, s>>>(partial, c, S, dgamma, dbeta);
+    const long long total = (long long)n * c * hw;
+    bn_bwd_apply_kernel<<<grid_for(total), kT, 0, s>>>(x, y, dy, save_mean, save_rstd, gamma, dgamma, dbeta, dx, c, hw, relu,
+                                                       1.f / (float)((long long)n * hw), total);
+    return cudaGetLastError();
+}
+
+// ws layout: [0,64) state (8 x u64) | [64, 64+1024) radix histogram | then 2 doubles per CTA of the loss kernel
+cudaError_t launch_train_ohem_fwd(const float* logits, const long long* label, const float* weight, float* prob, float* out3, void* ws,
+                                  int n, int c, int hw, long long ignore, float thresh, int min_kept, cudaStream_t s) {
+    const long long npix = (long long)n * hw;
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(ws);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + 64);
+    double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 64 + 1024);
+    cudaError_t e = cudaMemsetAsync(ws, 0, 64 + 1024, s);
+    if (e != cudaSuccess) return e;
+    const int grid = grid_for(npix);
+    ohem_prob_kernel<<<grid, kT, 0, s>>>(logits, label, prob, c, hw, npix, ignore, state);
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        ohem_hist_kernel<<<grid, kT, 0, s>>>(prob, npix, shift, state, hist);
+        ohem_select_kernel<<<1, 32, 0, s>>>(state, hist, shift, min_kept, thresh);
+    }
+    ohem_loss_kernel<<<grid, kT, 0, s>>>(logits, label, prob, weight, c, hw, npix, ignore, state, partial);
+    ohem_finalize_kernel<<<1, 32, 0, s>>>(partial, grid, state, out3);
+    return cudaGetLastError();
+}
+
+size_t train_ohem_workspace_bytes() { return 64 + 1024 + (size_t)num_sms() * 16 * 2 * sizeof(double) + 256; }
+
+cudaError_t launch_train_ohem_bwd(const float* logits, const long long* label, const float* weight, const float* prob,
+                                  const float* out3, const float* gout, float* dlogits, const void* ws, int n, int c, int hw,
+                                  long long ignore, cudaStream_t s) {
+    const long long npix = (long long)n * hw;
+    ohem_grad_kernel<<<grid_for(npix), kT, 0, s>>>(logits, label, prob, weight, c, hw, npix, ignore,
+                                                   reinterpret_cast<const unsigned long long*>(ws), out3, gout, dlogits);
+    return cudaGetLastError();
+}
+
+}  // namespace fscnn

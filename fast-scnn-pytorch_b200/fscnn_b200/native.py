@@ -64,6 +64,24 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'fscnn_conf_to_totals': (C.c_int, [C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong),
                                        C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    'fscnn_train_workspace_bytes': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    'fscnn_train_dwconv3x3_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_dwconv3x3_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_pwconv_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_pwconv_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_batchnorm_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                                C.c_int, C.c_void_p]),
+    'fscnn_train_batchnorm_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p]),
+    'fscnn_train_ohem_workspace_bytes': (C.c_int, [C.POINTER(C.c_size_t)]),
+    'fscnn_train_ohem_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                           C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_void_p]),
+    'fscnn_train_ohem_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]),
     'fscnn_stage_count': (C.c_int, [C.c_void_p]),
     'fscnn_stage_name': (C.c_char_p, [C.c_void_p, C.c_int]),
     'fscnn_forward_range': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -1,0 +1,225 @@
+"""Training-mode operators of the covered modules (first slice) as ``torch.autograd.Function``s
+over the C ABI (``fscnn_train_*`` in include/fscnn_b200.h, kernels in csrc/train.cu).
+
+What is covered: depthwise 3x3 conv, pointwise 1x1 conv, BatchNorm2d with batch statistics (+ the ReLU behind it) -- which is
+everything ``_DSConv``, ``_DWConv``, ``_ConvBNReLU(k=1)`` and ``LinearBottleneck`` (reference models/fast_scnn.py:49-115) do
+in ``model.train()`` -- and ``SoftmaxCrossEntropyOHEMLoss`` (utils/loss.py:127-182).  Tensors are fp32 NCHW CUDA tensors;
+there is no CPU path and no fallback to ATen's convolution / batch-norm kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import native
+
+_ws_cache = {}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(device: torch.device, channels: int, cout: int = 1, cin: int = 1) -> torch.Tensor:
+    need = C.c_size_t()
+    native.check(native.lib().fscnn_train_workspace_bytes(int(channels), int(cout), int(cin), C.byref(need)))
+    ws = _ws_cache.get(device)
+    if ws is None or ws.numel() < need.value:
+        ws = _ws_cache[device] = torch.empty(need.value, dtype=torch.uint8, device=device)
+    return ws
+
+
+def _check(x: torch.Tensor, what: str) -> torch.Tensor:
+    if not x.is_cuda:
+        raise RuntimeError(f'{what} is on {x.device}: the training operators run on CUDA devices only (there is no CPU fallback)')
+    if x.dtype != torch.float32:
+        raise ValueError(f'{what} must be float32, got {x.dtype}')
+    return x.contiguous()
+
+
+class DepthwiseConv3x3(torch.autograd.Function):
+    """nn.Conv2d(c, c, 3, stride, 1, groups=c, bias=False)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        x, w = _check(x, 'input'), _check(weight, 'weight')
+        n, c, h, wd = x.shape
+        if tuple(w.shape) != (c, 1, 3, 3):
+            raise ValueError(f'depthwise weight must be [{c},1,3,3], got {tuple(w.shape)}')
+        ho, wo = (h - 1) // stride + 1, (wd - 1) // stride + 1
+        y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            native.check(native.lib().fscnn_train_dwconv3x3_forward(x.data_ptr(), w.data_ptr(), y.data_ptr(), n, c, h, wd, stride, _stream()),
+                         'fscnn_train_dwconv3x3_forward')
+        ctx.save_for_backward(x, w)
+        ctx.stride = stride
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, c, h, wd = x.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        if dx is None and dw is None:
+            return None, None, None
+        ws = _workspace(x.device, c)
+        with torch.cuda.device(x.device):
+            native.check(native.lib().fscnn_train_dwconv3x3_backward(
+                x.data_ptr(), w.data_ptr(), dy.data_ptr(), dx.data_ptr() if dx is not None else None,
+                dw.data_ptr() if dw is not None else None, ws.data_ptr(), ws.numel(), n, c, h, wd, ctx.stride, _stream()),
+                'fscnn_train_dwconv3x3_backward')
+        return dx, dw, None
+
+
+class PointwiseConv(torch.autograd.Function):
+    """nn.Conv2d(cin, cout, 1, bias=False)"""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x, w = _check(x, 'input'), _check(weight, 'weight')
+        n, cin, h, wd = x.shape
+        cout = w.shape[0]
+        if tuple(w.shape) != (cout, cin, 1, 1):
+            raise ValueError(f'pointwise weight must be [cout,{cin},1,1], got {tuple(w.shape)}')
+        y = torch.empty((n, cout, h, wd), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            native.check(native.lib().fscnn_train_pwconv_forward(x.data_ptr(), w.data_ptr(), y.data_ptr(), n, cin, cout, h * wd, _stream()),
+                         'fscnn_train_pwconv_forward')
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, cin, h, wd = x.shape
+        cout = w.shape[0]
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.zeros_like(w) if need_dw else None
+        if dx is None and dw is None:
+            return None, None
+        ws = _workspace(x.device, 1, cout, cin)
+        with torch.cuda.device(x.device):
+            for i0 in range(0, n, 64):          # the weight gradient takes at most 64 images per call
+                m = min(64, n - i0)
+                part = torch.empty_like(w) if (need_dw and n > 64) else dw
+                native.check(native.lib().fscnn_train_pwconv_backward(
+                    x[i0:i0 + m].data_ptr(), w.data_ptr(), dy[i0:i0 + m].data_ptr(), dx[i0:i0 + m].data_ptr() if need_dx else None,
+                    part.data_ptr() if need_dw else None, ws.data_ptr(), ws.numel(), m, cin, cout, h * wd, _stream()),
+                    'fscnn_train_pwconv_backward')
+                if need_dw and n > 64:
+                    dw += part
+        return dx, dw
+
+
+class BatchNormReLU(torch.autograd.Function):
+    """nn.BatchNorm2d in training mode (batch statistics, in-place running-statistics update) + optional nn.ReLU"""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, relu):
+        x, gamma, beta = _check(x, 'input'), _check(gamma, 'weight'), _check(beta, 'bias')
+        n, c, h, wd = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        ws = _workspace(x.device, c)
+        with torch.cuda.device(x.device):
+            native.check(native.lib().fscnn_train_batchnorm_forward(
+                x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr() if running_mean is not None else None,
+                running_var.data_ptr() if running_var is not None else None, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                ws.data_ptr(), ws.numel(), n, c, h * wd, float(eps), float(momentum), int(bool(relu)), _stream()),
+                'fscnn_train_batchnorm_forward')
+        # the running statistics are buffers (no gradient) updated in place by the kernel; autograd does not track them.
+        # batchnorm_relu() bumps num_batches_tracked, which is what tells FastSCNN's eval engine to re-fold its weights.
+        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        ctx.relu = bool(relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        n, c, h, wd = x.shape
+        dx, dgamma, dbeta = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
+        ws = _workspace(x.device, c)
+        with torch.cuda.device(x.device):
+            native.check(native.lib().fscnn_train_batchnorm_backward(
+                x.data_ptr(), y.data_ptr(), dy.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), n, c, h * wd, int(ctx.relu), _stream()),
+                'fscnn_train_batchnorm_backward')
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+class OhemCrossEntropy(torch.autograd.Function):
+    """SoftmaxCrossEntropyOHEMLoss.forward (reference utils/loss.py:143-182) on the device"""
+
+    @staticmethod
+    def forward(ctx, logits, target, class_weight, ignore_label, thresh, min_kept):
+        logits = _check(logits, 'logits')
+        if target.dtype != torch.int64 or target.dim() != 3 or not target.is_cuda:
+            raise ValueError('target must be a CUDA int64 [N,H,W] tensor')
+        n, c, h, w = logits.shape
+        if tuple(target.shape) != (n, h, w):
+            raise ValueError(f'target shape {tuple(target.shape)} does not match logits {tuple(logits.shape)}')
+        target = target.contiguous()
+        if class_weight is not None:
+            class_weight = _check(class_weight, 'class weight')
+            if class_weight.numel() != c:
+                raise ValueError(f'class weight has {class_weight.numel()} entries for {c} classes')
+        need = C.c_size_t()
+        native.check(native.lib().fscnn_train_ohem_workspace_bytes(C.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=logits.device)
+        prob = torch.empty((n, h, w), dtype=torch.float32, device=logits.device)
+        out3 = torch.empty(3, dtype=torch.float32, device=logits.device)
+        with torch.cuda.device(logits.device):
+            native.check(native.lib().fscnn_train_ohem_forward(
+                logits.data_ptr(), target.data_ptr(), class_weight.data_ptr() if class_weight is not None else None, prob.data_ptr(),
+                out3.data_ptr(), ws.data_ptr(), ws.numel(), n, c, h * w, int(ignore_label), float(thresh), int(min_kept), _stream()),
+                'fscnn_train_ohem_forward')
+        ctx.save_for_backward(logits, target, prob, out3, ws)
+        ctx.class_weight, ctx.ignore_label = class_weight, int(ignore_label)
+        ctx.mark_non_differentiable(target)
+        return out3[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, target, prob, out3, ws = ctx.saved_tensors
+        n, c, h, w = logits.shape
+        dlogits = torch.empty_like(logits)
+        g = gout.to(torch.float32).reshape(1).contiguous()
+        cw = ctx.class_weight
+        with torch.cuda.device(logits.device):
+            native.check(native.lib().fscnn_train_ohem_backward(
+                logits.data_ptr(), target.data_ptr(), cw.data_ptr() if cw is not None else None, prob.data_ptr(), out3.data_ptr(),
+                g.data_ptr(), dlogits.data_ptr(), ws.data_ptr(), n, c, h * w, ctx.ignore_label, _stream()), 'fscnn_train_ohem_backward')
+        return dlogits, None, None, None, None, None
+
+
+def depthwise_conv3x3(x, weight, stride=1):
+    return DepthwiseConv3x3.apply(x, weight, int(stride))
+
+
+def pointwise_conv(x, weight):
+    return PointwiseConv.apply(x, weight)
+
+
+def batchnorm_relu(x, bn: torch.nn.BatchNorm2d, relu: bool):
+    """``bn`` in training mode followed by ReLU when ``relu``; updates ``bn``'s running statistics like nn.BatchNorm2d does
+    (momentum None = cumulative average is not used by the reference and is not supported)."""
+    if bn.momentum is None:
+        raise NotImplementedError('BatchNorm2d(momentum=None) is not used by the reference and not supported')
+    track = bn.track_running_stats and bn.running_mean is not None
+    y = BatchNormReLU.apply(x, bn.weight, bn.bias, bn.running_mean if track else None, bn.running_var if track else None,
+                            bn.eps, bn.momentum, relu)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return y
+
+
+def ohem_cross_entropy(logits, target, class_weight: Optional[torch.Tensor] = None, ignore_label=-1, thresh=0.7, min_kept=256):
+    return OhemCrossEntropy.apply(logits, target, class_weight, ignore_label, thresh, min_kept)

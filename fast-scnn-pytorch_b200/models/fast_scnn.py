@@ -44,11 +44,50 @@ IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
 
 class _ParamHolder(nn.Module):
-    """Base of the parameter-holding submodules: they are never called on their own."""
+    """Base of the parameter-holding submodules.  In eval mode they are never called on their own (the fused CUDA path has
+    no per-module entry point); in TRAINING mode the covered ones (ConvBNReLU 1x1, DSConv, DWConv, LinearBottleneck: the
+    first slice of SURVEY.md section 8 row f3) run through the training operators of fscnn_b200/train_ops.py and are
+    differentiable with ordinary ``loss.backward()``."""
 
-    def forward(self, *args, **kwargs):  # pragma: no cover - guard
-        raise RuntimeError(f'{type(self).__name__} only holds parameters; call FastSCNN.forward / predict / evaluate '
+    def forward(self, *args, **kwargs):
+        if self.training:
+            return self._train_forward(*args, **kwargs)
+        raise RuntimeError(f'{type(self).__name__} only holds parameters in eval mode; call FastSCNN.forward / predict / evaluate '
                            '(the fused CUDA path has no per-module entry point and no CPU fallback)')
+
+    def _train_forward(self, *args, **kwargs):
+        raise NotImplementedError(f'{type(self).__name__} has no training-mode forward yet: the training step covers ConvBNReLU '
+                                  '(1x1), DSConv, DWConv and LinearBottleneck so far (there is no eager-PyTorch fallback)')
+
+
+def _train_seq(seq, x):
+    """Runs an nn.Sequential of the covered layer kinds in training mode through the CUDA training operators: depthwise 3x3
+    / pointwise 1x1 convolutions without bias, BatchNorm2d with batch statistics fused with the ReLU that follows it."""
+    from fscnn_b200 import train_ops
+    layers = list(seq)
+    i = 0
+    while i < len(layers):
+        m = layers[i]
+        if isinstance(m, nn.Conv2d):
+            if m.bias is not None or m.dilation != (1, 1):
+                raise NotImplementedError('training operators cover bias-free, undilated convolutions')
+            if m.kernel_size == (1, 1) and m.groups == 1 and m.stride == (1, 1) and m.padding == (0, 0):
+                x = train_ops.pointwise_conv(x, m.weight)
+            elif m.kernel_size == (3, 3) and m.groups == m.in_channels == m.out_channels and m.padding == (1, 1) and m.stride[0] == m.stride[1]:
+                x = train_ops.depthwise_conv3x3(x, m.weight, m.stride[0])
+            else:
+                raise NotImplementedError(f'no training operator for {m} yet (covered: depthwise 3x3 pad 1, pointwise 1x1)')
+            i += 1
+        elif isinstance(m, nn.BatchNorm2d):
+            relu = i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU)
+            x = train_ops.batchnorm_relu(x, m, relu)
+            i += 2 if relu else 1
+        elif isinstance(m, _ParamHolder):
+            x = m(x)
+            i += 1
+        else:
+            raise NotImplementedError(f'no training operator for {type(m).__name__} yet')
+    return x
 
 
 def _conv_bn_relu(cin, cout, k=3, stride=1, padding=0):
@@ -62,6 +101,9 @@ class ConvBNReLU(_ParamHolder):
         super().__init__()
         self.conv = _conv_bn_relu(cin, cout, k, stride, padding)
 
+    def _train_forward(self, x):
+        return _train_seq(self.conv, x)
+
 
 class DSConv(_ParamHolder):
     """Depthwise 3x3 + BN + ReLU, pointwise 1x1 + BN + ReLU: ``conv.0,1,3,4`` (reference _DSConv, :64-79)."""
@@ -72,6 +114,9 @@ class DSConv(_ParamHolder):
             nn.Conv2d(channels, channels, 3, stride, 1, groups=channels, bias=False), nn.BatchNorm2d(channels),
             nn.ReLU(True), nn.Conv2d(channels, cout, 1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(True))
 
+    def _train_forward(self, x):
+        return _train_seq(self.conv, x)
+
 
 class DWConv(_ParamHolder):
     """Depthwise 3x3 + BN + ReLU: ``conv.0,1`` (reference _DWConv, :82-92)."""
@@ -80,6 +125,9 @@ class DWConv(_ParamHolder):
         super().__init__()
         self.conv = nn.Sequential(nn.Conv2d(channels, cout, 3, stride, 1, groups=channels, bias=False),
                                   nn.BatchNorm2d(cout), nn.ReLU(True))
+
+    def _train_forward(self, x):
+        return _train_seq(self.conv, x)
 
 
 class LinearBottleneck(_ParamHolder):
@@ -91,6 +139,10 @@ class LinearBottleneck(_ParamHolder):
         self.use_shortcut = stride == 1 and cin == cout
         self.block = nn.Sequential(ConvBNReLU(cin, cin * t, 1), DWConv(cin * t, cin * t, stride),
                                    nn.Conv2d(cin * t, cout, 1, bias=False), nn.BatchNorm2d(cout))
+
+    def _train_forward(self, x):
+        out = _train_seq(self.block, x)
+        return x + out if self.use_shortcut else out      # reference :111-115
 
 
 class PyramidPooling(_ParamHolder):
@@ -219,9 +271,10 @@ class FastSCNN(nn.Module):
     def _engine(self, device: torch.device):
         from fscnn_b200 import Engine
         if self.training:
-            raise NotImplementedError('FastSCNN (B200 build) implements the eval-mode forward path only; call '
-                                      'model.eval() first (the training step is a later milestone, and there is no '
-                                      'eager-PyTorch fallback)')
+            raise NotImplementedError('FastSCNN (B200 build): the whole-network forward runs in eval mode only; call '
+                                      'model.eval() first.  In training mode the covered submodules (ConvBNReLU 1x1, DSConv, '
+                                      'DWConv, LinearBottleneck) and fscnn_b200.train_ops.ohem_cross_entropy run on their own '
+                                      '(first slice of the training step); there is no eager-PyTorch fallback for the rest')
         if device.type != 'cuda':
             raise RuntimeError(f'FastSCNN (B200 build) runs on CUDA devices only, got a tensor on {device}; move the '
                                'model and the input to the GPU (there is no CPU fallback)')

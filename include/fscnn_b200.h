@@ -210,6 +210,49 @@ int fscnn_set_micro_batch(fscnn_ctx* ctx, int images);
  * "ffm_transposed" (FeatureFusionModule: resize on the tensor core), "ppm_tc" (PyramidPooling output stage). */
 int fscnn_set_option(fscnn_ctx* ctx, const char* key, int value);
 
+/* ---- training step, first slice (reference train.py:253-284) ------------------------------
+ * The building blocks of _DSConv / _DWConv / _ConvBNReLU(1x1) / LinearBottleneck in TRAINING mode (models/fast_scnn.py:49-115
+ * under model.train(): BatchNorm uses batch statistics and updates its running statistics) and of
+ * SoftmaxCrossEntropyOHEMLoss (utils/loss.py:127-182), forward and backward.  Tensors are fp32, contiguous, NCHW -- the layout
+ * torch.autograd hands them over in; `hw` = H*W.  Every call takes a caller-owned scratch buffer d_ws of at least
+ * fscnn_train_workspace_bytes(channels, cout, cin) bytes (16-byte aligned); reductions are two-stage and deterministic.
+ * The Python host wraps these in torch.autograd.Function (fscnn_b200/train_ops.py) so that the covered modules train through
+ * ordinary loss.backward().
+ *  dwconv3x3 : nn.Conv2d(c, c, 3, stride, 1, groups=c, bias=False)  (fast_scnn.py:70, :86)   d_w [c][3][3]
+ *  pwconv    : nn.Conv2d(cin, cout, 1, bias=False)                  (fast_scnn.py:73, :107)  d_w [cout][cin]
+ *  batchnorm : nn.BatchNorm2d(c) in train mode (+ the nn.ReLU that follows when relu != 0): y = (x - mean) * rstd * gamma + beta
+ *              with the batch's biased variance; d_running_mean / d_running_var (may both be NULL) are updated in place with
+ *              `momentum` and the unbiased variance, exactly like PyTorch; d_save_mean / d_save_rstd [c] feed the backward.
+ *              backward: d_dy is the gradient of the (ReLU'd) output y; d_y is needed for the ReLU mask when relu != 0.
+ * Any of d_dx / d_dw may be NULL in the conv backward calls when that gradient is not needed. */
+int fscnn_train_workspace_bytes(int max_channels, int max_cout, int max_cin, size_t* out_bytes);
+int fscnn_train_dwconv3x3_forward(const float* d_x, const float* d_w, float* d_y, int n, int c, int h, int w, int stride, void* stream);
+int fscnn_train_dwconv3x3_backward(const float* d_x, const float* d_w, const float* d_dy, float* d_dx, float* d_dw, void* d_ws,
+                                   size_t ws_bytes, int n, int c, int h, int w, int stride, void* stream);
+int fscnn_train_pwconv_forward(const float* d_x, const float* d_w, float* d_y, int n, int cin, int cout, int hw, void* stream);
+int fscnn_train_pwconv_backward(const float* d_x, const float* d_w, const float* d_dy, float* d_dx, float* d_dw, void* d_ws,
+                                size_t ws_bytes, int n, int cin, int cout, int hw, void* stream);
+int fscnn_train_batchnorm_forward(const float* d_x, const float* d_gamma, const float* d_beta, float* d_running_mean,
+                                  float* d_running_var, float* d_y, float* d_save_mean, float* d_save_rstd, void* d_ws, size_t ws_bytes,
+                                  int n, int c, int hw, float eps, float momentum, int relu, void* stream);
+int fscnn_train_batchnorm_backward(const float* d_x, const float* d_y, const float* d_dy, const float* d_gamma, const float* d_save_mean,
+                                   const float* d_save_rstd, float* d_dx, float* d_dgamma, float* d_dbeta, void* d_ws, size_t ws_bytes,
+                                   int n, int c, int hw, int relu, void* stream);
+
+/* SoftmaxCrossEntropyOHEMLoss.forward (utils/loss.py:143-182) without the host round trip: softmax probability of the target
+ * class per valid pixel (d_label int64 [n][hw], label != ignore_label), the min(num_valid, min_kept)-th smallest of them by an
+ * exact 4-pass radix select (replaces the host numpy argsort, loss.py:167-169), threshold = max(thresh, that value) unless
+ * min_kept >= num_valid (keep everything), then nn.CrossEntropyLoss(weight=d_class_weight or NULL, ignore_index) over the
+ * kept pixels.  d_prob [n][hw] float32 scratch that the backward re-reads; d_out3 = {loss, sum of kept weights, threshold};
+ * d_ws >= fscnn_train_ohem_workspace_bytes().  backward: d_dlogits [n][c][hw] = d_grad_out[0] * d loss / d logits. */
+int fscnn_train_ohem_workspace_bytes(size_t* out_bytes);
+int fscnn_train_ohem_forward(const float* d_logits, const long long* d_label, const float* d_class_weight, float* d_prob, float* d_out3,
+                             void* d_ws, size_t ws_bytes, int n, int c, int hw, long long ignore_label, float thresh, int min_kept,
+                             void* stream);
+int fscnn_train_ohem_backward(const float* d_logits, const long long* d_label, const float* d_class_weight, const float* d_prob,
+                              const float* d_out3, const float* d_grad_out, float* d_dlogits, const void* d_ws, int n, int c, int hw,
+                              long long ignore_label, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

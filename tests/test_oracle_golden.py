@@ -115,3 +115,19 @@ def test_torch_port_matches_reference(name):
     else:
         assert rel_err(logits[:, :, ::7, ::11], g['logits_sample']) < 2e-6
     assert (np.argmax(logits, 1) != g['mask']).mean() < 1e-4
+
+
+@pytest.mark.parametrize('name', ['train_ohem_kth', 'train_ohem_thresh', 'train_ohem_keepall', 'train_ohem_nc2'])
+def test_ohem_oracle_matches_reference_fixtures(name):
+    """The numpy restatement of SoftmaxCrossEntropyOHEMLoss (oracle/ohem_oracle.py) against loss / gradient vectors produced by
+    the unmodified reference under torch.autograd (oracle/gen_golden_train.py)."""
+    import os
+    import ohem_oracle as oo
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, name + '.npz'))
+    w = g['weight'] if g['weight'].size else None
+    loss, grad = oo.ohem_loss_and_grad(g['logits'], g['target'], w, -1, float(g['thresh']), int(g['min_kept']))
+    assert abs(loss - g['loss']) <= 1e-6 * abs(g['loss'])
+    assert np.abs(grad - g['dlogits']).max() <= 1e-6 * np.abs(g['dlogits']).max()
+    kept, thr = oo.ohem_select(g['logits'], g['target'], -1, float(g['thresh']), int(g['min_kept']))
+    assert np.array_equal(kept, np.abs(g['dlogits']).sum(1) > 0)
