@@ -11,7 +11,11 @@
 // are staged class-major in shared memory, so every class costs 9 conflict-free LDS per thread for
 // 32 output pixels.  Interpolation order matches ATen's upsample_bilinear2d: horizontal lerp first,
 // then vertical.  argmax keeps the FIRST maximal class and treats NaN as maximal, like torch.
+#include <cstdlib>
+
 #include "kernels.h"
+#include "tma_host.h"
+#include "umma.cuh"
 
 #include "../../include/fscnn_b200.h"
 
@@ -92,30 +96,45 @@ constexpr int kATH = kANW * 32;
 constexpr int kATR = kANW + 4;                   // staged low-res rows: 8 * kANW / 7.3 + 3 taps
 constexpr int kACS = kATR * kTC;                 // class stride of the staged tile
 constexpr int kACR = kATR - 1, kCC = kTC - 1;    // cells per staged tile
+constexpr int kCR = kTR - 1;                     // cell rows of the TMA kernel's 12-row box
 
-__device__ __forceinline__ unsigned int dominated_by(const float* __restrict__ Ls, int nc, int o, int ch, float margin) {
-    const float* pc = Ls + ch * kACS + o;
-    const float p0 = pc[0], p1 = pc[1], p2 = pc[kTC], p3 = pc[kTC + 1];
+// The staged logits come in two layouts: class-major [class][row][col] (PM = false: the staging loop of the direct kernel
+// transposes while it copies) and pixel-major [row][col][padded class] (PM = true: what a TMA box of the NHWC logits tensor
+// looks like).  `off` is the pixel index row * kTC + col in both.
+template <bool PM>
+__device__ __forceinline__ float ldl(const float* __restrict__ L, int c, int off, int ncp) {
+    return PM ? L[off * ncp + c] : L[c * kACS + off];
+}
+
+// o0..o3: pixel offsets of the cell's corners (row, col), (row, col+1), (row+1, col), (row+1, col+1), clamped at the image border
+template <bool PM>
+__device__ __forceinline__ unsigned int dominated_by(const float* __restrict__ L, int nc, int ncp, int o0, int o1, int o2, int o3,
+                                                     int ch, float margin) {
+    const float p0 = ldl<PM>(L, ch, o0, ncp), p1 = ldl<PM>(L, ch, o1, ncp), p2 = ldl<PM>(L, ch, o2, ncp), p3 = ldl<PM>(L, ch, o3, ncp);
     unsigned int elim = 0u;
+#pragma unroll 4
     for (int d = 0; d < nc; ++d) {
-        const float* pd = Ls + d * kACS + o;
-        const float m = fminf(fminf(p0 - pd[0], p1 - pd[1]), fminf(p2 - pd[kTC], p3 - pd[kTC + 1]));
+        const float m = fminf(fminf(p0 - ldl<PM>(L, d, o0, ncp), p1 - ldl<PM>(L, d, o1, ncp)),
+                              fminf(p2 - ldl<PM>(L, d, o2, ncp), p3 - ldl<PM>(L, d, o3, ncp)));
         const bool e = ch < d ? (m >= 0.f) : (m > margin);      // d == ch: m == 0 > margin is false
         elim |= (e ? 1u : 0u) << d;
     }
     return elim;
 }
 
-__device__ __forceinline__ unsigned int cell_survivors(const float* __restrict__ Ls, int nc, int o, float margin) {
+template <bool PM>
+__device__ __forceinline__ unsigned int cell_survivors(const float* __restrict__ L, int nc, int ncp, int o0, int o1, int o2, int o3,
+                                                       float margin) {
     int ch0 = 0, ch3 = 0;
-    float b0 = Ls[o], b3 = Ls[o + kTC + 1];
+    float b0 = ldl<PM>(L, 0, o0, ncp), b3 = ldl<PM>(L, 0, o3, ncp);
+#pragma unroll 4
     for (int c = 1; c < nc; ++c) {
-        const float v0 = Ls[c * kACS + o], v3 = Ls[c * kACS + o + kTC + 1];
+        const float v0 = ldl<PM>(L, c, o0, ncp), v3 = ldl<PM>(L, c, o3, ncp);
         if (v0 > b0) { b0 = v0; ch0 = c; }
         if (v3 > b3) { b3 = v3; ch3 = c; }
     }
-    unsigned int elim = dominated_by(Ls, nc, o, ch0, margin);
-    if (ch3 != ch0) elim |= dominated_by(Ls, nc, o, ch3, margin);
+    unsigned int elim = dominated_by<PM>(L, nc, ncp, o0, o1, o2, o3, ch0, margin);
+    if (ch3 != ch0) elim |= dominated_by<PM>(L, nc, ncp, o0, o1, o2, o3, ch3, margin);
     return ~elim & (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
 }
 
@@ -124,8 +143,8 @@ __device__ __forceinline__ unsigned int cell_survivors(const float* __restrict__
 // rows i >= KH between rows 1/2 (KH is warp-uniform and a template constant, so the vertical step is one FMUL + one FFMA
 // per pixel and unused staged rows are never read).  The winning class indices are kept packed, one byte per pixel, one
 // register per row (PRMT replaces the winner's byte), which is also the uint8 mask word the thread stores.
-template <int KH>
-__device__ __forceinline__ void argmax_half_fast(const float* __restrict__ Ls, unsigned int cand, const int (&ro)[3], const int (&co)[3],
+template <int KH, bool PM>
+__device__ __forceinline__ void argmax_half_fast(const float* __restrict__ Ls, int ncp, unsigned int cand, const int (&ro)[3], const int (&co)[3],
                                                  const float (&wx)[4][3], const float (&wa)[4], const float (&wb)[4], unsigned int (&idx)[4]) {
     float best[4][4];
 #pragma unroll
@@ -137,12 +156,11 @@ __device__ __forceinline__ void argmax_half_fast(const float* __restrict__ Ls, u
     while (cand) {
         const unsigned int c = __ffs(cand) - 1;
         cand &= cand - 1u;
-        const float* lc = Ls + c * kACS;
         float hrow[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             if ((KH == 4 && r == 2) || (KH == 0 && r == 0)) continue;      // staged rows this half never uses
-            const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
+            const float v0 = ldl<PM>(Ls, c, ro[r] + co[0], ncp), v1 = ldl<PM>(Ls, c, ro[r] + co[1], ncp), v2 = ldl<PM>(Ls, c, ro[r] + co[2], ncp);
 #pragma unroll
             for (int j = 0; j < 4; ++j) hrow[r][j] = fmaf(wx[j][2], v2, fmaf(wx[j][1], v1, wx[j][0] * v0));
         }
@@ -164,7 +182,8 @@ __device__ __forceinline__ void argmax_half_fast(const float* __restrict__ Ls, u
 // the 2 x 2 taps ATen reads per pixel -- a non-finite value under a zero weight of the 3-tap form would poison pixels torch
 // keeps finite.  hx = 1 - lx > 0 always, so a zero first weight marks the columns that use the second tap pair; sy marks
 // the rows that do.  Used when a staged logit is NaN / Inf or there are more classes than the candidate mask holds.
-__device__ __forceinline__ void argmax_half_generic(const float* __restrict__ Ls, int nc, const int (&ro)[3], const int (&co)[3],
+template <bool PM>
+__device__ __forceinline__ void argmax_half_generic(const float* __restrict__ Ls, int nc, int ncp, const int (&ro)[3], const int (&co)[3],
                                                     const float (&wx)[4][3], const float (&wa)[4], const float (&wb)[4],
                                                     unsigned int sy_mask, unsigned int (&idx)[4]) {
     float best[4][4];
@@ -175,11 +194,10 @@ __device__ __forceinline__ void argmax_half_generic(const float* __restrict__ Ls
         for (int j = 0; j < 4; ++j) best[i][j] = 0.f;
     }
     for (int c = 0; c < nc; ++c) {
-        const float* lc = Ls + c * kACS;
         float hrow[3][4];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const float v0 = lc[ro[r] + co[0]], v1 = lc[ro[r] + co[1]], v2 = lc[ro[r] + co[2]];
+            const float v0 = ldl<PM>(Ls, c, ro[r] + co[0], ncp), v1 = ldl<PM>(Ls, c, ro[r] + co[1], ncp), v2 = ldl<PM>(Ls, c, ro[r] + co[2], ncp);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const bool sx = wx[j][0] == 0.f;
@@ -409,7 +427,9 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
         const int qn = min(min((int)(scx * (float)min(xb + 127, W - 1)), wl - 1) - cb + 1, kCC);
         if (tid < rn * qn) {      // prune == 0 (tests, worst-case timing): every class stays a candidate everywhere
             const int R = tid / qn, Q = tid - R * qn;
-            cellmask[R * kCC + Q] = prune ? cell_survivors(Ls, nc, R * kTC + Q, margin) : (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+            const int o = R * kTC + Q;      // the staged tile holds clamped copies, so the +1 neighbours are always in range
+            cellmask[R * kCC + Q] = prune ? cell_survivors<false>(Ls, nc, ncp, o, o + 1, o + kTC, o + kTC + 1, margin)
+                                          : (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
         }
         __syncthreads();
     }
@@ -474,15 +494,15 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
                     for (int i = 0; i < 4; ++i) idx[i] = fill;
                 } else {
                     switch (kh) {
-                        case 0: argmax_half_fast<0>(Ls, cand, ro, co, wx, wa, wb, idx); break;
-                        case 1: argmax_half_fast<1>(Ls, cand, ro, co, wx, wa, wb, idx); break;
-                        case 2: argmax_half_fast<2>(Ls, cand, ro, co, wx, wa, wb, idx); break;
-                        case 3: argmax_half_fast<3>(Ls, cand, ro, co, wx, wa, wb, idx); break;
-                        default: argmax_half_fast<4>(Ls, cand, ro, co, wx, wa, wb, idx); break;
+                        case 0: argmax_half_fast<0, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                        case 1: argmax_half_fast<1, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                        case 2: argmax_half_fast<2, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                        case 3: argmax_half_fast<3, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                        default: argmax_half_fast<4, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
                     }
                 }
             } else {
-                argmax_half_generic(Ls, nc, ro, co, wx, wa, wb, sy_mask, idx);
+                argmax_half_generic<false>(Ls, nc, ncp, ro, co, wx, wa, wb, sy_mask, idx);
             }
 
             // ---- write the mask ----
@@ -593,6 +613,307 @@ upsample_argmax_kernel(const float* __restrict__ low, int nc, int ncp, void* __r
     }
 }
 
+// ---- the same stage as a PERSISTENT kernel whose inputs arrive by TMA, one tile ahead -----------------------------------
+// ncu on the direct kernel above (profiles/r02_tail_kernel.md): a fifth of its time is warps waiting for the label loads they
+// issued a moment earlier and another tenth for the logits of the tile; nothing overlaps them because every CTA does
+// load -> compare -> load -> count once and exits.  Here a CTA walks tiles (tile = blockIdx.x + k * gridDim.x) and the copy engine
+// runs ahead of it: ONE cp.async.bulk.tensor brings the 12 x 20 x padded-classes box of low-resolution logits of the next tile
+// into a raw buffer (pixel-major, the NHWC tensor's own layout; outside the tensor the engine zero-fills) as soon as the
+// current tile has been transposed out of it into the class-major, border-clamped tile the comparison code wants, and the
+// 64 x 128 label box of the next tile is requested as soon as this tile's labels have been counted.  The confusion bins stay
+// in shared memory for the CTA's whole life and reach the global accumulator once.  Needs 16-byte aligned label rows
+// (W * element size a multiple of 16); other shapes keep the direct kernel.
+template <int LDT>
+__global__ void __launch_bounds__(kThreads, LDT == FSCNN_I64 ? 2 : 3)
+upsample_argmax_tma_kernel(const __grid_constant__ CUtensorMap lmap, const __grid_constant__ CUtensorMap labmap, int nc, int ncp,
+                           void* __restrict__ mask, int mask_dtype, unsigned long long* __restrict__ conf, int hl, int wl, int H, int W,
+                           int tiles_x, int tiles_y, int ntiles, int prune) {
+    constexpr bool do_hist = LDT >= 0;
+    constexpr int esz = LDT == FSCNN_U8 ? 1 : (LDT == FSCNN_I32 ? 4 : 8);
+    extern __shared__ __align__(128) unsigned char tsm[];
+    const int lbytes = kTR * kTC * ncp * 4;                        // one logits box
+    const int lstride = (lbytes + 127) & ~127;
+    const float* raw = reinterpret_cast<const float*>(tsm);        // [12][20][ncp], as the copy engine delivers it
+    float* Ls = reinterpret_cast<float*>(tsm + lstride);           // [nc][12][20], clamped at the image border
+    unsigned char* labs = tsm + 2 * lstride;                       // [64][128] labels of the current tile
+    unsigned int* hist = reinterpret_cast<unsigned int*>(labs + (do_hist ? 64 * 128 * esz : 0));
+    __shared__ __align__(8) uint64_t bar_l, bar_lab;
+    __shared__ unsigned int tile_amax[2], blk_labeled, blk_correct;
+    __shared__ unsigned int cellmask[kCR * kCC];
+    static_assert(kTR == kATR, "the TMA kernel shares the direct kernel's class-major tile");
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float scy = H > 1 ? (float)(hl - 1) / (float)(H - 1) : 0.f;
+    const float scx = W > 1 ? (float)(wl - 1) / (float)(W - 1) : 0.f;
+    const int nb = (nc + 1) * (nc + 1);
+    auto tile_coords = [&](int tile, int& n, int& yb, int& xb) {
+        const int tx = tile % tiles_x, r = tile / tiles_x;
+        n = r / tiles_y; yb = (r % tiles_y) * 64; xb = tx * 128;
+    };
+    auto issue_logits = [&](int tile) {
+        int n, yb, xb;
+        tile_coords(tile, n, yb, xb);
+        const int rb = min((int)(scy * (float)yb), hl - 1), cb = min((int)(scx * (float)xb), wl - 1);
+        mbar_arrive_expect_tx(&bar_l, (uint32_t)lbytes);
+        tma_load_4d(smem_u32(raw), &lmap, 0, cb, rb, n, &bar_l);
+    };
+    auto issue_labels = [&](int tile) {
+        int n, yb, xb;
+        tile_coords(tile, n, yb, xb);
+        mbar_arrive_expect_tx(&bar_lab, 64u * 128u * esz);
+        tma_load_3d(smem_u32(labs), &labmap, xb, yb, n, &bar_lab);
+    };
+
+    if (tid == 0) {
+        mbar_init(&bar_l, 1); mbar_init(&bar_lab, 1);
+        fence_mbar_init();
+        tile_amax[0] = 0u; tile_amax[1] = 0u; blk_labeled = 0u; blk_correct = 0u;
+    }
+    if (do_hist)
+        for (int i = tid; i < nb; i += kThreads) hist[i] = 0u;
+    __syncthreads();
+    if (tid == 0) {
+        tma_prefetch_desc(&lmap);
+        issue_logits(blockIdx.x);
+        if (do_hist) { tma_prefetch_desc(&labmap); issue_labels(blockIdx.x); }
+    }
+
+    int it = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        int n, yb, xb;
+        tile_coords(tile, n, yb, xb);
+        const int rb = min((int)(scy * (float)yb), hl - 1);          // first staged low-res row / column
+        const int cb = min((int)(scx * (float)xb), wl - 1);
+        const int rmax = hl - 1 - rb, qmax = wl - 1 - cb;            // tile-relative clamps of the staged box
+        mbar_wait(&bar_l, it & 1);
+        // transpose the box into the class-major tile (clamped copies beyond the image border = ATen's x1 = min(x0 + 1, w - 1)),
+        // checking for NaN / Inf (-> the exact-semantics generic loop) and taking the largest |logit| (-> the margin) on the way.
+        // Items run pixel-fastest: conflict-free stores, 16-byte loads 4 * ncp bytes apart.
+        int nonfinite = 0;
+        float amax = 0.f;
+        {
+            const int nv = ncp >> 2;
+            for (int i = tid; i < kTR * kTC * nv; i += kThreads) {
+                const int v = i / (kTR * kTC), px = i - v * (kTR * kTC);
+                const int r = px / kTC, q = px - r * kTC;
+                const float4 t = *reinterpret_cast<const float4*>(raw + (min(r, rmax) * kTC + min(q, qmax)) * ncp + 4 * v);
+                const int c = 4 * v;
+                nonfinite |= !(fabsf(t.x) <= 3.4e38f) | !(fabsf(t.y) <= 3.4e38f) | !(fabsf(t.z) <= 3.4e38f) | !(fabsf(t.w) <= 3.4e38f);
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+                float* dst = Ls + c * kACS + px;
+                dst[0] = t.x;
+                if (c + 1 < nc) dst[kACS] = t.y;
+                if (c + 2 < nc) dst[2 * kACS] = t.z;
+                if (c + 3 < nc) dst[3 * kACS] = t.w;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0) atomicMax(&tile_amax[it & 1], __float_as_uint(amax));
+        if (tid == 0) tile_amax[(it + 1) & 1] = 0u;
+        const bool slow = (__syncthreads_or(nonfinite) != 0) || nc > 32;
+        // the raw box has been consumed: the copy engine may fetch the next tile's while this one is compared and counted
+        if (tid == 0 && tile + (int)gridDim.x < ntiles) issue_logits(tile + gridDim.x);
+        if (!slow) {
+            const float margin = 2e-6f * __uint_as_float(tile_amax[it & 1]) + 1e-30f;
+            const int rn = min(min((int)(scy * (float)min(yb + 63, H - 1)), hl - 1) - rb + 1, kCR);
+            const int qn = min(min((int)(scx * (float)min(xb + 127, W - 1)), wl - 1) - cb + 1, kCC);
+            if (tid < rn * qn) {
+                const int R = tid / qn, Q = tid - R * qn;
+                const int o = R * kTC + Q;
+                cellmask[R * kCC + Q] = prune ? cell_survivors<false>(Ls, nc, ncp, o, o + 1, o + kTC, o + kTC + 1, margin)
+                                              : (nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u));
+            }
+            __syncthreads();
+        }
+
+        const int x0 = xb + lane * 4, y0 = yb + warp * 8;
+        const bool live = (x0 < W) && (y0 < H);
+        if (live) {
+            float wx[4][3];
+            const int c0 = min((int)(scx * (float)x0), wl - 1);
+            bool second_col = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float fx = scx * (float)(x0 + j);
+                const int q = min((int)fx, wl - 1);
+                const float lx = fx - (float)q, hx = 1.f - lx;
+                const bool s = (q - c0) != 0;
+                second_col |= s;
+                wx[j][0] = s ? 0.f : hx; wx[j][1] = s ? hx : lx; wx[j][2] = s ? lx : 0.f;
+            }
+            const int r0 = min((int)(scy * (float)y0), hl - 1);
+            int ro[3], co[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ro[k] = (r0 + k - rb) * kTC;
+                co[k] = c0 + k - cb;
+            }
+            const unsigned int* cm = cellmask + (r0 - rb) * kCC + (c0 - cb);
+            const uint32_t hist_s = smem_u32(hist);
+            const int stride = nc + 1;
+            int run_key = -1;
+            unsigned int run = 0;
+            bool labels_ready = false;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int yh = y0 + 4 * half;
+                float wa[4], wb[4];
+                int kh = 0;
+                unsigned int sy_mask = 0u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float fy = scy * (float)(yh + i);
+                    const int r = min((int)fy, hl - 1);
+                    const float ly = fy - (float)r;
+                    wa[i] = 1.f - ly; wb[i] = ly;
+                    const bool s = (r - r0) != 0;
+                    kh += s ? 0 : 1;
+                    sy_mask |= (s ? 1u : 0u) << i;
+                }
+                unsigned int idx[4];
+                if (!slow) {
+                    unsigned int cand = 0u;
+                    if (kh > 0) cand |= cm[0] | (second_col ? cm[1] : 0u);
+                    if (kh < 4) cand |= cm[kCC] | (second_col ? cm[kCC + 1] : 0u);
+                    if ((cand & (cand - 1u)) == 0u) {
+                        const unsigned int fill = (unsigned int)(__ffs(cand) - 1) * 0x01010101u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) idx[i] = fill;
+                    } else {
+                        switch (kh) {
+                            case 0: argmax_half_fast<0, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                            case 1: argmax_half_fast<1, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                            case 2: argmax_half_fast<2, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                            case 3: argmax_half_fast<3, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                            default: argmax_half_fast<4, false>(Ls, ncp, cand, ro, co, wx, wa, wb, idx); break;
+                        }
+                    }
+                } else {
+                    argmax_half_generic<false>(Ls, nc, ncp, ro, co, wx, wa, wb, sy_mask, idx);
+                }
+                if (mask) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (yh + i < H) {
+                            const size_t off = ((size_t)n * H + (yh + i)) * W + x0;
+                            const int b0 = idx[i] & 255u, b1 = (idx[i] >> 8) & 255u, b2 = (idx[i] >> 16) & 255u, b3 = idx[i] >> 24;
+                            if (mask_dtype == FSCNN_U8) {
+                                unsigned char* m = reinterpret_cast<unsigned char*>(mask) + off;
+                                if ((W & 3) == 0) {
+                                    *reinterpret_cast<unsigned int*>(m) = idx[i];
+                                } else {
+                                    if (x0 < W) m[0] = (unsigned char)b0;
+                                    if (x0 + 1 < W) m[1] = (unsigned char)b1;
+                                    if (x0 + 2 < W) m[2] = (unsigned char)b2;
+                                    if (x0 + 3 < W) m[3] = (unsigned char)b3;
+                                }
+                            } else if (mask_dtype == FSCNN_I32) {
+                                int* m = reinterpret_cast<int*>(mask) + off;
+                                if ((W & 3) == 0) {
+                                    *reinterpret_cast<int4*>(m) = make_int4(b0, b1, b2, b3);
+                                } else {
+                                    if (x0 < W) m[0] = b0;
+                                    if (x0 + 1 < W) m[1] = b1;
+                                    if (x0 + 2 < W) m[2] = b2;
+                                    if (x0 + 3 < W) m[3] = b3;
+                                }
+                            } else {
+                                long long* m = reinterpret_cast<long long*>(mask) + off;
+                                if ((W & 3) == 0) {
+                                    *reinterpret_cast<longlong2*>(m) = make_longlong2(b0, b1);
+                                    *reinterpret_cast<longlong2*>(m + 2) = make_longlong2(b2, b3);
+                                } else {
+                                    if (x0 < W) m[0] = b0;
+                                    if (x0 + 1 < W) m[1] = b1;
+                                    if (x0 + 2 < W) m[2] = b2;
+                                    if (x0 + 3 < W) m[3] = b3;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (do_hist) {
+                    if (!labels_ready) { mbar_wait(&bar_lab, it & 1); labels_ready = true; }
+                    int code[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) code[i][j] = -1;
+                        // the label box sits in shared memory as [64 rows][128 columns]; rows / columns outside the image were
+                        // zero-filled by the copy engine and are skipped here
+                        if (yh + i < H) {
+                            const unsigned char* lp = labs + ((size_t)(warp * 8 + 4 * half + i) * 128 + lane * 4) * esz;
+                            if (LDT == FSCNN_U8) {
+                                const unsigned int v = *reinterpret_cast<const unsigned int*>(lp);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const unsigned int t = (v >> (8 * j)) & 255u;
+                                    code[i][j] = (int)min(t, (unsigned int)nc);
+                                }
+                            } else if (LDT == FSCNN_I32) {
+                                const int4 v = *reinterpret_cast<const int4*>(lp);
+                                const int t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) code[i][j] = t[j] < 0 ? -1 : min(t[j], nc);
+                            } else {
+                                const int4 a = *reinterpret_cast<const int4*>(lp), b = *reinterpret_cast<const int4*>(lp + 16);
+                                const int lo[4] = {a.x, a.z, b.x, b.z}, hi[4] = {a.y, a.w, b.y, b.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    code[i][j] = hi[j] < 0 ? -1 : ((hi[j] == 0 && (unsigned int)lo[j] < (unsigned int)nc) ? lo[j] : nc);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (x0 + j >= W) code[i][j] = -1;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int row = code[i][j];
+                            const bool ok = row >= 0;
+                            const int col = (int)((idx[i] >> (8 * j)) & 255u);
+                            const int key = row * stride + col;
+                            const bool brk = ok && key != run_key;
+                            red_shared_if(brk, hist_s + 4u * (uint32_t)max(run_key, 0), run);
+                            run = brk ? 1u : run + (ok ? 1u : 0u);
+                            run_key = brk ? key : run_key;
+                        }
+                    }
+                }
+            }
+            if (do_hist) red_shared_if(run != 0u, hist_s + 4u * (uint32_t)max(run_key, 0), run);
+        } else if (do_hist) {
+            mbar_wait(&bar_lab, it & 1);      // keep every thread's view of the barrier phase in step
+        }
+        __syncthreads();      // labels counted; the class-major tile and the cell masks are free
+        if (do_hist && tid == 0 && tile + (int)gridDim.x < ntiles) issue_labels(tile + gridDim.x);
+    }
+    if (!do_hist) return;
+    // the CTA's bins go to the global accumulator once; `labeled` is their sum and `correct` the sum of the diagonal
+    unsigned int labeled = 0, correct = 0;
+    for (int i = tid; i < nb; i += kThreads) {
+        const unsigned int v = hist[i];
+        if (v) atomicAdd(conf + i, (unsigned long long)v);
+        labeled += v;
+        correct += (i % (nc + 2) == 0 && i < nc * (nc + 2)) ? v : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        labeled += __shfl_xor_sync(0xffffffffu, labeled, o);
+        correct += __shfl_xor_sync(0xffffffffu, correct, o);
+    }
+    if (lane == 0) { atomicAdd(&blk_labeled, labeled); atomicAdd(&blk_correct, correct); }
+    __syncthreads();
+    if (tid == 0) {
+        if (blk_labeled) atomicAdd(conf + nb, (unsigned long long)blk_labeled);
+        if (blk_correct) atomicAdd(conf + nb + 1, (unsigned long long)blk_correct);
+    }
+}
+
 static size_t up_smem_bytes(int nc, bool hist, int rows = kTR) {
     size_t b = (size_t)nc * rows * kTC * sizeof(float);
     if (hist) b += (size_t)(nc + 1) * (nc + 1) * sizeof(unsigned int);
@@ -633,16 +954,75 @@ static cudaError_t run_up_argmax(const float* low, int nc, int ncp, void* mask, 
     return cudaGetLastError();
 }
 
+// the persistent TMA kernel when the shapes allow it: <= 32 classes worth of candidate mask is not required (the generic loop
+// runs inside it too), but the shared-memory bins are, and the label rows must be 16-byte aligned for the copy engine
+template <int LDT>
+static cudaError_t run_up_argmax_tma(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
+                                     unsigned long long* conf, int n, int hl, int wl, int h, int w, cudaStream_t s, bool prune, bool* used) {
+    constexpr int esz = LDT == FSCNN_U8 ? 1 : (LDT == FSCNN_I32 ? 4 : 8);
+    *used = false;
+    if (kTR != 12 || (LDT >= 0 && (nc + 1) * (nc + 1) > kHistMaxBins)) return cudaSuccess;
+    if (LDT >= 0 && ((reinterpret_cast<uintptr_t>(labels) & 15) || ((size_t)w * esz) % 16 || ((size_t)h * w * esz) % 16)) return cudaSuccess;
+    if ((reinterpret_cast<uintptr_t>(low) & 15) || (ncp & 3)) return cudaSuccess;
+    const size_t lbytes = ((size_t)kTR * kTC * ncp * 4 + 127) & ~(size_t)127;
+    const size_t smem = 2 * lbytes + (LDT >= 0 ? (size_t)64 * 128 * esz + (size_t)(nc + 1) * (nc + 1) * 4 : 0) + 128;   // raw box + class-major tile
+    if (smem > 200 * 1024) return cudaSuccess;
+    CUtensorMap lmap, labmap;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)ncp, (cuuint64_t)wl, (cuuint64_t)hl, (cuuint64_t)n};
+        const cuuint64_t strides[3] = {(cuuint64_t)ncp * 4, (cuuint64_t)wl * ncp * 4, (cuuint64_t)hl * wl * ncp * 4};
+        const cuuint32_t box[4] = {(cuuint32_t)ncp, (cuuint32_t)kTC, (cuuint32_t)kTR, 1};
+        if (ncp > 256 || make_tiled_map(&lmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, low, dims, strides, box) != cudaSuccess) return cudaSuccess;
+    }
+    labmap = lmap;
+    if (LDT >= 0) {
+        const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+        const cuuint64_t strides[2] = {(cuuint64_t)w * esz, (cuuint64_t)h * w * esz};
+        const cuuint32_t box[3] = {128, 64, 1};
+        const CUtensorMapDataType dt = LDT == FSCNN_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : (LDT == FSCNN_I32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_INT64);
+        if (make_tiled_map(&labmap, dt, 3, labels, dims, strides, box) != cudaSuccess) return cudaSuccess;
+    }
+    static unsigned long long configured = 0;
+    static size_t configured_bytes = 0;
+    static int ctas_per_sm[64] = {};
+    if (smem > configured_bytes) { configured = 0; configured_bytes = smem; }
+    cudaError_t e = ensure_dyn_smem(upsample_argmax_tma_kernel<LDT>, configured_bytes, configured);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = ctas_per_sm[dev & 63];
+    if (occ <= 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, upsample_argmax_tma_kernel<LDT>, kThreads, configured_bytes) != cudaSuccess || occ <= 0))
+        occ = 1;
+    const int tiles_x = ceil_div(w, 128), tiles_y = ceil_div(h, 64), ntiles = tiles_x * tiles_y * n;
+    const int grid = min(ntiles, num_sms() * occ);
+    upsample_argmax_tma_kernel<LDT><<<grid, kThreads, smem, s>>>(lmap, labmap, nc, ncp, mask, mask_dtype, conf, hl, wl, h, w, tiles_x, tiles_y,
+                                                                ntiles, prune ? 1 : 0);
+    *used = true;
+    return cudaGetLastError();
+}
+
+static int g_tail_tma = -1;   // FSCNN_TAIL_TMA=0 keeps the direct kernel (A/B timing)
+
 cudaError_t launch_up_argmax(const float* low, int nc, int ncp, void* mask, int mask_dtype, const void* labels,
                              int label_dtype, unsigned long long* conf, int n, int hl, int wl, int h, int w,
                              cudaStream_t s, bool prune) {
     // a 128-pixel tile row must interpolate inside at most 18 low-res cells (17 + the one to the right): ratio < 17/124
     if ((double)(hl - 1) * 7.3 > (double)(h - 1) || (double)(wl - 1) * 7.3 > (double)(w - 1)) return cudaErrorInvalidValue;
+    if (labels && label_dtype != FSCNN_U8 && label_dtype != FSCNN_I32 && label_dtype != FSCNN_I64) return cudaErrorInvalidValue;
+    if (g_tail_tma < 0) { const char* v = getenv("FSCNN_TAIL_TMA"); g_tail_tma = (v && v[0] == '0') ? 0 : 1; }
+    if (g_tail_tma) {
+        bool used = false;
+        cudaError_t e;
+        if (!labels) e = run_up_argmax_tma<-1>(low, nc, ncp, mask, mask_dtype, nullptr, nullptr, n, hl, wl, h, w, s, prune, &used);
+        else if (label_dtype == FSCNN_U8) e = run_up_argmax_tma<FSCNN_U8>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune, &used);
+        else if (label_dtype == FSCNN_I32) e = run_up_argmax_tma<FSCNN_I32>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune, &used);
+        else e = run_up_argmax_tma<FSCNN_I64>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune, &used);
+        if (e != cudaSuccess || used) return e;
+    }
     if (!labels) return run_up_argmax<-1>(low, nc, ncp, mask, mask_dtype, nullptr, nullptr, n, hl, wl, h, w, s, prune);
     if (label_dtype == FSCNN_U8) return run_up_argmax<FSCNN_U8>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune);
     if (label_dtype == FSCNN_I32) return run_up_argmax<FSCNN_I32>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune);
-    if (label_dtype == FSCNN_I64) return run_up_argmax<FSCNN_I64>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune);
-    return cudaErrorInvalidValue;
+    return run_up_argmax<FSCNN_I64>(low, nc, ncp, mask, mask_dtype, labels, conf, n, hl, wl, h, w, s, prune);
 }
 
 // ---- SegmentationMetric counting on existing class maps (utils/metric.py:73-105) ----
