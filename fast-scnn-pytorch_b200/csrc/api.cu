@@ -94,8 +94,7 @@ struct fscnn_ctx {
         size_t ffm_wd, ffm_bd, ffm_wcat, ffm_bcat;
         size_t head_w, head_b;
         size_t aux_w, aux_b, auxh_w, auxh_b;
-        size_t bn_we_img[9], bn_wp_img[9], bn_tab_img[9];   // bf16 tcgen05 operand images + constant tables (offsets still in floats)
-        size_t bn_weT_img[9], bn_wpT_img[9], bn_tabT_img[9]; // stride-1 layers: operands of the transposed-expand kernel
+        size_t bn_weT_img[9], bn_wpT_img[9], bn_tabT_img[9]; // bf16 tcgen05 operand images + constant tables of the transposed-expand kernels (offsets in floats)
         size_t ppm_wx_img;   // PPM out conv, x part + branch part as [128 x 128] operand images
         size_t ffm_tabT;   // FFM, transposed kernel: per-channel depthwise records + fused bias
         size_t ds_wp_img[4], head_img, ffm_img, stem_img, stem_img_u8, stem_b_u8, stem_imgx, stem_imgx_u8;
@@ -104,22 +103,15 @@ struct fscnn_ctx {
     StemW stem{};
     DsW ds[4]{};
     BneckW bn[9]{};
-    const bf16* bn_we_img[9]{};
-    const bf16* bn_wp_img[9]{};
-    const unsigned char* bn_tab_img[9]{};
     const bf16* bn_weT_img[9]{};
     const bf16* bn_wpT_img[9]{};
     const unsigned char* bn_tabT_img[9]{};
-    int s1_transposed = 1;   // bf16 stride-1 bottlenecks: transposed-expand kernel (0 = the three-role kernel)
-    int s2_transposed = 1;   // bf16 stride-2 bottlenecks: transposed-expand kernel (0 = bottleneck_tc.cu)
     const bf16* ds_wp_img[4]{};
     const bf16* head_img = nullptr;
     const bf16* ffm_img = nullptr;
     const unsigned char* ffm_tabT = nullptr;
     const bf16* ppm_wx_img = nullptr;
     int front_transposed = 1;  // bf16 fused front kernel with the transposed stem (0 = l2d_front_tc.cu)
-    int ppm_tc = 1;          // bf16 PPM output stage on the tensor core (0 = ppm.cu's fp32 register-tile contraction)
-    int ffm_transposed = 1;  // bf16 FFM: resize on the tensor core + depthwise out of TMEM (0 = ffm_tc.cu)
     const bf16* stem_img = nullptr;
     bf16* stem_img_u8 = nullptr;
     float* stem_b_u8 = nullptr;
@@ -255,14 +247,9 @@ void build_manifest_and_offsets(fscnn_ctx* c) {
     if (c->prec == FSCNN_PREC_BF16)
         for (int i = 0; i < 9; ++i) {
             const int ci = kBnecks[i].cin, ce = 6 * ci, co = kBnecks[i].cout;
-            f.bn_we_img[i] = take((size_t)ce * ci / 2);
-            f.bn_wp_img[i] = take((size_t)co * ce / 2);
-            f.bn_tab_img[i] = take((bottleneck_tc_tab_bytes(ci, co) + 3) / 4);
-            {
-                f.bn_weT_img[i] = take((bottleneck_s1t_we_bytes(ci) + 3) / 4);
-                f.bn_wpT_img[i] = take((bottleneck_s1t_wp_bytes(ci, co) + 3) / 4);
-                f.bn_tabT_img[i] = take((bottleneck_s1t_tab_bytes(ci, co) + 3) / 4);
-            }
+            f.bn_weT_img[i] = take((bottleneck_s1t_we_bytes(ci) + 3) / 4);
+            f.bn_wpT_img[i] = take((bottleneck_s1t_wp_bytes(ci, co) + 3) / 4);
+            f.bn_tabT_img[i] = take((bottleneck_s1t_tab_bytes(ci, co) + 3) / 4);
         }
     if (c->prec == FSCNN_PREC_BF16) {
         for (int i = 0; i < 4; ++i) f.ds_wp_img[i] = take((size_t)dss[i].cin * dss[i].cout / 2);
@@ -393,14 +380,11 @@ cudaError_t bottleneck_dispatch<float>(fscnn_ctx* c, int i, const float* in, flo
 template <>
 cudaError_t bottleneck_dispatch<bf16>(fscnn_ctx* c, int i, const bf16* in, bf16* out, int m, int hi, int wi, int ho, int wo,
                                       cudaStream_t s) {
-    if (kBnecks[i].stride == 2 && c->s2_transposed)
+    if (kBnecks[i].stride == 2)
         return launch_bottleneck_s2t_tc(kBnecks[i].cin, kBnecks[i].cout, in, c->bn_tabT_img[i], c->bn_weT_img[i], c->bn_wpT_img[i], out,
                                         m, hi, wi, ho, wo, s);
-    if (kBnecks[i].stride == 1 && c->s1_transposed)
-        return launch_bottleneck_s1t_tc(kBnecks[i].cin, kBnecks[i].cout, in, c->bn_tabT_img[i], c->bn_weT_img[i], c->bn_wpT_img[i], out,
-                                        m, hi, wi, s);
-    return launch_bottleneck_tc(kBnecks[i].cin, kBnecks[i].cout, kBnecks[i].stride, in, c->bn_tab_img[i], c->bn_we_img[i],
-                                c->bn_wp_img[i], out, m, hi, wi, ho, wo, s);
+    return launch_bottleneck_s1t_tc(kBnecks[i].cin, kBnecks[i].cout, in, c->bn_tabT_img[i], c->bn_weT_img[i], c->bn_wpT_img[i], out,
+                                    m, hi, wi, s);
 }
 
 template <>
@@ -421,8 +405,7 @@ cudaError_t ppm_dispatch<float>(fscnn_ctx* c, const float* in, float* rowsum, fl
 }
 template <>
 cudaError_t ppm_dispatch<bf16>(fscnn_ctx* c, const bf16* in, float* rowsum, float* z, bf16* z16, bf16* r_img, bf16* out, int m, int h, int w, cudaStream_t s) {
-    if (c->ppm_tc) return launch_ppm_tc(in, c->ppm, c->ppm_wx_img, rowsum, z, z16, r_img, out, m, h, w, s);
-    return launch_ppm<bf16>(in, c->ppm, rowsum, z, out, m, h, w, s);
+    return launch_ppm_tc(in, c->ppm, c->ppm_wx_img, rowsum, z, z16, r_img, out, m, h, w, s);
 }
 template <>
 cudaError_t ffm_dispatch<float>(fscnn_ctx* c, const float* higher, const float* lower, float* out, int m, int hh, int wh, int hl,
@@ -432,9 +415,9 @@ cudaError_t ffm_dispatch<float>(fscnn_ctx* c, const float* higher, const float* 
 template <>
 cudaError_t ffm_dispatch<bf16>(fscnn_ctx* c, const bf16* higher, const bf16* lower, bf16* out, int m, int hh, int wh, int hl,
                                int wl, cudaStream_t s) {
-    if (c->ffm_transposed && ffm_t_supported(hh, wh, hl, wl))
-        return launch_ffm_t_tc(higher, lower, c->ffm_tabT, c->ffm_img, out, m, hh, wh, hl, wl, s);
-    return launch_ffm_tc(higher, lower, c->ffm, c->ffm_img, out, m, hh, wh, hl, wl, s);
+    // the network's own resize ratio ((h/4 - 1) / (h - 1) <= 1/4 at every input size) always fits the kernel's 5 x 8 source patch
+    if (!ffm_t_supported(hh, wh, hl, wl)) return cudaErrorInvalidValue;
+    return launch_ffm_t_tc(higher, lower, c->ffm_tabT, c->ffm_img, out, m, hh, wh, hl, wl, s);
 }
 
 template <>
@@ -587,17 +570,6 @@ int fscnn_load_weights(fscnn_ctx* c, const fscnn_tensor* tensors, int n_tensors,
         L.fold(p + ".2", false, p + ".3", co, ce, 1, 0, P + f.bn_wp[i], co, P + f.bn_bp[i]);
         c->bn[i] = {P + f.bn_we[i], P + f.bn_be[i], P + f.bn_wd[i], P + f.bn_bd[i], P + f.bn_wp[i], P + f.bn_bp[i]};
         if (c->prec == FSCNN_PREC_BF16) {
-            bf16* we_img = reinterpret_cast<bf16*>(P + f.bn_we_img[i]);
-            bf16* wp_img = reinterpret_cast<bf16*>(P + f.bn_wp_img[i]);
-            const int chunk = bottleneck_tc_chunk(kBnecks[i].stride);
-            L.fold_umma(p + ".0.conv.0", p + ".0.conv.1", ce, ci, chunk, ci, we_img);   // expand: chunks of `chunk` rows
-            L.fold_umma(p + ".2", p + ".3", co, ce, co, chunk, wp_img);                 // project: chunks of `chunk` columns
-            c->bn_we_img[i] = we_img;
-            c->bn_wp_img[i] = wp_img;
-            unsigned char* tab = reinterpret_cast<unsigned char*>(P + f.bn_tab_img[i]);
-            if (!L.err && launch_pack_bneck_tab(c->bn[i], ce, co, tab, L.s) != cudaSuccess)
-                L.err = fail(FSCNN_ECUDA, "table pack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            c->bn_tab_img[i] = tab;
             {
                 bf16* weT = reinterpret_cast<bf16*>(P + f.bn_weT_img[i]);
                 bf16* wpT = reinterpret_cast<bf16*>(P + f.bn_wpT_img[i]);
@@ -688,10 +660,6 @@ int fscnn_set_input_format(fscnn_ctx* c, int format, const float* mean3, const f
 int fscnn_set_option(fscnn_ctx* c, const char* key, int value) {
     if (!c || !key) return fail(FSCNN_EINVAL, "null argument");
     if (!strcmp(key, "fuse_front")) { c->fuse_front = value ? 1 : 0; return FSCNN_OK; }
-    if (!strcmp(key, "s1_transposed")) { c->s1_transposed = value ? 1 : 0; return FSCNN_OK; }
-    if (!strcmp(key, "s2_transposed")) { c->s2_transposed = value ? 1 : 0; return FSCNN_OK; }
-    if (!strcmp(key, "ffm_transposed")) { c->ffm_transposed = value ? 1 : 0; return FSCNN_OK; }
-    if (!strcmp(key, "ppm_tc")) { c->ppm_tc = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "front_transposed")) { c->front_transposed = value ? 1 : 0; return FSCNN_OK; }
     if (!strcmp(key, "micro_batch")) return fscnn_set_micro_batch(c, value);
     return fail(FSCNN_ENOENT, "unknown option '%s'", key);

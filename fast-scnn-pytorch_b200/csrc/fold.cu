@@ -156,22 +156,6 @@ cudaError_t launch_dw_round_bf16(float* wd, int c, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// Per-bottleneck constant tables of the bf16 kernel, packed once so that one bulk copy brings them into shared memory:
-// [9][cexp] bf16 depthwise weights | [cexp] f32 expand bias | [cexp] f32 depthwise bias | [cout] f32 project bias
-__global__ void pack_bneck_tab_kernel(const float* __restrict__ wd, const float* __restrict__ be, const float* __restrict__ bd,
-                                      const float* __restrict__ bp, int cexp, int cout, unsigned char* __restrict__ out) {
-    bf16* wd_o = reinterpret_cast<bf16*>(out);
-    float* f_o = reinterpret_cast<float*>(out + (size_t)9 * cexp * 2);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * cexp; i += gridDim.x * blockDim.x) wd_o[i] = __float2bfloat16_rn(wd[i]);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cexp; i += gridDim.x * blockDim.x) { f_o[i] = be[i]; f_o[cexp + i] = bd[i]; }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cout; i += gridDim.x * blockDim.x) f_o[2 * cexp + i] = bp[i];
-}
-
-cudaError_t launch_pack_bneck_tab(const BneckW& w, int cexp, int cout, unsigned char* out, cudaStream_t s) {
-    pack_bneck_tab_kernel<<<8, 256, 0, s>>>(w.wd, w.be, w.bd, w.bp, cexp, cout, out);
-    return cudaGetLastError();
-}
-
 // Transposed stride-1 bottleneck kernel (bottleneck_s1t_tc.cu): the expand weights are the A operand, cut into chunks of 128
 // expanded channels (rows) x (cin + 16) K columns, 8x8 core matrices ordered [k/8][row/8] (LBO = 2048 B, SBO = 128 B).  The 16
 // extra K columns carry the BN-folded expand bias as bf16 head + remainder (relative error 2^-17), zeros elsewhere; rows past

@@ -78,17 +78,8 @@ cudaError_t launch_fold(const float* w, const float* cbias, const float* gamma, 
 // bf16 tensor-core (tcgen05 / TMEM) variants ------------------------------------------------------------
 cudaError_t launch_fold_umma(const float* w, const float* gamma, const float* var, int nrows, int kdim, int nc, int kc,
                              bf16* out, cudaStream_t s);
-// we_img: expand weights [6cin x cin] in chunks of CE rows; wp_img: project weights [cout x 6cin] in chunks of CE columns,
-// CE = bottleneck_tc_chunk(stride)
-int bottleneck_tc_chunk(int stride);
 // bf16 path: error-diffused rounding of a folded depthwise table [9][c] to bf16-representable values, in place
 cudaError_t launch_dw_round_bf16(float* wd, int c, cudaStream_t s);
-// tab_img: the constant tables packed by launch_pack_bneck_tab (bottleneck_tc_tab_bytes(cin, cout) bytes, 16-byte aligned)
-size_t bottleneck_tc_tab_bytes(int cin, int cout);
-cudaError_t launch_pack_bneck_tab(const BneckW& w, int cexp, int cout, unsigned char* out, cudaStream_t s);
-// stride-1 layers: three-role pipeline (bottleneck_s1_tc.cu); launch_bottleneck_tc dispatches to it
-cudaError_t launch_bottleneck_s1_tc(int cin, int cout, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
-                                    const bf16* wp_img, bf16* out, int n, int h, int w, cudaStream_t s);
 // stride-1 layers, transposed expand (bottleneck_s1t_tc.cu): the expanded tile goes TMEM -> registers, never through shared
 // memory.  we_img / tab from launch_pack_s1t, wp_img = launch_fold_umma(project, nc = cout, kc = 128) into a zeroed buffer.
 size_t bottleneck_s1t_we_bytes(int cin);
@@ -100,8 +91,6 @@ cudaError_t launch_bottleneck_s1t_tc(int cin, int cout, const bf16* in, const un
 // stride-2 layers, transposed expand over 2x2 sub-tiles of 4x8 output pixels (bottleneck_s2t_tc.cu); same operand images
 cudaError_t launch_bottleneck_s2t_tc(int cin, int cout, const bf16* in, const unsigned char* tab, const bf16* we_img,
                                      const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
-cudaError_t launch_bottleneck_tc(int cin, int cout, int stride, const bf16* in, const unsigned char* tab_img, const bf16* we_img,
-                                 const bf16* wp_img, bf16* out, int n, int hi, int wi, int ho, int wo, cudaStream_t s);
 
 // wp_img: pointwise weights [cout x cin] as one chunk; wh_img (head != nullptr): head weights [round_up(nc,16) x cout]
 cudaError_t launch_dsconv_tc(int cin, int cout, int stride, const bf16* in, const DsW& w, const bf16* wp_img, bf16* out,
@@ -120,9 +109,6 @@ cudaError_t launch_ppm_out_tc(const bf16* in, const bf16* wx_img, const bf16* z_
                               int h, int wd, cudaStream_t s);
 cudaError_t launch_ppm_tc(const bf16* in, const PpmW& w, const bf16* wx_img, float* rowsum, float* z, bf16* z16, bf16* r_img, bf16* out,
                           int n, int h, int wd, cudaStream_t s);
-// wcat_img: the stacked [128 x 192] weight (64 higher | 128 lower input channels) as one chunk
-cudaError_t launch_ffm_tc(const bf16* higher, const bf16* lower, const FfmW& w, const bf16* wcat_img, bf16* out, int n, int hh,
-                          int wh, int hl, int wl, cudaStream_t s);
 
 // w_img: stem weights [32 x 27] padded to K = 32 as one chunk
 cudaError_t launch_stem_tc(const void* x, const StemIn& in, const bf16* w_img, const float* bias, bf16* out, int n, int h,

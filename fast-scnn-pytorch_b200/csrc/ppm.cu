@@ -173,6 +173,5 @@ cudaError_t launch_ppm_tc(const bf16* in, const PpmW& w, const bf16* wx_img, flo
 }
 
 template cudaError_t launch_ppm<float>(const float*, const PpmW&, float*, float*, float*, int, int, int, cudaStream_t);
-template cudaError_t launch_ppm<bf16>(const bf16*, const PpmW&, float*, float*, bf16*, int, int, int, cudaStream_t);
 
 }  // namespace fscnn

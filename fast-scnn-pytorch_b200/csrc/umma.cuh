@@ -210,51 +210,6 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
-// Depthwise 3x3, stride 1, pad 1 (padding already materialised in the halo tile) + bias + ReLU for one output COLUMN:
-// the thread owns output column x (0..15) of an 8x16 tile, all 8 rows, 4 channels (k4).  It walks the 10 halo rows once
-// with a 3-row accumulator ring, so every halo value is loaded exactly three times per tile (once per horizontal tap).
-// Halo rows are ROWB bytes per pixel with the 16-byte chunks XOR-swizzled by (pixel & 7); the result goes to an
-// A-operand tile as 8-byte pieces.  sWd: shared-memory address of the bf16 [9][C] weight table (tap-major), Bd is [C] fp32.
-template <int ROWB, int IW>
-__device__ __forceinline__ void dw3x3_s1_col4(uint32_t sH, int x, int k4, uint32_t sWd, int C, const float* __restrict__ Bd,
-                                              uint32_t sA, int a_k8_base) {
-    const int k8 = k4 >> 1;
-    const uint32_t hsel = (k4 & 1) * 8;
-    uint2 wk[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wk[t] = lds64(sWd + (t * C + k4 * 4) * 2);
-    const float4 b4 = *reinterpret_cast<const float4*>(Bd + k4 * 4);
-    float acc[3][4];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { acc[i][0] = b4.x; acc[i][1] = b4.y; acc[i][2] = b4.z; acc[i][3] = b4.w; }
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint2 f[3];
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int pin = r * IW + x + kx;
-            f[kx] = lds64(sH + pin * ROWB + ((k8 ^ (pin & 7)) << 4) + hsel);
-        }
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int o = r - ky;
-            if (o >= 0 && o < 8) {
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    fhfma_x2(acc[o % 3][0], acc[o % 3][1], f[kx].x, wk[ky * 3 + kx].x);
-                    fhfma_x2(acc[o % 3][2], acc[o % 3][3], f[kx].y, wk[ky * 3 + kx].y);
-                }
-            }
-        }
-        if (r >= 2) {
-            const int o = r - 2, p = o * 16 + x;
-            float* a = acc[o % 3];
-            sts64(sA + a_tile_off(p, a_k8_base + k8) + hsel, packbf_relu(a[0], a[1]), packbf_relu(a[2], a[3]));
-            a[0] = b4.x; a[1] = b4.y; a[2] = b4.z; a[3] = b4.w;
-        }
-    }
-}
-
 // ---- helpers of the transposed-expand bottleneck kernels (bottleneck_s1t_tc.cu, bottleneck_s2t_tc.cu) ----
 __device__ __forceinline__ void tmem_ld_32x32b_x64(uint32_t taddr, uint32_t* r) {
     asm volatile(

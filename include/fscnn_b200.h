@@ -204,10 +204,9 @@ int64_t fscnn_launch_count(const fscnn_ctx* ctx);
  * whose tiles at the coarsest level fill whole waves of persistent CTAs; at most 128).  0 restores the default. */
 int fscnn_set_micro_batch(fscnn_ctx* ctx, int images);
 
-/* Tuning / A-B switches: "fuse_front" (1 = stem + dsconv1 as one kernel in the bf16 path, default),
- * "micro_batch" (as fscnn_set_micro_batch), and the bf16 kernel generations (1 = default, 0 = the kernels they replaced):
- * "s1_transposed" / "s2_transposed" (LinearBottleneck, stride 1 / 2: transposed expand, depthwise out of TMEM),
- * "ffm_transposed" (FeatureFusionModule: resize on the tensor core), "ppm_tc" (PyramidPooling output stage). */
+/* Tuning / A-B switches: "fuse_front" (1 = stem + dsconv1 as one kernel in the bf16 path, default), "micro_batch" (as
+ * fscnn_set_micro_batch), "front_transposed" (1 = the transposed-stem front kernel whenever the input rows are 16-byte aligned,
+ * default; 0 = always the kernel that also serves unaligned widths, l2d_front_tc.cu).  Unknown keys return FSCNN_EINVAL. */
 int fscnn_set_option(fscnn_ctx* ctx, const char* key, int value);
 
 /* ---- training step, first slice (reference train.py:253-284) ------------------------------

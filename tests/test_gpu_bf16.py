@@ -159,43 +159,26 @@ def test_bf16_persistent_pipelines_many_tiles(shape, batch, nc):
     assert (m32 != full_mask).float().mean().item() < MASK_TOL
 
 
-GEN_OPTIONS = ('s1_transposed', 's2_transposed', 'ffm_transposed', 'ppm_tc', 'front_transposed')
-
-
-@pytest.mark.parametrize('case', ['fwd_nc19_aux_n2_65x97', 'fwd_nc3_aux_n3_64x40'])
-def test_bf16_both_kernel_generations_in_isolation(case):
-    """The bottlenecks, the FFM and the PPM output stage exist in two bf16 generations: the transposed-expand / tensor-core
-    kernels (default) and the shared-memory-tile / register-tile kernels they replaced (fscnn_set_option(..., 0)).  Both
-    must meet the stage tolerance against the reference fixtures, and they must agree with each other to bf16 precision."""
-    g, sd, x, nc, aux = load_case(case)
-    model = build_model(sd, nc, aux, DEV, precision='bf16')
-    xd = torch.from_numpy(x).to(DEV)
-    eng = model._engine(DEV)
-    n, _, h, w = x.shape
-    names = eng.stage_names()
-    stages = [s for s in STAGE_IO if s[0].startswith('gfe.bottleneck') or s[0] in ('ffm', 'gfe.ppm')]
-    got = {}
-    try:
-        for gen in (1, 0):
-            for opt in GEN_OPTIONS:
-                eng.set_option(opt, gen)
-            for stage, ins, out in stages:
-                idx = names.index(stage)
-                for tap in ins:
-                    v = eng.tap_view(tap, n, h, w)
-                    v.copy_(nhwc(g['tap/' + tap]).to(DEV).to(v.dtype))
-                eng.forward_range(xd, idx, idx)
-                got[gen, stage] = eng.tap_view(out, n, h, w).permute(0, 3, 1, 2).float().cpu().numpy()
-                assert rel_err(got[gen, stage], g['tap/' + out]) < STAGE_TOL, (gen, stage)
-            # the fused front kernel (stem + dsconv1 in one launch) only runs when both stages are requested together
-            eng.forward_range(xd, names.index('stem'), names.index('l2d.dsconv1'))
-            got[gen, 'front'] = eng.tap_view('l2d.dsconv1', n, h, w).permute(0, 3, 1, 2).float().cpu().numpy()
-            assert rel_err(got[gen, 'front'], g['tap/l2d.dsconv1']) < STAGE_TOL, (gen, 'front')
-    finally:
-        for opt in GEN_OPTIONS:
-            eng.set_option(opt, 1)
-    for stage in [st[0] for st in stages] + ['front']:
-        assert rel_err(got[1, stage], got[0, stage]) < STAGE_TOL, stage
+def test_bf16_front_kernel_isolated_and_fused():
+    """Stem + dsconv1 run as ONE kernel whenever both stages are requested (the transposed front kernel for inputs with 16-byte
+    aligned rows, l2d_front_tc.cu otherwise); on its own the stem runs stem_tc.cu.  All of them against the reference fixtures."""
+    for case in ('fwd_nc19_aux_n2_65x97', 'fwd_nc3_aux_n3_64x40'):
+        g, sd, x, nc, aux = load_case(case)
+        model = build_model(sd, nc, aux, DEV, precision='bf16')
+        xd = torch.from_numpy(x).to(DEV)
+        eng = model._engine(DEV)
+        n, _, h, w = x.shape
+        names = eng.stage_names()
+        got = {}
+        try:
+            for gen in (1, 0):
+                eng.set_option('front_transposed', gen)
+                eng.forward_range(xd, names.index('stem'), names.index('l2d.dsconv1'))
+                got[gen] = eng.tap_view('l2d.dsconv1', n, h, w).permute(0, 3, 1, 2).float().cpu().numpy()
+                assert rel_err(got[gen], g['tap/l2d.dsconv1']) < STAGE_TOL, (case, gen)
+        finally:
+            eng.set_option('front_transposed', 1)
+        assert rel_err(got[1], got[0]) < STAGE_TOL
 
 
 def test_bf16_front_kernel_input_formats():
@@ -216,27 +199,19 @@ def test_bf16_front_kernel_input_formats():
             assert (new != old).float().mean().item() < MASK_TOL
 
 
-def test_bf16_transposed_kernels_many_tiles():
-    """Every CTA of the transposed kernels walks many tiles at 328x520 x 12 images (partial tiles in both directions at
-    every scale, border tiles on all four sides): the full forward must agree with the previous kernel generation within
-    the logit tolerance and give the same mask on all but a few near-tie pixels."""
+def test_bf16_many_tiles_against_the_fp32_path():
+    """Every persistent CTA of the bf16 kernels walks many tiles at 328x520 x 12 images (partial tiles in both directions at
+    every scale, border tiles on all four sides).  The exactness path (fp32, 1e-4 of the reference) is the truth here: logits
+    within the bf16 tolerance (rms and max), masks within the mask tolerance, everything finite."""
     nc, h, w, n = 19, 328, 520, 12
     sd = fo.make_state_dict(nc, False, 13)
     x = fo.make_input(n, h, w, 14)
-    model = build_model(sd, nc, False, DEV, precision='bf16')
-    eng = model._engine(DEV)
     xd = torch.from_numpy(x).to(DEV)
-    new_logits = model(xd)[0]
-    new_mask = model.predict(xd)
-    try:
-        for opt in GEN_OPTIONS:
-            eng.set_option(opt, 0)
-        old_logits = model(xd)[0]
-        old_mask = model.predict(xd)
-    finally:
-        for opt in GEN_OPTIONS:
-            eng.set_option(opt, 1)
-    assert torch.isfinite(new_logits).all()
-    scale = old_logits.abs().max().item()
-    assert (new_logits - old_logits).abs().max().item() / scale < LOGIT_TOL
-    assert (new_mask != old_mask).float().mean().item() < MASK_TOL
+    fast = build_model(sd, nc, False, DEV, precision='bf16')
+    exact = build_model(sd, nc, False, DEV, precision='fp32')
+    lf, le = fast(xd)[0], exact(xd)[0]
+    assert torch.isfinite(lf).all()
+    scale = le.abs().max().item()
+    d = (lf - le).abs()
+    assert d.max().item() / scale < 6e-2 and d.pow(2).mean().sqrt().item() / scale < 1.2e-2
+    assert (fast.predict(xd) != exact.predict(xd)).float().mean().item() < MASK_TOL

@@ -129,9 +129,10 @@ def test_kernel_generation_options_and_e2e_argument_checks():
     ctx = C.c_void_p()
     native.check(lib.fscnn_create(C.byref(ctx), 19, 0, native.PREC_BF16))
     try:
-        for key in (b's1_transposed', b's2_transposed', b'ffm_transposed', b'ppm_tc', b'front_transposed', b'fuse_front'):
+        for key in (b'front_transposed', b'fuse_front'):
             for v in (0, 1):
                 assert lib.fscnn_set_option(ctx, key, v) == 0, key
+        assert lib.fscnn_set_option(ctx, b's1_transposed', 0) < 0        # the superseded kernel generation is gone
         assert lib.fscnn_set_option(ctx, b'no_such_option', 1) < 0
         assert b'no_such_option' in lib.fscnn_last_error()
         nbytes = C.c_size_t()
