@@ -981,4 +981,58 @@ int fscnn_train_ohem_backward(const float* d_logits, const long long* d_label, c
     return FSCNN_OK;
 }
 
+#define FSCNN_TRAIN_CALL(expr, what)                                                                       \
+    do {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                           \
+        if (e_ != cudaSuccess) return fail(FSCNN_ECUDA, what " launch failed: %s", cudaGetErrorString(e_)); \
+        return FSCNN_OK;                                                                                   \
+    } while (0)
+
+int fscnn_train_im2col3x3(const float* d_x, float* d_cols, int n, int c, int h, int w, int stride, int pad, void* stream) {
+    if (!d_x || !d_cols) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || (stride != 1 && stride != 2) || (pad != 0 && pad != 1) || h + 2 * pad < 3 || w + 2 * pad < 3) return fail(FSCNN_EINVAL, "bad shape");
+    FSCNN_TRAIN_CALL(launch_train_im2col(d_x, d_cols, n, c, h, w, stride, pad, (cudaStream_t)stream), "im2col");
+}
+int fscnn_train_col2im3x3(const float* d_dcols, float* d_dx, int n, int c, int h, int w, int stride, int pad, void* stream) {
+    if (!d_dcols || !d_dx) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || (stride != 1 && stride != 2) || (pad != 0 && pad != 1) || h + 2 * pad < 3 || w + 2 * pad < 3) return fail(FSCNN_EINVAL, "bad shape");
+    FSCNN_TRAIN_CALL(launch_train_col2im(d_dcols, d_dx, n, c, h, w, stride, pad, (cudaStream_t)stream), "col2im");
+}
+int fscnn_train_bias_add(float* d_y, const float* d_bias, int n, int c, int hw, void* stream) {
+    if (!d_y || !d_bias || n < 1 || c < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad argument");
+    FSCNN_TRAIN_CALL(launch_train_bias_add(d_y, d_bias, n, c, hw, (cudaStream_t)stream), "bias add");
+}
+int fscnn_train_bias_grad(const float* d_dy, float* d_dbias, void* d_ws, size_t ws_bytes, int n, int c, int hw, void* stream) {
+    if (!d_dy || !d_dbias || n < 1 || c < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad argument");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_workspace_bytes(c, 1, 1));
+    if (rc) return rc;
+    FSCNN_TRAIN_CALL(launch_train_bias_grad(d_dy, d_dbias, d_ws, n, c, hw, (cudaStream_t)stream), "bias gradient");
+}
+int fscnn_train_bilinear(const float* d_in, float* d_out, int planes, int hi, int wi, int ho, int wo, int backward, void* stream) {
+    if (!d_in || !d_out || planes < 1 || hi < 1 || wi < 1 || ho < 1 || wo < 1) return fail(FSCNN_EINVAL, "bad argument");
+    FSCNN_TRAIN_CALL(launch_train_bilinear(d_in, d_out, planes, hi, wi, ho, wo, backward, (cudaStream_t)stream), "bilinear resize");
+}
+int fscnn_train_adaptive_avg_pool(const float* d_in, float* d_out, int planes, int h, int w, int bins, int backward, void* stream) {
+    if (!d_in || !d_out || planes < 1 || h < 1 || w < 1 || bins < 1) return fail(FSCNN_EINVAL, "bad argument");
+    FSCNN_TRAIN_CALL(launch_train_adaptive_pool(d_in, d_out, planes, h, w, bins, backward, (cudaStream_t)stream), "adaptive pool");
+}
+int fscnn_train_dropout(const float* d_x, float* d_y, float p, unsigned long long seed, int64_t numel, void* stream) {
+    if (!d_x || !d_y || numel < 1 || !(p >= 0.f && p < 1.f)) return fail(FSCNN_EINVAL, "bad argument");
+    FSCNN_TRAIN_CALL(launch_train_dropout(d_x, d_y, p, seed, numel, (cudaStream_t)stream), "dropout");
+}
+int fscnn_train_add_relu(const float* d_a, const float* d_b, float* d_y, int relu, int64_t numel, void* stream) {
+    if (!d_a || !d_b || !d_y || numel < 1) return fail(FSCNN_EINVAL, "bad argument");
+    FSCNN_TRAIN_CALL(launch_train_add_relu(d_a, d_b, d_y, relu, numel, (cudaStream_t)stream), "add");
+}
+int fscnn_train_relu_backward(const float* d_y, const float* d_dy, float* d_dx, int64_t numel, void* stream) {
+    if (!d_y || !d_dy || !d_dx || numel < 1) return fail(FSCNN_EINVAL, "bad argument");
+    FSCNN_TRAIN_CALL(launch_train_relu_bwd(d_y, d_dy, d_dx, numel, (cudaStream_t)stream), "relu backward");
+}
+int fscnn_train_sgd_step(float* d_param, const float* d_grad, float* d_momentum_buf, float lr, float momentum, float weight_decay,
+                         float grad_scale, int first_step, int64_t numel, void* stream) {
+    if (!d_param || !d_grad || !d_momentum_buf || numel < 1) return fail(FSCNN_EINVAL, "bad argument");
+    FSCNN_TRAIN_CALL(launch_train_sgd(d_param, d_grad, d_momentum_buf, lr, momentum, weight_decay, grad_scale, first_step, numel,
+                                      (cudaStream_t)stream), "SGD");
+}
+
 }  // extern "C"

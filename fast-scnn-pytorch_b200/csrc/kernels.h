@@ -141,6 +141,17 @@ cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float*
 cudaError_t launch_train_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
                                 const float* save_rstd, float* dx, float* dgamma, float* dbeta, void* ws, int n, int c, int hw,
                                 int relu, cudaStream_t s);
+cudaError_t launch_train_im2col(const float* x, float* cols, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s);
+cudaError_t launch_train_col2im(const float* dcols, float* dx, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s);
+cudaError_t launch_train_bias_add(float* y, const float* b, int n, int c, int hw, cudaStream_t s);
+cudaError_t launch_train_bias_grad(const float* dy, float* db, void* ws, int n, int c, int hw, cudaStream_t s);
+cudaError_t launch_train_bilinear(const float* in, float* out, int planes, int hi, int wi, int ho, int wo, int backward, cudaStream_t s);
+cudaError_t launch_train_adaptive_pool(const float* in, float* out, int planes, int h, int wd, int bins, int backward, cudaStream_t s);
+cudaError_t launch_train_dropout(const float* x, float* y, float p, unsigned long long seed, long long total, cudaStream_t s);
+cudaError_t launch_train_add_relu(const float* a, const float* b, float* y, int relu, long long total, cudaStream_t s);
+cudaError_t launch_train_relu_bwd(const float* y, const float* dy, float* dx, long long total, cudaStream_t s);
+cudaError_t launch_train_sgd(float* p, const float* g, float* buf, float lr, float momentum, float wd, float gscale, int first,
+                             long long total, cudaStream_t s);
 cudaError_t launch_train_ohem_fwd(const float* logits, const long long* label, const float* weight, float* prob, float* out3, void* ws,
                                   int n, int c, int hw, long long ignore, float thresh, int min_kept, cudaStream_t s);
 cudaError_t launch_train_ohem_bwd(const float* logits, const long long* label, const float* weight, const float* prob,

@@ -479,6 +479,201 @@ ohem_grad_kernel(const float* __restrict__ logits, const long long* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// the rest of the network's training-mode operators: dense 3x3 convolution (stem, aux head) through im2col + the GEMM
+// above, per-channel bias, bilinear resize with align_corners=True, adaptive average pooling (overlapping bins), dropout,
+// add + ReLU, and the SGD update
+// ---------------------------------------------------------------------------------------------------------------------
+// cols[n][(ci*9 + ky*3 + kx)][oy*Wo + ox] = x[n][ci][oy*s + ky - pad][ox*s + kx - pad] (0 outside)
+__global__ void __launch_bounds__(kT)
+im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ cols, int C, int H, int W, int Ho, int Wo, int stride, int pad,
+                 long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+        const long long r = i / ((long long)Wo * Ho);
+        const int k = (int)(r % (C * 9));
+        const long long n = r / (C * 9);
+        const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+        const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
+        cols[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + ((n * C + ci) * H + iy) * W + ix) : 0.f;
+    }
+}
+
+// dx[n][ci][iy][ix] = sum over the taps that read this pixel of dcols[n][ci*9 + ky*3 + kx][oy*Wo + ox]
+__global__ void __launch_bounds__(kT)
+col2im3x3_kernel(const float* __restrict__ dcols, float* __restrict__ dx, int C, int H, int W, int Ho, int Wo, int stride, int pad,
+                 long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int ix = (int)(i % W), iy = (int)((i / W) % H);
+        const long long plane = i / ((long long)W * H);
+        const int ci = (int)(plane % C);
+        const long long n = plane / C;
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ty = iy + pad - ky;
+            if (ty < 0 || ty % stride) continue;
+            const int oy = ty / stride;
+            if (oy >= Ho) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tx = ix + pad - kx;
+                if (tx < 0 || tx % stride) continue;
+                const int ox = tx / stride;
+                if (ox < Wo) acc += __ldg(dcols + ((n * C * 9 + ci * 9 + ky * 3 + kx) * Ho + oy) * Wo + ox);
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+bias_add_kernel(float* __restrict__ y, const float* __restrict__ b, int C, int HW, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT)
+        y[i] += __ldg(b + (int)((i / HW) % C));
+}
+
+// grid (C, S): partial[s][c] = sum of dy over this CTA's share of channel c
+__global__ void __launch_bounds__(kT)
+channel_sum_kernel(const float* __restrict__ dy, double* __restrict__ partial, int N, int C, int HW) {
+    __shared__ double sm[8];
+    const int c = blockIdx.x, S = gridDim.y;
+    double v[1] = {0.0};
+    const long long per = (long long)N * HW;
+    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT)
+        v[0] += (double)__ldg(dy + ((i / HW) * C + c) * HW + i % HW);
+    block_sum<1>(v, sm);
+    if (threadIdx.x == 0) partial[(long long)blockIdx.y * C + c] = v[0];
+}
+
+// F.interpolate(mode='bilinear', align_corners=True): the arithmetic of the eval path's kernels
+__device__ __forceinline__ void ac_coord(int o, float sc, int in, int& i0, int& i1, float& l) {
+    const float f = sc * (float)o;
+    i0 = min((int)f, in - 1);
+    i1 = min(i0 + 1, in - 1);
+    l = f - (float)i0;
+}
+
+__global__ void __launch_bounds__(kT)
+bilinear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, int Wi, int Ho, int Wo, long long total) {
+    const float scy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, scx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
+        const float* xp = x + (i / ((long long)Wo * Ho)) * Hi * Wi;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        ac_coord(oy, scy, Hi, y0, y1, ly);
+        ac_coord(ox, scx, Wi, x0, x1, lx);
+        const float top = fmaf(lx, __ldg(xp + y0 * Wi + x1), (1.f - lx) * __ldg(xp + y0 * Wi + x0));
+        const float bot = fmaf(lx, __ldg(xp + y1 * Wi + x1), (1.f - lx) * __ldg(xp + y1 * Wi + x0));
+        y[i] = fmaf(ly, bot, (1.f - ly) * top);
+    }
+}
+
+// gather form of the backward: every input pixel collects from the output pixels whose 2 x 2 taps include it (found by running
+// the forward's own index computation over the candidate range, so the two passes agree exactly); deterministic, no atomics
+__global__ void __launch_bounds__(kT)
+bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int Hi, int Wi, int Ho, int Wo, long long total) {
+    const float scy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, scx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int ix = (int)(i % Wi), iy = (int)((i / Wi) % Hi);
+        const float* dp = dy + (i / ((long long)Wi * Hi)) * Ho * Wo;
+        // output rows that can touch input row iy: floor(scy * oy) in {iy - 1, iy}
+        int oy_lo = 0, oy_hi = Ho - 1, ox_lo = 0, ox_hi = Wo - 1;
+        if (scy > 0.f) { oy_lo = max(0, (int)floorf((float)(iy - 1) / scy) - 1); oy_hi = min(Ho - 1, (int)ceilf((float)(iy + 1) / scy) + 1); }
+        if (scx > 0.f) { ox_lo = max(0, (int)floorf((float)(ix - 1) / scx) - 1); ox_hi = min(Wo - 1, (int)ceilf((float)(ix + 1) / scx) + 1); }
+        float acc = 0.f;
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            int y0, y1;
+            float ly;
+            ac_coord(oy, scy, Hi, y0, y1, ly);
+            const float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f);
+            if (wy == 0.f && y0 != iy && y1 != iy) continue;
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                int x0, x1;
+                float lx;
+                ac_coord(ox, scx, Wi, x0, x1, lx);
+                const float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
+                if (x0 == ix || x1 == ix) acc = fmaf(wy * wx, __ldg(dp + (long long)oy * Wo + ox), acc);
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+// nn.AdaptiveAvgPool2d(S): bin i covers [floor(i*h/S), ceil((i+1)*h/S)); bins overlap when h % S != 0
+__global__ void __launch_bounds__(kT)
+adaptive_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int S, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int bx = (int)(i % S), by = (int)((i / S) % S);
+        const float* xp = x + (i / (S * S)) * H * W;
+        const int y0 = (by * H) / S, y1 = ((by + 1) * H + S - 1) / S, x0 = (bx * W) / S, x1 = ((bx + 1) * W + S - 1) / S;
+        float acc = 0.f;
+        for (int yy = y0; yy < y1; ++yy)
+            for (int xx = x0; xx < x1; ++xx) acc += __ldg(xp + yy * W + xx);
+        y[i] = acc / (float)((y1 - y0) * (x1 - x0));
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+adaptive_pool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int S, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const int xx = (int)(i % W), yy = (int)((i / W) % H);
+        const float* dp = dy + (i / ((long long)W * H)) * S * S;
+        float acc = 0.f;
+        for (int by = 0; by < S; ++by) {
+            const int y0 = (by * H) / S, y1 = ((by + 1) * H + S - 1) / S;
+            if (yy < y0 || yy >= y1) continue;
+            for (int bx = 0; bx < S; ++bx) {
+                const int x0 = (bx * W) / S, x1 = ((bx + 1) * W + S - 1) / S;
+                if (xx >= x0 && xx < x1) acc += __ldg(dp + by * S + bx) / (float)((y1 - y0) * (x1 - x0));
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+// nn.Dropout(p) in train mode: keep with probability 1 - p, scale by 1 / (1 - p).  The keep decision is a counter-based hash
+// of (seed, element index), so forward and backward regenerate it instead of storing a mask.
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, long long i, float p) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);      // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * (1.f / 16777216.f) >= p;
+}
+__global__ void __launch_bounds__(kT)
+dropout_kernel(const float* __restrict__ x, float* __restrict__ y, float p, unsigned long long seed, long long total) {
+    const float scale = 1.f / (1.f - p);
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT)
+        y[i] = dropout_keep(seed, i, p) ? x[i] * scale : 0.f;
+}
+
+// y = relu(a + b); backward: g = dy where y > 0
+__global__ void __launch_bounds__(kT)
+add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int relu, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const float v = a[i] + b[i];
+        y[i] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+__global__ void __launch_bounds__(kT)
+relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+// torch.optim.SGD(momentum, weight_decay) on flat buffers (train.py:195-198): g += wd * p; buf = first ? g : m * buf + g; p -= lr * buf
+__global__ void __launch_bounds__(kT)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, float lr, float momentum, float wd, float gscale,
+           int first, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        const float gi = fmaf(wd, p[i], g[i] * gscale);
+        const float b = first ? gi : fmaf(momentum, buf[i], gi);
+        buf[i] = b;
+        p[i] -= lr * b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------------
 static int grid_for(long long total) {
@@ -604,6 +799,69 @@ cudaError_t launch_train_ohem_bwd(const float* logits, const long long* label, c
     const long long npix = (long long)n * hw;
     ohem_grad_kernel<<<grid_for(npix), kT, 0, s>>>(logits, label, prob, weight, c, hw, npix, ignore,
                                                    reinterpret_cast<const unsigned long long*>(ws), out3, gout, dlogits);
+    return cudaGetLastError();
+}
+
+
+// dense 3x3 convolution through im2col: cols [n][cin*9][ho*wo] (caller scratch), then the pointwise GEMMs with cin -> cin*9
+cudaError_t launch_train_im2col(const float* x, float* cols, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s) {
+    const int ho = (h + 2 * pad - 3) / stride + 1, wo = (wd + 2 * pad - 3) / stride + 1;
+    const long long total = (long long)n * c * 9 * ho * wo;
+    im2col3x3_kernel<<<grid_for(total), kT, 0, s>>>(x, cols, c, h, wd, ho, wo, stride, pad, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_col2im(const float* dcols, float* dx, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s) {
+    const int ho = (h + 2 * pad - 3) / stride + 1, wo = (wd + 2 * pad - 3) / stride + 1;
+    const long long total = (long long)n * c * h * wd;
+    col2im3x3_kernel<<<grid_for(total), kT, 0, s>>>(dcols, dx, c, h, wd, ho, wo, stride, pad, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_bias_add(float* y, const float* b, int n, int c, int hw, cudaStream_t s) {
+    const long long total = (long long)n * c * hw;
+    bias_add_kernel<<<grid_for(total), kT, 0, s>>>(y, b, c, hw, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_bias_grad(const float* dy, float* db, void* ws, int n, int c, int hw, cudaStream_t s) {
+    const int S = splits_for(c, (long long)n * hw);
+    channel_sum_kernel<<<dim3(c, S), kT, 0, s>>>(dy, reinterpret_cast<double*>(ws), n, c, hw);
+    reduce_partials_kernel<<<(c + kT - 1) / kT, kT, 0, s>>>(reinterpret_cast<const double*>(ws), db, c, S);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_bilinear(const float* in, float* out, int planes, int hi, int wi, int ho, int wo, int backward, cudaStream_t s) {
+    if (!backward) {
+        const long long total = (long long)planes * ho * wo;
+        bilinear_fwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, hi, wi, ho, wo, total);
+    } else {      // in = dy [planes][ho][wo], out = dx [planes][hi][wi]
+        const long long total = (long long)planes * hi * wi;
+        bilinear_bwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, hi, wi, ho, wo, total);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_train_adaptive_pool(const float* in, float* out, int planes, int h, int wd, int bins, int backward, cudaStream_t s) {
+    if (!backward) {
+        const long long total = (long long)planes * bins * bins;
+        adaptive_pool_fwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, h, wd, bins, total);
+    } else {      // in = dy [planes][S][S], out = dx [planes][h][w]
+        const long long total = (long long)planes * h * wd;
+        adaptive_pool_bwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, h, wd, bins, total);
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_train_dropout(const float* x, float* y, float p, unsigned long long seed, long long total, cudaStream_t s) {
+    dropout_kernel<<<grid_for(total), kT, 0, s>>>(x, y, p, seed, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_add_relu(const float* a, const float* b, float* y, int relu, long long total, cudaStream_t s) {
+    add_relu_kernel<<<grid_for(total), kT, 0, s>>>(a, b, y, relu, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_relu_bwd(const float* y, const float* dy, float* dx, long long total, cudaStream_t s) {
+    relu_bwd_kernel<<<grid_for(total), kT, 0, s>>>(y, dy, dx, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_train_sgd(float* p, const float* g, float* buf, float lr, float momentum, float wd, float gscale, int first,
+                             long long total, cudaStream_t s) {
+    sgd_kernel<<<grid_for(total), kT, 0, s>>>(p, g, buf, lr, momentum, wd, gscale, first, total);
     return cudaGetLastError();
 }
 

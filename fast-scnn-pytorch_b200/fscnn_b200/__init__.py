@@ -4,3 +4,4 @@ context plus its PyTorch-allocated weight and workspace buffers."""
 from .native import NativeError, lib, lib_path  # noqa: F401
 from .engine import Engine, PRECISIONS  # noqa: F401
 from .pipeline import StreamingEvaluator  # noqa: F401
+from .trainer import Trainer, poly_lr  # noqa: F401

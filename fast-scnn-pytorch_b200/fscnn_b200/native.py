@@ -77,6 +77,17 @@ _SIGNATURES = {
     'fscnn_train_batchnorm_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.c_void_p]),
+    'fscnn_train_im2col3x3': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_col2im3x3': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_bias_add': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_bias_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_bilinear': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_adaptive_avg_pool': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'fscnn_train_dropout': (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_ulonglong, C.c_int64, C.c_void_p]),
+    'fscnn_train_add_relu': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
+    'fscnn_train_relu_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'fscnn_train_sgd_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64,
+                                       C.c_void_p]),
     'fscnn_train_ohem_workspace_bytes': (C.c_int, [C.POINTER(C.c_size_t)]),
     'fscnn_train_ohem_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                            C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_void_p]),

@@ -223,3 +223,226 @@ def batchnorm_relu(x, bn: torch.nn.BatchNorm2d, relu: bool):
 
 def ohem_cross_entropy(logits, target, class_weight: Optional[torch.Tensor] = None, ignore_label=-1, thresh=0.7, min_kept=256):
     return OhemCrossEntropy.apply(logits, target, class_weight, ignore_label, thresh, min_kept)
+
+
+# ---- the remaining operators of the network (dense 3x3 conv, bias, bilinear resize, adaptive pooling, dropout, add + ReLU) ----
+def _lib():
+    return native.lib()
+
+
+class Conv3x3Dense(torch.autograd.Function):
+    """nn.Conv2d(cin, cout, 3, stride, pad, bias=False): im2col + the pointwise GEMM with cin -> cin * 9 (stem, aux head)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        x, w = _check(x, 'input'), _check(weight, 'weight')
+        n, c, h, wd = x.shape
+        cout = w.shape[0]
+        if tuple(w.shape) != (cout, c, 3, 3):
+            raise ValueError(f'dense weight must be [cout,{c},3,3], got {tuple(w.shape)}')
+        ho, wo = (h + 2 * pad - 3) // stride + 1, (wd + 2 * pad - 3) // stride + 1
+        cols = torch.empty((n, c * 9, ho * wo), dtype=torch.float32, device=x.device)
+        y = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            native.check(_lib().fscnn_train_im2col3x3(x.data_ptr(), cols.data_ptr(), n, c, h, wd, stride, pad, _stream()), 'fscnn_train_im2col3x3')
+            native.check(_lib().fscnn_train_pwconv_forward(cols.data_ptr(), w.data_ptr(), y.data_ptr(), n, c * 9, cout, ho * wo, _stream()),
+                         'fscnn_train_pwconv_forward')
+        ctx.save_for_backward(cols, w)
+        ctx.geom = (n, c, h, wd, stride, pad, ho, wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, w = ctx.saved_tensors
+        n, c, h, wd, stride, pad, ho, wo = ctx.geom
+        cout = w.shape[0]
+        dy = dy.contiguous()
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dcols = torch.empty_like(cols) if need_dx else None
+        dw = torch.zeros_like(w) if need_dw else None
+        ws = _workspace(dy.device, 1, cout, c * 9)
+        with torch.cuda.device(dy.device):
+            for i0 in range(0, n, 64):
+                m = min(64, n - i0)
+                part = torch.empty_like(w) if (need_dw and n > 64) else dw
+                native.check(_lib().fscnn_train_pwconv_backward(
+                    cols[i0:i0 + m].data_ptr(), w.data_ptr(), dy[i0:i0 + m].data_ptr(), dcols[i0:i0 + m].data_ptr() if need_dx else None,
+                    part.data_ptr() if need_dw else None, ws.data_ptr(), ws.numel(), m, c * 9, cout, ho * wo, _stream()),
+                    'fscnn_train_pwconv_backward')
+                if need_dw and n > 64:
+                    dw += part
+            dx = None
+            if need_dx:
+                dx = torch.empty((n, c, h, wd), dtype=torch.float32, device=dy.device)
+                native.check(_lib().fscnn_train_col2im3x3(dcols.data_ptr(), dx.data_ptr(), n, c, h, wd, stride, pad, _stream()),
+                             'fscnn_train_col2im3x3')
+        return dx, dw, None, None
+
+
+class BiasAdd(torch.autograd.Function):
+    """y = x + bias[c] (the bias of a 1x1 convolution)"""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        x, b = _check(x, 'input'), _check(bias, 'bias')
+        n, c, h, w = x.shape
+        y = x.clone()
+        with torch.cuda.device(x.device):
+            native.check(_lib().fscnn_train_bias_add(y.data_ptr(), b.data_ptr(), n, c, h * w, _stream()), 'fscnn_train_bias_add')
+        ctx.shape = (n, c, h * w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, hw = ctx.shape
+        dy = dy.contiguous()
+        db = None
+        if ctx.needs_input_grad[1]:
+            db = torch.empty(c, dtype=torch.float32, device=dy.device)
+            ws = _workspace(dy.device, c)
+            with torch.cuda.device(dy.device):
+                native.check(_lib().fscnn_train_bias_grad(dy.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), n, c, hw, _stream()),
+                             'fscnn_train_bias_grad')
+        return dy, db
+
+
+class BilinearResize(torch.autograd.Function):
+    """F.interpolate(x, size, mode='bilinear', align_corners=True)"""
+
+    @staticmethod
+    def forward(ctx, x, ho, wo):
+        x = _check(x, 'input')
+        n, c, hi, wi = x.shape
+        y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            native.check(_lib().fscnn_train_bilinear(x.data_ptr(), y.data_ptr(), n * c, hi, wi, ho, wo, 0, _stream()), 'fscnn_train_bilinear')
+        ctx.geom = (n, c, hi, wi, ho, wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, hi, wi, ho, wo = ctx.geom
+        dy = dy.contiguous()
+        dx = torch.empty((n, c, hi, wi), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            native.check(_lib().fscnn_train_bilinear(dy.data_ptr(), dx.data_ptr(), n * c, hi, wi, ho, wo, 1, _stream()), 'fscnn_train_bilinear')
+        return dx, None, None
+
+
+class AdaptiveAvgPool(torch.autograd.Function):
+    """nn.AdaptiveAvgPool2d(bins)"""
+
+    @staticmethod
+    def forward(ctx, x, bins):
+        x = _check(x, 'input')
+        n, c, h, w = x.shape
+        y = torch.empty((n, c, bins, bins), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            native.check(_lib().fscnn_train_adaptive_avg_pool(x.data_ptr(), y.data_ptr(), n * c, h, w, bins, 0, _stream()),
+                         'fscnn_train_adaptive_avg_pool')
+        ctx.geom = (n, c, h, w, bins)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, bins = ctx.geom
+        dy = dy.contiguous()
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            native.check(_lib().fscnn_train_adaptive_avg_pool(dy.data_ptr(), dx.data_ptr(), n * c, h, w, bins, 1, _stream()),
+                         'fscnn_train_adaptive_avg_pool')
+        return dx, None
+
+
+class Dropout(torch.autograd.Function):
+    """nn.Dropout(p) in train mode; the mask is regenerated from the seed in the backward"""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        x = _check(x, 'input')
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            native.check(_lib().fscnn_train_dropout(x.data_ptr(), y.data_ptr(), float(p), int(seed), x.numel(), _stream()), 'fscnn_train_dropout')
+        ctx.p, ctx.seed = float(p), int(seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        with torch.cuda.device(dy.device):
+            native.check(_lib().fscnn_train_dropout(dy.data_ptr(), dx.data_ptr(), ctx.p, ctx.seed, dy.numel(), _stream()), 'fscnn_train_dropout')
+        return dx, None, None
+
+
+class AddReLU(torch.autograd.Function):
+    """relu(a + b) (relu=False: a + b)"""
+
+    @staticmethod
+    def forward(ctx, a, b, relu):
+        a, b = _check(a, 'a'), _check(b, 'b')
+        if a.shape != b.shape:
+            raise ValueError(f'shapes differ: {tuple(a.shape)} vs {tuple(b.shape)}')
+        y = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            native.check(_lib().fscnn_train_add_relu(a.data_ptr(), b.data_ptr(), y.data_ptr(), int(bool(relu)), a.numel(), _stream()),
+                         'fscnn_train_add_relu')
+        ctx.relu = bool(relu)
+        if relu:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        if not ctx.relu:
+            return dy, dy, None
+        (y,) = ctx.saved_tensors
+        g = torch.empty_like(dy)
+        with torch.cuda.device(dy.device):
+            native.check(_lib().fscnn_train_relu_backward(y.data_ptr(), dy.data_ptr(), g.data_ptr(), dy.numel(), _stream()),
+                         'fscnn_train_relu_backward')
+        return g, g, None
+
+
+def conv3x3_dense(x, weight, stride, pad):
+    return Conv3x3Dense.apply(x, weight, int(stride), int(pad))
+
+
+def bias_add(x, bias):
+    return BiasAdd.apply(x, bias)
+
+
+def bilinear_resize(x, size):
+    return BilinearResize.apply(x, int(size[0]), int(size[1]))
+
+
+def adaptive_avg_pool(x, bins):
+    return AdaptiveAvgPool.apply(x, int(bins))
+
+
+_dropout_calls = [0]
+
+
+def dropout(x, p, training=True, seed=None):
+    """nn.Dropout(p).  ``seed`` None: drawn from torch's CPU generator, so ``torch.manual_seed`` makes runs reproducible."""
+    if not training or p == 0.0:
+        return x
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return Dropout.apply(x, float(p), seed)
+
+
+def add_relu(a, b, relu=True):
+    return AddReLU.apply(a, b, bool(relu))
+
+
+def sgd_step(param_flat, grad_flat, momentum_buf, lr, momentum=0.9, weight_decay=1e-4, grad_scale=1.0, first_step=False):
+    """torch.optim.SGD(momentum, weight_decay) (reference train.py:195-198) on flat fp32 buffers, one launch."""
+    for t in (param_flat, grad_flat, momentum_buf):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param_flat.numel():
+            raise ValueError('sgd_step takes three contiguous CUDA float32 buffers of equal length')
+    with torch.cuda.device(param_flat.device):
+        native.check(_lib().fscnn_train_sgd_step(param_flat.data_ptr(), grad_flat.data_ptr(), momentum_buf.data_ptr(), float(lr), float(momentum),
+                                                 float(weight_decay), float(grad_scale), int(bool(first_step)), param_flat.numel(), _stream()),
+                     'fscnn_train_sgd_step')

@@ -1,0 +1,93 @@
+"""One training step of the reference (train.py:241-306) on the B200 training operators.
+
+``Trainer`` owns what ``train.py`` sets up around the model: the loss (``MixSoftmaxCrossEntropyOHEMLoss``: OHEM cross entropy
+on the main head + ``aux_weight`` x the aux head, utils/loss.py:185-206), SGD with momentum and weight decay on ALL parameters
+(one param group, train.py:195-198), the poly learning-rate schedule (utils/lr_scheduler.py:66-91) and, under
+``torch.distributed``, DDP semantics: per-rank BatchNorm statistics, gradients averaged over the ranks with ONE NCCL all-reduce of
+a flat fp32 buffer (1.16 M parameters, 4.6 MB) followed by the same fused SGD update on every rank.
+
+Parameters and gradients live in two flat buffers (the module's parameters and their .grad are views into them), so the
+collective and the optimizer are one launch each.  The reference trains under fp16 autocast + GradScaler (train.py:73-74,
+:267-275: ``--use-fp16`` defaults to True); this path keeps fp32 throughout, which is the more exact of the two.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import train_ops
+
+# the 19 Cityscapes class weights hard-coded by the reference (utils/loss.py:135-137)
+OHEM_CLASS_WEIGHTS = (0.8373, 0.918, 0.866, 1.0345, 1.0166, 0.9969, 0.9754, 1.0489, 0.8786, 1.0023, 0.9539, 0.9843, 1.1116, 0.9037,
+                      1.0865, 1.0955, 1.0865, 1.1529, 1.0507)
+
+
+def poly_lr(base_lr: float, cur_iter: int, nepochs: int, iters_per_epoch: int, power: float = 0.9) -> float:
+    """LRScheduler(mode='poly') (utils/lr_scheduler.py:67-76, :91): base * (1 - T / N) ** power with N = nepochs * iters - 1."""
+    n = nepochs * iters_per_epoch - 1
+    return base_lr * (1.0 - cur_iter / n) ** power if n > 0 else base_lr
+
+
+class Trainer:
+    def __init__(self, model, base_lr=1e-2, momentum=0.9, weight_decay=1e-4, aux_weight=0.4, ignore_label=-1, ohem_thresh=0.7,
+                 ohem_min_kept=256, use_class_weights: Optional[bool] = None, nepochs=160, iters_per_epoch=1000, process_group=None):
+        self.model = model
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params or not params[0].is_cuda:
+            raise RuntimeError('move the model to a CUDA device before building the Trainer (there is no CPU path)')
+        dev = params[0].device
+        total = sum(p.numel() for p in params)
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.momentum_buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:      # parameters and their gradients become views into the flat buffers
+                n = p.numel()
+                self.flat_param[off:off + n].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + n].view_as(p)
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+                off += n
+        self.params = params
+        self.base_lr, self.momentum, self.weight_decay = float(base_lr), float(momentum), float(weight_decay)
+        self.aux_weight, self.ignore_label = float(aux_weight), int(ignore_label)
+        self.ohem_thresh, self.ohem_min_kept = float(ohem_thresh), int(ohem_min_kept)
+        self.nepochs, self.iters_per_epoch = int(nepochs), int(iters_per_epoch)
+        if use_class_weights is None:      # the reference always uses its 19 weights (only valid for 19 classes)
+            use_class_weights = model.num_classes == len(OHEM_CLASS_WEIGHTS)
+        self.class_weight = torch.tensor(OHEM_CLASS_WEIGHTS, dtype=torch.float32, device=dev) if use_class_weights else None
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.iteration = 0
+        if self.world > 1:      # every rank starts from rank 0's weights
+            dist.broadcast(self.flat_param, src=0, group=process_group)
+
+    def loss(self, outputs, target):
+        """MixSoftmaxCrossEntropyOHEMLoss.forward (utils/loss.py:191-206)."""
+        total = train_ops.ohem_cross_entropy(outputs[0], target, self.class_weight, self.ignore_label, self.ohem_thresh, self.ohem_min_kept)
+        for aux_out in outputs[1:]:
+            total = total + self.aux_weight * train_ops.ohem_cross_entropy(aux_out, target, self.class_weight, self.ignore_label,
+                                                                            self.ohem_thresh, self.ohem_min_kept)
+        return total
+
+    def step(self, images, target, lr: Optional[float] = None):
+        """zero_grad -> forward -> loss -> backward -> gradient all-reduce (mean) -> SGD (train.py:253-284).  Returns the loss
+        as a 0-d device tensor (no host synchronisation; the reference's loss.item() is the caller's choice)."""
+        self.model.train()
+        if lr is None:
+            lr = poly_lr(self.base_lr, self.iteration, self.nepochs, self.iters_per_epoch)
+        self.flat_grad.zero_()
+        for p in self.params:      # autograd accumulates into the flat-buffer views
+            if p.grad is None:
+                raise RuntimeError('a parameter lost its flat gradient view (zero_grad(set_to_none=True) was called on the model?)')
+        loss = self.loss(self.model(images), target)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        train_ops.sgd_step(self.flat_param, self.flat_grad, self.momentum_buf, lr, self.momentum, self.weight_decay,
+                           grad_scale=1.0 / self.world, first_step=self.iteration == 0)
+        self.iteration += 1
+        return loss.detach()

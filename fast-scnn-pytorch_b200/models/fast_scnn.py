@@ -69,19 +69,30 @@ def _train_seq(seq, x):
     while i < len(layers):
         m = layers[i]
         if isinstance(m, nn.Conv2d):
-            if m.bias is not None or m.dilation != (1, 1):
-                raise NotImplementedError('training operators cover bias-free, undilated convolutions')
+            if m.dilation != (1, 1):
+                raise NotImplementedError('training operators cover undilated convolutions')
             if m.kernel_size == (1, 1) and m.groups == 1 and m.stride == (1, 1) and m.padding == (0, 0):
                 x = train_ops.pointwise_conv(x, m.weight)
-            elif m.kernel_size == (3, 3) and m.groups == m.in_channels == m.out_channels and m.padding == (1, 1) and m.stride[0] == m.stride[1]:
+            elif (m.kernel_size == (3, 3) and m.groups == m.in_channels == m.out_channels and m.groups > 1 and m.padding == (1, 1)
+                  and m.stride[0] == m.stride[1]):
                 x = train_ops.depthwise_conv3x3(x, m.weight, m.stride[0])
+            elif m.kernel_size == (3, 3) and m.groups == 1 and m.stride[0] == m.stride[1] and m.padding in ((0, 0), (1, 1)):
+                x = train_ops.conv3x3_dense(x, m.weight, m.stride[0], m.padding[0])
             else:
-                raise NotImplementedError(f'no training operator for {m} yet (covered: depthwise 3x3 pad 1, pointwise 1x1)')
+                raise NotImplementedError(f'no training operator for {m} (covered: dense 3x3, depthwise 3x3 pad 1, pointwise 1x1)')
+            if m.bias is not None:
+                x = train_ops.bias_add(x, m.bias)
             i += 1
         elif isinstance(m, nn.BatchNorm2d):
             relu = i + 1 < len(layers) and isinstance(layers[i + 1], nn.ReLU)
             x = train_ops.batchnorm_relu(x, m, relu)
             i += 2 if relu else 1
+        elif isinstance(m, nn.ReLU):          # a ReLU that does not follow a BatchNorm (none in this network)
+            x = train_ops.add_relu(x, torch.zeros_like(x), True)
+            i += 1
+        elif isinstance(m, nn.Dropout):
+            x = train_ops.dropout(x, m.p, m.training)
+            i += 1
         elif isinstance(m, _ParamHolder):
             x = m(x)
             i += 1
@@ -141,8 +152,9 @@ class LinearBottleneck(_ParamHolder):
                                    nn.Conv2d(cin * t, cout, 1, bias=False), nn.BatchNorm2d(cout))
 
     def _train_forward(self, x):
+        from fscnn_b200 import train_ops
         out = _train_seq(self.block, x)
-        return x + out if self.use_shortcut else out      # reference :111-115
+        return train_ops.add_relu(x, out, False) if self.use_shortcut else out      # reference :111-115
 
 
 class PyramidPooling(_ParamHolder):
@@ -158,6 +170,15 @@ class PyramidPooling(_ParamHolder):
     def pool(self, x, size):   # kept: export scripts introspect ``ppm.pool`` (export_onnx_fixed.py:143-146)
         return nn.AdaptiveAvgPool2d(size)(x)
 
+    def _train_forward(self, x):   # reference :137-145
+        from fscnn_b200 import train_ops
+        size = x.shape[2:]
+        feats = [x]
+        for i, bins in enumerate((1, 2, 3, 6), start=1):
+            f = getattr(self, f'conv{i}')(train_ops.adaptive_avg_pool(x, bins))
+            feats.append(train_ops.bilinear_resize(f, size))
+        return self.out(torch.cat(feats, dim=1))
+
 
 class LearningToDownsample(_ParamHolder):
     """``conv`` (3->32 s2), ``dsconv1`` (32->48 s2), ``dsconv2`` (48->64 s2) (reference :148-161)."""
@@ -167,6 +188,9 @@ class LearningToDownsample(_ParamHolder):
         self.conv = ConvBNReLU(3, c1, 3, 2)
         self.dsconv1 = DSConv(c1, c2, 2)
         self.dsconv2 = DSConv(c2, cout, 2)
+
+    def _train_forward(self, x):   # reference :157-161
+        return self.dsconv2(self.dsconv1(self.conv(x)))
 
 
 class GlobalFeatureExtractor(_ParamHolder):
@@ -181,6 +205,12 @@ class GlobalFeatureExtractor(_ParamHolder):
             cin = planes
         self.ppm = PyramidPooling(block_channels[2], cout)
 
+    def _train_forward(self, x):   # reference :182-187
+        for i in (1, 2, 3):
+            for block in getattr(self, f'bottleneck{i}'):
+                x = block(x)
+        return self.ppm(x)
+
 
 class FeatureFusionModule(_ParamHolder):
     """``dwconv``, ``conv_lower_res`` and ``conv_higher_res`` (both 1x1 with bias + BN) (reference :190-218)."""
@@ -193,6 +223,13 @@ class FeatureFusionModule(_ParamHolder):
         self.conv_higher_res = nn.Sequential(nn.Conv2d(highter_in_channels, out_channels, 1), nn.BatchNorm2d(out_channels))
         self.relu = nn.ReLU(True)
 
+    def _train_forward(self, higher_res_feature, lower_res_feature):   # reference :207-218
+        from fscnn_b200 import train_ops
+        lower = train_ops.bilinear_resize(lower_res_feature, higher_res_feature.shape[2:])
+        lower = _train_seq(self.conv_lower_res, self.dwconv(lower))
+        higher = _train_seq(self.conv_higher_res, higher_res_feature)
+        return train_ops.add_relu(higher, lower, True)
+
 
 class Classifer(_ParamHolder):
     """``dsconv1``, ``dsconv2`` and ``conv`` = [Dropout, Conv2d(128, nc, 1)] (reference :221-237; the
@@ -203,6 +240,9 @@ class Classifer(_ParamHolder):
         self.dsconv1 = DSConv(channels, channels, stride)
         self.dsconv2 = DSConv(channels, channels, stride)
         self.conv = nn.Sequential(nn.Dropout(0.1), nn.Conv2d(channels, num_classes, 1))
+
+    def _train_forward(self, x):   # reference :233-237
+        return _train_seq(self.conv, self.dsconv2(self.dsconv1(x)))
 
 
 class _Runtime:
@@ -271,10 +311,8 @@ class FastSCNN(nn.Module):
     def _engine(self, device: torch.device):
         from fscnn_b200 import Engine
         if self.training:
-            raise NotImplementedError('FastSCNN (B200 build): the whole-network forward runs in eval mode only; call '
-                                      'model.eval() first.  In training mode the covered submodules (ConvBNReLU 1x1, DSConv, '
-                                      'DWConv, LinearBottleneck) and fscnn_b200.train_ops.ohem_cross_entropy run on their own '
-                                      '(first slice of the training step); there is no eager-PyTorch fallback for the rest')
+            raise RuntimeError('the fused inference engine serves eval mode; in training mode FastSCNN.forward runs the training '
+                               'operators (fscnn_b200/train_ops.py) and predict / evaluate are not available: call model.eval()')
         if device.type != 'cuda':
             raise RuntimeError(f'FastSCNN (B200 build) runs on CUDA devices only, got a tensor on {device}; move the '
                                'model and the input to the GPU (there is no CPU fallback)')
@@ -305,9 +343,30 @@ class FastSCNN(nn.Module):
     def forward(self, x, normalize=(IMAGENET_MEAN, IMAGENET_STD)):
         """Returns ``(logits,)`` or ``(logits, aux_logits)``: NCHW fp32 at the input resolution
         (reference models/fast_scnn.py:33-46).  ``normalize`` only applies to raw uint8 input."""
+        if self.training:
+            return self._train_forward(x)
         x = self._as_input(x)
         logits, aux = self._engine(x.device).forward_logits(x, want_aux=self.aux, norm=normalize)
         return (logits, aux) if self.aux else (logits,)
+
+    def _train_forward(self, x):
+        """The reference forward (models/fast_scnn.py:33-46) in TRAINING mode: BatchNorm with batch statistics (running statistics
+        updated), Dropout active, every operator a CUDA kernel of csrc/train.cu behind torch.autograd.Function wrappers
+        (fscnn_b200/train_ops.py), so ``loss.backward()`` works as usual.  fp32 NCHW tensors."""
+        from fscnn_b200 import train_ops
+        if x.dim() != 4 or x.size(1) != 3 or x.dtype != torch.float32:
+            raise ValueError(f'training forward expects a float32 [N,3,H,W] batch, got {x.dtype} {tuple(x.shape)}')
+        if not x.is_cuda:
+            raise RuntimeError(f'FastSCNN (B200 build) runs on CUDA devices only, got a tensor on {x.device} (there is no CPU fallback)')
+        size = x.shape[2:]
+        higher = self.learning_to_downsample(x)
+        t = self.global_feature_extractor(higher)
+        t = self.feature_fusion(higher, t)
+        t = self.classifier(t)
+        outputs = [train_ops.bilinear_resize(t, size)]
+        if self.aux:
+            outputs.append(train_ops.bilinear_resize(_train_seq(self.auxlayer, higher), size))
+        return tuple(outputs)
 
     # ---- fused fast paths (additions) ------------------------------------------------------------
     @torch.no_grad()

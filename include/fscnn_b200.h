@@ -238,6 +238,31 @@ int fscnn_train_batchnorm_backward(const float* d_x, const float* d_y, const flo
                                    const float* d_save_rstd, float* d_dx, float* d_dgamma, float* d_dbeta, void* d_ws, size_t ws_bytes,
                                    int n, int c, int hw, int relu, void* stream);
 
+/* The remaining training-mode operators of the network (fast_scnn.py:24-31, :118-145, :190-237; train.py:195-198):
+ *  im2col3x3 / col2im3x3 : the dense 3x3 convolutions (stem: stride 2 pad 0; aux head: stride 1 pad 1) run as im2col + the
+ *              pointwise GEMMs above with cin -> cin*9: d_cols [n][c*9][ho*wo], k = ci*9 + ky*3 + kx (PyTorch's weight order);
+ *              col2im3x3 folds the column gradient back into d_dx (gather form, deterministic)
+ *  bias_add / bias_grad  : the bias of feature_fusion.conv_*_res.0, classifier.conv.1, auxlayer.4 (in place) and its gradient
+ *  bilinear  : F.interpolate(mode='bilinear', align_corners=True) of [planes][hi][wi] -> [planes][ho][wo]; backward != 0: d_in is
+ *              the gradient [planes][ho][wo], d_out the input gradient [planes][hi][wi] (gather form, deterministic)
+ *  adaptive_avg_pool : nn.AdaptiveAvgPool2d(bins) with PyTorch's overlapping bins; backward != 0 as for bilinear
+ *  dropout   : nn.Dropout(p) in train mode; the keep mask is a counter-based hash of (seed, element), so the backward is the
+ *              same call on the gradient with the same seed
+ *  add_relu / relu_backward : y = relu(a + b) (relu = 0: plain add; FFM :217-218, residuals :114) and g = dy * [y > 0]
+ *  sgd_step  : torch.optim.SGD(momentum, weight_decay) on flat buffers: g' = grad * grad_scale + wd * p;
+ *              buf = first_step ? g' : momentum * buf + g'; p -= lr * buf */
+int fscnn_train_im2col3x3(const float* d_x, float* d_cols, int n, int c, int h, int w, int stride, int pad, void* stream);
+int fscnn_train_col2im3x3(const float* d_dcols, float* d_dx, int n, int c, int h, int w, int stride, int pad, void* stream);
+int fscnn_train_bias_add(float* d_y, const float* d_bias, int n, int c, int hw, void* stream);
+int fscnn_train_bias_grad(const float* d_dy, float* d_dbias, void* d_ws, size_t ws_bytes, int n, int c, int hw, void* stream);
+int fscnn_train_bilinear(const float* d_in, float* d_out, int planes, int hi, int wi, int ho, int wo, int backward, void* stream);
+int fscnn_train_adaptive_avg_pool(const float* d_in, float* d_out, int planes, int h, int w, int bins, int backward, void* stream);
+int fscnn_train_dropout(const float* d_x, float* d_y, float p, unsigned long long seed, int64_t numel, void* stream);
+int fscnn_train_add_relu(const float* d_a, const float* d_b, float* d_y, int relu, int64_t numel, void* stream);
+int fscnn_train_relu_backward(const float* d_y, const float* d_dy, float* d_dx, int64_t numel, void* stream);
+int fscnn_train_sgd_step(float* d_param, const float* d_grad, float* d_momentum_buf, float lr, float momentum, float weight_decay,
+                         float grad_scale, int first_step, int64_t numel, void* stream);
+
 /* SoftmaxCrossEntropyOHEMLoss.forward (utils/loss.py:143-182) without the host round trip: softmax probability of the target
  * class per valid pixel (d_label int64 [n][hw], label != ignore_label), the min(num_valid, min_kept)-th smallest of them by an
  * exact 4-pass radix select (replaces the host numpy argsort, loss.py:167-169), threshold = max(thresh, that value) unless

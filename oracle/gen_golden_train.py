@@ -30,6 +30,8 @@ def seed_module(m, seed):
             if isinstance(mod, torch.nn.Conv2d):
                 fan_in = mod.weight[0].numel()
                 mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)
+                if mod.bias is not None:
+                    mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.05)
             elif isinstance(mod, torch.nn.BatchNorm2d):
                 mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) * 0.4 + 0.8)
                 mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
@@ -71,8 +73,46 @@ def ohem_case(name, logits, target, use_weight, min_kept=256, thresh=0.7):
     print(name, 'loss', loss.item(), 'kept pixels', int((lg.grad.abs().sum(1) > 0).sum()))
 
 
+def network_case(name, nc, aux, x_shape, seed):
+    """One whole training step of the unmodified reference network (train.py:253-284 without the optimizer): FastSCNN in train
+    mode (BatchNorm batch statistics; Dropout p set to 0 because its mask cannot be reproduced bit for bit), the reference's
+    MixSoftmaxCrossEntropyOHEMLoss with aux weight 0.4, backward.  Per parameter the fixture keeps the gradient's L2 norm, sum and
+    every 13th element; plus the loss, a strided sample of both outputs and the updated BatchNorm buffers."""
+    from models.fast_scnn import FastSCNN
+    from utils.loss import MixSoftmaxCrossEntropyOHEMLoss
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import fastscnn_oracle as fo
+    model = FastSCNN(nc, aux=aux)
+    # recipe-D2 weights from numpy's frozen RandomState streams: the test rebuilds them from the seed (nothing to store)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in fo.make_state_dict(nc, aux, seed).items()})
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.train()
+    x = torch.from_numpy(fo.make_input(x_shape[0], x_shape[2], x_shape[3], seed + 1))
+    target = torch.from_numpy(fo.make_labels(x_shape[0], x_shape[2], x_shape[3], nc, seed + 2))
+    crit = MixSoftmaxCrossEntropyOHEMLoss(aux=aux, aux_weight=0.4, ignore_index=-1)
+    outputs = model(x)
+    loss = crit(outputs, target)
+    loss.backward()
+    out = {'loss': np.float32(loss.item()), 'meta': np.array([nc, int(aux), seed, x_shape[0], x_shape[2], x_shape[3]])}
+    for i, o in enumerate(outputs):
+        out[f'out{i}_sample'] = o.detach().numpy()[:, :, ::5, ::7]
+        out[f'out{i}_absmax'] = np.float32(o.detach().abs().max())
+    for k, v in model.state_dict().items():
+        if 'running' in k or 'num_batches' in k:
+            out['after/' + k] = v.detach().numpy()
+    for k, p in model.named_parameters():
+        gr = p.grad.numpy().ravel()
+        out['gstat/' + k] = np.array([np.sqrt((gr.astype(np.float64) ** 2).sum()), gr.astype(np.float64).sum()], np.float64)
+        out['gsample/' + k] = gr[::13].copy()
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **out)
+    print(name, 'loss', loss.item(), 'params', sum(p.numel() for p in model.parameters()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    network_case('train_net_nc19_aux', 19, True, (2, 3, 96, 128), 21)
     module_case('train_dsconv_32_48_s2', _DSConv(32, 48, 2), (2, 32, 25, 33), 11)
     module_case('train_dsconv_16_16_s1', _DSConv(16, 16, 1), (3, 16, 18, 20), 12)
     module_case('train_bottleneck_16_16_s1', LinearBottleneck(16, 16, 6, 1), (2, 16, 14, 22), 13)

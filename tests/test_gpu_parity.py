@@ -225,8 +225,8 @@ def test_errors_are_loud():
     with pytest.raises(NativeError):
         model(torch.zeros(1, 3, 2, 2, device=DEV))            # too small
     model.train()
-    with pytest.raises(NotImplementedError):
-        model(torch.zeros(1, 3, 64, 64, device=DEV))
+    with pytest.raises(RuntimeError):
+        model.predict(torch.zeros(1, 3, 64, 64, device=DEV))   # training mode runs the training operators; the fused engine is eval only
 
 
 @pytest.mark.parametrize('shape', [(2, 97, 131, 3), (1, 100, 132, 3)])   # row pitch not / is a multiple of 4 bytes
