@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument('--no-fp32', action='store_true', help='skip the short fp32 exactness-path timing')
     ap.add_argument('--no-latency', dest='latency', action='store_false', help='skip the batch-1 CUDA-graph latency')
     ap.add_argument('--only', default='', help="run one auxiliary measurement alone and print its JSON: 'eager'")
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement (BASELINE config 5)')
     ap.add_argument('--no-eager', action='store_true', help='skip the cuDNN-eager comparator on the same GPU')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary workloads (480x640, 360x640)')
     return ap.parse_args()
@@ -211,6 +212,48 @@ def gpu_eager_baseline(dev, h, w, nc, batches=(1, 16), reps=10):
             ms = a.elapsed_time(e) / reps
             res[f'{prec}_b{b}'] = {'images_per_s': b / (ms / 1e3), 'ms_per_step': ms}
         del x
+    # BASELINE config 5 on the same comparator: the reference op sequence in TRAINING mode (batch-statistics BatchNorm, aux head),
+    # F.cross_entropy on both heads (the OHEM pixel selection is left out: it only removes work), backward, torch.optim.SGD;
+    # fp32 and the fp16 autocast + GradScaler the reference actually trains with (train.py:73-74, :267-275)
+    import torch.nn.functional as F
+    try:
+        psd = {k: (v.to(dev).requires_grad_(v.dtype.is_floating_point and 'running' not in k))
+               for k, v in tp.to_torch_state_dict(fo.make_state_dict(nc, True, 7)).items()}
+        params = [v for v in psd.values() if v.requires_grad]
+        opt = torch.optim.SGD(params, lr=1e-2, momentum=0.9, weight_decay=1e-4)
+        fwd = getattr(tp.forward, '__wrapped__', tp.forward)
+        real_bn = tp._bn
+        tp._bn = lambda sd_, p_, t_: F.batch_norm(t_, sd_[p_ + '.running_mean'], sd_[p_ + '.running_var'], sd_[p_ + '.weight'], sd_[p_ + '.bias'],
+                                                  True, 0.1, 1e-5)
+        xt = torch.randn(16, 3, 768, 768, device=dev)
+        tt = torch.randint(-1, nc, (16, 768, 768), device=dev)
+        for prec in ('fp32', 'fp16_autocast'):
+            scaler = torch.amp.GradScaler('cuda', enabled=prec != 'fp32')
+
+            def tstep():
+                opt.zero_grad(set_to_none=True)
+                with torch.enable_grad(), torch.autocast('cuda', dtype=torch.float16, enabled=prec != 'fp32'):
+                    o = fwd(psd, xt, True)
+                    loss = F.cross_entropy(o[0].float(), tt, ignore_index=-1) + 0.4 * F.cross_entropy(o[1].float(), tt, ignore_index=-1)
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+                return loss
+            for _ in range(2):
+                tstep()
+            torch.cuda.synchronize()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                float(tstep())
+            e.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(e) / 3
+            res[f'train_step_{prec}_crop768_b16'] = {'images_per_s': 16 / (ms / 1e3), 'ms_per_step': ms}
+        tp._bn = real_bn
+        del psd, params, opt, xt, tt
+    except Exception as exc:      # the comparator must never take the bench line down
+        res['train_step_error'] = repr(exc)[:200]
     torch.backends.cudnn.benchmark = False
     torch.cuda.empty_cache()
     return res
@@ -461,6 +504,39 @@ def run_native_arm(args):
         del m2, met2, x2, l2, xu2, lu2
         torch.cuda.empty_cache()
 
+    # ---- BASELINE config 5: one training step (forward + backward + OHEM loss + gradient all-reduce + SGD), crop 768, batch 16/GPU ----
+    train = {}
+    if not args.no_train:
+        from fscnn_b200 import Trainer
+        torch.cuda.empty_cache()
+        tb, crop = 16, 768
+        mt = FastSCNN(nc, aux=True).train()
+        init_recipe_d2(mt, 3)
+        mt.to(dev)
+        trainer = Trainer(mt, base_lr=1e-2, aux_weight=0.4)
+        xt = smooth_images(tb, crop, crop, dev, 500 + rank, chunk=16)
+        tt = torch.randint(-1, nc, (tb, crop, crop), device=dev, dtype=torch.int64)
+        l0 = float(trainer.step(xt, tt))
+        trainer.step(xt, tt)
+        barrier()
+        tsteps = 3
+        ev0t, ev1t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0t.record()
+        for _ in range(tsteps):
+            last = trainer.step(xt, tt)
+        l1 = float(last)               # device -> host read of the loss, like the reference's loss.item() (train.py:283)
+        ev1t.record()
+        torch.cuda.synchronize()
+        t_ms = max_over_ranks(ev0t.elapsed_time(ev1t)) / tsteps
+        train = {'workload': f'train_step_nc{nc}_aux_crop{crop}_b{tb}_per_gpu: forward + backward + MixSoftmaxCrossEntropyOHEMLoss + '
+                             'gradient all-reduce + SGD(momentum, weight decay)',
+                 'value': tb * world / (t_ms / 1e3), 'unit': UNIT, 'ms_per_step': t_ms, 'n_gpus': world, 'scaling': 'weak', 'dtype': 'f32',
+                 'loss_first_step': l0, 'loss_after_5_steps': l1,
+                 'note': 'first, parity-checked version of the training path: fp32 CUDA-core kernels (csrc/train.cu), no tensor cores or '
+                         'fusion yet; DDP semantics (per-rank BatchNorm, one NCCL all-reduce of the flat 4.6 MB gradient buffer)'}
+        del trainer, mt, xt, tt
+        torch.cuda.empty_cache()
+
     # ---- the node's host->device ceiling: plain pinned copies of the e2e buffers, all ranks at once ----
     from fscnn_b200 import StreamingEvaluator
     e2e_steps = max(3, args.steps)
@@ -556,6 +632,8 @@ def run_native_arm(args):
     }
     if tus:
         out['tusimple_480x640_b512'] = tus
+    if train:
+        out['training_step'] = train
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
