@@ -80,9 +80,10 @@ dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* _
 }
 
 // dx[n,c,iy,ix] = sum over the taps (ky,kx) with oy*s + ky - 1 == iy, ox*s + kx - 1 == ix of dy[n,c,oy,ox] * w[c,ky,kx]
+template <int STRIDE>
 __global__ void __launch_bounds__(kT)
 dw_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int C, int H, int W, int Ho,
-                   int Wo, int stride, long long total) {
+                   int Wo, long long total) {
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
         const int ix = (int)(i % W), iy = (int)((i / W) % H);
         const long long plane = i / ((long long)W * H);
@@ -93,14 +94,14 @@ dw_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, fl
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int ty = iy + 1 - ky;
-            if (ty < 0 || ty % stride) continue;
-            const int oy = ty / stride;
+            if (ty < 0 || (STRIDE == 2 && (ty & 1))) continue;
+            const int oy = STRIDE == 2 ? ty >> 1 : ty;
             if (oy >= Ho) continue;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int tx = ix + 1 - kx;
-                if (tx < 0 || tx % stride) continue;
-                const int ox = tx / stride;
+                if (tx < 0 || (STRIDE == 2 && (tx & 1))) continue;
+                const int ox = STRIDE == 2 ? tx >> 1 : tx;
                 if (ox < Wo) acc = fmaf(__ldg(dp + (long long)oy * Wo + ox), __ldg(wp + ky * 3 + kx), acc);
             }
         }
@@ -213,6 +214,101 @@ gemm_kernel(GemmArgs g) {
         for (int j = 0; j < 4; ++j) {
             const int jj = j0 + tj * 4 + j;
             if (jj < g.N) C[(long long)m * g.ldc + jj] = acc[i][j];
+        }
+    }
+}
+
+// The forward / data-gradient shape of the same contraction: few output channels (M <= 768), many pixels per image (N = H*W,
+// unit stride in B and C), K = input channels.  64 x 128 tile, K chunks of 16, 256 threads x (4 channels x 8 pixels); the
+// thread's pixels are two groups of 4, 64 apart, so that a warp's 16-byte shared-memory reads are contiguous; the next
+// chunk's global loads are issued before the current chunk is multiplied.
+__global__ void __launch_bounds__(kT)
+gemm_pix_kernel(GemmArgs g) {
+    constexpr int BM = 64, BN = 128, BK = 16;
+    __shared__ __align__(16) float As[BK][BM + 4], Bs[BK][BN + 4];
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+    const float* A = g.A + b * g.sAb;
+    const float* B = g.B + b * g.sBb;
+    const bool vec = ((g.sBk & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    const bool a_k_fast = g.sAk == 1;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float ra[4];
+    float4 rb[2];
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {      // A: 64 x 16
+            const int i = tid + r * kT;
+            const int k = a_k_fast ? i % BK : i / BM, m = a_k_fast ? i / BK : i % BM;
+            ra[r] = (m0 + m < g.M && k0 + k < g.K) ? __ldg(A + (long long)(m0 + m) * g.sAm + (long long)(k0 + k) * g.sAk) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {      // B: 16 x 128 as float4
+            const int i = tid + r * kT, k = i / 32, j = (i % 32) * 4;
+            const float* src = B + (long long)(k0 + k) * g.sBk + j0 + j;
+            if (k0 + k < g.K && vec && j0 + j + 3 < g.N) {
+                rb[r] = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = (k0 + k < g.K && j0 + j + q < g.N) ? __ldg(src + q) : 0.f;
+                rb[r] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = tid + r * kT;
+            const int k = a_k_fast ? i % BK : i / BM, m = a_k_fast ? i / BK : i % BM;
+            As[k][m] = ra[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * kT, k = i / 32, j = (i % 32) * 4;
+            *reinterpret_cast<float4*>(&Bs[k][j]) = rb[r];
+        }
+    };
+    load_tiles(0);
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+        store_tiles();
+        __syncthreads();
+        if (k0 + BK < g.K) load_tiles(k0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* C = g.C + (long long)b * g.sCb;
+    const bool cvec = ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int jj = j0 + h * 64 + tx * 4;
+            float* dst = C + (long long)m * g.ldc + jj;
+            if (cvec && jj + 3 < g.N) {
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (jj + q < g.N) dst[q] = acc[i][4 * h + q];
+            }
         }
     }
 }
@@ -690,9 +786,15 @@ static int splits_for(int channels, long long per_channel) {
     return (int)want;
 }
 
+// split-K partials of the pointwise weight gradient: as many as fill the GPU a few times over, bounded by 32 MB of scratch
+static int pw_parts_max(int cout, int cin) {
+    long long p = (8ll << 20) / ((long long)cout * cin);
+    return (int)(p < 64 ? 64 : (p > 1024 ? 1024 : p));
+}
+
 size_t train_workspace_bytes(int channels_max, int cout, int cin) {
-    // reductions: 64 splits x channels x 9 doubles; pointwise weight gradient: up to 64 split-K partials of [cout][cin] floats
-    return (size_t)64 * channels_max * 9 * sizeof(double) + (size_t)64 * cout * cin * sizeof(float) + 4096;
+    // reductions: 64 splits x channels x 9 doubles; pointwise weight gradient: pw_parts_max split-K partials of [cout][cin] floats
+    return (size_t)64 * channels_max * 9 * sizeof(double) + (size_t)pw_parts_max(cout, cin) * cout * cin * sizeof(float) + 4096;
 }
 
 cudaError_t launch_train_dw_fwd(const float* x, const float* w, float* y, int n, int c, int h, int wd, int stride, cudaStream_t s) {
@@ -707,7 +809,8 @@ cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy,
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
     if (dx) {
         const long long total = (long long)n * c * h * wd;
-        dw_bwd_data_kernel<<<grid_for(total), kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, stride, total);
+        if (stride == 2) dw_bwd_data_kernel<2><<<grid_for(total), kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, total);
+        else dw_bwd_data_kernel<1><<<grid_for(total), kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, total);
     }
     if (dw) {
         const int S = splits_for(c, (long long)n * ho * wo);
@@ -719,7 +822,7 @@ cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy,
 
 cudaError_t launch_train_pw_fwd(const float* x, const float* w, float* y, int n, int cin, int cout, int hw, cudaStream_t s) {
     GemmArgs g{w, x, y, cout, hw, cin, 0, cin, 1, (long long)cin * hw, hw, 1, (long long)cout * hw, hw, 1};
-    gemm_kernel<<<dim3((hw + 63) / 64, (cout + 63) / 64, n), kT, 0, s>>>(g);
+    gemm_pix_kernel<<<dim3((hw + 127) / 128, (cout + 63) / 64, n), kT, 0, s>>>(g);
     return cudaGetLastError();
 }
 
@@ -727,17 +830,18 @@ cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy,
                                 int cout, int hw, cudaStream_t s) {
     if (dx) {      // dx[n] = W^T dy[n]
         GemmArgs g{w, dy, dx, cin, hw, cout, 0, 1, cin, (long long)cout * hw, hw, 1, (long long)cin * hw, hw, 1};
-        gemm_kernel<<<dim3((hw + 63) / 64, (cin + 63) / 64, n), kT, 0, s>>>(g);
+        gemm_pix_kernel<<<dim3((hw + 127) / 128, (cin + 63) / 64, n), kT, 0, s>>>(g);
     }
-    if (dw) {      // dW = sum_n dy[n] x[n]^T, split over the pixels of every image
-        int splitk = (int)((long long)num_sms() * 2 / ((long long)n * ((cin + 63) / 64) * ((cout + 63) / 64)));
+    if (dw) {      // dW = sum_n dy[n] x[n]^T, split over the pixels of every image: enough CTAs to fill the GPU ~4 times
+        const int tiles = ((cin + 63) / 64) * ((cout + 63) / 64), pmax = pw_parts_max(cout, cin);
+        if (n > pmax) return cudaErrorInvalidValue;      // the caller chunks the batch
+        int splitk = (4 * num_sms() + n * tiles - 1) / (n * tiles);
         const int maxk = (hw + 255) / 256;
         if (splitk > maxk) splitk = maxk;
+        if (splitk > pmax / n) splitk = pmax / n;
         if (splitk < 1) splitk = 1;
-        while ((long long)n * splitk > 64) { if (splitk > 1) --splitk; else break; }
         const int parts = n * splitk;
         float* partial = reinterpret_cast<float*>(ws);
-        if (parts > 64) return cudaErrorInvalidValue;      // the caller chunks the batch (train_workspace_bytes holds 64 partials)
         GemmArgs g{dy, x, partial, cout, cin, hw, (long long)cout * hw, hw, 1, (long long)cin * hw, 1, hw, (long long)cout * cin, cin, splitk};
         gemm_kernel<<<dim3((cin + 63) / 64, (cout + 63) / 64, parts), kT, 0, s>>>(g);
         reduce_partials_f_kernel<<<(cout * cin + kT - 1) / kT, kT, 0, s>>>(partial, dw, cout * cin, parts);
