@@ -1,6 +1,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list as a markdown table.
-    python tools/ncu_launch_summary.py launches.csv 'title' 'command' > profiles/xxx_summary.md"""
-import collections, csv, sys
+    python tools/ncu_launch_summary.py launches.csv 'title' 'command' [raw list name] [kernel-name regex to keep] > profiles/xxx_summary.md"""
+import collections, csv, re, sys
+keep = re.compile(sys.argv[5]) if len(sys.argv) > 5 else None
 rows = list(csv.reader(open(sys.argv[1])))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == 'ID')
 hdr = rows[hi]; col = {h: i for i, h in enumerate(hdr)}
@@ -11,6 +12,8 @@ for r in rows[hi + 1:]:
     v = float(r[col['Metric Value']].replace(',', '')); u = r[col['Metric Unit']]
     v = v / 1e3 if u == 'ns' else (v * 1e3 if u == 'ms' else v)
     name = r[col['Kernel Name']]
+    if keep and not keep.search(name):
+        continue
     short = name.split('(')[0].replace('void ', '').replace('fscnn::', '')
     a = agg.setdefault(short, [0, 0.0, r[col['Grid Size']], r[col['Block Size']]])
     a[0] += 1; a[1] += v
