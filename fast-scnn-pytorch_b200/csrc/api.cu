@@ -484,8 +484,13 @@ int64_t fscnn_conf_len(int num_classes) { return (int64_t)(num_classes + 1) * (n
 
 int fscnn_create(fscnn_ctx** out, int num_classes, int aux, int precision) {
     if (!out) return fail(FSCNN_EINVAL, "null output pointer");
-    if (num_classes < 1 || num_classes > 256) return fail(FSCNN_EINVAL, "num_classes %d outside [1, 256]", num_classes);
     if (precision != FSCNN_PREC_FP32 && precision != FSCNN_PREC_BF16) return fail(FSCNN_EINVAL, "unknown precision %d", precision);
+    // capability limits, stated here instead of at the first forward: the x8 upsample stages 960 bytes of shared memory per class
+    // (227 KB: 240 classes), the bf16 head kernel keeps 2 x round_up(nc, 16) accumulator columns next to 256 others in TMEM (128)
+    const int max_nc = precision == FSCNN_PREC_BF16 ? 128 : 240;
+    if (num_classes < 1 || num_classes > max_nc)
+        return fail(FSCNN_EINVAL, "num_classes %d outside [1, %d] for the %s path", num_classes, max_nc,
+                    precision == FSCNN_PREC_BF16 ? "bf16" : "fp32");
     fscnn_ctx* c = new fscnn_ctx();
     c->nc = num_classes;
     c->ncp = (num_classes + 3) & ~3;
@@ -811,6 +816,17 @@ int fscnn_colorize(const void* d_mask, int mask_dtype, int64_t n_pixels, const u
     if ((uintptr_t)d_rgb & 3) return fail(FSCNN_EINVAL, "rgb output must be 4-byte aligned");
     cudaError_t e = launch_colorize(d_mask, mask_dtype, n_pixels, h_palette768, d_rgb, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(FSCNN_ECUDA, "colorize launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_overlay(const unsigned char* d_image, const void* d_mask, int mask_dtype, int64_t n_pixels, const unsigned char* h_palette768,
+                  const unsigned int* h_draw_classes8, double alpha, unsigned char* d_out, void* stream) {
+    if (n_pixels < 0 || !h_palette768 || !h_draw_classes8 || !(alpha >= 0.0 && alpha <= 1.0)) return fail(FSCNN_EINVAL, "bad argument");
+    if (n_pixels == 0) return FSCNN_OK;
+    if (!d_image || !d_mask || !d_out) return fail(FSCNN_EINVAL, "null device pointer");
+    if (!valid_label_dtype(mask_dtype)) return fail(FSCNN_EINVAL, "bad dtype %d", mask_dtype);
+    cudaError_t e = launch_overlay(d_image, d_mask, mask_dtype, n_pixels, h_palette768, h_draw_classes8, alpha, d_out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "overlay launch failed: %s", cudaGetErrorString(e));
     return FSCNN_OK;
 }
 

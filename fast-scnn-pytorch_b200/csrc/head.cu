@@ -1130,4 +1130,41 @@ cudaError_t launch_colorize(const void* mask, int dtype, long long npix, const u
     return cudaGetLastError();
 }
 
+
+// ---- overlay of a class map on the frame it was predicted from (reference demo_tusimple.py:87-104 create_overlay, the host
+//      numpy version: overlay[m] = (1 - alpha) * image[m] + alpha * colour[m], truncated to uint8, for the pixels m of the drawn
+//      classes).  One pass on the device; float64 arithmetic like numpy's so that the truncation lands on the same side. ----
+struct OverlayTab { unsigned char rgb[768]; unsigned int draw[8]; };      // palette + bit c set = class c is drawn
+
+__global__ void __launch_bounds__(kThreads)
+overlay_kernel(const unsigned char* __restrict__ image, const void* __restrict__ mask, int dtype, long long npix, OverlayTab tab,
+               double alpha, unsigned char* __restrict__ out) {
+    __shared__ unsigned char ps[768];
+    __shared__ unsigned int draw[8];
+    for (int i = threadIdx.x; i < 768; i += kThreads) ps[i] = tab.rgb[i];
+    if (threadIdx.x < 8) draw[threadIdx.x] = tab.draw[threadIdx.x];
+    __syncthreads();
+    for (long long q = (long long)blockIdx.x * kThreads + threadIdx.x; q < npix; q += (long long)gridDim.x * kThreads) {
+        const long long v = load_label(mask, dtype, (size_t)q);
+        const bool on = v >= 0 && v < 256 && ((draw[v >> 5] >> (v & 31)) & 1u);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const unsigned char px = image[3 * q + c];
+            out[3 * q + c] = on ? (unsigned char)((1.0 - alpha) * (double)px + alpha * (double)ps[3 * (int)v + c]) : px;
+        }
+    }
+}
+
+cudaError_t launch_overlay(const unsigned char* image, const void* mask, int dtype, long long npix, const unsigned char* palette768,
+                           const unsigned int* draw8, double alpha, unsigned char* out, cudaStream_t s) {
+    if (npix <= 0) return cudaSuccess;
+    OverlayTab tab;
+    for (int i = 0; i < 768; ++i) tab.rgb[i] = palette768[i];
+    for (int i = 0; i < 8; ++i) tab.draw[i] = draw8[i];
+    long long blocks = (npix + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    overlay_kernel<<<(unsigned)blocks, kThreads, 0, s>>>(image, mask, dtype, npix, tab, alpha, out);
+    return cudaGetLastError();
+}
+
 }  // namespace fscnn

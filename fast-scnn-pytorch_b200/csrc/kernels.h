@@ -68,6 +68,10 @@ cudaError_t launch_e2e_postprocess(const float* low, int nc, int ncp, int n, int
 cudaError_t launch_colorize(const void* mask, int dtype, long long npix, const unsigned char* palette768, unsigned char* rgb,
                             cudaStream_t s);
 
+// out = image with the pixels of the drawn classes blended towards their palette colour (demo_tusimple.py:87-104)
+cudaError_t launch_overlay(const unsigned char* image, const void* mask, int dtype, long long npix, const unsigned char* palette768,
+                           const unsigned int* draw8, double alpha, unsigned char* out, cudaStream_t s);
+
 // BN folding + repack (load time).  out_w[k'][co] = w[co][k] * gamma/sqrt(var+eps); with taps > 1 and
 // `tap_major` the k index (ci*taps + tap) is permuted to (tap*cin + ci).  out_b = beta + (cbias - mean)*scale.
 cudaError_t launch_fold(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,

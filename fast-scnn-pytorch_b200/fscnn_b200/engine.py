@@ -234,6 +234,9 @@ class Engine:
         names = self.stage_names()
         last = names.index('cls.dsconv2+head')
         out = torch.empty((n, self.num_classes, out_h, out_w), dtype=torch.float32, device=self.device)
+        probe = native.Tap()      # fscnn_forward_range takes at most one micro-batch: chunk by what the engine plans for this shape
+        native.check(self.lib.fscnn_tap_info(self._ctx, n, h, w, b'cls.logits_lowres', C.byref(probe)), 'fscnn_tap_info')
+        chunk = max(1, min(chunk, probe.n))
         with torch.cuda.device(self.device):
             for i0 in range(0, n, chunk):
                 xs = x[i0:i0 + chunk]

@@ -56,6 +56,7 @@ _SIGNATURES = {
     'fscnn_confusion_from_mask': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p,
                                             C.c_void_p]),
     'fscnn_colorize': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.c_void_p, C.c_void_p]),
+    'fscnn_overlay': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_char_p, C.POINTER(C.c_uint), C.c_double, C.c_void_p, C.c_void_p]),
     'fscnn_e2e_preprocess': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.c_void_p, C.c_void_p]),
     'fscnn_e2e_postprocess': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -37,9 +37,17 @@ class EndToEndPreprocessing(nn.Module):
         if x.device.type != 'cuda':
             raise RuntimeError('the B200 build runs on CUDA tensors only (no CPU fallback)')
         eng = self._backbone[0]._engine(x.device)
-        mean = self.mean.flatten().tolist() if self.mean is not None else None
-        std = self.std.flatten().tolist() if self.std is not None else None
-        return eng.e2e_preprocess(x.detach(), self.base_size, mean, std)
+        return eng.e2e_preprocess(x.detach(), self.base_size, *self._host_norm())
+
+    def _host_norm(self):
+        """mean / std as host lists for the kernel's arguments, read back from the buffers only when they change (a .tolist() per
+        call would synchronise the device on every frame batch)."""
+        if self.mean is None:
+            return None, None
+        key = (self.mean.data_ptr(), self.mean._version, self.std.data_ptr(), self.std._version)
+        if getattr(self, '_norm_cache', (None,))[0] != key:
+            self._norm_cache = (key, self.mean.flatten().tolist(), self.std.flatten().tolist())
+        return self._norm_cache[1], self._norm_cache[2]
 
 
 class EndToEndFastSCNN(nn.Module):

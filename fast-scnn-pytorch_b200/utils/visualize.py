@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ['get_color_pallete', 'colorize', 'palette_for']
+__all__ = ['get_color_pallete', 'colorize', 'overlay', 'palette_for']
 
 _CITYS = (128, 64, 128, 244, 35, 232, 70, 70, 70, 102, 102, 156, 190, 153, 153, 153, 153, 153, 250, 170, 30, 220, 220, 0,
           107, 142, 35, 152, 251, 152, 0, 130, 180, 220, 20, 60, 255, 0, 0, 0, 0, 142, 0, 0, 70, 0, 60, 100, 0, 80, 100,
@@ -71,3 +71,33 @@ def colorize(mask, dataset='citys', out=None):
         native.check(native.lib().fscnn_colorize(mask.data_ptr(), codes[mask.dtype], mask.numel(), pal, rgb.data_ptr(),
                                                  torch.cuda.current_stream().cuda_stream), 'fscnn_colorize')
     return rgb
+
+
+def overlay(image, mask, classes=(1,), colors=None, dataset='tusimple', alpha=0.5, out=None):
+    """Blend the pixels of ``classes`` towards their colour on the frame (reference demo_tusimple.py:87-104 ``create_overlay``:
+    ``overlay[m] = (1 - alpha) * image[m] + alpha * colour``, truncated to uint8), on the device.
+
+    image: CUDA uint8 [...,H,W,3]; mask: CUDA class map [...,H,W] (uint8 / int32 / int64); ``colors``: {class: (r, g, b)} overriding
+    the dataset palette (the reference draws lane class 1 in green: ``overlay(img, mask, classes=(1,), colors={1: (0, 255, 0)})``)."""
+    import ctypes as C
+    import torch
+    from fscnn_b200 import native
+    codes = {torch.uint8: native.U8, torch.int32: native.I32, torch.int64: native.I64}
+    if not (image.is_cuda and mask.is_cuda) or image.dtype != torch.uint8 or mask.dtype not in codes:
+        raise ValueError('overlay expects a CUDA uint8 [...,H,W,3] frame and a CUDA uint8 / int32 / int64 class map')
+    if tuple(image.shape) != tuple(mask.shape) + (3,) or image.device != mask.device:
+        raise ValueError(f'frame {tuple(image.shape)} and class map {tuple(mask.shape)} do not match')
+    image, mask = image.contiguous(), mask.contiguous()
+    pal = palette_for(dataset)
+    for c, rgb in (colors or {}).items():
+        pal[int(c)] = rgb
+    draw = (C.c_uint * 8)()
+    for c in classes:
+        if not 0 <= int(c) < 256:
+            raise ValueError(f'class {c} outside [0, 256)')
+        draw[int(c) >> 5] |= 1 << (int(c) & 31)
+    res = out if out is not None else torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        native.check(native.lib().fscnn_overlay(image.data_ptr(), mask.data_ptr(), codes[mask.dtype], mask.numel(), pal.tobytes(), draw,
+                                                float(alpha), res.data_ptr(), torch.cuda.current_stream().cuda_stream), 'fscnn_overlay')
+    return res

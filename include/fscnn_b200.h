@@ -77,6 +77,7 @@ const char* fscnn_last_error(void);
 
 /* Replaces FastSCNN.__init__ (models/fast_scnn.py:16-31): builds the layer plan for
  * `num_classes` outputs, with or without the aux head.  `precision` is FSCNN_PREC_*. */
+/* num_classes: 1..240 (FSCNN_PREC_FP32) or 1..128 (FSCNN_PREC_BF16); anything else is refused here with a message. */
 int fscnn_create(fscnn_ctx** out, int num_classes, int aux, int precision);
 void fscnn_destroy(fscnn_ctx* ctx);
 
@@ -150,6 +151,13 @@ int fscnn_conf_to_totals(const long long* h_conf, int num_classes, long long* h_
  * 256 x (R,G,B); d_rgb is [n_pixels][3] uint8. */
 int fscnn_colorize(const void* d_mask, int mask_dtype, int64_t n_pixels, const unsigned char* h_palette768,
                    unsigned char* d_rgb, void* stream);
+
+/* Overlay of a class map on the frame it belongs to (the step after the path in demo_tusimple.py:87-104, create_overlay):
+ * d_out[p] = (uint8)((1 - alpha) * d_image[p] + alpha * palette[d_mask[p]]) for the pixels whose class is marked in the 256-bit
+ * set h_draw_classes8 (bit c of word c / 32), d_image[p] elsewhere.  d_image / d_out uint8 [n_pixels][3]; float64 arithmetic and
+ * truncation like the reference's numpy expression; h_palette768 and h_draw_classes8 are HOST memory. */
+int fscnn_overlay(const unsigned char* d_image, const void* d_mask, int mask_dtype, int64_t n_pixels, const unsigned char* h_palette768,
+                  const unsigned int* h_draw_classes8, double alpha, unsigned char* d_out, void* stream);
 
 /* The camera-frame wrapper around the path: replaces EndToEndPreprocessing.forward and the tail of
  * EndToEndFastSCNN.forward (export_onnx_fixed.py:43-60, :78-98).

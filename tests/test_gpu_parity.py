@@ -298,3 +298,25 @@ def test_colorize_kernel():
         m = torch.from_numpy(rng.randint(0, 19, size=(2, 37, 53)).astype(np.int64)).to(dt).to(DEV)
         rgb = colorize(m, 'citys').cpu().numpy()
         assert np.array_equal(rgb, palette_for('citys')[m.cpu().numpy().astype(np.int64)])
+
+
+def test_colorize_and_overlay_against_reference_vectors():
+    """Device palette rendering against the reference's complete tables, and the overlay kernel against create_overlay()
+    (demo_tusimple.py:87-104) run from the unmodified reference source (oracle/gen_golden_visual.py), bit for bit."""
+    import os
+    from conftest import GOLDEN
+    from utils.visualize import colorize, overlay
+    g = np.load(os.path.join(GOLDEN, 'palettes.npz'))
+    m = torch.from_numpy(g['cls_map']).to(DEV)
+    assert np.array_equal(colorize(m, 'citys').cpu().numpy(), g['rgb_citys'])
+    assert np.array_equal(colorize(m.to(torch.uint8), 'tusimple').cpu().numpy(), g['rgb_voc'])
+    allc = torch.arange(256, device=DEV, dtype=torch.int32).view(1, 16, 16)
+    assert np.array_equal(colorize(allc, 'tusimple').cpu().numpy()[0].reshape(256, 3), g['voc'])
+    o = np.load(os.path.join(GOLDEN, 'overlay.npz'))
+    frame = torch.from_numpy(o['frame']).to(DEV)
+    lane = torch.from_numpy(o['lane'].astype(np.uint8)).to(DEV)          # class 1 = lane
+    for alpha in (0.5, 0.3, 0.85):
+        for dt in (torch.uint8, torch.int64):
+            got = overlay(frame, lane.to(dt), classes=(1,), colors={1: (0, 255, 0)}, alpha=alpha).cpu().numpy()
+            assert np.array_equal(got, o[f'overlay_{alpha}']), (alpha, dt)
+    assert torch.equal(overlay(frame, lane, classes=(), alpha=0.5), frame)      # nothing drawn: the frame comes back

@@ -121,6 +121,30 @@ def test_palette_output_matches_reference_tables():
     assert tuple(np.asarray(get_color_pallete(np.array([[1, 2]]), 'tusimple').convert('RGB'))[0, 1]) == (0, 128, 0)
 
 
+def test_palettes_equal_the_reference_tables_entry_for_entry():
+    """The complete colour tables and a get_color_pallete round trip against vectors produced by the unmodified reference
+    (oracle/gen_golden_visual.py)."""
+    from conftest import GOLDEN
+    from utils.visualize import get_color_pallete, palette_for
+    g = np.load(os.path.join(GOLDEN, 'palettes.npz'))
+    assert np.array_equal(palette_for('citys')[:19], g['citys'])
+    assert np.array_equal(palette_for('tusimple'), g['voc']) and np.array_equal(palette_for('pascal_voc'), g['voc'])
+    assert np.array_equal(np.asarray(get_color_pallete(g['cls_map'].copy(), 'citys').convert('RGB')), g['rgb_citys'])
+    assert np.array_equal(np.asarray(get_color_pallete(g['cls_map'].copy(), 'tusimple').convert('RGB')), g['rgb_voc'])
+
+
+def test_create_rejects_unsupported_class_counts_up_front():
+    from fscnn_b200 import native
+    lib = native.lib()
+    ctx = C.c_void_p()
+    assert lib.fscnn_create(C.byref(ctx), 129, 0, native.PREC_BF16) < 0 and b'bf16' in lib.fscnn_last_error()
+    assert lib.fscnn_create(C.byref(ctx), 241, 0, native.PREC_FP32) < 0
+    native.check(lib.fscnn_create(C.byref(ctx), 128, 0, native.PREC_BF16))
+    lib.fscnn_destroy(ctx)
+    native.check(lib.fscnn_create(C.byref(ctx), 240, 0, native.PREC_FP32))
+    lib.fscnn_destroy(ctx)
+
+
 def test_kernel_generation_options_and_e2e_argument_checks():
     """No GPU needed: the option keys of the bf16 kernel generations exist, unknown keys are refused, and the camera-frame
     entry points validate their arguments before touching the device."""
