@@ -180,17 +180,23 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             if (rp_on) {
                 const uint8_t* patch = sm + oRaw + (lt & 1) * kRaw + rp_src;
                 const uint32_t pl = sPl + (lt & 1) * kPlanes;
+                // all fifteen loads first: the stores below are asm volatile with a memory clobber, which the compiler will not
+                // move a load across, so a load -> pack -> store loop pays the shared-memory latency once per row (ncu: 28 % of the
+                // kernel's stall samples sat on the packs waiting for their loads)
+                float v[5][3];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {
-                    float v0, v1, v2;
                     if (FMT == FSCNN_IN_U8_NHWC) {
                         const unsigned char* qp = patch + 7 * k * (kRW * 4);
-                        v0 = (float)qp[0]; v1 = (float)qp[1]; v2 = (float)qp[2];
+                        v[k][0] = (float)qp[0]; v[k][1] = (float)qp[1]; v[k][2] = (float)qp[2];
                     } else {
                         const float* qp = reinterpret_cast<const float*>(patch + 7 * k * (PLD * 4));
-                        v0 = qp[0]; v1 = qp[PR * PLD]; v2 = qp[2 * PR * PLD];
+                        v[k][0] = qp[0]; v[k][1] = qp[PR * PLD]; v[k][2] = qp[2 * PR * PLD];
                     }
-                    const uint32_t lo = packbf(v0, v1), hi = packbf(v2, 1.f);   // X = 1: carries the bias through the MMA
+                }
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const uint32_t lo = packbf(v[k][0], v[k][1]), hi = packbf(v[k][2], 1.f);   // X = 1: carries the bias through the MMA
                     if (rp_r0[k] >= 0) {
                         if (rp_c0 >= 0) sts64(pl + rp_r0[k] + rp_c0, lo, hi);
                         if (rp_c1 >= 0) sts64(pl + rp_r0[k] + rp_c1, lo, hi);
