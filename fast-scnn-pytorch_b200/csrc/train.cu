@@ -474,35 +474,45 @@ ohem_hist_kernel(const float* __restrict__ prob, long long npix, int shift, cons
     if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
 
-// picks the bucket that holds the wanted rank, narrows prefix / rank; after the last pass fixes the threshold
-__global__ void ohem_select_kernel(unsigned long long* __restrict__ state, unsigned int* __restrict__ hist, int shift, int min_kept,
-                                   float thresh) {
-    if (threadIdx.x != 0) return;
-    if (shift == 24) {      // first pass: decide the mode
-        const unsigned long long nv = state[0];
-        state[4] = ((unsigned long long)min_kept >= nv) ? 1ull : 0ull;
-        state[1] = 0ull;
-        const unsigned long long k = nv < (unsigned long long)min_kept ? nv : (unsigned long long)min_kept;
-        state[2] = k > 0 ? k - 1 : 0;      // 0-based rank of the order statistic (loss.py:168)
-        state[3] = (unsigned long long)__float_as_uint(thresh);
-    }
-    unsigned long long rank = state[2];
-    unsigned int prefix = (unsigned int)state[1];
-    for (int b = 0; b < 256; ++b) {
-        const unsigned int cnt = hist[b];
-        hist[b] = 0u;
-        if (rank < cnt) {
-            prefix |= (unsigned int)b << shift;
-            for (int r = b + 1; r < 256; ++r) hist[r] = 0u;
-            break;
+// picks the bucket that holds the wanted rank, narrows prefix / rank; after the last pass fixes the threshold.
+// One CTA of 256 threads: thread b owns bucket b, an inclusive scan over the counts finds the bucket in a few steps.
+__global__ void __launch_bounds__(256)
+ohem_select_kernel(unsigned long long* __restrict__ state, unsigned int* __restrict__ hist, int shift, int min_kept, float thresh) {
+    __shared__ unsigned long long scan[256];
+    __shared__ unsigned long long rank_s;
+    __shared__ unsigned int prefix_s;
+    const int b = threadIdx.x;
+    if (b == 0) {
+        if (shift == 24) {      // first pass: decide the mode
+            const unsigned long long nv = state[0];
+            state[4] = ((unsigned long long)min_kept >= nv) ? 1ull : 0ull;
+            state[1] = 0ull;
+            const unsigned long long k = nv < (unsigned long long)min_kept ? nv : (unsigned long long)min_kept;
+            state[2] = k > 0 ? k - 1 : 0;      // 0-based rank of the order statistic (loss.py:168)
+            state[3] = (unsigned long long)__float_as_uint(thresh);
         }
-        rank -= cnt;
+        rank_s = state[2];
+        prefix_s = (unsigned int)state[1];
     }
-    state[1] = prefix;
-    state[2] = rank;
-    if (shift == 0 && min_kept > 0 && state[0] > 0) {
-        const float kth = __uint_as_float(prefix);
-        if (kth > thresh) state[3] = (unsigned long long)prefix;      // loss.py:170-171
+    const unsigned int cnt = hist[b];
+    hist[b] = 0u;
+    scan[b] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {      // Hillis-Steele inclusive scan
+        const unsigned long long v = b >= o ? scan[b - o] : 0ull;
+        __syncthreads();
+        scan[b] += v;
+        __syncthreads();
+    }
+    const unsigned long long rank = rank_s, incl = scan[b], excl = incl - cnt;
+    if (rank >= excl && rank < incl) {       // exactly one bucket holds the rank (none when there are no valid pixels)
+        const unsigned int prefix = prefix_s | ((unsigned int)b << shift);
+        state[1] = prefix;
+        state[2] = rank - excl;
+        if (shift == 0 && min_kept > 0 && state[0] > 0) {
+            const float kth = __uint_as_float(prefix);
+            if (kth > thresh) state[3] = (unsigned long long)prefix;      // loss.py:170-171
+        }
     }
 }
 
@@ -533,14 +543,17 @@ ohem_loss_kernel(const float* __restrict__ logits, const long long* __restrict__
     if (threadIdx.x == 0) { partial[blockIdx.x * 2] = v[0]; partial[blockIdx.x * 2 + 1] = v[1]; }
 }
 
-// out[0] = loss = sum w*nll / sum w, out[1] = sum w, out[2] = kept-mode threshold (for inspection)
-__global__ void ohem_finalize_kernel(const double* __restrict__ partial, int nblocks, const unsigned long long* __restrict__ state,
-                                     float* __restrict__ out) {
+// out[0] = loss = sum w*nll / sum w, out[1] = sum w, out[2] = kept-mode threshold (for inspection); one CTA sums the partials
+__global__ void __launch_bounds__(kT)
+ohem_finalize_kernel(const double* __restrict__ partial, int nblocks, const unsigned long long* __restrict__ state,
+                     float* __restrict__ out) {
+    __shared__ double sm[2 * 8];
+    double v[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += kT) { v[0] += partial[2 * i]; v[1] += partial[2 * i + 1]; }
+    block_sum<2>(v, sm);
     if (threadIdx.x != 0) return;
-    double a = 0.0, b = 0.0;
-    for (int i = 0; i < nblocks; ++i) { a += partial[2 * i]; b += partial[2 * i + 1]; }
-    out[0] = (float)(a / b);           // 0/0 = NaN when nothing is kept, like torch's mean over an empty selection
-    out[1] = (float)b;
+    out[0] = (float)(v[0] / v[1]);     // 0/0 = NaN when nothing is kept, like torch's mean over an empty selection
+    out[1] = (float)v[1];
     out[2] = __uint_as_float((unsigned int)state[3]);
 }
 
@@ -888,10 +901,10 @@ cudaError_t launch_train_ohem_fwd(const float* logits, const long long* label, c
     ohem_prob_kernel<<<grid, kT, 0, s>>>(logits, label, prob, c, hw, npix, ignore, state);
     for (int shift = 24; shift >= 0; shift -= 8) {
         ohem_hist_kernel<<<grid, kT, 0, s>>>(prob, npix, shift, state, hist);
-        ohem_select_kernel<<<1, 32, 0, s>>>(state, hist, shift, min_kept, thresh);
+        ohem_select_kernel<<<1, 256, 0, s>>>(state, hist, shift, min_kept, thresh);
     }
     ohem_loss_kernel<<<grid, kT, 0, s>>>(logits, label, prob, weight, c, hw, npix, ignore, state, partial);
-    ohem_finalize_kernel<<<1, 32, 0, s>>>(partial, grid, state, out3);
+    ohem_finalize_kernel<<<1, kT, 0, s>>>(partial, grid, state, out3);
     return cudaGetLastError();
 }
 
