@@ -997,6 +997,32 @@ int fscnn_train_ohem_backward(const float* d_logits, const long long* d_label, c
     return FSCNN_OK;
 }
 
+int fscnn_train_ohem_upsampled_forward(const float* d_low_logits, const long long* d_label, const float* d_class_weight, float* d_prob,
+                                       float* d_out3, void* d_ws, size_t ws_bytes, int n, int c, int hl, int wl, int h, int w,
+                                       long long ignore_label, float thresh, int min_kept, void* stream) {
+    if (!d_low_logits || !d_label || !d_prob || !d_out3) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || hl < 1 || wl < 1 || h < 1 || w < 1 || min_kept < 0) return fail(FSCNN_EINVAL, "bad shape");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_ohem_workspace_bytes());
+    if (rc) return rc;
+    cudaError_t e = launch_train_ohem_up_fwd(d_low_logits, d_label, d_class_weight, d_prob, d_out3, d_ws, n, c, hl, wl, h, w, ignore_label,
+                                             thresh, min_kept, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "fused upsample + OHEM forward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_ohem_upsampled_backward(const float* d_low_logits, const long long* d_label, const float* d_class_weight, const float* d_prob,
+                                        const float* d_out3, const float* d_grad_out, float* d_dlow, const void* d_ws, int n, int c, int hl,
+                                        int wl, int h, int w, long long ignore_label, void* stream) {
+    if (!d_low_logits || !d_label || !d_prob || !d_out3 || !d_grad_out || !d_dlow || !d_ws) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || c < 1 || hl < 1 || wl < 1 || h < 1 || w < 1) return fail(FSCNN_EINVAL, "bad shape");
+    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1) || c > 128)
+        return fail(FSCNN_EINVAL, "the fused backward needs an upsampling ratio >= 7 and <= 128 classes (%dx%d -> %dx%d, %d classes)", hl, wl, h, w, c);
+    cudaError_t e = launch_train_ohem_up_bwd(d_low_logits, d_label, d_class_weight, d_prob, d_out3, d_grad_out, d_dlow, d_ws, n, c, hl, wl, h, w,
+                                             ignore_label, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "fused upsample + OHEM backward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
 #define FSCNN_TRAIN_CALL(expr, what)                                                                       \
     do {                                                                                                   \
         cudaError_t e_ = (expr);                                                                           \

@@ -145,6 +145,12 @@ cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float*
 cudaError_t launch_train_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
                                 const float* save_rstd, float* dx, float* dgamma, float* dbeta, void* ws, int n, int c, int hw,
                                 int relu, cudaStream_t s);
+cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, const float* weight, float* prob, float* out3, void* ws,
+                                     int n, int c, int hl, int wl, int h, int w, long long ignore, float thresh, int min_kept,
+                                     cudaStream_t s);
+cudaError_t launch_train_ohem_up_bwd(const float* low, const long long* label, const float* weight, const float* prob, const float* out3,
+                                     const float* gout, float* dlow, const void* ws, int n, int c, int hl, int wl, int h, int w,
+                                     long long ignore, cudaStream_t s);
 cudaError_t launch_train_im2col(const float* x, float* cols, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s);
 cudaError_t launch_train_col2im(const float* dcols, float* dx, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s);
 cudaError_t launch_train_bias_add(float* y, const float* b, int n, int c, int hw, cudaStream_t s);

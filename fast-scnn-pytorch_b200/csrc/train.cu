@@ -587,6 +587,211 @@ ohem_grad_kernel(const float* __restrict__ logits, const long long* __restrict__
     }
 }
 
+// F.interpolate(mode='bilinear', align_corners=True): the arithmetic of the eval path's kernels (SURVEY appendix B)
+__device__ __forceinline__ void ac_coord(int o, float sc, int in, int& i0, int& i1, float& l) {
+    const float f = sc * (float)o;
+    i0 = min((int)f, in - 1);
+    i1 = min(i0 + 1, in - 1);
+    l = f - (float)i0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The loss of a head straight from its LOW-RESOLUTION logits: F.interpolate(x, size, 'bilinear', align_corners=True)
+// (fast_scnn.py:40, :44) composed with the OHEM cross entropy.  The full-resolution logits (16 x 19 x 768 x 768 fp32 = 717 MB per
+// head at BASELINE config 5) and their gradient never exist: every kernel re-interpolates the 19 values of a pixel from the
+// L2-resident low-resolution tensor with exactly bilinear_fwd_kernel's arithmetic, so the selection and the loss are bit-identical
+// to the unfused pair.  The backward scatters d loss / d logit through the resize's transpose: a CTA owns 64 rows x 32 columns of
+// pixels, reduces each class's contribution over the lanes that share a low-resolution column (segmented shuffle), accumulates into
+// a shared-memory tile of the low-resolution gradient and flushes it with float atomics (summation order is not deterministic).
+// ---------------------------------------------------------------------------------------------------------------------
+struct UpGeom { int C, hl, wl, H, W; float scy, scx; };
+
+__device__ __forceinline__ float up_value(const float* __restrict__ base, int wl, int y0, int y1, int x0, int x1, float ly, float lx) {
+    const float top = fmaf(lx, __ldg(base + y0 * wl + x1), (1.f - lx) * __ldg(base + y0 * wl + x0));
+    const float bot = fmaf(lx, __ldg(base + y1 * wl + x1), (1.f - lx) * __ldg(base + y1 * wl + x0));
+    return fmaf(ly, bot, (1.f - ly) * top);
+}
+
+// CT > 0: class count known at compile time -> the pixel's interpolated logits live in registers and are computed once;
+// CT == 0: any class count, the values are re-interpolated in every pass.
+template <int CT>
+struct UpVals {
+    float v[CT > 0 ? CT : 1];
+    __device__ __forceinline__ void load(const float* __restrict__ lp, const UpGeom& g, int y0, int y1, int x0, int x1, float ly, float lx) {
+        if (CT > 0) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) v[c] = up_value(lp + (long long)c * g.hl * g.wl, g.wl, y0, y1, x0, x1, ly, lx);
+        }
+    }
+    __device__ __forceinline__ float get(int c, const float* __restrict__ lp, const UpGeom& g, int y0, int y1, int x0, int x1, float ly,
+                                         float lx) const {
+        return CT > 0 ? v[c] : up_value(lp + (long long)c * g.hl * g.wl, g.wl, y0, y1, x0, x1, ly, lx);
+    }
+};
+#define UP_FOR_CLASSES(c) _Pragma("unroll") for (int c = 0; c < (CT > 0 ? CT : g.C); ++c)
+
+template <int CT>
+__global__ void __launch_bounds__(kT)
+ohem_up_prob_kernel(const float* __restrict__ low, const long long* __restrict__ label, float* __restrict__ prob, UpGeom g, long long npix,
+                    long long ignore, unsigned long long* __restrict__ state) {
+    unsigned int valid = 0;
+    const long long HW = (long long)g.H * g.W;
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long lab = label[i];
+        float out = __uint_as_float(0x7f800000u);
+        if (lab != ignore) {
+            valid += 1;
+            const long long n = i / HW;
+            const int y = (int)((i % HW) / g.W), x = (int)(i % g.W);
+            int y0, y1, x0, x1;
+            float ly, lx;
+            ac_coord(y, g.scy, g.hl, y0, y1, ly);
+            ac_coord(x, g.scx, g.wl, x0, x1, lx);
+            const float* lp = low + n * g.C * g.hl * g.wl;
+            UpVals<CT> u;
+            u.load(lp, g, y0, y1, x0, x1, ly, lx);
+            float mx = -FLT_MAX;
+            UP_FOR_CLASSES(c) mx = fmaxf(mx, u.get(c, lp, g, y0, y1, x0, x1, ly, lx));
+            float sum = 0.f, el = 0.f;
+            UP_FOR_CLASSES(c) {
+                const float e = expf(u.get(c, lp, g, y0, y1, x0, x1, ly, lx) - mx);
+                sum += e;
+                if (c == lab) el = e;
+            }
+            out = el / sum;
+        }
+        prob[i] = out;
+    }
+    valid = (unsigned int)warp_sumf((float)valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(state, (unsigned long long)valid);
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kT)
+ohem_up_loss_kernel(const float* __restrict__ low, const long long* __restrict__ label, const float* __restrict__ prob,
+                    const float* __restrict__ weight, UpGeom g, long long npix, long long ignore,
+                    const unsigned long long* __restrict__ state, double* __restrict__ partial) {
+    __shared__ double sm[2 * 8];
+    const bool keep_all = state[4] != 0ull;
+    const float thr = __uint_as_float((unsigned int)state[3]);
+    const long long HW = (long long)g.H * g.W;
+    double v[2] = {0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long lab = label[i];
+        if (lab == ignore || !(keep_all || prob[i] <= thr)) continue;
+        const long long n = i / HW;
+        const int y = (int)((i % HW) / g.W), x = (int)(i % g.W);
+        int y0, y1, x0, x1;
+        float ly, lx;
+        ac_coord(y, g.scy, g.hl, y0, y1, ly);
+        ac_coord(x, g.scx, g.wl, x0, x1, lx);
+        const float* lp = low + n * g.C * g.hl * g.wl;
+        UpVals<CT> u;
+        u.load(lp, g, y0, y1, x0, x1, ly, lx);
+        float mx = -FLT_MAX;
+        UP_FOR_CLASSES(c) mx = fmaxf(mx, u.get(c, lp, g, y0, y1, x0, x1, ly, lx));
+        float sum = 0.f, vl = 0.f;
+        UP_FOR_CLASSES(c) {
+            const float t = u.get(c, lp, g, y0, y1, x0, x1, ly, lx);
+            sum += expf(t - mx);
+            if (c == lab) vl = t;
+        }
+        const float nll = -((vl - mx) - logf(sum));
+        const float w = weight ? __ldg(weight + lab) : 1.f;
+        v[0] += (double)w * (double)nll;
+        v[1] += (double)w;
+    }
+    block_sum<2>(v, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 2] = v[0]; partial[blockIdx.x * 2 + 1] = v[1]; }
+}
+
+// grid (ceil(W/32), ceil(H/64), N); block 256 = 8 warps; warp w walks rows 8w .. 8w+7 of the tile, lane = column
+constexpr int kUpTR = 12, kUpTC = 8;      // low-resolution rows / columns a 64 x 32 pixel tile can touch at ratios <= 1/7
+template <int CT>
+__global__ void __launch_bounds__(kT)
+ohem_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__ label, const float* __restrict__ prob,
+                    const float* __restrict__ weight, UpGeom g, long long ignore, const unsigned long long* __restrict__ state,
+                    const float* __restrict__ loss_out, const float* __restrict__ gout, float* __restrict__ dlow) {
+    extern __shared__ float acc[];       // [C][kUpTR][kUpTC]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z, yb = blockIdx.y * 64, xb = blockIdx.x * 32;
+    for (int i = tid; i < g.C * kUpTR * kUpTC; i += kT) acc[i] = 0.f;
+    __syncthreads();
+    const bool keep_all = state[4] != 0ull;
+    const float thr = __uint_as_float((unsigned int)state[3]);
+    const float scale = __ldg(gout) / __ldg(loss_out + 1);
+    const int ry0 = min((int)(g.scy * (float)yb), g.hl - 1), rx0 = min((int)(g.scx * (float)xb), g.wl - 1);
+    const float* lp = low + (long long)n * g.C * g.hl * g.wl;
+    const int x = xb + lane;
+    int x0 = 0, x1 = 0;
+    float lx = 0.f;
+    if (x < g.W) ac_coord(x, g.scx, g.wl, x0, x1, lx);
+    // lanes that share x0 are contiguous: segment heads and the lanes each reduction step may add, once per thread
+    const int prev_x0 = __shfl_up_sync(0xffffffffu, x0, 1);
+    const bool head = lane == 0 || prev_x0 != x0;
+    unsigned int same = 0u;            // bit k: lane + 2^k is in this lane's segment
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int ux0 = __shfl_down_sync(0xffffffffu, x0, 1 << k);
+        if (lane + (1 << k) < 32 && ux0 == x0) same |= 1u << k;
+    }
+    for (int rr = 0; rr < 8; ++rr) {
+        const int y = yb + warp * 8 + rr;
+        if (y >= g.H) break;                                   // warp-uniform
+        const long long i = ((long long)n * g.H + y) * g.W + x;
+        long long lab = ignore;
+        bool kept = false;
+        if (x < g.W) {
+            lab = label[i];
+            kept = lab != ignore && (keep_all || prob[i] <= thr);
+        }
+        if (__ballot_sync(0xffffffffu, kept) == 0u) continue;  // nothing kept in this row segment
+        int y0, y1;
+        float ly;
+        ac_coord(y, g.scy, g.hl, y0, y1, ly);
+        UpVals<CT> u;
+        float mx = -FLT_MAX, sum = 1.f;
+        if (kept) {
+            u.load(lp, g, y0, y1, x0, x1, ly, lx);
+            UP_FOR_CLASSES(c) mx = fmaxf(mx, u.get(c, lp, g, y0, y1, x0, x1, ly, lx));
+            sum = 0.f;
+            UP_FOR_CLASSES(c) sum += expf(u.get(c, lp, g, y0, y1, x0, x1, ly, lx) - mx);
+        } else if (CT > 0) {
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : 1); ++c) u.v[c] = 0.f;
+        }
+        const float w = kept ? (weight ? __ldg(weight + lab) : 1.f) * scale : 0.f, inv = 1.f / sum;
+        const int ay0 = (y0 - ry0) * kUpTC, ay1 = (y1 - ry0) * kUpTC, ax0 = x0 - rx0, ax1 = x1 - rx0;
+        UP_FOR_CLASSES(c) {
+            float gc = 0.f;
+            if (kept) gc = w * (expf(u.get(c, lp, g, y0, y1, x0, x1, ly, lx) - mx) * inv - (c == lab ? 1.f : 0.f));
+            float a = gc * (1.f - lx), b = gc * lx;           // towards columns x0 and x1
+            // segmented sum over the lanes that share x0: after the loop the segment head holds the total
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float ua = __shfl_down_sync(0xffffffffu, a, 1 << k), ub = __shfl_down_sync(0xffffffffu, b, 1 << k);
+                if ((same >> k) & 1u) { a += ua; b += ub; }
+            }
+            if (head && x < g.W && (a != 0.f || b != 0.f)) {
+                float* ac = acc + c * kUpTR * kUpTC;
+                atomicAdd(ac + ay0 + ax0, (1.f - ly) * a);
+                atomicAdd(ac + ay0 + ax1, (1.f - ly) * b);
+                atomicAdd(ac + ay1 + ax0, ly * a);
+                atomicAdd(ac + ay1 + ax1, ly * b);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < g.C * kUpTR * kUpTC; i += kT) {
+        const float v = acc[i];
+        if (v != 0.f) {
+            const int c = i / (kUpTR * kUpTC), r = (i / kUpTC) % kUpTR, q = i % kUpTC;
+            const int yy = ry0 + r, xx = rx0 + q;
+            if (yy < g.hl && xx < g.wl) atomicAdd(dlow + (((long long)n * g.C + c) * g.hl + yy) * g.wl + xx, v);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // the rest of the network's training-mode operators: dense 3x3 convolution (stem, aux head) through im2col + the GEMM
 // above, per-channel bias, bilinear resize with align_corners=True, adaptive average pooling (overlapping bins), dropout,
@@ -652,14 +857,6 @@ channel_sum_kernel(const float* __restrict__ dy, double* __restrict__ partial, i
         v[0] += (double)__ldg(dy + ((i / HW) * C + c) * HW + i % HW);
     block_sum<1>(v, sm);
     if (threadIdx.x == 0) partial[(long long)blockIdx.y * C + c] = v[0];
-}
-
-// F.interpolate(mode='bilinear', align_corners=True): the arithmetic of the eval path's kernels (SURVEY appendix B)
-__device__ __forceinline__ void ac_coord(int o, float sc, int in, int& i0, int& i1, float& l) {
-    const float f = sc * (float)o;
-    i0 = min((int)f, in - 1);
-    i1 = min(i0 + 1, in - 1);
-    l = f - (float)i0;
 }
 
 __global__ void __launch_bounds__(kT)
@@ -979,6 +1176,54 @@ cudaError_t launch_train_relu_bwd(const float* y, const float* dy, float* dx, lo
 cudaError_t launch_train_sgd(float* p, const float* g, float* buf, float lr, float momentum, float wd, float gscale, int first,
                              long long total, cudaStream_t s) {
     sgd_kernel<<<grid_for(total), kT, 0, s>>>(p, g, buf, lr, momentum, wd, gscale, first, total);
+    return cudaGetLastError();
+}
+
+
+static UpGeom up_geom(int c, int hl, int wl, int h, int w) {
+    UpGeom g{c, hl, wl, h, w, h > 1 ? (float)(hl - 1) / (float)(h - 1) : 0.f, w > 1 ? (float)(wl - 1) / (float)(w - 1) : 0.f};
+    return g;
+}
+
+cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, const float* weight, float* prob, float* out3, void* ws,
+                                     int n, int c, int hl, int wl, int h, int w, long long ignore, float thresh, int min_kept,
+                                     cudaStream_t s) {
+    const long long npix = (long long)n * h * w;
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(ws);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + 64);
+    double* partial = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 64 + 1024);
+    cudaError_t e = cudaMemsetAsync(ws, 0, 64 + 1024, s);
+    if (e != cudaSuccess) return e;
+    const UpGeom g = up_geom(c, hl, wl, h, w);
+    const int grid = grid_for(npix);
+    if (c == 19) ohem_up_prob_kernel<19><<<grid, kT, 0, s>>>(low, label, prob, g, npix, ignore, state);
+    else if (c == 2) ohem_up_prob_kernel<2><<<grid, kT, 0, s>>>(low, label, prob, g, npix, ignore, state);
+    else ohem_up_prob_kernel<0><<<grid, kT, 0, s>>>(low, label, prob, g, npix, ignore, state);
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        ohem_hist_kernel<<<grid, kT, 0, s>>>(prob, npix, shift, state, hist);
+        ohem_select_kernel<<<1, 256, 0, s>>>(state, hist, shift, min_kept, thresh);
+    }
+    if (c == 19) ohem_up_loss_kernel<19><<<grid, kT, 0, s>>>(low, label, prob, weight, g, npix, ignore, state, partial);
+    else if (c == 2) ohem_up_loss_kernel<2><<<grid, kT, 0, s>>>(low, label, prob, weight, g, npix, ignore, state, partial);
+    else ohem_up_loss_kernel<0><<<grid, kT, 0, s>>>(low, label, prob, weight, g, npix, ignore, state, partial);
+    ohem_finalize_kernel<<<1, kT, 0, s>>>(partial, grid, state, out3);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_ohem_up_bwd(const float* low, const long long* label, const float* weight, const float* prob, const float* out3,
+                                     const float* gout, float* dlow, const void* ws, int n, int c, int hl, int wl, int h, int w,
+                                     long long ignore, cudaStream_t s) {
+    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1)) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)c * kUpTR * kUpTC * sizeof(float);
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(dlow, 0, (size_t)n * c * hl * wl * sizeof(float), s);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((w + 31) / 32, (h + 63) / 64, n);
+    const UpGeom g = up_geom(c, hl, wl, h, w);
+    const unsigned long long* state = reinterpret_cast<const unsigned long long*>(ws);
+    if (c == 19) ohem_up_grad_kernel<19><<<grid, kT, smem, s>>>(low, label, prob, weight, g, ignore, state, out3, gout, dlow);
+    else if (c == 2) ohem_up_grad_kernel<2><<<grid, kT, smem, s>>>(low, label, prob, weight, g, ignore, state, out3, gout, dlow);
+    else ohem_up_grad_kernel<0><<<grid, kT, smem, s>>>(low, label, prob, weight, g, ignore, state, out3, gout, dlow);
     return cudaGetLastError();
 }
 

@@ -200,6 +200,64 @@ class OhemCrossEntropy(torch.autograd.Function):
         return dlogits, None, None, None, None, None
 
 
+class OhemCrossEntropyUpsampled(torch.autograd.Function):
+    """ohem_cross_entropy(bilinear_resize(low, size), target) without materialising the full-resolution logits or their gradient"""
+
+    @staticmethod
+    def forward(ctx, low, target, class_weight, ignore_label, thresh, min_kept):
+        low = _check(low, 'low-resolution logits')
+        if target.dtype != torch.int64 or target.dim() != 3 or not target.is_cuda:
+            raise ValueError('target must be a CUDA int64 [N,H,W] tensor')
+        n, c, hl, wl = low.shape
+        if target.shape[0] != n:
+            raise ValueError(f'target batch {target.shape[0]} does not match logits batch {n}')
+        h, w = int(target.shape[1]), int(target.shape[2])
+        target = target.contiguous()
+        if class_weight is not None:
+            class_weight = _check(class_weight, 'class weight')
+            if class_weight.numel() != c:
+                raise ValueError(f'class weight has {class_weight.numel()} entries for {c} classes')
+        need = C.c_size_t()
+        native.check(native.lib().fscnn_train_ohem_workspace_bytes(C.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=low.device)
+        prob = torch.empty((n, h, w), dtype=torch.float32, device=low.device)
+        out3 = torch.empty(3, dtype=torch.float32, device=low.device)
+        with torch.cuda.device(low.device):
+            native.check(native.lib().fscnn_train_ohem_upsampled_forward(
+                low.data_ptr(), target.data_ptr(), class_weight.data_ptr() if class_weight is not None else None, prob.data_ptr(),
+                out3.data_ptr(), ws.data_ptr(), ws.numel(), n, c, hl, wl, h, w, int(ignore_label), float(thresh), int(min_kept), _stream()),
+                'fscnn_train_ohem_upsampled_forward')
+        ctx.save_for_backward(low, target, prob, out3, ws)
+        ctx.class_weight, ctx.ignore_label = class_weight, int(ignore_label)
+        ctx.mark_non_differentiable(target)
+        return out3[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        low, target, prob, out3, ws = ctx.saved_tensors
+        n, c, hl, wl = low.shape
+        h, w = int(target.shape[1]), int(target.shape[2])
+        dlow = torch.empty_like(low)
+        g = gout.to(torch.float32).reshape(1).contiguous()
+        cw = ctx.class_weight
+        with torch.cuda.device(low.device):
+            native.check(native.lib().fscnn_train_ohem_upsampled_backward(
+                low.data_ptr(), target.data_ptr(), cw.data_ptr() if cw is not None else None, prob.data_ptr(), out3.data_ptr(), g.data_ptr(),
+                dlow.data_ptr(), ws.data_ptr(), n, c, hl, wl, h, w, ctx.ignore_label, _stream()), 'fscnn_train_ohem_upsampled_backward')
+        return dlow, None, None, None, None, None
+
+
+def ohem_cross_entropy_upsampled(low_logits, target, class_weight: Optional[torch.Tensor] = None, ignore_label=-1, thresh=0.7, min_kept=256):
+    """``ohem_cross_entropy(F.interpolate(low_logits, target.shape[1:], 'bilinear', align_corners=True), target, ...)`` fused: what the
+    reference computes with models/fast_scnn.py:40 followed by utils/loss.py:143-182.  Falls back to the two-step form when the
+    upsampling ratio is below 7 or there are more than 128 classes."""
+    n, c, hl, wl = low_logits.shape
+    h, w = target.shape[1], target.shape[2]
+    if (hl - 1) * 7 > h - 1 or (wl - 1) * 7 > w - 1 or c > 128:
+        return ohem_cross_entropy(bilinear_resize(low_logits, (h, w)), target, class_weight, ignore_label, thresh, min_kept)
+    return OhemCrossEntropyUpsampled.apply(low_logits, target, class_weight, ignore_label, thresh, min_kept)
+
+
 def depthwise_conv3x3(x, weight, stride=1):
     return DepthwiseConv3x3.apply(x, weight, int(stride))
 

@@ -33,8 +33,10 @@ def poly_lr(base_lr: float, cur_iter: int, nepochs: int, iters_per_epoch: int, p
 
 class Trainer:
     def __init__(self, model, base_lr=1e-2, momentum=0.9, weight_decay=1e-4, aux_weight=0.4, ignore_label=-1, ohem_thresh=0.7,
-                 ohem_min_kept=256, use_class_weights: Optional[bool] = None, nepochs=160, iters_per_epoch=1000, process_group=None):
+                 ohem_min_kept=256, use_class_weights: Optional[bool] = None, nepochs=160, iters_per_epoch=1000, process_group=None,
+                 fused_loss: bool = True):
         self.model = model
+        self.fused_loss = bool(fused_loss)
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
             raise RuntimeError('move the model to a CUDA device before building the Trainer (there is no CPU path)')
@@ -65,6 +67,16 @@ class Trainer:
         if self.world > 1:      # every rank starts from rank 0's weights
             dist.broadcast(self.flat_param, src=0, group=process_group)
 
+    def loss_from_lowres(self, lowres_outputs, target):
+        """The same loss from the heads' LOW-RESOLUTION logits: the final x8 bilinear resize (models/fast_scnn.py:40, :44) is fused
+        into the OHEM kernels (train_ops.ohem_cross_entropy_upsampled)."""
+        total = train_ops.ohem_cross_entropy_upsampled(lowres_outputs[0], target, self.class_weight, self.ignore_label, self.ohem_thresh,
+                                                       self.ohem_min_kept)
+        for aux_out in lowres_outputs[1:]:
+            total = total + self.aux_weight * train_ops.ohem_cross_entropy_upsampled(aux_out, target, self.class_weight, self.ignore_label,
+                                                                                      self.ohem_thresh, self.ohem_min_kept)
+        return total
+
     def loss(self, outputs, target):
         """MixSoftmaxCrossEntropyOHEMLoss.forward (utils/loss.py:191-206)."""
         total = train_ops.ohem_cross_entropy(outputs[0], target, self.class_weight, self.ignore_label, self.ohem_thresh, self.ohem_min_kept)
@@ -83,7 +95,10 @@ class Trainer:
         for p in self.params:      # autograd accumulates into the flat-buffer views
             if p.grad is None:
                 raise RuntimeError('a parameter lost its flat gradient view (zero_grad(set_to_none=True) was called on the model?)')
-        loss = self.loss(self.model(images), target)
+        if self.fused_loss and hasattr(self.model, '_train_forward_lowres'):
+            loss = self.loss_from_lowres(self.model._train_forward_lowres(images), target)
+        else:
+            loss = self.loss(self.model(images), target)
         loss.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)

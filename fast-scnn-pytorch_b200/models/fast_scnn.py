@@ -359,13 +359,21 @@ class FastSCNN(nn.Module):
         if not x.is_cuda:
             raise RuntimeError(f'FastSCNN (B200 build) runs on CUDA devices only, got a tensor on {x.device} (there is no CPU fallback)')
         size = x.shape[2:]
+        return tuple(train_ops.bilinear_resize(t, size) for t in self._train_forward_lowres(x))
+
+    def _train_forward_lowres(self, x):
+        """The training forward up to the heads' low-resolution logits (1/8 scale), before the final x8 resize of :40 / :44.
+        ``fscnn_b200.Trainer`` feeds these to the fused upsample + OHEM loss, so the full-resolution logits are never stored."""
+        if x.dim() != 4 or x.size(1) != 3 or x.dtype != torch.float32:
+            raise ValueError(f'training forward expects a float32 [N,3,H,W] batch, got {x.dtype} {tuple(x.shape)}')
+        if not x.is_cuda:
+            raise RuntimeError(f'FastSCNN (B200 build) runs on CUDA devices only, got a tensor on {x.device} (there is no CPU fallback)')
         higher = self.learning_to_downsample(x)
         t = self.global_feature_extractor(higher)
         t = self.feature_fusion(higher, t)
-        t = self.classifier(t)
-        outputs = [train_ops.bilinear_resize(t, size)]
+        outputs = [self.classifier(t)]
         if self.aux:
-            outputs.append(train_ops.bilinear_resize(_train_seq(self.auxlayer, higher), size))
+            outputs.append(_train_seq(self.auxlayer, higher))
         return tuple(outputs)
 
     # ---- fused fast paths (additions) ------------------------------------------------------------
