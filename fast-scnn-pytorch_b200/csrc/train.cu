@@ -218,6 +218,89 @@ gemm_kernel(GemmArgs g) {
     }
 }
 
+// The weight-gradient shape: a small output (M = cout, N = cin) and a very long K (the pixels of an image slice), both operands
+// with unit stride along K.  64 x 64 tile, K chunks of 32 read as float4 along K (128 contiguous bytes per row) and prefetched into
+// registers while the previous chunk is multiplied; `splitk` CTAs along grid.z share one image's pixels.
+__global__ void __launch_bounds__(kT)
+gemm_wgrad_kernel(GemmArgs g) {
+    constexpr int BM = 64, BN = 64, BK = 32;
+    __shared__ __align__(16) float As[BK][BM + 4], Bs[BK][BN + 4];
+    const int b = blockIdx.z / g.splitk, sk = blockIdx.z % g.splitk;
+    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, tm = tid / 16, tj = tid % 16;
+    const float* A = g.A + b * g.sAb;
+    const float* B = g.B + b * g.sBb;
+    const int kper = ((g.K + g.splitk - 1) / g.splitk + BK - 1) / BK * BK;
+    const int k_begin = sk * kper, k_end = min(g.K, k_begin + kper);
+    const bool avec = ((g.sAm & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool bvec = ((g.sBj & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 ra[2], rb[2];
+    auto load4 = [&](const float* base, long long row_stride, int row, int row_limit, int k, bool vec) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < row_limit) {
+            const float* src = base + (long long)row * row_stride + k;
+            if (vec && k + 3 < k_end) {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = k + q < k_end ? __ldg(src + q) : 0.f;
+                v = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        return v;
+    };
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {      // 64 rows x 8 float4 per operand
+            const int i = tid + r * kT, row = i / 8, k4 = (i % 8) * 4;
+            ra[r] = load4(A, g.sAm, m0 + row, g.M, k0 + k4, avec && ((k0 + k4) & 3) == 0);
+            rb[r] = load4(B, g.sBj, j0 + row, g.N, k0 + k4, bvec && ((k0 + k4) & 3) == 0);
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * kT, row = i / 8, k4 = (i % 8) * 4;
+            As[k4][row] = ra[r].x; As[k4 + 1][row] = ra[r].y; As[k4 + 2][row] = ra[r].z; As[k4 + 3][row] = ra[r].w;
+            Bs[k4][row] = rb[r].x; Bs[k4 + 1][row] = rb[r].y; Bs[k4 + 2][row] = rb[r].z; Bs[k4 + 3][row] = rb[r].w;
+        }
+    };
+    if (k_begin < k_end) load_tiles(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        store_tiles();
+        __syncthreads();
+        if (k0 + BK < k_end) load_tiles(k0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
+            const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tj * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* C = g.C + (long long)blockIdx.z * g.sCb;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + tm * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jj = j0 + tj * 4 + j;
+            if (jj < g.N) C[(long long)m * g.ldc + jj] = acc[i][j];
+        }
+    }
+}
+
 // The forward / data-gradient shape of the same contraction: few output channels (M <= 768), many pixels per image (N = H*W,
 // unit stride in B and C), K = input channels.  64 x 128 tile, K chunks of 16, 256 threads x (4 channels x 8 pixels); the
 // thread's pixels are two groups of 4, 64 apart, so that a warp's 16-byte shared-memory reads are contiguous; the next
@@ -1053,7 +1136,7 @@ cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy,
         const int parts = n * splitk;
         float* partial = reinterpret_cast<float*>(ws);
         GemmArgs g{dy, x, partial, cout, cin, hw, (long long)cout * hw, hw, 1, (long long)cin * hw, 1, hw, (long long)cout * cin, cin, splitk};
-        gemm_kernel<<<dim3((cin + 63) / 64, (cout + 63) / 64, parts), kT, 0, s>>>(g);
+        gemm_wgrad_kernel<<<dim3((cin + 63) / 64, (cout + 63) / 64, parts), kT, 0, s>>>(g);
         reduce_partials_f_kernel<<<(cout * cin + kT - 1) / kT, kT, 0, s>>>(partial, dw, cout * cin, parts);
     }
     return cudaGetLastError();
