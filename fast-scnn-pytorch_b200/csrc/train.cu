@@ -876,6 +876,257 @@ ohem_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Strip form of the three kernels above for a class count known at compile time (2 / 19).  A warp owns 32 adjacent output columns
+// and walks kStripRows rows of them; a thread (one column) keeps, per class, the two horizontally interpolated low-resolution rows
+// its column sits between (top / bot: the inner two fmaf of up_value, refreshed only when the row pair changes, every ~8 rows at
+// ratio 1/8), so a pixel costs one vertical fmaf per class instead of four loads and three interpolations: the values are
+// bit-identical to up_value.  The backward accumulates a thread's gradient per class and low-resolution row in registers while the
+// row pair stays the same, then reduces over the lanes that share a low-resolution column (segmented shuffle) and adds the four
+// corner sums straight into dlow (red.global.add.f32; summation order is not deterministic): no shared memory, ~8x fewer
+// reductions and atomics than one per row.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kStripRows = 32;
+
+template <int CT>
+struct UpRows {
+    float top[CT], bot[CT];
+    int y0, y1;
+    __device__ __forceinline__ void fetch(float (&dst)[CT], const float* __restrict__ lp, const UpGeom& g, int yy, int x0, int x1, float lx) {
+        const float* r = lp + yy * g.wl;
+        const int plane = g.hl * g.wl;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) dst[c] = fmaf(lx, __ldg(r + c * plane + x1), (1.f - lx) * __ldg(r + c * plane + x0));
+    }
+    // (ny0, ny1) is warp-uniform
+    __device__ __forceinline__ void advance(const float* __restrict__ lp, const UpGeom& g, int ny0, int ny1, int x0, int x1, float lx) {
+        if (ny0 == y0 && ny1 == y1) return;
+        if (ny0 == y1) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) top[c] = bot[c];
+        } else {
+            fetch(top, lp, g, ny0, x0, x1, lx);
+        }
+        if (ny1 == ny0) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) bot[c] = top[c];
+        } else {
+            fetch(bot, lp, g, ny1, x0, x1, lx);
+        }
+        y0 = ny0; y1 = ny1;
+    }
+    __device__ __forceinline__ float value(int c, float ly) const { return fmaf(ly, bot[c], (1.f - ly) * top[c]); }
+};
+
+struct StripIter {          // strips ordered (image, row block, column strip): neighbouring warps share low-resolution rows
+    int CS, RB;
+    long long total;
+    __device__ __forceinline__ StripIter(const UpGeom& g, int n) : CS((g.W + 31) / 32), RB((g.H + kStripRows - 1) / kStripRows) {
+        total = (long long)n * RB * CS;
+    }
+    __device__ __forceinline__ void at(long long s, int& n, int& yb, int& xb) const {
+        xb = (int)(s % CS) * 32;
+        yb = (int)((s / CS) % RB) * kStripRows;
+        n = (int)(s / ((long long)CS * RB));
+    }
+};
+
+template <int CT>
+__global__ void __launch_bounds__(kT)
+ohem_strip_prob_kernel(const float* __restrict__ low, const long long* __restrict__ label, float* __restrict__ prob, UpGeom g, int nimg,
+                       long long ignore, unsigned long long* __restrict__ state) {
+    const int lane = threadIdx.x & 31;
+    const StripIter it(g, nimg);
+    unsigned int valid = 0;
+    for (long long s = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); s < it.total; s += (long long)gridDim.x * (kT / 32)) {
+        int n, yb, xb;
+        it.at(s, n, yb, xb);
+        const int x = xb + lane;
+        int x0, x1;
+        float lx;
+        ac_coord(min(x, g.W - 1), g.scx, g.wl, x0, x1, lx);
+        const float* lp = low + (long long)n * CT * g.hl * g.wl;
+        UpRows<CT> rows;
+        rows.y0 = rows.y1 = -1;
+        const int yend = min(g.H, yb + kStripRows);
+        for (int y = yb; y < yend; ++y) {
+            int y0, y1;
+            float ly;
+            ac_coord(y, g.scy, g.hl, y0, y1, ly);
+            rows.advance(lp, g, y0, y1, x0, x1, lx);
+            if (x >= g.W) continue;
+            const long long i = ((long long)n * g.H + y) * g.W + x;
+            const long long lab = label[i];
+            float out = __uint_as_float(0x7f800000u);
+            if (lab != ignore) {
+                valid += 1;
+                float v[CT], mx = -FLT_MAX;
+#pragma unroll
+                for (int c = 0; c < CT; ++c) { v[c] = rows.value(c, ly); mx = fmaxf(mx, v[c]); }
+                float sum = 0.f, el = 0.f;
+#pragma unroll
+                for (int c = 0; c < CT; ++c) {
+                    const float e = expf(v[c] - mx);
+                    sum += e;
+                    if (c == lab) el = e;
+                }
+                out = el / sum;
+            }
+            prob[i] = out;
+        }
+    }
+    valid = (unsigned int)warp_sumf((float)valid);
+    if (lane == 0 && valid) atomicAdd(state, (unsigned long long)valid);
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kT)
+ohem_strip_loss_kernel(const float* __restrict__ low, const long long* __restrict__ label, const float* __restrict__ prob,
+                       const float* __restrict__ weight, UpGeom g, int nimg, long long ignore,
+                       const unsigned long long* __restrict__ state, double* __restrict__ partial) {
+    __shared__ double sm[2 * 8];
+    const int lane = threadIdx.x & 31;
+    const bool keep_all = state[4] != 0ull;
+    const float thr = __uint_as_float((unsigned int)state[3]);
+    const StripIter it(g, nimg);
+    double acc[2] = {0.0, 0.0};
+    for (long long s = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); s < it.total; s += (long long)gridDim.x * (kT / 32)) {
+        int n, yb, xb;
+        it.at(s, n, yb, xb);
+        const int x = xb + lane;
+        int x0, x1;
+        float lx;
+        ac_coord(min(x, g.W - 1), g.scx, g.wl, x0, x1, lx);
+        const float* lp = low + (long long)n * CT * g.hl * g.wl;
+        UpRows<CT> rows;
+        rows.y0 = rows.y1 = -1;
+        const int yend = min(g.H, yb + kStripRows);
+        for (int y = yb; y < yend; ++y) {
+            const long long i = ((long long)n * g.H + y) * g.W + x;
+            long long lab = ignore;
+            bool kept = false;
+            if (x < g.W) {
+                lab = label[i];
+                kept = lab != ignore && (keep_all || prob[i] <= thr);
+            }
+            if (__ballot_sync(0xffffffffu, kept) == 0u) continue;
+            int y0, y1;
+            float ly;
+            ac_coord(y, g.scy, g.hl, y0, y1, ly);
+            rows.advance(lp, g, y0, y1, x0, x1, lx);
+            if (!kept) continue;
+            float v[CT], mx = -FLT_MAX;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) { v[c] = rows.value(c, ly); mx = fmaxf(mx, v[c]); }
+            float sum = 0.f, vl = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                sum += expf(v[c] - mx);
+                if (c == lab) vl = v[c];
+            }
+            const float nll = -((vl - mx) - logf(sum));
+            const float w = weight ? __ldg(weight + lab) : 1.f;
+            acc[0] += (double)w * (double)nll;
+            acc[1] += (double)w;
+        }
+    }
+    block_sum<2>(acc, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 2] = acc[0]; partial[blockIdx.x * 2 + 1] = acc[1]; }
+}
+
+template <int CT>
+__global__ void __launch_bounds__(kT)
+ohem_strip_grad_kernel(const float* __restrict__ low, const long long* __restrict__ label, const float* __restrict__ prob,
+                       const float* __restrict__ weight, UpGeom g, int nimg, long long ignore,
+                       const unsigned long long* __restrict__ state, const float* __restrict__ loss_out, const float* __restrict__ gout,
+                       float* __restrict__ dlow) {
+    const int lane = threadIdx.x & 31;
+    const bool keep_all = state[4] != 0ull;
+    const float thr = __uint_as_float((unsigned int)state[3]);
+    const float scale = __ldg(gout) / __ldg(loss_out + 1);
+    const StripIter it(g, nimg);
+    const int plane = g.hl * g.wl;
+    for (long long s = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); s < it.total; s += (long long)gridDim.x * (kT / 32)) {
+        int n, yb, xb;
+        it.at(s, n, yb, xb);
+        const int x = xb + lane;
+        int x0, x1;
+        float lx;
+        ac_coord(min(x, g.W - 1), g.scx, g.wl, x0, x1, lx);
+        // lanes that share x0 are contiguous: segment heads and the lanes each reduction step may add
+        const int prev_x0 = __shfl_up_sync(0xffffffffu, x0, 1);
+        const bool head = lane == 0 || prev_x0 != x0;
+        unsigned int same = 0u;            // bit k: lane + 2^k is in this lane's segment
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int ux0 = __shfl_down_sync(0xffffffffu, x0, 1 << k);
+            if (lane + (1 << k) < 32 && ux0 == x0) same |= 1u << k;
+        }
+        const float* lp = low + (long long)n * CT * plane;
+        float* dp = dlow + (long long)n * CT * plane;
+        UpRows<CT> rows;
+        rows.y0 = rows.y1 = -1;
+        float a0[CT], a1[CT];              // gradient towards rows y0 / y1 of this thread's column, all classes
+#pragma unroll
+        for (int c = 0; c < CT; ++c) a0[c] = a1[c] = 0.f;
+        bool dirty = false;                // warp-uniform: something was accumulated since the last flush
+        auto flush = [&]() {
+            const float hx = 1.f - lx;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                float p = a0[c] * hx, q = a0[c] * lx, r = a1[c] * hx, t = a1[c] * lx;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float up = __shfl_down_sync(0xffffffffu, p, 1 << k), uq = __shfl_down_sync(0xffffffffu, q, 1 << k);
+                    const float ur = __shfl_down_sync(0xffffffffu, r, 1 << k), ut = __shfl_down_sync(0xffffffffu, t, 1 << k);
+                    if ((same >> k) & 1u) { p += up; q += uq; r += ur; t += ut; }
+                }
+                if (head) {
+                    float* d0 = dp + c * plane + rows.y0 * g.wl;
+                    float* d1 = dp + c * plane + rows.y1 * g.wl;
+                    if (p != 0.f) atomicAdd(d0 + x0, p);
+                    if (q != 0.f) atomicAdd(d0 + x1, q);
+                    if (r != 0.f) atomicAdd(d1 + x0, r);
+                    if (t != 0.f) atomicAdd(d1 + x1, t);
+                }
+                a0[c] = a1[c] = 0.f;
+            }
+        };
+        const int yend = min(g.H, yb + kStripRows);
+        for (int y = yb; y < yend; ++y) {
+            const long long i = ((long long)n * g.H + y) * g.W + x;
+            long long lab = ignore;
+            bool kept = false;
+            if (x < g.W) {
+                lab = label[i];
+                kept = lab != ignore && (keep_all || prob[i] <= thr);
+            }
+            if (__ballot_sync(0xffffffffu, kept) == 0u) continue;
+            int y0, y1;
+            float ly;
+            ac_coord(y, g.scy, g.hl, y0, y1, ly);
+            if (dirty && (y0 != rows.y0 || y1 != rows.y1)) { flush(); dirty = false; }
+            rows.advance(lp, g, y0, y1, x0, x1, lx);
+            dirty = true;
+            if (!kept) continue;
+            float v[CT], mx = -FLT_MAX;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) { v[c] = rows.value(c, ly); mx = fmaxf(mx, v[c]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) { v[c] = expf(v[c] - mx); sum += v[c]; }
+            const float w = (weight ? __ldg(weight + lab) : 1.f) * scale, inv = 1.f / sum, hy = 1.f - ly;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const float gc = w * (v[c] * inv - (c == lab ? 1.f : 0.f));
+                a0[c] = fmaf(hy, gc, a0[c]);
+                a1[c] = fmaf(ly, gc, a1[c]);
+            }
+        }
+        if (dirty) flush();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // the rest of the network's training-mode operators: dense 3x3 convolution (stem, aux head) through im2col + the GEMM
 // above, per-channel bias, bilinear resize with align_corners=True, adaptive average pooling (overlapping bins), dropout,
 // add + ReLU, and the SGD update
@@ -1263,6 +1514,14 @@ cudaError_t launch_train_sgd(float* p, const float* g, float* buf, float lr, flo
 }
 
 
+// CTAs of 8 warps over the (image, row block, column strip) strips of the strip kernels, capped like grid_for (the loss kernel writes
+// one partial pair per CTA into the num_sms * 16 slots of train_ohem_workspace_bytes)
+static int strip_grid(int n, int h, int w) {
+    const long long strips = (long long)n * ((h + kStripRows - 1) / kStripRows) * ((w + 31) / 32);
+    const long long ctas = (strips + kT / 32 - 1) / (kT / 32), cap = (long long)num_sms() * 16;
+    return (int)(ctas < cap ? (ctas > 0 ? ctas : 1) : cap);
+}
+
 static UpGeom up_geom(int c, int hl, int wl, int h, int w) {
     UpGeom g{c, hl, wl, h, w, h > 1 ? (float)(hl - 1) / (float)(h - 1) : 0.f, w > 1 ? (float)(wl - 1) / (float)(w - 1) : 0.f};
     return g;
@@ -1278,34 +1537,37 @@ cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, c
     cudaError_t e = cudaMemsetAsync(ws, 0, 64 + 1024, s);
     if (e != cudaSuccess) return e;
     const UpGeom g = up_geom(c, hl, wl, h, w);
-    const int grid = grid_for(npix);
-    if (c == 19) ohem_up_prob_kernel<19><<<grid, kT, 0, s>>>(low, label, prob, g, npix, ignore, state);
-    else if (c == 2) ohem_up_prob_kernel<2><<<grid, kT, 0, s>>>(low, label, prob, g, npix, ignore, state);
+    const int grid = grid_for(npix), sgrid = strip_grid(n, h, w);
+    if (c == 19) ohem_strip_prob_kernel<19><<<sgrid, kT, 0, s>>>(low, label, prob, g, n, ignore, state);
+    else if (c == 2) ohem_strip_prob_kernel<2><<<sgrid, kT, 0, s>>>(low, label, prob, g, n, ignore, state);
     else ohem_up_prob_kernel<0><<<grid, kT, 0, s>>>(low, label, prob, g, npix, ignore, state);
     for (int shift = 24; shift >= 0; shift -= 8) {
         ohem_hist_kernel<<<grid, kT, 0, s>>>(prob, npix, shift, state, hist);
         ohem_select_kernel<<<1, 256, 0, s>>>(state, hist, shift, min_kept, thresh);
     }
-    if (c == 19) ohem_up_loss_kernel<19><<<grid, kT, 0, s>>>(low, label, prob, weight, g, npix, ignore, state, partial);
-    else if (c == 2) ohem_up_loss_kernel<2><<<grid, kT, 0, s>>>(low, label, prob, weight, g, npix, ignore, state, partial);
+    const bool strip = c == 19 || c == 2;
+    if (c == 19) ohem_strip_loss_kernel<19><<<sgrid, kT, 0, s>>>(low, label, prob, weight, g, n, ignore, state, partial);
+    else if (c == 2) ohem_strip_loss_kernel<2><<<sgrid, kT, 0, s>>>(low, label, prob, weight, g, n, ignore, state, partial);
     else ohem_up_loss_kernel<0><<<grid, kT, 0, s>>>(low, label, prob, weight, g, npix, ignore, state, partial);
-    ohem_finalize_kernel<<<1, kT, 0, s>>>(partial, grid, state, out3);
+    ohem_finalize_kernel<<<1, kT, 0, s>>>(partial, strip ? sgrid : grid, state, out3);
     return cudaGetLastError();
 }
 
 cudaError_t launch_train_ohem_up_bwd(const float* low, const long long* label, const float* weight, const float* prob, const float* out3,
                                      const float* gout, float* dlow, const void* ws, int n, int c, int hl, int wl, int h, int w,
                                      long long ignore, cudaStream_t s) {
-    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1)) return cudaErrorInvalidValue;
+    const bool strip = c == 19 || c == 2;
     const size_t smem = (size_t)c * kUpTR * kUpTC * sizeof(float);
-    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    if (!strip && ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1) || smem > 48 * 1024))
+        return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(dlow, 0, (size_t)n * c * hl * wl * sizeof(float), s);
     if (e != cudaSuccess) return e;
     const dim3 grid((w + 31) / 32, (h + 63) / 64, n);
+    const int sgrid = strip_grid(n, h, w);
     const UpGeom g = up_geom(c, hl, wl, h, w);
     const unsigned long long* state = reinterpret_cast<const unsigned long long*>(ws);
-    if (c == 19) ohem_up_grad_kernel<19><<<grid, kT, smem, s>>>(low, label, prob, weight, g, ignore, state, out3, gout, dlow);
-    else if (c == 2) ohem_up_grad_kernel<2><<<grid, kT, smem, s>>>(low, label, prob, weight, g, ignore, state, out3, gout, dlow);
+    if (c == 19) ohem_strip_grad_kernel<19><<<sgrid, kT, 0, s>>>(low, label, prob, weight, g, n, ignore, state, out3, gout, dlow);
+    else if (c == 2) ohem_strip_grad_kernel<2><<<sgrid, kT, 0, s>>>(low, label, prob, weight, g, n, ignore, state, out3, gout, dlow);
     else ohem_up_grad_kernel<0><<<grid, kT, smem, s>>>(low, label, prob, weight, g, ignore, state, out3, gout, dlow);
     return cudaGetLastError();
 }
