@@ -953,15 +953,15 @@ int fscnn_train_batchnorm_forward(const float* d_x, const float* d_gamma, const 
     return FSCNN_OK;
 }
 
-int fscnn_train_batchnorm_backward(const float* d_x, const float* d_y, const float* d_dy, const float* d_gamma, const float* d_save_mean,
+int fscnn_train_batchnorm_backward(const float* d_x, const float* d_dy, const float* d_gamma, const float* d_beta, const float* d_save_mean,
                                    const float* d_save_rstd, float* d_dx, float* d_dgamma, float* d_dbeta, void* d_ws, size_t ws_bytes,
                                    int n, int c, int hw, int relu, void* stream) {
-    if (!d_x || !d_dy || !d_gamma || !d_save_mean || !d_save_rstd || !d_dx || !d_dgamma || !d_dbeta || (relu && !d_y))
+    if (!d_x || !d_dy || !d_gamma || !d_save_mean || !d_save_rstd || !d_dx || !d_dgamma || !d_dbeta || (relu && !d_beta))
         return fail(FSCNN_EINVAL, "null device pointer");
     if (n < 1 || c < 1 || hw < 1) return fail(FSCNN_EINVAL, "bad shape");
     int rc = train_ws_ok(d_ws, ws_bytes, train_workspace_bytes(c, 1, 1));
     if (rc) return rc;
-    cudaError_t e = launch_train_bn_bwd(d_x, d_y, d_dy, d_gamma, d_save_mean, d_save_rstd, d_dx, d_dgamma, d_dbeta, d_ws, n, c, hw, relu,
+    cudaError_t e = launch_train_bn_bwd(d_x, d_dy, d_gamma, d_beta, d_save_mean, d_save_rstd, d_dx, d_dgamma, d_dbeta, d_ws, n, c, hw, relu,
                                         (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(FSCNN_ECUDA, "batchnorm backward launch failed: %s", cudaGetErrorString(e));
     return FSCNN_OK;

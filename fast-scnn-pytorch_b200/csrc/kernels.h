@@ -142,7 +142,7 @@ cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy,
 cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                 float* y, float* save_mean, float* save_rstd, void* ws, int n, int c, int hw, float eps,
                                 float momentum, int relu, cudaStream_t s);
-cudaError_t launch_train_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+cudaError_t launch_train_bn_bwd(const float* x, const float* dy, const float* gamma, const float* beta, const float* save_mean,
                                 const float* save_rstd, float* dx, float* dgamma, float* dbeta, void* ws, int n, int c, int hw,
                                 int relu, cudaStream_t s);
 cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, const float* weight, float* prob, float* out3, void* ws,

@@ -13,6 +13,7 @@
 // torch.autograd of the unmodified reference modules); the tensor-core / fused versions of the eval path's design are the
 // next step of this row and are NOT claimed here.
 #include <cfloat>
+#include <initializer_list>
 
 #include "kernels.h"
 
@@ -55,88 +56,230 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* sm /* [NV][8]
 // ---------------------------------------------------------------------------------------------------------------------
 // depthwise 3x3, pad 1
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kT)
-dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
-              int stride, long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
-        const long long plane = i / ((long long)Wo * Ho);
-        const int c = (int)(plane % C);
-        const float* xp = x + plane * H * W;
-        const float* wp = w + c * 9;
-        float acc = 0.f;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * stride + ky - 1;
-            if (iy < 0 || iy >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * stride + kx - 1;
-                if (ix >= 0 && ix < W) acc = fmaf(__ldg(xp + (long long)iy * W + ix), __ldg(wp + ky * 3 + kx), acc);
-            }
-        }
-        y[i] = acc;
-    }
-}
+// All depthwise kernels share one shape: a warp owns 32 adjacent columns of one (image, channel) plane and walks kDwRows rows of
+// them with the 3 x 3 window in registers.  A row costs one coalesced load per lane; the left / right neighbours come from the
+// adjacent lanes by shuffle (lanes 0 / 31 load theirs), so every input element is read once per row block and no index is divided
+// per element.  Rows / columns outside the image are zeros, which leaves the fmaf chain of a border pixel exact.
+constexpr int kDwRows = 32;
+constexpr unsigned int kFull = 0xffffffffu;
+struct Row3 { float l, m, r; };
 
-// dx[n,c,iy,ix] = sum over the taps (ky,kx) with oy*s + ky - 1 == iy, ox*s + kx - 1 == ix of dy[n,c,oy,ox] * w[c,ky,kx]
+// stride 1: the values at columns ox - 1, ox, ox + 1 of row iy (iy is warp-uniform)
+__device__ __forceinline__ Row3 dw_row1(const float* __restrict__ p, int iy, int H, int W, int ox, int lane) {
+    Row3 v{0.f, 0.f, 0.f};
+    if (iy < 0 || iy >= H) return v;
+    const float* r = p + (long long)iy * W;
+    v.m = ox < W ? __ldg(r + ox) : 0.f;
+    v.l = __shfl_up_sync(kFull, v.m, 1);
+    v.r = __shfl_down_sync(kFull, v.m, 1);
+    if (lane == 0) v.l = ox > 0 ? __ldg(r + ox - 1) : 0.f;
+    if (lane == 31) v.r = ox + 1 < W ? __ldg(r + ox + 1) : 0.f;
+    return v;
+}
+// stride 2: the values at columns 2 ox - 1, 2 ox, 2 ox + 1 of row iy
+__device__ __forceinline__ Row3 dw_row2(const float* __restrict__ p, int iy, int H, int W, int ox, int lane, bool vec2) {
+    Row3 v{0.f, 0.f, 0.f};
+    if (iy < 0 || iy >= H) return v;
+    const float* r = p + (long long)iy * W;
+    const int ix = 2 * ox;
+    if (vec2 && ix + 1 < W) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(r + ix));
+        v.m = t.x; v.r = t.y;
+    } else {
+        v.m = ix < W ? __ldg(r + ix) : 0.f;
+        v.r = ix + 1 < W ? __ldg(r + ix + 1) : 0.f;
+    }
+    v.l = __shfl_up_sync(kFull, v.r, 1);
+    if (lane == 0) v.l = ix > 0 ? __ldg(r + ix - 1) : 0.f;
+    return v;
+}
+__device__ __forceinline__ float dot9(const Row3& a, const Row3& b, const Row3& c, const float (&k)[9]) {
+    float acc = 0.f;
+    acc = fmaf(a.l, k[0], acc); acc = fmaf(a.m, k[1], acc); acc = fmaf(a.r, k[2], acc);
+    acc = fmaf(b.l, k[3], acc); acc = fmaf(b.m, k[4], acc); acc = fmaf(b.r, k[5], acc);
+    acc = fmaf(c.l, k[6], acc); acc = fmaf(c.m, k[7], acc); acc = fmaf(c.r, k[8], acc);
+    return acc;
+}
+__device__ __forceinline__ void outer9(float g, const Row3& a, const Row3& b, const Row3& c, float (&acc)[9]) {
+    acc[0] = fmaf(g, a.l, acc[0]); acc[1] = fmaf(g, a.m, acc[1]); acc[2] = fmaf(g, a.r, acc[2]);
+    acc[3] = fmaf(g, b.l, acc[3]); acc[4] = fmaf(g, b.m, acc[4]); acc[5] = fmaf(g, b.r, acc[5]);
+    acc[6] = fmaf(g, c.l, acc[6]); acc[7] = fmaf(g, c.m, acc[7]); acc[8] = fmaf(g, c.r, acc[8]);
+}
+// a warp's 9 partial sums -> dwacc[c][9] (double, zeroed by the launcher)
+__device__ __forceinline__ void dw_flush(const float (&acc)[9], double* __restrict__ dwacc, int c, int lane) {
+    double mine = 0.0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const double v = warp_sum((double)acc[t]);
+        if (lane == t) mine = v;
+    }
+    if (lane < 9 && mine != 0.0) atomicAdd(dwacc + c * 9 + lane, mine);
+}
+struct DwTasks {      // tasks ordered (plane, row block, column block)
+    int RB, CB;
+    long long total;
+    __device__ __forceinline__ void at(long long t, long long& plane, int& y0, int& x0) const {
+        x0 = (int)(t % CB) * 32;
+        y0 = (int)((t / CB) % RB) * kDwRows;
+        plane = t / ((long long)CB * RB);
+    }
+};
+
+// y = depthwise(x) over output rows / columns (Ho, Wo); flip: the taps are read back to front (the stride-1 data gradient is the
+// same correlation of dy with the flipped kernel)
 template <int STRIDE>
 __global__ void __launch_bounds__(kT)
-dw_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int C, int H, int W, int Ho,
-                   int Wo, long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        const int ix = (int)(i % W), iy = (int)((i / W) % H);
-        const long long plane = i / ((long long)W * H);
-        const int c = (int)(plane % C);
-        const float* dp = dy + plane * Ho * Wo;
-        const float* wp = w + c * 9;
-        float acc = 0.f;
+dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
+              DwTasks tk, int flip, int vec2) {
+    const int lane = threadIdx.x & 31;
+    for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
+        long long plane;
+        int oy0, ox0;
+        tk.at(t, plane, oy0, ox0);
+        const int c = (int)(plane % C), ox = ox0 + lane, oy1 = min(Ho, oy0 + kDwRows);
+        float k[9];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int ty = iy + 1 - ky;
-            if (ty < 0 || (STRIDE == 2 && (ty & 1))) continue;
-            const int oy = STRIDE == 2 ? ty >> 1 : ty;
-            if (oy >= Ho) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int tx = ix + 1 - kx;
-                if (tx < 0 || (STRIDE == 2 && (tx & 1))) continue;
-                const int ox = STRIDE == 2 ? tx >> 1 : tx;
-                if (ox < Wo) acc = fmaf(__ldg(dp + (long long)oy * Wo + ox), __ldg(wp + ky * 3 + kx), acc);
+        for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + (flip ? 8 - i : i));
+        const float* xp = x + plane * H * W;
+        float* yp = y + plane * Ho * Wo;
+        if (STRIDE == 1) {
+            Row3 a = dw_row1(xp, oy0 - 1, H, W, ox, lane), b = dw_row1(xp, oy0, H, W, ox, lane);
+#pragma unroll 4
+            for (int oy = oy0; oy < oy1; ++oy) {
+                const Row3 cc = dw_row1(xp, oy + 1, H, W, ox, lane);
+                const float o = dot9(a, b, cc, k);
+                if (ox < Wo) yp[(long long)oy * Wo + ox] = o;
+                a = b; b = cc;
+            }
+        } else {
+            Row3 a = dw_row2(xp, 2 * oy0 - 1, H, W, ox, lane, vec2);
+#pragma unroll 2
+            for (int oy = oy0; oy < oy1; ++oy) {
+                const Row3 b = dw_row2(xp, 2 * oy, H, W, ox, lane, vec2), cc = dw_row2(xp, 2 * oy + 1, H, W, ox, lane, vec2);
+                const float o = dot9(a, b, cc, k);
+                if (ox < Wo) yp[(long long)oy * Wo + ox] = o;
+                a = cc;
             }
         }
-        dx[i] = acc;
     }
 }
 
-// dw[c,ky,kx] = sum over n,oy,ox of dy[n,c,oy,ox] * x[n,c,oy*s+ky-1,ox*s+kx-1].  grid (C, S): partial[s][c][9] (double)
+// stride 1 backward, both gradients from one pass over x and dy:
+//   dx[iy,ix] = sum dy[iy+1-ky, ix+1-kx] w[ky,kx]   (DX)      dw[c,ky,kx] += dy[oy,ox] x[oy+ky-1, ox+kx-1]   (DWG)
+template <bool DX, bool DWG>
 __global__ void __launch_bounds__(kT)
-dw_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ partial, int N, int C, int H,
-                     int W, int Ho, int Wo, int stride) {
-    __shared__ double sm[9 * 8];
-    const int c = blockIdx.x, S = gridDim.y;
-    double acc[9];
+dw_bwd1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ dy, float* __restrict__ dx,
+               double* __restrict__ dwacc, int C, int H, int W, DwTasks tk) {
+    const int lane = threadIdx.x & 31;
+    for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
+        long long plane;
+        int oy0, ox0;
+        tk.at(t, plane, oy0, ox0);
+        const int c = (int)(plane % C), ox = ox0 + lane, oy1 = min(H, oy0 + kDwRows);
+        float k[9], acc[9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = 0.0;
-    const long long per = (long long)N * Ho * Wo;
-    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT) {
-        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho), n = (int)(i / ((long long)Wo * Ho));
-        const float g = __ldg(dy + (((long long)n * C + c) * Ho + oy) * Wo + ox);
-        const float* xp = x + ((long long)n * C + c) * H * W;
+        for (int i = 0; i < 9; ++i) { k[i] = DX ? __ldg(w + c * 9 + 8 - i) : 0.f; acc[i] = 0.f; }
+        const float* gp = dy + plane * H * W;
+        const float* xp = x + plane * H * W;
+        Row3 ga = dw_row1(gp, oy0 - 1, H, W, ox, lane), gb = dw_row1(gp, oy0, H, W, ox, lane);
+        Row3 xa{0.f, 0.f, 0.f}, xb{0.f, 0.f, 0.f};
+        if (DWG) { xa = dw_row1(xp, oy0 - 1, H, W, ox, lane); xb = dw_row1(xp, oy0, H, W, ox, lane); }
+#pragma unroll 2
+        for (int oy = oy0; oy < oy1; ++oy) {
+            Row3 gc{0.f, 0.f, 0.f}, xc{0.f, 0.f, 0.f};
+            if (DX) gc = dw_row1(gp, oy + 1, H, W, ox, lane);
+            else if (oy + 1 < H) gc.m = ox < W ? __ldg(gp + (long long)(oy + 1) * W + ox) : 0.f;
+            if (DWG) xc = dw_row1(xp, oy + 1, H, W, ox, lane);
+            if (DX && ox < W) dx[plane * H * W + (long long)oy * W + ox] = dot9(ga, gb, gc, k);
+            if (DWG) outer9(gb.m, xa, xb, xc, acc);
+            ga = gb; gb = gc; xa = xb; xb = xc;
+        }
+        if (DWG) dw_flush(acc, dwacc, c, lane);
+    }
+}
+
+// stride 2 data gradient, lane = dy column ox -> dx columns 2 ox and 2 ox + 1, dy row oy -> dx rows 2 oy and 2 oy + 1:
+//   dx[2oy  ][2ox] = d w11                      dx[2oy  ][2ox+1] = dn w10 + d w12
+//   dx[2oy+1][2ox] = nd w01 + d w21             dx[2oy+1][2ox+1] = ndn w00 + nd w02 + dn w20 + d w22
+// with d = dy[oy][ox], dn = dy[oy][ox+1], nd / ndn the same in row oy + 1 (zeros outside)
+__global__ void __launch_bounds__(kT)
+dw_bwd2_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int C, int H, int W, int Ho,
+                    int Wo, DwTasks tk, int vec2) {
+    const int lane = threadIdx.x & 31;
+    for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
+        long long plane;
+        int oy0, ox0;
+        tk.at(t, plane, oy0, ox0);
+        const int c = (int)(plane % C), ox = ox0 + lane, oy1 = min(Ho, oy0 + kDwRows);
+        float k[9];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = oy * stride + ky - 1;
-            if (iy < 0 || iy >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = ox * stride + kx - 1;
-                if (ix >= 0 && ix < W) acc[ky * 3 + kx] += (double)g * (double)__ldg(xp + (long long)iy * W + ix);
+        for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
+        const float* gp = dy + plane * Ho * Wo;
+        float* dp = dx + plane * H * W;
+        auto row = [&](int oy, float& d, float& dn) {
+            d = dn = 0.f;
+            if (oy >= Ho) return;
+            const float* r = gp + (long long)oy * Wo;
+            d = ox < Wo ? __ldg(r + ox) : 0.f;
+            dn = __shfl_down_sync(kFull, d, 1);
+            if (lane == 31) dn = ox + 1 < Wo ? __ldg(r + ox + 1) : 0.f;
+        };
+        float d, dn;
+        row(oy0, d, dn);
+#pragma unroll 2
+        for (int oy = oy0; oy < oy1; ++oy) {
+            float nd, ndn;
+            row(oy + 1, nd, ndn);
+            const int iy = 2 * oy, ix = 2 * ox;
+            const float e0 = d * k[4], e1 = fmaf(dn, k[3], d * k[5]);
+            const float o0 = fmaf(nd, k[1], d * k[7]), o1 = fmaf(ndn, k[0], fmaf(nd, k[2], fmaf(dn, k[6], d * k[8])));
+            if (vec2 && ix + 1 < W) {
+                *reinterpret_cast<float2*>(dp + (long long)iy * W + ix) = make_float2(e0, e1);
+                if (iy + 1 < H) *reinterpret_cast<float2*>(dp + (long long)(iy + 1) * W + ix) = make_float2(o0, o1);
+            } else {
+                if (ix < W) dp[(long long)iy * W + ix] = e0;
+                if (ix + 1 < W) dp[(long long)iy * W + ix + 1] = e1;
+                if (iy + 1 < H) {
+                    if (ix < W) dp[(long long)(iy + 1) * W + ix] = o0;
+                    if (ix + 1 < W) dp[(long long)(iy + 1) * W + ix + 1] = o1;
+                }
             }
+            d = nd; dn = ndn;
         }
     }
-    block_sum<9>(acc, sm);
-    if (threadIdx.x == 0)
-        for (int t = 0; t < 9; ++t) partial[((long long)blockIdx.y * C + c) * 9 + t] = acc[t];
+}
+
+// stride 2 weight gradient: the forward's walk with dy[oy][ox] against the 3 x 3 input window
+__global__ void __launch_bounds__(kT)
+dw_bwd2_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ dwacc, int C, int H, int W,
+                      int Ho, int Wo, DwTasks tk, int vec2) {
+    const int lane = threadIdx.x & 31;
+    for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
+        long long plane;
+        int oy0, ox0;
+        tk.at(t, plane, oy0, ox0);
+        const int c = (int)(plane % C), ox = ox0 + lane, oy1 = min(Ho, oy0 + kDwRows);
+        float acc[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+        const float* xp = x + plane * H * W;
+        const float* gp = dy + plane * Ho * Wo;
+        Row3 a = dw_row2(xp, 2 * oy0 - 1, H, W, ox, lane, vec2);
+#pragma unroll 2
+        for (int oy = oy0; oy < oy1; ++oy) {
+            const Row3 b = dw_row2(xp, 2 * oy, H, W, ox, lane, vec2), cc = dw_row2(xp, 2 * oy + 1, H, W, ox, lane, vec2);
+            const float g = ox < Wo ? __ldg(gp + (long long)oy * Wo + ox) : 0.f;
+            outer9(g, a, b, cc, acc);
+            a = cc;
+        }
+        dw_flush(acc, dwacc, c, lane);
+    }
+}
+
+__global__ void __launch_bounds__(kT)
+double_to_float_kernel(const double* __restrict__ in, float* __restrict__ out, int count) {
+    const int i = blockIdx.x * kT + threadIdx.x;
+    if (i < count) out[i] = (float)in[i];
 }
 
 // out[i] = sum_s partial[s][i]
@@ -408,17 +551,49 @@ reduce_partials_f_kernel(const float* __restrict__ partial, float* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------------------
 // BatchNorm2d with batch statistics (train mode) + optional ReLU
 // ---------------------------------------------------------------------------------------------------------------------
+// The normalised value, one rounding sequence shared by the forward and by the backward's ReLU mask (y > 0 <=> bn_value > 0), so the
+// backward never reads y.
+__device__ __forceinline__ float bn_value(float x, float mu, float rs, float gamma, float beta) {
+    return __fmaf_rn(__fmul_rn(__fsub_rn(x, mu), rs), gamma, beta);
+}
+
+// The per-channel reductions walk channel c's N planes of HW values; a CTA (c, s) owns the s-th slice of every plane.  VEC: HW is a
+// multiple of 4 and the tensors are 16-byte aligned -> the slice is walked as float4 with ONE flattened index over (image, vector)
+// (a 32-bit division per 16 bytes); otherwise nested scalar loops.
+struct ChanSlice { int lo, hi; };       // element range inside a plane
+__device__ __forceinline__ ChanSlice chan_slice(int HW, int S, int s, int gran) {
+    const int units = (HW + gran - 1) / gran, per = (units + S - 1) / S;
+    ChanSlice r{min(HW, s * per * gran), min(HW, (s + 1) * per * gran)};
+    return r;
+}
+
 // grid (C, S): partial[s][c][2] = {sum x, sum x^2} over this CTA's share of the N*HW values of channel c
+template <bool VEC>
 __global__ void __launch_bounds__(kT)
 bn_stats_kernel(const float* __restrict__ x, double* __restrict__ partial, int N, int C, int HW) {
     __shared__ double sm[2 * 8];
     const int c = blockIdx.x, S = gridDim.y;
+    const ChanSlice sl = chan_slice(HW, S, blockIdx.y, VEC ? 4 : 1);
     double v[2] = {0.0, 0.0};
-    const long long per = (long long)N * HW;
-    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT) {
-        const int n = (int)(i / HW), p = (int)(i % HW);
-        const double t = (double)__ldg(x + ((long long)n * C + c) * HW + p);
-        v[0] += t; v[1] += t * t;
+    if (VEC) {
+        const int nv = (sl.hi - sl.lo) >> 2, total = N * nv;
+#pragma unroll 4
+        for (int i = threadIdx.x; i < total; i += kT) {
+            const int n = i / nv, q = i - n * nv;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(x + ((long long)n * C + c) * HW + sl.lo) + q);
+            const float s1 = (t.x + t.y) + (t.z + t.w);
+            const float s2 = fmaf(t.x, t.x, t.y * t.y) + fmaf(t.z, t.z, t.w * t.w);
+            v[0] += (double)s1; v[1] += (double)s2;
+        }
+    } else {
+        for (int n = 0; n < N; ++n) {
+            const float* xp = x + ((long long)n * C + c) * HW;
+#pragma unroll 4
+            for (int p = sl.lo + threadIdx.x; p < sl.hi; p += kT) {
+                const double t = (double)__ldg(xp + p);
+                v[0] += t; v[1] += t * t;
+            }
+        }
     }
     block_sum<2>(v, sm);
     if (threadIdx.x == 0) { partial[((long long)blockIdx.y * C + c) * 2] = v[0]; partial[((long long)blockIdx.y * C + c) * 2 + 1] = v[1]; }
@@ -445,35 +620,73 @@ bn_finalize_kernel(const double* __restrict__ partial, int C, int S, long long c
     }
 }
 
+// elementwise passes: grid (planes = N*C, chunks); a CTA owns kT * 16 consecutive elements of one plane, so the channel's constants
+// are loaded once and no index is divided
+constexpr int kEltChunk = kT * 16;
+
+template <bool VEC>
 __global__ void __launch_bounds__(kT)
 bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int C, int HW, int relu,
-                long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        const int c = (int)((i / HW) % C);
-        float v = (x[i] - __ldg(mean + c)) * __ldg(rstd + c) * __ldg(gamma + c) + __ldg(beta + c);
-        if (relu) v = fmaxf(v, 0.f);
-        y[i] = v;
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int C, int HW, int relu) {
+    const int c = blockIdx.x % C;
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
+    const long long base = (long long)blockIdx.x * HW;
+    const int lo = blockIdx.y * kEltChunk, hi = min(HW, lo + kEltChunk);
+    const float floor_ = relu ? 0.f : -FLT_MAX;
+    if (VEC) {
+        const float4* xp = reinterpret_cast<const float4*>(x + base);
+        float4* yp = reinterpret_cast<float4*>(y + base);
+#pragma unroll 4
+        for (int q = (lo >> 2) + threadIdx.x; q < (hi >> 2); q += kT) {
+            const float4 t = __ldg(xp + q);
+            float4 o;
+            o.x = fmaxf(bn_value(t.x, mu, rs, ga, be), floor_); o.y = fmaxf(bn_value(t.y, mu, rs, ga, be), floor_);
+            o.z = fmaxf(bn_value(t.z, mu, rs, ga, be), floor_); o.w = fmaxf(bn_value(t.w, mu, rs, ga, be), floor_);
+            yp[q] = o;
+        }
+    } else {
+#pragma unroll 4
+        for (int p = lo + threadIdx.x; p < hi; p += kT) y[base + p] = fmaxf(bn_value(__ldg(x + base + p), mu, rs, ga, be), floor_);
     }
 }
 
-// grid (C, S): partial[s][c][2] = {sum g, sum g * xhat}, g = dy masked by the ReLU (y > 0) when relu
+// grid (C, S): partial[s][c][2] = {sum g, sum g * xhat}, g = dy masked by the ReLU (bn_value > 0) when relu
+template <bool VEC>
 __global__ void __launch_bounds__(kT)
-bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, double* __restrict__ partial, int N, int C,
-                     int HW, int relu) {
+bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     double* __restrict__ partial, int N, int C, int HW, int relu) {
     __shared__ double sm[2 * 8];
     const int c = blockIdx.x, S = gridDim.y;
-    const float mu = __ldg(mean + c), rs = __ldg(rstd + c);
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
+    const ChanSlice sl = chan_slice(HW, S, blockIdx.y, VEC ? 4 : 1);
     double v[2] = {0.0, 0.0};
-    const long long per = (long long)N * HW;
-    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT) {
-        const int n = (int)(i / HW), p = (int)(i % HW);
-        const long long e = ((long long)n * C + c) * HW + p;
-        float g = __ldg(dy + e);
-        if (relu && !(__ldg(y + e) > 0.f)) g = 0.f;
-        v[0] += (double)g;
-        v[1] += (double)g * (double)((__ldg(x + e) - mu) * rs);
+    auto one = [&](float xv, float g, float& s1, float& s2) {
+        if (relu && !(bn_value(xv, mu, rs, ga, be) > 0.f)) g = 0.f;
+        s1 += g;
+        s2 = fmaf(g, (xv - mu) * rs, s2);
+    };
+    if (VEC) {
+        const int nv = (sl.hi - sl.lo) >> 2, total = N * nv;
+#pragma unroll 2
+        for (int i = threadIdx.x; i < total; i += kT) {
+            const int n = i / nv, q = i - n * nv;
+            const long long e = ((long long)n * C + c) * HW + sl.lo;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(x + e) + q), g = __ldg(reinterpret_cast<const float4*>(dy + e) + q);
+            float s1 = 0.f, s2 = 0.f;
+            one(t.x, g.x, s1, s2); one(t.y, g.y, s1, s2); one(t.z, g.z, s1, s2); one(t.w, g.w, s1, s2);
+            v[0] += (double)s1; v[1] += (double)s2;
+        }
+    } else {
+        for (int n = 0; n < N; ++n) {
+            const long long e = ((long long)n * C + c) * HW;
+#pragma unroll 4
+            for (int p = sl.lo + threadIdx.x; p < sl.hi; p += kT) {
+                float s1 = 0.f, s2 = 0.f;
+                one(__ldg(x + e + p), __ldg(dy + e + p), s1, s2);
+                v[0] += (double)s1; v[1] += (double)s2;
+            }
+        }
     }
     block_sum<2>(v, sm);
     if (threadIdx.x == 0) { partial[((long long)blockIdx.y * C + c) * 2] = v[0]; partial[((long long)blockIdx.y * C + c) * 2 + 1] = v[1]; }
@@ -490,17 +703,35 @@ bn_bwd_finalize_kernel(const double* __restrict__ partial, int C, int S, float* 
     dgamma[c] = (float)ss;
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(kT)
-bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
-                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx, int C, int HW,
-                    int relu, float inv_count, long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        const int c = (int)((i / HW) % C);
-        float g = dy[i];
-        if (relu && !(y[i] > 0.f)) g = 0.f;
-        const float rs = __ldg(rstd + c), xh = (x[i] - __ldg(mean + c)) * rs;
-        dx[i] = __ldg(gamma + c) * rs * (g - __ldg(dbeta + c) * inv_count - xh * __ldg(dgamma + c) * inv_count);
+                    int relu, float inv_count) {
+    const int c = blockIdx.x % C;
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
+    const float k0 = ga * rs, k1 = __ldg(dbeta + c) * inv_count, k2 = __ldg(dgamma + c) * inv_count;
+    const long long base = (long long)blockIdx.x * HW;
+    const int lo = blockIdx.y * kEltChunk, hi = min(HW, lo + kEltChunk);
+    auto one = [&](float xv, float g) {
+        if (relu && !(bn_value(xv, mu, rs, ga, be) > 0.f)) g = 0.f;
+        return k0 * (g - k1 - (xv - mu) * rs * k2);
+    };
+    if (VEC) {
+        const float4* xp = reinterpret_cast<const float4*>(x + base);
+        const float4* gp = reinterpret_cast<const float4*>(dy + base);
+        float4* op = reinterpret_cast<float4*>(dx + base);
+#pragma unroll 2
+        for (int q = (lo >> 2) + threadIdx.x; q < (hi >> 2); q += kT) {
+            const float4 t = __ldg(xp + q), g = __ldg(gp + q);
+            float4 o;
+            o.x = one(t.x, g.x); o.y = one(t.y, g.y); o.z = one(t.z, g.z); o.w = one(t.w, g.w);
+            op[q] = o;
+        }
+    } else {
+#pragma unroll 4
+        for (int p = lo + threadIdx.x; p < hi; p += kT) dx[base + p] = one(__ldg(x + base + p), __ldg(dy + base + p));
     }
 }
 
@@ -1341,26 +1572,50 @@ size_t train_workspace_bytes(int channels_max, int cout, int cin) {
     return (size_t)64 * channels_max * 9 * sizeof(double) + (size_t)pw_parts_max(cout, cin) * cout * cin * sizeof(float) + 4096;
 }
 
+static DwTasks dw_tasks(long long planes, int rows, int cols) {
+    DwTasks t{(rows + kDwRows - 1) / kDwRows, (cols + 31) / 32, 0};
+    t.total = planes * t.RB * t.CB;
+    return t;
+}
+static int dw_grid(const DwTasks& t) {
+    const long long ctas = (t.total + kT / 32 - 1) / (kT / 32), cap = (long long)num_sms() * 16;
+    return (int)(ctas < cap ? (ctas > 0 ? ctas : 1) : cap);
+}
+static bool vec2_ok(int wd, std::initializer_list<const void*> ptrs) {
+    if (wd & 1) return false;
+    for (const void* p : ptrs)
+        if (reinterpret_cast<uintptr_t>(p) & 7) return false;
+    return true;
+}
+
 cudaError_t launch_train_dw_fwd(const float* x, const float* w, float* y, int n, int c, int h, int wd, int stride, cudaStream_t s) {
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
-    const long long total = (long long)n * c * ho * wo;
-    dw_fwd_kernel<<<grid_for(total), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, stride, total);
+    const DwTasks tk = dw_tasks((long long)n * c, ho, wo);
+    if (stride == 2) dw_fwd_kernel<2><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0, vec2_ok(wd, {x}));
+    else dw_fwd_kernel<1><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0, 0);
     return cudaGetLastError();
 }
 
+// ws: c * 9 doubles of weight-gradient accumulators
 cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, void* ws, int n, int c, int h,
                                 int wd, int stride, cudaStream_t s) {
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
-    if (dx) {
-        const long long total = (long long)n * c * h * wd;
-        if (stride == 2) dw_bwd_data_kernel<2><<<grid_for(total), kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, total);
-        else dw_bwd_data_kernel<1><<<grid_for(total), kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, total);
-    }
+    double* dwacc = reinterpret_cast<double*>(ws);
     if (dw) {
-        const int S = splits_for(c, (long long)n * ho * wo);
-        dw_bwd_weight_kernel<<<dim3(c, S), kT, 0, s>>>(x, dy, reinterpret_cast<double*>(ws), n, c, h, wd, ho, wo, stride);
-        reduce_partials_kernel<<<(c * 9 + kT - 1) / kT, kT, 0, s>>>(reinterpret_cast<const double*>(ws), dw, c * 9, S);
+        cudaError_t e = cudaMemsetAsync(dwacc, 0, (size_t)c * 9 * sizeof(double), s);
+        if (e != cudaSuccess) return e;
     }
+    const DwTasks tk = dw_tasks((long long)n * c, ho, wo);
+    const int grid = dw_grid(tk);
+    if (stride == 1) {
+        if (dx && dw) dw_bwd1_kernel<true, true><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);
+        else if (dx) dw_bwd1_kernel<true, false><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);
+        else if (dw) dw_bwd1_kernel<false, true><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);
+    } else {
+        if (dx) dw_bwd2_data_kernel<<<grid, kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, tk, vec2_ok(wd, {dx}));
+        if (dw) dw_bwd2_weight_kernel<<<grid, kT, 0, s>>>(x, dy, dwacc, c, h, wd, ho, wo, tk, vec2_ok(wd, {x}));
+    }
+    if (dw) double_to_float_kernel<<<(c * 9 + kT - 1) / kT, kT, 0, s>>>(dwacc, dw, c * 9);
     return cudaGetLastError();
 }
 
@@ -1393,29 +1648,43 @@ cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy,
     return cudaGetLastError();
 }
 
+static bool vec4_ok(int hw, std::initializer_list<const void*> ptrs) {
+    if (hw & 3) return false;
+    for (const void* p : ptrs)
+        if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+    return true;
+}
+
 cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                 float* y, float* save_mean, float* save_rstd, void* ws, int n, int c, int hw, float eps,
                                 float momentum, int relu, cudaStream_t s) {
     const int S = splits_for(c, (long long)n * hw);
     double* partial = reinterpret_cast<double*>(ws);
-    bn_stats_kernel<<<dim3(c, S), kT, 0, s>>>(x, partial, n, c, hw);
+    const bool vec = vec4_ok(hw, {x, y});
+    if (vec) bn_stats_kernel<true><<<dim3(c, S), kT, 0, s>>>(x, partial, n, c, hw);
+    else bn_stats_kernel<false><<<dim3(c, S), kT, 0, s>>>(x, partial, n, c, hw);
     bn_finalize_kernel<<<(c + kT - 1) / kT, kT, 0, s>>>(partial, c, S, (long long)n * hw, eps, momentum, save_mean, save_rstd,
                                                          running_mean, running_var);
-    const long long total = (long long)n * c * hw;
-    bn_apply_kernel<<<grid_for(total), kT, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, c, hw, relu, total);
+    const dim3 grid(n * c, (hw + kEltChunk - 1) / kEltChunk);
+    if (vec) bn_apply_kernel<true><<<grid, kT, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, c, hw, relu);
+    else bn_apply_kernel<false><<<grid, kT, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, c, hw, relu);
     return cudaGetLastError();
 }
 
-cudaError_t launch_train_bn_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+// `beta` is needed for the ReLU mask (recomputed from x with the forward's own arithmetic: y is never read)
+cudaError_t launch_train_bn_bwd(const float* x, const float* dy, const float* gamma, const float* beta, const float* save_mean,
                                 const float* save_rstd, float* dx, float* dgamma, float* dbeta, void* ws, int n, int c, int hw,
                                 int relu, cudaStream_t s) {
     const int S = splits_for(c, (long long)n * hw);
     double* partial = reinterpret_cast<double*>(ws);
-    bn_bwd_reduce_kernel<<<dim3(c, S), kT, 0, s>>>(x, y, dy, save_mean, save_rstd, partial, n, c, hw, relu);
+    const bool vec = vec4_ok(hw, {x, dy, dx});
+    if (vec) bn_bwd_reduce_kernel<true><<<dim3(c, S), kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, partial, n, c, hw, relu);
+    else bn_bwd_reduce_kernel<false><<<dim3(c, S), kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, partial, n, c, hw, relu);
     bn_bwd_finalize_kernel<<<(c + kT - 1) / kT, kT, 0, s>>>(partial, c, S, dgamma, dbeta);
-    const long long total = (long long)n * c * hw;
-    bn_bwd_apply_kernel<<<grid_for(total), kT, 0, s>>>(x, y, dy, save_mean, save_rstd, gamma, dgamma, dbeta, dx, c, hw, relu,
-                                                       1.f / (float)((long long)n * hw), total);
+    const dim3 grid(n * c, (hw + kEltChunk - 1) / kEltChunk);
+    const float inv = 1.f / (float)((long long)n * hw);
+    if (vec) bn_bwd_apply_kernel<true><<<grid, kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, dgamma, dbeta, dx, c, hw, relu, inv);
+    else bn_bwd_apply_kernel<false><<<grid, kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, dgamma, dbeta, dx, c, hw, relu, inv);
     return cudaGetLastError();
 }
 

@@ -136,20 +136,20 @@ class BatchNormReLU(torch.autograd.Function):
                 'fscnn_train_batchnorm_forward')
         # the running statistics are buffers (no gradient) updated in place by the kernel; autograd does not track them.
         # batchnorm_relu() bumps num_batches_tracked, which is what tells FastSCNN's eval engine to re-fold its weights.
-        ctx.save_for_backward(x, y, gamma, mean, rstd)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)      # the backward recomputes the ReLU mask from x: y is not kept
         ctx.relu = bool(relu)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, gamma, mean, rstd = ctx.saved_tensors
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
         n, c, h, wd = x.shape
         dx, dgamma, dbeta = torch.empty_like(x), torch.empty_like(gamma), torch.empty_like(gamma)
         ws = _workspace(x.device, c)
         with torch.cuda.device(x.device):
             native.check(native.lib().fscnn_train_batchnorm_backward(
-                x.data_ptr(), y.data_ptr(), dy.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+                x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
                 dgamma.data_ptr(), dbeta.data_ptr(), ws.data_ptr(), ws.numel(), n, c, h * wd, int(ctx.relu), _stream()),
                 'fscnn_train_batchnorm_backward')
         return dx, dgamma, dbeta, None, None, None, None, None

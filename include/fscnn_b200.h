@@ -230,7 +230,8 @@ int fscnn_set_option(fscnn_ctx* ctx, const char* key, int value);
  *  batchnorm : nn.BatchNorm2d(c) in train mode (+ the nn.ReLU that follows when relu != 0): y = (x - mean) * rstd * gamma + beta
  *              with the batch's biased variance; d_running_mean / d_running_var (may both be NULL) are updated in place with
  *              `momentum` and the unbiased variance, exactly like PyTorch; d_save_mean / d_save_rstd [c] feed the backward.
- *              backward: d_dy is the gradient of the (ReLU'd) output y; d_y is needed for the ReLU mask when relu != 0.
+ *              backward: d_dy is the gradient of the (ReLU'd) output y; the ReLU mask (y > 0) is recomputed from d_x with the
+ *              forward's own arithmetic, so y itself is never read (d_beta is needed for that when relu != 0).
  * Any of d_dx / d_dw may be NULL in the conv backward calls when that gradient is not needed. */
 int fscnn_train_workspace_bytes(int max_channels, int max_cout, int max_cin, size_t* out_bytes);
 int fscnn_train_dwconv3x3_forward(const float* d_x, const float* d_w, float* d_y, int n, int c, int h, int w, int stride, void* stream);
@@ -242,7 +243,7 @@ int fscnn_train_pwconv_backward(const float* d_x, const float* d_w, const float*
 int fscnn_train_batchnorm_forward(const float* d_x, const float* d_gamma, const float* d_beta, float* d_running_mean,
                                   float* d_running_var, float* d_y, float* d_save_mean, float* d_save_rstd, void* d_ws, size_t ws_bytes,
                                   int n, int c, int hw, float eps, float momentum, int relu, void* stream);
-int fscnn_train_batchnorm_backward(const float* d_x, const float* d_y, const float* d_dy, const float* d_gamma, const float* d_save_mean,
+int fscnn_train_batchnorm_backward(const float* d_x, const float* d_dy, const float* d_gamma, const float* d_beta, const float* d_save_mean,
                                    const float* d_save_rstd, float* d_dx, float* d_dgamma, float* d_dbeta, void* d_ws, size_t ws_bytes,
                                    int n, int c, int hw, int relu, void* stream);
 
