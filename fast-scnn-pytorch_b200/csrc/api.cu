@@ -1058,9 +1058,10 @@ int fscnn_train_adaptive_avg_pool(const float* d_in, float* d_out, int planes, i
     if (!d_in || !d_out || planes < 1 || h < 1 || w < 1 || bins < 1) return fail(FSCNN_EINVAL, "bad argument");
     FSCNN_TRAIN_CALL(launch_train_adaptive_pool(d_in, d_out, planes, h, w, bins, backward, (cudaStream_t)stream), "adaptive pool");
 }
-int fscnn_train_dropout(const float* d_x, float* d_y, float p, unsigned long long seed, int64_t numel, void* stream) {
+int fscnn_train_dropout(const float* d_x, float* d_y, float p, unsigned long long seed, const unsigned long long* d_step, int64_t numel,
+                        void* stream) {
     if (!d_x || !d_y || numel < 1 || !(p >= 0.f && p < 1.f)) return fail(FSCNN_EINVAL, "bad argument");
-    FSCNN_TRAIN_CALL(launch_train_dropout(d_x, d_y, p, seed, numel, (cudaStream_t)stream), "dropout");
+    FSCNN_TRAIN_CALL(launch_train_dropout(d_x, d_y, p, seed, d_step, numel, (cudaStream_t)stream), "dropout");
 }
 int fscnn_train_add_relu(const float* d_a, const float* d_b, float* d_y, int relu, int64_t numel, void* stream) {
     if (!d_a || !d_b || !d_y || numel < 1) return fail(FSCNN_EINVAL, "bad argument");
@@ -1070,6 +1071,12 @@ int fscnn_train_relu_backward(const float* d_y, const float* d_dy, float* d_dx, 
     if (!d_y || !d_dy || !d_dx || numel < 1) return fail(FSCNN_EINVAL, "bad argument");
     FSCNN_TRAIN_CALL(launch_train_relu_bwd(d_y, d_dy, d_dx, numel, (cudaStream_t)stream), "relu backward");
 }
+int fscnn_train_set_math(int mode) {
+    if (train_set_math(mode)) return fail(FSCNN_EINVAL, "math mode must be 0 (fp32) or 1 (TF32)");
+    return FSCNN_OK;
+}
+int fscnn_train_get_math(void) { return train_get_math(); }
+
 int fscnn_train_sgd_step(float* d_param, const float* d_grad, float* d_momentum_buf, float lr, float momentum, float weight_decay,
                          float grad_scale, int first_step, int64_t numel, void* stream) {
     if (!d_param || !d_grad || !d_momentum_buf || numel < 1) return fail(FSCNN_EINVAL, "bad argument");

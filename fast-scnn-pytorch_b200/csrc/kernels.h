@@ -139,6 +139,8 @@ cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy,
 cudaError_t launch_train_pw_fwd(const float* x, const float* w, float* y, int n, int cin, int cout, int hw, cudaStream_t s);
 cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, void* ws, int n, int cin,
                                 int cout, int hw, cudaStream_t s);
+int train_set_math(int mode);
+int train_get_math();
 cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                 float* y, float* save_mean, float* save_rstd, void* ws, int n, int c, int hw, float eps,
                                 float momentum, int relu, cudaStream_t s);
@@ -157,7 +159,8 @@ cudaError_t launch_train_bias_add(float* y, const float* b, int n, int c, int hw
 cudaError_t launch_train_bias_grad(const float* dy, float* db, void* ws, int n, int c, int hw, cudaStream_t s);
 cudaError_t launch_train_bilinear(const float* in, float* out, int planes, int hi, int wi, int ho, int wo, int backward, cudaStream_t s);
 cudaError_t launch_train_adaptive_pool(const float* in, float* out, int planes, int h, int wd, int bins, int backward, cudaStream_t s);
-cudaError_t launch_train_dropout(const float* x, float* y, float p, unsigned long long seed, long long total, cudaStream_t s);
+cudaError_t launch_train_dropout(const float* x, float* y, float p, unsigned long long seed, const unsigned long long* d_step, long long total,
+                                 cudaStream_t s);
 cudaError_t launch_train_add_relu(const float* a, const float* b, float* y, int relu, long long total, cudaStream_t s);
 cudaError_t launch_train_relu_bwd(const float* y, const float* dy, float* dx, long long total, cudaStream_t s);
 cudaError_t launch_train_sgd(float* p, const float* g, float* buf, float lr, float momentum, float wd, float gscale, int first,

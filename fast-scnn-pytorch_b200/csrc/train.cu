@@ -298,7 +298,7 @@ reduce_partials_kernel(const double* __restrict__ partial, float* __restrict__ o
 //   forward      : A = W[cout][cin] (sAb 0),            B = x[n] ([cin][hw]),        C = y[n]
 //   data gradient: A = W^T (sAm 1, sAk cin),            B = dy[n] ([cout][hw]),      C = dx[n]
 //   weight grad. : A = dy[n] ([cout][hw]),              B = x[n]^T (sBk 1, sBj hw),  C = partial[b] ([cout][cin]), then reduced
-// 64 x 64 tile, K chunks of 16, 256 threads x (4 x 4) outputs.  `splitk` CTAs along grid.z share one batch item's K range.
+// Two kernels, one per shape class; `splitk` CTAs along grid.z share one batch item's K range in the weight gradient.
 // ---------------------------------------------------------------------------------------------------------------------
 struct GemmArgs {
     const float *A, *B;
@@ -307,59 +307,6 @@ struct GemmArgs {
     long long sAb, sAm, sAk, sBb, sBk, sBj, sCb;
     int ldc, splitk;
 };
-
-__global__ void __launch_bounds__(kT)
-gemm_kernel(GemmArgs g) {
-    constexpr int BM = 64, BN = 64, BK = 16;
-    __shared__ float As[BK][BM + 4], Bs[BK][BN + 4];
-    const int b = blockIdx.z / g.splitk, sk = blockIdx.z % g.splitk;
-    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
-    const int tid = threadIdx.x, tm = tid / 16, tj = tid % 16;
-    const float* A = g.A + b * g.sAb;
-    const float* B = g.B + b * g.sBb;
-    const int kper = ((g.K + g.splitk - 1) / g.splitk + BK - 1) / BK * BK;
-    const int k_begin = sk * kper, k_end = min(g.K, k_begin + kper);
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    // thread order inside a tile load follows the unit-stride dimension of the operand
-    const bool a_k_fast = g.sAk == 1, b_j_fast = g.sBj == 1;
-    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
-        for (int i = tid; i < BM * BK; i += kT) {
-            const int k = a_k_fast ? i % BK : i / BM, m = a_k_fast ? i / BK : i % BM;
-            As[k][m] = (m0 + m < g.M && k0 + k < k_end) ? __ldg(A + (long long)(m0 + m) * g.sAm + (long long)(k0 + k) * g.sAk) : 0.f;
-        }
-        for (int i = tid; i < BN * BK; i += kT) {
-            const int j = b_j_fast ? i % BN : i / BK, k = b_j_fast ? i / BN : i % BK;
-            Bs[k][j] = (j0 + j < g.N && k0 + k < k_end) ? __ldg(B + (long long)(k0 + k) * g.sBk + (long long)(j0 + j) * g.sBj) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[k][tm * 4]);
-            const float4 bb = *reinterpret_cast<const float4*>(&Bs[k][tj * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    float* C = g.C + (long long)blockIdx.z * g.sCb;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + tm * 4 + i;
-        if (m >= g.M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int jj = j0 + tj * 4 + j;
-            if (jj < g.N) C[(long long)m * g.ldc + jj] = acc[i][j];
-        }
-    }
-}
 
 // The weight-gradient shape: a small output (M = cout, N = cin) and a very long K (the pixels of an image slice), both operands
 // with unit stride along K.  64 x 64 tile, K chunks of 32 read as float4 along K (128 contiguous bytes per row) and prefetched into
@@ -537,6 +484,246 @@ gemm_pix_kernel(GemmArgs g) {
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same two contractions on the tensor cores (mma.sync m16n8k8, TF32 operands rounded to nearest, fp32 accumulators): 10 mantissa
+// bits per operand, which is what cuDNN convolutions do by default under torch.backends.cudnn.allow_tf32 and about what the
+// reference's fp16 autocast keeps; opt-in through fscnn_train_set_math(1).  TERMS = 3 is the split form (x = hi + lo, products
+// lo_a hi_b + hi_a lo_b + hi_a hi_b, ~21 mantissa bits): measured on a B200 it is no faster than the fp32 FMA kernels (4.25 vs 4.6 ms
+// for the forward / data-gradient GEMMs of a config-5 step) and 3-8x less accurate, so it is not reachable from the ABI.
+// Shared-memory tiles use pitches of 8 (k-major tiles) or 4 (k-fastest tiles) modulo 32 words, so the per-lane fragment loads of
+// a warp hit 32 distinct banks.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+template <int TERMS>
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_hi(x);
+    lo = TERMS == 3 ? tf32_hi(x - __uint_as_float(hi)) : 0u;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+template <int TERMS>
+__device__ __forceinline__ void mma_split(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
+                                          const uint32_t (&bl)[2]) {
+    if (TERMS == 3) { mma_tf32(d, al, bh); mma_tf32(d, ah, bl); }
+    mma_tf32(d, ah, bh);
+}
+
+// forward / data gradient: C[b][m][j] = sum_k A(m,k) B[b][k][j]; 64 x 128 tile, K chunks of 16, 8 warps as 2 x 4, warp tile 32 x 32
+template <int TERMS>
+__global__ void __launch_bounds__(kT)
+gemm_pix_mma_kernel(GemmArgs g) {
+    constexpr int BM = 64, BN = 128, BK = 16, PA = BM + 8, PB = BN + 8;
+    __shared__ __align__(16) float As[BK][PA], Bs[BK][PB];
+    const int b = blockIdx.z;
+    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;
+    const float* A = g.A + b * g.sAb;
+    const float* B = g.B + b * g.sBb;
+    const bool vec = ((g.sBk & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    const bool a_k_fast = g.sAk == 1;
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    float ra[4];
+    float4 rb[2];
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {      // A: 64 x 16
+            const int i = tid + r * kT;
+            const int k = a_k_fast ? i % BK : i / BM, m = a_k_fast ? i / BK : i % BM;
+            ra[r] = (m0 + m < g.M && k0 + k < g.K) ? __ldg(A + (long long)(m0 + m) * g.sAm + (long long)(k0 + k) * g.sAk) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {      // B: 16 x 128 as float4
+            const int i = tid + r * kT, k = i / 32, j = (i % 32) * 4;
+            const float* src = B + (long long)(k0 + k) * g.sBk + j0 + j;
+            if (k0 + k < g.K && vec && j0 + j + 3 < g.N) {
+                rb[r] = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = (k0 + k < g.K && j0 + j + q < g.N) ? __ldg(src + q) : 0.f;
+                rb[r] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = tid + r * kT;
+            const int k = a_k_fast ? i % BK : i / BM, m = a_k_fast ? i / BK : i % BM;
+            As[k][m] = ra[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * kT, k = i / 32, j = (i % 32) * 4;
+            *reinterpret_cast<float4*>(&Bs[k][j]) = rb[r];
+        }
+    };
+    load_tiles(0);
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+        store_tiles();
+        __syncthreads();
+        if (k0 + BK < g.K) load_tiles(k0 + BK);
+#pragma unroll
+        for (int ks = 0; ks < BK; ks += 8) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int m = wm + i * 16 + gq;
+                tf32_split<TERMS>(As[ks + tq][m], ah[i][0], al[i][0]);
+                tf32_split<TERMS>(As[ks + tq][m + 8], ah[i][1], al[i][1]);
+                tf32_split<TERMS>(As[ks + tq + 4][m], ah[i][2], al[i][2]);
+                tf32_split<TERMS>(As[ks + tq + 4][m + 8], ah[i][3], al[i][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = wn + j * 8 + gq;
+                tf32_split<TERMS>(Bs[ks + tq][n], bh[j][0], bl[j][0]);
+                tf32_split<TERMS>(Bs[ks + tq + 4][n], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_split<TERMS>(acc[i][j], ah[i], al[i], bh[j], bl[j]);
+        }
+        __syncthreads();
+    }
+    float* C = g.C + (long long)b * g.sCb;
+    const bool cvec = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 7) == 0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = m0 + wm + i * 16 + gq + h * 8;
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int jj = j0 + wn + j * 8 + 2 * tq;
+                float* dst = C + (long long)m * g.ldc + jj;
+                if (cvec && jj + 1 < g.N) {
+                    *reinterpret_cast<float2*>(dst) = make_float2(acc[i][j][2 * h], acc[i][j][2 * h + 1]);
+                } else {
+                    if (jj < g.N) dst[0] = acc[i][j][2 * h];
+                    if (jj + 1 < g.N) dst[1] = acc[i][j][2 * h + 1];
+                }
+            }
+        }
+}
+
+// weight gradient: C[part][m][j] = sum over this part's k of A[b][m][k] B[b][j][k] (both operands k-fastest); 64 x 64 tile, K chunks
+// of 32, 8 warps as 2 x 4, warp tile 32 x 16
+template <int TERMS>
+__global__ void __launch_bounds__(kT)
+gemm_wgrad_mma_kernel(GemmArgs g) {
+    constexpr int BM = 64, BN = 64, BK = 32, P = BK + 4;
+    __shared__ __align__(16) float As[BM][P], Bs[BN][P];
+    const int b = blockIdx.z / g.splitk, sk = blockIdx.z % g.splitk;
+    const int m0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+    const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+    const float* A = g.A + b * g.sAb;
+    const float* B = g.B + b * g.sBb;
+    const int kper = ((g.K + g.splitk - 1) / g.splitk + BK - 1) / BK * BK;
+    const int k_begin = sk * kper, k_end = min(g.K, k_begin + kper);
+    const bool avec = ((g.sAm & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const bool bvec = ((g.sBj & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    float acc[2][2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    float4 ra[2], rb[2];
+    auto load4 = [&](const float* base, long long row_stride, int row, int row_limit, int k, bool vec) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < row_limit) {
+            const float* src = base + (long long)row * row_stride + k;
+            if (vec && k + 3 < k_end) {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+                float t[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) t[q] = k + q < k_end ? __ldg(src + q) : 0.f;
+                v = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        return v;
+    };
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {      // 64 rows x 8 float4 per operand
+            const int i = tid + r * kT, row = i / 8, k4 = (i % 8) * 4;
+            ra[r] = load4(A, g.sAm, m0 + row, g.M, k0 + k4, avec && ((k0 + k4) & 3) == 0);
+            rb[r] = load4(B, g.sBj, j0 + row, g.N, k0 + k4, bvec && ((k0 + k4) & 3) == 0);
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = tid + r * kT, row = i / 8, k4 = (i % 8) * 4;
+            *reinterpret_cast<float4*>(&As[row][k4]) = ra[r];
+            *reinterpret_cast<float4*>(&Bs[row][k4]) = rb[r];
+        }
+    };
+    if (k_begin < k_end) load_tiles(k_begin);
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        store_tiles();
+        __syncthreads();
+        if (k0 + BK < k_end) load_tiles(k0 + BK);
+#pragma unroll
+        for (int ks = 0; ks < BK; ks += 8) {
+            uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int m = wm + i * 16 + gq;
+                tf32_split<TERMS>(As[m][ks + tq], ah[i][0], al[i][0]);
+                tf32_split<TERMS>(As[m + 8][ks + tq], ah[i][1], al[i][1]);
+                tf32_split<TERMS>(As[m][ks + tq + 4], ah[i][2], al[i][2]);
+                tf32_split<TERMS>(As[m + 8][ks + tq + 4], ah[i][3], al[i][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n = wn + j * 8 + gq;
+                tf32_split<TERMS>(Bs[n][ks + tq], bh[j][0], bl[j][0]);
+                tf32_split<TERMS>(Bs[n][ks + tq + 4], bh[j][1], bl[j][1]);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) mma_split<TERMS>(acc[i][j], ah[i], al[i], bh[j], bl[j]);
+        }
+        __syncthreads();
+    }
+    float* C = g.C + (long long)blockIdx.z * g.sCb;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = m0 + wm + i * 16 + gq + h * 8;
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int jj = j0 + wn + j * 8 + 2 * tq;
+                if (jj < g.N) C[(long long)m * g.ldc + jj] = acc[i][j][2 * h];
+                if (jj + 1 < g.N) C[(long long)m * g.ldc + jj + 1] = acc[i][j][2 * h + 1];
+            }
+        }
 }
 
 __global__ void __launch_bounds__(kT)
@@ -1513,8 +1700,10 @@ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, long long 
     return (float)(z >> 40) * (1.f / 16777216.f) >= p;
 }
 __global__ void __launch_bounds__(kT)
-dropout_kernel(const float* __restrict__ x, float* __restrict__ y, float p, unsigned long long seed, long long total) {
+dropout_kernel(const float* __restrict__ x, float* __restrict__ y, float p, unsigned long long seed,
+               const unsigned long long* __restrict__ d_step, long long total) {
     const float scale = 1.f / (1.f - p);
+    if (d_step) seed += 0xD1342543DE82EF95ull * (*d_step + 1ull);
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT)
         y[i] = dropout_keep(seed, i, p) ? x[i] * scale : 0.f;
 }
@@ -1619,9 +1808,23 @@ cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy,
     return cudaGetLastError();
 }
 
+// 0: fp32 FMA kernels (default), 1: TF32 operands on the tensor cores
+static int g_train_math = 0;
+int train_set_math(int mode) {
+    if (mode < 0 || mode > 1) return -1;
+    g_train_math = mode;
+    return 0;
+}
+int train_get_math() { return g_train_math; }
+
+static void launch_gemm_pix(const GemmArgs& g, dim3 grid, cudaStream_t s) {
+    if (g_train_math == 0) gemm_pix_kernel<<<grid, kT, 0, s>>>(g);
+    else gemm_pix_mma_kernel<1><<<grid, kT, 0, s>>>(g);
+}
+
 cudaError_t launch_train_pw_fwd(const float* x, const float* w, float* y, int n, int cin, int cout, int hw, cudaStream_t s) {
     GemmArgs g{w, x, y, cout, hw, cin, 0, cin, 1, (long long)cin * hw, hw, 1, (long long)cout * hw, hw, 1};
-    gemm_pix_kernel<<<dim3((hw + 127) / 128, (cout + 63) / 64, n), kT, 0, s>>>(g);
+    launch_gemm_pix(g, dim3((hw + 127) / 128, (cout + 63) / 64, n), s);
     return cudaGetLastError();
 }
 
@@ -1629,7 +1832,7 @@ cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy,
                                 int cout, int hw, cudaStream_t s) {
     if (dx) {      // dx[n] = W^T dy[n]
         GemmArgs g{w, dy, dx, cin, hw, cout, 0, 1, cin, (long long)cout * hw, hw, 1, (long long)cin * hw, hw, 1};
-        gemm_pix_kernel<<<dim3((hw + 127) / 128, (cin + 63) / 64, n), kT, 0, s>>>(g);
+        launch_gemm_pix(g, dim3((hw + 127) / 128, (cin + 63) / 64, n), s);
     }
     if (dw) {      // dW = sum_n dy[n] x[n]^T, split over the pixels of every image: enough CTAs to fill the GPU ~4 times
         const int tiles = ((cin + 63) / 64) * ((cout + 63) / 64), pmax = pw_parts_max(cout, cin);
@@ -1642,7 +1845,9 @@ cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy,
         const int parts = n * splitk;
         float* partial = reinterpret_cast<float*>(ws);
         GemmArgs g{dy, x, partial, cout, cin, hw, (long long)cout * hw, hw, 1, (long long)cin * hw, 1, hw, (long long)cout * cin, cin, splitk};
-        gemm_wgrad_kernel<<<dim3((cin + 63) / 64, (cout + 63) / 64, parts), kT, 0, s>>>(g);
+        const dim3 grid((cin + 63) / 64, (cout + 63) / 64, parts);
+        if (g_train_math == 0) gemm_wgrad_kernel<<<grid, kT, 0, s>>>(g);
+        else gemm_wgrad_mma_kernel<1><<<grid, kT, 0, s>>>(g);
         reduce_partials_f_kernel<<<(cout * cin + kT - 1) / kT, kT, 0, s>>>(partial, dw, cout * cin, parts);
     }
     return cudaGetLastError();
@@ -1764,8 +1969,9 @@ cudaError_t launch_train_adaptive_pool(const float* in, float* out, int planes, 
     }
     return cudaGetLastError();
 }
-cudaError_t launch_train_dropout(const float* x, float* y, float p, unsigned long long seed, long long total, cudaStream_t s) {
-    dropout_kernel<<<grid_for(total), kT, 0, s>>>(x, y, p, seed, total);
+cudaError_t launch_train_dropout(const float* x, float* y, float p, unsigned long long seed, const unsigned long long* d_step, long long total,
+                                 cudaStream_t s) {
+    dropout_kernel<<<grid_for(total), kT, 0, s>>>(x, y, p, seed, d_step, total);
     return cudaGetLastError();
 }
 cudaError_t launch_train_add_relu(const float* a, const float* b, float* y, int relu, long long total, cudaStream_t s) {

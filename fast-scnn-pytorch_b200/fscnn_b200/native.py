@@ -84,9 +84,11 @@ _SIGNATURES = {
     'fscnn_train_bias_grad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'fscnn_train_bilinear': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'fscnn_train_adaptive_avg_pool': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    'fscnn_train_dropout': (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_ulonglong, C.c_int64, C.c_void_p]),
+    'fscnn_train_dropout': (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_ulonglong, C.c_void_p, C.c_int64, C.c_void_p]),
     'fscnn_train_add_relu': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     'fscnn_train_relu_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'fscnn_train_set_math': (C.c_int, [C.c_int]),
+    'fscnn_train_get_math': (C.c_int, []),
     'fscnn_train_sgd_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64,
                                        C.c_void_p]),
     'fscnn_train_ohem_workspace_bytes': (C.c_int, [C.POINTER(C.c_size_t)]),

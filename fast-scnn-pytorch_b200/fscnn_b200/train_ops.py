@@ -18,6 +18,23 @@ from . import native
 _ws_cache = {}
 
 
+MATH_MODES = {'fp32': 0, 'tf32': 1}
+
+
+def set_matmul_precision(mode: str) -> None:
+    """Arithmetic of the pointwise / dense 3x3 contractions of the training operators (process-wide, fscnn_train_set_math):
+    'fp32' (default) = FMA on the CUDA cores; 'tf32' = TF32 operands on the tensor cores with fp32 accumulation (what cuDNN does
+    under torch's default allow_tf32, and about the precision of the reference's fp16 autocast)."""
+    if mode not in MATH_MODES:
+        raise ValueError(f'matmul precision must be one of {sorted(MATH_MODES)}, got {mode!r}')
+    native.check(native.lib().fscnn_train_set_math(MATH_MODES[mode]), 'fscnn_train_set_math')
+
+
+def get_matmul_precision() -> str:
+    code = native.lib().fscnn_train_get_math()
+    return next(k for k, v in MATH_MODES.items() if v == code)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -412,6 +429,18 @@ class AdaptiveAvgPool(torch.autograd.Function):
         return dx, None
 
 
+# A device int64 counter mixed into every dropout seed when set (Trainer's CUDA-graph mode bumps it before each replay, so a
+# captured step draws fresh masks); None: the seed alone decides.
+_dropout_step: Optional[torch.Tensor] = None
+
+
+def set_dropout_step_counter(counter: Optional[torch.Tensor]) -> None:
+    global _dropout_step
+    if counter is not None and (not counter.is_cuda or counter.dtype != torch.int64 or counter.numel() != 1):
+        raise ValueError('the dropout step counter must be a CUDA int64 tensor with one element')
+    _dropout_step = counter
+
+
 class Dropout(torch.autograd.Function):
     """nn.Dropout(p) in train mode; the mask is regenerated from the seed in the backward"""
 
@@ -419,9 +448,11 @@ class Dropout(torch.autograd.Function):
     def forward(ctx, x, p, seed):
         x = _check(x, 'input')
         y = torch.empty_like(x)
+        step = _dropout_step.data_ptr() if _dropout_step is not None else None
         with torch.cuda.device(x.device):
-            native.check(_lib().fscnn_train_dropout(x.data_ptr(), y.data_ptr(), float(p), int(seed), x.numel(), _stream()), 'fscnn_train_dropout')
-        ctx.p, ctx.seed = float(p), int(seed)
+            native.check(_lib().fscnn_train_dropout(x.data_ptr(), y.data_ptr(), float(p), int(seed), step, x.numel(), _stream()),
+                         'fscnn_train_dropout')
+        ctx.p, ctx.seed, ctx.step = float(p), int(seed), step
         return y
 
     @staticmethod
@@ -429,7 +460,8 @@ class Dropout(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
         with torch.cuda.device(dy.device):
-            native.check(_lib().fscnn_train_dropout(dy.data_ptr(), dx.data_ptr(), ctx.p, ctx.seed, dy.numel(), _stream()), 'fscnn_train_dropout')
+            native.check(_lib().fscnn_train_dropout(dy.data_ptr(), dx.data_ptr(), ctx.p, ctx.seed, ctx.step, dy.numel(), _stream()),
+                         'fscnn_train_dropout')
         return dx, None, None
 
 

@@ -34,9 +34,18 @@ def poly_lr(base_lr: float, cur_iter: int, nepochs: int, iters_per_epoch: int, p
 class Trainer:
     def __init__(self, model, base_lr=1e-2, momentum=0.9, weight_decay=1e-4, aux_weight=0.4, ignore_label=-1, ohem_thresh=0.7,
                  ohem_min_kept=256, use_class_weights: Optional[bool] = None, nepochs=160, iters_per_epoch=1000, process_group=None,
-                 fused_loss: bool = True):
+                 fused_loss: bool = True, cuda_graph: bool = False, graph_warmup: int = 3, matmul_precision: Optional[str] = None):
+        """``cuda_graph``: after ``graph_warmup`` eager steps, zero_grad + forward + loss + backward are captured once into a CUDA
+        graph per input shape and replayed (the ~780 kernel launches of a step cost more host time than the kernels take on a
+        B200); the gradient all-reduce and the SGD update stay outside the graph, so the learning rate remains a host value.
+        ``matmul_precision``: 'fp32' or 'tf32' for the pointwise / dense 3x3 contractions (train_ops.set_matmul_precision;
+        process-wide); None leaves the current setting."""
         self.model = model
         self.fused_loss = bool(fused_loss)
+        if matmul_precision is not None:
+            train_ops.set_matmul_precision(matmul_precision)
+        self.cuda_graph, self.graph_warmup = bool(cuda_graph), int(graph_warmup)
+        self._graph = self._graph_key = self._static_x = self._static_t = self._static_loss = None
         params = [p for p in model.parameters() if p.requires_grad]
         if not params or not params[0].is_cuda:
             raise RuntimeError('move the model to a CUDA device before building the Trainer (there is no CPU path)')
@@ -64,6 +73,7 @@ class Trainer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.iteration = 0
+        self._dropout_step = torch.zeros(1, dtype=torch.int64, device=dev) if self.cuda_graph else None
         if self.world > 1:      # every rank starts from rank 0's weights
             dist.broadcast(self.flat_param, src=0, group=process_group)
 
@@ -91,18 +101,49 @@ class Trainer:
         self.model.train()
         if lr is None:
             lr = poly_lr(self.base_lr, self.iteration, self.nepochs, self.iters_per_epoch)
-        self.flat_grad.zero_()
         for p in self.params:      # autograd accumulates into the flat-buffer views
             if p.grad is None:
                 raise RuntimeError('a parameter lost its flat gradient view (zero_grad(set_to_none=True) was called on the model?)')
-        if self.fused_loss and hasattr(self.model, '_train_forward_lowres'):
-            loss = self.loss_from_lowres(self.model._train_forward_lowres(images), target)
+        if self.cuda_graph and self.iteration >= self.graph_warmup:
+            loss = self._graph_forward_backward(images, target)
         else:
-            loss = self.loss(self.model(images), target)
-        loss.backward()
+            loss = self._forward_backward(images, target)
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         train_ops.sgd_step(self.flat_param, self.flat_grad, self.momentum_buf, lr, self.momentum, self.weight_decay,
                            grad_scale=1.0 / self.world, first_step=self.iteration == 0)
         self.iteration += 1
+        return loss
+
+    def _forward_backward(self, images, target):
+        self.flat_grad.zero_()
+        if self.fused_loss and hasattr(self.model, '_train_forward_lowres'):
+            loss = self.loss_from_lowres(self.model._train_forward_lowres(images), target)
+        else:
+            loss = self.loss(self.model(images), target)
+        loss.backward()
         return loss.detach()
+
+    def _graph_forward_backward(self, images, target):
+        """Replays the captured zero_grad + forward + loss + backward on static copies of the inputs (captured on first use per input
+        shape).  Dropout masks change from replay to replay through a device step counter mixed into every dropout seed.  The
+        returned loss is the graph's static output tensor: it is overwritten by the next step."""
+        key = (tuple(images.shape), images.dtype, tuple(target.shape), target.dtype)
+        if self._graph is None or key != self._graph_key:
+            self._static_x, self._static_t = images.detach().clone(), target.detach().clone()
+            torch.cuda.synchronize(images.device)
+            graph = torch.cuda.CUDAGraph()
+            train_ops.set_dropout_step_counter(self._dropout_step)
+            try:
+                with torch.cuda.graph(graph):
+                    self._static_loss = self._forward_backward(self._static_x, self._static_t)
+            finally:
+                train_ops.set_dropout_step_counter(None)
+            self._graph, self._graph_key = graph, key
+        if images.data_ptr() != self._static_x.data_ptr():
+            self._static_x.copy_(images, non_blocking=True)
+        if target.data_ptr() != self._static_t.data_ptr():
+            self._static_t.copy_(target, non_blocking=True)
+        self._dropout_step += 1
+        self._graph.replay()
+        return self._static_loss

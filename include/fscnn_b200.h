@@ -256,7 +256,8 @@ int fscnn_train_batchnorm_backward(const float* d_x, const float* d_dy, const fl
  *              the gradient [planes][ho][wo], d_out the input gradient [planes][hi][wi] (gather form, deterministic)
  *  adaptive_avg_pool : nn.AdaptiveAvgPool2d(bins) with PyTorch's overlapping bins; backward != 0 as for bilinear
  *  dropout   : nn.Dropout(p) in train mode; the keep mask is a counter-based hash of (seed, element), so the backward is the
- *              same call on the gradient with the same seed
+ *              same call on the gradient with the same seed; d_step (may be NULL) points to a device counter that is mixed into the
+ *              seed when the kernel runs, so a captured CUDA graph of the step draws a fresh mask on every replay
  *  add_relu / relu_backward : y = relu(a + b) (relu = 0: plain add; FFM :217-218, residuals :114) and g = dy * [y > 0]
  *  sgd_step  : torch.optim.SGD(momentum, weight_decay) on flat buffers: g' = grad * grad_scale + wd * p;
  *              buf = first_step ? g' : momentum * buf + g'; p -= lr * buf */
@@ -266,9 +267,18 @@ int fscnn_train_bias_add(float* d_y, const float* d_bias, int n, int c, int hw, 
 int fscnn_train_bias_grad(const float* d_dy, float* d_dbias, void* d_ws, size_t ws_bytes, int n, int c, int hw, void* stream);
 int fscnn_train_bilinear(const float* d_in, float* d_out, int planes, int hi, int wi, int ho, int wo, int backward, void* stream);
 int fscnn_train_adaptive_avg_pool(const float* d_in, float* d_out, int planes, int h, int w, int bins, int backward, void* stream);
-int fscnn_train_dropout(const float* d_x, float* d_y, float p, unsigned long long seed, int64_t numel, void* stream);
+int fscnn_train_dropout(const float* d_x, float* d_y, float p, unsigned long long seed, const unsigned long long* d_step, int64_t numel,
+                        void* stream);
 int fscnn_train_add_relu(const float* d_a, const float* d_b, float* d_y, int relu, int64_t numel, void* stream);
 int fscnn_train_relu_backward(const float* d_y, const float* d_dy, float* d_dx, int64_t numel, void* stream);
+/* Arithmetic of the pointwise / dense-3x3 contractions of the training operators (process-wide; not a per-call argument because
+ * torch.backends.cuda.matmul.allow_tf32, the switch it mirrors, is process-wide too):
+ *   0  fp32 FMA on the CUDA cores (default; the mode the parity tests pin to 1e-4)
+ *   1  TF32 operands (rounded to nearest, 10 mantissa bits) on the tensor cores, fp32 accumulators: what cuDNN does for convolutions
+ *      when torch's allow_tf32 is on (its default) and about what the reference's fp16 autocast (train.py:267-275) keeps
+ * Returns FSCNN_EINVAL for any other mode.  fscnn_train_get_math returns the current mode. */
+int fscnn_train_set_math(int mode);
+int fscnn_train_get_math(void);
 int fscnn_train_sgd_step(float* d_param, const float* d_grad, float* d_momentum_buf, float lr, float momentum, float weight_decay,
                          float grad_scale, int first_step, int64_t numel, void* stream);
 

@@ -278,3 +278,91 @@ def test_fused_upsample_ohem_equals_the_two_step_form(n, c, hl, wl, h, w, scale,
     (3.0 * lb).backward()
     assert float(la.detach()) == float(lb.detach())
     assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 1e-5
+
+
+def test_tf32_matmul_mode_is_close_to_fp32_and_really_different():
+    """fscnn_train_set_math(1): the pointwise forward / data gradient / weight gradient on the tensor cores with TF32 operands.  Against
+    the fp32 FMA kernels the error must sit at the TF32 rounding level (2^-11 per operand, averaged over the contraction), well
+    above fp32 noise (so the tensor-core kernels really ran) and below 3e-3 of the tensor's absmax; the mode is process-wide and
+    is restored."""
+    from fscnn_b200 import train_ops
+    g = torch.Generator(device='cpu').manual_seed(11)
+    results = {}
+    try:
+        for mode in ('fp32', 'tf32'):
+            train_ops.set_matmul_precision(mode)
+            assert train_ops.get_matmul_precision() == mode
+            outs = []
+            for n, cin, cout, h, w in [(2, 64, 384, 24, 28), (3, 130, 50, 17, 19), (1, 32, 19, 40, 36)]:      # aligned and ragged
+                gg = torch.Generator(device='cpu').manual_seed(100 + cin)
+                x = torch.randn(n, cin, h, w, generator=gg).to(DEV).requires_grad_(True)
+                wt = (torch.randn(cout, cin, 1, 1, generator=gg) / cin ** 0.5).to(DEV).requires_grad_(True)
+                dy = torch.randn(n, cout, h, w, generator=gg).to(DEV)
+                y = train_ops.pointwise_conv(x, wt)
+                y.backward(dy)
+                outs += [y.detach().cpu().numpy(), x.grad.cpu().numpy(), wt.grad.cpu().numpy()]
+            results[mode] = outs
+    finally:
+        train_ops.set_matmul_precision('fp32')
+    del g
+    for a, b in zip(results['fp32'], results['tf32']):
+        e = rel_err(b, a)
+        assert 1e-6 < e < 3e-3, e
+    with pytest.raises(ValueError):
+        train_ops.set_matmul_precision('fp16')
+
+
+def test_trainer_cuda_graph_replays_match_eager_steps():
+    """Trainer(cuda_graph=True): two eager warm-up steps, then the captured zero_grad + forward + loss + backward replayed; with
+    Dropout switched off the parameters after five steps must agree with an eager Trainer's to float-atomics noise, on inputs that
+    CHANGE from step to step (the graph copies them into its static buffers)."""
+    import fastscnn_oracle as fo
+    from fscnn_b200 import Trainer
+    from models.fast_scnn import FastSCNN
+    nc = 19
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in fo.make_state_dict(nc, True, 9).items()}
+    batches = [(torch.from_numpy(fo.make_input(2, 96, 128, 20 + i)).to(DEV), torch.from_numpy(fo.make_labels(2, 96, 128, nc, 40 + i)).to(DEV))
+               for i in range(5)]
+    trainers = []
+    for use_graph in (False, True):
+        m = FastSCNN(nc, aux=True)
+        m.load_state_dict(sd)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        # fused_loss=False: deterministic loss kernels on both sides (the fused loss sums its backward with float atomics, and OHEM's pixel
+        # selection amplifies last-bit differences over steps)
+        trainers.append(Trainer(m.to(DEV).train(), base_lr=0.01, nepochs=1, iters_per_epoch=10, cuda_graph=use_graph, graph_warmup=2,
+                                fused_loss=False))
+    losses = [[], []]
+    for x, t in batches:
+        for k, tr in enumerate(trainers):
+            losses[k].append(float(tr.step(x, t)))
+    assert trainers[1]._graph is not None
+    np.testing.assert_allclose(losses[1], losses[0], rtol=2e-4)
+    for (k, a), (_, b) in zip(trainers[0].model.named_parameters(), trainers[1].model.named_parameters()):
+        assert rel_err(b.detach().cpu().numpy(), a.detach().cpu().numpy()) < 2e-4, k
+    for (k, a), (_, b) in zip(trainers[0].model.named_buffers(), trainers[1].model.named_buffers()):
+        assert rel_err(b.detach().float().cpu().numpy(), a.detach().float().cpu().numpy()) < 2e-4, k
+
+
+def test_dropout_step_counter_changes_the_mask():
+    """The device step counter behind CUDA-graph replays: same seed + same counter = same mask, a bumped counter = a new mask with the
+    same keep rate, and the backward regenerates the forward's mask."""
+    from fscnn_b200 import train_ops
+    x = torch.ones(4, 8, 32, 32, device=DEV, requires_grad=True)
+    counter = torch.zeros(1, dtype=torch.int64, device=DEV)
+    train_ops.set_dropout_step_counter(counter)
+    try:
+        a = train_ops.dropout(x, 0.25, True, seed=123)
+        b = train_ops.dropout(x, 0.25, True, seed=123)
+        counter += 1
+        c = train_ops.dropout(x, 0.25, True, seed=123)
+        c.sum().backward()
+    finally:
+        train_ops.set_dropout_step_counter(None)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(float((c != 0).float().mean()) - 0.75) < 0.02
+    assert torch.equal(x.grad, c.detach())
+    with pytest.raises(ValueError):
+        train_ops.set_dropout_step_counter(torch.zeros(1))

@@ -1,6 +1,6 @@
 """Per-kernel device time of one training step (BASELINE config 5) from the CUPTI activity trace (torch.profiler: kernels run
 back to back as in a real step, unlike the serialised cold-cache ncu launch list).
-    python tools/train_kernel_times.py [batch=16] [crop=768] [steps=3]"""
+    python tools/train_kernel_times.py [batch=16] [crop=768] [steps=3] [fp32|tf32]"""
 import collections
 import os
 import sys
@@ -18,6 +18,9 @@ from models.fast_scnn import FastSCNN
 tb = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 crop = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+if len(sys.argv) > 4:
+    from fscnn_b200 import train_ops
+    train_ops.set_matmul_precision(sys.argv[4])
 dev = torch.device('cuda', 0)
 m = FastSCNN(19, aux=True).train()
 bench.init_recipe_d2(m, 3)
