@@ -64,33 +64,39 @@ constexpr int kDwRows = 32;
 constexpr unsigned int kFull = 0xffffffffu;
 struct Row3 { float l, m, r; };
 
-// stride 1: the values at columns ox - 1, ox, ox + 1 of row iy (iy is warp-uniform)
+// stride 1: the values at columns ox - 1, ox, ox + 1 of row iy.  Branch-free (out-of-range rows read nothing and give zeros through
+// predicated loads), so the loads of an unrolled walk are all issued before the first one is needed.
 __device__ __forceinline__ Row3 dw_row1(const float* __restrict__ p, int iy, int H, int W, int ox, int lane) {
-    Row3 v{0.f, 0.f, 0.f};
-    if (iy < 0 || iy >= H) return v;
-    const float* r = p + (long long)iy * W;
-    v.m = ox < W ? __ldg(r + ox) : 0.f;
+    const bool rok = (unsigned)iy < (unsigned)H;
+    const float* r = p + (long long)(rok ? iy : 0) * W;
+    Row3 v;
+    v.m = (rok && ox < W) ? __ldg(r + ox) : 0.f;
+    float edge = 0.f;                    // lane 0: column ox - 1, lane 31: column ox + 1
+    const int ex = lane == 0 ? ox - 1 : ox + 1;
+    if ((lane == 0 || lane == 31) && rok && ex >= 0 && ex < W) edge = __ldg(r + ex);
     v.l = __shfl_up_sync(kFull, v.m, 1);
     v.r = __shfl_down_sync(kFull, v.m, 1);
-    if (lane == 0) v.l = ox > 0 ? __ldg(r + ox - 1) : 0.f;
-    if (lane == 31) v.r = ox + 1 < W ? __ldg(r + ox + 1) : 0.f;
+    if (lane == 0) v.l = edge;
+    if (lane == 31) v.r = edge;
     return v;
 }
 // stride 2: the values at columns 2 ox - 1, 2 ox, 2 ox + 1 of row iy
 __device__ __forceinline__ Row3 dw_row2(const float* __restrict__ p, int iy, int H, int W, int ox, int lane, bool vec2) {
-    Row3 v{0.f, 0.f, 0.f};
-    if (iy < 0 || iy >= H) return v;
-    const float* r = p + (long long)iy * W;
+    const bool rok = (unsigned)iy < (unsigned)H;
+    const float* r = p + (long long)(rok ? iy : 0) * W;
     const int ix = 2 * ox;
-    if (vec2 && ix + 1 < W) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(r + ix));
+    Row3 v;
+    if (vec2) {                          // warp-uniform; W is even, so ix < W implies ix + 1 < W
+        const float2 t = (rok && ix < W) ? __ldg(reinterpret_cast<const float2*>(r + ix)) : make_float2(0.f, 0.f);
         v.m = t.x; v.r = t.y;
     } else {
-        v.m = ix < W ? __ldg(r + ix) : 0.f;
-        v.r = ix + 1 < W ? __ldg(r + ix + 1) : 0.f;
+        v.m = (rok && ix < W) ? __ldg(r + ix) : 0.f;
+        v.r = (rok && ix + 1 < W) ? __ldg(r + ix + 1) : 0.f;
     }
+    float edge = 0.f;
+    if (lane == 0 && rok && ix > 0 && ix - 1 < W) edge = __ldg(r + ix - 1);
     v.l = __shfl_up_sync(kFull, v.r, 1);
-    if (lane == 0) v.l = ix > 0 ? __ldg(r + ix - 1) : 0.f;
+    if (lane == 0) v.l = edge;
     return v;
 }
 __device__ __forceinline__ float dot9(const Row3& a, const Row3& b, const Row3& c, const float (&k)[9]) {
@@ -153,7 +159,7 @@ dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* _
             }
         } else {
             Row3 a = dw_row2(xp, 2 * oy0 - 1, H, W, ox, lane, vec2);
-#pragma unroll 2
+#pragma unroll 4
             for (int oy = oy0; oy < oy1; ++oy) {
                 const Row3 b = dw_row2(xp, 2 * oy, H, W, ox, lane, vec2), cc = dw_row2(xp, 2 * oy + 1, H, W, ox, lane, vec2);
                 const float o = dot9(a, b, cc, k);
@@ -184,11 +190,11 @@ dw_bwd1_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
         Row3 ga = dw_row1(gp, oy0 - 1, H, W, ox, lane), gb = dw_row1(gp, oy0, H, W, ox, lane);
         Row3 xa{0.f, 0.f, 0.f}, xb{0.f, 0.f, 0.f};
         if (DWG) { xa = dw_row1(xp, oy0 - 1, H, W, ox, lane); xb = dw_row1(xp, oy0, H, W, ox, lane); }
-#pragma unroll 2
+#pragma unroll 4
         for (int oy = oy0; oy < oy1; ++oy) {
             Row3 gc{0.f, 0.f, 0.f}, xc{0.f, 0.f, 0.f};
             if (DX) gc = dw_row1(gp, oy + 1, H, W, ox, lane);
-            else if (oy + 1 < H) gc.m = ox < W ? __ldg(gp + (long long)(oy + 1) * W + ox) : 0.f;
+            else gc.m = (oy + 1 < H && ox < W) ? __ldg(gp + (long long)min(oy + 1, H - 1) * W + ox) : 0.f;
             if (DWG) xc = dw_row1(xp, oy + 1, H, W, ox, lane);
             if (DX && ox < W) dx[plane * H * W + (long long)oy * W + ox] = dot9(ga, gb, gc, k);
             if (DWG) outer9(gb.m, xa, xb, xc, acc);
@@ -217,16 +223,17 @@ dw_bwd2_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, f
         const float* gp = dy + plane * Ho * Wo;
         float* dp = dx + plane * H * W;
         auto row = [&](int oy, float& d, float& dn) {
-            d = dn = 0.f;
-            if (oy >= Ho) return;
-            const float* r = gp + (long long)oy * Wo;
-            d = ox < Wo ? __ldg(r + ox) : 0.f;
+            const bool rok = oy < Ho;
+            const float* r = gp + (long long)(rok ? oy : 0) * Wo;
+            d = (rok && ox < Wo) ? __ldg(r + ox) : 0.f;
+            float edge = 0.f;
+            if (lane == 31 && rok && ox + 1 < Wo) edge = __ldg(r + ox + 1);
             dn = __shfl_down_sync(kFull, d, 1);
-            if (lane == 31) dn = ox + 1 < Wo ? __ldg(r + ox + 1) : 0.f;
+            if (lane == 31) dn = edge;
         };
         float d, dn;
         row(oy0, d, dn);
-#pragma unroll 2
+#pragma unroll 4
         for (int oy = oy0; oy < oy1; ++oy) {
             float nd, ndn;
             row(oy + 1, nd, ndn);
@@ -265,7 +272,7 @@ dw_bwd2_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy,
         const float* xp = x + plane * H * W;
         const float* gp = dy + plane * Ho * Wo;
         Row3 a = dw_row2(xp, 2 * oy0 - 1, H, W, ox, lane, vec2);
-#pragma unroll 2
+#pragma unroll 4
         for (int oy = oy0; oy < oy1; ++oy) {
             const Row3 b = dw_row2(xp, 2 * oy, H, W, ox, lane, vec2), cc = dw_row2(xp, 2 * oy + 1, H, W, ox, lane, vec2);
             const float g = ox < Wo ? __ldg(gp + (long long)oy * Wo + ox) : 0.f;
@@ -1303,7 +1310,7 @@ ohem_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__
 // corner sums straight into dlow (red.global.add.f32; summation order is not deterministic): no shared memory, ~8x fewer
 // reductions and atomics than one per row.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kStripRows = 32;
+constexpr int kStripRows = 32, kStripAhead = 4;
 
 template <int CT>
 struct UpRows {
@@ -1366,14 +1373,22 @@ ohem_strip_prob_kernel(const float* __restrict__ low, const long long* __restric
         UpRows<CT> rows;
         rows.y0 = rows.y1 = -1;
         const int yend = min(g.H, yb + kStripRows);
-        for (int y = yb; y < yend; ++y) {
+        for (int yq = yb; yq < yend; yq += kStripAhead) {
+        long long labs[kStripAhead];          // the labels of kStripAhead rows are requested before the first one is used
+#pragma unroll
+        for (int j = 0; j < kStripAhead; ++j)
+            labs[j] = (x < g.W && yq + j < yend) ? __ldg(label + ((long long)n * g.H + yq + j) * g.W + x) : ignore;
+#pragma unroll
+        for (int j = 0; j < kStripAhead; ++j) {
+            const int y = yq + j;
+            if (y >= yend) break;
             int y0, y1;
             float ly;
             ac_coord(y, g.scy, g.hl, y0, y1, ly);
             rows.advance(lp, g, y0, y1, x0, x1, lx);
             if (x >= g.W) continue;
             const long long i = ((long long)n * g.H + y) * g.W + x;
-            const long long lab = label[i];
+            const long long lab = labs[j];
             float out = __uint_as_float(0x7f800000u);
             if (lab != ignore) {
                 valid += 1;
@@ -1390,6 +1405,7 @@ ohem_strip_prob_kernel(const float* __restrict__ low, const long long* __restric
                 out = el / sum;
             }
             prob[i] = out;
+        }
         }
     }
     valid = (unsigned int)warp_sumf((float)valid);
@@ -1418,14 +1434,22 @@ ohem_strip_loss_kernel(const float* __restrict__ low, const long long* __restric
         UpRows<CT> rows;
         rows.y0 = rows.y1 = -1;
         const int yend = min(g.H, yb + kStripRows);
-        for (int y = yb; y < yend; ++y) {
-            const long long i = ((long long)n * g.H + y) * g.W + x;
-            long long lab = ignore;
-            bool kept = false;
-            if (x < g.W) {
-                lab = label[i];
-                kept = lab != ignore && (keep_all || prob[i] <= thr);
-            }
+        for (int yq = yb; yq < yend; yq += kStripAhead) {
+        long long labs[kStripAhead];
+        float prs[kStripAhead];
+#pragma unroll
+        for (int j = 0; j < kStripAhead; ++j) {
+            const bool in = x < g.W && yq + j < yend;
+            const long long i = ((long long)n * g.H + yq + j) * g.W + x;
+            labs[j] = in ? __ldg(label + i) : ignore;
+            prs[j] = in ? __ldg(prob + i) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kStripAhead; ++j) {
+            const int y = yq + j;
+            if (y >= yend) break;
+            const long long lab = labs[j];
+            const bool kept = lab != ignore && (keep_all || prs[j] <= thr);
             if (__ballot_sync(0xffffffffu, kept) == 0u) continue;
             int y0, y1;
             float ly;
@@ -1445,6 +1469,7 @@ ohem_strip_loss_kernel(const float* __restrict__ low, const long long* __restric
             const float w = weight ? __ldg(weight + lab) : 1.f;
             acc[0] += (double)w * (double)nll;
             acc[1] += (double)w;
+        }
         }
     }
     block_sum<2>(acc, sm);
@@ -1510,14 +1535,22 @@ ohem_strip_grad_kernel(const float* __restrict__ low, const long long* __restric
             }
         };
         const int yend = min(g.H, yb + kStripRows);
-        for (int y = yb; y < yend; ++y) {
-            const long long i = ((long long)n * g.H + y) * g.W + x;
-            long long lab = ignore;
-            bool kept = false;
-            if (x < g.W) {
-                lab = label[i];
-                kept = lab != ignore && (keep_all || prob[i] <= thr);
-            }
+        for (int yq = yb; yq < yend; yq += kStripAhead) {
+        long long labs[kStripAhead];
+        float prs[kStripAhead];
+#pragma unroll
+        for (int j = 0; j < kStripAhead; ++j) {
+            const bool in = x < g.W && yq + j < yend;
+            const long long i = ((long long)n * g.H + yq + j) * g.W + x;
+            labs[j] = in ? __ldg(label + i) : ignore;
+            prs[j] = in ? __ldg(prob + i) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kStripAhead; ++j) {
+            const int y = yq + j;
+            if (y >= yend) break;
+            const long long lab = labs[j];
+            const bool kept = lab != ignore && (keep_all || prs[j] <= thr);
             if (__ballot_sync(0xffffffffu, kept) == 0u) continue;
             int y0, y1;
             float ly;
@@ -1540,6 +1573,7 @@ ohem_strip_grad_kernel(const float* __restrict__ low, const long long* __restric
                 a1[c] = fmaf(ly, gc, a1[c]);
             }
         }
+        }
         if (dirty) flush();
     }
 }
@@ -1550,17 +1584,19 @@ ohem_strip_grad_kernel(const float* __restrict__ low, const long long* __restric
 // add + ReLU, and the SGD update
 // ---------------------------------------------------------------------------------------------------------------------
 // cols[n][(ci*9 + ky*3 + kx)][oy*Wo + ox] = x[n][ci][oy*s + ky - pad][ox*s + kx - pad] (0 outside)
+// grid (n * C * 9 column rows, chunks of kEltChunk pixels): the tap of a row is decoded once per CTA, a pixel costs one 32-bit division
 __global__ void __launch_bounds__(kT)
-im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ cols, int C, int H, int W, int Ho, int Wo, int stride, int pad,
-                 long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        const int ox = (int)(i % Wo), oy = (int)((i / Wo) % Ho);
-        const long long r = i / ((long long)Wo * Ho);
-        const int k = (int)(r % (C * 9));
-        const long long n = r / (C * 9);
-        const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ cols, int C, int H, int W, int Ho, int Wo, int stride, int pad) {
+    const int k = blockIdx.x % (C * 9), n = blockIdx.x / (C * 9);
+    const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+    const float* xp = x + ((long long)n * C + ci) * H * W;
+    float* cp = cols + (long long)blockIdx.x * Ho * Wo;
+    const int lo = blockIdx.y * kEltChunk, hi = min(Ho * Wo, lo + kEltChunk);
+#pragma unroll 4
+    for (int p = lo + threadIdx.x; p < hi; p += kT) {
+        const int oy = p / Wo, ox = p - oy * Wo;
         const int iy = oy * stride + ky - pad, ix = ox * stride + kx - pad;
-        cols[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + ((n * C + ci) * H + iy) * W + ix) : 0.f;
+        cp[p] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xp + (long long)iy * W + ix) : 0.f;
     }
 }
 
@@ -1928,8 +1964,7 @@ cudaError_t launch_train_ohem_bwd(const float* logits, const long long* label, c
 // dense 3x3 convolution through im2col: cols [n][cin*9][ho*wo] (caller scratch), then the pointwise GEMMs with cin -> cin*9
 cudaError_t launch_train_im2col(const float* x, float* cols, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s) {
     const int ho = (h + 2 * pad - 3) / stride + 1, wo = (wd + 2 * pad - 3) / stride + 1;
-    const long long total = (long long)n * c * 9 * ho * wo;
-    im2col3x3_kernel<<<grid_for(total), kT, 0, s>>>(x, cols, c, h, wd, ho, wo, stride, pad, total);
+    im2col3x3_kernel<<<dim3(n * c * 9, (ho * wo + kEltChunk - 1) / kEltChunk), kT, 0, s>>>(x, cols, c, h, wd, ho, wo, stride, pad);
     return cudaGetLastError();
 }
 cudaError_t launch_train_col2im(const float* dcols, float* dx, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s) {
