@@ -507,34 +507,51 @@ def run_native_arm(args):
     # ---- BASELINE config 5: one training step (forward + backward + OHEM loss + gradient all-reduce + SGD), crop 768, batch 16/GPU ----
     train = {}
     if not args.no_train:
-        from fscnn_b200 import Trainer
+        from fscnn_b200 import Trainer, train_ops
         torch.cuda.empty_cache()
         tb, crop = 16, 768
-        mt = FastSCNN(nc, aux=True).train()
-        init_recipe_d2(mt, 3)
-        mt.to(dev)
-        trainer = Trainer(mt, base_lr=1e-2, aux_weight=0.4)
         xt = smooth_images(tb, crop, crop, dev, 500 + rank, chunk=16)
         tt = torch.randint(-1, nc, (tb, crop, crop), device=dev, dtype=torch.int64)
-        l0 = float(trainer.step(xt, tt))
-        trainer.step(xt, tt)
-        barrier()
-        tsteps = 3
-        ev0t, ev1t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0t.record()
-        for _ in range(tsteps):
-            last = trainer.step(xt, tt)
-        l1 = float(last)               # device -> host read of the loss, like the reference's loss.item() (train.py:283)
-        ev1t.record()
-        torch.cuda.synchronize()
-        t_ms = max_over_ranks(ev0t.elapsed_time(ev1t)) / tsteps
+
+        def time_trainer(precision, graph, tsteps):
+            mt = FastSCNN(nc, aux=True).train()
+            init_recipe_d2(mt, 3)
+            mt.to(dev)
+            trainer = Trainer(mt, base_lr=1e-2, aux_weight=0.4, cuda_graph=graph, graph_warmup=2, matmul_precision=precision)
+            l0 = float(trainer.step(xt, tt))
+            for _ in range(3):             # the third of these captures the graph (graph mode)
+                trainer.step(xt, tt)
+            barrier()
+            ev0t, ev1t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0t.record()
+            for _ in range(tsteps):
+                last = trainer.step(xt, tt)
+            l1 = float(last)           # device -> host read of the loss, like the reference's loss.item() (train.py:283)
+            ev1t.record()
+            torch.cuda.synchronize()
+            t_ms = max_over_ranks(ev0t.elapsed_time(ev1t)) / tsteps
+            del trainer, mt
+            torch.cuda.empty_cache()
+            return t_ms, l0, l1
+
+        try:
+            eager_ms, _, _ = time_trainer('fp32', False, 3)
+            tf32_ms, _, tf32_l1 = time_trainer('tf32', True, 5)
+            t_ms, l0, l1 = time_trainer('fp32', True, 5)
+        finally:
+            train_ops.set_matmul_precision('fp32')
         train = {'workload': f'train_step_nc{nc}_aux_crop{crop}_b{tb}_per_gpu: forward + backward + MixSoftmaxCrossEntropyOHEMLoss + '
                              'gradient all-reduce + SGD(momentum, weight decay)',
                  'value': tb * world / (t_ms / 1e3), 'unit': UNIT, 'ms_per_step': t_ms, 'n_gpus': world, 'scaling': 'weak', 'dtype': 'f32',
-                 'loss_first_step': l0, 'loss_after_5_steps': l1,
-                 'note': 'first, parity-checked version of the training path: fp32 CUDA-core kernels (csrc/train.cu), no tensor cores or '
-                         'fusion yet; DDP semantics (per-rank BatchNorm, one NCCL all-reduce of the flat 4.6 MB gradient buffer)'}
-        del trainer, mt, xt, tt
+                 'loss_first_step': l0, 'loss_after_9_steps': l1,
+                 'launch_mode': 'CUDA graph of zero_grad + forward + loss + backward, replayed; all-reduce + SGD outside the graph',
+                 'eager_launch_ms_per_step': eager_ms,
+                 'tf32': {'value': tb * world / (tf32_ms / 1e3), 'ms_per_step': tf32_ms, 'loss_after_9_steps': tf32_l1,
+                          'note': 'fscnn_train_set_math(1): TF32 operands on the tensor cores for the pointwise / dense 3x3 contractions '
+                                  '(what cuDNN does under torch allow_tf32, the comparator\'s fp32 line); everything else fp32'},
+                 'note': 'fp32 CUDA kernels (csrc/train.cu) behind autograd wrappers; DDP semantics (per-rank BatchNorm, one NCCL '
+                         'all-reduce of the flat 4.6 MB gradient buffer)'}
+        del xt, tt
         torch.cuda.empty_cache()
 
     # ---- the node's host->device ceiling: plain pinned copies of the e2e buffers, all ranks at once ----

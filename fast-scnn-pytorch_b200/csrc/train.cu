@@ -204,6 +204,107 @@ dw_bwd1_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
     }
 }
 
+// Stride 1, width a multiple of 4 and at most 128, 16-byte aligned planes: a lane owns FOUR adjacent columns (one float4 per row), the
+// W / 4 lanes of a group span the whole row, so the only neighbours a lane needs are its two adjacent lanes' edge values (zero
+// padding at the group's ends), and a warp runs 32 / (W / 4) groups -- row blocks of possibly different planes -- side by side.
+// ~2.4x fewer instructions per pixel than the one-column walk.  `in` is convolved with k (read back to front when flip) into `out`
+// when OUT; DWG accumulates dw[c] += in_centre x window(xin), reduced per group through a shared-memory slab.
+struct Row6 { float l, a, b, c, d, r; };
+__device__ __forceinline__ Row6 dw_row4(const float* __restrict__ p, int iy, int H, int W, int col, bool active, bool first, bool last) {
+    const bool ok = active && (unsigned)iy < (unsigned)H;
+    const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(p + (long long)iy * W + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    Row6 o{0.f, v.x, v.y, v.z, v.w, 0.f};
+    const float l = __shfl_up_sync(kFull, v.w, 1), r = __shfl_down_sync(kFull, v.x, 1);
+    o.l = first ? 0.f : l;
+    o.r = last ? 0.f : r;
+    return o;
+}
+__device__ __forceinline__ float dot3x3(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2,
+                                        const float (&k)[9]) {
+    float acc = 0.f;
+    acc = fmaf(a0, k[0], acc); acc = fmaf(a1, k[1], acc); acc = fmaf(a2, k[2], acc);
+    acc = fmaf(b0, k[3], acc); acc = fmaf(b1, k[4], acc); acc = fmaf(b2, k[5], acc);
+    acc = fmaf(c0, k[6], acc); acc = fmaf(c1, k[7], acc); acc = fmaf(c2, k[8], acc);
+    return acc;
+}
+__device__ __forceinline__ void outer3x3(float g, float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2,
+                                         float (&acc)[9]) {
+    acc[0] = fmaf(g, a0, acc[0]); acc[1] = fmaf(g, a1, acc[1]); acc[2] = fmaf(g, a2, acc[2]);
+    acc[3] = fmaf(g, b0, acc[3]); acc[4] = fmaf(g, b1, acc[4]); acc[5] = fmaf(g, b2, acc[5]);
+    acc[6] = fmaf(g, c0, acc[6]); acc[7] = fmaf(g, c1, acc[7]); acc[8] = fmaf(g, c2, acc[8]);
+}
+
+template <bool OUT, bool DWG>
+__global__ void __launch_bounds__(kT)
+dw_s1v4_kernel(const float* __restrict__ in, const float* __restrict__ xin, const float* __restrict__ w, float* __restrict__ out,
+               double* __restrict__ dwacc, int C, int H, int W, int RB, long long tasks, int flip) {
+    __shared__ float slab[kT / 32][32][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = W >> 2, G = 32 / L, grp = lane / L, j = lane - grp * L;
+    const bool lane_ok = grp < G, first = j == 0, last = j == L - 1;
+    const long long wtasks = (tasks + G - 1) / G;
+    for (long long wt = (long long)blockIdx.x * (kT / 32) + warp; wt < wtasks; wt += (long long)gridDim.x * (kT / 32)) {
+        const long long t = wt * G + grp;
+        const bool active = lane_ok && t < tasks;
+        const long long plane = active ? t / RB : 0;
+        const int oy0 = active ? (int)(t - plane * RB) * kDwRows : 0, oy1 = active ? min(H, oy0 + kDwRows) : 0;
+        const int c = (int)(plane % C), col = 4 * j;
+        float k[9], acc[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { k[i] = OUT ? __ldg(w + c * 9 + (flip ? 8 - i : i)) : 0.f; acc[i] = 0.f; }
+        const float* ip = in + plane * H * W;
+        const float* xp = DWG ? xin + plane * H * W : nullptr;
+        float* op = OUT ? out + plane * H * W : nullptr;
+        Row6 ga = dw_row4(ip, oy0 - 1, H, W, col, active, first, last), gb = dw_row4(ip, oy0, H, W, col, active, first, last);
+        Row6 xa{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, xb = xa;
+        if (DWG) { xa = dw_row4(xp, oy0 - 1, H, W, col, active, first, last); xb = dw_row4(xp, oy0, H, W, col, active, first, last); }
+#pragma unroll 2
+        for (int r = 0; r < kDwRows; ++r) {
+            const int oy = oy0 + r;
+            const bool row_ok = oy < oy1;                       // per group
+            Row6 gc{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, xc = gc;
+            if (OUT) gc = dw_row4(ip, oy + 1, H, W, col, active && row_ok, first, last);
+            else if (active && oy + 1 < oy1 + 1 && oy + 1 < H) {       // only the centre values are needed
+                const float4 v = __ldg(reinterpret_cast<const float4*>(ip + (long long)(oy + 1) * W + col));
+                gc.a = v.x; gc.b = v.y; gc.c = v.z; gc.d = v.w;
+            }
+            if (DWG) xc = dw_row4(xp, oy + 1, H, W, col, active && row_ok, first, last);
+            if (OUT && row_ok) {
+                float4 o;
+                o.x = dot3x3(ga.l, ga.a, ga.b, gb.l, gb.a, gb.b, gc.l, gc.a, gc.b, k);
+                o.y = dot3x3(ga.a, ga.b, ga.c, gb.a, gb.b, gb.c, gc.a, gc.b, gc.c, k);
+                o.z = dot3x3(ga.b, ga.c, ga.d, gb.b, gb.c, gb.d, gc.b, gc.c, gc.d, k);
+                o.w = dot3x3(ga.c, ga.d, ga.r, gb.c, gb.d, gb.r, gc.c, gc.d, gc.r, k);
+                *reinterpret_cast<float4*>(op + (long long)oy * W + col) = o;
+            }
+            if (DWG && row_ok) {
+                outer3x3(gb.a, xa.l, xa.a, xa.b, xb.l, xb.a, xb.b, xc.l, xc.a, xc.b, acc);
+                outer3x3(gb.b, xa.a, xa.b, xa.c, xb.a, xb.b, xb.c, xc.a, xc.b, xc.c, acc);
+                outer3x3(gb.c, xa.b, xa.c, xa.d, xb.b, xb.c, xb.d, xc.b, xc.c, xc.d, acc);
+                outer3x3(gb.d, xa.c, xa.d, xa.r, xb.c, xb.d, xb.r, xc.c, xc.d, xc.r, acc);
+            }
+            ga = gb; gb = gc; xa = xb; xb = xc;
+        }
+        if (DWG) {      // per-group sum through the warp's slab, then 9 double atomics by the group's first lane
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 9; ++i) slab[warp][lane][i] = acc[i];
+            __syncwarp();
+            if (active && first) {
+                double tot[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) tot[i] = 0.0;
+                for (int q = 0; q < L; ++q)
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) tot[i] += (double)slab[warp][lane + q][i];
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+                    if (tot[i] != 0.0) atomicAdd(dwacc + c * 9 + i, tot[i]);
+            }
+        }
+    }
+}
+
 // stride 2 data gradient, lane = dy column ox -> dx columns 2 ox and 2 ox + 1, dy row oy -> dx rows 2 oy and 2 oy + 1:
 //   dx[2oy  ][2ox] = d w11                      dx[2oy  ][2ox+1] = dn w10 + d w12
 //   dx[2oy+1][2ox] = nd w01 + d w21             dx[2oy+1][2ox+1] = ndn w00 + nd w02 + dn w20 + d w22
@@ -1813,8 +1914,26 @@ static bool vec2_ok(int wd, std::initializer_list<const void*> ptrs) {
     return true;
 }
 
+static bool dw_v4_ok(int wd, std::initializer_list<const void*> ptrs) {
+    if ((wd & 3) || wd > 128 || wd < 4) return false;
+    for (const void* p : ptrs)
+        if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+    return true;
+}
+static int dw_v4_grid(long long tasks, int wd) {
+    const int G = 32 / (wd / 4);
+    const long long wtasks = (tasks + G - 1) / G, ctas = (wtasks + kT / 32 - 1) / (kT / 32), cap = (long long)num_sms() * 16;
+    return (int)(ctas < cap ? (ctas > 0 ? ctas : 1) : cap);
+}
+
 cudaError_t launch_train_dw_fwd(const float* x, const float* w, float* y, int n, int c, int h, int wd, int stride, cudaStream_t s) {
     const int ho = (h - 1) / stride + 1, wo = (wd - 1) / stride + 1;
+    if (stride == 1 && dw_v4_ok(wd, {x, y})) {
+        const int rb = (h + kDwRows - 1) / kDwRows;
+        const long long tasks = (long long)n * c * rb;
+        dw_s1v4_kernel<true, false><<<dw_v4_grid(tasks, wd), kT, 0, s>>>(x, nullptr, w, y, nullptr, c, h, wd, rb, tasks, 0);
+        return cudaGetLastError();
+    }
     const DwTasks tk = dw_tasks((long long)n * c, ho, wo);
     if (stride == 2) dw_fwd_kernel<2><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0, vec2_ok(wd, {x}));
     else dw_fwd_kernel<1><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0, 0);
@@ -1832,7 +1951,14 @@ cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy,
     }
     const DwTasks tk = dw_tasks((long long)n * c, ho, wo);
     const int grid = dw_grid(tk);
-    if (stride == 1) {
+    if (stride == 1 && dw_v4_ok(wd, {x, dy, dx ? dx : dy})) {
+        const int rb = (h + kDwRows - 1) / kDwRows;
+        const long long tasks = (long long)n * c * rb;
+        const int g4 = dw_v4_grid(tasks, wd);
+        if (dx && dw) dw_s1v4_kernel<true, true><<<g4, kT, 0, s>>>(dy, x, w, dx, dwacc, c, h, wd, rb, tasks, 1);
+        else if (dx) dw_s1v4_kernel<true, false><<<g4, kT, 0, s>>>(dy, nullptr, w, dx, dwacc, c, h, wd, rb, tasks, 1);
+        else if (dw) dw_s1v4_kernel<false, true><<<g4, kT, 0, s>>>(dy, x, w, nullptr, dwacc, c, h, wd, rb, tasks, 1);
+    } else if (stride == 1) {
         if (dx && dw) dw_bwd1_kernel<true, true><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);
         else if (dx) dw_bwd1_kernel<true, false><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);
         else if (dw) dw_bwd1_kernel<false, true><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);

@@ -253,7 +253,10 @@ def test_trainer_steps_match_torch_sgd():
         opt.step()
     assert losses[2] < losses[0]
     for (k, a), (_, b) in zip(ours.named_parameters(), ref.named_parameters()):
-        assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < 1e-5, k
+        # (1e-4, not fp32 epsilon: the two optimizers round differently by an ulp, and two more steps through batch-statistics
+        # BatchNorm and the OHEM pixel selection amplify that -- measured 1e-5 ... 4e-5 on the small BatchNorm biases; a wrong
+        # momentum / weight-decay / learning-rate rule shows up at 1e-2)
+        assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < 1e-4, k
     ours.eval()                                   # and the trained weights go straight back into the fused inference engine
     with torch.no_grad():
         mask = ours.predict(x)
@@ -366,3 +369,32 @@ def test_dropout_step_counter_changes_the_mask():
     assert torch.equal(x.grad, c.detach())
     with pytest.raises(ValueError):
         train_ops.set_dropout_step_counter(torch.zeros(1))
+
+
+@pytest.mark.parametrize('n,c,h,w,stride', [(3, 24, 24, 24, 1), (2, 16, 40, 48, 1), (2, 8, 33, 128, 1), (2, 8, 30, 132, 1), (2, 12, 37, 41, 1),
+                                            (2, 12, 37, 41, 2), (2, 16, 64, 96, 2)])
+def test_depthwise_kernels_against_torch_and_run_to_run(n, c, h, w, stride):
+    """Every depthwise kernel variant (float4 groups for stride 1 with widths that are multiples of 4 up to 128 -- 6, 12 and 32 lanes
+    per row here --, the one-column walk for everything else, stride 2 with and without 8-byte rows) against torch.nn.functional.conv2d,
+    and twice in a row: outputs and input gradients must be bit-identical between runs, weight gradients (double atomics, rounded to
+    float once) equal to the last bit or one off."""
+    import torch.nn.functional as F
+    from fscnn_b200 import train_ops
+    g = torch.Generator(device='cpu').manual_seed(1000 + h * w + stride)
+    x0 = torch.randn(n, c, h, w, generator=g).to(DEV)
+    w0 = torch.randn(c, 1, 3, 3, generator=g).to(DEV)
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    dy = torch.randn(n, c, ho, wo, generator=g).to(DEV)
+    runs = []
+    for _ in range(2):
+        x, wt = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+        y = train_ops.depthwise_conv3x3(x, wt, stride)
+        y.backward(dy)
+        runs.append((y.detach(), x.grad, wt.grad))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    assert float((runs[0][2] - runs[1][2]).abs().max()) <= 2e-7 * float(runs[0][2].abs().max())
+    xr, wr = x0.double().requires_grad_(True), w0.double().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, stride, 1, 1, c)
+    yr.backward(dy.double())
+    for got, want in zip(runs[0], (yr.detach(), xr.grad, wr.grad)):
+        assert rel_err(got.cpu().numpy(), want.float().cpu().numpy()) < 2e-6
