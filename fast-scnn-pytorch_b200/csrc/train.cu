@@ -80,25 +80,33 @@ __device__ __forceinline__ Row3 dw_row1(const float* __restrict__ p, int iy, int
     if (lane == 31) v.r = edge;
     return v;
 }
-// stride 2: the values at columns 2 ox - 1, 2 ox, 2 ox + 1 of row iy
-__device__ __forceinline__ Row3 dw_row2(const float* __restrict__ p, int iy, int H, int W, int ox, int lane, bool vec2) {
-    const bool rok = (unsigned)iy < (unsigned)H;
+// stride 2: the values at columns 2 ox - 1, 2 ox, 2 ox + 1 of row iy, in two phases so that a kernel can request several rows
+// before the first shuffle needs one of them: raw2_load issues the (predicated) loads, raw2_row builds the triple
+struct Raw2 { float e, o, edge; };
+template <bool VEC2>
+__device__ __forceinline__ Raw2 raw2_load(const float* __restrict__ p, int iy, int H, int W, int ox, int lane, bool want) {
+    const bool rok = want && (unsigned)iy < (unsigned)H;
     const float* r = p + (long long)(rok ? iy : 0) * W;
     const int ix = 2 * ox;
-    Row3 v;
-    if (vec2) {                          // warp-uniform; W is even, so ix < W implies ix + 1 < W
+    Raw2 v;
+    if (VEC2) {                          // W is even, so ix < W implies ix + 1 < W
         const float2 t = (rok && ix < W) ? __ldg(reinterpret_cast<const float2*>(r + ix)) : make_float2(0.f, 0.f);
-        v.m = t.x; v.r = t.y;
+        v.e = t.x; v.o = t.y;
     } else {
-        v.m = (rok && ix < W) ? __ldg(r + ix) : 0.f;
-        v.r = (rok && ix + 1 < W) ? __ldg(r + ix + 1) : 0.f;
+        v.e = (rok && ix < W) ? __ldg(r + ix) : 0.f;
+        v.o = (rok && ix + 1 < W) ? __ldg(r + ix + 1) : 0.f;
     }
-    float edge = 0.f;
-    if (lane == 0 && rok && ix > 0 && ix - 1 < W) edge = __ldg(r + ix - 1);
-    v.l = __shfl_up_sync(kFull, v.r, 1);
-    if (lane == 0) v.l = edge;
+    v.edge = (lane == 0 && rok && ix > 0 && ix - 1 < W) ? __ldg(r + ix - 1) : 0.f;
     return v;
 }
+__device__ __forceinline__ Row3 raw2_row(const Raw2& v, int lane) {
+    Row3 o;
+    o.m = v.e; o.r = v.o;
+    o.l = __shfl_up_sync(kFull, v.o, 1);
+    if (lane == 0) o.l = v.edge;
+    return o;
+}
+constexpr int kDw2U = 4;      // output rows per batch of loads in the stride-2 kernels
 __device__ __forceinline__ float dot9(const Row3& a, const Row3& b, const Row3& c, const float (&k)[9]) {
     float acc = 0.f;
     acc = fmaf(a.l, k[0], acc); acc = fmaf(a.m, k[1], acc); acc = fmaf(a.r, k[2], acc);
@@ -133,10 +141,10 @@ struct DwTasks {      // tasks ordered (plane, row block, column block)
 
 // y = depthwise(x) over output rows / columns (Ho, Wo); flip: the taps are read back to front (the stride-1 data gradient is the
 // same correlation of dy with the flipped kernel)
-template <int STRIDE>
+template <int STRIDE, bool VEC2>
 __global__ void __launch_bounds__(kT)
 dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int C, int H, int W, int Ho, int Wo,
-              DwTasks tk, int flip, int vec2) {
+              DwTasks tk, int flip) {
     const int lane = threadIdx.x & 31;
     for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
         long long plane;
@@ -158,13 +166,18 @@ dw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* _
                 a = b; b = cc;
             }
         } else {
-            Row3 a = dw_row2(xp, 2 * oy0 - 1, H, W, ox, lane, vec2);
-#pragma unroll 4
-            for (int oy = oy0; oy < oy1; ++oy) {
-                const Row3 b = dw_row2(xp, 2 * oy, H, W, ox, lane, vec2), cc = dw_row2(xp, 2 * oy + 1, H, W, ox, lane, vec2);
-                const float o = dot9(a, b, cc, k);
-                if (ox < Wo) yp[(long long)oy * Wo + ox] = o;
-                a = cc;
+            Row3 a = raw2_row(raw2_load<VEC2>(xp, 2 * oy0 - 1, H, W, ox, lane, true), lane);
+            for (int oyb = oy0; oyb < oy1; oyb += kDw2U) {
+                Raw2 raw[2 * kDw2U];
+#pragma unroll
+                for (int i = 0; i < 2 * kDw2U; ++i) raw[i] = raw2_load<VEC2>(xp, 2 * oyb + i, H, W, ox, lane, oyb + (i >> 1) < oy1);
+#pragma unroll
+                for (int u = 0; u < kDw2U; ++u) {
+                    const Row3 b = raw2_row(raw[2 * u], lane), cc = raw2_row(raw[2 * u + 1], lane);
+                    const float o = dot9(a, b, cc, k);
+                    if (oyb + u < oy1 && ox < Wo) yp[(long long)(oyb + u) * Wo + ox] = o;
+                    a = cc;
+                }
             }
         }
     }
@@ -309,9 +322,10 @@ dw_s1v4_kernel(const float* __restrict__ in, const float* __restrict__ xin, cons
 //   dx[2oy  ][2ox] = d w11                      dx[2oy  ][2ox+1] = dn w10 + d w12
 //   dx[2oy+1][2ox] = nd w01 + d w21             dx[2oy+1][2ox+1] = ndn w00 + nd w02 + dn w20 + d w22
 // with d = dy[oy][ox], dn = dy[oy][ox+1], nd / ndn the same in row oy + 1 (zeros outside)
+template <bool VEC2>
 __global__ void __launch_bounds__(kT)
 dw_bwd2_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int C, int H, int W, int Ho,
-                    int Wo, DwTasks tk, int vec2) {
+                    int Wo, DwTasks tk) {
     const int lane = threadIdx.x & 31;
     for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
         long long plane;
@@ -323,44 +337,60 @@ dw_bwd2_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, f
         for (int i = 0; i < 9; ++i) k[i] = __ldg(w + c * 9 + i);
         const float* gp = dy + plane * Ho * Wo;
         float* dp = dx + plane * H * W;
-        auto row = [&](int oy, float& d, float& dn) {
-            const bool rok = oy < Ho;
+        // phase 1 of a dy row: its value and lane 31's right neighbour; phase 2: the neighbour of every lane
+        auto load = [&](int oy, bool want, float& d, float& edge) {
+            const bool rok = want && oy < Ho;
             const float* r = gp + (long long)(rok ? oy : 0) * Wo;
             d = (rok && ox < Wo) ? __ldg(r + ox) : 0.f;
-            float edge = 0.f;
-            if (lane == 31 && rok && ox + 1 < Wo) edge = __ldg(r + ox + 1);
-            dn = __shfl_down_sync(kFull, d, 1);
-            if (lane == 31) dn = edge;
+            edge = (lane == 31 && rok && ox + 1 < Wo) ? __ldg(r + ox + 1) : 0.f;
+        };
+        auto right = [&](float d, float edge) {
+            const float dn = __shfl_down_sync(kFull, d, 1);
+            return lane == 31 ? edge : dn;
         };
         float d, dn;
-        row(oy0, d, dn);
-#pragma unroll 4
-        for (int oy = oy0; oy < oy1; ++oy) {
-            float nd, ndn;
-            row(oy + 1, nd, ndn);
-            const int iy = 2 * oy, ix = 2 * ox;
-            const float e0 = d * k[4], e1 = fmaf(dn, k[3], d * k[5]);
-            const float o0 = fmaf(nd, k[1], d * k[7]), o1 = fmaf(ndn, k[0], fmaf(nd, k[2], fmaf(dn, k[6], d * k[8])));
-            if (vec2 && ix + 1 < W) {
-                *reinterpret_cast<float2*>(dp + (long long)iy * W + ix) = make_float2(e0, e1);
-                if (iy + 1 < H) *reinterpret_cast<float2*>(dp + (long long)(iy + 1) * W + ix) = make_float2(o0, o1);
-            } else {
-                if (ix < W) dp[(long long)iy * W + ix] = e0;
-                if (ix + 1 < W) dp[(long long)iy * W + ix + 1] = e1;
-                if (iy + 1 < H) {
-                    if (ix < W) dp[(long long)(iy + 1) * W + ix] = o0;
-                    if (ix + 1 < W) dp[(long long)(iy + 1) * W + ix + 1] = o1;
+        {
+            float e0;
+            load(oy0, true, d, e0);
+            dn = right(d, e0);
+        }
+        for (int oyb = oy0; oyb < oy1; oyb += kDw2U) {
+            float rd[kDw2U], re[kDw2U];
+#pragma unroll
+            for (int u = 0; u < kDw2U; ++u) load(oyb + u + 1, oyb + u < oy1, rd[u], re[u]);
+#pragma unroll
+            for (int u = 0; u < kDw2U; ++u) {
+                const int oy = oyb + u;
+                const float nd = rd[u], ndn = right(rd[u], re[u]);
+                const int iy = 2 * oy, ix = 2 * ox;
+                const float e0 = d * k[4], e1 = fmaf(dn, k[3], d * k[5]);
+                const float o0 = fmaf(nd, k[1], d * k[7]), o1 = fmaf(ndn, k[0], fmaf(nd, k[2], fmaf(dn, k[6], d * k[8])));
+                if (oy < oy1) {
+                    if (VEC2) {
+                        if (ix < W) {
+                            *reinterpret_cast<float2*>(dp + (long long)iy * W + ix) = make_float2(e0, e1);
+                            if (iy + 1 < H) *reinterpret_cast<float2*>(dp + (long long)(iy + 1) * W + ix) = make_float2(o0, o1);
+                        }
+                    } else {
+                        if (ix < W) dp[(long long)iy * W + ix] = e0;
+                        if (ix + 1 < W) dp[(long long)iy * W + ix + 1] = e1;
+                        if (iy + 1 < H) {
+                            if (ix < W) dp[(long long)(iy + 1) * W + ix] = o0;
+                            if (ix + 1 < W) dp[(long long)(iy + 1) * W + ix + 1] = o1;
+                        }
+                    }
                 }
+                d = nd; dn = ndn;
             }
-            d = nd; dn = ndn;
         }
     }
 }
 
 // stride 2 weight gradient: the forward's walk with dy[oy][ox] against the 3 x 3 input window
+template <bool VEC2>
 __global__ void __launch_bounds__(kT)
 dw_bwd2_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ dwacc, int C, int H, int W,
-                      int Ho, int Wo, DwTasks tk, int vec2) {
+                      int Ho, int Wo, DwTasks tk) {
     const int lane = threadIdx.x & 31;
     for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
         long long plane;
@@ -372,13 +402,20 @@ dw_bwd2_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy,
         for (int i = 0; i < 9; ++i) acc[i] = 0.f;
         const float* xp = x + plane * H * W;
         const float* gp = dy + plane * Ho * Wo;
-        Row3 a = dw_row2(xp, 2 * oy0 - 1, H, W, ox, lane, vec2);
-#pragma unroll 4
-        for (int oy = oy0; oy < oy1; ++oy) {
-            const Row3 b = dw_row2(xp, 2 * oy, H, W, ox, lane, vec2), cc = dw_row2(xp, 2 * oy + 1, H, W, ox, lane, vec2);
-            const float g = ox < Wo ? __ldg(gp + (long long)oy * Wo + ox) : 0.f;
-            outer9(g, a, b, cc, acc);
-            a = cc;
+        Row3 a = raw2_row(raw2_load<VEC2>(xp, 2 * oy0 - 1, H, W, ox, lane, true), lane);
+        for (int oyb = oy0; oyb < oy1; oyb += kDw2U) {
+            Raw2 raw[2 * kDw2U];
+            float g[kDw2U];
+#pragma unroll
+            for (int i = 0; i < 2 * kDw2U; ++i) raw[i] = raw2_load<VEC2>(xp, 2 * oyb + i, H, W, ox, lane, oyb + (i >> 1) < oy1);
+#pragma unroll
+            for (int u = 0; u < kDw2U; ++u) g[u] = (oyb + u < oy1 && ox < Wo) ? __ldg(gp + (long long)(oyb + u) * Wo + ox) : 0.f;
+#pragma unroll
+            for (int u = 0; u < kDw2U; ++u) {
+                const Row3 b = raw2_row(raw[2 * u], lane), cc = raw2_row(raw[2 * u + 1], lane);
+                outer9(g[u], a, b, cc, acc);
+                a = cc;
+            }
         }
         dw_flush(acc, dwacc, c, lane);
     }
@@ -1937,8 +1974,9 @@ cudaError_t launch_train_dw_fwd(const float* x, const float* w, float* y, int n,
         return cudaGetLastError();
     }
     const DwTasks tk = dw_tasks((long long)n * c, ho, wo);
-    if (stride == 2) dw_fwd_kernel<2><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0, vec2_ok(wd, {x}));
-    else dw_fwd_kernel<1><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0, 0);
+    if (stride == 2 && vec2_ok(wd, {x})) dw_fwd_kernel<2, true><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0);
+    else if (stride == 2) dw_fwd_kernel<2, false><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0);
+    else dw_fwd_kernel<1, false><<<dw_grid(tk), kT, 0, s>>>(x, w, y, c, h, wd, ho, wo, tk, 0);
     return cudaGetLastError();
 }
 
@@ -1965,8 +2003,10 @@ cudaError_t launch_train_dw_bwd(const float* x, const float* w, const float* dy,
         else if (dx) dw_bwd1_kernel<true, false><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);
         else if (dw) dw_bwd1_kernel<false, true><<<grid, kT, 0, s>>>(x, w, dy, dx, dwacc, c, h, wd, tk);
     } else {
-        if (dx) dw_bwd2_data_kernel<<<grid, kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, tk, vec2_ok(wd, {dx}));
-        if (dw) dw_bwd2_weight_kernel<<<grid, kT, 0, s>>>(x, dy, dwacc, c, h, wd, ho, wo, tk, vec2_ok(wd, {x}));
+        if (dx && vec2_ok(wd, {dx})) dw_bwd2_data_kernel<true><<<grid, kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, tk);
+        else if (dx) dw_bwd2_data_kernel<false><<<grid, kT, 0, s>>>(dy, w, dx, c, h, wd, ho, wo, tk);
+        if (dw && vec2_ok(wd, {x})) dw_bwd2_weight_kernel<true><<<grid, kT, 0, s>>>(x, dy, dwacc, c, h, wd, ho, wo, tk);
+        else if (dw) dw_bwd2_weight_kernel<false><<<grid, kT, 0, s>>>(x, dy, dwacc, c, h, wd, ho, wo, tk);
     }
     if (dw) double_to_float_kernel<<<(c * 9 + kT - 1) / kT, kT, 0, s>>>(dwacc, dw, c * 9);
     return cudaGetLastError();
