@@ -223,14 +223,20 @@ dw_bwd1_kernel(const float* __restrict__ x, const float* __restrict__ w, const f
 // ~2.4x fewer instructions per pixel than the one-column walk.  `in` is convolved with k (read back to front when flip) into `out`
 // when OUT; DWG accumulates dw[c] += in_centre x window(xin), reduced per group through a shared-memory slab.
 struct Row6 { float l, a, b, c, d, r; };
-__device__ __forceinline__ Row6 dw_row4(const float* __restrict__ p, int iy, int H, int W, int col, bool active, bool first, bool last) {
-    const bool ok = active && (unsigned)iy < (unsigned)H;
-    const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(p + (long long)iy * W + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+// two phases, so that a kernel can request several rows before the first shuffle needs one of them
+__device__ __forceinline__ float4 raw4_load(const float* __restrict__ p, int iy, int H, int W, int col, bool want) {
+    const bool ok = want && (unsigned)iy < (unsigned)H;
+    return ok ? __ldg(reinterpret_cast<const float4*>(p + (long long)(ok ? iy : 0) * W + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ Row6 raw4_row(const float4& v, bool first, bool last) {
     Row6 o{0.f, v.x, v.y, v.z, v.w, 0.f};
     const float l = __shfl_up_sync(kFull, v.w, 1), r = __shfl_down_sync(kFull, v.x, 1);
     o.l = first ? 0.f : l;
     o.r = last ? 0.f : r;
     return o;
+}
+__device__ __forceinline__ Row6 dw_row4(const float* __restrict__ p, int iy, int H, int W, int col, bool active, bool first, bool last) {
+    return raw4_row(raw4_load(p, iy, H, W, col, active), first, last);
 }
 __device__ __forceinline__ float dot3x3(float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2,
                                         const float (&k)[9]) {
@@ -271,32 +277,38 @@ dw_s1v4_kernel(const float* __restrict__ in, const float* __restrict__ xin, cons
         Row6 ga = dw_row4(ip, oy0 - 1, H, W, col, active, first, last), gb = dw_row4(ip, oy0, H, W, col, active, first, last);
         Row6 xa{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, xb = xa;
         if (DWG) { xa = dw_row4(xp, oy0 - 1, H, W, col, active, first, last); xb = dw_row4(xp, oy0, H, W, col, active, first, last); }
-#pragma unroll 2
-        for (int r = 0; r < kDwRows; ++r) {
-            const int oy = oy0 + r;
-            const bool row_ok = oy < oy1;                       // per group
-            Row6 gc{0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, xc = gc;
-            if (OUT) gc = dw_row4(ip, oy + 1, H, W, col, active && row_ok, first, last);
-            else if (active && oy + 1 < oy1 + 1 && oy + 1 < H) {       // only the centre values are needed
-                const float4 v = __ldg(reinterpret_cast<const float4*>(ip + (long long)(oy + 1) * W + col));
-                gc.a = v.x; gc.b = v.y; gc.c = v.z; gc.d = v.w;
+        constexpr int U = 4;
+        for (int rb = 0; rb < kDwRows; rb += U) {
+            float4 rg[U], rx[U];                                // rows oy + 1 of the next U outputs, requested together
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int oy = oy0 + rb + u;
+                rg[u] = raw4_load(ip, oy + 1, H, W, col, active && oy < oy1);
+                if (DWG) rx[u] = raw4_load(xp, oy + 1, H, W, col, active && oy < oy1);
             }
-            if (DWG) xc = dw_row4(xp, oy + 1, H, W, col, active && row_ok, first, last);
-            if (OUT && row_ok) {
-                float4 o;
-                o.x = dot3x3(ga.l, ga.a, ga.b, gb.l, gb.a, gb.b, gc.l, gc.a, gc.b, k);
-                o.y = dot3x3(ga.a, ga.b, ga.c, gb.a, gb.b, gb.c, gc.a, gc.b, gc.c, k);
-                o.z = dot3x3(ga.b, ga.c, ga.d, gb.b, gb.c, gb.d, gc.b, gc.c, gc.d, k);
-                o.w = dot3x3(ga.c, ga.d, ga.r, gb.c, gb.d, gb.r, gc.c, gc.d, gc.r, k);
-                *reinterpret_cast<float4*>(op + (long long)oy * W + col) = o;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int oy = oy0 + rb + u;
+                const bool row_ok = oy < oy1;                   // per group
+                Row6 gc{0.f, rg[u].x, rg[u].y, rg[u].z, rg[u].w, 0.f}, xc{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (OUT) gc = raw4_row(rg[u], first, last);
+                if (DWG) xc = raw4_row(rx[u], first, last);
+                if (OUT && row_ok) {
+                    float4 o;
+                    o.x = dot3x3(ga.l, ga.a, ga.b, gb.l, gb.a, gb.b, gc.l, gc.a, gc.b, k);
+                    o.y = dot3x3(ga.a, ga.b, ga.c, gb.a, gb.b, gb.c, gc.a, gc.b, gc.c, k);
+                    o.z = dot3x3(ga.b, ga.c, ga.d, gb.b, gb.c, gb.d, gc.b, gc.c, gc.d, k);
+                    o.w = dot3x3(ga.c, ga.d, ga.r, gb.c, gb.d, gb.r, gc.c, gc.d, gc.r, k);
+                    *reinterpret_cast<float4*>(op + (long long)oy * W + col) = o;
+                }
+                if (DWG && row_ok) {
+                    outer3x3(gb.a, xa.l, xa.a, xa.b, xb.l, xb.a, xb.b, xc.l, xc.a, xc.b, acc);
+                    outer3x3(gb.b, xa.a, xa.b, xa.c, xb.a, xb.b, xb.c, xc.a, xc.b, xc.c, acc);
+                    outer3x3(gb.c, xa.b, xa.c, xa.d, xb.b, xb.c, xb.d, xc.b, xc.c, xc.d, acc);
+                    outer3x3(gb.d, xa.c, xa.d, xa.r, xb.c, xb.d, xb.r, xc.c, xc.d, xc.r, acc);
+                }
+                ga = gb; gb = gc; xa = xb; xb = xc;
             }
-            if (DWG && row_ok) {
-                outer3x3(gb.a, xa.l, xa.a, xa.b, xb.l, xb.a, xb.b, xc.l, xc.a, xc.b, acc);
-                outer3x3(gb.b, xa.a, xa.b, xa.c, xb.a, xb.b, xb.c, xc.a, xc.b, xc.c, acc);
-                outer3x3(gb.c, xa.b, xa.c, xa.d, xb.b, xb.c, xb.d, xc.b, xc.c, xc.d, acc);
-                outer3x3(gb.d, xa.c, xa.d, xa.r, xb.c, xb.d, xb.r, xc.c, xc.d, xc.r, acc);
-            }
-            ga = gb; gb = gc; xa = xb; xb = xc;
         }
         if (DWG) {      // per-group sum through the warp's slab, then 9 double atomics by the group's first lane
             __syncwarp();
