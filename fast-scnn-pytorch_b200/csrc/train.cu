@@ -1753,14 +1753,14 @@ im2col3x3_kernel(const float* __restrict__ x, float* __restrict__ cols, int C, i
 }
 
 // dx[n][ci][iy][ix] = sum over the taps that read this pixel of dcols[n][ci*9 + ky*3 + kx][oy*Wo + ox]
+// grid (n * C planes, chunks of kEltChunk input pixels)
 __global__ void __launch_bounds__(kT)
-col2im3x3_kernel(const float* __restrict__ dcols, float* __restrict__ dx, int C, int H, int W, int Ho, int Wo, int stride, int pad,
-                 long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        const int ix = (int)(i % W), iy = (int)((i / W) % H);
-        const long long plane = i / ((long long)W * H);
-        const int ci = (int)(plane % C);
-        const long long n = plane / C;
+col2im3x3_kernel(const float* __restrict__ dcols, float* __restrict__ dx, int C, int H, int W, int Ho, int Wo, int stride, int pad) {
+    const float* dc = dcols + (long long)blockIdx.x * 9 * Ho * Wo;      // rows (n * C + ci) * 9 + tap
+    float* xp = dx + (long long)blockIdx.x * H * W;
+    const int lo = blockIdx.y * kEltChunk, hi = min(H * W, lo + kEltChunk);
+    for (int p = lo + threadIdx.x; p < hi; p += kT) {
+        const int iy = p / W, ix = p - iy * W;
         float acc = 0.f;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -1773,17 +1773,21 @@ col2im3x3_kernel(const float* __restrict__ dcols, float* __restrict__ dx, int C,
                 const int tx = ix + pad - kx;
                 if (tx < 0 || tx % stride) continue;
                 const int ox = tx / stride;
-                if (ox < Wo) acc += __ldg(dcols + ((n * C * 9 + ci * 9 + ky * 3 + kx) * Ho + oy) * Wo + ox);
+                if (ox < Wo) acc += __ldg(dc + ((long long)(ky * 3 + kx) * Ho + oy) * Wo + ox);
             }
         }
-        dx[i] = acc;
+        xp[p] = acc;
     }
 }
 
+// grid (n * C planes, chunks of kEltChunk pixels)
 __global__ void __launch_bounds__(kT)
-bias_add_kernel(float* __restrict__ y, const float* __restrict__ b, int C, int HW, long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT)
-        y[i] += __ldg(b + (int)((i / HW) % C));
+bias_add_kernel(float* __restrict__ y, const float* __restrict__ b, int C, int HW) {
+    const float bv = __ldg(b + blockIdx.x % C);
+    float* yp = y + (long long)blockIdx.x * HW;
+    const int lo = blockIdx.y * kEltChunk, hi = min(HW, lo + kEltChunk);
+#pragma unroll 4
+    for (int p = lo + threadIdx.x; p < hi; p += kT) yp[p] += bv;
 }
 
 // grid (C, S): partial[s][c] = sum of dy over this CTA's share of channel c
@@ -1791,10 +1795,15 @@ __global__ void __launch_bounds__(kT)
 channel_sum_kernel(const float* __restrict__ dy, double* __restrict__ partial, int N, int C, int HW) {
     __shared__ double sm[8];
     const int c = blockIdx.x, S = gridDim.y;
+    const ChanSlice sl = chan_slice(HW, S, blockIdx.y, 1);
     double v[1] = {0.0};
-    const long long per = (long long)N * HW;
-    for (long long i = (long long)blockIdx.y * kT + threadIdx.x; i < per; i += (long long)S * kT)
-        v[0] += (double)__ldg(dy + ((i / HW) * C + c) * HW + i % HW);
+    for (int n = 0; n < N; ++n) {
+        const float* dp = dy + ((long long)n * C + c) * HW;
+        float part = 0.f;
+#pragma unroll 4
+        for (int p = sl.lo + threadIdx.x; p < sl.hi; p += kT) part += __ldg(dp + p);
+        v[0] += (double)part;
+    }
     block_sum<1>(v, sm);
     if (threadIdx.x == 0) partial[(long long)blockIdx.y * C + c] = v[0];
 }
@@ -1818,11 +1827,14 @@ bilinear_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int Hi, 
 // gather form of the backward: every input pixel collects from the output pixels whose 2 x 2 taps include it (found by running
 // the forward's own index computation over the candidate range, so the two passes agree exactly); deterministic, no atomics
 __global__ void __launch_bounds__(kT)
-bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int Hi, int Wi, int Ho, int Wo, long long total) {
+bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int Hi, int Wi, int Ho, int Wo) {      // grid (planes, chunks)
     const float scy = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, scx = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        const int ix = (int)(i % Wi), iy = (int)((i / Wi) % Hi);
-        const float* dp = dy + (i / ((long long)Wi * Hi)) * Ho * Wo;
+    const float* dp = dy + (long long)blockIdx.x * Ho * Wo;
+    const long long obase = (long long)blockIdx.x * Hi * Wi;
+    const int lo = blockIdx.y * kEltChunk, hi = min(Hi * Wi, lo + kEltChunk);
+    for (int pp = lo + threadIdx.x; pp < hi; pp += kT) {
+        const int iy = pp / Wi, ix = pp - iy * Wi;
+        const long long i = obase + pp;
         // output rows that can touch input row iy: floor(scy * oy) in {iy - 1, iy}
         int oy_lo = 0, oy_hi = Ho - 1, ox_lo = 0, ox_hi = Wo - 1;
         if (scy > 0.f) { oy_lo = max(0, (int)floorf((float)(iy - 1) / scy) - 1); oy_hi = min(Ho - 1, (int)ceilf((float)(iy + 1) / scy) + 1); }
@@ -2149,13 +2161,11 @@ cudaError_t launch_train_im2col(const float* x, float* cols, int n, int c, int h
 }
 cudaError_t launch_train_col2im(const float* dcols, float* dx, int n, int c, int h, int wd, int stride, int pad, cudaStream_t s) {
     const int ho = (h + 2 * pad - 3) / stride + 1, wo = (wd + 2 * pad - 3) / stride + 1;
-    const long long total = (long long)n * c * h * wd;
-    col2im3x3_kernel<<<grid_for(total), kT, 0, s>>>(dcols, dx, c, h, wd, ho, wo, stride, pad, total);
+    col2im3x3_kernel<<<dim3(n * c, (h * wd + kEltChunk - 1) / kEltChunk), kT, 0, s>>>(dcols, dx, c, h, wd, ho, wo, stride, pad);
     return cudaGetLastError();
 }
 cudaError_t launch_train_bias_add(float* y, const float* b, int n, int c, int hw, cudaStream_t s) {
-    const long long total = (long long)n * c * hw;
-    bias_add_kernel<<<grid_for(total), kT, 0, s>>>(y, b, c, hw, total);
+    bias_add_kernel<<<dim3(n * c, (hw + kEltChunk - 1) / kEltChunk), kT, 0, s>>>(y, b, c, hw);
     return cudaGetLastError();
 }
 cudaError_t launch_train_bias_grad(const float* dy, float* db, void* ws, int n, int c, int hw, cudaStream_t s) {
@@ -2169,8 +2179,7 @@ cudaError_t launch_train_bilinear(const float* in, float* out, int planes, int h
         const long long total = (long long)planes * ho * wo;
         bilinear_fwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, hi, wi, ho, wo, total);
     } else {      // in = dy [planes][ho][wo], out = dx [planes][hi][wi]
-        const long long total = (long long)planes * hi * wi;
-        bilinear_bwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, hi, wi, ho, wo, total);
+        bilinear_bwd_kernel<<<dim3(planes, (hi * wi + kEltChunk - 1) / kEltChunk), kT, 0, s>>>(in, out, hi, wi, ho, wo);
     }
     return cudaGetLastError();
 }
