@@ -13,6 +13,7 @@
 // torch.autograd of the unmodified reference modules); the tensor-core / fused versions of the eval path's design are the
 // next step of this row and are NOT claimed here.
 #include <cfloat>
+#include <cstdlib>
 #include <initializer_list>
 
 #include "kernels.h"
@@ -2050,7 +2051,16 @@ static void launch_gemm_pix(const GemmArgs& g, dim3 grid, cudaStream_t s) {
     else gemm_pix_mma_kernel<1><<<grid, kT, 0, s>>>(g);
 }
 
+static bool tc_enabled() {
+    static const bool off = getenv("FSCNN_TRAIN_NO_TC") != nullptr;      // A/B switch: keep the mma.sync kernels in TF32 mode
+    return g_train_math == 1 && !off;
+}
+
 cudaError_t launch_train_pw_fwd(const float* x, const float* w, float* y, int n, int cin, int cout, int hw, cudaStream_t s) {
+    if (tc_enabled()) {
+        const cudaError_t e = launch_gemm_pix_tc(w, x, y, cout, hw, cin, n, cin, true, s);
+        if (e != cudaErrorNotSupported) return e;
+    }
     GemmArgs g{w, x, y, cout, hw, cin, 0, cin, 1, (long long)cin * hw, hw, 1, (long long)cout * hw, hw, 1};
     launch_gemm_pix(g, dim3((hw + 127) / 128, (cout + 63) / 64, n), s);
     return cudaGetLastError();
@@ -2059,8 +2069,13 @@ cudaError_t launch_train_pw_fwd(const float* x, const float* w, float* y, int n,
 cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, void* ws, int n, int cin,
                                 int cout, int hw, cudaStream_t s) {
     if (dx) {      // dx[n] = W^T dy[n]
-        GemmArgs g{w, dy, dx, cin, hw, cout, 0, 1, cin, (long long)cout * hw, hw, 1, (long long)cin * hw, hw, 1};
-        launch_gemm_pix(g, dim3((hw + 127) / 128, (cin + 63) / 64, n), s);
+        cudaError_t e = tc_enabled() ? launch_gemm_pix_tc(w, dy, dx, cin, hw, cout, n, cin, false, s) : cudaErrorNotSupported;
+        if (e == cudaErrorNotSupported) {
+            GemmArgs g{w, dy, dx, cin, hw, cout, 0, 1, cin, (long long)cout * hw, hw, 1, (long long)cin * hw, hw, 1};
+            launch_gemm_pix(g, dim3((hw + 127) / 128, (cin + 63) / 64, n), s);
+        } else if (e != cudaSuccess) {
+            return e;
+        }
     }
     if (dw) {      // dW = sum_n dy[n] x[n]^T, split over the pixels of every image: enough CTAs to fill the GPU ~4 times
         const int tiles = ((cin + 63) / 64) * ((cout + 63) / 64), pmax = pw_parts_max(cout, cin);
