@@ -7,16 +7,19 @@
 //   data gradient A(m, k) = W[k][m]    (m contiguous  -> MN-major A operand)
 //   B = x[b] / dy[b]: [k][pixels], pixels contiguous -> MN-major B operand
 //
-// The tensors are fp32 NCHW as autograd hands them over, so operands are staged with 16-byte cp.async straight into the
-// SWIZZLE_NONE canonical layouts (a 16-byte piece = 4 TF32 values = one core-matrix row; out-of-range rows are zero-filled by the
-// copy), three K chunks of 32 in flight per CTA:
-//   K-major  A : piece (row m, k/4)      at (k/4) * 2048 + m * 16                              LBO 2048 (K pieces), SBO 128 (8-row groups)
-//   MN-major A : piece (k, 4 rows m/4)   at (k/8) * 4096 + (m/4) * 128 + (k%8) * 16            LBO 4096 (K groups), SBO 128 (4-row groups)
-//   MN-major B : piece (k, 4 pixels j/4) at (k/8) * 4096 + (j/4) * 128 + (k%8) * 16            the same with pixels for rows
-// One thread issues four MMAs (K = 8 each) per chunk and commits them to the stage's mbarrier; the four warps read their TMEM lane
-// quarters back with tcgen05.ld and store rows of 32 pixels.  Two CTAs per SM (96 KB of stages, 128 TMEM columns each) overlap one
-// CTA's epilogue with the other's contraction.  The legacy mma.sync kernels of train.cu (which top out near 77 TFLOP/s on a B200)
-// stay as the path for shapes whose rows are not 16-byte aligned (the stem's 27-row im2col matrix).
+// The tensors are fp32 NCHW as autograd hands them over, so operands are staged with 16-byte cp.async (a piece = 4 TF32 values;
+// out-of-range rows / columns / K tails are zero-filled by the copy) straight into the layouts the tensor core reads:
+//   K-major  A : SWIZZLE_NONE core matrices (8 rows x 16 bytes): piece (row m, k/4) at (k/4) * 2064 + m * 16; LBO 2064, SBO 128
+//   MN-major A / B : MN-major TF32 operands exist only in the SWIZZLE_128B_BASE32B layout (with SWIZZLE_NONE kind::tf32 returns
+//                zeros -- measured; CUTLASS says the same): atoms of 4 k rows x 128 bytes, 32-byte pieces XORed with the row index
+// A CTA (4 warps) walks output tiles of 128 channels x 256 (or 128) pixels with 4 (3) K chunks of 16 (32) in flight; one thread issues
+// the chunk's MMAs (K = 8 each) and commits them to the stage's mbarrier; the accumulator is read back with tcgen05.ld, transposed
+// through the stage the tile's last chunk vacated and stored as rows of 128 contiguous bytes.  Two CTAs per SM overlap one CTA's
+// epilogue with the other's contraction.  Measured on a B200 (config 5, 96 x 96 layers): 3.2-3.7 TB/s of operand + result traffic
+// against 1.9-2.7 for the legacy mma.sync kernels of train.cu, which stay as the path for rows that are not 16-byte aligned (the
+// stem's 27-row im2col matrix) and for the weight gradient.  What the measurements said on the way: storing the accumulator
+// straight from the tcgen05.ld registers (32 rows x 16 bytes per instruction) cost 40-55 % of the kernel; 512-byte operand rows
+// (128-pixel tiles) reach 2.7 TB/s, 1 KB rows 3.2 -- DRAM page locality, not the tensor core, sets the pace.
 #include <cstdint>
 #include <cstdlib>
 
@@ -27,9 +30,20 @@ namespace fscnn {
 
 namespace {
 constexpr int kTcT = 128;                         // 4 warps = the four TMEM lane quarters
-constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32, kTcST = 3;
-constexpr int kTcABytes = kTcBM * kTcBK * 4, kTcBBytes = kTcBK * kTcBN * 4, kTcStage = kTcABytes + kTcBBytes;
-constexpr size_t kTcSmem = (size_t)kTcST * kTcStage + 1024;      // + room to align the stages to 1024 bytes (swizzle atoms)
+constexpr int kTcBM = 128;
+constexpr int kTcALbo = 2048 + 16;                  // K-major A: K pieces 2064 bytes apart, so the pieces of a row land in different bank groups
+// Two tilings: 256 pixels x 16 input channels per stage, 4 stages (1 KB contiguous per operand row: DRAM pages are used twice as
+// well as with 512-byte rows -- 3.2 instead of 2.7 TB/s on the 96 x 96 layers) and 128 x 32, 3 stages, for the small planes (24 x 24 =
+// 576 pixels, where a 256-wide tile wastes a quarter of the work).  Either way a stage holds 16 KB of B and <= 16.5 KB of A.
+template <int BN_>
+struct TcCfg {
+    static constexpr int BN = BN_, BK = BN_ == 256 ? 16 : 32, ST = BN_ == 256 ? 4 : 3;
+    static constexpr int BBytes = BK * BN * 4;                                  // 16 KB, 1024-byte aligned swizzle atoms
+    static constexpr int ABytes = (BK / 4) * kTcALbo;                           // >= the MN-major form (BK x 128 x 4 bytes)
+    static constexpr int Stage = (BBytes + ABytes + 1023) / 1024 * 1024;
+    static constexpr int MnLbo = (BK / 4) * 512;                                // MN atoms (32 values) one column of K atoms apart
+    static constexpr size_t Smem = (size_t)ST * Stage + 1024;                   // + room to align the stages to 1024 bytes
+};
 
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n, bool a_mn, bool b_mn) {
     // c_format F32 (1) at bit 4, a_format / b_format TF32 (2) at bits 7 / 10, a_major / b_major at bits 15 / 16, N >> 3 at 17, M >> 4 at 24
@@ -50,9 +64,9 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
 // kind::tf32 return zeros -- measured): atoms of 4 k rows x 128 bytes (32 values along MN), the 32-byte pieces of a row XORed with
 // the row index (Swizzle<2,5,2> on the byte address).  A [32 k][128 mn] chunk is 8 x 4 atoms: K atoms 512 bytes apart (SBO), MN
 // atoms 4096 bytes apart (LBO).  `g4` = index of the 16-byte piece along MN (4 values).
-__device__ __forceinline__ uint32_t mn_piece_off(int k, int g4) {
+__device__ __forceinline__ uint32_t mn_piece_off(int k, int g4, int mn_lbo) {
     const int r = k & 3, c32 = (g4 >> 1) & 3;
-    return (uint32_t)((g4 >> 3) * 4096 + (k >> 2) * 512 + r * 128 + ((c32 ^ r) << 5) + (g4 & 1) * 16);
+    return (uint32_t)((g4 >> 3) * mn_lbo + (k >> 2) * 512 + r * 128 + ((c32 ^ r) << 5) + (g4 & 1) * 16);
 }
 __device__ __forceinline__ uint64_t make_smem_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
@@ -68,14 +82,16 @@ struct TcGemmArgs {
     const float *A, *B;
     float* C;
     int M, N, K, nb;                 // output channels, pixels per image, input channels, images
-    uint32_t idesc_xor;              // debug
+    uint32_t dbg;                    // bit 1: skip the epilogue's global stores (timing experiments); 0 in production
     long long lda;                   // A_KMAJOR: row stride of W (elements); else: stride between k rows of W
     long long sBb, sCb;              // per-image strides of B and C; their row stride is N
 };
 
-template <bool A_KMAJOR>
+template <bool A_KMAJOR, int BN>
 __global__ void __launch_bounds__(kTcT, 2)
 gemm_pix_tc_kernel(TcGemmArgs g) {
+    using Cf = TcCfg<BN>;
+    constexpr int kTcBN = Cf::BN, kTcBK = Cf::BK, kTcST = Cf::ST, kTcStage = Cf::Stage, kTcBBytes = Cf::BBytes, kTcMnLbo = Cf::MnLbo;
     extern __shared__ __align__(128) uint8_t tc_smem[];
     __shared__ __align__(8) uint64_t bar_free[kTcST], bar_acc;
     __shared__ uint32_t tmem_base_s;
@@ -98,7 +114,7 @@ gemm_pix_tc_kernel(TcGemmArgs g) {
         mbar_init(&bar_acc, 1);
         fence_mbar_init();
     }
-    if (warp == 0) { tmem_alloc(&tmem_base_s, 128); tmem_relinquish(); }
+    if (warp == 0) { tmem_alloc(&tmem_base_s, kTcBN); tmem_relinquish(); }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -108,32 +124,32 @@ gemm_pix_tc_kernel(TcGemmArgs g) {
         const int tl = gc / nchunks, chunk = gc - tl * nchunks;
         int b, m0, j0;
         tile_at(tl, b, m0, j0);
-        const uint32_t sA = s0 + (gc % kTcST) * kTcStage, sB = sA + kTcABytes;
+        const uint32_t sB = s0 + (gc % kTcST) * kTcStage, sA = sB + kTcBBytes;
         const int k0 = chunk * kTcBK;
         const float* Bp = g.B + b * g.sBb;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < kTcBM * kTcBK / 4 / kTcT; ++r) {
             const int i = tid + r * kTcT;
-            if (A_KMAJOR) {                  // piece (kq = k / 4, row m): lanes along m -> conflict-free shared-memory writes
-                const int m = i & 127, kq = i >> 7;
+            if (A_KMAJOR) {                  // piece (row m, kq = k / 4): BK / 4 lanes read the contiguous bytes of a row's chunk
+                const int kq = i & (kTcBK / 4 - 1), m = i / (kTcBK / 4);
                 const bool ok = m0 + m < g.M && k0 + 4 * kq < g.K;
-                cp_async16z(sA + kq * 2048 + m * 16, ok ? g.A + (long long)(m0 + m) * g.lda + k0 + 4 * kq : g.A, ok);
+                cp_async16z(sA + kq * kTcALbo + m * 16, ok ? g.A + (long long)(m0 + m) * g.lda + k0 + 4 * kq : g.A, ok);
             } else {                         // piece (k, 4 rows mg = m / 4): a warp covers one k row's 128 rows = 512 contiguous bytes
                 const int mg = i & 31, k = i >> 5;
                 const bool ok = k0 + k < g.K && m0 + 4 * mg < g.M;
-                cp_async16z(sA + mn_piece_off(k, mg), ok ? g.A + (long long)(k0 + k) * g.lda + m0 + 4 * mg : g.A, ok);
+                cp_async16z(sA + mn_piece_off(k, mg, kTcMnLbo), ok ? g.A + (long long)(k0 + k) * g.lda + m0 + 4 * mg : g.A, ok);
             }
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < kTcBN * kTcBK / 4 / kTcT; ++r) {
             const int i = tid + r * kTcT;
-            const int jg = i & 31, k = i >> 5;
+            const int jg = i & (kTcBN / 4 - 1), k = i / (kTcBN / 4);
             const bool ok = k0 + k < g.K && j0 + 4 * jg < g.N;
-            cp_async16z(sB + mn_piece_off(k, jg), ok ? Bp + (long long)(k0 + k) * g.N + j0 + 4 * jg : Bp, ok);
+            cp_async16z(sB + mn_piece_off(k, jg, kTcMnLbo), ok ? Bp + (long long)(k0 + k) * g.N + j0 + 4 * jg : Bp, ok);
         }
     };
 
-    const uint32_t idesc = make_idesc_tf32(kTcBM, kTcBN, !A_KMAJOR, true) ^ (g.idesc_xor & ~1u);
+    constexpr uint32_t idesc = make_idesc_tf32(kTcBM, kTcBN, !A_KMAJOR, true);
 #pragma unroll
     for (int s = 0; s < kTcST - 1; ++s) {
         if (s < total) issue(s);
@@ -147,11 +163,11 @@ gemm_pix_tc_kernel(TcGemmArgs g) {
         __syncthreads();
         if (tid == 0) {
             tc_fence_after_sync();
-            const uint32_t sA = s0 + (gc % kTcST) * kTcStage, sB = sA + kTcABytes;
+            const uint32_t sB = s0 + (gc % kTcST) * kTcStage, sA = sB + kTcBBytes;
 #pragma unroll
             for (int j = 0; j < kTcBK / 8; ++j) {
-                const uint32_t lbo = g.idesc_xor & 1u ? 512u : 4096u, sbo = g.idesc_xor & 1u ? 4096u : 512u;      // debug: bit 0 swaps
-                const uint64_t da = A_KMAJOR ? make_smem_desc(sA + j * 2 * 2048, 2048, 128) : make_smem_desc_mn32(sA + j * 1024, lbo, sbo);
+                const uint32_t lbo = kTcMnLbo, sbo = 512u;
+                const uint64_t da = A_KMAJOR ? make_smem_desc(sA + j * 2 * kTcALbo, kTcALbo, 128) : make_smem_desc_mn32(sA + j * 1024, lbo, sbo);
                 const uint64_t db = make_smem_desc_mn32(sB + j * 1024, lbo, sbo);
                 umma_tf32_ss(tmem, da, db, idesc, (chunk | j) != 0);
             }
@@ -169,20 +185,30 @@ gemm_pix_tc_kernel(TcGemmArgs g) {
             tile_at(tl, b, m0, j0);
             mbar_wait(&bar_acc, tl & 1);
             tc_fence_after_sync();
-            const int m = m0 + warp * 32 + lane;
-            float* Cp = g.C + b * g.sCb + (long long)m * g.N + j0;
+            // A lane holds one output row (its TMEM lane) x 32 pixels: stored directly, a warp instruction would touch 32 rows x 16
+            // bytes.  The warp transposes each 32 x 32 block through a 4 KB slab (16-byte pieces XORed with the row, conflict-free)
+            // inside the stage the tile's last chunk just vacated (its MMAs have completed: bar_acc), and writes 4 rows x 128
+            // contiguous bytes per instruction.
+            const uint32_t slab = s0 + (gc % kTcST) * kTcStage + warp * 4096;
+            float* Cb = g.C + b * g.sCb + (long long)(m0 + warp * 32) * g.N + j0;
 #pragma unroll 1
             for (int cb = 0; cb < kTcBN / 32; ++cb) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, r);
                 tmem_ld_wait();
-                if (m < g.M) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (j0 + cb * 32 + 4 * q < g.N)
-                            *reinterpret_cast<float4*>(Cp + cb * 32 + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                                                           __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                for (int q = 0; q < 8; ++q) sts128(slab + lane * 128 + ((q ^ (lane & 7)) << 4), r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+                __syncwarp();
+                if (!(g.dbg & 2u)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + (lane >> 3), q = lane & 7;
+                        const uint4 v = lds128(slab + row * 128 + ((q ^ (row & 7)) << 4));
+                        if (m0 + warp * 32 + row < g.M && j0 + cb * 32 + 4 * q < g.N)
+                            *reinterpret_cast<uint4*>(Cb + (long long)row * g.N + cb * 32 + 4 * q) = v;
+                    }
                 }
+                __syncwarp();
             }
             chunk = 0;
             ++tl;
@@ -190,7 +216,7 @@ gemm_pix_tc_kernel(TcGemmArgs g) {
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, kTcBN);
 }
 
 static bool tc_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -201,14 +227,26 @@ cudaError_t launch_gemm_pix_tc(const float* A, const float* B, float* C, int M, 
                                cudaStream_t s) {
     if (!tc_aligned16(A) || !tc_aligned16(B) || !tc_aligned16(C) || (N & 3) || (lda & 3) || (a_kmajor ? (K & 3) : (M & 3)))
         return cudaErrorNotSupported;
-    static unsigned long long done_k = 0, done_m = 0;
-    cudaError_t e = a_kmajor ? ensure_dyn_smem(gemm_pix_tc_kernel<true>, kTcSmem, done_k) : ensure_dyn_smem(gemm_pix_tc_kernel<false>, kTcSmem, done_m);
-    if (e != cudaSuccess) return e;
-    TcGemmArgs g{A, B, C, M, N, K, nb, getenv("FSCNN_TC_IDESC_XOR") ? (uint32_t)strtoul(getenv("FSCNN_TC_IDESC_XOR"), nullptr, 0) : 0u, lda, (long long)K * N, (long long)M * N};
-    const long long tiles = (long long)nb * ((N + kTcBN - 1) / kTcBN) * ((M + kTcBM - 1) / kTcBM);
+    TcGemmArgs g{A, B, C, M, N, K, nb, 0u, lda, (long long)K * N, (long long)M * N};
+    const bool wide = N >= 2048;
+    const int bn = wide ? 256 : 128;
+    const long long tiles = (long long)nb * ((N + bn - 1) / bn) * ((M + kTcBM - 1) / kTcBM);
     const int ctas = (int)(tiles < 2ll * num_sms() ? tiles : 2ll * num_sms());
-    if (a_kmajor) gemm_pix_tc_kernel<true><<<ctas, kTcT, kTcSmem, s>>>(g);
-    else gemm_pix_tc_kernel<false><<<ctas, kTcT, kTcSmem, s>>>(g);
+    static unsigned long long done[4] = {0, 0, 0, 0};
+    cudaError_t e;
+    if (a_kmajor && wide) {
+        if ((e = ensure_dyn_smem(gemm_pix_tc_kernel<true, 256>, TcCfg<256>::Smem, done[0])) != cudaSuccess) return e;
+        gemm_pix_tc_kernel<true, 256><<<ctas, kTcT, TcCfg<256>::Smem, s>>>(g);
+    } else if (a_kmajor) {
+        if ((e = ensure_dyn_smem(gemm_pix_tc_kernel<true, 128>, TcCfg<128>::Smem, done[1])) != cudaSuccess) return e;
+        gemm_pix_tc_kernel<true, 128><<<ctas, kTcT, TcCfg<128>::Smem, s>>>(g);
+    } else if (wide) {
+        if ((e = ensure_dyn_smem(gemm_pix_tc_kernel<false, 256>, TcCfg<256>::Smem, done[2])) != cudaSuccess) return e;
+        gemm_pix_tc_kernel<false, 256><<<ctas, kTcT, TcCfg<256>::Smem, s>>>(g);
+    } else {
+        if ((e = ensure_dyn_smem(gemm_pix_tc_kernel<false, 128>, TcCfg<128>::Smem, done[3])) != cudaSuccess) return e;
+        gemm_pix_tc_kernel<false, 128><<<ctas, kTcT, TcCfg<128>::Smem, s>>>(g);
+    }
     return cudaGetLastError();
 }
 

@@ -284,10 +284,10 @@ def test_fused_upsample_ohem_equals_the_two_step_form(n, c, hl, wl, h, w, scale,
 
 
 def test_tf32_matmul_mode_is_close_to_fp32_and_really_different():
-    """fscnn_train_set_math(1): the pointwise forward / data gradient / weight gradient on the tensor cores with TF32 operands.  Against
-    the fp32 FMA kernels the error must sit at the TF32 rounding level (2^-11 per operand, averaged over the contraction), well
-    above fp32 noise (so the tensor-core kernels really ran) and below 3e-3 of the tensor's absmax; the mode is process-wide and
-    is restored."""
+    """fscnn_train_set_math(1): the pointwise forward / data gradient (tcgen05.mma.kind::tf32, accumulator in TMEM; mma.sync for rows
+    that are not 16-byte aligned) and weight gradient (mma.sync) on the tensor cores with TF32 operands.  Against the fp32 FMA kernels
+    the error must sit at the TF32 level (10 mantissa bits per operand, averaged over the contraction), well above fp32 noise (so the
+    tensor-core kernels really ran) and below 3e-3 of the tensor's absmax; the mode is process-wide and is restored."""
     from fscnn_b200 import train_ops
     g = torch.Generator(device='cpu').manual_seed(11)
     results = {}
@@ -296,7 +296,9 @@ def test_tf32_matmul_mode_is_close_to_fp32_and_really_different():
             train_ops.set_matmul_precision(mode)
             assert train_ops.get_matmul_precision() == mode
             outs = []
-            for n, cin, cout, h, w in [(2, 64, 384, 24, 28), (3, 130, 50, 17, 19), (1, 32, 19, 40, 36)]:      # aligned and ragged
+            # aligned (tcgen05 kernels: 128-pixel tiles, 256-pixel tiles from 2048 pixels up, several channel blocks, partial tiles)
+            # and ragged (mma.sync kernels)
+            for n, cin, cout, h, w in [(2, 64, 384, 24, 28), (3, 130, 50, 17, 19), (1, 32, 19, 40, 36), (2, 48, 160, 44, 60), (1, 20, 64, 52, 48)]:
                 gg = torch.Generator(device='cpu').manual_seed(100 + cin)
                 x = torch.randn(n, cin, h, w, generator=gg).to(DEV).requires_grad_(True)
                 wt = (torch.randn(cout, cin, 1, 1, generator=gg) / cin ** 0.5).to(DEV).requires_grad_(True)
