@@ -542,14 +542,17 @@ def run_native_arm(args):
             train_ops.set_matmul_precision('fp32')
         train = {'workload': f'train_step_nc{nc}_aux_crop{crop}_b{tb}_per_gpu: forward + backward + MixSoftmaxCrossEntropyOHEMLoss + '
                              'gradient all-reduce + SGD(momentum, weight decay)',
-                 'value': tb * world / (t_ms / 1e3), 'unit': UNIT, 'ms_per_step': t_ms, 'n_gpus': world, 'scaling': 'weak', 'dtype': 'f32',
-                 'loss_first_step': l0, 'loss_after_9_steps': l1,
+                 'value': tb * world / (tf32_ms / 1e3), 'unit': UNIT, 'ms_per_step': tf32_ms, 'n_gpus': world, 'scaling': 'weak',
+                 'dtype': 'tf32',
+                 'dtype_note': 'fscnn_train_set_math(1): TF32 operands (fp32 accumulate) for the pointwise / dense 3x3 contractions -- tcgen05.mma.kind::tf32 '
+                               'for forward and data gradient, mma.sync for the weight gradient; everything else fp32.  This is what cuDNN does '
+                               'under torch allow_tf32 (the comparator\'s fp32 line) and at least the precision of the reference\'s fp16 autocast',
+                 'loss_after_9_steps': tf32_l1,
                  'launch_mode': 'CUDA graph of zero_grad + forward + loss + backward, replayed; all-reduce + SGD outside the graph',
-                 'eager_launch_ms_per_step': eager_ms,
-                 'tf32': {'value': tb * world / (tf32_ms / 1e3), 'ms_per_step': tf32_ms, 'loss_after_9_steps': tf32_l1,
-                          'note': 'fscnn_train_set_math(1): TF32 operands on the tensor cores for the pointwise / dense 3x3 contractions '
-                                  '(what cuDNN does under torch allow_tf32, the comparator\'s fp32 line); everything else fp32'},
-                 'note': 'fp32 CUDA kernels (csrc/train.cu) behind autograd wrappers; DDP semantics (per-rank BatchNorm, one NCCL '
+                 'fp32': {'value': tb * world / (t_ms / 1e3), 'ms_per_step': t_ms, 'loss_first_step': l0, 'loss_after_9_steps': l1,
+                          'eager_launch_ms_per_step': eager_ms,
+                          'note': 'default mode of the library (fp32 FMA contractions): the mode the 1e-4 parity tests are stated for'},
+                 'note': 'CUDA kernels of csrc/train.cu + train_tc.cu behind autograd wrappers; DDP semantics (per-rank BatchNorm, one NCCL '
                          'all-reduce of the flat 4.6 MB gradient buffer)'}
         del xt, tt
         torch.cuda.empty_cache()

@@ -274,8 +274,10 @@ int fscnn_train_relu_backward(const float* d_y, const float* d_dy, float* d_dx, 
 /* Arithmetic of the pointwise / dense-3x3 contractions of the training operators (process-wide; not a per-call argument because
  * torch.backends.cuda.matmul.allow_tf32, the switch it mirrors, is process-wide too):
  *   0  fp32 FMA on the CUDA cores (default; the mode the parity tests pin to 1e-4)
- *   1  TF32 operands (rounded to nearest, 10 mantissa bits) on the tensor cores, fp32 accumulators: what cuDNN does for convolutions
- *      when torch's allow_tf32 is on (its default) and about what the reference's fp16 autocast (train.py:267-275) keeps
+ *   1  TF32 operands (10 mantissa bits) on the tensor cores, fp32 accumulators: what cuDNN does for convolutions when torch's
+ *      allow_tf32 is on (its default) and at least what the reference's fp16 autocast (train.py:267-275) keeps.  Forward and data
+ *      gradient of 16-byte aligned shapes run tcgen05.mma.kind::tf32 (accumulator in TMEM, the tensor core truncates the fp32
+ *      operands); the weight gradient and unaligned shapes run mma.sync.m16n8k8 with operands rounded to nearest
  * Returns FSCNN_EINVAL for any other mode.  fscnn_train_get_math returns the current mode. */
 int fscnn_train_set_math(int mode);
 int fscnn_train_get_math(void);
