@@ -1,17 +1,18 @@
-// train.cu -- first slice of the training step (BASELINE config 5): the building blocks of
-// _DSConv / _DWConv / _ConvBNReLU(1x1) / LinearBottleneck in TRAINING mode and the OHEM loss, forward and backward, as
-// fp32 CUDA kernels behind the C ABI (fscnn_train_* in include/fscnn_b200.h).
+// train.cu -- the training step (BASELINE config 5): every layer of the network in TRAINING mode and the
+// OHEM loss, forward and backward, as CUDA kernels behind the C ABI (fscnn_train_* in include/fscnn_b200.h).
 //
 //   depthwise 3x3 (pad 1, stride 1/2, groups = C)   nn.Conv2d(c, c, 3, s, 1, groups=c)      models/fast_scnn.py:70, :86
-//   pointwise 1x1                                    nn.Conv2d(cin, cout, 1)                 models/fast_scnn.py:73, :107
+//   pointwise 1x1 / dense 3x3 through im2col        nn.Conv2d(cin, cout, 1) / (.., 3, ..)   models/fast_scnn.py:73, :107, :24-31
 //   BatchNorm2d, batch statistics (+ ReLU)           nn.BatchNorm2d in train mode            models/fast_scnn.py:71-75
-//   SoftmaxCrossEntropyOHEMLoss                      utils/loss.py:127-182 (host numpy argsort -> device radix select)
+//   SoftmaxCrossEntropyOHEMLoss (+ the final resize) utils/loss.py:127-182 (host numpy argsort -> device radix select)
+//   bias, bilinear resize, adaptive pooling, dropout, add + ReLU, SGD
 //
-// Tensors keep PyTorch's layout (NCHW fp32, contiguous) because autograd hands them over that way; every reduction is
-// two-stage (per-CTA partials in a caller-provided workspace, then one finalising CTA) so results do not depend on atomics
-// ordering.  These kernels are the parity-checked reference point of the training path (tests/test_gpu_train.py against
-// torch.autograd of the unmodified reference modules); the tensor-core / fused versions of the eval path's design are the
-// next step of this row and are NOT claimed here.
+// Tensors keep PyTorch's layout (NCHW fp32, contiguous) because autograd hands them over that way.  Reductions that feed parameters
+// are fp64: per-CTA partials + one finalising pass (BatchNorm, pointwise weight gradient), or double atomics rounded to float once
+// (depthwise weight gradient); the fused loss backward adds into the low-resolution gradient with float atomics.  The contractions
+// are fp32 FMA by default; fscnn_train_set_math(1) moves them to the tensor cores with TF32 operands (train_tc.cu: tcgen05; here: the
+// mma.sync kernels for the weight gradient and unaligned shapes).  Parity: tests/test_gpu_train.py against torch.autograd of the
+// unmodified reference modules.
 #include <cfloat>
 #include <cstdlib>
 #include <initializer_list>

@@ -8,7 +8,9 @@ a flat fp32 buffer (1.16 M parameters, 4.6 MB) followed by the same fused SGD up
 
 Parameters and gradients live in two flat buffers (the module's parameters and their .grad are views into them), so the
 collective and the optimizer are one launch each.  The reference trains under fp16 autocast + GradScaler (train.py:73-74,
-:267-275: ``--use-fp16`` defaults to True); this path keeps fp32 throughout, which is the more exact of the two.
+:267-275: ``--use-fp16`` defaults to True); this path keeps fp32 tensors throughout and fp32 arithmetic by default
+(``matmul_precision='tf32'`` moves the contractions to the tensor cores with TF32 operands and fp32 accumulation, still at least the
+precision of fp16 autocast).  ``cuda_graph=True`` replays zero_grad + forward + loss + backward from a captured CUDA graph.
 """
 from __future__ import annotations
 
