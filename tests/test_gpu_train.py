@@ -193,24 +193,26 @@ def test_whole_network_train_step_matches_reference_fixture():
     assert glob < 2e-2
 
 
-def _float64_truth(model, x, target, kept, trainer):
+def _float64_truth(model, x, target, kept, trainer, dtype=torch.float64):
     """Parameter gradients of the same step in float64 on ATen (the checker): training-mode BatchNorm, no dropout, weighted cross
-    entropy over exactly the pixels `kept` per head, aux weight as in the trainer."""
+    entropy over exactly the pixels `kept` per head, aux weight as in the trainer.  dtype=torch.float32 gives the same operator
+    sequence through cuDNN in float32 (with whatever torch.backends.cudnn.allow_tf32 says): the yardstick of the TF32 mode."""
     import torch.nn.functional as F
     import fastscnn_torch_port as port
-    sd = {k: v.detach().double().requires_grad_(v.dtype.is_floating_point and 'running' not in k) for k, v in model.state_dict().items()}
+    sd = {k: (v.detach().to(dtype) if v.dtype.is_floating_point else v.detach()).requires_grad_(v.dtype.is_floating_point and 'running' not in k)
+          for k, v in model.state_dict().items()}
     real_bn = port._bn
     port._bn = lambda s, p, t: F.batch_norm(t, None, None, s[p + '.weight'], s[p + '.bias'], True, 0.1, 1e-5)
     try:
         with torch.enable_grad():
             fwd = getattr(port.forward, '__wrapped__', port.forward)
-            outs = fwd(sd, x.double(), aux=len(kept) > 1)
+            outs = fwd(sd, x.to(dtype), aux=len(kept) > 1)
     finally:
         port._bn = real_bn
     total = 0.0
     for i, (o, keep) in enumerate(zip(outs, kept)):
         tgt = torch.where(keep, target, torch.full_like(target, -1))
-        w = trainer.class_weight.double() if trainer.class_weight is not None else None
+        w = trainer.class_weight.to(dtype) if trainer.class_weight is not None else None
         li = F.cross_entropy(o, tgt, weight=w, ignore_index=-1)
         total = total + (li if i == 0 else trainer.aux_weight * li)
     names = [k for k, v in sd.items() if v.requires_grad]
@@ -400,3 +402,68 @@ def test_depthwise_kernels_against_torch_and_run_to_run(n, c, h, w, stride):
     yr.backward(dy.double())
     for got, want in zip(runs[0], (yr.detach(), xr.grad, wr.grad)):
         assert rel_err(got.cpu().numpy(), want.float().cpu().numpy()) < 2e-6
+
+
+def test_tf32_training_step_against_cudnn_tf32():
+    """The whole training step with TF32 contractions (tcgen05 forward / data gradient, mma.sync weight gradient): loss within 5e-4 of
+    the fp32 mode, and every parameter gradient as close to a float64 run of the same step (same kept pixels) as the reference
+    operator sequence gets through cuDNN with TF32 convolutions on this GPU (torch's default allow_tf32; factor 2, floor 2e-2 of the
+    gradient's norm).  Gradients of the first layers pass back through ~45 TF32 contractions and are cancelling sums: cuDNN's own
+    TF32 run is tens of per cent off the truth there, which is why the bound is relative to it.  Then four steps from a CUDA graph:
+    the loss must go down."""
+    import fastscnn_oracle as fo
+    from fscnn_b200 import Trainer, train_ops
+    from models.fast_scnn import FastSCNN
+    nc = 19
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in fo.make_state_dict(nc, True, 13).items()}
+    x = torch.from_numpy(fo.make_input(2, 128, 192, 50)).to(DEV)
+    target = torch.from_numpy(fo.make_labels(2, 128, 192, nc, 51)).to(DEV)
+
+    def fresh():
+        m = FastSCNN(nc, aux=True)
+        m.load_state_dict(sd)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.momentum = 0.0                     # several forwards below must see the same buffers
+        return m.to(DEV).train()
+
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    try:
+        model = fresh()
+        trainer = Trainer(model, aux_weight=0.4, fused_loss=False)
+        outs = model(x)
+        loss32 = trainer.loss(outs, target)
+        kept = [(g_.abs().sum(1) > 0) for g_ in torch.autograd.grad(loss32, outs)]
+        truth = _float64_truth(model, x, target, kept, trainer)
+        torch.backends.cudnn.allow_tf32 = True
+        yard = _float64_truth(model, x, target, kept, trainer, dtype=torch.float32)
+        train_ops.set_matmul_precision('tf32')
+        model.zero_grad()
+        for p in model.parameters():
+            p.grad = None
+        outs = model(x)
+        # the same kept pixels as the truth: plain weighted cross entropy on them, like _float64_truth
+        import torch.nn.functional as F
+        total = 0.0
+        for i, (o, keep) in enumerate(zip(outs, kept)):
+            li = F.cross_entropy(o, torch.where(keep, target, torch.full_like(target, -1)), weight=trainer.class_weight, ignore_index=-1)
+            total = total + (li if i == 0 else trainer.aux_weight * li)
+        assert abs(float(total) - float(loss32)) <= 5e-4 * abs(float(loss32))
+        total.backward()
+        worst = 0.0
+        for k, p in model.named_parameters():
+            t = truth[k].ravel()
+            scale = max(np.linalg.norm(t), 1e-4 * np.sqrt(t.size))
+            d_ours = np.linalg.norm(p.grad.detach().cpu().numpy().ravel().astype(np.float64) - t) / scale
+            d_yard = np.linalg.norm(yard[k].ravel().astype(np.float64) - t) / scale
+            worst = max(worst, d_ours / max(d_yard, 1e-2))
+            assert d_ours <= max(2e-2, 2.0 * d_yard), (k, d_ours, d_yard)
+        print('worst ratio of our TF32 gradient error to cuDNN TF32 (floored at 1e-2):', worst)
+        tr = Trainer(fresh(), base_lr=0.01, nepochs=1, iters_per_epoch=10, cuda_graph=True, graph_warmup=1, matmul_precision='tf32')
+        losses = [float(tr.step(x, target)) for _ in range(4)]
+        assert losses[-1] < losses[0], losses
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+        train_ops.set_matmul_precision('fp32')
