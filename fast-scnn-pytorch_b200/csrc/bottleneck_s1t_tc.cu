@@ -108,6 +108,7 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
         const int tx = tile % tiles_x, r = tile / tiles_x;
         n = r / tiles_y; oy0 = (r % tiles_y) * C::TH; ox0 = tx * C::TW;
     };
+    pdl_launch_dependents();
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -146,19 +147,20 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
             };
             constexpr uint32_t idesc_exp = make_idesc_bf16(128, C::NB);
             tma_prefetch_desc(&xmap);
-            load_x(0);
-            if (XB == 2 && my_tiles > 1) load_x(1);
             if (WRES) {      // all weight chunks, once (the project controller waits on the same barrier)
                 mbar_arrive_expect_tx(&bar_wres, NCH * (C::WE_BYTES + C::WP_BYTES));
                 for (int e = 0; e < NCH; ++e) {
                     bulk_g2s(sm + C::oWe + e * C::WE_BYTES, we_img + (size_t)e * CM * C::KA, C::WE_BYTES, &bar_wres);
                     bulk_g2s(sm + C::oWp + e * C::WP_BYTES, wp_img + (size_t)e * COUT * CM, C::WP_BYTES, &bar_wres);
                 }
-                mbar_wait(&bar_wres, 0);
             } else {
                 prefetch_we(0);
                 if (total > 1) prefetch_we(1);
             }
+            pdl_wait();      // the weights are on their way; the halo tiles are the previous stage's output
+            load_x(0);
+            if (XB == 2 && my_tiles > 1) load_x(1);
+            if (WRES) mbar_wait(&bar_wres, 0);
 #pragma unroll 1
             for (int ke = 0; ke < total; ++ke) {
                 const int lt = ke / NCH, e = ke - lt * NCH, xb = lt % XB;
@@ -228,6 +230,7 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
         }
     } else {
         // =========================== compute warps ===========================
+        pdl_wait();      // (the residual is read from global memory, the output written to it)
         const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter = warp % 4 (hardware rule), row strip (output rows 2s, 2s+1)
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float* Bp_g = reinterpret_cast<const float*>(tab + (size_t)NCH * CM * 32);
@@ -404,9 +407,8 @@ static cudaError_t run_s1t(const bf16* in, const unsigned char* tab, const bf16*
     if (e != cudaSuccess) return e;
     const int tiles_x = ceil_div(w, C::TW), tiles_y = ceil_div(h, C::TH), ntiles = tiles_x * tiles_y * n;
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    bottleneck_s1t_kernel<CIN, COUT, RES><<<grid, kTThreads, C::smem_bytes, s>>>(xmap, in, tab, we_img, wp_img, out, h, w, tiles_x,
-                                                                                 tiles_y, ntiles);
-    return cudaGetLastError();
+    return launch_pdl(bottleneck_s1t_kernel<CIN, COUT, RES>, grid, kTThreads, C::smem_bytes, s, xmap, in, tab, we_img, wp_img, out, h, w, tiles_x,
+                      tiles_y, ntiles);
 }
 
 cudaError_t launch_bottleneck_s1t_tc(int cin, int cout, const bf16* in, const unsigned char* tab, const bf16* we_img,

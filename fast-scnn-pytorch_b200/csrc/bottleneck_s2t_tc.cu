@@ -82,6 +82,7 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
         const int tx = tile % tiles_x, r = tile / tiles_x;
         n = r / tiles_y; oy0 = (r % tiles_y) * C::TH; ox0 = tx * C::TW;
     };
+    pdl_launch_dependents();
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -116,9 +117,10 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
             };
             constexpr uint32_t idesc_exp = make_idesc_bf16(128, C::NB);
             tma_prefetch_desc(&xmap);
-            for (int j = 0; j < NSUB; ++j) load_x(0, j);
             prefetch_we(0);
             if (total > 1) prefetch_we(1);
+            pdl_wait();      // the weights are on their way; the halo tiles are the previous stage's output
+            for (int j = 0; j < NSUB; ++j) load_x(0, j);
 #pragma unroll 1
             for (int g = 0; g < total; ++g) {
                 const int lt = g / NCH, e = g - lt * NCH;
@@ -179,6 +181,7 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
         }
     } else {
         // =========================== compute warps ===========================
+        pdl_wait();
         const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter (32 expanded channels), output row of the sub-tile
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const float* Bp_g = reinterpret_cast<const float*>(tab + (size_t)NCH * CM * 32);
@@ -309,9 +312,8 @@ static cudaError_t run_s2t(const bf16* in, const unsigned char* tab, const bf16*
     if (e != cudaSuccess) return e;
     const int tiles_x = ceil_div(wo, C::TW), tiles_y = ceil_div(ho, C::TH), ntiles = tiles_x * tiles_y * n;
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    bottleneck_s2t_kernel<CIN, COUT><<<grid, kS2Threads, C::smem_bytes, s>>>(xmap, tab, we_img, wp_img, out, hi, wi, ho, wo, tiles_x,
-                                                                             tiles_y, ntiles);
-    return cudaGetLastError();
+    return launch_pdl(bottleneck_s2t_kernel<CIN, COUT>, grid, kS2Threads, C::smem_bytes, s, xmap, tab, we_img, wp_img, out, hi, wi, ho, wo, tiles_x,
+                      tiles_y, ntiles);
 }
 
 cudaError_t launch_bottleneck_s2t_tc(int cin, int cout, const bf16* in, const unsigned char* tab, const bf16* we_img,

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace fscnn {
 
@@ -136,6 +137,12 @@ inline int num_sms() {
     return v;
 }
 
+// FSCNN_NO_PDL=1 launches the stage kernels without the programmatic-serialization attribute (A/B switch, bench.py --latency)
+inline bool pdl_enabled() {
+    static const bool on = getenv("FSCNN_NO_PDL") == nullptr;
+    return on;
+}
+
 // Opt a kernel into `bytes` of dynamic shared memory once per device (the attribute is per context).
 template <typename F>
 inline cudaError_t ensure_dyn_smem(F* func, size_t bytes, unsigned long long& done_mask) {
@@ -146,6 +153,27 @@ inline cudaError_t ensure_dyn_smem(F* func, size_t bytes, unsigned long long& do
     e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) done_mask |= 1ull << (dev & 63);
     return e;
+}
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// The stage kernels of a forward run back to back on one stream; at small batches a kernel's set-up (barrier init, TMEM
+// allocation, weight copies into shared memory: 3-5 us) is a third of its life.  Launched with the programmatic-serialization
+// attribute, kernel k+1 may start while kernel k is still running: it does its set-up, then blocks in pdl_wait() until kernel k has
+// completed and its writes are visible, and only then touches activations (reads its inputs, and -- because every output depends
+// on an input -- writes its outputs).  pdl_launch_dependents() at the top of a kernel lets ITS successor start early in turn.
+// Both instructions are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace fscnn

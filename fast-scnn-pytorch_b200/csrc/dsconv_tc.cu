@@ -78,6 +78,7 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
         n = r / tiles_y; oy0 = (r % tiles_y) * C::TH; ox0 = tx * C::TW;
     };
 
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(&bar_w, 1);
         for (int i = 0; i < 2; ++i) {
@@ -119,6 +120,7 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
             mbar_arrive_expect_tx(&bar_w, C::B_BYTES + (HEAD ? ncp16 * COUT * 2 : 0));
             bulk_g2s(sm + C::oB, wp_img, C::B_BYTES, &bar_w);
             if (HEAD) bulk_g2s(sm + C::oB2, wh_img, ncp16 * COUT * 2, &bar_w);
+            pdl_wait();      // the weights are on their way; the halo tiles are the previous stage's output
             load_halo(0);
             if (my_tiles > 1) load_halo(1);
             mbar_wait(&bar_w, 0);
@@ -151,6 +153,7 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
         }
     } else {
         // =========================== compute warps ===========================
+        pdl_wait();
         // epilogue of tile lt: TMEM[lt&1] -> bias, ReLU -> global (or, HEAD, the head's A operand over A[lt&1])
         const int q = warp & 3, part = warp >> 2;
         auto epilogue = [&](int lt) {
@@ -321,9 +324,8 @@ static cudaError_t run_ds_tc(const bf16* in, const DsW& w, const bf16* wp_img, b
     if (e != cudaSuccess) return e;
     const int tiles_x = ceil_div(wo, C::TW), tiles_y = ceil_div(ho, C::TH), ntiles = tiles_x * tiles_y * n;
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    dsconv_tc_kernel<CIN, COUT, STRIDE, HEAD><<<grid, kDsNTall, smem, s>>>(xmap, w, wp_img, out, h, wh_img, ncp16, logits, ho, wo, tiles_x,
-                                                                            tiles_y, ntiles);
-    return cudaGetLastError();
+    return launch_pdl(dsconv_tc_kernel<CIN, COUT, STRIDE, HEAD>, grid, kDsNTall, smem, s, xmap, w, wp_img, out, h, wh_img, ncp16, logits, ho, wo,
+                      tiles_x, tiles_y, ntiles);
 }
 
 cudaError_t launch_dsconv_tc(int cin, int cout, int stride, const bf16* in, const DsW& w, const bf16* wp_img, bf16* out,

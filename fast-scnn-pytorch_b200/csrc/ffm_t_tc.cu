@@ -65,6 +65,7 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
         ry0 = min((int)(scy * (float)max(oy0 - 1, 0)), Hl - 1);
         rx0 = min((int)(scx * (float)max(ox0 - 1, 0)), Wl - 1);
     };
+    pdl_launch_dependents();
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -106,6 +107,7 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
             };
             constexpr uint32_t idesc_rs = make_idesc_bf16(128, kNB) | (1u << 15);   // A (= the patch) is MN-major
             tma_prefetch_desc(&lmap);
+            pdl_wait();      // `lower` is the previous stage's output
             load_patch(0);
             if (my_tiles > 1) load_patch(1);
 #pragma unroll 1
@@ -141,6 +143,7 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
             tma_prefetch_desc(&hmap);
             mbar_arrive_expect_tx(&bar_w, W_BYTES);
             bulk_g2s(sm + oW, wcat_img, W_BYTES, &bar_w);
+            pdl_wait();      // the weights are on their way; `higher` is an earlier stage's output
             load_hi(0);
             if (my_tiles > 1) load_hi(1);
             mbar_wait(&bar_w, 0);
@@ -173,6 +176,7 @@ ffm_t_kernel(const __grid_constant__ CUtensorMap hmap, const __grid_constant__ C
         }
     } else {
         // =========================== compute warps ===========================
+        pdl_wait();
         const int q = warp & 3, s = warp >> 2;            // TMEM lane quarter, row strip (output rows 2s, 2s+1) / 32-column slice
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         // one row of the interpolation matrix per thread: lanes 0..22 of warps 0..7 (8 x 23 = 184 >= 180 rows): two builder warps
@@ -329,8 +333,7 @@ cudaError_t launch_ffm_t_tc(const bf16* higher, const bf16* lower, const unsigne
     if (e != cudaSuccess) return e;
     const int tiles_x = ceil_div(wh, 16), tiles_y = ceil_div(hh, 8), ntiles = tiles_x * tiles_y * n;
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
-    ffm_t_kernel<<<grid, kFThreads, kSmemT, s>>>(hmap, lmap, tab, wcat_img, out, hh, wh, hl, wl, tiles_x, tiles_y, ntiles);
-    return cudaGetLastError();
+    return launch_pdl(ffm_t_kernel, grid, kFThreads, kSmemT, s, hmap, lmap, tab, wcat_img, out, hh, wh, hl, wl, tiles_x, tiles_y, ntiles);
 }
 
 }  // namespace fscnn

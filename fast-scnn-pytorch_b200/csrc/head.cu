@@ -664,6 +664,7 @@ upsample_argmax_tma_kernel(const __grid_constant__ CUtensorMap lmap, const __gri
         tma_load_3d(smem_u32(labs), &labmap, xb, yb, n, &bar_lab);
     };
 
+    pdl_launch_dependents();
     if (tid == 0) {
         mbar_init(&bar_l, 1); mbar_init(&bar_lab, 1);
         fence_mbar_init();
@@ -672,6 +673,7 @@ upsample_argmax_tma_kernel(const __grid_constant__ CUtensorMap lmap, const __gri
     if (do_hist)
         for (int i = tid; i < nb; i += kThreads) hist[i] = 0u;
     __syncthreads();
+    pdl_wait();      // the low-resolution logits are the previous stage's output; mask / confusion writes follow them
     if (tid == 0) {
         tma_prefetch_desc(&lmap);
         issue_logits(blockIdx.x);
@@ -995,10 +997,9 @@ static cudaError_t run_up_argmax_tma(const float* low, int nc, int ncp, void* ma
         occ = 1;
     const int tiles_x = ceil_div(w, 128), tiles_y = ceil_div(h, 64), ntiles = tiles_x * tiles_y * n;
     const int grid = min(ntiles, num_sms() * occ);
-    upsample_argmax_tma_kernel<LDT><<<grid, kThreads, smem, s>>>(lmap, labmap, nc, ncp, mask, mask_dtype, conf, hl, wl, h, w, tiles_x, tiles_y,
-                                                                ntiles, prune ? 1 : 0);
     *used = true;
-    return cudaGetLastError();
+    return launch_pdl(upsample_argmax_tma_kernel<LDT>, grid, kThreads, smem, s, lmap, labmap, nc, ncp, mask, mask_dtype, conf, hl, wl, h, w, tiles_x,
+                      tiles_y, ntiles, prune ? 1 : 0);
 }
 
 static int g_tail_tma = -1;   // FSCNN_TAIL_TMA=0 keeps the direct kernel (A/B timing)

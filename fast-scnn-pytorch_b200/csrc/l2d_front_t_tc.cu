@@ -64,6 +64,7 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
         const int tx = tile % tiles_x, r = tile / tiles_x;
         n = r / tiles_y; oy0 = (r % tiles_y) * 8; ox0 = tx * 16;
     };
+    pdl_launch_dependents();
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -98,6 +99,7 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
+    pdl_wait();      // set-up done (weights only); the input patches and the output belong to the stream order
 
     if (warp == kCW) {
         // =========================== stem controller ===========================
@@ -335,7 +337,8 @@ cudaError_t launch_l2d_front_t_tc(const void* x, const StemIn& in, const bf16* w
         if (make_tiled_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, x, dims, strides, box) != cudaSuccess) return cudaErrorNotSupported;
         cudaError_t e = ensure_dyn_smem(l2d_front_t_kernel<FSCNN_IN_U8_NHWC>, kSmemFT, cfg_u8);
         if (e != cudaSuccess) return e;
-        l2d_front_t_kernel<FSCNN_IN_U8_NHWC><<<grid, kFTThreads, kSmemFT, s>>>(xmap, ws_img, w, wp_img, out, h1, w1, h2, w2, tiles_x, tiles_y, ntiles);
+        e = launch_pdl(l2d_front_t_kernel<FSCNN_IN_U8_NHWC>, grid, kFTThreads, kSmemFT, s, xmap, ws_img, w, wp_img, out, h1, w1, h2, w2, tiles_x, tiles_y, ntiles);
+        if (e != cudaSuccess) return e;
     } else {
         if (wd % 4 != 0) return cudaErrorNotSupported;
         const cuuint64_t dims[3] = {(cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)n * 3};
@@ -344,7 +347,8 @@ cudaError_t launch_l2d_front_t_tc(const void* x, const StemIn& in, const bf16* w
         if (make_tiled_map(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, x, dims, strides, box) != cudaSuccess) return cudaErrorNotSupported;
         cudaError_t e = ensure_dyn_smem(l2d_front_t_kernel<FSCNN_IN_F32_NCHW>, kSmemFT, cfg_f32);
         if (e != cudaSuccess) return e;
-        l2d_front_t_kernel<FSCNN_IN_F32_NCHW><<<grid, kFTThreads, kSmemFT, s>>>(xmap, ws_img, w, wp_img, out, h1, w1, h2, w2, tiles_x, tiles_y, ntiles);
+        e = launch_pdl(l2d_front_t_kernel<FSCNN_IN_F32_NCHW>, grid, kFTThreads, kSmemFT, s, xmap, ws_img, w, wp_img, out, h1, w1, h2, w2, tiles_x, tiles_y, ntiles);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }

@@ -22,6 +22,8 @@ __device__ __forceinline__ int bin_end(int i, int n, int s) { return ((i + 1) * 
 template <typename T>
 __global__ void __launch_bounds__(kPpmC) ppm_rowsum_kernel(const T* __restrict__ in, float* __restrict__ rowsum, int h, int wd) {
     const int y = blockIdx.x, n = blockIdx.y, c = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const int scales[4] = {1, 2, 3, 6};
     const T* row = in + (((size_t)n * h + y) * wd) * kPpmC + c;
     float* o = rowsum + (((size_t)n * h + y) * kPpmCols) * kPpmC + c;
@@ -45,6 +47,8 @@ __global__ void __launch_bounds__(kPpmC) ppm_branch_kernel(const float* __restri
     __shared__ float mean[kPpmC];
     __shared__ float feat[32];
     const int bin = blockIdx.x, n = blockIdx.y, c = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (bin >= kPpmBins) {   // zero padding of the operand image
         z16[(size_t)n * kPpmC * 64 + ((size_t)(bin >> 3) * 16 + (c >> 3)) * 64 + (c & 7) * 8 + (bin & 7)] = __float2bfloat16_rn(0.f);
         return;
@@ -167,8 +171,10 @@ cudaError_t launch_ppm(const T* in, const PpmW& w, float* rowsum, float* z, T* o
 // bf16 path with the output stage on the tensor core (ppm_tc.cu)
 cudaError_t launch_ppm_tc(const bf16* in, const PpmW& w, const bf16* wx_img, float* rowsum, float* z, bf16* z16, bf16* r_img, bf16* out,
                           int n, int h, int wd, cudaStream_t s) {
-    ppm_rowsum_kernel<bf16><<<dim3(h, n), kPpmC, 0, s>>>(in, rowsum, h, wd);
-    ppm_branch_kernel<<<dim3(64, n), kPpmC, 0, s>>>(rowsum, w, z, z16, h, wd);
+    cudaError_t e = launch_pdl(ppm_rowsum_kernel<bf16>, dim3(h, n), kPpmC, 0, s, in, rowsum, h, wd);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(ppm_branch_kernel, dim3(64, n), kPpmC, 0, s, (const float*)rowsum, w, z, z16, h, wd);
+    if (e != cudaSuccess) return e;
     return launch_ppm_out_tc(in, wx_img, z16, w.bo, r_img, out, n, h, wd, s);
 }
 

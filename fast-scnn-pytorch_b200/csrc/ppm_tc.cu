@@ -25,6 +25,8 @@ __device__ __forceinline__ int pbin_start(int i, int n, int s) { return (i * n) 
 
 // R[y][x][0:64]: bilinear align_corners weights of the 1 + 4 + 9 + 36 pooled bins at pixel (y, x); columns 50..63 zero
 __global__ void ppm_fill_r_kernel(bf16* __restrict__ r, int h, int wd) {
+    pdl_launch_dependents();
+    pdl_wait();      // r may still be read by the previous forward's output stage
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= h * wd) return;
     const int y = p / wd, x = p % wd;
@@ -61,12 +63,14 @@ ppm_out_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, n = blockIdx.y;
     const int oy0 = (tile / tiles_x) * 8, ox0 = (tile % tiles_x) * 16;
+    pdl_launch_dependents();
     if (tid == 0) { mbar_init(&bar_ld, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
     if (warp == 0) { tmem_alloc(&tmem_base_s, 128); tmem_relinquish(); }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
+    pdl_wait();
     if (warp == 4) {
         if (lane == 0) {
             mbar_arrive_expect_tx(&bar_ld, X_BYTES + R_BYTES + W_BYTES + Z_BYTES);
@@ -124,15 +128,15 @@ cudaError_t launch_ppm_out_tc(const bf16* in, const bf16* wx_img, const bf16* z_
     static unsigned long long configured = 0;
     cudaError_t e = ensure_dyn_smem(ppm_out_tc_kernel, (size_t)kSmemP, configured);
     if (e != cudaSuccess) return e;
-    ppm_fill_r_kernel<<<ceil_div(h * wd, 128), 128, 0, s>>>(r_img, h, wd);
+    e = launch_pdl(ppm_fill_r_kernel, ceil_div(h * wd, 128), 128, 0, s, r_img, h, wd);
+    if (e != cudaSuccess) return e;
     CUtensorMap xmap, rmap;
     e = make_nhwc_halo_map(&xmap, in, n, h, wd, kC, 8, 16);
     if (e != cudaSuccess) return e;
     e = make_nhwc_halo_map(&rmap, r_img, 1, h, wd, kBinsP, 8, 16);
     if (e != cudaSuccess) return e;
     const int tiles_x = ceil_div(wd, 16), tiles_y = ceil_div(h, 8);
-    ppm_out_tc_kernel<<<dim3(tiles_x * tiles_y, n), kPThreads, kSmemP, s>>>(xmap, rmap, wx_img, z_img, bias, out, h, wd, tiles_x, tiles_y);
-    return cudaGetLastError();
+    return launch_pdl(ppm_out_tc_kernel, dim3(tiles_x * tiles_y, n), kPThreads, kSmemP, s, xmap, rmap, wx_img, z_img, bias, out, h, wd, tiles_x, tiles_y);
 }
 
 }  // namespace fscnn
