@@ -450,7 +450,7 @@ def test_tf32_training_step_against_cudnn_tf32():
         for i, (o, keep) in enumerate(zip(outs, kept)):
             li = F.cross_entropy(o, torch.where(keep, target, torch.full_like(target, -1)), weight=trainer.class_weight, ignore_index=-1)
             total = total + (li if i == 0 else trainer.aux_weight * li)
-        assert abs(float(total) - float(loss32)) <= 5e-4 * abs(float(loss32))
+        assert abs(float(total.detach()) - float(loss32.detach())) <= 5e-4 * abs(float(loss32.detach()))
         total.backward()
         worst = 0.0
         for k, p in model.named_parameters():
