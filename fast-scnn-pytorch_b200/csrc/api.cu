@@ -1071,6 +1071,20 @@ int fscnn_train_relu_backward(const float* d_y, const float* d_dy, float* d_dx, 
     if (!d_y || !d_dy || !d_dx || numel < 1) return fail(FSCNN_EINVAL, "bad argument");
     FSCNN_TRAIN_CALL(launch_train_relu_bwd(d_y, d_dy, d_dx, numel, (cudaStream_t)stream), "relu backward");
 }
+int fscnn_train_stem_forward(const float* d_x, const float* d_w, float* d_y, int n, int h, int w, void* stream) {
+    if (!d_x || !d_w || !d_y) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || h < 3 || w < 3) return fail(FSCNN_EINVAL, "bad shape");
+    FSCNN_TRAIN_CALL(launch_train_stem_fwd(d_x, d_w, d_y, n, h, w, (cudaStream_t)stream), "stem forward");
+}
+int fscnn_train_stem_weight_grad(const float* d_x, const float* d_dy, float* d_dw, void* d_ws, size_t ws_bytes, int n, int h, int w,
+                                 void* stream) {
+    if (!d_x || !d_dy || !d_dw) return fail(FSCNN_EINVAL, "null device pointer");
+    if (n < 1 || h < 3 || w < 3) return fail(FSCNN_EINVAL, "bad shape");
+    int rc = train_ws_ok(d_ws, ws_bytes, train_workspace_bytes(32, 1, 1));
+    if (rc) return rc;
+    FSCNN_TRAIN_CALL(launch_train_stem_wgrad(d_x, d_dy, d_dw, d_ws, n, h, w, (cudaStream_t)stream), "stem weight gradient");
+}
+
 int fscnn_train_set_math(int mode) {
     if (train_set_math(mode)) return fail(FSCNN_EINVAL, "math mode must be 0 (fp32) or 1 (TF32)");
     return FSCNN_OK;

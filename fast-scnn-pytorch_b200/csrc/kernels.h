@@ -142,6 +142,8 @@ cudaError_t launch_train_pw_bwd(const float* x, const float* w, const float* dy,
 // tcgen05 TF32 pointwise contraction (train_tc.cu); cudaErrorNotSupported = shape not 16-byte aligned, use the mma.sync kernel
 cudaError_t launch_gemm_pix_tc(const float* A, const float* B, float* C, int M, int N, int K, int nb, long long lda, bool a_kmajor,
                                cudaStream_t s);
+cudaError_t launch_train_stem_fwd(const float* x, const float* w, float* y, int n, int h, int wd, cudaStream_t s);
+cudaError_t launch_train_stem_wgrad(const float* x, const float* dy, float* dw, void* ws, int n, int h, int wd, cudaStream_t s);
 int train_set_math(int mode);
 int train_get_math();
 cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,

@@ -1733,6 +1733,179 @@ ohem_strip_grad_kernel(const float* __restrict__ low, const long long* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The stem, LearningToDownsample.conv = nn.Conv2d(3, 32, 3, stride 2, padding 0) (models/fast_scnn.py:153, :24-31), directly: through
+// im2col its 27-row column matrix (253 MB at config 5, rows of 146 689 pixels that no 16-byte copy can take) is written once and
+// read twice.  Same walk as the stride-2 depthwise: a lane owns an output column and carries the 3 x 3 x 3 input window in
+// registers down the rows; the 27 x 32 weights sit in shared memory k-major and are read as broadcast float4.
+//   forward : 32 accumulators per thread, 864 FMAs per pixel against 216 broadcast LDS.128
+//   weight gradient : the 32 output channels in 8 groups of 4 (blockIdx.y), 4 x 27 accumulators per thread over all of a warp's
+//                     pixels, then warp shuffle -> shared memory over the CTA's warps -> 108 double atomics per CTA
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kStemCo = 32, kStemK = 27, kStemRows = 16;
+
+struct StemWin { float v[3][3][3]; };      // [channel][row of the window][column]
+
+// rows 2 oy + r0 .. of the window for the three channels; columns 2 ox, 2 ox + 1, 2 ox + 2 (the last one is the next lane's first)
+template <bool VEC2>
+__device__ __forceinline__ void stem_load_row(const float* __restrict__ xn, int plane, int iy, int H, int W, int ox, int lane, bool want,
+                                              float (&e)[3], float (&o)[3], float (&edge)[3]) {
+    const bool rok = want && iy < H;
+    const int ix = 2 * ox;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float* r = xn + (long long)c * plane + (long long)(rok ? iy : 0) * W;
+        if (VEC2) {
+            const float2 t = (rok && ix + 1 < W) ? __ldg(reinterpret_cast<const float2*>(r + ix)) : make_float2(0.f, 0.f);
+            e[c] = t.x; o[c] = t.y;
+        } else {
+            e[c] = (rok && ix < W) ? __ldg(r + ix) : 0.f;
+            o[c] = (rok && ix + 1 < W) ? __ldg(r + ix + 1) : 0.f;
+        }
+        edge[c] = (lane == 31 && rok && ix + 2 < W) ? __ldg(r + ix + 2) : 0.f;
+    }
+}
+__device__ __forceinline__ void stem_set_row(StemWin& w, int row, const float (&e)[3], const float (&o)[3], const float (&edge)[3], int lane) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float nx = __shfl_down_sync(kFull, e[c], 1);
+        w.v[c][row][0] = e[c]; w.v[c][row][1] = o[c]; w.v[c][row][2] = lane == 31 ? edge[c] : nx;
+    }
+}
+
+struct StemTasks {      // tasks ordered (image, row block, column block)
+    int RB, CB;
+    long long total;
+    __device__ __forceinline__ void at(long long t, int& n, int& y0, int& x0) const {
+        x0 = (int)(t % CB) * 32;
+        y0 = (int)((t / CB) % RB) * kStemRows;
+        n = (int)(t / ((long long)CB * RB));
+    }
+};
+
+template <bool VEC2>
+__global__ void __launch_bounds__(kT)
+stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int H, int W, int Ho, int Wo, StemTasks tk) {
+    __shared__ __align__(16) float ws[kStemK][kStemCo];
+    for (int i = threadIdx.x; i < kStemK * kStemCo; i += kT) ws[i % kStemK][i / kStemK] = __ldg(w + i);      // w[co][k] -> ws[k][co]
+    __syncthreads();
+    const int lane = threadIdx.x & 31, plane = H * W;
+    for (long long t = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); t < tk.total; t += (long long)gridDim.x * (kT / 32)) {
+        int n, oy0, ox0;
+        tk.at(t, n, oy0, ox0);
+        const int ox = ox0 + lane, oy1 = min(Ho, oy0 + kStemRows);
+        const float* xn = x + (long long)n * 3 * plane;
+        float* yn = y + (long long)n * kStemCo * Ho * Wo;
+        StemWin win;
+        float e[3], o[3], ed[3];
+        stem_load_row<VEC2>(xn, plane, 2 * oy0, H, W, ox, lane, true, e, o, ed);
+        stem_set_row(win, 0, e, o, ed, lane);
+        for (int oy = oy0; oy < oy1; ++oy) {
+            float e1[3], o1[3], d1[3], e2[3], o2[3], d2[3];
+            stem_load_row<VEC2>(xn, plane, 2 * oy + 1, H, W, ox, lane, true, e1, o1, d1);
+            stem_load_row<VEC2>(xn, plane, 2 * oy + 2, H, W, ox, lane, true, e2, o2, d2);
+            stem_set_row(win, 1, e1, o1, d1, lane);
+            stem_set_row(win, 2, e2, o2, d2, lane);
+            float acc[kStemCo];
+#pragma unroll
+            for (int c = 0; c < kStemCo; ++c) acc[c] = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float v = win.v[ci][ky][kx];
+                        const float4* wr = reinterpret_cast<const float4*>(ws[ci * 9 + ky * 3 + kx]);
+#pragma unroll
+                        for (int q = 0; q < kStemCo / 4; ++q) {
+                            const float4 w4 = wr[q];
+                            acc[4 * q] = fmaf(v, w4.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+                        }
+                    }
+            if (ox < Wo) {
+                float* yp = yn + (long long)oy * Wo + ox;
+#pragma unroll
+                for (int c = 0; c < kStemCo; ++c) yp[(long long)c * Ho * Wo] = acc[c];
+            }
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) win.v[ci][0][kx] = win.v[ci][2][kx];      // row 2 oy + 2 is row 0 of the next window
+        }
+    }
+}
+
+// grid (pixel CTAs, 8 channel groups); 128 threads
+constexpr int kStemWT = 128;
+template <bool VEC2>
+__global__ void __launch_bounds__(kStemWT)
+stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, double* __restrict__ dwacc, int H, int W, int Ho, int Wo,
+                  StemTasks tk) {
+    __shared__ float red[kStemWT / 32][4 * kStemK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, plane = H * W, g = blockIdx.y;
+    float acc[4][kStemK];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < kStemK; ++k) acc[i][k] = 0.f;
+    for (long long t = (long long)blockIdx.x * (kStemWT / 32) + warp; t < tk.total; t += (long long)gridDim.x * (kStemWT / 32)) {
+        int n, oy0, ox0;
+        tk.at(t, n, oy0, ox0);
+        const int ox = ox0 + lane, oy1 = min(Ho, oy0 + kStemRows);
+        const float* xn = x + (long long)n * 3 * plane;
+        const float* gn = dy + ((long long)n * kStemCo + 4 * g) * Ho * Wo;
+        StemWin win;
+        float e[3], o[3], ed[3];
+        stem_load_row<VEC2>(xn, plane, 2 * oy0, H, W, ox, lane, true, e, o, ed);
+        stem_set_row(win, 0, e, o, ed, lane);
+        for (int oyb = oy0; oyb < oy1; oyb += 2) {      // two output rows per batch of loads (four input rows + eight gradients)
+            float re[4][3], ro[4][3], rd[4][3], gv[2][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) stem_load_row<VEC2>(xn, plane, 2 * oyb + 1 + r, H, W, ox, lane, oyb + (r >> 1) < oy1, re[r], ro[r], rd[r]);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    gv[u][i] = (oyb + u < oy1 && ox < Wo) ? __ldg(gn + (long long)i * Ho * Wo + (long long)(oyb + u) * Wo + ox) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                stem_set_row(win, 1, re[2 * u], ro[2 * u], rd[2 * u], lane);
+                stem_set_row(win, 2, re[2 * u + 1], ro[2 * u + 1], rd[2 * u + 1], lane);
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float v = win.v[ci][ky][kx];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) acc[i][ci * 9 + ky * 3 + kx] = fmaf(gv[u][i], v, acc[i][ci * 9 + ky * 3 + kx]);
+                        }
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) win.v[ci][0][kx] = win.v[ci][2][kx];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < kStemK; ++k) {
+            const float s = warp_sumf(acc[i][k]);
+            if (lane == 0) red[warp][i * kStemK + k] = s;
+        }
+    __syncthreads();
+    if (threadIdx.x < 4 * kStemK) {
+        double tot = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < kStemWT / 32; ++wq) tot += (double)red[wq][threadIdx.x];
+        if (tot != 0.0) atomicAdd(dwacc + (4 * g) * kStemK + threadIdx.x, tot);      // dw[co][k], co = 4 g + i: contiguous over (i, k)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // the rest of the network's training-mode operators: dense 3x3 convolution (stem, aux head) through im2col + the GEMM
 // above, per-channel bias, bilinear resize with align_corners=True, adaptive average pooling (overlapping bins), dropout,
 // add + ReLU, and the SGD update
@@ -2235,6 +2408,36 @@ static int strip_grid(int n, int h, int w) {
     const long long strips = (long long)n * ((h + kStripRows - 1) / kStripRows) * ((w + 31) / 32);
     const long long ctas = (strips + kT / 32 - 1) / (kT / 32), cap = (long long)num_sms() * 16;
     return (int)(ctas < cap ? (ctas > 0 ? ctas : 1) : cap);
+}
+
+static StemTasks stem_tasks(int n, int ho, int wo) {
+    StemTasks t{(ho + kStemRows - 1) / kStemRows, (wo + 31) / 32, 0};
+    t.total = (long long)n * t.RB * t.CB;
+    return t;
+}
+// y [n][32][ho][wo] = conv3x3 stride 2 pad 0 of x [n][3][h][w] with w [32][3][3][3]
+cudaError_t launch_train_stem_fwd(const float* x, const float* w, float* y, int n, int h, int wd, cudaStream_t s) {
+    const int ho = (h - 3) / 2 + 1, wo = (wd - 3) / 2 + 1;
+    const StemTasks tk = stem_tasks(n, ho, wo);
+    const long long ctas = (tk.total + kT / 32 - 1) / (kT / 32), cap = (long long)num_sms() * 16;
+    const int grid = (int)(ctas < cap ? (ctas > 0 ? ctas : 1) : cap);
+    if (vec2_ok(wd, {x})) stem_fwd_kernel<true><<<grid, kT, 0, s>>>(x, w, y, h, wd, ho, wo, tk);
+    else stem_fwd_kernel<false><<<grid, kT, 0, s>>>(x, w, y, h, wd, ho, wo, tk);
+    return cudaGetLastError();
+}
+// dw [32][3][3][3]; ws: 864 doubles
+cudaError_t launch_train_stem_wgrad(const float* x, const float* dy, float* dw, void* ws, int n, int h, int wd, cudaStream_t s) {
+    const int ho = (h - 3) / 2 + 1, wo = (wd - 3) / 2 + 1;
+    double* dwacc = reinterpret_cast<double*>(ws);
+    cudaError_t e = cudaMemsetAsync(dwacc, 0, (size_t)kStemCo * kStemK * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    const StemTasks tk = stem_tasks(n, ho, wo);
+    const long long want = (tk.total + kStemWT / 32 - 1) / (kStemWT / 32), cap = (long long)num_sms() * 3 / 4;
+    const dim3 grid((unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 8);
+    if (vec2_ok(wd, {x})) stem_wgrad_kernel<true><<<grid, kStemWT, 0, s>>>(x, dy, dwacc, h, wd, ho, wo, tk);
+    else stem_wgrad_kernel<false><<<grid, kStemWT, 0, s>>>(x, dy, dwacc, h, wd, ho, wo, tk);
+    double_to_float_kernel<<<(kStemCo * kStemK + kT - 1) / kT, kT, 0, s>>>(dwacc, dw, kStemCo * kStemK);
+    return cudaGetLastError();
 }
 
 static UpGeom up_geom(int c, int hl, int wl, int h, int w) {

@@ -495,7 +495,41 @@ class AddReLU(torch.autograd.Function):
         return g, g, None
 
 
+class StemConv(torch.autograd.Function):
+    """nn.Conv2d(3, 32, 3, stride=2, padding=0, bias=False), the network's first layer (models/fast_scnn.py:153), without the column
+    matrix: the input window walks down the rows in registers (csrc/train.cu, stem_fwd_kernel / stem_wgrad_kernel).  The input
+    image takes no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        x, w = _check(x, 'input'), _check(weight, 'weight')
+        n, c, h, wd = x.shape
+        ho, wo = (h - 3) // 2 + 1, (wd - 3) // 2 + 1
+        y = torch.empty((n, 32, ho, wo), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            native.check(_lib().fscnn_train_stem_forward(x.data_ptr(), w.data_ptr(), y.data_ptr(), n, h, wd, _stream()), 'fscnn_train_stem_forward')
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        if not ctx.needs_input_grad[1]:
+            return None, None
+        dy = dy.contiguous()
+        n, c, h, wd = x.shape
+        dw = torch.empty_like(w)
+        ws = _workspace(x.device, 32)
+        with torch.cuda.device(x.device):
+            native.check(_lib().fscnn_train_stem_weight_grad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), ws.data_ptr(), ws.numel(), n, h, wd,
+                                                             _stream()), 'fscnn_train_stem_weight_grad')
+        return None, dw
+
+
 def conv3x3_dense(x, weight, stride, pad):
+    if (tuple(weight.shape) == (32, 3, 3, 3) and int(stride) == 2 and int(pad) == 0 and x.dim() == 4 and x.shape[1] == 3
+            and x.shape[2] >= 3 and x.shape[3] >= 3 and not x.requires_grad):
+        return StemConv.apply(x, weight)
     return Conv3x3Dense.apply(x, weight, int(stride), int(pad))
 
 

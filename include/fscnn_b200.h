@@ -261,6 +261,12 @@ int fscnn_train_batchnorm_backward(const float* d_x, const float* d_dy, const fl
  *  add_relu / relu_backward : y = relu(a + b) (relu = 0: plain add; FFM :217-218, residuals :114) and g = dy * [y > 0]
  *  sgd_step  : torch.optim.SGD(momentum, weight_decay) on flat buffers: g' = grad * grad_scale + wd * p;
  *              buf = first_step ? g' : momentum * buf + g'; p -= lr * buf */
+/* The stem, LearningToDownsample.conv = nn.Conv2d(3, 32, 3, stride 2, padding 0, bias=False) (fast_scnn.py:153), without the column
+ * matrix: d_x [n][3][h][w], d_w [32][3][3][3], d_y / d_dy [n][32][(h-3)/2+1][(w-3)/2+1]; the weight gradient wants the training
+ * workspace (fscnn_train_workspace_bytes(32, 1, 1)).  The input image has no gradient. */
+int fscnn_train_stem_forward(const float* d_x, const float* d_w, float* d_y, int n, int h, int w, void* stream);
+int fscnn_train_stem_weight_grad(const float* d_x, const float* d_dy, float* d_dw, void* d_ws, size_t ws_bytes, int n, int h, int w,
+                                 void* stream);
 int fscnn_train_im2col3x3(const float* d_x, float* d_cols, int n, int c, int h, int w, int stride, int pad, void* stream);
 int fscnn_train_col2im3x3(const float* d_dcols, float* d_dx, int n, int c, int h, int w, int stride, int pad, void* stream);
 int fscnn_train_bias_add(float* d_y, const float* d_bias, int n, int c, int hw, void* stream);

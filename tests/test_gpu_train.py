@@ -467,3 +467,32 @@ def test_tf32_training_step_against_cudnn_tf32():
     finally:
         torch.backends.cudnn.allow_tf32 = old_tf32
         train_ops.set_matmul_precision('fp32')
+
+
+@pytest.mark.parametrize('n,h,w', [(2, 65, 97), (1, 96, 160), (2, 70, 131), (1, 35, 36)])
+def test_stem_conv_direct_kernels_against_torch(n, h, w):
+    """The direct stem kernels (Conv2d(3, 32, 3, stride 2, padding 0): window in registers, no column matrix) against F.conv2d in
+    float64, forward and weight gradient, at even and odd widths (8-byte row loads or not), partial column / row blocks; and
+    against the im2col path they replace (taken when the input wants a gradient)."""
+    import torch.nn.functional as F
+    from fscnn_b200 import train_ops
+    g = torch.Generator(device='cpu').manual_seed(7 * h + w)
+    x = torch.randn(n, 3, h, w, generator=g).to(DEV)
+    wt0 = (torch.randn(32, 3, 3, 3, generator=g) / 5).to(DEV)
+    ho, wo = (h - 3) // 2 + 1, (w - 3) // 2 + 1
+    dy = torch.randn(n, 32, ho, wo, generator=g).to(DEV)
+    wt = wt0.clone().requires_grad_(True)
+    y = train_ops.conv3x3_dense(x, wt, 2, 0)
+    assert y.grad_fn is not None and 'StemConv' in type(y.grad_fn).__name__
+    y.backward(dy)
+    wr = wt0.double().requires_grad_(True)
+    yr = F.conv2d(x.double(), wr, None, 2, 0)
+    yr.backward(dy.double())
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().float().cpu().numpy()) < 2e-6
+    assert rel_err(wt.grad.cpu().numpy(), wr.grad.float().cpu().numpy()) < 5e-6
+    xg, wt2 = x.clone().requires_grad_(True), wt0.clone().requires_grad_(True)
+    y2 = train_ops.conv3x3_dense(xg, wt2, 2, 0)              # the im2col path (input gradient wanted)
+    assert 'Conv3x3Dense' in type(y2.grad_fn).__name__
+    y2.backward(dy)
+    assert rel_err(y.detach().cpu().numpy(), y2.detach().cpu().numpy()) < 2e-6
+    assert rel_err(wt.grad.cpu().numpy(), wt2.grad.cpu().numpy()) < 5e-6
