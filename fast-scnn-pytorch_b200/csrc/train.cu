@@ -1731,7 +1731,7 @@ ohem_strip_grad_kernel(const float* __restrict__ low, const long long* __restric
             for (int c = 0; c < CT; ++c) { v[c] = rows.value(c, ly); mx = fmaxf(mx, v[c]); }
             float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) { v[c] = expf(v[c] - mx); sum += v[c]; }
+            for (int c = 0; c < CT; ++c) { v[c] = __expf(v[c] - mx); sum += v[c]; }      // (ex2.approx: 2e-7 relative here, the gradient tolerates it; the selection and the loss keep expf)
             const float w = (weight ? __ldg(weight + lab) : 1.f) * scale, inv = 1.f / sum, hy = 1.f - ly;
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
