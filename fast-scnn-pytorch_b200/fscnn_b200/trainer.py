@@ -57,12 +57,14 @@ class Trainer:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.momentum_buf = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
+        self._grad_views = []
         with torch.no_grad():
             for p in params:      # parameters and their gradients become views into the flat buffers
                 n = p.numel()
                 self.flat_param[off:off + n].copy_(p.reshape(-1))
                 p.data = self.flat_param[off:off + n].view_as(p)
-                p.grad = self.flat_grad[off:off + n].view_as(p)
+                self._grad_views.append(self.flat_grad[off:off + n].view_as(p))
+                p.grad = self._grad_views[-1]
                 off += n
         self.params = params
         self.base_lr, self.momentum, self.weight_decay = float(base_lr), float(momentum), float(weight_decay)
@@ -103,9 +105,6 @@ class Trainer:
         self.model.train()
         if lr is None:
             lr = poly_lr(self.base_lr, self.iteration, self.nepochs, self.iters_per_epoch)
-        for p in self.params:      # autograd accumulates into the flat-buffer views
-            if p.grad is None:
-                raise RuntimeError('a parameter lost its flat gradient view (zero_grad(set_to_none=True) was called on the model?)')
         if self.cuda_graph and self.iteration >= self.graph_warmup:
             loss = self._graph_forward_backward(images, target)
         else:
@@ -118,12 +117,25 @@ class Trainer:
         return loss
 
     def _forward_backward(self, images, target):
-        self.flat_grad.zero_()
+        """zero_grad + forward + loss + backward, leaving the gradients in the flat buffer.  With .grad pointing at the flat views
+        autograd would ADD every produced gradient to it (148 small kernels per step on top of zeroing the buffer); instead .grad is
+        cleared, autograd stores the gradients it produces, and one multi-tensor copy moves them into the flat views, which .grad
+        then points at again (what zero_grad(set_to_none=True) + backward leaves, packed)."""
+        for p in self.params:
+            p.grad = None
         if self.fused_loss and hasattr(self.model, '_train_forward_lowres'):
             loss = self.loss_from_lowres(self.model._train_forward_lowres(images), target)
         else:
             loss = self.loss(self.model(images), target)
         loss.backward()
+        with torch.no_grad():
+            missing = [v for p, v in zip(self.params, self._grad_views) if p.grad is None]
+            if missing:                      # a parameter that took no part in this forward: its gradient is zero
+                torch._foreach_zero_(missing)
+            have = [(v, p.grad) for p, v in zip(self.params, self._grad_views) if p.grad is not None]
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for p, v in zip(self.params, self._grad_views):
+            p.grad = v
         return loss.detach()
 
     def _graph_forward_backward(self, images, target):
