@@ -337,6 +337,9 @@ int run_stages(fscnn_ctx* c, const void* x, int m, const Dims& d, const WsPlan& 
     cudaError_t e = cudaSuccess;
     auto at = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
     auto atf = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    // programmatic dependent launch for launch sets of up to 16 Mpixel of input (8 Cityscapes images); the tail kernel launched
+    // after this call for the same images follows the same hint
+    pdl_hint() = (long long)m * d.h * d.w <= (16ll << 20);
     for (int st = first; st <= last && e == cudaSuccess; ++st) {
         if (st == kStem && last >= kDs1 && front_fused<T>(c, x, at(p.ds1), m, d, s, &e)) {
             ++st;   // dsconv1 is done too

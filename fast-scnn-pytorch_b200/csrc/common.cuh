@@ -137,10 +137,17 @@ inline int num_sms() {
     return v;
 }
 
-// FSCNN_NO_PDL=1 launches the stage kernels without the programmatic-serialization attribute (A/B switch, bench.py --latency)
+// Whether the stage kernels launched next by this thread get the programmatic-serialization attribute.  The forward sets the hint
+// per launch set (api.cu run_stages): on for small ones, where a stage lives tens of microseconds and its set-up is worth hiding;
+// off for the large micro-batches of the throughput regime, where the overlap buys nothing and measured 0.7 % slower (17 326 vs
+// 17 452 images/s at 111 images per launch, twice).  FSCNN_NO_PDL=1 / FSCNN_PDL_ALWAYS=1 force it off / on (A/B switches).
+inline bool& pdl_hint() {
+    static thread_local bool hint = true;
+    return hint;
+}
 inline bool pdl_enabled() {
-    static const bool on = getenv("FSCNN_NO_PDL") == nullptr;
-    return on;
+    static const bool off = getenv("FSCNN_NO_PDL") != nullptr, always = getenv("FSCNN_PDL_ALWAYS") != nullptr;
+    return !off && (always || pdl_hint());
 }
 
 // Opt a kernel into `bytes` of dynamic shared memory once per device (the attribute is per context).

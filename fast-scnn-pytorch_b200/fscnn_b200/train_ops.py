@@ -117,7 +117,7 @@ class PointwiseConv(torch.autograd.Function):
         cout = w.shape[0]
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx = torch.empty_like(x) if need_dx else None
-        dw = torch.zeros_like(w) if need_dw else None
+        dw = (torch.zeros_like(w) if n > 64 else torch.empty_like(w)) if need_dw else None      # chunks of 64 images accumulate
         if dx is None and dw is None:
             return None, None
         ws = _workspace(x.device, 1, cout, cin)
@@ -334,7 +334,7 @@ class Conv3x3Dense(torch.autograd.Function):
         dy = dy.contiguous()
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dcols = torch.empty_like(cols) if need_dx else None
-        dw = torch.zeros_like(w) if need_dw else None
+        dw = (torch.zeros_like(w) if n > 64 else torch.empty_like(w)) if need_dw else None      # chunks of 64 images accumulate
         ws = _workspace(dy.device, 1, cout, c * 9)
         with torch.cuda.device(dy.device):
             for i0 in range(0, n, 64):
