@@ -138,9 +138,9 @@ inline int num_sms() {
 }
 
 // Whether the stage kernels launched next by this thread get the programmatic-serialization attribute.  The forward sets the hint
-// per launch set (api.cu run_stages): on for small ones, where a stage lives tens of microseconds and its set-up is worth hiding;
-// off for the large micro-batches of the throughput regime, where the overlap buys nothing and measured 0.7 % slower (17 326 vs
-// 17 452 images/s at 111 images per launch, twice).  FSCNN_NO_PDL=1 / FSCNN_PDL_ALWAYS=1 force it off / on (A/B switches).
+// per launch set (api.cu run_stages): on up to 160 Mpixel of input, where a stage's set-up is worth hiding (batch 1: -4.5 % latency;
+// 16 / 32 / 64 images per launch: +3.1 / +1.5 / +0.1 % images/s); off for the largest micro-batches, where it measured 0.7 % slower
+// (17 326 vs 17 452 images/s at 111 images per launch, twice).  FSCNN_NO_PDL=1 / FSCNN_PDL_ALWAYS=1 force it off / on (A/B switches).
 inline bool& pdl_hint() {
     static thread_local bool hint = true;
     return hint;
