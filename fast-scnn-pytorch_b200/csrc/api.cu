@@ -1002,13 +1002,13 @@ int fscnn_train_ohem_backward(const float* d_logits, const long long* d_label, c
 }
 
 int fscnn_train_ohem_upsampled_forward(const float* d_low_logits, const long long* d_label, const float* d_class_weight, float* d_prob,
-                                       float* d_out3, void* d_ws, size_t ws_bytes, int n, int c, int hl, int wl, int h, int w,
+                                       float* d_nll, float* d_out3, void* d_ws, size_t ws_bytes, int n, int c, int hl, int wl, int h, int w,
                                        long long ignore_label, float thresh, int min_kept, void* stream) {
     if (!d_low_logits || !d_label || !d_prob || !d_out3) return fail(FSCNN_EINVAL, "null device pointer");
     if (n < 1 || c < 1 || hl < 1 || wl < 1 || h < 1 || w < 1 || min_kept < 0) return fail(FSCNN_EINVAL, "bad shape");
     int rc = train_ws_ok(d_ws, ws_bytes, train_ohem_workspace_bytes());
     if (rc) return rc;
-    cudaError_t e = launch_train_ohem_up_fwd(d_low_logits, d_label, d_class_weight, d_prob, d_out3, d_ws, n, c, hl, wl, h, w, ignore_label,
+    cudaError_t e = launch_train_ohem_up_fwd(d_low_logits, d_label, d_class_weight, d_prob, d_nll, d_out3, d_ws, n, c, hl, wl, h, w, ignore_label,
                                              thresh, min_kept, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(FSCNN_ECUDA, "fused upsample + OHEM forward launch failed: %s", cudaGetErrorString(e));
     return FSCNN_OK;

@@ -152,7 +152,7 @@ cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float*
 cudaError_t launch_train_bn_bwd(const float* x, const float* dy, const float* gamma, const float* beta, const float* save_mean,
                                 const float* save_rstd, float* dx, float* dgamma, float* dbeta, void* ws, int n, int c, int hw,
                                 int relu, cudaStream_t s);
-cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, const float* weight, float* prob, float* out3, void* ws,
+cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, const float* weight, float* prob, float* nll, float* out3, void* ws,
                                      int n, int c, int hl, int wl, int h, int w, long long ignore, float thresh, int min_kept,
                                      cudaStream_t s);
 cudaError_t launch_train_ohem_up_bwd(const float* low, const long long* label, const float* weight, const float* prob, const float* out3,

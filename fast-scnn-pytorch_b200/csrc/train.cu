@@ -1522,8 +1522,8 @@ struct StripIter {          // strips ordered (image, row block, column strip): 
 
 template <int CT>
 __global__ void __launch_bounds__(kT)
-ohem_strip_prob_kernel(const float* __restrict__ low, const long long* __restrict__ label, float* __restrict__ prob, UpGeom g, int nimg,
-                       long long ignore, unsigned long long* __restrict__ state) {
+ohem_strip_prob_kernel(const float* __restrict__ low, const long long* __restrict__ label, float* __restrict__ prob,
+                       float* __restrict__ nll_out, UpGeom g, int nimg, long long ignore, unsigned long long* __restrict__ state) {
     const int lane = threadIdx.x & 31;
     const StripIter it(g, nimg);
     unsigned int valid = 0;
@@ -1554,27 +1554,50 @@ ohem_strip_prob_kernel(const float* __restrict__ low, const long long* __restric
             if (x >= g.W) continue;
             const long long i = ((long long)n * g.H + y) * g.W + x;
             const long long lab = labs[j];
-            float out = __uint_as_float(0x7f800000u);
+            float out = __uint_as_float(0x7f800000u), nll = 0.f;
             if (lab != ignore) {
                 valid += 1;
                 float v[CT], mx = -FLT_MAX;
 #pragma unroll
                 for (int c = 0; c < CT; ++c) { v[c] = rows.value(c, ly); mx = fmaxf(mx, v[c]); }
-                float sum = 0.f, el = 0.f;
+                float sum = 0.f, el = 0.f, vl = 0.f;
 #pragma unroll
                 for (int c = 0; c < CT; ++c) {
                     const float e = expf(v[c] - mx);
                     sum += e;
-                    if (c == lab) el = e;
+                    if (c == lab) { el = e; vl = v[c]; }
                 }
                 out = el / sum;
+                nll = -((vl - mx) - logf(sum));      // the loss kernel's own expression on the same values: it only has to read it
             }
             prob[i] = out;
+            if (nll_out) nll_out[i] = nll;
         }
         }
     }
     valid = (unsigned int)warp_sumf((float)valid);
     if (lane == 0 && valid) atomicAdd(state, (unsigned long long)valid);
+}
+
+// the loss over the kept pixels from the per-pixel negative log-likelihood the probability kernel left behind
+__global__ void __launch_bounds__(kT)
+ohem_nll_loss_kernel(const long long* __restrict__ label, const float* __restrict__ prob, const float* __restrict__ nll,
+                     const float* __restrict__ weight, long long npix, long long ignore, const unsigned long long* __restrict__ state,
+                     double* __restrict__ partial) {
+    __shared__ double sm[2 * 8];
+    const bool keep_all = state[4] != 0ull;
+    const float thr = __uint_as_float((unsigned int)state[3]);
+    double acc[2] = {0.0, 0.0};
+#pragma unroll 4
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long lab = __ldg(label + i);
+        if (lab == ignore || !(keep_all || __ldg(prob + i) <= thr)) continue;
+        const float w = weight ? __ldg(weight + lab) : 1.f;
+        acc[0] += (double)w * (double)__ldg(nll + i);
+        acc[1] += (double)w;
+    }
+    block_sum<2>(acc, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x * 2] = acc[0]; partial[blockIdx.x * 2 + 1] = acc[1]; }
 }
 
 template <int CT>
@@ -2458,8 +2481,8 @@ static UpGeom up_geom(int c, int hl, int wl, int h, int w) {
     return g;
 }
 
-cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, const float* weight, float* prob, float* out3, void* ws,
-                                     int n, int c, int hl, int wl, int h, int w, long long ignore, float thresh, int min_kept,
+cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, const float* weight, float* prob, float* nll, float* out3,
+                                     void* ws, int n, int c, int hl, int wl, int h, int w, long long ignore, float thresh, int min_kept,
                                      cudaStream_t s) {
     const long long npix = (long long)n * h * w;
     unsigned long long* state = reinterpret_cast<unsigned long long*>(ws);
@@ -2469,14 +2492,19 @@ cudaError_t launch_train_ohem_up_fwd(const float* low, const long long* label, c
     if (e != cudaSuccess) return e;
     const UpGeom g = up_geom(c, hl, wl, h, w);
     const int grid = grid_for(npix), sgrid = strip_grid(n, h, w);
-    if (c == 19) ohem_strip_prob_kernel<19><<<sgrid, kT, 0, s>>>(low, label, prob, g, n, ignore, state);
-    else if (c == 2) ohem_strip_prob_kernel<2><<<sgrid, kT, 0, s>>>(low, label, prob, g, n, ignore, state);
+    const bool strip = c == 19 || c == 2;
+    if (c == 19) ohem_strip_prob_kernel<19><<<sgrid, kT, 0, s>>>(low, label, prob, nll, g, n, ignore, state);
+    else if (c == 2) ohem_strip_prob_kernel<2><<<sgrid, kT, 0, s>>>(low, label, prob, nll, g, n, ignore, state);
     else ohem_up_prob_kernel<0><<<grid, kT, 0, s>>>(low, label, prob, g, npix, ignore, state);
     for (int shift = 24; shift >= 0; shift -= 8) {
         ohem_hist_kernel<<<grid, kT, 0, s>>>(prob, npix, shift, state, hist);
         ohem_select_kernel<<<1, 256, 0, s>>>(state, hist, shift, min_kept, thresh);
     }
-    const bool strip = c == 19 || c == 2;
+    if (strip && nll) {
+        ohem_nll_loss_kernel<<<grid, kT, 0, s>>>(label, prob, nll, weight, npix, ignore, state, partial);
+        ohem_finalize_kernel<<<1, kT, 0, s>>>(partial, grid, state, out3);
+        return cudaGetLastError();
+    }
     if (c == 19) ohem_strip_loss_kernel<19><<<sgrid, kT, 0, s>>>(low, label, prob, weight, g, n, ignore, state, partial);
     else if (c == 2) ohem_strip_loss_kernel<2><<<sgrid, kT, 0, s>>>(low, label, prob, weight, g, n, ignore, state, partial);
     else ohem_up_loss_kernel<0><<<grid, kT, 0, s>>>(low, label, prob, weight, g, npix, ignore, state, partial);

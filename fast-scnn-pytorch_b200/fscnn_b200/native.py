@@ -98,7 +98,7 @@ _SIGNATURES = {
                                            C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int, C.c_void_p]),
     'fscnn_train_ohem_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]),
-    'fscnn_train_ohem_upsampled_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+    'fscnn_train_ohem_upsampled_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int,
                                                      C.c_void_p]),
     'fscnn_train_ohem_upsampled_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

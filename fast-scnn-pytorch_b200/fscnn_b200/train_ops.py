@@ -238,11 +238,12 @@ class OhemCrossEntropyUpsampled(torch.autograd.Function):
         native.check(native.lib().fscnn_train_ohem_workspace_bytes(C.byref(need)))
         ws = torch.empty(need.value, dtype=torch.uint8, device=low.device)
         prob = torch.empty((n, h, w), dtype=torch.float32, device=low.device)
+        nll = torch.empty((n, h, w), dtype=torch.float32, device=low.device)      # scratch of the forward only (not saved)
         out3 = torch.empty(3, dtype=torch.float32, device=low.device)
         with torch.cuda.device(low.device):
             native.check(native.lib().fscnn_train_ohem_upsampled_forward(
                 low.data_ptr(), target.data_ptr(), class_weight.data_ptr() if class_weight is not None else None, prob.data_ptr(),
-                out3.data_ptr(), ws.data_ptr(), ws.numel(), n, c, hl, wl, h, w, int(ignore_label), float(thresh), int(min_kept), _stream()),
+                nll.data_ptr(), out3.data_ptr(), ws.data_ptr(), ws.numel(), n, c, hl, wl, h, w, int(ignore_label), float(thresh), int(min_kept), _stream()),
                 'fscnn_train_ohem_upsampled_forward')
         ctx.save_for_backward(low, target, prob, out3, ws)
         ctx.class_weight, ctx.ignore_label = class_weight, int(ignore_label)

@@ -309,9 +309,12 @@ int fscnn_train_ohem_backward(const float* d_logits, const long long* d_label, c
  * cross entropy, so the full-resolution logits and their gradient (717 MB each per head at 16 x 19 x 768 x 768) never exist.
  * Selection and loss are bit-identical to fscnn_train_bilinear + fscnn_train_ohem_forward; the backward writes
  * d_dlow [n][c][hl][wl] = d_grad_out[0] * d loss / d low-resolution logits (float atomics: summation order not deterministic).
- * The backward needs (hl-1)*7 <= h-1, (wl-1)*7 <= w-1 and c <= 128. */
+ * d_nll (may be NULL): [n][h][w] float32 scratch; with it (and 2 or 19 classes) the probability pass leaves each pixel's negative
+ * log-likelihood there and the loss pass only reads it instead of interpolating and exponentiating all classes a second time
+ * (same expression on the same values: the loss stays bit-identical).
+ * The backward needs (hl-1)*7 <= h-1, (wl-1)*7 <= w-1 and c <= 128 unless c is 2 or 19. */
 int fscnn_train_ohem_upsampled_forward(const float* d_low_logits, const long long* d_label, const float* d_class_weight, float* d_prob,
-                                       float* d_out3, void* d_ws, size_t ws_bytes, int n, int c, int hl, int wl, int h, int w,
+                                       float* d_nll, float* d_out3, void* d_ws, size_t ws_bytes, int n, int c, int hl, int wl, int h, int w,
                                        long long ignore_label, float thresh, int min_kept, void* stream);
 int fscnn_train_ohem_upsampled_backward(const float* d_low_logits, const long long* d_label, const float* d_class_weight, const float* d_prob,
                                         const float* d_out3, const float* d_grad_out, float* d_dlow, const void* d_ws, int n, int c, int hl,
