@@ -2071,15 +2071,20 @@ bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int Hi
 
 // nn.AdaptiveAvgPool2d(S): bin i covers [floor(i*h/S), ceil((i+1)*h/S)); bins overlap when h % S != 0
 __global__ void __launch_bounds__(kT)
-adaptive_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int S, long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+adaptive_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int S, long long total) {      // a warp per bin
+    const int lane = threadIdx.x & 31;
+    for (long long i = (long long)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); i < total; i += (long long)gridDim.x * (kT / 32)) {
         const int bx = (int)(i % S), by = (int)((i / S) % S);
         const float* xp = x + (i / (S * S)) * H * W;
         const int y0 = (by * H) / S, y1 = ((by + 1) * H + S - 1) / S, x0 = (bx * W) / S, x1 = ((bx + 1) * W + S - 1) / S;
+        const int bw = x1 - x0, cnt = (y1 - y0) * bw;
         float acc = 0.f;
-        for (int yy = y0; yy < y1; ++yy)
-            for (int xx = x0; xx < x1; ++xx) acc += __ldg(xp + yy * W + xx);
-        y[i] = acc / (float)((y1 - y0) * (x1 - x0));
+        for (int e = lane; e < cnt; e += 32) {
+            const int r = e / bw;
+            acc += __ldg(xp + (y0 + r) * W + x0 + (e - r * bw));
+        }
+        acc = warp_sumf(acc);
+        if (lane == 0) y[i] = acc / (float)cnt;
     }
 }
 
@@ -2411,7 +2416,7 @@ cudaError_t launch_train_bilinear(const float* in, float* out, int planes, int h
 cudaError_t launch_train_adaptive_pool(const float* in, float* out, int planes, int h, int wd, int bins, int backward, cudaStream_t s) {
     if (!backward) {
         const long long total = (long long)planes * bins * bins;
-        adaptive_pool_fwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, h, wd, bins, total);
+        adaptive_pool_fwd_kernel<<<grid_for(total * 32), kT, 0, s>>>(in, out, h, wd, bins, total);
     } else {      // in = dy [planes][S][S], out = dx [planes][h][w]
         const long long total = (long long)planes * h * wd;
         adaptive_pool_bwd_kernel<<<grid_for(total), kT, 0, s>>>(in, out, h, wd, bins, total);
