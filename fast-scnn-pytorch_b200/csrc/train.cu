@@ -945,13 +945,25 @@ bn_stats_kernel(const float* __restrict__ x, double* __restrict__ partial, int N
     if (threadIdx.x == 0) { partial[((long long)blockIdx.y * C + c) * 2] = v[0]; partial[((long long)blockIdx.y * C + c) * 2 + 1] = v[1]; }
 }
 
-// The S partial pairs of channel c summed by the calling warp (every lane returns the totals; fixed order, so every CTA that needs
-// a channel's statistics derives bit-identical values and no finalising launch sits between the reduction and the elementwise pass).
-__device__ __forceinline__ void chan_totals(const double* __restrict__ partial, int C, int S, int c, double& s, double& ss) {
-    s = ss = 0.0;
-    for (int k = threadIdx.x & 31; k < S; k += 32) { s += partial[((long long)k * C + c) * 2]; ss += partial[((long long)k * C + c) * 2 + 1]; }
-    s = warp_sum(s);
-    ss = warp_sum(ss);
+// mean / biased variance -> save_mean, save_rstd; running stats with momentum and the UNBIASED variance (PyTorch semantics)
+__global__ void __launch_bounds__(kT)
+bn_finalize_kernel(const double* __restrict__ partial, int C, int S, long long count, float eps, float momentum,
+                   float* __restrict__ save_mean, float* __restrict__ save_rstd, float* __restrict__ running_mean,
+                   float* __restrict__ running_var) {
+    const int c = blockIdx.x * kT + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < S; ++k) { s += partial[((long long)k * C + c) * 2]; ss += partial[((long long)k * C + c) * 2 + 1]; }
+    const double mean = s / (double)count;
+    double var = ss / (double)count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
+    }
 }
 
 // elementwise passes: grid (planes = N*C, chunks); a CTA owns kT * 16 consecutive elements of one plane, so the channel's constants
@@ -960,35 +972,10 @@ constexpr int kEltChunk = kT * 16;
 
 template <bool VEC>
 __global__ void __launch_bounds__(kT)
-bn_apply_kernel(const float* __restrict__ x, const double* __restrict__ partial, int S, long long count, float eps, float momentum,
-                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ save_mean, float* __restrict__ save_rstd,
-                float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ y, int C, int HW, int relu) {
-    __shared__ float stat[2];
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y, int C, int HW, int relu) {
     const int c = blockIdx.x % C;
-    if (threadIdx.x < 32) {
-        // mean / biased variance -> save_mean, save_rstd; running stats with momentum and the UNBIASED variance (PyTorch semantics),
-        // written by the one CTA that owns the first chunk of the channel's first plane
-        double sx, sxx;
-        chan_totals(partial, C, S, c, sx, sxx);
-        const double mean = sx / (double)count;
-        double var = sxx / (double)count - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float mu_f = (float)mean, rs_f = (float)(1.0 / sqrt(var + (double)eps));
-        if (threadIdx.x == 0) {
-            stat[0] = mu_f; stat[1] = rs_f;
-            if ((int)blockIdx.x < C && blockIdx.y == 0) {
-                save_mean[c] = mu_f;
-                save_rstd[c] = rs_f;
-                if (running_mean) {
-                    const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
-                    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
-                    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unbiased);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const float mu = stat[0], rs = stat[1], ga = __ldg(gamma + c), be = __ldg(beta + c);
+    const float mu = __ldg(mean + c), rs = __ldg(rstd + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
     const long long base = (long long)blockIdx.x * HW;
     const int lo = blockIdx.y * kEltChunk, hi = min(HW, lo + kEltChunk);
     const float floor_ = relu ? 0.f : -FLT_MAX;
@@ -1051,26 +1038,26 @@ bn_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
     if (threadIdx.x == 0) { partial[((long long)blockIdx.y * C + c) * 2] = v[0]; partial[((long long)blockIdx.y * C + c) * 2 + 1] = v[1]; }
 }
 
-// dbeta = sum g, dgamma = sum g*xhat (from the reduction's partials, see chan_totals); dx = gamma * rstd * (g - dbeta/m - xhat * dgamma/m)
+// dbeta = sum g, dgamma = sum g*xhat; dx = gamma * rstd * (g - dbeta/m - xhat * dgamma/m)
+__global__ void __launch_bounds__(kT)
+bn_bwd_finalize_kernel(const double* __restrict__ partial, int C, int S, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int c = blockIdx.x * kT + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < S; ++k) { s += partial[((long long)k * C + c) * 2]; ss += partial[((long long)k * C + c) * 2 + 1]; }
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)ss;
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(kT)
 bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    const double* __restrict__ partial, int S, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx,
-                    int C, int HW, int relu, float inv_count) {
-    __shared__ float tot[2];
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ dx, int C, int HW,
+                    int relu, float inv_count) {
     const int c = blockIdx.x % C;
-    if (threadIdx.x < 32) {
-        double sg, sgx;
-        chan_totals(partial, C, S, c, sg, sgx);
-        if (threadIdx.x == 0) {
-            tot[0] = (float)sg; tot[1] = (float)sgx;
-            if ((int)blockIdx.x < C && blockIdx.y == 0) { dbeta[c] = (float)sg; dgamma[c] = (float)sgx; }
-        }
-    }
-    __syncthreads();
     const float mu = __ldg(mean + c), rs = __ldg(rstd + c), ga = __ldg(gamma + c), be = __ldg(beta + c);
-    const float k0 = ga * rs, k1 = tot[0] * inv_count, k2 = tot[1] * inv_count;
+    const float k0 = ga * rs, k1 = __ldg(dbeta + c) * inv_count, k2 = __ldg(dgamma + c) * inv_count;
     const long long base = (long long)blockIdx.x * HW;
     const int lo = blockIdx.y * kEltChunk, hi = min(HW, lo + kEltChunk);
     auto one = [&](float xv, float g) {
@@ -2326,12 +2313,11 @@ cudaError_t launch_train_bn_fwd(const float* x, const float* gamma, const float*
     const bool vec = vec4_ok(hw, {x, y});
     if (vec) bn_stats_kernel<true><<<dim3(c, S), kT, 0, s>>>(x, partial, n, c, hw);
     else bn_stats_kernel<false><<<dim3(c, S), kT, 0, s>>>(x, partial, n, c, hw);
+    bn_finalize_kernel<<<(c + kT - 1) / kT, kT, 0, s>>>(partial, c, S, (long long)n * hw, eps, momentum, save_mean, save_rstd,
+                                                         running_mean, running_var);
     const dim3 grid(n * c, (hw + kEltChunk - 1) / kEltChunk);
-    const long long count = (long long)n * hw;
-    if (vec) bn_apply_kernel<true><<<grid, kT, 0, s>>>(x, partial, S, count, eps, momentum, gamma, beta, save_mean, save_rstd, running_mean,
-                                                      running_var, y, c, hw, relu);
-    else bn_apply_kernel<false><<<grid, kT, 0, s>>>(x, partial, S, count, eps, momentum, gamma, beta, save_mean, save_rstd, running_mean,
-                                                    running_var, y, c, hw, relu);
+    if (vec) bn_apply_kernel<true><<<grid, kT, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, c, hw, relu);
+    else bn_apply_kernel<false><<<grid, kT, 0, s>>>(x, save_mean, save_rstd, gamma, beta, y, c, hw, relu);
     return cudaGetLastError();
 }
 
@@ -2344,10 +2330,11 @@ cudaError_t launch_train_bn_bwd(const float* x, const float* dy, const float* ga
     const bool vec = vec4_ok(hw, {x, dy, dx});
     if (vec) bn_bwd_reduce_kernel<true><<<dim3(c, S), kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, partial, n, c, hw, relu);
     else bn_bwd_reduce_kernel<false><<<dim3(c, S), kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, partial, n, c, hw, relu);
+    bn_bwd_finalize_kernel<<<(c + kT - 1) / kT, kT, 0, s>>>(partial, c, S, dgamma, dbeta);
     const dim3 grid(n * c, (hw + kEltChunk - 1) / kEltChunk);
     const float inv = 1.f / (float)((long long)n * hw);
-    if (vec) bn_bwd_apply_kernel<true><<<grid, kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, partial, S, dgamma, dbeta, dx, c, hw, relu, inv);
-    else bn_bwd_apply_kernel<false><<<grid, kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, partial, S, dgamma, dbeta, dx, c, hw, relu, inv);
+    if (vec) bn_bwd_apply_kernel<true><<<grid, kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, dgamma, dbeta, dx, c, hw, relu, inv);
+    else bn_bwd_apply_kernel<false><<<grid, kT, 0, s>>>(x, dy, save_mean, save_rstd, gamma, beta, dgamma, dbeta, dx, c, hw, relu, inv);
     return cudaGetLastError();
 }
 
