@@ -123,10 +123,11 @@ class Trainer:
         then points at again (what zero_grad(set_to_none=True) + backward leaves, packed)."""
         for p in self.params:
             p.grad = None
-        if self.fused_loss and hasattr(self.model, '_train_forward_lowres'):
-            loss = self.loss_from_lowres(self.model._train_forward_lowres(images), target)
-        else:
-            loss = self.loss(self.model(images), target)
+        with train_ops.deferred_batch_counters():
+            if self.fused_loss and hasattr(self.model, '_train_forward_lowres'):
+                loss = self.loss_from_lowres(self.model._train_forward_lowres(images), target)
+            else:
+                loss = self.loss(self.model(images), target)
         loss.backward()
         with torch.no_grad():
             missing = [v for p, v in zip(self.params, self._grad_views) if p.grad is None]
