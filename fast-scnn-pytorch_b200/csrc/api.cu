@@ -1027,6 +1027,47 @@ int fscnn_train_ohem_upsampled_backward(const float* d_low_logits, const long lo
     return FSCNN_OK;
 }
 
+int fscnn_train_criterion_workspace_bytes(size_t* out) {
+    if (!out) return fail(FSCNN_EINVAL, "bad argument");
+    *out = train_criterion_workspace_bytes();
+    return FSCNN_OK;
+}
+
+static int criterion_args_ok(int kind, int n, int c, int hl, int wl, int h, int w, float gamma) {
+    if (kind < FSCNN_CRITERION_CE || kind > FSCNN_CRITERION_FOCAL_DICE) return fail(FSCNN_EINVAL, "unknown criterion %d", kind);
+    if (n < 1 || c < 1 || hl < 1 || wl < 1 || h < 1 || w < 1 || hl > h || wl > w) return fail(FSCNN_EINVAL, "bad shape");
+    if (kind == FSCNN_CRITERION_FOCAL_DICE && !(gamma >= 1.f)) return fail(FSCNN_EINVAL, "focal gamma %g < 1 is not supported", (double)gamma);
+    return FSCNN_OK;
+}
+
+int fscnn_train_criterion_forward(const float* d_logits, const long long* d_label, double* d_out6, void* d_ws, size_t ws_bytes, int kind,
+                                  int n, int c, int hl, int wl, int h, int w, long long ignore_label, float smooth, float alpha, float gamma,
+                                  float dice_weight, void* stream) {
+    if (!d_logits || !d_label || !d_out6) return fail(FSCNN_EINVAL, "null device pointer");
+    int rc = criterion_args_ok(kind, n, c, hl, wl, h, w, gamma);
+    if (rc) return rc;
+    rc = train_ws_ok(d_ws, ws_bytes, train_criterion_workspace_bytes());
+    if (rc) return rc;
+    cudaError_t e = launch_train_criterion_fwd(d_logits, d_label, d_out6, d_ws, kind, n, c, hl, wl, h, w, ignore_label, smooth, alpha, gamma,
+                                               dice_weight, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "criterion forward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
+int fscnn_train_criterion_backward(const float* d_logits, const long long* d_label, const double* d_out6, const float* d_grad_out,
+                                   float* d_dlogits, int kind, int n, int c, int hl, int wl, int h, int w, long long ignore_label, float smooth,
+                                   float alpha, float gamma, float dice_weight, void* stream) {
+    if (!d_logits || !d_label || !d_out6 || !d_grad_out || !d_dlogits) return fail(FSCNN_EINVAL, "null device pointer");
+    int rc = criterion_args_ok(kind, n, c, hl, wl, h, w, gamma);
+    if (rc) return rc;
+    if ((hl != h || wl != w) && ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1) || c > 128))
+        return fail(FSCNN_EINVAL, "the fused backward needs an upsampling ratio >= 7 and <= 128 classes (%dx%d -> %dx%d, %d classes)", hl, wl, h, w, c);
+    cudaError_t e = launch_train_criterion_bwd(d_logits, d_label, d_out6, d_grad_out, d_dlogits, kind, n, c, hl, wl, h, w, ignore_label, smooth,
+                                               alpha, gamma, dice_weight, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(FSCNN_ECUDA, "criterion backward launch failed: %s", cudaGetErrorString(e));
+    return FSCNN_OK;
+}
+
 #define FSCNN_TRAIN_CALL(expr, what)                                                                       \
     do {                                                                                                   \
         cudaError_t e_ = (expr);                                                                           \

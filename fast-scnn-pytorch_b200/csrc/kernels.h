@@ -175,5 +175,13 @@ cudaError_t launch_train_ohem_fwd(const float* logits, const long long* label, c
 cudaError_t launch_train_ohem_bwd(const float* logits, const long long* label, const float* weight, const float* prob,
                                   const float* out3, const float* gout, float* dlogits, const void* ws, int n, int c, int hw,
                                   long long ignore, cudaStream_t s);
+// the reference's other criteria (cross entropy / dice / focal + dice), at label resolution or fused with the head's final resize
+size_t train_criterion_workspace_bytes();
+cudaError_t launch_train_criterion_fwd(const float* logits, const long long* label, double* out6, void* ws, int kind, int n, int c, int hl,
+                                       int wl, int h, int w, long long ignore, float smooth, float alpha, float gamma, float dice_w,
+                                       cudaStream_t s);
+cudaError_t launch_train_criterion_bwd(const float* logits, const long long* label, const double* out6, const float* gout, float* dlogits,
+                                       int kind, int n, int c, int hl, int wl, int h, int w, long long ignore, float smooth, float alpha,
+                                       float gamma, float dice_w, cudaStream_t s);
 
 }  // namespace fscnn

@@ -2523,4 +2523,341 @@ cudaError_t launch_train_ohem_up_bwd(const float* low, const long long* label, c
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's other training criteria (utils/loss.py), per head, with or without the head's final resize fused in:
+//   kind 0  nn.CrossEntropyLoss(ignore_index) as MixSoftmaxCrossEntropyLoss applies it to every head (loss.py:103-124): mean of the
+//           negative log-likelihood over the pixels whose label is not ignore_label
+//   kind 1  DiceLoss (loss.py:12-39, train.py's DEFAULT --loss-type): p = softmax(x)[:, 1] (sigmoid for one channel), t = float(label)
+//           of EVERY pixel (no ignore label), 1 - (2 sum(p t) + smooth) / (sum p + sum t + smooth)
+//   kind 2  FocalDiceLoss (loss.py:71-100): (1 - dice_weight) * mean(alpha (1 - pt)^gamma ce) + dice_weight * DiceLoss, ce =
+//           F.cross_entropy(reduction='none') (labels equal to -100 contribute 0 but count in the mean) or, for one channel,
+//           F.binary_cross_entropy(sigmoid(x), t) with its log clamp at -100
+// (hl, wl) == (h, w): `logits` are at label resolution and the backward writes d loss / d logits directly (deterministic).
+// Otherwise `logits` are a head's low-resolution output and F.interpolate(size=(h, w), 'bilinear', align_corners=True)
+// (fast_scnn.py:40, :44) is composed with the criterion exactly as for the OHEM loss above: same interpolation arithmetic
+// (up_value), the full-resolution logits and their gradient never exist, the backward scatters through the resize's transpose
+// (shared-memory tile + float atomics).  Sums are fp64 per-CTA partials reduced by one CTA in a fixed order.
+// Labels outside [0, C) that are not the ignore label (-100 for kind 2) make torch raise; here they are skipped like ignored ones.
+// ---------------------------------------------------------------------------------------------------------------------
+enum { kCritCE = 0, kCritDice = 1, kCritFocalDice = 2 };
+struct CritArgs { int kind; long long ignore; float smooth, alpha, gamma, dice_w; };
+
+template <int CT, bool UP>
+struct CritPix {
+    float v[CT > 0 ? CT : 1];
+    const float* lp;        // UP: the image's low-resolution planes; else: this pixel in plane 0
+    long long cs;           // class stride in elements
+    int wl, y0, y1, x0, x1;
+    float ly, lx;
+    __device__ __forceinline__ float fetch(int c) const {
+        return UP ? up_value(lp + (long long)c * cs, wl, y0, y1, x0, x1, ly, lx) : __ldg(lp + (long long)c * cs);
+    }
+    __device__ __forceinline__ void load() {
+        if (CT > 0) {
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : 1); ++c) v[c] = fetch(c);
+        }
+    }
+    __device__ __forceinline__ float get(int c) const { return CT > 0 ? v[c] : fetch(c); }
+};
+#define CRIT_FOR_CLASSES(c) _Pragma("unroll") for (int c = 0; c < (CT > 0 ? CT : C); ++c)
+
+__device__ __forceinline__ float crit_sigmoid(float z) { return 1.f / (1.f + expf(-z)); }
+
+// acc: kind 0 {sum nll, count, -, -}; kinds 1, 2 {sum p t, sum p, sum t, sum focal}
+template <int CT, bool UP>
+__device__ __forceinline__ void crit_pixel_fwd(const CritPix<CT, UP>& u, int C, long long lab, const CritArgs& a, double (&acc)[4]) {
+    if (C == 1 && a.kind != kCritCE) {
+        const float p = crit_sigmoid(u.get(0)), t = (float)lab;
+        acc[0] += (double)(p * t); acc[1] += (double)p; acc[2] += (double)t;
+        if (a.kind == kCritFocalDice) {
+            const float ce = -(t * fmaxf(logf(p), -100.f) + (1.f - t) * fmaxf(logf(1.f - p), -100.f));
+            const float pt = t == 1.f ? p : 1.f - p;
+            acc[3] += (double)(a.alpha * powf(1.f - pt, a.gamma) * ce);
+        }
+        return;
+    }
+    float mx = -FLT_MAX;
+    CRIT_FOR_CLASSES(c) mx = fmaxf(mx, u.get(c));
+    float sum = 0.f, vl = 0.f, e1 = 0.f;
+    CRIT_FOR_CLASSES(c) {
+        const float t = u.get(c), e = expf(t - mx);
+        sum += e;
+        if (c == lab) vl = t;
+        if (c == 1) e1 = e;
+    }
+    const bool valid = lab >= 0 && lab < C && lab != a.ignore;
+    if (a.kind == kCritCE) {
+        if (valid) { acc[0] += (double)(-((vl - mx) - logf(sum))); acc[1] += 1.0; }
+        return;
+    }
+    const float p1 = e1 / sum, t = (float)lab;
+    acc[0] += (double)(p1 * t); acc[1] += (double)p1; acc[2] += (double)t;
+    if (a.kind == kCritFocalDice && valid) {
+        const float ce = -((vl - mx) - logf(sum)), pt = expf(-ce);
+        acc[3] += (double)(a.alpha * powf(1.f - pt, a.gamma) * ce);
+    }
+}
+
+// scalars of the backward, derived once per thread from the forward's sums: d loss / d p = da * t + db for the dice term
+struct CritScal { float sce, da, db, sf; };
+__device__ __forceinline__ CritScal crit_scalars(const double* __restrict__ out, float gout, const CritArgs& a) {
+    CritScal s{0.f, 0.f, 0.f, 0.f};
+    if (a.kind == kCritCE) {
+        s.sce = (float)((double)gout / out[2]);
+    } else {
+        const double I = out[1], D = out[2] + out[3] + (double)a.smooth;
+        const double k = (double)gout * (a.kind == kCritFocalDice ? (double)a.dice_w : 1.0);
+        s.da = (float)(-2.0 / D * k);
+        s.db = (float)((2.0 * I + (double)a.smooth) / (D * D) * k);
+        if (a.kind == kCritFocalDice) s.sf = (float)((double)gout * (1.0 - (double)a.dice_w) / out[5]);
+    }
+    return s;
+}
+
+// one channel (sigmoid): d loss / d logit of this pixel
+__device__ __forceinline__ float crit_grad_binary(float z, long long lab, const CritArgs& a, const CritScal& s) {
+    const float p = crit_sigmoid(z), t = (float)lab;
+    float gp = s.da * t + s.db;
+    if (a.kind == kCritFocalDice) {
+        const float ce = -(t * fmaxf(logf(p), -100.f) + (1.f - t) * fmaxf(logf(1.f - p), -100.f));
+        const float dce = (p - t) / fmaxf((1.f - p) * p, 1e-12f);            // binary_cross_entropy's own backward
+        const float pt = t == 1.f ? p : 1.f - p, dpt = t == 1.f ? 1.f : -1.f, om = 1.f - pt;
+        gp += s.sf * a.alpha * (powf(om, a.gamma) * dce - a.gamma * powf(om, a.gamma - 1.f) * dpt * ce);
+    }
+    return gp * p * (1.f - p);
+}
+
+// softmax statistics of a pixel for the backward: g_c = wce * (p_c - [c == lab]) + wd * ([c == 1] - p_c), p_c = exp(v_c - mx) * inv
+template <int CT, bool UP>
+__device__ __forceinline__ void crit_pixel_bwd_coef(const CritPix<CT, UP>& u, int C, long long lab, const CritArgs& a, const CritScal& s,
+                                                    float& mx, float& inv, float& wce, float& wd) {
+    mx = -FLT_MAX;
+    CRIT_FOR_CLASSES(c) mx = fmaxf(mx, u.get(c));
+    float sum = 0.f, el = 0.f, e1 = 0.f;
+    CRIT_FOR_CLASSES(c) {
+        const float e = expf(u.get(c) - mx);
+        sum += e;
+        if (c == lab) el = e;
+        if (c == 1) e1 = e;
+    }
+    inv = 1.f / sum;
+    const bool valid = lab >= 0 && lab < C && lab != a.ignore;
+    wce = 0.f; wd = 0.f;
+    if (a.kind == kCritCE) {
+        if (valid) wce = s.sce;
+        return;
+    }
+    wd = (s.da * (float)lab + s.db) * (e1 * inv);
+    if (a.kind == kCritFocalDice && valid) {
+        const float pt = el * inv, ce = -logf(pt), om = 1.f - pt;
+        wce = s.sf * a.alpha * (powf(om, a.gamma) + a.gamma * powf(om, a.gamma - 1.f) * pt * ce);
+    }
+}
+
+template <int CT, bool UP>
+__global__ void __launch_bounds__(kT)
+crit_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ label, UpGeom g, long long npix, CritArgs a,
+                double* __restrict__ partial) {
+    __shared__ double sm[4 * 8];
+    const int C = g.C;
+    const long long HW = (long long)g.H * g.W;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long n = i / HW, p = i % HW;
+        CritPix<CT, UP> u;
+        if (UP) {
+            const int y = (int)(p / g.W), x = (int)(p % g.W);
+            ac_coord(y, g.scy, g.hl, u.y0, u.y1, u.ly);
+            ac_coord(x, g.scx, g.wl, u.x0, u.x1, u.lx);
+            u.lp = logits + n * C * g.hl * g.wl; u.cs = (long long)g.hl * g.wl; u.wl = g.wl;
+        } else {
+            u.lp = logits + n * C * HW + p; u.cs = HW;
+        }
+        u.load();
+        crit_pixel_fwd<CT, UP>(u, C, label[i], a, acc);
+    }
+    block_sum<4>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) partial[blockIdx.x * 4 + k] = acc[k];
+    }
+}
+
+// out (doubles): {loss, S0, S1, S2, S3, npix}; kind 0: S0 = sum nll, S1 = count; kinds 1, 2: S0 = sum p t, S1 = sum p, S2 = sum t,
+// S3 = sum of the focal terms
+__global__ void __launch_bounds__(kT)
+crit_finalize_kernel(const double* __restrict__ partial, int nblocks, long long npix, CritArgs a, double* __restrict__ out) {
+    __shared__ double sm[4 * 8];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < nblocks; i += kT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] += partial[4 * i + k];
+    }
+    block_sum<4>(v, sm);
+    if (threadIdx.x != 0) return;
+    double loss;
+    if (a.kind == kCritCE) {
+        loss = v[0] / v[1];            // 0/0 = NaN when every pixel is ignored, like torch
+    } else {
+        const double dice = (2.0 * v[0] + (double)a.smooth) / (v[1] + v[2] + (double)a.smooth);
+        loss = 1.0 - dice;
+        if (a.kind == kCritFocalDice) loss = (1.0 - (double)a.dice_w) * (v[3] / (double)npix) + (double)a.dice_w * loss;
+    }
+    out[0] = loss; out[1] = v[0]; out[2] = v[1]; out[3] = v[2]; out[4] = v[3]; out[5] = (double)npix;
+}
+
+// logits at label resolution: dlogits[n][c][p] written directly
+template <int CT>
+__global__ void __launch_bounds__(kT)
+crit_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ label, int C, long long HW, long long npix, CritArgs a,
+                 const double* __restrict__ out, const float* __restrict__ gout, float* __restrict__ dlogits) {
+    const CritScal s = crit_scalars(out, __ldg(gout), a);
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
+        const long long n = i / HW, p = i % HW, lab = label[i];
+        CritPix<CT, false> u;
+        u.lp = logits + n * C * HW + p; u.cs = HW;
+        u.load();
+        float* dp = dlogits + n * C * HW + p;
+        if (C == 1 && a.kind != kCritCE) { dp[0] = crit_grad_binary(u.get(0), lab, a, s); continue; }
+        float mx, inv, wce, wd;
+        crit_pixel_bwd_coef<CT, false>(u, C, lab, a, s, mx, inv, wce, wd);
+        CRIT_FOR_CLASSES(c) {
+            const float pc = expf(u.get(c) - mx) * inv;
+            dp[(long long)c * HW] = wce * (pc - (c == lab ? 1.f : 0.f)) + wd * ((c == 1 ? 1.f : 0.f) - pc);
+        }
+    }
+}
+
+// low-resolution logits: grid (ceil(W/32), ceil(H/64), N), the tile / segmented-shuffle / shared-memory scheme of ohem_up_grad_kernel
+template <int CT>
+__global__ void __launch_bounds__(kT)
+crit_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__ label, UpGeom g, CritArgs a, const double* __restrict__ out,
+                    const float* __restrict__ gout, float* __restrict__ dlow) {
+    extern __shared__ float acc[];       // [C][kUpTR][kUpTC]
+    const int C = g.C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.z, yb = blockIdx.y * 64, xb = blockIdx.x * 32;
+    for (int i = tid; i < C * kUpTR * kUpTC; i += kT) acc[i] = 0.f;
+    __syncthreads();
+    const CritScal s = crit_scalars(out, __ldg(gout), a);
+    const int ry0 = min((int)(g.scy * (float)yb), g.hl - 1), rx0 = min((int)(g.scx * (float)xb), g.wl - 1);
+    const int x = xb + lane;
+    const bool live_x = x < g.W;
+    CritPix<CT, true> u;
+    u.lp = low + (long long)n * C * g.hl * g.wl; u.cs = (long long)g.hl * g.wl; u.wl = g.wl;
+    u.x0 = 0; u.x1 = 0; u.lx = 0.f;
+    if (live_x) ac_coord(x, g.scx, g.wl, u.x0, u.x1, u.lx);
+    const int prev_x0 = __shfl_up_sync(0xffffffffu, u.x0, 1);
+    const bool head = lane == 0 || prev_x0 != u.x0;
+    unsigned int same = 0u;            // bit k: lane + 2^k is in this lane's segment (lanes that share x0 are contiguous)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int ux0 = __shfl_down_sync(0xffffffffu, u.x0, 1 << k);
+        if (lane + (1 << k) < 32 && ux0 == u.x0) same |= 1u << k;
+    }
+    for (int rr = 0; rr < 8; ++rr) {
+        const int y = yb + warp * 8 + rr;
+        if (y >= g.H) break;                                   // warp-uniform
+        ac_coord(y, g.scy, g.hl, u.y0, u.y1, u.ly);
+        long long lab = a.ignore;
+        float mx = 0.f, inv = 0.f, wce = 0.f, wd = 0.f, gb = 0.f;
+        const bool binary = C == 1 && a.kind != kCritCE;
+        if (live_x) {
+            lab = label[((long long)n * g.H + y) * g.W + x];
+            u.load();
+            if (binary) gb = crit_grad_binary(u.get(0), lab, a, s);
+            else crit_pixel_bwd_coef<CT, true>(u, C, lab, a, s, mx, inv, wce, wd);
+        } else if (CT > 0) {
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : 1); ++c) u.v[c] = 0.f;
+        }
+        const int ay0 = (u.y0 - ry0) * kUpTC, ay1 = (u.y1 - ry0) * kUpTC, ax0 = u.x0 - rx0, ax1 = u.x1 - rx0;
+        CRIT_FOR_CLASSES(c) {
+            float gc = 0.f;
+            if (live_x) {
+                if (binary) gc = gb;
+                else if (wce != 0.f || wd != 0.f) {
+                    const float pc = expf(u.get(c) - mx) * inv;
+                    gc = wce * (pc - (c == lab ? 1.f : 0.f)) + wd * ((c == 1 ? 1.f : 0.f) - pc);
+                }
+            }
+            float ga = gc * (1.f - u.lx), gbx = gc * u.lx;       // towards columns x0 and x1
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float ua = __shfl_down_sync(0xffffffffu, ga, 1 << k), ub = __shfl_down_sync(0xffffffffu, gbx, 1 << k);
+                if ((same >> k) & 1u) { ga += ua; gbx += ub; }
+            }
+            if (head && live_x && (ga != 0.f || gbx != 0.f)) {
+                float* ac = acc + c * kUpTR * kUpTC;
+                atomicAdd(ac + ay0 + ax0, (1.f - u.ly) * ga);
+                atomicAdd(ac + ay0 + ax1, (1.f - u.ly) * gbx);
+                atomicAdd(ac + ay1 + ax0, u.ly * ga);
+                atomicAdd(ac + ay1 + ax1, u.ly * gbx);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < C * kUpTR * kUpTC; i += kT) {
+        const float v = acc[i];
+        if (v != 0.f) {
+            const int c = i / (kUpTR * kUpTC), r = (i / kUpTC) % kUpTR, q = i % kUpTC;
+            const int yy = ry0 + r, xx = rx0 + q;
+            if (yy < g.hl && xx < g.wl) atomicAdd(dlow + (((long long)n * C + c) * g.hl + yy) * g.wl + xx, v);
+        }
+    }
+}
+
+size_t train_criterion_workspace_bytes() { return (size_t)num_sms() * 16 * 4 * sizeof(double) + 256; }
+
+template <bool UP>
+static void launch_crit_fwd(int c, int grid, const float* logits, const long long* label, const UpGeom& g, long long npix, const CritArgs& a,
+                            double* partial, cudaStream_t s) {
+    if (c == 1) crit_fwd_kernel<1, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
+    else if (c == 2) crit_fwd_kernel<2, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
+    else if (c == 19) crit_fwd_kernel<19, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
+    else crit_fwd_kernel<0, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
+}
+
+cudaError_t launch_train_criterion_fwd(const float* logits, const long long* label, double* out6, void* ws, int kind, int n, int c, int hl,
+                                       int wl, int h, int w, long long ignore, float smooth, float alpha, float gamma, float dice_w,
+                                       cudaStream_t s) {
+    const long long npix = (long long)n * h * w;
+    const CritArgs a{kind, ignore, smooth, alpha, gamma, dice_w};
+    const UpGeom g = up_geom(c, hl, wl, h, w);
+    const int grid = grid_for(npix);
+    double* partial = reinterpret_cast<double*>(ws);
+    if (hl == h && wl == w) launch_crit_fwd<false>(c, grid, logits, label, g, npix, a, partial, s);
+    else launch_crit_fwd<true>(c, grid, logits, label, g, npix, a, partial, s);
+    crit_finalize_kernel<<<1, kT, 0, s>>>(partial, grid, npix, a, out6);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_train_criterion_bwd(const float* logits, const long long* label, const double* out6, const float* gout, float* dlogits,
+                                       int kind, int n, int c, int hl, int wl, int h, int w, long long ignore, float smooth, float alpha,
+                                       float gamma, float dice_w, cudaStream_t s) {
+    const long long npix = (long long)n * h * w;
+    const CritArgs a{kind, ignore, smooth, alpha, gamma, dice_w};
+    if (hl == h && wl == w) {
+        const int grid = grid_for(npix);
+        const long long hw = (long long)h * w;
+        if (c == 1) crit_grad_kernel<1><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
+        else if (c == 2) crit_grad_kernel<2><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
+        else if (c == 19) crit_grad_kernel<19><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
+        else crit_grad_kernel<0><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
+        return cudaGetLastError();
+    }
+    const size_t smem = (size_t)c * kUpTR * kUpTC * sizeof(float);
+    if ((double)(hl - 1) * 7.0 > (double)(h - 1) || (double)(wl - 1) * 7.0 > (double)(w - 1) || smem > 48 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(dlogits, 0, (size_t)n * c * hl * wl * sizeof(float), s);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((w + 31) / 32, (h + 63) / 64, n);
+    const UpGeom g = up_geom(c, hl, wl, h, w);
+    if (c == 1) crit_up_grad_kernel<1><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
+    else if (c == 2) crit_up_grad_kernel<2><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
+    else if (c == 19) crit_up_grad_kernel<19><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
+    else crit_up_grad_kernel<0><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
+    return cudaGetLastError();
+}
+
 }  // namespace fscnn

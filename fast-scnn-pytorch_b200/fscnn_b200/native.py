@@ -104,6 +104,11 @@ _SIGNATURES = {
     'fscnn_train_ohem_upsampled_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                       C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong,
                                                       C.c_void_p]),
+    'fscnn_train_criterion_workspace_bytes': (C.c_int, [C.POINTER(C.c_size_t)]),
+    'fscnn_train_criterion_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    'fscnn_train_criterion_backward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     'fscnn_stage_count': (C.c_int, [C.c_void_p]),
     'fscnn_stage_name': (C.c_char_p, [C.c_void_p, C.c_int]),
     'fscnn_forward_range': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

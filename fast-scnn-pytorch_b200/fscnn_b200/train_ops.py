@@ -276,6 +276,64 @@ def ohem_cross_entropy_upsampled(low_logits, target, class_weight: Optional[torc
     return OhemCrossEntropyUpsampled.apply(low_logits, target, class_weight, ignore_label, thresh, min_kept)
 
 
+CRITERIA = {'ce': 0, 'dice': 1, 'focal_dice': 2}
+
+
+class Criterion(torch.autograd.Function):
+    """One head's cross entropy / dice / focal + dice term (reference utils/loss.py:103-124, :12-39, :71-100) on the device.
+    ``logits`` are either at the labels' resolution or a head's low-resolution output, in which case the final
+    ``F.interpolate(..., 'bilinear', align_corners=True)`` (models/fast_scnn.py:40, :44) is composed with the criterion and the
+    full-resolution logits never exist (fscnn_train_criterion_*)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, kind, ignore_label, smooth, alpha, gamma, dice_weight):
+        logits = _check(logits, 'logits')
+        if target.dtype != torch.int64 or target.dim() != 3 or not target.is_cuda:
+            raise ValueError('target must be a CUDA int64 [N,H,W] tensor')
+        n, c, hl, wl = logits.shape
+        if target.shape[0] != n:
+            raise ValueError(f'target batch {target.shape[0]} does not match logits batch {n}')
+        h, w = int(target.shape[1]), int(target.shape[2])
+        target = target.contiguous()
+        need = C.c_size_t()
+        native.check(native.lib().fscnn_train_criterion_workspace_bytes(C.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=logits.device)
+        out6 = torch.empty(6, dtype=torch.float64, device=logits.device)
+        ctx.args = (int(kind), n, c, hl, wl, h, w, int(ignore_label), float(smooth), float(alpha), float(gamma), float(dice_weight))
+        with torch.cuda.device(logits.device):
+            native.check(native.lib().fscnn_train_criterion_forward(logits.data_ptr(), target.data_ptr(), out6.data_ptr(), ws.data_ptr(),
+                                                                     ws.numel(), *ctx.args, _stream()), 'fscnn_train_criterion_forward')
+        ctx.save_for_backward(logits, target, out6)
+        ctx.mark_non_differentiable(target)
+        return out6[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, target, out6 = ctx.saved_tensors
+        dlogits = torch.empty_like(logits)
+        g = gout.to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(logits.device):
+            native.check(native.lib().fscnn_train_criterion_backward(logits.data_ptr(), target.data_ptr(), out6.data_ptr(), g.data_ptr(),
+                                                                      dlogits.data_ptr(), *ctx.args, _stream()), 'fscnn_train_criterion_backward')
+        return dlogits, None, None, None, None, None, None, None
+
+
+def criterion(logits, target, kind: str, ignore_label=-1, smooth=1e-6, alpha=0.5, gamma=2.0, dice_weight=0.5):
+    """``kind``: 'ce' = nn.CrossEntropyLoss(ignore_index=ignore_label) (the per-head term of MixSoftmaxCrossEntropyLoss), 'dice' =
+    DiceLoss(smooth), 'focal_dice' = FocalDiceLoss(alpha, gamma, dice_weight, smooth) -- reference utils/loss.py.  When ``logits`` are
+    smaller than ``target`` they are a head's low-resolution output and the x8 bilinear resize is fused (ratios below 7 or more than 128
+    classes take the resize kernel first)."""
+    if kind not in CRITERIA:
+        raise ValueError(f'criterion must be one of {sorted(CRITERIA)}, got {kind!r}')
+    n, c, hl, wl = logits.shape
+    h, w = int(target.shape[1]), int(target.shape[2])
+    if (hl, wl) != (h, w) and ((hl - 1) * 7 > h - 1 or (wl - 1) * 7 > w - 1 or c > 128):
+        logits = bilinear_resize(logits, (h, w))
+    if kind == 'focal_dice' and ignore_label == -1:
+        ignore_label = -100       # F.cross_entropy's default ignore_index: what FocalDiceLoss.focal_loss runs with
+    return Criterion.apply(logits, target, CRITERIA[kind], ignore_label, smooth, alpha, gamma, dice_weight)
+
+
 def depthwise_conv3x3(x, weight, stride=1):
     return DepthwiseConv3x3.apply(x, weight, int(stride))
 

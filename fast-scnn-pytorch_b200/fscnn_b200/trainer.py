@@ -36,14 +36,23 @@ def poly_lr(base_lr: float, cur_iter: int, nepochs: int, iters_per_epoch: int, p
 class Trainer:
     def __init__(self, model, base_lr=1e-2, momentum=0.9, weight_decay=1e-4, aux_weight=0.4, ignore_label=-1, ohem_thresh=0.7,
                  ohem_min_kept=256, use_class_weights: Optional[bool] = None, nepochs=160, iters_per_epoch=1000, process_group=None,
-                 fused_loss: bool = True, cuda_graph: bool = False, graph_warmup: int = 3, matmul_precision: Optional[str] = None):
-        """``cuda_graph``: after ``graph_warmup`` eager steps, zero_grad + forward + loss + backward are captured once into a CUDA
+                 fused_loss: bool = True, cuda_graph: bool = False, graph_warmup: int = 3, matmul_precision: Optional[str] = None,
+                 loss_type: str = 'ohem', dice_smooth: float = 1e-6, focal_alpha: float = 0.5, focal_gamma: float = 2.0,
+                 focal_dice_weight: float = 0.5):
+        """``loss_type``: the criterion train.py builds (train.py:182-192) -- 'ohem' = MixSoftmaxCrossEntropyOHEMLoss (its
+        --loss-type ce, BASELINE config 5), 'dice' = MixDiceLoss (train.py's default), 'ce' = MixSoftmaxCrossEntropyLoss,
+        'focal_dice' = FocalDiceLoss on the main head (the reference's own call hands it the output tuple and fails in
+        loss.py:82, pred.dim()).  ``cuda_graph``: after ``graph_warmup`` eager steps, zero_grad + forward + loss + backward are captured once into a CUDA
         graph per input shape and replayed (the ~780 kernel launches of a step cost more host time than the kernels take on a
         B200); the gradient all-reduce and the SGD update stay outside the graph, so the learning rate remains a host value.
         ``matmul_precision``: 'fp32' or 'tf32' for the pointwise / dense 3x3 contractions (train_ops.set_matmul_precision;
         process-wide); None leaves the current setting."""
         self.model = model
         self.fused_loss = bool(fused_loss)
+        if loss_type not in ('ohem', 'ce', 'dice', 'focal_dice'):
+            raise ValueError(f"loss_type must be 'ohem', 'ce', 'dice' or 'focal_dice', got {loss_type!r}")
+        self.loss_type = loss_type
+        self.dice_smooth, self.focal = float(dice_smooth), (float(focal_alpha), float(focal_gamma), float(focal_dice_weight))
         if matmul_precision is not None:
             train_ops.set_matmul_precision(matmul_precision)
         self.cuda_graph, self.graph_warmup = bool(cuda_graph), int(graph_warmup)
@@ -81,9 +90,25 @@ class Trainer:
         if self.world > 1:      # every rank starts from rank 0's weights
             dist.broadcast(self.flat_param, src=0, group=process_group)
 
+    def _other_criterion(self, outputs, target):
+        """MixSoftmaxCrossEntropyLoss (loss.py:103-124), MixDiceLoss (:42-68) or FocalDiceLoss (:71-100) over the heads; logits
+        smaller than the target are resized inside the loss kernels (train_ops.criterion)."""
+        if self.loss_type == 'focal_dice':
+            a, g, dw = self.focal
+            return train_ops.criterion(outputs[0], target, 'focal_dice', ignore_label=-100, smooth=self.dice_smooth, alpha=a, gamma=g,
+                                       dice_weight=dw)
+        heads = outputs if self.loss_type == 'ce' else outputs[:2]      # MixDiceLoss looks at the first aux prediction only
+        total = train_ops.criterion(heads[0], target, self.loss_type, ignore_label=self.ignore_label, smooth=self.dice_smooth)
+        for aux_out in heads[1:]:
+            total = total + self.aux_weight * train_ops.criterion(aux_out, target, self.loss_type, ignore_label=self.ignore_label,
+                                                                   smooth=self.dice_smooth)
+        return total
+
     def loss_from_lowres(self, lowres_outputs, target):
         """The same loss from the heads' LOW-RESOLUTION logits: the final x8 bilinear resize (models/fast_scnn.py:40, :44) is fused
         into the OHEM kernels (train_ops.ohem_cross_entropy_upsampled)."""
+        if self.loss_type != 'ohem':
+            return self._other_criterion(lowres_outputs, target)
         total = train_ops.ohem_cross_entropy_upsampled(lowres_outputs[0], target, self.class_weight, self.ignore_label, self.ohem_thresh,
                                                        self.ohem_min_kept)
         for aux_out in lowres_outputs[1:]:
@@ -92,7 +117,9 @@ class Trainer:
         return total
 
     def loss(self, outputs, target):
-        """MixSoftmaxCrossEntropyOHEMLoss.forward (utils/loss.py:191-206)."""
+        """MixSoftmaxCrossEntropyOHEMLoss.forward (utils/loss.py:191-206), or the criterion ``loss_type`` names."""
+        if self.loss_type != 'ohem':
+            return self._other_criterion(outputs, target)
         total = train_ops.ohem_cross_entropy(outputs[0], target, self.class_weight, self.ignore_label, self.ohem_thresh, self.ohem_min_kept)
         for aux_out in outputs[1:]:
             total = total + self.aux_weight * train_ops.ohem_cross_entropy(aux_out, target, self.class_weight, self.ignore_label,

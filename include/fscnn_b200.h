@@ -320,6 +320,36 @@ int fscnn_train_ohem_upsampled_backward(const float* d_low_logits, const long lo
                                         const float* d_out3, const float* d_grad_out, float* d_dlow, const void* d_ws, int n, int c, int hl,
                                         int wl, int h, int w, long long ignore_label, void* stream);
 
+/* The reference's other training criteria (utils/loss.py), one head per call (the aux-head mix -- loss.py:112-116, :56-68 -- is
+ * a weighted sum of calls on the host side):
+ *   FSCNN_CRITERION_CE          nn.CrossEntropyLoss(ignore_index = ignore_label), the term MixSoftmaxCrossEntropyLoss applies to every
+ *                               head (loss.py:103-124): mean negative log-likelihood over the pixels with label != ignore_label
+ *   FSCNN_CRITERION_DICE        DiceLoss (loss.py:12-39; train.py:70's DEFAULT --loss-type, through MixDiceLoss loss.py:42-68):
+ *                               p = softmax(x)[:, 1] (sigmoid(x) when c == 1), t = float(label) of EVERY pixel, loss =
+ *                               1 - (2 sum(p t) + smooth) / (sum p + sum t + smooth); ignore_label is not used
+ *   FSCNN_CRITERION_FOCAL_DICE  FocalDiceLoss (loss.py:71-100): (1 - dice_weight) * mean(alpha (1 - pt)^gamma ce) + dice_weight * DiceLoss
+ *                               with ce = F.cross_entropy(reduction='none') (pass ignore_label = -100, torch's default: such pixels add 0
+ *                               to the mean over all pixels) or, for c == 1, F.binary_cross_entropy(sigmoid(x), t); gamma >= 1
+ * d_logits [n][c][hl][wl] float32, d_label [n][h][w] int64.  (hl, wl) == (h, w): the logits are at label resolution (what
+ * FastSCNN.forward returns in training mode) and the backward is deterministic.  Otherwise d_logits is a head's LOW-RESOLUTION output
+ * and F.interpolate(size=(h, w), mode='bilinear', align_corners=True) (models/fast_scnn.py:40, :44) is composed with the criterion, as
+ * in fscnn_train_ohem_upsampled_*: the full-resolution logits and their gradient never exist; the backward then needs
+ * (hl-1)*7 <= h-1, (wl-1)*7 <= w-1, c <= 128 and adds with float atomics.
+ * d_out6 (float64): {loss, S0, S1, S2, S3, pixels} -- CE: S0 = sum of nll, S1 = pixels counted; dice: S0 = sum(p t), S1 = sum p,
+ * S2 = sum t, S3 = sum of the focal terms; the backward re-reads it.  d_dlogits [n][c][hl][wl] = d_grad_out[0] * d loss / d logits.
+ * Labels outside [0, c) other than ignore_label make torch raise; here they count as ignored in the CE / focal terms.
+ * d_ws >= fscnn_train_criterion_workspace_bytes(). */
+#define FSCNN_CRITERION_CE 0
+#define FSCNN_CRITERION_DICE 1
+#define FSCNN_CRITERION_FOCAL_DICE 2
+int fscnn_train_criterion_workspace_bytes(size_t* out_bytes);
+int fscnn_train_criterion_forward(const float* d_logits, const long long* d_label, double* d_out6, void* d_ws, size_t ws_bytes, int kind,
+                                  int n, int c, int hl, int wl, int h, int w, long long ignore_label, float smooth, float alpha, float gamma,
+                                  float dice_weight, void* stream);
+int fscnn_train_criterion_backward(const float* d_logits, const long long* d_label, const double* d_out6, const float* d_grad_out,
+                                   float* d_dlogits, int kind, int n, int c, int hl, int wl, int h, int w, long long ignore_label, float smooth,
+                                   float alpha, float gamma, float dice_weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

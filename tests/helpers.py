@@ -62,3 +62,22 @@ def check_bf16_against_yardstick(ours, yard):
     if not ours['mask'] <= min(yard['mask'] + BF16_MASK_SLACK, BF16_MASK_BACKSTOP):
         bad.append(f"mask disagreement {ours['mask']:.3%} > reference bf16 {yard['mask']:.3%} + {BF16_MASK_SLACK:.1%}")
     return bad
+
+
+# tests/golden/train_loss_cases.npz (oracle/gen_golden_loss.py): criterion, its keyword arguments, weight of the second head
+LOSS_CASES = {
+    'dice_c2': ('dice', {}, None),
+    'dice_c1_sigmoid': ('dice', {}, None),
+    'dice_smooth1': ('dice', {'smooth': 1.0}, None),
+    'mixdice_aux': ('dice', {}, 0.4),
+    'mixdice_aux_low': ('dice', {}, 0.4),
+    'dice_c19_labels': ('dice', {}, None),
+    'ce_c19_aux': ('ce', {'ignore_label': -1}, 0.4),
+    'ce_c19_aux_low': ('ce', {'ignore_label': -1}, 0.4),
+    'ce_c2_noaux': ('ce', {'ignore_label': -1}, None),
+    'ce_c5_low_odd': ('ce', {'ignore_label': -1}, None),
+    'focal_c2': ('focal_dice', {}, None),
+    'focal_c2_low': ('focal_dice', {}, None),
+    'focal_c3_ignore100': ('focal_dice', {'alpha': 0.25, 'gamma': 3.0, 'dice_weight': 0.3}, None),
+    'focal_c1_bce': ('focal_dice', {}, None),
+}

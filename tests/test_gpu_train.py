@@ -496,3 +496,96 @@ def test_stem_conv_direct_kernels_against_torch(n, h, w):
     y2.backward(dy)
     assert rel_err(y.detach().cpu().numpy(), y2.detach().cpu().numpy()) < 2e-6
     assert rel_err(wt.grad.cpu().numpy(), wt2.grad.cpu().numpy()) < 5e-6
+
+
+# ---- the reference's other criteria: MixSoftmaxCrossEntropyLoss, DiceLoss / MixDiceLoss (train.py's default), FocalDiceLoss ----
+def _loss_module(kind, kw, aux_weight):
+    from utils import loss as L
+    if kind == 'dice':
+        return (L.MixDiceLoss(aux=True, aux_weight=aux_weight, **kw), False) if aux_weight is not None else (L.DiceLoss(**kw), True)
+    if kind == 'ce':
+        return L.MixSoftmaxCrossEntropyLoss(aux=aux_weight is not None, aux_weight=aux_weight or 0.2, **kw), False
+    return L.FocalDiceLoss(**kw), True
+
+
+def test_criteria_match_reference_fixtures():
+    """utils/loss.py drop-ins (device kernels behind the reference's class names) against the loss and the gradients the unmodified
+    reference classes produce under torch.autograd (oracle/gen_golden_loss.py); '*_low' cases hand over LOW-RESOLUTION logits, the
+    reference side resizes them first (models/fast_scnn.py:40).  Loss 1e-5 relative, gradients 2e-5 of absmax."""
+    from helpers import LOSS_CASES
+    g = _load('train_loss_cases')
+    for name, (kind, kw, aux_weight) in LOSS_CASES.items():
+        crit, single = _loss_module(kind, kw, aux_weight)
+        target = torch.from_numpy(g[name + '/target']).to(DEV)
+        heads = [torch.from_numpy(g[f'{name}/logits{i}']).to(DEV).requires_grad_(True) for i in range(2 if aux_weight is not None else 1)]
+        loss = crit(heads[0], target) if single else crit(tuple(heads), target)
+        (3.0 * loss).backward()
+        want = float(g[name + '/loss'])
+        assert abs(float(loss.detach()) - want) <= 1e-5 * abs(want), (name, float(loss.detach()), want)
+        for i, t in enumerate(heads):
+            assert rel_err(t.grad.cpu().numpy(), 3.0 * g[f'{name}/grad{i}']) < 2e-5, (name, i)
+
+
+@pytest.mark.parametrize('kind,n,c,hl,wl,h,w', [('ce', 2, 19, 12, 16, 96, 128), ('dice', 2, 2, 9, 13, 65, 97), ('focal_dice', 1, 2, 12, 12, 96, 96),
+                                                 ('ce', 1, 7, 10, 20, 80, 160), ('dice', 2, 1, 6, 8, 48, 64), ('focal_dice', 2, 4, 5, 9, 40, 70)])
+def test_fused_upsample_criteria_equal_the_two_step_form_and_the_oracle(kind, n, c, hl, wl, h, w):
+    """criterion(low) with the resize inside the loss kernels == criterion(bilinear_resize(low)) (same interpolation arithmetic: the
+    loss agrees to rounding of the final sum), and both follow the float64 oracle."""
+    import loss_oracle as lo
+    from fscnn_b200 import train_ops
+    gen = torch.Generator().manual_seed(100 + c + hl)
+    low = (torch.randn((n, c, hl, wl), generator=gen) * 3.0)
+    if kind == 'ce':
+        target = torch.randint(-1, c, (n, h, w), generator=gen)
+    elif kind == 'dice' or c <= 2:
+        target = (torch.rand((n, h, w), generator=gen) < 0.3).long()
+    else:
+        target = torch.randint(0, c, (n, h, w), generator=gen)
+        target[torch.rand((n, h, w), generator=gen) < 0.05] = -100
+    a = low.clone().to(DEV).requires_grad_(True)
+    b = low.clone().to(DEV).requires_grad_(True)
+    t = target.to(DEV)
+    fused = train_ops.criterion(a, t, kind)
+    two = train_ops.criterion(train_ops.bilinear_resize(b, (h, w)), t, kind)
+    fused.backward()
+    two.backward()
+    fused, two = fused.detach(), two.detach()
+    assert abs(float(fused) - float(two)) <= 1e-6 * abs(float(two))
+    assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < 2e-5
+    want, grad = lo.criterion_upsampled(kind, low.numpy(), target.numpy())
+    assert abs(float(fused) - want) <= 1e-5 * abs(want)
+    assert rel_err(a.grad.cpu().numpy(), grad.astype(np.float32)) < 2e-5
+
+
+def test_trainer_with_the_default_dice_criterion():
+    """train.py's default --loss-type (MixDiceLoss) on a 2-class model with the aux head: the Trainer's fused-resize loss equals
+    utils.loss.MixDiceLoss on the model's full-resolution training outputs, and a few steps reduce it; 'ce' and 'focal_dice' step too."""
+    import fastscnn_oracle as fo
+    from fscnn_b200 import Trainer
+    from models.fast_scnn import FastSCNN
+    from utils.loss import MixDiceLoss
+    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in fo.make_state_dict(2, True, seed=9).items()}
+    x = torch.from_numpy(fo.make_input(2, 64, 96, seed=3)).to(DEV)
+    t = (torch.rand((2, 64, 96), generator=torch.Generator().manual_seed(1)) < 0.25).long().to(DEV)
+    model = FastSCNN(2, aux=True)
+    model.load_state_dict(sd)
+    model.to(DEV).train()
+    trainer = Trainer(model, base_lr=1e-2, loss_type='dice')
+    for m in model.modules():      # identical forward twice: no dropout
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    with torch.no_grad():
+        low = model._train_forward_lowres(x)
+        full = model(x)
+        fused = float(trainer.loss_from_lowres(low, t))
+        ref = float(MixDiceLoss(aux=True, aux_weight=0.4)(full, t))
+    assert abs(fused - ref) <= 1e-5 * abs(ref)
+    losses = [float(trainer.step(x, t)) for _ in range(6)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    for kind in ('ce', 'focal_dice'):
+        m2 = FastSCNN(2, aux=True)
+        m2.load_state_dict(sd)
+        m2.to(DEV).train()
+        tr = Trainer(m2, base_lr=1e-2, loss_type=kind)
+        ls = [float(tr.step(x, t)) for _ in range(4)]
+        assert all(np.isfinite(ls)) and ls[-1] < ls[0], (kind, ls)

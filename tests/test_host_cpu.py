@@ -171,3 +171,35 @@ def test_kernel_generation_options_and_e2e_argument_checks():
     assert lib.fscnn_e2e_preprocess(dummy, native.U8, 1, 8, 8, 16, mean, None, dummy, None) < 0            # mean without std
     assert lib.fscnn_e2e_postprocess(dummy, 33, 36, 1, 4, 4, 32, 32, 8, 8, 1, dummy, None) < 0             # more than 32 classes
     assert lib.fscnn_e2e_postprocess(dummy, 4, 2, 1, 4, 4, 32, 32, 8, 8, 1, dummy, None) < 0               # padded < classes
+
+
+def test_loss_module_mirrors_the_reference_interface():
+    """utils/loss.py: the reference's class names, constructor defaults (utils/loss.py:15, :45, :74, :104, :128, :186) and its
+    call-time failures that need no device."""
+    import inspect
+    import pytest
+    import torch
+    from utils import loss as L
+
+    def defaults(cls):
+        return {k: v.default for k, v in inspect.signature(cls.__init__).parameters.items() if v.default is not inspect.Parameter.empty}
+
+    assert L.__all__ == ['MixSoftmaxCrossEntropyLoss', 'MixSoftmaxCrossEntropyOHEMLoss', 'DiceLoss', 'MixDiceLoss']
+    assert defaults(L.DiceLoss) == {'smooth': 1e-6}
+    assert defaults(L.MixDiceLoss) == {'aux': True, 'aux_weight': 0.4, 'smooth': 1e-6}
+    assert defaults(L.FocalDiceLoss) == {'alpha': 0.5, 'gamma': 2.0, 'dice_weight': 0.5, 'smooth': 1e-6}
+    assert defaults(L.MixSoftmaxCrossEntropyLoss) == {'aux': True, 'aux_weight': 0.2, 'ignore_label': -1}
+    assert defaults(L.SoftmaxCrossEntropyOHEMLoss) == {'ignore_label': -1, 'thresh': 0.7, 'min_kept': 256, 'use_weight': True}
+    assert defaults(L.MixSoftmaxCrossEntropyOHEMLoss) == {'aux': False, 'aux_weight': 0.2, 'ignore_index': -1}
+    assert isinstance(L.MixSoftmaxCrossEntropyLoss(), torch.nn.CrossEntropyLoss) and L.MixSoftmaxCrossEntropyLoss().ignore_index == -1
+    assert issubclass(L.MixSoftmaxCrossEntropyOHEMLoss, L.SoftmaxCrossEntropyOHEMLoss)
+    w = L.SoftmaxCrossEntropyOHEMLoss().weight
+    assert w.shape == (19,) and abs(float(w[0]) - 0.8373) < 1e-6 and abs(float(w[18]) - 1.0507) < 1e-6
+    assert L.SoftmaxCrossEntropyOHEMLoss(use_weight=False).weight is None
+    pred, target = torch.zeros(1, 2, 8, 8), torch.zeros(1, 8, 8, dtype=torch.int64)
+    with pytest.raises(AttributeError):      # loss.py:82: pred.dim() on the tuple train.py hands over
+        L.FocalDiceLoss()((pred, pred), target)
+    with pytest.raises(TypeError):           # loss.py:124: nn.CrossEntropyLoss.forward(pred0, pred1, target)
+        L.MixSoftmaxCrossEntropyLoss(aux=False)((pred, pred), target)
+    with pytest.raises(RuntimeError):        # CPU tensors: there is no CPU path
+        L.DiceLoss()(pred, target)

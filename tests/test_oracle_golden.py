@@ -131,3 +131,30 @@ def test_ohem_oracle_matches_reference_fixtures(name):
     assert np.abs(grad - g['dlogits']).max() <= 1e-6 * np.abs(g['dlogits']).max()
     kept, thr = oo.ohem_select(g['logits'], g['target'], -1, float(g['thresh']), int(g['min_kept']))
     assert np.array_equal(kept, np.abs(g['dlogits']).sum(1) > 0)
+
+
+def test_loss_oracle_matches_reference_fixtures():
+    """The numpy restatement of the cross-entropy / dice / focal + dice criteria (oracle/loss_oracle.py), alone and composed with
+    the heads' final bilinear resize, against loss / gradient vectors produced by the unmodified reference classes under
+    torch.autograd (oracle/gen_golden_loss.py)."""
+    import os
+    import loss_oracle as lo
+    from conftest import GOLDEN
+    from helpers import LOSS_CASES
+    g = np.load(os.path.join(GOLDEN, 'train_loss_cases.npz'))
+    for name, (kind, kw, aux_weight) in LOSS_CASES.items():
+        target = g[name + '/target']
+        total, grads = 0.0, []
+        for i in range(2 if aux_weight is not None else 1):
+            low = g[f'{name}/logits{i}']
+            scale = 1.0 if i == 0 else aux_weight
+            if low.shape[2:] != target.shape[1:]:
+                loss, grad = lo.criterion_upsampled(kind, low, target, **kw)
+            else:
+                loss, grad = lo.CRITERIA[kind](low, target, **kw)
+            total += scale * loss
+            grads.append(scale * grad)
+        assert abs(total - float(g[name + '/loss'])) <= 2e-6 * abs(float(g[name + '/loss'])), name
+        for i, grad in enumerate(grads):
+            ref = g[f'{name}/grad{i}']
+            assert np.abs(grad - ref).max() <= 2e-5 * np.abs(ref).max(), (name, i)
