@@ -651,3 +651,14 @@ def sgd_step(param_flat, grad_flat, momentum_buf, lr, momentum=0.9, weight_decay
         native.check(_lib().fscnn_train_sgd_step(param_flat.data_ptr(), grad_flat.data_ptr(), momentum_buf.data_ptr(), float(lr), float(momentum),
                                                  float(weight_decay), float(grad_scale), int(bool(first_step)), param_flat.numel(), _stream()),
                      'fscnn_train_sgd_step')
+
+
+def adamw_step(param_flat, grad_flat, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+    """torch.optim.AdamW (reference train_bdd100k.py:183-185) on flat fp32 buffers, one launch; ``step`` counts from 1."""
+    for t in (param_flat, grad_flat, exp_avg, exp_avg_sq):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != param_flat.numel():
+            raise ValueError('adamw_step takes four contiguous CUDA float32 buffers of equal length')
+    with torch.cuda.device(param_flat.device):
+        native.check(_lib().fscnn_train_adamw_step(param_flat.data_ptr(), grad_flat.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                                   float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                                                   float(grad_scale), int(step), param_flat.numel(), _stream()), 'fscnn_train_adamw_step')

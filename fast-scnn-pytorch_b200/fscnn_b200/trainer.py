@@ -38,11 +38,13 @@ class Trainer:
                  ohem_min_kept=256, use_class_weights: Optional[bool] = None, nepochs=160, iters_per_epoch=1000, process_group=None,
                  fused_loss: bool = True, cuda_graph: bool = False, graph_warmup: int = 3, matmul_precision: Optional[str] = None,
                  loss_type: str = 'ohem', dice_smooth: float = 1e-6, focal_alpha: float = 0.5, focal_gamma: float = 2.0,
-                 focal_dice_weight: float = 0.5):
+                 focal_dice_weight: float = 0.5, optimizer: str = 'sgd', betas=(0.9, 0.999), adam_eps: float = 1e-8):
         """``loss_type``: the criterion train.py builds (train.py:182-192) -- 'ohem' = MixSoftmaxCrossEntropyOHEMLoss (its
         --loss-type ce, BASELINE config 5), 'dice' = MixDiceLoss (train.py's default), 'ce' = MixSoftmaxCrossEntropyLoss,
         'focal_dice' = FocalDiceLoss on the main head (the reference's own call hands it the output tuple and fails in
-        loss.py:82, pred.dim()).  ``cuda_graph``: after ``graph_warmup`` eager steps, zero_grad + forward + loss + backward are captured once into a CUDA
+        loss.py:82, pred.dim()).  ``optimizer``: 'sgd' = torch.optim.SGD(momentum, weight_decay) (train.py:195-198,
+        train_custom_finetune.py:102) or 'adamw' = torch.optim.AdamW(lr, weight_decay) with ``betas`` / ``adam_eps`` (train_bdd100k.py:183;
+        pass the weight decay that script uses).  ``cuda_graph``: after ``graph_warmup`` eager steps, zero_grad + forward + loss + backward are captured once into a CUDA
         graph per input shape and replayed (the ~780 kernel launches of a step cost more host time than the kernels take on a
         B200); the gradient all-reduce and the SGD update stay outside the graph, so the learning rate remains a host value.
         ``matmul_precision``: 'fp32' or 'tf32' for the pointwise / dense 3x3 contractions (train_ops.set_matmul_precision;
@@ -64,7 +66,11 @@ class Trainer:
         total = sum(p.numel() for p in params)
         self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.momentum_buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.momentum_buf = torch.zeros(total, dtype=torch.float32, device=dev)      # SGD momentum / AdamW first moment
+        if optimizer not in ('sgd', 'adamw'):
+            raise ValueError(f"optimizer must be 'sgd' or 'adamw', got {optimizer!r}")
+        self.optimizer, self.betas, self.adam_eps = optimizer, (float(betas[0]), float(betas[1])), float(adam_eps)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev) if optimizer == 'adamw' else None
         off = 0
         self._grad_views = []
         with torch.no_grad():
@@ -138,8 +144,12 @@ class Trainer:
             loss = self._forward_backward(images, target)
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
-        train_ops.sgd_step(self.flat_param, self.flat_grad, self.momentum_buf, lr, self.momentum, self.weight_decay,
-                           grad_scale=1.0 / self.world, first_step=self.iteration == 0)
+        if self.optimizer == 'adamw':
+            train_ops.adamw_step(self.flat_param, self.flat_grad, self.momentum_buf, self.exp_avg_sq, lr, self.iteration + 1, self.betas,
+                                 self.adam_eps, self.weight_decay, grad_scale=1.0 / self.world)
+        else:
+            train_ops.sgd_step(self.flat_param, self.flat_grad, self.momentum_buf, lr, self.momentum, self.weight_decay,
+                               grad_scale=1.0 / self.world, first_step=self.iteration == 0)
         self.iteration += 1
         return loss
 

@@ -589,3 +589,37 @@ def test_trainer_with_the_default_dice_criterion():
         tr = Trainer(m2, base_lr=1e-2, loss_type=kind)
         ls = [float(tr.step(x, t)) for _ in range(4)]
         assert all(np.isfinite(ls)) and ls[-1] < ls[0], (kind, ls)
+
+
+def test_adamw_step_matches_torch_adamw():
+    """fscnn_train_adamw_step (train_bdd100k.py:183's optimizer) against torch.optim.AdamW over five steps on a flat buffer with changing
+    learning rates, then through the Trainer on the network."""
+    import fastscnn_oracle as fo
+    from fscnn_b200 import Trainer, train_ops
+    from models.fast_scnn import FastSCNN
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn(100_003, generator=gen)
+    ours = p0.clone().to(DEV)
+    ref = torch.nn.Parameter(p0.clone().to(DEV))
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=1e-4)
+    m, v = torch.zeros_like(ours), torch.zeros_like(ours)
+    for step in range(1, 6):
+        g = torch.randn(p0.shape, generator=gen).to(DEV) * (0.1 if step % 2 else 3.0)
+        lr = 1e-3 * (1.0 - step / 10.0) ** 0.9
+        for gp in opt.param_groups:
+            gp['lr'] = lr
+        ref.grad = g.clone()
+        opt.step()
+        train_ops.adamw_step(ours, 2.0 * g, m, v, lr, step, weight_decay=1e-4, grad_scale=0.5)
+    assert rel_err(ours.cpu().numpy(), ref.detach().cpu().numpy()) < 1e-6
+    state = opt.state[ref]
+    assert rel_err(m.cpu().numpy(), state['exp_avg'].cpu().numpy()) < 1e-6
+    assert rel_err(v.cpu().numpy(), state['exp_avg_sq'].cpu().numpy()) < 1e-6
+    model = FastSCNN(2, aux=True)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(a)) for k, a in fo.make_state_dict(2, True, seed=9).items()})
+    model.to(DEV).train()
+    x = torch.from_numpy(fo.make_input(2, 64, 96, seed=3)).to(DEV)
+    t = (torch.rand((2, 64, 96), generator=gen) < 0.25).long().to(DEV)
+    trainer = Trainer(model, base_lr=1e-3, weight_decay=1e-4, loss_type='dice', optimizer='adamw')
+    losses = [float(trainer.step(x, t)) for _ in range(6)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
