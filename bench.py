@@ -521,11 +521,11 @@ def run_native_arm(args):
         xt = smooth_images(tb, crop, crop, dev, 500 + rank, chunk=16)
         tt = torch.randint(-1, nc, (tb, crop, crop), device=dev, dtype=torch.int64)
 
-        def time_trainer(precision, graph, tsteps):
-            mt = FastSCNN(nc, aux=True).train()
+        def time_trainer(precision, graph, tsteps, classes=nc, tt=tt, **trainer_kw):
+            mt = FastSCNN(classes, aux=True).train()
             init_recipe_d2(mt, 3)
             mt.to(dev)
-            trainer = Trainer(mt, base_lr=1e-2, aux_weight=0.4, cuda_graph=graph, graph_warmup=2, matmul_precision=precision)
+            trainer = Trainer(mt, base_lr=1e-2, aux_weight=0.4, cuda_graph=graph, graph_warmup=2, matmul_precision=precision, **trainer_kw)
             l0 = float(trainer.step(xt, tt))
             for _ in range(3):             # the third of these captures the graph (graph mode)
                 trainer.step(xt, tt)
@@ -546,6 +546,14 @@ def run_native_arm(args):
             eager_ms, _, _ = time_trainer('fp32', False, 3)
             tf32_ms, _, tf32_l1 = time_trainer('tf32', True, 5)
             t_ms, l0, l1 = time_trainer('fp32', True, 5)
+            # train.py's other criteria / train_bdd100k.py's optimizer on the same step (TF32, CUDA graph): lane labels for the 2-class
+            # dice settings (train.py's default --loss-type), plain cross entropy on the 19-class labels
+            lane = (torch.rand((tb, crop, crop), device=dev) < 0.1).long()
+            other = {'dice_nc2_sgd_ms': time_trainer('tf32', True, 4, classes=2, tt=lane, loss_type='dice')[0],
+                     'dice_nc2_adamw_ms': time_trainer('tf32', True, 4, classes=2, tt=lane, loss_type='dice', optimizer='adamw')[0],
+                     'focal_dice_nc2_sgd_ms': time_trainer('tf32', True, 4, classes=2, tt=lane, loss_type='focal_dice')[0],
+                     'ce_nc19_sgd_ms': time_trainer('tf32', True, 4, loss_type='ce')[0]}
+            del lane
         finally:
             train_ops.set_matmul_precision('fp32')
         train = {'workload': f'train_step_nc{nc}_aux_crop{crop}_b{tb}_per_gpu: forward + backward + MixSoftmaxCrossEntropyOHEMLoss + '
@@ -560,6 +568,7 @@ def run_native_arm(args):
                  'fp32': {'value': tb * world / (t_ms / 1e3), 'ms_per_step': t_ms, 'loss_first_step': l0, 'loss_after_9_steps': l1,
                           'eager_launch_ms_per_step': eager_ms,
                           'note': 'default mode of the library (fp32 FMA contractions): the mode the 1e-4 parity tests are stated for'},
+                 'other_criteria_ms_per_step': other,
                  'note': 'CUDA kernels of csrc/train.cu + train_tc.cu behind autograd wrappers; DDP semantics (per-rank BatchNorm, one NCCL '
                          'all-reduce of the flat 4.6 MB gradient buffer)'}
         del xt, tt

@@ -1143,10 +1143,10 @@ int fscnn_train_sgd_step(float* d_param, const float* d_grad, float* d_momentum_
                                       (cudaStream_t)stream), "SGD");
 }
 
-int fscnn_train_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, float lr, float beta1, float beta2,
+int fscnn_train_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, float lr, double beta1, double beta2,
                            float eps, float weight_decay, float grad_scale, int64_t step, int64_t numel, void* stream) {
     if (!d_param || !d_grad || !d_exp_avg || !d_exp_avg_sq || numel < 1 || step < 1) return fail(FSCNN_EINVAL, "bad argument");
-    if (!(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f)) return fail(FSCNN_EINVAL, "betas must lie in [0, 1)");
+    if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0)) return fail(FSCNN_EINVAL, "betas must lie in [0, 1)");
     FSCNN_TRAIN_CALL(launch_train_adamw(d_param, d_grad, d_exp_avg, d_exp_avg_sq, lr, beta1, beta2, eps, weight_decay, grad_scale, step, numel,
                                         (cudaStream_t)stream), "AdamW");
 }

@@ -170,7 +170,7 @@ cudaError_t launch_train_add_relu(const float* a, const float* b, float* y, int 
 cudaError_t launch_train_relu_bwd(const float* y, const float* dy, float* dx, long long total, cudaStream_t s);
 cudaError_t launch_train_sgd(float* p, const float* g, float* buf, float lr, float momentum, float wd, float gscale, int first,
                              long long total, cudaStream_t s);
-cudaError_t launch_train_adamw(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd, float gscale,
+cudaError_t launch_train_adamw(float* p, const float* g, float* m, float* v, float lr, double b1, double b2, float eps, float wd, float gscale,
                                long long step, long long total, cudaStream_t s);
 cudaError_t launch_train_ohem_fwd(const float* logits, const long long* label, const float* weight, float* prob, float* out3, void* ws,
                                   int n, int c, int hw, long long ignore, float thresh, int min_kept, cudaStream_t s);

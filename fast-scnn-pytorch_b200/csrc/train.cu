@@ -2140,13 +2140,13 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
 // torch.optim.AdamW (decoupled weight decay; train_bdd100k.py:183-185) on flat buffers: p *= 1 - lr wd; m = b1 m + (1 - b1) g;
 // v = b2 v + (1 - b2) g^2; p -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps) with the bias corrections bc = 1 - beta^step from the host
 __global__ void __launch_bounds__(kT)
-adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float lr, float b1, float b2,
-             float eps, float wd, float gscale, float step_size, float rsqrt_bc2, long long total) {
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float lr, float omb1, float b2,
+             float omb2, float eps, float wd, float gscale, float step_size, float rsqrt_bc2, long long total) {
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
         const float gi = g[i] * gscale;
         const float pi = p[i] * (1.f - lr * wd);
-        const float mi = m[i] + (gi - m[i]) * (1.f - b1);              // torch's lerp form of b1 m + (1 - b1) g
-        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        const float mi = m[i] + (gi - m[i]) * omb1;                    // torch's lerp form of b1 m + (1 - b1) g
+        const float vi = fmaf(b2, v[i], omb2 * gi * gi);               // 1 - beta comes from the host in double, like torch's scalars
         m[i] = mi;
         v[i] = vi;
         p[i] = pi - step_size * (mi / (sqrtf(vi) * rsqrt_bc2 + eps));
@@ -2446,11 +2446,11 @@ cudaError_t launch_train_sgd(float* p, const float* g, float* buf, float lr, flo
     return cudaGetLastError();
 }
 
-cudaError_t launch_train_adamw(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, float wd, float gscale,
+cudaError_t launch_train_adamw(float* p, const float* g, float* m, float* v, float lr, double b1, double b2, float eps, float wd, float gscale,
                                long long step, long long total, cudaStream_t s) {
-    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
-    adamw_kernel<<<grid_for(total), kT, 0, s>>>(p, g, m, v, lr, b1, b2, eps, wd, gscale, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)),
-                                                total);
+    const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+    adamw_kernel<<<grid_for(total), kT, 0, s>>>(p, g, m, v, lr, (float)(1.0 - b1), (float)b2, (float)(1.0 - b2), eps, wd, gscale,
+                                                (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), total);
     return cudaGetLastError();
 }
 

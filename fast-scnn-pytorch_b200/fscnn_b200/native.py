@@ -93,7 +93,7 @@ _SIGNATURES = {
     'fscnn_train_get_math': (C.c_int, []),
     'fscnn_train_sgd_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64,
                                        C.c_void_p]),
-    'fscnn_train_adamw_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+    'fscnn_train_adamw_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_double, C.c_double, C.c_float, C.c_float,
                                          C.c_float, C.c_int64, C.c_int64, C.c_void_p]),
     'fscnn_train_ohem_workspace_bytes': (C.c_int, [C.POINTER(C.c_size_t)]),
     'fscnn_train_ohem_forward': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,

@@ -294,7 +294,7 @@ int fscnn_train_sgd_step(float* d_param, const float* d_grad, float* d_momentum_
  * (0.9, 0.999), eps = 1e-8) on flat fp32 buffers, one launch: decoupled weight decay, first / second moment buffers d_exp_avg /
  * d_exp_avg_sq (zero before the first step), bias corrections from `step` (1 for the first call).  The gradient is read as
  * d_grad * grad_scale (1 / world size after a summing all-reduce). */
-int fscnn_train_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, float lr, float beta1, float beta2,
+int fscnn_train_adamw_step(float* d_param, const float* d_grad, float* d_exp_avg, float* d_exp_avg_sq, float lr, double beta1, double beta2,
                            float eps, float weight_decay, float grad_scale, int64_t step, int64_t numel, void* stream);
 
 /* SoftmaxCrossEntropyOHEMLoss.forward (utils/loss.py:143-182) without the host round trip: softmax probability of the target
