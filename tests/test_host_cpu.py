@@ -203,3 +203,19 @@ def test_loss_module_mirrors_the_reference_interface():
         L.MixSoftmaxCrossEntropyLoss(aux=False)((pred, pred), target)
     with pytest.raises(RuntimeError):        # CPU tensors: there is no CPU path
         L.DiceLoss()(pred, target)
+
+
+def test_lr_scheduler_is_bit_identical_to_the_reference():
+    """utils/lr_scheduler.LRScheduler against learning rates the reference class produced (tests/golden/lr_scheduler_cases.json, written
+    by running both classes side by side in the build container): every mode, offsets, epoch-based steps; and Trainer's poly_lr agrees."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from fscnn_b200 import poly_lr
+    from utils.lr_scheduler import LRScheduler
+    for case in json.load(open(os.path.join(GOLDEN, 'lr_scheduler_cases.json'))):
+        sched = LRScheduler(**case['kwargs'])
+        assert [sched(i) for i in case['iters']] == case['lr'], case['kwargs']
+    sched = LRScheduler(mode='poly', base_lr=0.01, nepochs=60, iters_per_epoch=176, power=0.9)
+    for it in (0, 1, 500, 60 * 176 - 2):
+        assert abs(sched(it) - poly_lr(0.01, it, 60, 176)) <= 1e-15
