@@ -623,3 +623,53 @@ def test_adamw_step_matches_torch_adamw():
     trainer = Trainer(model, base_lr=1e-3, weight_decay=1e-4, loss_type='dice', optimizer='adamw')
     losses = [float(trainer.step(x, t)) for _ in range(6)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize('use_fp16,loss_type', [(True, 'dice'), (False, 'ce_ohem'), (True, 'ce_plain')])
+def test_reference_training_loop_body_runs_on_the_drop_in_modules(use_fp16, loss_type):
+    """The statements of the reference's training iteration (train.py:257-284: LRScheduler -> param_group['lr'] -> zero_grad ->
+    [autocast] forward + criterion -> [GradScaler] backward + optimizer.step) with the objects train.py builds (:169, :182-198,
+    :205-207), imported from this package instead: get_fast_scnn, utils.loss criteria, torch.optim.SGD on the module's parameters,
+    utils.lr_scheduler.  The training operators keep fp32 under autocast; the loss must fall on a fixed batch."""
+    import fastscnn_oracle as fo
+    from torch.cuda.amp import GradScaler, autocast
+    from models.fast_scnn import get_fast_scnn
+    from utils.loss import MixDiceLoss, MixSoftmaxCrossEntropyLoss, MixSoftmaxCrossEntropyOHEMLoss
+    from utils.lr_scheduler import LRScheduler
+    model = get_fast_scnn(dataset='citys', aux=True).to(DEV)                                   # train.py:169
+    if loss_type == 'dice':
+        criterion = MixDiceLoss(aux=True, aux_weight=0.4).to(DEV)                              # train.py:184
+        targets = (torch.rand((2, 96, 128), generator=torch.Generator().manual_seed(2)) < 0.3).long().to(DEV)
+    elif loss_type == 'ce_ohem':
+        criterion = MixSoftmaxCrossEntropyOHEMLoss(aux=True, aux_weight=0.4, ignore_index=-1).to(DEV)     # train.py:190-191
+        targets = torch.from_numpy(fo.make_labels(2, 96, 128, 19, seed=4)).to(DEV)
+    else:
+        criterion = MixSoftmaxCrossEntropyLoss(True, 0.4, ignore_index=-1).to(DEV)             # train_custom_finetune.py:99
+        targets = torch.from_numpy(fo.make_labels(2, 96, 128, 19, seed=4)).to(DEV)
+    optimizer = torch.optim.SGD(model.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-4)  # train.py:195-198
+    scaler = GradScaler() if use_fp16 else None                                                # train.py:201
+    lr_scheduler = LRScheduler(mode='poly', base_lr=1e-2, nepochs=2, iters_per_epoch=4, power=0.9)
+    images = torch.from_numpy(fo.make_input(2, 96, 128, seed=8)).to(DEV)
+    model.train()
+    losses = []
+    for cur_iters in range(6):
+        cur_lr = lr_scheduler(cur_iters)
+        for param_group in optimizer.param_groups:
+            param_group['lr'] = cur_lr
+        optimizer.zero_grad()
+        if use_fp16:
+            with autocast():
+                outputs = model(images)
+                loss = criterion(outputs, targets)
+            scaler.scale(loss).backward()
+            scaler.step(optimizer)
+            scaler.update()
+        else:
+            outputs = model(images)
+            loss = criterion(outputs, targets)
+            loss.backward()
+            optimizer.step()
+        losses.append(loss.item())
+    assert outputs[0].shape == (2, 19, 96, 128) and outputs[0].dtype == torch.float32 and len(outputs) == 2
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert all(torch.isfinite(p).all() for p in model.parameters())
