@@ -34,6 +34,8 @@ def poly_lr(base_lr: float, cur_iter: int, nepochs: int, iters_per_epoch: int, p
 
 
 class Trainer:
+    loss_type = 'ohem'      # class-level default: MixSoftmaxCrossEntropyOHEMLoss (BASELINE config 5)
+
     def __init__(self, model, base_lr=1e-2, momentum=0.9, weight_decay=1e-4, aux_weight=0.4, ignore_label=-1, ohem_thresh=0.7,
                  ohem_min_kept=256, use_class_weights: Optional[bool] = None, nepochs=160, iters_per_epoch=1000, process_group=None,
                  fused_loss: bool = True, cuda_graph: bool = False, graph_warmup: int = 3, matmul_precision: Optional[str] = None,
