@@ -2577,15 +2577,17 @@ struct CritPix {
     __device__ __forceinline__ float fetch(int c) const {
         return UP ? up_value(lp + (long long)c * cs, wl, y0, y1, x0, x1, ly, lx) : __ldg(lp + (long long)c * cs);
     }
-    __device__ __forceinline__ void load() {
+    // CT > 0: a compile-time BOUND on the class count (1, 2, 4, 8, 16, 19, 32): the pixel's values are fetched once into registers
+    // and every class loop is unrolled CT times with the tail (c >= C) predicated off; CT == 0: any count, values re-fetched per pass
+    __device__ __forceinline__ void load(int C) {
         if (CT > 0) {
 #pragma unroll
-            for (int c = 0; c < (CT > 0 ? CT : 1); ++c) v[c] = fetch(c);
+            for (int c = 0; c < (CT > 0 ? CT : 1); ++c) v[c] = c < C ? fetch(c) : 0.f;
         }
     }
     __device__ __forceinline__ float get(int c) const { return CT > 0 ? v[c] : fetch(c); }
 };
-#define CRIT_FOR_CLASSES(c) _Pragma("unroll") for (int c = 0; c < (CT > 0 ? CT : C); ++c)
+#define CRIT_FOR_CLASSES(c) _Pragma("unroll") for (int c = 0; c < (CT > 0 ? CT : C); ++c) if (CT == 0 || c < C)
 
 __device__ __forceinline__ float crit_sigmoid(float z) { return 1.f / (1.f + expf(-z)); }
 
@@ -2688,18 +2690,21 @@ crit_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
     const int C = g.C;
     const long long HW = (long long)g.H * g.W;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const bool small = npix <= 0x7fffffffLL;       // 32-bit index arithmetic (a 64-bit division costs ~100 instructions per pixel)
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
-        const long long n = i / HW, p = i % HW;
+        long long n, p;
+        if (small) { const unsigned int q = (unsigned int)i / (unsigned int)HW; n = q; p = (unsigned int)i - q * (unsigned int)HW; }
+        else { n = i / HW; p = i % HW; }
         CritPix<CT, UP> u;
         if (UP) {
-            const int y = (int)(p / g.W), x = (int)(p % g.W);
+            const int y = small ? (int)((unsigned int)p / (unsigned int)g.W) : (int)(p / g.W), x = (int)(p - (long long)y * g.W);
             ac_coord(y, g.scy, g.hl, u.y0, u.y1, u.ly);
             ac_coord(x, g.scx, g.wl, u.x0, u.x1, u.lx);
             u.lp = logits + n * C * g.hl * g.wl; u.cs = (long long)g.hl * g.wl; u.wl = g.wl;
         } else {
             u.lp = logits + n * C * HW + p; u.cs = HW;
         }
-        u.load();
+        u.load(C);
         crit_pixel_fwd<CT, UP>(u, C, label[i], a, acc);
     }
     block_sum<4>(acc, sm);
@@ -2738,11 +2743,15 @@ __global__ void __launch_bounds__(kT)
 crit_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ label, int C, long long HW, long long npix, CritArgs a,
                  const double* __restrict__ out, const float* __restrict__ gout, float* __restrict__ dlogits) {
     const CritScal s = crit_scalars(out, __ldg(gout), a);
+    const bool small = npix <= 0x7fffffffLL;
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < npix; i += (long long)gridDim.x * kT) {
-        const long long n = i / HW, p = i % HW, lab = label[i];
+        long long n, p;
+        if (small) { const unsigned int q = (unsigned int)i / (unsigned int)HW; n = q; p = (unsigned int)i - q * (unsigned int)HW; }
+        else { n = i / HW; p = i % HW; }
+        const long long lab = label[i];
         CritPix<CT, false> u;
         u.lp = logits + n * C * HW + p; u.cs = HW;
-        u.load();
+        u.load(C);
         float* dp = dlogits + n * C * HW + p;
         if (C == 1 && a.kind != kCritCE) { dp[0] = crit_grad_binary(u.get(0), lab, a, s); continue; }
         float mx, inv, wce, wd;
@@ -2790,7 +2799,7 @@ crit_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__
         const bool binary = C == 1 && a.kind != kCritCE;
         if (live_x) {
             lab = label[((long long)n * g.H + y) * g.W + x];
-            u.load();
+            u.load(C);
             if (binary) gb = crit_grad_binary(u.get(0), lab, a, s);
             else crit_pixel_bwd_coef<CT, true>(u, C, lab, a, s, mx, inv, wce, wd);
         } else if (CT > 0) {
@@ -2833,15 +2842,20 @@ crit_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__
     }
 }
 
+// register-resident class values up to 32 classes: the smallest compile-time bound that holds c (19 = Cityscapes keeps its own)
+static int crit_bucket(int c) { return c <= 2 ? c : c <= 4 ? 4 : c <= 8 ? 8 : c <= 16 ? 16 : c == 19 ? 19 : c <= 32 ? 32 : 0; }
+
 size_t train_criterion_workspace_bytes() { return (size_t)num_sms() * 16 * 4 * sizeof(double) + 256; }
 
 template <bool UP>
 static void launch_crit_fwd(int c, int grid, const float* logits, const long long* label, const UpGeom& g, long long npix, const CritArgs& a,
                             double* partial, cudaStream_t s) {
-    if (c == 1) crit_fwd_kernel<1, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
-    else if (c == 2) crit_fwd_kernel<2, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
-    else if (c == 19) crit_fwd_kernel<19, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
-    else crit_fwd_kernel<0, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial);
+#define CRIT_FWD(CTV) crit_fwd_kernel<CTV, UP><<<grid, kT, 0, s>>>(logits, label, g, npix, a, partial)
+    switch (crit_bucket(c)) {
+        case 1: CRIT_FWD(1); break;   case 2: CRIT_FWD(2); break;   case 4: CRIT_FWD(4); break;   case 8: CRIT_FWD(8); break;
+        case 16: CRIT_FWD(16); break; case 19: CRIT_FWD(19); break; case 32: CRIT_FWD(32); break; default: CRIT_FWD(0); break;
+    }
+#undef CRIT_FWD
 }
 
 cudaError_t launch_train_criterion_fwd(const float* logits, const long long* label, double* out6, void* ws, int kind, int n, int c, int hl,
@@ -2866,10 +2880,12 @@ cudaError_t launch_train_criterion_bwd(const float* logits, const long long* lab
     if (hl == h && wl == w) {
         const int grid = grid_for(npix);
         const long long hw = (long long)h * w;
-        if (c == 1) crit_grad_kernel<1><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
-        else if (c == 2) crit_grad_kernel<2><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
-        else if (c == 19) crit_grad_kernel<19><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
-        else crit_grad_kernel<0><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits);
+#define CRIT_GRAD(CTV) crit_grad_kernel<CTV><<<grid, kT, 0, s>>>(logits, label, c, hw, npix, a, out6, gout, dlogits)
+        switch (crit_bucket(c)) {
+            case 1: CRIT_GRAD(1); break;   case 2: CRIT_GRAD(2); break;   case 4: CRIT_GRAD(4); break;   case 8: CRIT_GRAD(8); break;
+            case 16: CRIT_GRAD(16); break; case 19: CRIT_GRAD(19); break; case 32: CRIT_GRAD(32); break; default: CRIT_GRAD(0); break;
+        }
+#undef CRIT_GRAD
         return cudaGetLastError();
     }
     const size_t smem = (size_t)c * kUpTR * kUpTC * sizeof(float);
@@ -2878,10 +2894,12 @@ cudaError_t launch_train_criterion_bwd(const float* logits, const long long* lab
     if (e != cudaSuccess) return e;
     const dim3 grid((w + 31) / 32, (h + 63) / 64, n);
     const UpGeom g = up_geom(c, hl, wl, h, w);
-    if (c == 1) crit_up_grad_kernel<1><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
-    else if (c == 2) crit_up_grad_kernel<2><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
-    else if (c == 19) crit_up_grad_kernel<19><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
-    else crit_up_grad_kernel<0><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits);
+#define CRIT_UPG(CTV) crit_up_grad_kernel<CTV><<<grid, kT, smem, s>>>(logits, label, g, a, out6, gout, dlogits)
+    switch (crit_bucket(c)) {
+        case 1: CRIT_UPG(1); break;   case 2: CRIT_UPG(2); break;   case 4: CRIT_UPG(4); break;   case 8: CRIT_UPG(8); break;
+        case 16: CRIT_UPG(16); break; case 19: CRIT_UPG(19); break; case 32: CRIT_UPG(32); break; default: CRIT_UPG(0); break;
+    }
+#undef CRIT_UPG
     return cudaGetLastError();
 }
 

@@ -1,1 +1,2 @@
-"""Drop-in for the hot-path part of the reference ``utils`` package (utils/metric.py)."""
+"""Drop-ins for the reference ``utils`` package around the hot path: metric.py (SegmentationMetric), visualize.py (palettes,
+overlay), loss.py (the training criteria) and lr_scheduler.py."""

@@ -527,7 +527,8 @@ def test_criteria_match_reference_fixtures():
 
 
 @pytest.mark.parametrize('kind,n,c,hl,wl,h,w', [('ce', 2, 19, 12, 16, 96, 128), ('dice', 2, 2, 9, 13, 65, 97), ('focal_dice', 1, 2, 12, 12, 96, 96),
-                                                 ('ce', 1, 7, 10, 20, 80, 160), ('dice', 2, 1, 6, 8, 48, 64), ('focal_dice', 2, 4, 5, 9, 40, 70)])
+                                                 ('ce', 1, 7, 10, 20, 80, 160), ('dice', 2, 1, 6, 8, 48, 64), ('focal_dice', 2, 4, 5, 9, 40, 70),
+                                                 ('ce', 1, 12, 6, 8, 48, 64), ('focal_dice', 1, 21, 6, 8, 48, 64), ('ce', 1, 40, 6, 8, 48, 64)])
 def test_fused_upsample_criteria_equal_the_two_step_form_and_the_oracle(kind, n, c, hl, wl, h, w):
     """criterion(low) with the resize inside the loss kernels == criterion(bilinear_resize(low)) (same interpolation arithmetic: the
     loss agrees to rounding of the final sum), and both follow the float64 oracle."""

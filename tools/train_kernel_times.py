@@ -1,6 +1,6 @@
 """Per-kernel device time of one training step (BASELINE config 5) from the CUPTI activity trace (torch.profiler: kernels run
 back to back as in a real step, unlike the serialised cold-cache ncu launch list).
-    python tools/train_kernel_times.py [batch=16] [crop=768] [steps=3] [fp32|tf32]"""
+    python tools/train_kernel_times.py [batch=16] [crop=768] [steps=3] [fp32|tf32] [ohem|ce|dice|focal_dice] [classes=19] [sgd|adamw]"""
 import collections
 import os
 import sys
@@ -21,13 +21,19 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 if len(sys.argv) > 4:
     from fscnn_b200 import train_ops
     train_ops.set_matmul_precision(sys.argv[4])
+loss_type = sys.argv[5] if len(sys.argv) > 5 else 'ohem'
+nc = int(sys.argv[6]) if len(sys.argv) > 6 else 19
+optimizer = sys.argv[7] if len(sys.argv) > 7 else 'sgd'
 dev = torch.device('cuda', 0)
-m = FastSCNN(19, aux=True).train()
+m = FastSCNN(nc, aux=True).train()
 bench.init_recipe_d2(m, 3)
 m.to(dev)
-tr = Trainer(m)
+tr = Trainer(m, loss_type=loss_type, optimizer=optimizer)
 x = bench.smooth_images(tb, crop, crop, dev, 1, chunk=16)
-t = torch.randint(-1, 19, (tb, crop, crop), device=dev)
+if loss_type in ('dice', 'focal_dice'):      # lane-like binary labels (train.py's default setting)
+    t = (torch.rand((tb, crop, crop), device=dev) < 0.1).long()
+else:
+    t = torch.randint(-1, nc, (tb, crop, crop), device=dev)
 for _ in range(3):
     tr.step(x, t)
 torch.cuda.synchronize()
@@ -46,7 +52,7 @@ for ev in prof.events():
     a[0] += 1
     a[1] += ev.device_time_total if hasattr(ev, 'device_time_total') else ev.cuda_time_total
 tot = sum(a[1] for a in agg.values())
-print(f'{steps} steps, batch {tb}, crop {crop}: {tot / steps / 1e3:.2f} ms of kernel time per step')
+print(f'{steps} steps, batch {tb}, crop {crop}, {nc} classes, loss {loss_type}, {optimizer}: {tot / steps / 1e3:.2f} ms of kernel time per step')
 print('| kernel | launches / step | us / step | us / launch | share |\n|---|---|---|---|---|')
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     if a[1] / tot < 0.002:
