@@ -291,9 +291,11 @@ class Criterion(torch.autograd.Function):
         if target.dtype != torch.int64 or target.dim() != 3 or not target.is_cuda:
             raise ValueError('target must be a CUDA int64 [N,H,W] tensor')
         n, c, hl, wl = logits.shape
-        if target.shape[0] != n:
-            raise ValueError(f'target batch {target.shape[0]} does not match logits batch {n}')
+        if target.shape[0] != n or target.device != logits.device:
+            raise ValueError(f'target [{target.shape[0]}, ...] on {target.device} does not match logits [{n}, ...] on {logits.device}')
         h, w = int(target.shape[1]), int(target.shape[2])
+        if hl > h or wl > w:
+            raise ValueError(f'logits {hl}x{wl} are larger than the target {h}x{w}')
         target = target.contiguous()
         need = C.c_size_t()
         native.check(native.lib().fscnn_train_criterion_workspace_bytes(C.byref(need)))
