@@ -2590,6 +2590,34 @@ struct CritPix {
 #define CRIT_FOR_CLASSES(c) _Pragma("unroll") for (int c = 0; c < (CT > 0 ? CT : C); ++c) if (CT == 0 || c < C)
 
 __device__ __forceinline__ float crit_sigmoid(float z) { return 1.f / (1.f + expf(-z)); }
+// x^g for the focal term: the reference's default gamma = 2 (and the 1 its derivative needs) without the general powf (uniform branch)
+__device__ __forceinline__ float crit_pow(float x, float g) { return g == 2.f ? x * x : (g == 1.f ? x : (g == 3.f ? x * x * x : powf(x, g))); }
+
+// Row cache of the fused-resize kernels whose threads own a COLUMN and walk rows (CT > 0): per class the two horizontally
+// interpolated low-resolution rows the current output row sits between -- the inner two fmaf of up_value, refreshed only when the
+// row pair changes (every ~8 rows at ratio 1/8) -- so a pixel costs one vertical fmaf per class and the value is bit-identical to
+// up_value's.
+template <int CT>
+struct CritRows {
+    float top[CT > 0 ? CT : 1], bot[CT > 0 ? CT : 1];
+    int y0 = -1, y1 = -1;
+    __device__ __forceinline__ void values(CritPix<CT, true>& u, int C) {
+        if (CT == 0) return;
+        if (u.y0 != y0 || u.y1 != y1) {          // warp-uniform: a warp's lanes share the output row
+            y0 = u.y0; y1 = u.y1;
+#pragma unroll
+            for (int c = 0; c < (CT > 0 ? CT : 1); ++c) {
+                if (c < C) {
+                    const float* base = u.lp + (long long)c * u.cs;
+                    top[c] = fmaf(u.lx, __ldg(base + y0 * u.wl + u.x1), (1.f - u.lx) * __ldg(base + y0 * u.wl + u.x0));
+                    bot[c] = fmaf(u.lx, __ldg(base + y1 * u.wl + u.x1), (1.f - u.lx) * __ldg(base + y1 * u.wl + u.x0));
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < (CT > 0 ? CT : 1); ++c) u.v[c] = c < C ? fmaf(u.ly, bot[c], (1.f - u.ly) * top[c]) : 0.f;
+    }
+};
 
 // acc: kind 0 {sum nll, count, -, -}; kinds 1, 2 {sum p t, sum p, sum t, sum focal}
 template <int CT, bool UP>
@@ -2600,7 +2628,7 @@ __device__ __forceinline__ void crit_pixel_fwd(const CritPix<CT, UP>& u, int C, 
         if (a.kind == kCritFocalDice) {
             const float ce = -(t * fmaxf(logf(p), -100.f) + (1.f - t) * fmaxf(logf(1.f - p), -100.f));
             const float pt = t == 1.f ? p : 1.f - p;
-            acc[3] += (double)(a.alpha * powf(1.f - pt, a.gamma) * ce);
+            acc[3] += (double)(a.alpha * crit_pow(1.f - pt, a.gamma) * ce);
         }
         return;
     }
@@ -2622,7 +2650,7 @@ __device__ __forceinline__ void crit_pixel_fwd(const CritPix<CT, UP>& u, int C, 
     acc[0] += (double)(p1 * t); acc[1] += (double)p1; acc[2] += (double)t;
     if (a.kind == kCritFocalDice && valid) {
         const float ce = -((vl - mx) - logf(sum)), pt = expf(-ce);
-        acc[3] += (double)(a.alpha * powf(1.f - pt, a.gamma) * ce);
+        acc[3] += (double)(a.alpha * crit_pow(1.f - pt, a.gamma) * ce);
     }
 }
 
@@ -2650,20 +2678,22 @@ __device__ __forceinline__ float crit_grad_binary(float z, long long lab, const 
         const float ce = -(t * fmaxf(logf(p), -100.f) + (1.f - t) * fmaxf(logf(1.f - p), -100.f));
         const float dce = (p - t) / fmaxf((1.f - p) * p, 1e-12f);            // binary_cross_entropy's own backward
         const float pt = t == 1.f ? p : 1.f - p, dpt = t == 1.f ? 1.f : -1.f, om = 1.f - pt;
-        gp += s.sf * a.alpha * (powf(om, a.gamma) * dce - a.gamma * powf(om, a.gamma - 1.f) * dpt * ce);
+        gp += s.sf * a.alpha * (crit_pow(om, a.gamma) * dce - a.gamma * crit_pow(om, a.gamma - 1.f) * dpt * ce);
     }
     return gp * p * (1.f - p);
 }
 
 // softmax statistics of a pixel for the backward: g_c = wce * (p_c - [c == lab]) + wd * ([c == 1] - p_c), p_c = exp(v_c - mx) * inv
+// (CT > 0: the exponentials stay in ev[] for the caller's gradient loop)
 template <int CT, bool UP>
 __device__ __forceinline__ void crit_pixel_bwd_coef(const CritPix<CT, UP>& u, int C, long long lab, const CritArgs& a, const CritScal& s,
-                                                    float& mx, float& inv, float& wce, float& wd) {
+                                                    float& mx, float& inv, float& wce, float& wd, float (&ev)[CT > 0 ? CT : 1]) {
     mx = -FLT_MAX;
     CRIT_FOR_CLASSES(c) mx = fmaxf(mx, u.get(c));
     float sum = 0.f, el = 0.f, e1 = 0.f;
     CRIT_FOR_CLASSES(c) {
         const float e = expf(u.get(c) - mx);
+        if (CT > 0) ev[CT > 0 ? c : 0] = e;
         sum += e;
         if (c == lab) el = e;
         if (c == 1) e1 = e;
@@ -2678,7 +2708,7 @@ __device__ __forceinline__ void crit_pixel_bwd_coef(const CritPix<CT, UP>& u, in
     wd = (s.da * (float)lab + s.db) * (e1 * inv);
     if (a.kind == kCritFocalDice && valid) {
         const float pt = el * inv, ce = -logf(pt), om = 1.f - pt;
-        wce = s.sf * a.alpha * (powf(om, a.gamma) + a.gamma * powf(om, a.gamma - 1.f) * pt * ce);
+        wce = s.sf * a.alpha * (crit_pow(om, a.gamma) + a.gamma * crit_pow(om, a.gamma - 1.f) * pt * ce);
     }
 }
 
@@ -2706,6 +2736,40 @@ crit_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ 
         }
         u.load(C);
         crit_pixel_fwd<CT, UP>(u, C, label[i], a, acc);
+    }
+    block_sum<4>(acc, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) partial[blockIdx.x * 4 + k] = acc[k];
+    }
+}
+
+// The fused-resize forward for register-resident class counts: tiles of 64 rows x 32 columns walked by a capped grid (one partial
+// per CTA, reduced in a fixed order), lane = column, warp = 8 rows; no per-pixel index divisions, row cache as above.
+template <int CT>
+__global__ void __launch_bounds__(kT)
+crit_strip_fwd_kernel(const float* __restrict__ low, const long long* __restrict__ label, UpGeom g, int tiles_x, int tiles_y, int ntiles,
+                      CritArgs a, double* __restrict__ partial) {
+    __shared__ double sm[4 * 8];
+    const int C = g.C, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = tile % tiles_x, r = tile / tiles_x, ty = r % tiles_y, n = r / tiles_y;
+        const int x = tx * 32 + lane;
+        if (x >= g.W) continue;
+        CritPix<CT, true> u;
+        u.lp = low + (long long)n * C * g.hl * g.wl; u.cs = (long long)g.hl * g.wl; u.wl = g.wl;
+        ac_coord(x, g.scx, g.wl, u.x0, u.x1, u.lx);
+        CritRows<CT> rows;
+        const int y_first = ty * 64 + warp * 8;
+        const long long* lab = label + ((long long)n * g.H + y_first) * g.W + x;
+#pragma unroll 1
+        for (int rr = 0; rr < 8; ++rr) {
+            if (y_first + rr >= g.H) break;
+            ac_coord(y_first + rr, g.scy, g.hl, u.y0, u.y1, u.ly);
+            rows.values(u, C);
+            crit_pixel_fwd<CT, true>(u, C, lab[(long long)rr * g.W], a, acc);
+        }
     }
     block_sum<4>(acc, sm);
     if (threadIdx.x == 0) {
@@ -2754,10 +2818,10 @@ crit_grad_kernel(const float* __restrict__ logits, const long long* __restrict__
         u.load(C);
         float* dp = dlogits + n * C * HW + p;
         if (C == 1 && a.kind != kCritCE) { dp[0] = crit_grad_binary(u.get(0), lab, a, s); continue; }
-        float mx, inv, wce, wd;
-        crit_pixel_bwd_coef<CT, false>(u, C, lab, a, s, mx, inv, wce, wd);
+        float mx, inv, wce, wd, ev[CT > 0 ? CT : 1];
+        crit_pixel_bwd_coef<CT, false>(u, C, lab, a, s, mx, inv, wce, wd, ev);
         CRIT_FOR_CLASSES(c) {
-            const float pc = expf(u.get(c) - mx) * inv;
+            const float pc = (CT > 0 ? ev[CT > 0 ? c : 0] : expf(u.get(c) - mx)) * inv;
             dp[(long long)c * HW] = wce * (pc - (c == lab ? 1.f : 0.f)) + wd * ((c == 1 ? 1.f : 0.f) - pc);
         }
     }
@@ -2790,18 +2854,53 @@ crit_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__
         const int ux0 = __shfl_down_sync(0xffffffffu, u.x0, 1 << k);
         if (lane + (1 << k) < 32 && ux0 == u.x0) same |= 1u << k;
     }
+    CritRows<CT> rows;
+    // register-resident counts up to 19: a thread's gradient is accumulated per class for the two low-resolution rows of the current
+    // row pair and reduced over the lanes / added to the tile only when the pair changes (every ~8 rows) instead of once per row
+    constexpr bool kAccum = CT > 0 && CT <= 19;
+    float g0[kAccum ? CT : 1], g1[kAccum ? CT : 1];
+    int fy0 = -1, fy1 = -1;
+    if (kAccum) {
+#pragma unroll
+        for (int c = 0; c < (kAccum ? CT : 1); ++c) { g0[c] = 0.f; g1[c] = 0.f; }
+    }
+    auto flush = [&]() {          // executed by whole warps (the row pair is warp-uniform)
+        if (!kAccum || fy0 < 0) return;
+        const int ay0 = (fy0 - ry0) * kUpTC, ay1 = (fy1 - ry0) * kUpTC, ax0 = u.x0 - rx0, ax1 = u.x1 - rx0;
+#pragma unroll
+        for (int c = 0; c < (kAccum ? CT : 1); ++c) {
+            if (c < C) {
+                float a0 = g0[c] * (1.f - u.lx), b0 = g0[c] * u.lx, a1 = g1[c] * (1.f - u.lx), b1 = g1[c] * u.lx;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float ua0 = __shfl_down_sync(0xffffffffu, a0, 1 << k), ub0 = __shfl_down_sync(0xffffffffu, b0, 1 << k);
+                    const float ua1 = __shfl_down_sync(0xffffffffu, a1, 1 << k), ub1 = __shfl_down_sync(0xffffffffu, b1, 1 << k);
+                    if ((same >> k) & 1u) { a0 += ua0; b0 += ub0; a1 += ua1; b1 += ub1; }
+                }
+                if (head && live_x) {
+                    float* ac = acc + c * kUpTR * kUpTC;
+                    if (a0 != 0.f) atomicAdd(ac + ay0 + ax0, a0);
+                    if (b0 != 0.f) atomicAdd(ac + ay0 + ax1, b0);
+                    if (a1 != 0.f) atomicAdd(ac + ay1 + ax0, a1);
+                    if (b1 != 0.f) atomicAdd(ac + ay1 + ax1, b1);
+                }
+                g0[c] = 0.f; g1[c] = 0.f;
+            }
+        }
+    };
     for (int rr = 0; rr < 8; ++rr) {
         const int y = yb + warp * 8 + rr;
         if (y >= g.H) break;                                   // warp-uniform
         ac_coord(y, g.scy, g.hl, u.y0, u.y1, u.ly);
+        if (kAccum && (u.y0 != fy0 || u.y1 != fy1)) { flush(); fy0 = u.y0; fy1 = u.y1; }
         long long lab = a.ignore;
-        float mx = 0.f, inv = 0.f, wce = 0.f, wd = 0.f, gb = 0.f;
+        float mx = 0.f, inv = 0.f, wce = 0.f, wd = 0.f, gb = 0.f, ev[CT > 0 ? CT : 1];
         const bool binary = C == 1 && a.kind != kCritCE;
         if (live_x) {
             lab = label[((long long)n * g.H + y) * g.W + x];
-            u.load(C);
+            rows.values(u, C);
             if (binary) gb = crit_grad_binary(u.get(0), lab, a, s);
-            else crit_pixel_bwd_coef<CT, true>(u, C, lab, a, s, mx, inv, wce, wd);
+            else crit_pixel_bwd_coef<CT, true>(u, C, lab, a, s, mx, inv, wce, wd, ev);
         } else if (CT > 0) {
 #pragma unroll
             for (int c = 0; c < (CT > 0 ? CT : 1); ++c) u.v[c] = 0.f;
@@ -2812,9 +2911,14 @@ crit_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__
             if (live_x) {
                 if (binary) gc = gb;
                 else if (wce != 0.f || wd != 0.f) {
-                    const float pc = expf(u.get(c) - mx) * inv;
+                    const float pc = (CT > 0 ? ev[CT > 0 ? c : 0] : expf(u.get(c) - mx)) * inv;
                     gc = wce * (pc - (c == lab ? 1.f : 0.f)) + wd * ((c == 1 ? 1.f : 0.f) - pc);
                 }
+            }
+            if (kAccum) {
+                g0[kAccum ? c : 0] = fmaf(gc, 1.f - u.ly, g0[kAccum ? c : 0]);
+                g1[kAccum ? c : 0] = fmaf(gc, u.ly, g1[kAccum ? c : 0]);
+                continue;
             }
             float ga = gc * (1.f - u.lx), gbx = gc * u.lx;       // towards columns x0 and x1
 #pragma unroll
@@ -2831,6 +2935,7 @@ crit_up_grad_kernel(const float* __restrict__ low, const long long* __restrict__
             }
         }
     }
+    flush();
     __syncthreads();
     for (int i = tid; i < C * kUpTR * kUpTC; i += kT) {
         const float v = acc[i];
@@ -2866,9 +2971,24 @@ cudaError_t launch_train_criterion_fwd(const float* logits, const long long* lab
     const UpGeom g = up_geom(c, hl, wl, h, w);
     const int grid = grid_for(npix);
     double* partial = reinterpret_cast<double*>(ws);
-    if (hl == h && wl == w) launch_crit_fwd<false>(c, grid, logits, label, g, npix, a, partial, s);
-    else launch_crit_fwd<true>(c, grid, logits, label, g, npix, a, partial, s);
-    crit_finalize_kernel<<<1, kT, 0, s>>>(partial, grid, npix, a, out6);
+    int nparts = grid;
+    if (hl == h && wl == w) {
+        launch_crit_fwd<false>(c, grid, logits, label, g, npix, a, partial, s);
+    } else if (crit_bucket(c) == 0) {
+        launch_crit_fwd<true>(c, grid, logits, label, g, npix, a, partial, s);
+    } else {
+        const int tiles_x = (w + 31) / 32, tiles_y = (h + 63) / 64;
+        const long long nt = (long long)tiles_x * tiles_y * n, cap = (long long)num_sms() * 16;
+        if (nt > 0x7fffffffLL) return cudaErrorInvalidValue;
+        nparts = (int)(nt < cap ? nt : cap);
+#define CRIT_SFWD(CTV) crit_strip_fwd_kernel<CTV><<<nparts, kT, 0, s>>>(logits, label, g, tiles_x, tiles_y, (int)nt, a, partial)
+        switch (crit_bucket(c)) {
+            case 1: CRIT_SFWD(1); break;   case 2: CRIT_SFWD(2); break;   case 4: CRIT_SFWD(4); break;   case 8: CRIT_SFWD(8); break;
+            case 16: CRIT_SFWD(16); break; case 19: CRIT_SFWD(19); break; default: CRIT_SFWD(32); break;
+        }
+#undef CRIT_SFWD
+    }
+    crit_finalize_kernel<<<1, kT, 0, s>>>(partial, nparts, npix, a, out6);
     return cudaGetLastError();
 }
 
