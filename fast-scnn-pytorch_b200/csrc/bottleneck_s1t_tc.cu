@@ -133,26 +133,36 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
         // (An event loop polling every barrier from one thread reacted thousands of cycles late: each poll is a dependent
         // test + branch of a single warp sharing its scheduler with four FMA-bound warps.  mbarrier.try_wait parks the warp in
         // hardware instead, and the expand / project sides no longer queue behind each other's blocking MMA issue.)
-        if (lane == 0) {
+        // (the whole warp walks the loop converged; asynchronous operations are issued by the lane elect.sync names: behind a
+        // `lane == 0` branch every tcgen05.mma / bulk copy gets a vote loop over the active lanes, and this thread's instruction
+        // latency sits on the weight-streaming path of the 96- / 128-channel layers -- see bottleneck_s2t_tc.cu)
+        {
             auto prefetch_we = [&](int g) {
-                mbar_arrive_expect_tx(&bar_we[g & 1], C::WE_BYTES);
-                bulk_g2s(sm + C::oWe + (g & 1) * C::WE_BYTES, we_img + (size_t)(g % NCH) * CM * C::KA, C::WE_BYTES, &bar_we[g & 1]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_we[g & 1], C::WE_BYTES);
+                    bulk_g2s(sm + C::oWe + (g & 1) * C::WE_BYTES, we_img + (size_t)(g % NCH) * CM * C::KA, C::WE_BYTES, &bar_we[g & 1]);
+                }
             };
             auto load_x = [&](int lt) {
                 int n, oy0, ox0;
                 tile_origin(lt, n, oy0, ox0);
                 const int xb = lt % XB;
-                mbar_arrive_expect_tx(&bar_x[xb], C::X_BYTES);
-                tma_load_halo(sX + xb * C::XS, &xmap, ox0 - 1, oy0 - 1, n, &bar_x[xb]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_x[xb], C::X_BYTES);
+                    tma_load_halo(sX + xb * C::XS, &xmap, ox0 - 1, oy0 - 1, n, &bar_x[xb]);
+                }
             };
             constexpr uint32_t idesc_exp = make_idesc_bf16(128, C::NB);
-            tma_prefetch_desc(&xmap);
+            if (elect_one()) tma_prefetch_desc(&xmap);
             if (WRES) {      // all weight chunks, once (the project controller waits on the same barrier)
-                mbar_arrive_expect_tx(&bar_wres, NCH * (C::WE_BYTES + C::WP_BYTES));
-                for (int e = 0; e < NCH; ++e) {
-                    bulk_g2s(sm + C::oWe + e * C::WE_BYTES, we_img + (size_t)e * CM * C::KA, C::WE_BYTES, &bar_wres);
-                    bulk_g2s(sm + C::oWp + e * C::WP_BYTES, wp_img + (size_t)e * COUT * CM, C::WP_BYTES, &bar_wres);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_wres, NCH * (C::WE_BYTES + C::WP_BYTES));
+                    for (int e = 0; e < NCH; ++e) {
+                        bulk_g2s(sm + C::oWe + e * C::WE_BYTES, we_img + (size_t)e * CM * C::KA, C::WE_BYTES, &bar_wres);
+                        bulk_g2s(sm + C::oWp + e * C::WP_BYTES, wp_img + (size_t)e * COUT * CM, C::WP_BYTES, &bar_wres);
+                    }
                 }
+                __syncwarp();
             } else {
                 prefetch_we(0);
                 if (total > 1) prefetch_we(1);
@@ -167,22 +177,25 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 if (!WRES) mbar_wait(&bar_we[ke & 1], (ke >> 1) & 1);                    // its weight chunk
                 if (e == 0) mbar_wait(&bar_x[xb], (lt / XB) & 1);                         // its halo tile
                 if (ke >= 2) mbar_wait(&bar_tmfree[ke & 1], ((ke - 2) >> 1) & 1);         // its accumulator, drained by chunk ke-2
-                T_STAMP(true, ke, 10);
+                T_STAMP(lane == 0, ke, 10);
                 tc_fence_after_sync();
                 // descriptors advance by adding to the 14-bit start-address field (bytes >> 4): a handful of instructions per MMA
                 const uint64_t da0 = make_smem_desc(sWe + (WRES ? e : (ke & 1)) * C::WE_BYTES, 2048, 128);
                 const uint64_t db0 = make_smem_desc(sX + xb * C::XS, PIN * 16, 128);
                 const uint32_t dacc = tmem + (ke & 1) * C::NB;
+                if (elect_one()) {
 #pragma unroll
-                for (int k16 = 0; k16 < CIN / 16; ++k16)
-                    umma_bf16_ss(dacc, da0 + (uint64_t)(k16 * ((2 * 2048) >> 4)), db0 + (uint64_t)(k16 * ((2 * PIN * 16) >> 4)), idesc_exp, k16 > 0);
-                umma_bf16_ss(dacc, da0 + (uint64_t)((CIN / 16) * ((2 * 2048) >> 4)), make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
-                umma_commit(&bar_exp[ke & 1]);
-                T_STAMP(true, ke, 11);
+                    for (int k16 = 0; k16 < CIN / 16; ++k16)
+                        umma_bf16_ss(dacc, da0 + (uint64_t)(k16 * ((2 * 2048) >> 4)), db0 + (uint64_t)(k16 * ((2 * PIN * 16) >> 4)), idesc_exp, k16 > 0);
+                    umma_bf16_ss(dacc, da0 + (uint64_t)((CIN / 16) * ((2 * 2048) >> 4)), make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
+                    umma_commit(&bar_exp[ke & 1]);
+                }
+                __syncwarp();
+                T_STAMP(lane == 0, ke, 11);
                 const bool more_w = !WRES && ke + 2 < total, more_x = (e == NCH - 1) && (lt + XB < my_tiles);
                 if (more_w || more_x) {
                     mbar_wait(&bar_exp[ke & 1], (ke >> 1) & 1);       // expand(ke) has completed: what it read may be overwritten
-                    T_STAMP(true, ke, 12);
+                    T_STAMP(lane == 0, ke, 12);
                     if (more_w) prefetch_we(ke + 2);
                     if (more_x) load_x(lt + XB);
                 }
@@ -190,10 +203,12 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
         }
     } else if (warp == kTWarps + 1) {
         // =========================== project controller ===========================
-        if (lane == 0) {
+        {
             auto prefetch_wp = [&](int g) {
-                mbar_arrive_expect_tx(&bar_wp[g % WPB], C::WP_BYTES);
-                bulk_g2s(sm + C::oWp + (g % WPB) * C::WP_BYTES, wp_img + (size_t)(g % NCH) * COUT * CM, C::WP_BYTES, &bar_wp[g % WPB]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_wp[g % WPB], C::WP_BYTES);
+                    bulk_g2s(sm + C::oWp + (g % WPB) * C::WP_BYTES, wp_img + (size_t)(g % NCH) * COUT * CM, C::WP_BYTES, &bar_wp[g % WPB]);
+                }
             };
             constexpr uint32_t idesc_proj = make_idesc_bf16(128, COUT) | (1u << 15);   // A (= D) is MN-major
             if (WRES) {
@@ -208,22 +223,25 @@ bottleneck_s1t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __re
                 if (!WRES) mbar_wait(&bar_wp[kp % WPB], (kp / WPB) & 1);                  // its weight chunk
                 if (e == 0 && lt > 0) mbar_wait(&bar_projfree, (lt - 1) & 1);             // the previous tile's accumulator has been read
                 mbar_wait(&bar_dready[kp % DB], (kp / DB) & 1);                           // D written by the depthwise threads
-                T_STAMP(true, kp, 8);
+                T_STAMP(lane == 0, kp, 8);
                 tc_fence_after_sync();
                 const uint64_t da0 = make_smem_desc(sD + (kp % DB) * C::D_BYTES, C::D_LBO, C::D_SBO);
                 const uint64_t db0 = make_smem_desc(sWp + (WRES ? e : kp % WPB) * C::WP_BYTES, COUT * 16, 128);
                 const bool half = (C::CEXP - e * CM) < CM;       // the last chunk of a 576-channel layer holds 64 channels
+                if (elect_one()) {
 #pragma unroll
-                for (int k16 = 0; k16 < CM / 16; ++k16)
-                    if (k16 < CM / 32 || !half)
-                        umma_bf16_ss(tmem + C::TM_PROJ, da0 + (uint64_t)(k16 * ((2 * C::D_LBO) >> 4)),
-                                     db0 + (uint64_t)(k16 * ((2 * COUT * 16) >> 4)), idesc_proj, (e | k16) != 0);
-                umma_commit(&bar_proj[kp % DB]);
-                if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
-                T_STAMP(true, kp, 9);
+                    for (int k16 = 0; k16 < CM / 16; ++k16)
+                        if (k16 < CM / 32 || !half)
+                            umma_bf16_ss(tmem + C::TM_PROJ, da0 + (uint64_t)(k16 * ((2 * C::D_LBO) >> 4)),
+                                         db0 + (uint64_t)(k16 * ((2 * COUT * 16) >> 4)), idesc_proj, (e | k16) != 0);
+                    umma_commit(&bar_proj[kp % DB]);
+                    if (e == NCH - 1) umma_commit(&bar_tiledone);   // one phase per TILE for the output epilogue
+                }
+                __syncwarp();
+                T_STAMP(lane == 0, kp, 9);
                 if (!WRES && kp + WPB < total) {
                     mbar_wait(&bar_proj[kp % DB], (kp / DB) & 1);     // project(kp) has completed: its weight buffer is free
-                    T_STAMP(true, kp, 13);
+                    T_STAMP(lane == 0, kp, 13);
                     prefetch_wp(kp + WPB);
                 }
             }

@@ -59,6 +59,16 @@ struct T2Cfg {
     static_assert((NSUB - 1) * XS + (CIN / 8 - 1) * PIN * 16 + NB * 16 <= smem_bytes, "B-tile overrun");
 };
 
+#ifdef FSCNN_PHASE_TIMING   // debug build only: clock64 stamps of units 24..35 (the third tile of a 64-channel layer) of CTA 5
+__device__ long long g_s2t_phase[12 * 16];
+#define U_STAMP(cond, uu, slot) do { if (COUT == 64 && blockIdx.x == 5 && (cond) && (uu) >= 24 && (uu) < 36) g_s2t_phase[((uu) - 24) * 16 + (slot)] = clock64(); } while (0)
+extern "C" int fscnn_debug_s2t_phases(long long* out192) {
+    return cudaMemcpyFromSymbol(out192, g_s2t_phase, sizeof(long long) * 192) == cudaSuccess ? 0 : -1;
+}
+#else
+#define U_STAMP(cond, uu, slot) do { } while (0)
+#endif
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kS2Threads, 1)
 bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned char* __restrict__ tab, const bf16* __restrict__ we_img,
@@ -104,23 +114,45 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
 
     if (warp == kS2Warps) {
         // =========================== expand controller ===========================
-        if (lane == 0) {
+        // The whole warp walks the loop converged and every asynchronous operation is issued by the lane elect.sync names: behind a
+        // `lane == 0` branch each tcgen05.mma / bulk copy is wrapped in a vote loop over the active lanes (6 extra instructions each),
+        // and this single thread's instruction latency is what paces the stride-2 kernel (phase stamps: ~100 instructions = ~1 200
+        // cycles per unit against 424 cycles of MMA work).
+        {
             auto prefetch_we = [&](int g) {
-                mbar_arrive_expect_tx(&bar_we[g & 1], C::WE_BYTES);
-                bulk_g2s(sm + C::oWe + (g & 1) * C::WE_BYTES, we_img + (size_t)(g % NCH) * CM * C::KA, C::WE_BYTES, &bar_we[g & 1]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_we[g & 1], C::WE_BYTES);
+                    bulk_g2s(sm + C::oWe + (g & 1) * C::WE_BYTES, we_img + (size_t)(g % NCH) * CM * C::KA, C::WE_BYTES, &bar_we[g & 1]);
+                }
             };
             auto load_x = [&](int lt, int sub) {      // input halo of sub-tile (sub >> 1, sub & 1): rows 2*oy - 1 .., columns 2*ox - 1 ..
                 int n, oy0, ox0;
                 tile_origin(lt, n, oy0, ox0);
-                mbar_arrive_expect_tx(&bar_x[sub], C::X_BYTES);
-                tma_load_halo(sX + sub * C::XS, &xmap, 2 * (ox0 + C::SW * (sub & 1)) - 1, 2 * (oy0 + C::SH * (sub >> 1)) - 1, n, &bar_x[sub]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_x[sub], C::X_BYTES);
+                    tma_load_halo(sX + sub * C::XS, &xmap, 2 * (ox0 + C::SW * (sub & 1)) - 1, 2 * (oy0 + C::SH * (sub >> 1)) - 1, n, &bar_x[sub]);
+                }
             };
             constexpr uint32_t idesc_exp = make_idesc_bf16(128, C::NB);
-            tma_prefetch_desc(&xmap);
+            if (elect_one()) tma_prefetch_desc(&xmap);
             prefetch_we(0);
             if (total > 1) prefetch_we(1);
             pdl_wait();      // the weights are on their way; the halo tiles are the previous stage's output
             for (int j = 0; j < NSUB; ++j) load_x(0, j);
+            // Reloads that must follow the completion of expand(u) (the weight buffer two chunks on, the sub-tile's halo of the next
+            // tile) are issued one unit LATE: after expand(u+1) has been issued, when expand(u) has long completed.  Waiting for it right
+            // after its own commit (the first version) parked this warp for a whole MMA sequence on every unit of a tile's last chunk
+            // while the tensor core had nothing queued (phase stamps, tools/phase_timing.py: 770 of 1 700 cycles per unit there).
+            int pend_u = -1, pend_g = 0, pend_lt = 0, pend_sub = 0;
+            bool pend_w = false, pend_x = false;
+            auto flush_pending = [&]() {
+                if (pend_u < 0) return;
+                mbar_wait(&bar_exp[pend_u & 1], (pend_u >> 1) & 1);      // expand(pend_u) has completed: what it read may be overwritten
+                U_STAMP(lane == 0, pend_u, 11);
+                if (pend_w) prefetch_we(pend_g + 2);
+                if (pend_x) load_x(pend_lt + 1, pend_sub);
+                pend_u = -1;
+            };
 #pragma unroll 1
             for (int g = 0; g < total; ++g) {
                 const int lt = g / NCH, e = g - lt * NCH;
@@ -129,24 +161,28 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
                 for (int sub = 0; sub < NSUB; ++sub) {
                     const int u = g * NSUB + sub;                                          // unit: accumulator buffer u & 1
                     if (e == 0) mbar_wait(&bar_x[sub], lt & 1);                            // the sub-tile's halo
+                    U_STAMP(lane == 0, u, 8);
                     if (u >= 2) mbar_wait(&bar_tmfree[u & 1], ((u - 2) >> 1) & 1);         // accumulator drained by unit u-2
+                    U_STAMP(lane == 0, u, 9);
                     tc_fence_after_sync();
                     const uint64_t da0 = make_smem_desc(sWe + (g & 1) * C::WE_BYTES, 2048, 128);
                     const uint64_t db0 = make_smem_desc(sX + sub * C::XS, PIN * 16, 128);
                     const uint32_t dacc = tmem + (u & 1) * C::NB;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k16 = 0; k16 < CIN / 16; ++k16)
-                        umma_bf16_ss(dacc, da0 + (uint64_t)(k16 * ((2 * 2048) >> 4)), db0 + (uint64_t)(k16 * ((2 * PIN * 16) >> 4)), idesc_exp, k16 > 0);
-                    umma_bf16_ss(dacc, da0 + (uint64_t)((CIN / 16) * ((2 * 2048) >> 4)), make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
-                    umma_commit(&bar_exp[u & 1]);
-                    const bool more_w = (sub == NSUB - 1) && (g + 2 < total), more_x = (e == NCH - 1) && (lt + 1 < my_tiles);
-                    if (more_w || more_x) {
-                        mbar_wait(&bar_exp[u & 1], (u >> 1) & 1);     // expand(u) has completed: what it read may be overwritten
-                        if (more_w) prefetch_we(g + 2);
-                        if (more_x) load_x(lt + 1, sub);
+                        for (int k16 = 0; k16 < CIN / 16; ++k16)
+                            umma_bf16_ss(dacc, da0 + (uint64_t)(k16 * ((2 * 2048) >> 4)), db0 + (uint64_t)(k16 * ((2 * PIN * 16) >> 4)), idesc_exp, k16 > 0);
+                        umma_bf16_ss(dacc, da0 + (uint64_t)((CIN / 16) * ((2 * 2048) >> 4)), make_smem_desc(sOnes, 128, 0), idesc_exp, 1);
+                        umma_commit(&bar_exp[u & 1]);
                     }
+                    __syncwarp();
+                    U_STAMP(lane == 0, u, 10);
+                    flush_pending();                                  // unit u-1's reloads (bar_exp[(u-1) & 1]: no phase can alias, unit u+1 is not issued yet)
+                    const bool more_w = (sub == NSUB - 1) && (g + 2 < total), more_x = (e == NCH - 1) && (lt + 1 < my_tiles);
+                    if (more_w || more_x) { pend_u = u; pend_g = g; pend_lt = lt; pend_sub = sub; pend_w = more_w; pend_x = more_x; }
                 }
             }
+            flush_pending();
         }
     } else if (warp == kS2Warps + 1) {
         // =========================== project controller ===========================
@@ -164,6 +200,7 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
                 mbar_wait(&bar_wp[kp & 1], (kp >> 1) & 1);                                // its weight chunk
                 if (e == 0 && lt > 0) mbar_wait(&bar_projfree, (lt - 1) & 1);             // the previous tile's accumulator has been read
                 mbar_wait(&bar_dready[kp % DB], (kp / DB) & 1);                           // D written by the depthwise threads (4 sub-tiles)
+                U_STAMP(true, kp * NSUB + 3, 12);
                 tc_fence_after_sync();
                 const uint64_t da0 = make_smem_desc(sD + (kp % DB) * C::D_BYTES, C::D_LBO, C::D_SBO);
                 const uint64_t db0 = make_smem_desc(sWp + (kp & 1) * C::WP_BYTES, COUT * 16, 128);
@@ -231,7 +268,10 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
 #pragma unroll 1
             for (int sub = 0; sub < NSUB; ++sub) {
                 const int u = g * NSUB + sub;
+                U_STAMP(tid == 0, u, 0);
+                U_STAMP(tid == 15 * 32, u, 6);
                 mbar_wait(&bar_exp[u & 1], (u >> 1) & 1);        // expand(u) has completed
+                U_STAMP(tid == 0, u, 1);
                 tc_fence_after_sync();
                 uint32_t Ep[3][9];                               // halo rows 2s .. 2s+2, column pairs (2i, 2i+1), ReLU'd bf16
                 {
@@ -250,6 +290,8 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tmfree[u & 1]);  // expand(u+2) may overwrite this accumulator
+                U_STAMP(tid == 0, u, 2);
+                U_STAMP(tid == 15 * 32, u, 7);
                 // zero padding of the depthwise conv: halo columns / rows outside the image (border tiles only)
                 const int ix0 = 2 * (ox0 + C::SW * (sub & 1)) - 1, iy0 = 2 * (oy0 + C::SH * (sub >> 1)) - 1 + 2 * s;
                 if (ix0 == -1 && ix0 + IW <= Wi) {               // left image border: only halo column 0 is outside
@@ -284,14 +326,18 @@ bottleneck_s2t_kernel(const __grid_constant__ CUtensorMap xmap, const unsigned c
                         for (int x = 0; x < 8; ++x)
                             acc[x] = fhfma_sel((ky | kx) ? acc[x] : bd, Ep[ky][(2 * x + kx) >> 1], (2 * x + kx) & 1, wq[(ky * 3 + kx) >> 1],
                                                (ky * 3 + kx) & 1);
+                U_STAMP(tid == 0, u, 3);
                 if (sub == 0 && g >= DB) mbar_wait(&bar_proj[g % DB], (g / DB - 1) & 1);   // project(g-DB) has completed: this D buffer is free
+                U_STAMP(tid == 0, u, 4);
                 sts128(d0 + sub * (4 * C::D_SBO), packbf_relu(acc[0], acc[1]), packbf_relu(acc[2], acc[3]), packbf_relu(acc[4], acc[5]),
                        packbf_relu(acc[6], acc[7]));
             }
             fence_async_proxy();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_dready[g % DB]);
+            U_STAMP(tid == 0, g * NSUB + 3, 5);
             if (e == 0 && lt >= 1) output_epilogue(lt - 1, pn, poy0, pox0);   // deferred by one chunk: keeps the pipeline fed
+            U_STAMP(tid == 0, g * NSUB + 3, 13);
         }
         output_epilogue(my_tiles - 1, n, oy0, ox0);
     }

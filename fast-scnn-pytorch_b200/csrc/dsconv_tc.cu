@@ -109,17 +109,24 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
 
     if (warp == kDsNT / 32) {
         // =========================== control warp ===========================
-        if (lane == 0) {
+        // (converged warp, asynchronous operations by the lane elect.sync names: no per-lane vote loop around every tcgen05.mma /
+        // TMA instruction, see bottleneck_s2t_tc.cu)
+        {
             auto load_halo = [&](int lt) {
                 int n, oy0, ox0;
                 tile_origin(blockIdx.x + lt * gstep, n, oy0, ox0);
-                mbar_arrive_expect_tx(&bar_h[lt & 1], PIN * CIN * 2);
-                tma_load_halo(sH + (lt & 1) * C::H_BYTES, &xmap, ox0 * STRIDE - 1, oy0 * STRIDE - 1, n, &bar_h[lt & 1]);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bar_h[lt & 1], PIN * CIN * 2);
+                    tma_load_halo(sH + (lt & 1) * C::H_BYTES, &xmap, ox0 * STRIDE - 1, oy0 * STRIDE - 1, n, &bar_h[lt & 1]);
+                }
             };
-            tma_prefetch_desc(&xmap);
-            mbar_arrive_expect_tx(&bar_w, C::B_BYTES + (HEAD ? ncp16 * COUT * 2 : 0));
-            bulk_g2s(sm + C::oB, wp_img, C::B_BYTES, &bar_w);
-            if (HEAD) bulk_g2s(sm + C::oB2, wh_img, ncp16 * COUT * 2, &bar_w);
+            if (elect_one()) {
+                tma_prefetch_desc(&xmap);
+                mbar_arrive_expect_tx(&bar_w, C::B_BYTES + (HEAD ? ncp16 * COUT * 2 : 0));
+                bulk_g2s(sm + C::oB, wp_img, C::B_BYTES, &bar_w);
+                if (HEAD) bulk_g2s(sm + C::oB2, wh_img, ncp16 * COUT * 2, &bar_w);
+            }
+            __syncwarp();
             pdl_wait();      // the weights are on their way; the halo tiles are the previous stage's output
             load_halo(0);
             if (my_tiles > 1) load_halo(1);
@@ -129,23 +136,29 @@ dsconv_tc_kernel(const __grid_constant__ CUtensorMap xmap, DsW w, const bf16* __
             auto issue_head = [&](int lt) {   // head MMA of tile lt: A2 (over A[lt&1]) x head weights -> TMEM head[lt&1]
                 mbar_wait(&bar_a2[lt & 1], (lt >> 1) & 1);
                 tc_fence_after_sync();
+                if (elect_one()) {
 #pragma unroll
-                for (int k16 = 0; k16 < COUT / 16; ++k16)
-                    umma_bf16_ss(tmem + TM_HEAD + (lt & 1) * ncp16, make_smem_desc(sA + (lt & 1) * C::A_BYTES + k16 * 4096, 2048, 128),
-                                 make_smem_desc(sB2 + k16 * 2 * (ncp16 * 16), ncp16 * 16, 128), idesc2, k16 > 0);
-                umma_commit(&bar_head[lt & 1]);
+                    for (int k16 = 0; k16 < COUT / 16; ++k16)
+                        umma_bf16_ss(tmem + TM_HEAD + (lt & 1) * ncp16, make_smem_desc(sA + (lt & 1) * C::A_BYTES + k16 * 4096, 2048, 128),
+                                     make_smem_desc(sB2 + k16 * 2 * (ncp16 * 16), ncp16 * 16, 128), idesc2, k16 > 0);
+                    umma_commit(&bar_head[lt & 1]);
+                }
+                __syncwarp();
             };
 #pragma unroll 1
             for (int lt = 0; lt < my_tiles; ++lt) {
                 mbar_wait(&bar_a[lt & 1], (lt >> 1) & 1);        // depthwise(lt) written (writers fenced the async proxy); halo[lt&1] is dead
                 tc_fence_after_sync();
-                umma_bf16_ss(tmem + (lt & 1) * COUT, make_smem_desc(smem_u32(sm + C::oOnes), 128, 0),
-                             make_smem_desc(smem_u32(sm + C::oBias), COUT * 16, 128), idesc, 0);   // bias
+                if (elect_one()) {
+                    umma_bf16_ss(tmem + (lt & 1) * COUT, make_smem_desc(smem_u32(sm + C::oOnes), 128, 0),
+                                 make_smem_desc(smem_u32(sm + C::oBias), COUT * 16, 128), idesc, 0);   // bias
 #pragma unroll
-                for (int k16 = 0; k16 < CIN / 16; ++k16)
-                    umma_bf16_ss(tmem + (lt & 1) * COUT, make_smem_desc(sA + (lt & 1) * C::A_BYTES + k16 * 4096, 2048, 128),
-                                 make_smem_desc(sB + k16 * 2 * (COUT * 16), COUT * 16, 128), idesc, 1);
-                umma_commit(&bar_mma[lt & 1]);
+                    for (int k16 = 0; k16 < CIN / 16; ++k16)
+                        umma_bf16_ss(tmem + (lt & 1) * COUT, make_smem_desc(sA + (lt & 1) * C::A_BYTES + k16 * 4096, 2048, 128),
+                                     make_smem_desc(sB + k16 * 2 * (COUT * 16), COUT * 16, 128), idesc, 1);
+                    umma_commit(&bar_mma[lt & 1]);
+                }
+                __syncwarp();
                 if (lt + 2 < my_tiles) load_halo(lt + 2);
                 if (HEAD && lt >= 1) issue_head(lt - 1);
             }

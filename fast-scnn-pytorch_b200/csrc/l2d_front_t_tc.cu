@@ -47,6 +47,16 @@ constexpr int TM_PW = 2 * NB;                          // stem accumulators 2 x 
 static_assert(kSmemFT <= 227 * 1024 - 256, "shared memory");
 }  // namespace
 
+#ifdef FSCNN_PHASE_TIMING   // debug build only: clock64 stamps of tiles 8..15 of CTA 5 (fp32 input kernel)
+__device__ long long g_front_t_phase[8 * 16];
+#define F_STAMP(cond, tt, slot) do { if (FMT == FSCNN_IN_F32_NCHW && blockIdx.x == 5 && (cond) && (tt) >= 8 && (tt) < 16) g_front_t_phase[((tt) - 8) * 16 + (slot)] = clock64(); } while (0)
+extern "C" int fscnn_debug_front_t_phases(long long* out128) {
+    return cudaMemcpyFromSymbol(out128, g_front_t_phase, sizeof(long long) * 128) == cudaSuccess ? 0 : -1;
+}
+#else
+#define F_STAMP(cond, tt, slot) do { } while (0)
+#endif
+
 template <int FMT>
 __global__ void __launch_bounds__(kFTThreads, 1)
 l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restrict__ ws_img, DsW w, const bf16* __restrict__ wp_img,
@@ -123,9 +133,13 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             if (my_tiles > 1) load_patch(1);
 #pragma unroll 1
             for (int t = 0; t < my_tiles; ++t) {
+                F_STAMP(true, t, 0);
                 mbar_wait(&bar_planes[t & 1], (t >> 1) & 1);      // planes of tile t written: its raw patch buffer is free
+                F_STAMP(true, t, 1);
                 if (t + 2 < my_tiles) load_patch(t + 2);
+                F_STAMP(true, t, 2);
                 if (t >= 2) mbar_wait(&bar_tmfree[t & 1], ((t - 2) >> 1) & 1);
+                F_STAMP(true, t, 3);
                 tc_fence_after_sync();
                 const uint32_t pl = sPl + (t & 1) * kPlanes, dacc = tmem + (t & 1) * NB;
 #pragma unroll
@@ -135,6 +149,7 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
                         umma_bf16_ss(dacc, make_smem_desc(sZ + ky * kZ + (96 - 32 * j) * 16, 224 * 16, 128),
                                      make_smem_desc(pl + j * kSubP + (ky & 1) * kOdd + (ky >> 1) * kPitch, 16, 128), idesc_s, (j | ky) != 0);
                 umma_commit(&bar_exp[t & 1]);
+                F_STAMP(true, t, 4);
             }
         }
     } else if (warp == kCW + 1) {
@@ -252,7 +267,9 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             tx += step_x; if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
             ty += step_y; if (ty >= tiles_y) { ty -= tiles_y; ++n; }
             n += step_n;
+            F_STAMP(tid == 0, t, 5);
             mbar_wait(&bar_exp[t & 1], (t >> 1) & 1);            // stem(t) has completed
+            F_STAMP(tid == 0, t, 6);
             tc_fence_after_sync();
             uint32_t Ep[3][9];                                   // stem rows 2s .. 2s+2, column pairs (2i, 2i+1), ReLU'd bf16
             {
@@ -271,6 +288,7 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tmfree[t & 1]);      // stem(t+2) may overwrite this accumulator
+            F_STAMP(tid == 0, t, 7);
             // zero padding of the depthwise conv: stem pixels outside the stem image (border tiles only)
             const int ix0 = 2 * (ox0 + 8 * (q & 1)) - 1, iy0 = 2 * (oy0 + 4 * (q >> 1)) - 1 + 2 * s;
             if (ix0 < 0 || ix0 + 18 > W1) {
@@ -299,17 +317,22 @@ l2d_front_t_kernel(const __grid_constant__ CUtensorMap xmap, const bf16* __restr
                     for (int x = 0; x < 8; ++x)
                         acc[x] = fhfma_sel((ky | kx) ? acc[x] : bd, Ep[ky][(2 * x + kx) >> 1], (2 * x + kx) & 1, wq[(ky * 3 + kx) >> 1],
                                            (ky * 3 + kx) & 1);
+            F_STAMP(tid == 0, t, 8);
             if (t + 2 < my_tiles) {       // planes[t&1] are free (stem(t) has completed); the stem of tile t+2 runs during tile t+1
                 mbar_wait(&bar_patch[t & 1], ((t + 2) >> 1) & 1);
+                F_STAMP(tid == 0, t, 9);
                 repack(t + 2);
             }
+            F_STAMP(tid == 0, t, 10);
             if (t >= 2) mbar_wait(&bar_proj[t & 1], ((t - 2) >> 1) & 1);   // pointwise(t-2) has completed: D[t&1] is free
             sts128(sD + (t & 1) * 8192 + (q * 4 + s) * 512 + (lane >> 3) * 128 + (lane & 7) * 16, packbf_relu(acc[0], acc[1]),
                    packbf_relu(acc[2], acc[3]), packbf_relu(acc[4], acc[5]), packbf_relu(acc[6], acc[7]));
             fence_async_proxy();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bar_dready[t & 1]); if (t + 2 < my_tiles) mbar_arrive(&bar_planes[t & 1]); }
+            F_STAMP(tid == 0, t, 11);
             if (t >= 1) epilogue(t - 1, pn, poy0, pox0);
+            F_STAMP(tid == 0, t, 12);
         }
         epilogue(my_tiles - 1, cn, oy0, ox0);
     }

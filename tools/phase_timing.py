@@ -60,7 +60,7 @@ if hasattr(lib, 'fscnn_debug_s1_phases') and lib.fscnn_debug_s1_phases(sbuf) == 
         print(f'  chunk {8 + c}: {r[0]:8d} {r[1]:8d} {r[2]:8d} {r[3]:8d}      {r[4]:8d} {r[5]:8d} {r[6]:8d} {r[7]:8d}')
 
 tbuf = (C.c_longlong * 384)()
-if hasattr(lib, 'fscnn_debug_s1t_phases') and lib.fscnn_debug_s1t_phases(tbuf) == 0:
+if hasattr(lib, 'fscnn_debug_s1t_phases') and lib.fscnn_debug_s1t_phases(tbuf) == 0 and any(v > 0 for v in tbuf):
     t = list(tbuf)
     t0 = min(v for v in t if v > 0)
     print('transposed stride-1 bottleneck, chunks 12..19 of CTA 5 (cycles since the first stamp)')
@@ -72,3 +72,24 @@ if hasattr(lib, 'fscnn_debug_s1t_phases') and lib.fscnn_debug_s1t_phases(tbuf) =
     for c in range(8):
         print(f'  chunk {12 + c} top: ' + ' '.join(f'{(v - t0 if v > 0 else -1):6d}' for v in t[256 + c * 16:256 + c * 16 + 16]))
         print(f'  chunk {12 + c} Dwr: ' + ' '.join(f'{(v - t0 if v > 0 else -1):6d}' for v in t[128 + c * 16:128 + c * 16 + 16]))
+
+ubuf = (C.c_longlong * 192)()
+if hasattr(lib, 'fscnn_debug_s2t_phases') and lib.fscnn_debug_s2t_phases(ubuf) == 0 and any(v > 0 for v in ubuf):
+    t = list(ubuf)
+    t0 = min(v for v in t if v > 0)
+    print('transposed stride-2 bottleneck <64,64>, units 24..35 (= chunks 6..8 x 4 sub-tiles) of CTA 5 (cycles since the first stamp)')
+    print('  warp0: top | exp done | ldtm+cvt, tmfree | fma done | D free | dready | w15 top | w15 tmfree || ctl: top | tm free | committed | reloads issued | proj: D ready || epilogue end')
+    for u in range(12):
+        r = [(v - t0 if v > 0 else -1) for v in t[u * 16:u * 16 + 16]]
+        print(f'  unit {24 + u}: ' + ' '.join(f'{v:7d}' for v in r[:8]) + ' || ' + ' '.join(f'{v:7d}' for v in r[8:13]) + ' || ' + f'{r[13]:7d}')
+
+vbuf = (C.c_longlong * 128)()
+if hasattr(lib, 'fscnn_debug_front_t_phases') and lib.fscnn_debug_front_t_phases(vbuf) == 0 and any(v > 0 for v in vbuf):
+    t = list(vbuf)
+    t0 = min(v for v in t if v > 0)
+    print('transposed front kernel (fp32 input), tiles 8..15 of CTA 5 (cycles since the first stamp)')
+    print('  stem ctl: top | planes ready | patch(t+2) issued | tm free | committed || warp0: top | stem done | ldtm+cvt | fma done | patch(t+2) here | repacked | D + planes published | epilogue(t-1) done')
+    for k in range(8):
+        r = [(v - t0 if v > 0 else -1) for v in t[k * 16:k * 16 + 16]]
+        print(f'  tile {8 + k}: ' + ' '.join(f'{v:7d}' for v in r[:5]) + ' || ' + ' '.join(f'{v:7d}' for v in r[5:13]))
+
