@@ -11,7 +11,7 @@
 //            over the chunks of 128 expanded channels; + bias (+ residual) -> bf16 NHWC.
 //
 // One persistent CTA per SM: 16 compute warps (TMEM lane quarter = warp % 4, row strip = warp / 4) + two controller warps
-// (lane 0 each): one issues the halo loads, expand weight copies and expand MMAs, the other the project weight copies and
+// (converged, issuing through elect.sync): one issues the halo loads, expand weight copies and expand MMAs, the other the project weight copies and
 // project MMAs, both in order with blocking mbarrier waits.  The expand accumulator and the
 // weight chunks are double-buffered: the tensor core works two chunks ahead of the CUDA cores; every hand-off is an mbarrier.
 #include "kernels.h"

@@ -5,7 +5,7 @@
 // runs as a second MMA on the activated tile and only fp32 low-resolution logits are written.
 //
 // Persistent, warp-specialised, software-pipelined over 8x16-pixel output tiles (one CTA per SM):
-//   control warp (lane 0) : one TMA tensor copy per halo tile (zero-filled padding, [c/8][pixel][8 ch] layout, double
+//   control warp (elect)  : one TMA tensor copy per halo tile (zero-filled padding, [c/8][pixel][8 ch] layout, double
 //                           buffered, two tiles ahead), the pointwise weights once, every tcgen05.mma + commit
 //   16 compute warps, iteration t:
 //       depthwise(t)      : halo[t&1] -> 3x3 + bias + ReLU -> bf16 A[t&1] (A-operand layout); arrive -> MMA(t) is issued
