@@ -118,10 +118,10 @@ class SoftmaxCrossEntropyOHEMLoss(nn.Module):
             self.weight = None
 
     def forward(self, predict, target, weight=None):
-        assert not target.requires_grad
-        assert predict.dim() == 4
-        assert target.dim() == 3
-        assert predict.size(0) == target.size(0), "{0} vs {1} ".format(predict.size(0), target.size(0))
+        # the reference's own argument checks (loss.py:144-147) are assertions; keep the exception type
+        if target.requires_grad or predict.dim() != 4 or target.dim() != 3 or predict.shape[0] != target.shape[0]:
+            raise AssertionError(f'expected logits [N,C,h,w] and a label map [N,H,W] without gradient, got {tuple(predict.shape)} and '
+                                 f'{tuple(target.shape)}')
         w = self.weight
         if w is not None and w.device != predict.device:
             w = self.weight = w.to(predict.device)
