@@ -219,3 +219,18 @@ def test_lr_scheduler_is_bit_identical_to_the_reference():
     sched = LRScheduler(mode='poly', base_lr=0.01, nepochs=60, iters_per_epoch=176, power=0.9)
     for it in (0, 1, 500, 60 * 176 - 2):
         assert abs(sched(it) - poly_lr(0.01, it, 60, 176)) <= 1e-15
+
+
+def test_criterion_argument_checks_need_no_device():
+    """train_ops.criterion / adamw_step refuse bad arguments before any kernel could see them."""
+    import pytest
+    import torch
+    from fscnn_b200 import train_ops
+    logits, target = torch.zeros(1, 2, 8, 8), torch.zeros(1, 8, 8, dtype=torch.int64)
+    with pytest.raises(ValueError):
+        train_ops.criterion(logits, target, 'hinge')
+    with pytest.raises(RuntimeError):                      # CPU tensors: no CPU path
+        train_ops.criterion(logits, target, 'ce')
+    with pytest.raises(ValueError):
+        train_ops.adamw_step(torch.zeros(4), torch.zeros(4), torch.zeros(4), torch.zeros(4), 1e-3, 1)
+    assert train_ops.CRITERIA == {'ce': 0, 'dice': 1, 'focal_dice': 2}
